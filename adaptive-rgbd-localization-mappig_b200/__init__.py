@@ -1,0 +1,339 @@
+"""Host-side Python mirror of the C ABI in include/orbfront.h (ctypes over liborbfront_b200.so).
+
+The directory name is not a valid Python identifier; load it with
+    importlib.util.spec_from_file_location("orbfront_b200", ".../adaptive-rgbd-localization-mappig_b200/__init__.py")
+(tests/conftest.py, bench.py and __graft_entry__.py do exactly that).  Everything here is plumbing: numpy
+arrays in, numpy arrays out, every call lands in a CUDA kernel of the shared library.  There is no CPU
+fallback: if the library is missing it is built with nvcc, and if no CUDA device is present Context()
+raises OrbfError(ORBF_ERR_CUDA).
+"""
+import ctypes as C
+import importlib.util
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "liborbfront_b200.so"
+
+KEYPOINT_DT = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                        ("octave", "<i4"), ("class_id", "<i4")])
+DMATCH_DT = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+CAND_DT = np.dtype([("x", "<i4"), ("y", "<i4"), ("score", "<i4")])
+HYP_DT = np.dtype([("n_refined", "<i4"), ("rounds", "<i4"), ("refined_error", "<f8"), ("T", "<f4", (16,))])
+RANSAC_RESULT_DT = np.dtype([("ok", "<i4"), ("rmse", "<f4"), ("T12", "<f4", (16,)), ("n_inliers", "<i4"), ("n_good", "<i4"),
+                             ("real_iters", "<i4"), ("valid_iters", "<i4"), ("used_identity", "<i4"), ("_pad", "<i4"),
+                             ("depth_cov_used", "<f8")])
+
+STATUS = {0: "ORBF_OK", 1: "ORBF_ERR_ARG", 2: "ORBF_ERR_CAPACITY", 3: "ORBF_ERR_GEOMETRY", 4: "ORBF_ERR_CUDA",
+          5: "ORBF_ERR_ALIGNMENT", 6: "ORBF_ERR_STATE"}
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("nfeatures", C.c_int32), ("nlevels", C.c_int32),
+                ("scale_factor", C.c_float), ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
+                ("max_frames", C.c_int32), ("max_pairs", C.c_int32), ("device", C.c_int32),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
+                ("depth_factor", C.c_float)]
+
+
+class RansacConfig(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("min_inlier_th", C.c_uint32), ("max_mahal", C.c_float),
+                ("sample_size", C.c_uint32), ("check_depth", C.c_int32), ("sort_mode", C.c_int32),
+                ("depth_cov", C.c_double), ("seed", C.c_uint32)]
+
+
+class RansacResult(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("rmse", C.c_float), ("T12", C.c_float * 16), ("n_inliers", C.c_int32),
+                ("n_good", C.c_int32), ("real_iters", C.c_int32), ("valid_iters", C.c_int32), ("used_identity", C.c_int32),
+                ("depth_cov_used", C.c_double)]
+
+
+assert C.sizeof(RansacResult) == RANSAC_RESULT_DT.itemsize, (C.sizeof(RansacResult), RANSAC_RESULT_DT.itemsize)
+
+
+class OrbfError(RuntimeError):
+    def __init__(self, status, what, detail=""):
+        self.status = status
+        super().__init__(f"{what}: {STATUS.get(status, status)} {detail}".strip())
+
+
+def build(force=False):
+    spec = importlib.util.spec_from_file_location("_orbf_build", _HERE / "build.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force)
+
+
+_lib = None
+
+
+def lib():
+    """Load (building first if needed) the shared library.  Raises if it cannot be produced: no fallback."""
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB_PATH))
+        L.orbf_status_string.restype = C.c_char_p
+        L.orbf_last_error.restype = C.c_char_p
+        L.orbf_last_error.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_config(**kw):
+    cfg = Config()
+    lib().orbf_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def default_ransac_config(**kw):
+    cfg = RansacConfig()
+    lib().orbf_default_ransac_config(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def descriptor_distance(a, b):
+    """Matcher::DescriptorDistance (matcher.cpp:355-358) for NORM_HAMMING rows."""
+    a = np.ascontiguousarray(a, np.uint8).ravel(); b = np.ascontiguousarray(b, np.uint8).ravel()
+    d = C.c_int32(0)
+    rc = lib().orbf_descriptor_distance(_p(a), _p(b), len(a), C.byref(d))
+    if rc:
+        raise OrbfError(rc, "descriptor_distance")
+    return d.value
+
+
+class Context:
+    """One per GPU.  Mirrors ORBextractor + Matcher + Ransac + Kabsch behind the C ABI."""
+
+    def __init__(self, **kw):
+        self.cfg = default_config(**kw)
+        self._h = C.c_void_p(None)
+        rc = lib().orbf_create(C.byref(self.cfg), C.byref(self._h))
+        if rc:
+            detail = lib().orbf_last_error(self._h).decode() if self._h else ""
+            if self._h:
+                lib().orbf_destroy(self._h)
+                self._h = C.c_void_p(None)
+            raise OrbfError(rc, "orbf_create", detail)
+        cap = C.c_int32(0)
+        self._chk(lib().orbf_keypoint_capacity(self._h, C.byref(cap)), "keypoint_capacity")
+        self.K = cap.value
+        self.L = self.cfg.nlevels
+
+    def close(self):
+        if self._h:
+            lib().orbf_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc:
+            raise OrbfError(rc, what, lib().orbf_last_error(self._h).decode() if self._h else "")
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(lib().orbf_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        self._chk(lib().orbf_synchronize(self._h), "synchronize")
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        self._chk(lib().orbf_launch_count(self._h, C.byref(n)), "launch_count")
+        return n.value
+
+    def tables(self):
+        L = self.L
+        f = [np.zeros(L, np.float32) for _ in range(4)]
+        i = [np.zeros(L, np.int32) for _ in range(3)]
+        self._chk(lib().orbf_get_tables(self._h, _p(f[0]), _p(f[1]), _p(f[2]), _p(f[3]), _p(i[0]), _p(i[1]), _p(i[2])), "get_tables")
+        return dict(scale=f[0], inv_scale=f[1], sigma2=f[2], inv_sigma2=f[3], nfeat=i[0], level_w=i[1], level_h=i[2])
+
+    # ---- extraction ----
+    def extract(self, img):
+        """ORBextractor::operator()(image, mask, keypoints, descriptors): host in, host out."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape if img.ndim == 2 else (0, 0)
+        kps = np.zeros(self.K, KEYPOINT_DT); desc = np.zeros((self.K, 32), np.uint8); n = C.c_int32(0)
+        self._chk(lib().orbf_extract(self._h, _p(img) if img.size else None, w, h, w, _p(kps), _p(desc), self.K, C.byref(n)), "extract")
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames, depths=None, slot0=0):
+        """frames: [n, H, W] u8 host array (pinned or pageable); depths: [n, H, W] u16 or None.  Asynchronous."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+        n, h, w = frames.shape
+        if depths is not None:
+            assert depths.dtype == np.uint16 and depths.shape == frames.shape and depths.flags.c_contiguous
+        self._chk(lib().orbf_extract_batch(self._h, slot0, n, _p(frames), C.c_int64(w), C.c_int64(w * h), _p(depths),
+                                           C.c_int64(w), C.c_int64(w * h)), "extract_batch")
+
+    def extract_batch_device(self, d_gray_ptr, pitch, frame_stride, n, d_depth_ptr=0, depth_pitch=0, depth_frame_stride=0, slot0=0):
+        self._chk(lib().orbf_extract_batch_device(self._h, slot0, n, C.c_void_p(d_gray_ptr), C.c_int64(pitch), C.c_int64(frame_stride),
+                                                  C.c_void_p(d_depth_ptr) if d_depth_ptr else None, C.c_int64(depth_pitch),
+                                                  C.c_int64(depth_frame_stride)), "extract_batch_device")
+
+    def frame_counts(self, n, slot0=0):
+        out = np.zeros(n, np.int32)
+        self._chk(lib().orbf_frame_counts(self._h, slot0, n, _p(out)), "frame_counts")
+        return out
+
+    def download_frame(self, slot):
+        kps = np.zeros(self.K, KEYPOINT_DT); desc = np.zeros((self.K, 32), np.uint8); xyz = np.zeros((self.K, 3), np.float32)
+        n = C.c_int32(0)
+        self._chk(lib().orbf_download_frame(self._h, slot, _p(kps), _p(desc), _p(xyz), self.K, C.byref(n)), "download_frame")
+        return kps[:n.value].copy(), desc[:n.value].copy(), xyz[:n.value].copy()
+
+    def pyramid_level(self, slot, level, blurred=False):
+        t = self.tables()
+        w, h = int(t["level_w"][level]), int(t["level_h"][level])
+        out = np.zeros((h, w), np.uint8)
+        self._chk(lib().orbf_pyramid_level(self._h, slot, level, int(blurred), _p(out), w), "pyramid_level")
+        return out
+
+    def level_candidates(self, slot, level):
+        n = C.c_int32(0)
+        rc = lib().orbf_level_candidates(self._h, slot, level, None, 0, C.byref(n))
+        if rc not in (0, 2):
+            self._chk(rc, "level_candidates")
+        out = np.zeros(max(n.value, 1), CAND_DT)
+        self._chk(lib().orbf_level_candidates(self._h, slot, level, _p(out), len(out), C.byref(n)), "level_candidates")
+        return out[:n.value].copy()
+
+    def level_keypoint_counts(self, slot):
+        out = np.zeros(self.L, np.int32)
+        self._chk(lib().orbf_level_keypoint_counts(self._h, slot, _p(out)), "level_keypoint_counts")
+        return out
+
+    # ---- matching ----
+    def knn2(self, q, t):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        o = [np.full(len(q), -1, np.int32) for _ in range(4)]
+        self._chk(lib().orbf_knn2(self._h, _p(q), len(q), _p(t), len(t), _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3])), "knn2")
+        return tuple(o)
+
+    def knn_match(self, q, t, ratio, cross_check=False):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        out = np.zeros(max(len(q), 1), DMATCH_DT); n = C.c_int32(0)
+        self._chk(lib().orbf_knn_match(self._h, _p(q), len(q), _p(t), len(t), C.c_float(ratio), int(cross_check), _p(out), len(out),
+                                       C.byref(n)), "knn_match")
+        return out[:n.value].copy()
+
+    def match_pairs(self, pairs, ratio, cross_check=False):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._chk(lib().orbf_match_pairs(self._h, _p(pairs), len(pairs), C.c_float(ratio), int(cross_check)), "match_pairs")
+        return len(pairs)
+
+    def download_matches(self, pair):
+        out = np.zeros(self.K, DMATCH_DT); n = C.c_int32(0)
+        self._chk(lib().orbf_download_matches(self._h, pair, _p(out), self.K, C.byref(n)), "download_matches")
+        return out[:n.value].copy()
+
+    def download_knn(self, pair):
+        o = [np.zeros(self.K, np.int32) for _ in range(4)]; n = C.c_int32(0)
+        self._chk(lib().orbf_download_knn(self._h, pair, _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3]), self.K, C.byref(n)), "download_knn")
+        return tuple(a[:n.value].copy() for a in o)
+
+    def match_counts(self, npairs):
+        out = np.zeros(npairs, np.int32)
+        self._chk(lib().orbf_match_counts(self._h, npairs, _p(out)), "match_counts")
+        return out
+
+    # ---- RANSAC / Kabsch ----
+    def ransac_iterate(self, src_xyz, dst_xyz, m12, sample_table=None, **kw):
+        cfg = default_ransac_config(**kw)
+        src = np.ascontiguousarray(src_xyz, np.float32); dst = np.ascontiguousarray(dst_xyz, np.float32)
+        m12 = np.ascontiguousarray(m12, DMATCH_DT)
+        res = RansacResult()
+        inl = np.zeros(max(len(m12), 1), DMATCH_DT); hyp = np.zeros(cfg.iterations, HYP_DT)
+        good = np.zeros(max(len(m12), 1), DMATCH_DT); tab_out = np.full((cfg.iterations, cfg.sample_size), -1, np.int32)
+        tab = None if sample_table is None else np.ascontiguousarray(sample_table, np.int32)
+        self._chk(lib().orbf_ransac_iterate(self._h, C.byref(cfg), _p(src), len(src), _p(dst), len(dst), _p(m12), len(m12), _p(tab),
+                                            _p(inl), len(inl), C.byref(res), _p(hyp), _p(good), _p(tab_out)), "ransac_iterate")
+        return dict(ok=bool(res.ok), rmse=float(res.rmse), T12=np.array(res.T12, np.float32).reshape(4, 4),
+                    inliers=inl[:res.n_inliers].copy(), n_good=res.n_good, real_iters=res.real_iters, valid_iters=res.valid_iters,
+                    used_identity=bool(res.used_identity), depth_cov=float(res.depth_cov_used), hyp=hyp,
+                    good_sorted=good[:res.n_good].copy(), sample_table=tab_out)
+
+    def ransac_pairs(self, npairs, **kw):
+        cfg = default_ransac_config(**kw)
+        self._chk(lib().orbf_ransac_pairs(self._h, npairs, C.byref(cfg)), "ransac_pairs")
+
+    def download_ransac(self, pair):
+        res = RansacResult(); inl = np.zeros(self.K, DMATCH_DT)
+        self._chk(lib().orbf_download_ransac(self._h, pair, C.byref(res), _p(inl), self.K), "download_ransac")
+        return dict(ok=bool(res.ok), rmse=float(res.rmse), T12=np.array(res.T12, np.float32).reshape(4, 4),
+                    inliers=inl[:res.n_inliers].copy(), n_good=res.n_good, real_iters=res.real_iters, valid_iters=res.valid_iters,
+                    used_identity=bool(res.used_identity), depth_cov=float(res.depth_cov_used))
+
+    def download_ransac_summary(self, npairs):
+        out = np.zeros(npairs, RANSAC_RESULT_DT)
+        self._chk(lib().orbf_download_ransac_summary(self._h, npairs, _p(out)), "download_ransac_summary")
+        return out
+
+    def kabsch(self, A, B):
+        A = np.ascontiguousarray(A, np.float32).reshape(-1, 3); B = np.ascontiguousarray(B, np.float32).reshape(-1, 3)
+        T = np.zeros(16, np.float32)
+        self._chk(lib().orbf_kabsch(self._h, _p(A) if len(A) else None, _p(B) if len(B) else None, len(A), _p(T)), "kabsch")
+        return T.reshape(4, 4)
+
+    # ---- keyframe store ----
+    def kfdb_reserve(self, n):
+        self._chk(lib().orbf_kfdb_reserve(self._h, n), "kfdb_reserve")
+
+    def kfdb_add_from_slot(self, kf, slot):
+        self._chk(lib().orbf_kfdb_add_from_slot(self._h, kf, slot), "kfdb_add_from_slot")
+
+    def kfdb_add_host(self, kf, desc):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        self._chk(lib().orbf_kfdb_add_host(self._h, kf, _p(desc), len(desc)), "kfdb_add_host")
+
+    def kfdb_device_buffers(self):
+        d = C.c_void_p(None); cnt = C.c_void_p(None); rows = C.c_int32(0); n = C.c_int32(0)
+        self._chk(lib().orbf_kfdb_device_buffers(self._h, C.byref(d), C.byref(cnt), C.byref(rows), C.byref(n)), "kfdb_device_buffers")
+        return d.value, cnt.value, rows.value, n.value
+
+    def kfdb_match(self, q, kf0, nkf, ratio):
+        q = np.ascontiguousarray(q, np.uint8)
+        o = [np.zeros((nkf, len(q)), np.int32) for _ in range(4)]; surv = np.zeros(nkf, np.int32)
+        self._chk(lib().orbf_kfdb_match(self._h, _p(q), len(q), kf0, nkf, C.c_float(ratio), _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3]),
+                                        _p(surv)), "kfdb_match")
+        return o[0], o[1], o[2], o[3], surv
+
+
+# ---- host-side selftest hooks of csrc/replay.h (no GPU needed) ----
+def selftest_introsort(m):
+    m = np.ascontiguousarray(m, DMATCH_DT).copy()
+    rc = lib().orbf_selftest_introsort(_p(m), len(m))
+    if rc:
+        raise OrbfError(rc, "selftest_introsort")
+    return m
+
+
+def selftest_glibc_rand(seed, n):
+    out = np.zeros(n, np.int32)
+    rc = lib().orbf_selftest_glibc_rand(C.c_uint32(seed), n, _p(out))
+    if rc:
+        raise OrbfError(rc, "selftest_glibc_rand")
+    return out
+
+
+def selftest_sample_table(seed, M, iterations=200, sample_size=4):
+    out = np.zeros((iterations, sample_size), np.int32)
+    rc = lib().orbf_selftest_sample_table(C.c_uint32(seed), M, iterations, sample_size, _p(out))
+    if rc:
+        raise OrbfError(rc, "selftest_sample_table")
+    return out

@@ -1,0 +1,458 @@
+// csrc/c_abi.cu — extern "C" entry points of include/orbfront.h (the drop-in boundary).
+// Host <-> device staging lives here; every stage itself is a CUDA kernel (no CPU fallback anywhere).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "orbf_internal.h"
+#include "replay.h"
+
+#define CTX_ENTER(c)                                                                   \
+    do {                                                                               \
+        if (!(c)) return ORBF_ERR_ARG;                                                 \
+        cudaError_t e_ = cudaSetDevice((c)->cfg.device);                               \
+        if (e_ != cudaSuccess) return orbf_cuda_fail((c), e_, "cudaSetDevice", __FILE__, __LINE__); \
+    } while (0)
+#define TRY(x) do { int r__ = (x); if (r__ != ORBF_OK) return r__; } while (0)
+
+struct DistanceLess { ORBF_HD bool operator()(const orbf_dmatch& a, const orbf_dmatch& b) const { return a.distance < b.distance; } };
+
+static int run_extract(orbf_context* c, int slot0, int n)
+{
+    TRY(orbf_launch_pyramid(c, slot0, n));
+    TRY(orbf_launch_fast(c, slot0, n));
+    TRY(orbf_launch_quadtree(c, slot0, n));
+    TRY(orbf_launch_blur(c, slot0, n));
+    TRY(orbf_launch_describe(c, slot0, n));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_extract_batch_device(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems)
+{
+    CTX_ENTER(c);
+    if (!d_gray || n < 1 || slot0 < 0 || slot0 + n > c->B || gray_pitch < c->cfg.width) return ORBF_ERR_ARG;
+    if (((uintptr_t)d_gray & 15) || (gray_pitch & 15) || (gray_frame_stride & 15)) return ORBF_ERR_ALIGNMENT;
+    if (d_depth && depth_pitch_elems < c->cfg.width) return ORBF_ERR_ARG;
+    c->cur_gray = d_gray; c->cur_grayPitch = (int)gray_pitch; c->cur_grayFrameStride = gray_frame_stride;
+    c->cur_depth = d_depth; c->cur_depthPitch = (int)depth_pitch_elems; c->cur_depthFrameStride = depth_frame_stride_elems;
+    c->cur_slot0 = slot0; c->cur_n = n;
+    return run_extract(c, slot0, n);
+}
+
+extern "C" int orbf_extract_batch(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems)
+{
+    CTX_ENTER(c);
+    if (!gray || n < 1 || slot0 < 0 || slot0 + n > c->B || gray_stride < c->cfg.width) return ORBF_ERR_ARG;
+    const int w = c->cfg.width, h = c->cfg.height;
+    uint8_t* dIn = c->d_in + (size_t)slot0 * c->inPlane;
+    if (gray_frame_stride == gray_stride * h) {
+        ORBF_CUDA(c, cudaMemcpy2DAsync(dIn, c->inPitch, gray, gray_stride, w, (size_t)h * n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            ORBF_CUDA(c, cudaMemcpy2DAsync(dIn + (size_t)i * c->inPlane, c->inPitch, gray + (size_t)i * gray_frame_stride, gray_stride,
+                w, h, cudaMemcpyHostToDevice, c->stream));
+    }
+    uint16_t* dDepth = nullptr;
+    if (depth) {
+        if (depth_stride_elems < w) return ORBF_ERR_ARG;
+        dDepth = c->d_depthIn + (size_t)slot0 * w * h;
+        if (depth_stride_elems == w && depth_frame_stride_elems == (int64_t)w * h) {
+            ORBF_CUDA(c, cudaMemcpyAsync(dDepth, depth, (size_t)n * w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        } else {
+            for (int i = 0; i < n; ++i)
+                ORBF_CUDA(c, cudaMemcpy2DAsync(dDepth + (size_t)i * w * h, (size_t)w * 2, depth + (size_t)i * depth_frame_stride_elems,
+                    (size_t)depth_stride_elems * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    c->cur_gray = dIn; c->cur_grayPitch = c->inPitch; c->cur_grayFrameStride = (long long)c->inPlane;
+    c->cur_depth = dDepth; c->cur_depthPitch = w; c->cur_depthFrameStride = (long long)w * h;
+    c->cur_slot0 = slot0; c->cur_n = n;
+    return run_extract(c, slot0, n);
+}
+
+extern "C" int orbf_frame_counts(orbf_context* c, int32_t slot0, int32_t n, int32_t* counts)
+{
+    CTX_ENTER(c);
+    if (!counts || n < 1 || slot0 < 0 || slot0 + n > c->B) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(counts, c->d_count + slot0, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_download_frame(orbf_context* c, int32_t slot, orbf_keypoint* kps, uint8_t* desc, float* xyz, int32_t cap,
+    int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || slot < 0 || slot >= c->B) return ORBF_ERR_ARG;
+    TRY(orbf_launch_pack_aos(c, slot, 1));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int n = c->h_counts[0];
+    *n_out = n;
+    if (n > cap) return ORBF_ERR_CAPACITY;
+    if (n == 0) return ORBF_OK;
+    const size_t o = (size_t)slot * c->K;
+    if (kps) ORBF_CUDA(c, cudaMemcpyAsync(c->h_kp, c->d_kpAos + o, n * sizeof(orbf_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (desc) ORBF_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc + o * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (xyz) {
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz, c->d_ptx + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + c->K, c->d_pty + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + 2 * c->K, c->d_ptz + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (kps) memcpy(kps, c->h_kp, n * sizeof(orbf_keypoint));
+    if (desc) memcpy(desc, c->h_desc, (size_t)n * 32);
+    if (xyz) for (int i = 0; i < n; ++i) { xyz[3 * i] = c->h_xyz[i]; xyz[3 * i + 1] = c->h_xyz[c->K + i]; xyz[3 * i + 2] = c->h_xyz[2 * c->K + i]; }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_extract(orbf_context* c, const uint8_t* img, int32_t width, int32_t height, int32_t stride, orbf_keypoint* kps,
+    uint8_t* desc, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out) return ORBF_ERR_ARG;
+    *n_out = 0;
+    if (!img || width == 0 || height == 0) return ORBF_OK;     // _image.empty(): outputs untouched (orbextractor.cpp:758-759)
+    if (width != c->cfg.width || height != c->cfg.height || stride < width) return ORBF_ERR_ARG;
+    TRY(orbf_extract_batch(c, 0, 1, img, stride, (int64_t)stride * height, nullptr, 0, 0));
+    return orbf_download_frame(c, 0, kps, desc, nullptr, cap, n_out);
+}
+
+extern "C" int orbf_pyramid_level(orbf_context* c, int32_t slot, int32_t level, int32_t blurred, uint8_t* out, int32_t out_stride)
+{
+    CTX_ENTER(c);
+    if (!out || slot < 0 || slot >= c->B || level < 0 || level >= c->L || out_stride < c->lg[level].w) return ORBF_ERR_ARG;
+    if (!blurred && level == 0 && !c->cur_gray) return ORBF_ERR_STATE;
+    PyrView pv = orbf_pyr_view(c, blurred != 0);
+    const LevelView& lv = pv.lv[level];
+    ORBF_CUDA(c, cudaMemcpy2DAsync(out, out_stride, lv.base + (long long)slot * lv.frameStride, lv.pitch, lv.w, lv.h,
+        cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_level_candidates(orbf_context* c, int32_t slot, int32_t level, orbf_cand* out, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || slot < 0 || slot >= c->B || level < 0 || level >= c->L) return ORBF_ERR_ARG;
+    int n = 0;
+    ORBF_CUDA(c, cudaMemcpyAsync(&n, c->d_candCount + slot * ORBF_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    if (n > cap) return ORBF_ERR_CAPACITY;
+    if (n == 0 || !out) return ORBF_OK;
+    std::vector<uint32_t> tmp(n);
+    ORBF_CUDA(c, cudaMemcpyAsync(tmp.data(), c->d_cand + (size_t)slot * c->candTotal + c->lg[level].candOff, n * sizeof(uint32_t),
+        cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) { out[i].x = tmp[i] & 0x7FF; out[i].y = (tmp[i] >> 11) & 0x7FF; out[i].score = tmp[i] >> 22; }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_level_keypoint_counts(orbf_context* c, int32_t slot, int32_t* counts)
+{
+    CTX_ENTER(c);
+    if (!counts || slot < 0 || slot >= c->B) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(counts, c->d_lkpCount + slot * ORBF_MAX_LEVELS, c->L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// matching
+// ------------------------------------------------------------------------------------------------------
+static int ensure_desc_stage(orbf_context* c, int rows)
+{
+    if (rows <= c->descStageRows) return ORBF_OK;
+    if (c->d_qdesc) cudaFree(c->d_qdesc);
+    if (c->d_tdesc) cudaFree(c->d_tdesc);
+    c->d_qdesc = c->d_tdesc = nullptr; c->descStageRows = 0;
+    ORBF_CUDA(c, cudaMalloc((void**)&c->d_qdesc, (size_t)rows * 32));
+    ORBF_CUDA(c, cudaMalloc((void**)&c->d_tdesc, (size_t)rows * 32));
+    c->descStageRows = rows;
+    return ORBF_OK;
+}
+
+static int standalone_knn(orbf_context* c, const uint8_t* q, int nq, const uint8_t* t, int nt, bool cross, MatchSet& ms)
+{
+    // pair slot 0 holds the result; K bounds both sets because the packed key stores a 16-bit index per slot row
+    if (nq < 0 || nt < 0 || nq > c->K || nt > 65535) return ORBF_ERR_ARG;
+    TRY(ensure_desc_stage(c, std::max(std::max(nq, nt), 1)));
+    if (nq) ORBF_CUDA(c, cudaMemcpyAsync(c->d_qdesc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
+    if (nt) ORBF_CUDA(c, cudaMemcpyAsync(c->d_tdesc, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
+    ms.qdesc = c->d_qdesc; ms.tdesc = c->d_tdesc; ms.qStride = ms.tStride = 0; ms.qCounts = ms.tCounts = nullptr; ms.pairs = nullptr;
+    ms.nq = nq; ms.nt = nt; ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
+    if (cross && nt > c->K) return ORBF_ERR_ARG;
+    return orbf_launch_knn2(c, ms, 1, cross);
+}
+
+static void unpack_knn(const uint32_t* kk, int nq, int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2)
+{
+    for (int i = 0; i < nq; ++i) {
+        const uint32_t a = kk[2 * i], b = kk[2 * i + 1];
+        if (idx1) idx1[i] = (a == 0xFFFFFFFFu) ? -1 : (int)(a & 0xFFFF);
+        if (d1) d1[i] = (a == 0xFFFFFFFFu) ? -1 : (int)(a >> 16);
+        if (idx2) idx2[i] = (b == 0xFFFFFFFFu) ? -1 : (int)(b & 0xFFFF);
+        if (d2) d2[i] = (b == 0xFFFFFFFFu) ? -1 : (int)(b >> 16);
+    }
+}
+
+extern "C" int orbf_knn2(orbf_context* c, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx1, int32_t* d1,
+    int32_t* idx2, int32_t* d2)
+{
+    CTX_ENTER(c);
+    if ((nq > 0 && !q) || (nt > 0 && !t)) return ORBF_ERR_ARG;
+    if (nq == 0) return ORBF_OK;
+    if (nt == 0) { unpack_knn(std::vector<uint32_t>(2 * (size_t)nq, 0xFFFFFFFFu).data(), nq, idx1, d1, idx2, d2); return ORBF_OK; }
+    MatchSet ms;
+    TRY(standalone_knn(c, q, nq, t, nt, false, ms));
+    std::vector<uint32_t> kk(2 * (size_t)nq);
+    ORBF_CUDA(c, cudaMemcpyAsync(kk.data(), c->d_knn, kk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    unpack_knn(kk.data(), nq, idx1, d1, idx2, d2);
+    return ORBF_OK;
+}
+
+extern "C" int orbf_knn_match(orbf_context* c, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, float ratio,
+    int32_t cross_check, orbf_dmatch* out, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || (nq > 0 && !q) || (nt > 0 && !t)) return ORBF_ERR_ARG;
+    *n_out = 0;
+    if (nq == 0 || nt < 2) return ORBF_OK;      // the reference indexes matchesKnn[i][1] (matcher.cpp:65): needs >= 2 train rows
+    MatchSet ms;
+    TRY(standalone_knn(c, q, nq, t, nt, cross_check != 0, ms));
+    TRY(orbf_launch_match_select(c, ms, 1, ratio, cross_check != 0));
+    c->lastNPairs = 1; c->pairsFromSlots = false;
+    return orbf_download_matches(c, 0, out, cap, n_out);
+}
+
+extern "C" int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes, int32_t* dist)
+{
+    if (!a || !b || !dist || nbytes < 0) return ORBF_ERR_ARG;
+    int d = 0;
+    for (int i = 0; i < nbytes; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+    *dist = d;
+    return ORBF_OK;
+}
+
+static MatchSet slot_match_set(orbf_context* c)
+{
+    MatchSet ms;
+    ms.qdesc = c->d_desc; ms.tdesc = c->d_desc; ms.qStride = ms.tStride = (long long)c->K * 32;
+    ms.qCounts = ms.tCounts = c->d_count; ms.pairs = c->d_pairs; ms.nq = 0; ms.nt = 0;
+    ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
+    return ms;
+}
+
+extern "C" int orbf_match_pairs(orbf_context* c, const int32_t* pairs, int32_t npairs, float ratio, int32_t cross_check)
+{
+    CTX_ENTER(c);
+    if (!pairs || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
+    for (int i = 0; i < 2 * npairs; ++i) if (pairs[i] < 0 || pairs[i] >= c->B) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_pairs, pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    MatchSet ms = slot_match_set(c);
+    TRY(orbf_launch_knn2(c, ms, npairs, cross_check != 0));
+    TRY(orbf_launch_match_select(c, ms, npairs, ratio, cross_check != 0));
+    c->lastNPairs = npairs; c->pairsFromSlots = true;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_download_matches(orbf_context* c, int32_t pair, orbf_dmatch* out, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || pair < 0 || pair >= c->P) return ORBF_ERR_ARG;
+    int n = 0;
+    ORBF_CUDA(c, cudaMemcpyAsync(&n, c->d_matchCount + pair, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    if (n > cap) return ORBF_ERR_CAPACITY;
+    if (n && out) {
+        ORBF_CUDA(c, cudaMemcpyAsync(out, c->d_matches + (size_t)pair * c->K, n * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_download_knn(orbf_context* c, int32_t pair, int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t cap,
+    int32_t* nq_out)
+{
+    CTX_ENTER(c);
+    if (!nq_out || pair < 0 || pair >= c->P || !c->pairsFromSlots) return ORBF_ERR_ARG;
+    int pr[2], nq = 0;
+    ORBF_CUDA(c, cudaMemcpyAsync(pr, c->d_pairs + 2 * pair, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(&nq, c->d_count + pr[0], sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *nq_out = nq;
+    if (nq > cap) return ORBF_ERR_CAPACITY;
+    std::vector<uint32_t> kk(2 * (size_t)std::max(nq, 1));
+    ORBF_CUDA(c, cudaMemcpyAsync(kk.data(), c->d_knn + (size_t)pair * c->K * 2, (size_t)nq * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    unpack_knn(kk.data(), nq, idx1, d1, idx2, d2);
+    return ORBF_OK;
+}
+
+extern "C" int orbf_match_counts(orbf_context* c, int32_t npairs, int32_t* counts)
+{
+    CTX_ENTER(c);
+    if (!counts || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(counts, c->d_matchCount, npairs * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// RANSAC / Kabsch
+// ------------------------------------------------------------------------------------------------------
+extern "C" int orbf_ransac_pairs(orbf_context* c, int32_t npairs, const orbf_ransac_config* cfg)
+{
+    CTX_ENTER(c);
+    if (!cfg || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
+    if (!c->pairsFromSlots || npairs > c->lastNPairs) return ORBF_ERR_STATE;
+    RansacSet rs;
+    rs.sx = c->d_ptx; rs.sy = c->d_pty; rs.sz = c->d_ptz; rs.tx = c->d_ptx; rs.ty = c->d_pty; rs.tz = c->d_ptz;
+    rs.slotStride = c->K; rs.pairs = c->d_pairs; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount;
+    rs.nsrc = rs.ndst = c->K;
+    return orbf_launch_ransac(c, rs, npairs, *cfg, nullptr);
+}
+
+extern "C" int orbf_download_ransac(orbf_context* c, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap)
+{
+    CTX_ENTER(c);
+    if (!out || pair < 0 || pair >= c->P) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(out, c->d_rres + pair, sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (out->n_inliers > cap) return ORBF_ERR_CAPACITY;
+    if (inliers && out->n_inliers > 0) {
+        ORBF_CUDA(c, cudaMemcpyAsync(inliers, c->d_inliers + (size_t)pair * c->K, out->n_inliers * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost,
+            c->stream));
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_download_ransac_summary(orbf_context* c, int32_t npairs, orbf_ransac_result* out)
+{
+    CTX_ENTER(c);
+    if (!out || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(out, c->d_rres, npairs * sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc,
+    const float* dst_xyz, int32_t ndst, const orbf_dmatch* m12, int32_t nm, const int32_t* sample_table, orbf_dmatch* inliers_out,
+    int32_t cap, orbf_ransac_result* out, orbf_hyp_trace* hyp_trace, orbf_dmatch* good_sorted_out, int32_t* sample_table_out)
+{
+    CTX_ENTER(c);
+    if (!cfg || !out || nsrc < 0 || ndst < 0 || nm < 0 || (nm > 0 && (!m12 || !src_xyz || !dst_xyz))) return ORBF_ERR_ARG;
+    if (nm > c->K) return ORBF_ERR_CAPACITY;
+    for (int i = 0; i < nm; ++i)
+        if (m12[i].queryIdx < 0 || m12[i].queryIdx >= nsrc || m12[i].trainIdx < 0 || m12[i].trainIdx >= ndst) return ORBF_ERR_ARG;
+    const int rows = std::max(std::max(nsrc, ndst), 1);
+    if (rows > c->xyzStageRows) {
+        if (c->d_sxyz) cudaFree(c->d_sxyz);
+        if (c->d_txyz) cudaFree(c->d_txyz);
+        c->d_sxyz = c->d_txyz = nullptr; c->xyzStageRows = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_sxyz, (size_t)rows * 3 * sizeof(float)));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_txyz, (size_t)rows * 3 * sizeof(float)));
+        c->xyzStageRows = rows;
+    }
+    const int R = c->xyzStageRows;
+    std::vector<float> soa((size_t)R * 3, 0.f);
+    for (int i = 0; i < nsrc; ++i) { soa[i] = src_xyz[3 * i]; soa[R + i] = src_xyz[3 * i + 1]; soa[2 * (size_t)R + i] = src_xyz[3 * i + 2]; }
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_sxyz, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < ndst; ++i) { soa[i] = dst_xyz[3 * i]; soa[R + i] = dst_xyz[3 * i + 1]; soa[2 * (size_t)R + i] = dst_xyz[3 * i + 2]; }
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_txyz, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (nm) ORBF_CUDA(c, cudaMemcpyAsync(c->d_matches, m12, nm * sizeof(orbf_dmatch), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_matchCount, &nm, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->pairsFromSlots = false; c->lastNPairs = 1;
+    const int tabN = cfg->iterations * (int)cfg->sample_size;
+    int* dTab = nullptr;
+    if (sample_table) {
+        if (tabN > c->userSamplesCap) {
+            if (c->d_userSamples) cudaFree(c->d_userSamples);
+            c->d_userSamples = nullptr; c->userSamplesCap = 0;
+            ORBF_CUDA(c, cudaMalloc((void**)&c->d_userSamples, (size_t)tabN * sizeof(int)));
+            c->userSamplesCap = tabN;
+        }
+        ORBF_CUDA(c, cudaMemcpyAsync(c->d_userSamples, sample_table, (size_t)tabN * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+        dTab = c->d_userSamples;
+    }
+    orbf_ransac_config cf = *cfg;
+    if (cf.depth_cov < 0.0) {   // standalone call: latch within this call only (matches one oracle call with depth_cov < 0)
+        const double neg = -1.0;
+        ORBF_CUDA(c, cudaMemcpyAsync(c->d_depthCov, &neg, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    RansacSet rs;
+    rs.sx = c->d_sxyz; rs.sy = c->d_sxyz + R; rs.sz = c->d_sxyz + 2 * (size_t)R;
+    rs.tx = c->d_txyz; rs.ty = c->d_txyz + R; rs.tz = c->d_txyz + 2 * (size_t)R;
+    rs.slotStride = 0; rs.pairs = nullptr; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount; rs.nsrc = nsrc; rs.ndst = ndst;
+    TRY(orbf_launch_ransac(c, rs, 1, cf, dTab));
+    TRY(orbf_download_ransac(c, 0, out, inliers_out, cap));
+    if (hyp_trace) ORBF_CUDA(c, cudaMemcpyAsync(hyp_trace, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
+    if (good_sorted_out && out->n_good > 0)
+        ORBF_CUDA(c, cudaMemcpyAsync(good_sorted_out, c->d_good, (size_t)out->n_good * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+    if (sample_table_out) ORBF_CUDA(c, cudaMemcpyAsync(sample_table_out, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_kabsch(orbf_context* c, const float* A, const float* B, int32_t n, float* T16)
+{
+    CTX_ENTER(c);
+    if (!T16 || n < 0 || (n > 0 && (!A || !B))) return ORBF_ERR_ARG;
+    const int need = 6 * std::max(n, 1) + 16;
+    if (need > c->kabschCap) {
+        if (c->d_kabsch) cudaFree(c->d_kabsch);
+        c->d_kabsch = nullptr; c->kabschCap = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_kabsch, (size_t)need * sizeof(float)));
+        c->kabschCap = need;
+    }
+    float* dA = c->d_kabsch + 16; float* dB = dA + 3 * (size_t)std::max(n, 1);
+    if (n) {
+        ORBF_CUDA(c, cudaMemcpyAsync(dA, A, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(dB, B, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    TRY(orbf_launch_kabsch(c, dA, dB, n, c->d_kabsch));
+    ORBF_CUDA(c, cudaMemcpyAsync(T16, c->d_kabsch, 16 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+// ---- test hooks for the host+device restatements in replay.h (pinned against libstdc++ / glibc in tests) ----
+extern "C" int orbf_selftest_introsort(orbf_dmatch* m, int32_t n)
+{
+    if (!m || n < 0) return ORBF_ERR_ARG;
+    replay::IntroSort<orbf_dmatch, DistanceLess> s{ m, DistanceLess() };
+    s.sort(n);
+    return ORBF_OK;
+}
+
+extern "C" int orbf_selftest_glibc_rand(uint32_t seed, int32_t n, int32_t* out)
+{
+    if (!out || n < 0) return ORBF_ERR_ARG;
+    replay::GlibcRand g;
+    g.seed(seed);
+    for (int i = 0; i < n; ++i) out[i] = g.next();
+    return ORBF_OK;
+}
+
+extern "C" int orbf_selftest_sample_table(uint32_t seed, int32_t M, int32_t iterations, int32_t sample_size, int32_t* table)
+{
+    if (!table || sample_size < 1 || sample_size > 8) return ORBF_ERR_ARG;
+    replay::GlibcRand g;
+    g.seed(seed);
+    for (int k = 0; k < iterations; ++k) {
+        if (M >= sample_size) replay::sample_row(g, M, sample_size, table + (size_t)k * sample_size);
+        else for (int s = 0; s < sample_size; ++s) table[(size_t)k * sample_size + s] = -1;
+    }
+    return ORBF_OK;
+}

@@ -1,0 +1,369 @@
+// csrc/context.cu — context lifecycle, extractor tables and device-memory layout.
+// Tables follow ORBextractor::ORBextractor (reference Features/orbextractor.cpp:346-404), the level
+// sizes ComputePyramid (:833-838), the FAST cell grid ComputeKeyPointsOctTree (:665-703), the quadtree
+// roots DistributeOctTree (:470-489) and the resize coefficients cv::resize(INTER_LINEAR, 8U) as
+// called at :846 (OpenCV fixed-point bilinear, 11-bit coefficients).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "orbf_internal.h"
+
+int orbf_cuda_fail(orbf_context* ctx, cudaError_t e, const char* what, const char* file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    if (ctx) ctx->lastError = buf;
+    return ORBF_ERR_CUDA;
+}
+
+static inline int cv_round_f(float v) { return (int)nearbyintf(v); }
+static inline int cv_round_d(double v) { return (int)nearbyint(v); }
+
+static void build_resize_tab(int src, int dst, ResizeCoef* out)
+{
+    const double inv_scale = (double)dst / src;
+    const double scale = 1. / inv_scale;
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (s < 0) { f = 0; s = 0; }
+        if (s >= src - 1) { f = 0; s = src - 1; }
+        out[d].ofs = (short)s;
+        out[d].a0 = (short)cv_round_f((1.f - f) * 2048.f);
+        out[d].a1 = (short)cv_round_f(f * 2048.f);
+        out[d].pad = 0;
+    }
+}
+
+template <typename T>
+static int dalloc(orbf_context* ctx, T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    ORBF_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_abi_version(void) { return ORBF_ABI_VERSION; }
+
+extern "C" void orbf_default_config(orbf_config* c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->width = 640; c->height = 480;
+    c->nfeatures = 1000; c->nlevels = 8; c->scale_factor = 1.2f;   // Utils/common.h:77, Features/extractor.cpp:86
+    c->ini_th_fast = 20; c->min_th_fast = 7;
+    c->max_frames = 1; c->max_pairs = 0; c->device = 0;
+    c->fx = 517.3f; c->fy = 516.5f; c->cx = 318.6f; c->cy = 255.3f;   // Utils/common.h:35-38 (FR1)
+    c->mbf = 40.0f;
+    c->depth_factor = 1.0f / 5000.0f;
+}
+
+extern "C" void orbf_default_ransac_config(orbf_ransac_config* c)
+{
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->iterations = 200; c->min_inlier_th = 20; c->max_mahal = 3.0f; c->sample_size = 4;   // Odometry/ransac.cpp:9-12
+    c->check_depth = 1; c->sort_mode = 0; c->depth_cov = -1.0; c->seed = 42;
+}
+
+extern "C" const char* orbf_status_string(int s)
+{
+    switch (s) {
+    case ORBF_OK: return "ok";
+    case ORBF_ERR_ARG: return "bad argument";
+    case ORBF_ERR_CAPACITY: return "output capacity too small";
+    case ORBF_ERR_GEOMETRY: return "image too small for pyramid / patch borders";
+    case ORBF_ERR_CUDA: return "CUDA error (see orbf_last_error)";
+    case ORBF_ERR_ALIGNMENT: return "device pointer or pitch not 16-byte aligned";
+    case ORBF_ERR_STATE: return "call order violated";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char* orbf_last_error(const orbf_context* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
+
+static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::vector<CellDesc>& cells)
+{
+    const orbf_config& g = c->cfg;
+    const int L = g.nlevels;
+    c->L = L;
+    const double scaleFactor = (double)g.scale_factor;
+    c->scale[0] = 1.0f; c->sigma2[0] = 1.0f;
+    for (int i = 1; i < L; ++i) {
+        c->scale[i] = (float)((double)c->scale[i - 1] * scaleFactor);
+        c->sigma2[i] = c->scale[i] * c->scale[i];
+    }
+    for (int i = 0; i < L; ++i) { c->invScale[i] = 1.0f / c->scale[i]; c->invSigma2[i] = 1.0f / c->sigma2[i]; }
+    const float factor = (float)(1.0 / scaleFactor);
+    float desired = (float)g.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)L));
+    int sum = 0;
+    for (int l = 0; l < L - 1; ++l) {
+        c->lg[l].nfeat = cv_round_f(desired);
+        sum += c->lg[l].nfeat;
+        desired *= factor;
+    }
+    c->lg[L - 1].nfeat = std::max(g.nfeatures - sum, 0);
+    {   // umax (orbextractor.cpp:389-403)
+        int v, v0;
+        const int vmax = (int)floor(ORBF_HALF_PATCH * sqrtf(2.f) / 2 + 1);
+        const int vmin = (int)ceil(ORBF_HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = ORBF_HALF_PATCH * ORBF_HALF_PATCH;
+        for (v = 0; v < 16; ++v) c->umax[v] = 0;
+        for (v = 0; v <= vmax; ++v) c->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+        for (v = ORBF_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+            while (c->umax[v0] == c->umax[v0 + 1]) ++v0;
+            c->umax[v] = v0;
+            ++v0;
+        }
+    }
+    int cellSlot = 0, candOff = 0, kpOff = 0;
+    c->maxCellW = c->maxCellH = 0;
+    for (int l = 0; l < L; ++l) {
+        LevelGeom& q = c->lg[l];
+        q.w = cv_round_f((float)g.width * c->invScale[l]);
+        q.h = cv_round_f((float)g.height * c->invScale[l]);
+        if (q.w < 2 * ORBF_EDGE + 8 || q.h < 2 * ORBF_EDGE + 8 || q.w > 2047 + 2 * ORBF_MINB || q.h > 2047 + 2 * ORBF_MINB)
+            return ORBF_ERR_GEOMETRY;
+        q.pitch = align_up(q.w, 128);
+        q.plane = (size_t)q.pitch * q.h;
+        q.scale = c->scale[l];
+        q.scaledPatch = (int)(31 * c->scale[l]);
+        if (l > 0) {
+            q.tabX = (int)tab.size(); tab.resize(tab.size() + q.w);
+            build_resize_tab(c->lg[l - 1].w, q.w, &tab[q.tabX]);
+            q.tabY = (int)tab.size(); tab.resize(tab.size() + q.h);
+            build_resize_tab(c->lg[l - 1].h, q.h, &tab[q.tabY]);
+        } else q.tabX = q.tabY = 0;
+        // FAST cell grid
+        const int minB = ORBF_MINB, maxBX = q.w - ORBF_EDGE + 3, maxBY = q.h - ORBF_EDGE + 3;
+        const float W = 30;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        q.cellsX = (int)(width / W); q.cellsY = (int)(height / W);
+        if (q.cellsX < 1 || q.cellsY < 1) return ORBF_ERR_GEOMETRY;
+        q.wCell = (int)ceilf(width / q.cellsX); q.hCell = (int)ceilf(height / q.cellsY);
+        q.cell0 = (int)cells.size();
+        q.candOff = candOff;
+        int cap = 0;
+        for (int i = 0; i < q.cellsY; ++i) {
+            const float iniY = (float)(minB + i * q.hCell);
+            float maxY = iniY + q.hCell + 6;
+            if (iniY >= maxBY - 3) continue;
+            if (maxY > maxBY) maxY = (float)maxBY;
+            for (int j = 0; j < q.cellsX; ++j) {
+                const float iniX = (float)(minB + j * q.wCell);
+                float maxX = iniX + q.wCell + 6;
+                if (iniX >= maxBX - 6) continue;
+                if (maxX > maxBX) maxX = (float)maxBX;
+                const int cw = (int)maxX - (int)iniX - 6, ch = (int)maxY - (int)iniY - 6;
+                if (cw <= 0 || ch <= 0) continue;   // cv::FAST scores nothing on a ROI thinner than 7
+                CellDesc d;
+                d.level = (short)l; d.x0 = (short)((int)iniX + 3); d.y0 = (short)((int)iniY + 3);
+                d.w = (short)cw; d.h = (short)ch;
+                d.relx = (short)(-minB); d.rely = (short)(-minB); d.pad = 0;
+                d.slotOff = cellSlot;
+                d.cap = ((cw + 1) / 2) * ((ch + 1) / 2);   // strict 8-neighbour maxima: <= 1 per 2x2 block
+                cellSlot += d.cap; cap += d.cap;
+                c->maxCellW = std::max(c->maxCellW, cw); c->maxCellH = std::max(c->maxCellH, ch);
+                cells.push_back(d);
+            }
+        }
+        q.nCells = (int)cells.size() - q.cell0;
+        q.candCap = cap;
+        candOff += cap;
+        // quadtree roots (orbextractor.cpp:470-472)
+        q.nIni = (int)roundf((float)(maxBX - minB) / (float)(maxBY - minB));
+        if (q.nIni < 1) return ORBF_ERR_GEOMETRY;
+        q.hX = (float)(maxBX - minB) / q.nIni;
+        q.kpCap = std::max(4 * q.nIni, q.nfeat + 3);
+        q.kpOff = kpOff;
+        kpOff += q.kpCap;
+    }
+    c->nCellsTotal = (int)cells.size();
+    c->cellSlotTotal = cellSlot;
+    c->candTotal = candOff;
+    c->kpStageTotal = kpOff;
+    c->K = align_up(kpOff, 32);
+    return ORBF_OK;
+}
+
+extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
+{
+    if (!cfg || !out) return ORBF_ERR_ARG;
+    *out = nullptr;
+    if (cfg->nlevels < 1 || cfg->nlevels > ORBF_MAX_LEVELS || cfg->width < 1 || cfg->height < 1 || cfg->nfeatures < 1
+        || cfg->max_frames < 1 || !(cfg->scale_factor > 1.0f) || cfg->ini_th_fast < 1 || cfg->min_th_fast < 1
+        || cfg->ini_th_fast > 254 || cfg->min_th_fast > cfg->ini_th_fast)
+        return ORBF_ERR_ARG;
+    orbf_context* c = new (std::nothrow) orbf_context();
+    if (!c) return ORBF_ERR_ARG;
+    c->cfg = *cfg;
+    c->B = cfg->max_frames;
+    c->P = cfg->max_pairs > 0 ? cfg->max_pairs : cfg->max_frames;
+    c->launches = 0; c->stream = nullptr; c->ownStream = false;
+    c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
+    c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;
+    std::vector<ResizeCoef> tab; std::vector<CellDesc> cells;
+    int rc = build_geometry(c, tab, cells);
+    if (rc != ORBF_OK) { delete c; return rc; }
+
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { delete c; return ORBF_ERR_CUDA; }   // no CPU fallback: fail loudly
+    auto fail = [&](int code) { *out = c; return code; };       // caller may read orbf_last_error, then destroy
+    {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) { orbf_cuda_fail(c, e2, "cudaStreamCreate", __FILE__, __LINE__); return fail(ORBF_ERR_CUDA); }
+        c->ownStream = true;
+    }
+    const size_t B = c->B, K = c->K, P = c->P;
+    c->inPitch = align_up(cfg->width, 128);
+    c->inPlane = (size_t)c->inPitch * cfg->height;
+#define TRY(x) do { int r__ = (x); if (r__ != ORBF_OK) return fail(r__); } while (0)
+    TRY(dalloc(c, &c->d_in, B * c->inPlane));
+    TRY(dalloc(c, &c->d_depthIn, B * (size_t)cfg->width * cfg->height));
+    c->d_pyr[0] = nullptr;
+    for (int l = 0; l < c->L; ++l) {
+        if (l > 0) TRY(dalloc(c, &c->d_pyr[l], B * c->lg[l].plane));
+        TRY(dalloc(c, &c->d_blur[l], B * c->lg[l].plane));
+    }
+    TRY(dalloc(c, &c->d_resizeTab, tab.size()));
+    TRY(dalloc(c, &c->d_cells, cells.size()));
+    TRY(dalloc(c, &c->d_lg, (size_t)ORBF_MAX_LEVELS));
+    TRY(dalloc(c, &c->d_cellCand, B * c->cellSlotTotal));
+    TRY(dalloc(c, &c->d_cellCount, B * c->nCellsTotal));
+    TRY(dalloc(c, &c->d_cand, B * c->candTotal));
+    TRY(dalloc(c, &c->d_candCount, B * ORBF_MAX_LEVELS));
+    TRY(dalloc(c, &c->d_nodeScratch, B * c->candTotal));
+    TRY(dalloc(c, &c->d_lkp, B * c->kpStageTotal));
+    TRY(dalloc(c, &c->d_lkpCount, B * ORBF_MAX_LEVELS));
+    TRY(dalloc(c, &c->d_kpx, B * K)); TRY(dalloc(c, &c->d_kpy, B * K)); TRY(dalloc(c, &c->d_kpsize, B * K));
+    TRY(dalloc(c, &c->d_kpangle, B * K)); TRY(dalloc(c, &c->d_kpresp, B * K));
+    TRY(dalloc(c, &c->d_ptx, B * K)); TRY(dalloc(c, &c->d_pty, B * K)); TRY(dalloc(c, &c->d_ptz, B * K));
+    TRY(dalloc(c, &c->d_uright, B * K));
+    TRY(dalloc(c, &c->d_kpoct, B * K)); TRY(dalloc(c, &c->d_kplxy, B * K));
+    TRY(dalloc(c, &c->d_desc, B * K * 32));
+    TRY(dalloc(c, &c->d_count, B));
+    TRY(dalloc(c, &c->d_kpAos, B * K));
+    TRY(dalloc(c, &c->d_pairs, P * 2));
+    TRY(dalloc(c, &c->d_knn, P * K * 2));
+    TRY(dalloc(c, &c->d_rev, P * K));
+    TRY(dalloc(c, &c->d_matches, P * K));
+    TRY(dalloc(c, &c->d_matchCount, P));
+    TRY(dalloc(c, &c->d_good, P * K));
+    TRY(dalloc(c, &c->d_goodCount, P));
+    TRY(dalloc(c, &c->d_rres, P));
+    TRY(dalloc(c, &c->d_inliers, P * K));
+    TRY(dalloc(c, &c->d_depthCov, 1));
+    c->d_samples = nullptr; c->d_hyp = nullptr;
+    c->d_qdesc = c->d_tdesc = nullptr; c->d_sxyz = c->d_txyz = nullptr;
+    c->d_kfDesc = nullptr; c->d_kfCount = nullptr;
+    c->d_pts = nullptr; c->ptsCap = 0; c->d_userSamples = nullptr; c->userSamplesCap = 0; c->d_kabsch = nullptr; c->kabschCap = 0;
+    c->d_kfKnn = nullptr; c->d_kfSurv = nullptr; c->d_kfPairs = nullptr; c->d_kfQCount = nullptr; c->kfOutCap = 0;
+    c->h_kp = nullptr; c->h_desc = nullptr; c->h_xyz = nullptr; c->h_counts = nullptr;
+    auto cu = [&](cudaError_t e3, const char* w) { if (e3 != cudaSuccess) { orbf_cuda_fail(c, e3, w, __FILE__, __LINE__); return false; } return true; };
+    if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice), "cells")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemcpy(c->d_lg, c->lg, sizeof(LevelGeom) * ORBF_MAX_LEVELS, cudaMemcpyHostToDevice), "lg")) return fail(ORBF_ERR_CUDA);
+    { const double neg = -1.0; if (!cu(cudaMemcpy(c->d_depthCov, &neg, sizeof(double), cudaMemcpyHostToDevice), "depthCov")) return fail(ORBF_ERR_CUDA); }
+    if (!cu(cudaMemset(c->d_count, 0, B * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemset(c->d_matchCount, 0, P * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemset(c->d_lkpCount, 0, B * ORBF_MAX_LEVELS * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemset(c->d_candCount, 0, B * ORBF_MAX_LEVELS * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMallocHost((void**)&c->h_kp, K * sizeof(orbf_keypoint)), "pinned")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMallocHost((void**)&c->h_desc, K * 32), "pinned")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMallocHost((void**)&c->h_xyz, K * 3 * sizeof(float)), "pinned")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMallocHost((void**)&c->h_counts, (std::max(B, P) + 16) * sizeof(int)), "pinned")) return fail(ORBF_ERR_CUDA);
+#undef TRY
+    *out = c;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_destroy(orbf_context* c)
+{
+    if (!c) return ORBF_ERR_ARG;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
+        c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
+        c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
+        c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_inliers, c->d_depthCov,
+        c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts,
+        c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int l = 0; l < c->L; ++l) { if (c->d_pyr[l]) cudaFree(c->d_pyr[l]); if (c->d_blur[l]) cudaFree(c->d_blur[l]); }
+    if (c->h_kp) cudaFreeHost(c->h_kp);
+    if (c->h_desc) cudaFreeHost(c->h_desc);
+    if (c->h_xyz) cudaFreeHost(c->h_xyz);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_set_stream(orbf_context* c, void* s)
+{
+    if (!c) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->ownStream = false;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_synchronize(orbf_context* c)
+{
+    if (!c) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_launch_count(const orbf_context* c, int64_t* n)
+{
+    if (!c || !n) return ORBF_ERR_ARG;
+    *n = c->launches;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_get_tables(const orbf_context* c, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+    int32_t* nfeat, int32_t* lw, int32_t* lh)
+{
+    if (!c) return ORBF_ERR_ARG;
+    for (int l = 0; l < c->L; ++l) {
+        if (scale) scale[l] = c->scale[l];
+        if (inv_scale) inv_scale[l] = c->invScale[l];
+        if (sigma2) sigma2[l] = c->sigma2[l];
+        if (inv_sigma2) inv_sigma2[l] = c->invSigma2[l];
+        if (nfeat) nfeat[l] = c->lg[l].nfeat;
+        if (lw) lw[l] = c->lg[l].w;
+        if (lh) lh[l] = c->lg[l].h;
+    }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_keypoint_capacity(const orbf_context* c, int32_t* cap)
+{
+    if (!c || !cap) return ORBF_ERR_ARG;
+    *cap = c->K;
+    return ORBF_OK;
+}
+
+PyrView orbf_pyr_view(const orbf_context* c, bool blurred)
+{
+    PyrView v;
+    memset(&v, 0, sizeof(v));
+    v.nlevels = c->L;
+    for (int l = 0; l < c->L; ++l) {
+        LevelView& q = v.lv[l];
+        q.w = c->lg[l].w; q.h = c->lg[l].h;
+        if (blurred) { q.base = c->d_blur[l]; q.pitch = c->lg[l].pitch; q.frameStride = (long long)c->lg[l].plane; }
+        else if (l == 0) {
+            // level 0 is the caller's input plane (mvImagePyramid[0] is a copy of the image, orbextractor.cpp:855)
+            q.base = c->cur_gray - (long long)c->cur_slot0 * c->cur_grayFrameStride;
+            q.pitch = c->cur_grayPitch; q.frameStride = c->cur_grayFrameStride;
+        } else { q.base = c->d_pyr[l]; q.pitch = c->lg[l].pitch; q.frameStride = (long long)c->lg[l].plane; }
+    }
+    return v;
+}

@@ -1,0 +1,198 @@
+// csrc/describe.cu — per-keypoint stages, one warp per keypoint:
+//   * intensity-centroid orientation (reference IC_Angle, Features/orbextractor.cpp:14-39) on the un-blurred
+//     level: lanes cover u = -15..15 of each patch row, int32 moments, shuffle reduction, then cv::fastAtan2
+//     restated with explicit round-to-nearest f32 ops (no FMA);
+//   * steered rBRIEF-256 (computeOrbDescriptor, orbextractor.cpp:43-85) on the blurred level: lane k builds
+//     descriptor byte k from 16 rotated test points (x*b + y*a, x*a - y*b with separate mul/add, cvRound =
+//     round-half-even);
+//   * output assembly (orbextractor.cpp:731-740, 805-811): pt += 16 (already in level coords), octave, size,
+//     pt *= scale[level]; rows ordered level-major then quadtree list order;
+//   * Frame::ExtractFeatures' depth gather + unprojection (Core/frame.cpp:148-164) into SoA x/y/z.
+#include "orbf_internal.h"
+
+namespace {
+
+__constant__ int c_umax[16];
+__constant__ __align__(16) int8_t c_pattern[1024];
+const int8_t h_pattern[1024] = {
+#include "rbrief_pattern.inc"
+};
+
+struct DescParams {
+    PyrView raw, blur;
+    const uint32_t* lkp; const int* lkpCount;
+    int kpStageTotal, K, slot0, L;
+    int kpOff[ORBF_MAX_LEVELS]; float scale[ORBF_MAX_LEVELS]; int scaledPatch[ORBF_MAX_LEVELS];
+    float *kpx, *kpy, *kpsize, *kpangle, *kpresp, *ptx, *pty, *ptz, *uright;
+    int* kpoct; uint32_t* kplxy; uint8_t* desc; int* count;
+    const uint16_t* depth; long long depthFrameStride; int depthPitch;   // elements
+    int width, height;
+    float cx, cy, invfx, invfy, mbf, depthFactor;
+};
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float scale = (float)(180 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+constexpr int DS_WARPS = 4;
+
+__global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(DescParams P)
+{
+    __shared__ int sPat[32 * 9];   // byte row i at words [9i, 9i+8): 9-word stride keeps lanes on distinct banks
+    for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) {
+        const int row = i >> 3, k = i & 7;
+        sPat[row * 9 + k] = *reinterpret_cast<const int*>(&c_pattern[4 * i]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = P.slot0 + blockIdx.y;
+    const int i = blockIdx.x * DS_WARPS + warp;
+    const int* lc = P.lkpCount + slot * ORBF_MAX_LEVELS;
+    int level = -1, before = 0, total = 0;
+    for (int l = 0; l < P.L; ++l) {
+        const int c = lc[l];
+        if (level < 0 && i < total + c) { level = l; before = total; }
+        total += c;
+    }
+    if (i == 0 && lane == 0) P.count[slot] = total;
+    if (level < 0) return;
+    const uint32_t key = P.lkp[(long long)slot * P.kpStageTotal + P.kpOff[level] + (i - before)];
+    const int x = (int)(key & 0x7FF) + ORBF_MINB, y = (int)((key >> 11) & 0x7FF) + ORBF_MINB;
+    const int score = (int)(key >> 22);
+
+    // ---- orientation ---------------------------------------------------------------------------------
+    const LevelView rv = P.raw.lv[level];
+    const uint8_t* c = rv.base + (long long)slot * rv.frameStride + (long long)y * rv.pitch + x;
+    const int u = lane - ORBF_HALF_PATCH;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int au = abs(u);
+#pragma unroll
+        for (int v = -ORBF_HALF_PATCH; v <= ORBF_HALF_PATCH; ++v) {
+            if (au <= c_umax[v < 0 ? -v : v]) {
+                const int val = __ldg(c + v * rv.pitch + u);
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- steered BRIEF ------------------------------------------------------------------------------
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ar = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)ar), b = (float)sin((double)ar);
+    const LevelView bv = P.blur.lv[level];
+    const uint8_t* cb = bv.base + (long long)slot * bv.frameStride + (long long)y * bv.pitch + x;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int w = sPat[lane * 9 + k];
+        const float x0 = (float)(int8_t)(w & 0xFF), y0 = (float)(int8_t)((w >> 8) & 0xFF);
+        const float x1 = (float)(int8_t)((w >> 16) & 0xFF), y1 = (float)(int8_t)((w >> 24) & 0xFF);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = __ldg(cb + r0 * bv.pitch + c0), t1 = __ldg(cb + r1 * bv.pitch + c1);
+        val |= (t0 < t1) << k;
+    }
+    const long long o = (long long)slot * P.K + i;
+    P.desc[o * 32 + lane] = (uint8_t)val;
+
+    // ---- keypoint record + depth unprojection ----------------------------------------------------------
+    if (lane == 0) {
+        float fx = (float)x, fy = (float)y;
+        if (level != 0) { fx = __fmul_rn(fx, P.scale[level]); fy = __fmul_rn(fy, P.scale[level]); }
+        P.kpx[o] = fx; P.kpy[o] = fy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
+        P.kpresp[o] = (float)score; P.kpoct[o] = level; P.kplxy[o] = (uint32_t)x | ((uint32_t)y << 16);
+        float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
+        if (P.depth) {
+            const int ui = (int)fx, vi = (int)fy;     // float -> int truncation of the (distorted) keypoint (frame.cpp:155)
+            if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
+                const float z = __fmul_rn((float)__ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui),
+                    P.depthFactor);
+                if (z > 0) {
+                    ur = __fsub_rn(fx, __fdiv_rn(P.mbf, z));
+                    X = __fmul_rn(__fmul_rn(__fsub_rn(fx, P.cx), z), P.invfx);
+                    Y = __fmul_rn(__fmul_rn(__fsub_rn(fy, P.cy), z), P.invfy);
+                    Z = z;
+                }
+            }
+        }
+        P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;
+    }
+}
+
+__global__ void pack_aos_kernel(const float* kpx, const float* kpy, const float* kpsize, const float* kpangle, const float* kpresp,
+    const int* kpoct, const int* count, orbf_keypoint* out, int K, int slot0)
+{
+    const int slot = slot0 + blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count[slot]) return;
+    const long long o = (long long)slot * K + i;
+    orbf_keypoint k;
+    k.x = kpx[o]; k.y = kpy[o]; k.size = kpsize[o]; k.angle = kpangle[o]; k.response = kpresp[o]; k.octave = kpoct[o]; k.class_id = -1;
+    out[o] = k;
+}
+
+bool g_constReady[64] = { false };
+
+}  // namespace
+
+int orbf_launch_describe(orbf_context* c, int slot0, int n)
+{
+    const int dev = c->cfg.device;
+    if (dev < 64 && !g_constReady[dev]) {
+        ORBF_CUDA(c, cudaMemcpyToSymbol(c_umax, c->umax, sizeof(int) * 16));
+        ORBF_CUDA(c, cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+        g_constReady[dev] = true;
+    }
+    DescParams P;
+    P.raw = orbf_pyr_view(c, false); P.blur = orbf_pyr_view(c, true);
+    P.lkp = c->d_lkp; P.lkpCount = c->d_lkpCount; P.kpStageTotal = c->kpStageTotal; P.K = c->K; P.slot0 = slot0; P.L = c->L;
+    for (int l = 0; l < c->L; ++l) { P.kpOff[l] = c->lg[l].kpOff; P.scale[l] = c->scale[l]; P.scaledPatch[l] = c->lg[l].scaledPatch; }
+    P.kpx = c->d_kpx; P.kpy = c->d_kpy; P.kpsize = c->d_kpsize; P.kpangle = c->d_kpangle; P.kpresp = c->d_kpresp;
+    P.ptx = c->d_ptx; P.pty = c->d_pty; P.ptz = c->d_ptz; P.uright = c->d_uright;
+    P.kpoct = c->d_kpoct; P.kplxy = c->d_kplxy; P.desc = c->d_desc; P.count = c->d_count;
+    if (c->cur_depth) {
+        P.depth = c->cur_depth - (long long)c->cur_slot0 * c->cur_depthFrameStride;
+        P.depthFrameStride = c->cur_depthFrameStride; P.depthPitch = c->cur_depthPitch;
+    } else { P.depth = nullptr; P.depthFrameStride = 0; P.depthPitch = 0; }
+    P.width = c->cfg.width; P.height = c->cfg.height;
+    P.cx = c->cfg.cx; P.cy = c->cfg.cy; P.invfx = 1.0f / c->cfg.fx; P.invfy = 1.0f / c->cfg.fy;
+    P.mbf = c->cfg.mbf; P.depthFactor = c->cfg.depth_factor;
+    dim3 grid((c->K + DS_WARPS - 1) / DS_WARPS, n);
+    describe_kernel<<<grid, DS_WARPS * 32, 0, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+int orbf_launch_pack_aos(orbf_context* c, int slot0, int n)
+{
+    dim3 grid((c->K + 127) / 128, n);
+    pack_aos_kernel<<<grid, 128, 0, c->stream>>>(c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp, c->d_kpoct, c->d_count,
+        c->d_kpAos, c->K, slot0);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}

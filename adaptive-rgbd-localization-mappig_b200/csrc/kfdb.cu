@@ -1,0 +1,122 @@
+// csrc/kfdb.cu — device-resident keyframe descriptor store and many-to-many brute-force matching
+// (BASELINE config 5).  The reference keeps keyframe descriptors in KeyFrame::mDescriptors (copied from the
+// Frame, Core/keyframe.cpp:30-40) and indexes keyframes in Core/keyframedatabase.*; its Query is DBoW3
+// inverted-file scoring, so brute-force matching against every keyframe has no literal counterpart
+// (quirk Q13): per keyframe it is defined as Matcher::KnnMatch's kNN-2 + ratio (matcher.cpp:23-35).
+// Layout: desc [kfCap][K][32] u8 + counts [kfCap]; one contiguous buffer so an NCCL all-gather of a rank's
+// shard is a single call on orbf_kfdb_device_buffers().
+#include <algorithm>
+#include <vector>
+
+#include "orbf_internal.h"
+
+#define CTX_ENTER(c)                                                                   \
+    do {                                                                               \
+        if (!(c)) return ORBF_ERR_ARG;                                                 \
+        cudaError_t e_ = cudaSetDevice((c)->cfg.device);                               \
+        if (e_ != cudaSuccess) return orbf_cuda_fail((c), e_, "cudaSetDevice", __FILE__, __LINE__); \
+    } while (0)
+#define TRY(x) do { int r__ = (x); if (r__ != ORBF_OK) return r__; } while (0)
+
+extern "C" int orbf_kfdb_reserve(orbf_context* c, int32_t maxKf)
+{
+    CTX_ENTER(c);
+    if (maxKf < 1) return ORBF_ERR_ARG;
+    if (maxKf <= c->kfCap) return ORBF_OK;
+    uint8_t* nd = nullptr; int* nc = nullptr;
+    ORBF_CUDA(c, cudaMalloc((void**)&nd, (size_t)maxKf * c->K * 32));
+    ORBF_CUDA(c, cudaMalloc((void**)&nc, (size_t)maxKf * sizeof(int)));
+    ORBF_CUDA(c, cudaMemsetAsync(nc, 0, (size_t)maxKf * sizeof(int), c->stream));
+    if (c->kfCap > 0) {
+        ORBF_CUDA(c, cudaMemcpyAsync(nd, c->d_kfDesc, (size_t)c->kfCap * c->K * 32, cudaMemcpyDeviceToDevice, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(nc, c->d_kfCount, (size_t)c->kfCap * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_kfDesc) cudaFree(c->d_kfDesc);
+    if (c->d_kfCount) cudaFree(c->d_kfCount);
+    c->d_kfDesc = nd; c->d_kfCount = nc; c->kfCap = maxKf;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_kfdb_add_from_slot(orbf_context* c, int32_t kf, int32_t slot)
+{
+    CTX_ENTER(c);
+    if (kf < 0 || kf >= c->kfCap || slot < 0 || slot >= c->B) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfDesc + (size_t)kf * c->K * 32, c->d_desc + (size_t)slot * c->K * 32, (size_t)c->K * 32,
+        cudaMemcpyDeviceToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfCount + kf, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_kfdb_add_host(orbf_context* c, int32_t kf, const uint8_t* desc, int32_t n)
+{
+    CTX_ENTER(c);
+    if (kf < 0 || kf >= c->kfCap || n < 0 || n > c->K || (n > 0 && !desc)) return ORBF_ERR_ARG;
+    if (n) ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfDesc + (size_t)kf * c->K * 32, desc, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfCount + kf, &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_kfdb_device_buffers(orbf_context* c, uint8_t** d_desc, int32_t** d_counts, int32_t* rows_per_kf, int32_t* n_kf)
+{
+    if (!c) return ORBF_ERR_ARG;
+    if (d_desc) *d_desc = c->d_kfDesc;
+    if (d_counts) *d_counts = c->d_kfCount;
+    if (rows_per_kf) *rows_per_kf = c->K;
+    if (n_kf) *n_kf = c->kfCap;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_kfdb_match(orbf_context* c, const uint8_t* q, int32_t nq, int32_t kf0, int32_t nkf, float ratio, int32_t* idx1,
+    int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors)
+{
+    CTX_ENTER(c);
+    if (!q || nq < 1 || nq > c->K || kf0 < 0 || nkf < 1 || kf0 + nkf > c->kfCap) return ORBF_ERR_ARG;
+    if (nkf > c->kfOutCap) {
+        if (c->d_kfKnn) cudaFree(c->d_kfKnn);
+        if (c->d_kfSurv) cudaFree(c->d_kfSurv);
+        if (c->d_kfPairs) cudaFree(c->d_kfPairs);
+        if (c->d_kfQCount) cudaFree(c->d_kfQCount);
+        c->d_kfKnn = nullptr; c->d_kfSurv = nullptr; c->d_kfPairs = nullptr; c->d_kfQCount = nullptr; c->kfOutCap = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_kfKnn, (size_t)nkf * c->K * 2 * sizeof(uint32_t)));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_kfSurv, (size_t)nkf * sizeof(int)));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_kfPairs, (size_t)nkf * 2 * sizeof(int)));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_kfQCount, sizeof(int)));
+        c->kfOutCap = nkf;
+    }
+    if (nq > c->descStageRows) {
+        if (c->d_qdesc) cudaFree(c->d_qdesc);
+        if (c->d_tdesc) cudaFree(c->d_tdesc);
+        c->d_qdesc = c->d_tdesc = nullptr; c->descStageRows = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_qdesc, (size_t)nq * 32));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_tdesc, (size_t)nq * 32));
+        c->descStageRows = nq;
+    }
+    std::vector<int> pairs(2 * (size_t)nkf);
+    for (int i = 0; i < nkf; ++i) { pairs[2 * i] = 0; pairs[2 * i + 1] = kf0 + i; }
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_qdesc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfPairs, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfQCount, &nq, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    MatchSet ms;
+    ms.qdesc = c->d_qdesc; ms.tdesc = c->d_kfDesc; ms.qStride = 0; ms.tStride = (long long)c->K * 32;
+    ms.qCounts = c->d_kfQCount; ms.tCounts = c->d_kfCount; ms.pairs = c->d_kfPairs; ms.nq = nq; ms.nt = 0;
+    ms.knn = c->d_kfKnn; ms.rev = nullptr; ms.matches = nullptr; ms.matchCount = c->d_kfSurv;
+    TRY(orbf_launch_knn2(c, ms, nkf, false));
+    TRY(orbf_launch_match_select(c, ms, nkf, ratio, false));
+    std::vector<uint32_t> kk((size_t)nkf * c->K * 2);
+    ORBF_CUDA(c, cudaMemcpyAsync(kk.data(), c->d_kfKnn, kk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (survivors) ORBF_CUDA(c, cudaMemcpyAsync(survivors, c->d_kfSurv, (size_t)nkf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < nkf; ++k)
+        for (int i = 0; i < nq; ++i) {
+            const uint32_t a = kk[((size_t)k * c->K + i) * 2], b = kk[((size_t)k * c->K + i) * 2 + 1];
+            const size_t o = (size_t)k * nq + i;
+            if (idx1) idx1[o] = (a == 0xFFFFFFFFu) ? -1 : (int)(a & 0xFFFF);
+            if (d1) d1[o] = (a == 0xFFFFFFFFu) ? -1 : (int)(a >> 16);
+            if (idx2) idx2[o] = (b == 0xFFFFFFFFu) ? -1 : (int)(b & 0xFFFF);
+            if (d2) d2[o] = (b == 0xFFFFFFFFu) ? -1 : (int)(b >> 16);
+        }
+    return ORBF_OK;
+}

@@ -1,0 +1,164 @@
+// csrc/orbf_internal.h — context layout and kernel launch prototypes shared by the .cu files.
+// Device memory layout (all per frame slot s in [0, max_frames)), see DESIGN.md §3:
+//   level images   pyr[l]   : [B][h_l][pitch_l] u8, pitch_l = align128(w_l); level 0 = caller's input plane
+//   blurred levels blur[l]  : same geometry
+//   cell candidates          : [B][cellSlotTotal] u32 (x|y<<11|score<<22, relative to minBorder) + [B][nCells] counts
+//   level candidates         : [B][candTotal] u32 in reference order + [B][L] counts
+//   level keypoints          : [B][kpStageTotal] u32 (quadtree output, list order) + [B][L] counts
+//   frame SoA                : kp_x,kp_y,kp_size,kp_angle,kp_resp [B][K] f32; kp_oct [B][K] i32; kp_lxy [B][K] u32;
+//                              desc [B][K][32] u8; pt_x,pt_y,pt_z,u_right [B][K] f32; count [B]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/orbfront.h"
+
+#define ORBF_EDGE 19
+#define ORBF_MINB 16          // EDGE_THRESHOLD - 3 (orbextractor.cpp:672)
+#define ORBF_HALF_PATCH 15
+#define ORBF_MAX_SAMPLE 8
+
+struct LevelView {
+    const uint8_t* base;      // address of slot 0's plane
+    long long frameStride;    // bytes between consecutive slots
+    int pitch, w, h;
+};
+struct PyrView { LevelView lv[ORBF_MAX_LEVELS]; int nlevels; };
+
+struct ResizeCoef { short ofs, a0, a1, pad; };
+
+struct CellDesc {             // one FAST cell (orbextractor.cpp:688-723): scored interior in level coordinates
+    short level, x0, y0, w, h;
+    short relx, rely;         // offset added to cell-local coords to get minBorder-relative coords
+    short pad;
+    int slotOff;              // offset of this cell's slots inside a frame's cell-candidate buffer
+    int cap;
+};
+
+struct LevelGeom {
+    int w, h, pitch;
+    size_t plane;             // bytes per slot plane
+    int nfeat;
+    int cellsX, cellsY, wCell, hCell, cell0, nCells;
+    int candOff, candCap;     // contiguous candidate list (per frame offsets, entries)
+    int kpOff, kpCap;         // quadtree output staging
+    int nIni; float hX;
+    float scale;
+    int scaledPatch;
+    int tabX, tabY;           // offsets into d_resizeTab of the x / y coefficient tables (level l from l-1)
+};
+
+struct orbf_context {
+    orbf_config cfg;
+    int L;
+    LevelGeom lg[ORBF_MAX_LEVELS];
+    float scale[ORBF_MAX_LEVELS], invScale[ORBF_MAX_LEVELS], sigma2[ORBF_MAX_LEVELS], invSigma2[ORBF_MAX_LEVELS];
+    int umax[16];
+    int B, P;                 // frame slots, pair slots
+    int K;                    // keypoint capacity per frame (multiple of 32)
+    int nCellsTotal, cellSlotTotal, candTotal, kpStageTotal, maxCellW, maxCellH;
+    cudaStream_t stream;
+    bool ownStream;
+    int64_t launches;
+    std::string lastError;
+
+    // inputs
+    uint8_t* d_in; int inPitch; size_t inPlane;
+    uint16_t* d_depthIn;
+    const uint8_t* cur_gray; long long cur_grayFrameStride; int cur_grayPitch; int cur_slot0, cur_n;
+    const uint16_t* cur_depth; long long cur_depthFrameStride; int cur_depthPitch;
+    // pyramid
+    uint8_t* d_pyr[ORBF_MAX_LEVELS];
+    uint8_t* d_blur[ORBF_MAX_LEVELS];
+    ResizeCoef* d_resizeTab;
+    CellDesc* d_cells;
+    LevelGeom* d_lg;
+    uint32_t* d_cellCand; int* d_cellCount;
+    uint32_t* d_cand; int* d_candCount;
+    uint16_t* d_nodeScratch;
+    uint32_t* d_lkp; int* d_lkpCount;
+    float *d_kpx, *d_kpy, *d_kpsize, *d_kpangle, *d_kpresp, *d_ptx, *d_pty, *d_ptz, *d_uright;
+    int* d_kpoct; uint32_t* d_kplxy; uint8_t* d_desc; int* d_count;
+    orbf_keypoint* d_kpAos;   // staging for D2H in cv::KeyPoint layout
+    // host staging (pinned)
+    orbf_keypoint* h_kp; uint8_t* h_desc; float* h_xyz; int* h_counts;
+
+    // matching (pair slots)
+    int* d_pairs;             // [P][2]
+    uint32_t* d_knn;          // [P][K][2] packed (dist<<16 | idx) best, second
+    uint32_t* d_rev;          // [P][K] packed best query per train (cross-check)
+    orbf_dmatch* d_matches; int* d_matchCount;   // [P][K]
+    int lastNPairs; bool pairsFromSlots;
+    // standalone matching staging
+    uint8_t* d_qdesc; uint8_t* d_tdesc; int descStageRows;
+
+    // RANSAC (pair slots)
+    orbf_dmatch* d_good; int* d_goodCount;        // [P][K] filtered + sorted
+    int* d_samples;                               // [P][iters][S]
+    orbf_hyp_trace* d_hyp; int hypCap;            // [P][iters]
+    orbf_ransac_result* d_rres;                   // [P]
+    orbf_dmatch* d_inliers;                       // [P][K]
+    double* d_depthCov;                           // [1] latched covariance
+    float* d_sxyz; float* d_txyz;                 // standalone staging: SoA x|y|z, grown on demand
+    int xyzStageRows;
+    void* d_pts; size_t ptsCap;                   // packed sorted correspondences [P][K] (ransac.cu: Pt6)
+    int* d_userSamples; int userSamplesCap;
+    float* d_kabsch;                              // staging for orbf_kabsch
+    int kabschCap;
+
+    // keyframe store
+    uint8_t* d_kfDesc; int* d_kfCount; int kfCap;
+    uint32_t* d_kfKnn; int* d_kfSurv; int* d_kfPairs; int* d_kfQCount; int kfOutCap;
+};
+
+// ---- error helpers --------------------------------------------------------------------------------
+int orbf_cuda_fail(orbf_context* ctx, cudaError_t e, const char* what, const char* file, int line);
+#define ORBF_CUDA(ctx, call)                                                              \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) return orbf_cuda_fail((ctx), e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define ORBF_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                  \
+        (ctx)->launches++;                                                                \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) return orbf_cuda_fail((ctx), e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+__host__ __device__ static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// ---- stage launchers (each enqueues on ctx->stream for slots [slot0, slot0+n)) ---------------------
+PyrView orbf_pyr_view(const orbf_context* ctx, bool blurred);
+int orbf_launch_pyramid(orbf_context* ctx, int slot0, int n);
+int orbf_launch_blur(orbf_context* ctx, int slot0, int n);
+int orbf_launch_fast(orbf_context* ctx, int slot0, int n);
+int orbf_launch_quadtree(orbf_context* ctx, int slot0, int n);
+int orbf_launch_describe(orbf_context* ctx, int slot0, int n);
+int orbf_launch_pack_aos(orbf_context* ctx, int slot0, int n);
+// matching: query/train descriptor matrices addressed per pair
+struct MatchSet {
+    const uint8_t* qdesc; const uint8_t* tdesc;   // base of slot 0 (row stride 32 B)
+    long long qStride, tStride;                    // bytes per slot (K*32), 0 when every pair uses slot 0
+    const int* qCounts; const int* tCounts;        // per-slot row counts (NULL => nq / nt)
+    const int* pairs;                              // [npairs][2] (query slot, train slot); NULL => slots (0, 0)
+    int nq, nt;
+    uint32_t* knn;                                 // out [npairs][K][2] packed (dist<<16 | trainIdx): best, second
+    uint32_t* rev;                                 // out [npairs][K]    packed (dist<<16 | queryIdx): best query per train row
+    orbf_dmatch* matches; int* matchCount;         // out [npairs][K], [npairs]   (matches may be NULL: count only)
+};
+int orbf_launch_knn2(orbf_context* ctx, const MatchSet& ms, int npairs, bool cross);
+int orbf_launch_match_select(orbf_context* ctx, const MatchSet& ms, int npairs, float ratio, bool cross);
+// RANSAC
+struct RansacSet {
+    const float *sx, *sy, *sz, *tx, *ty, *tz;     // SoA bases of slot 0 (or standalone arrays)
+    long long slotStride;                          // elements per slot (K) or 0
+    const int* pairs;                              // [npairs][2] or NULL
+    const orbf_dmatch* matches; const int* matchCount;   // [P][K] input matches
+    int nsrc, ndst;
+};
+int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int n, float* dT);
+int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int npairs, const orbf_ransac_config& cfg,
+    const int* d_userSamples);

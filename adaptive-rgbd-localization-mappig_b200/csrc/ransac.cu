@@ -1,0 +1,607 @@
+// csrc/ransac.cu — RANSAC-Kabsch 3D-3D (reference Ransac::Iterate and helpers, Odometry/ransac.cpp:155-431;
+// Kabsch::Compute, Odometry/kabsch.cpp:14-57).
+//
+// Three kernels per batch of frame pairs:
+//   prepare : depth filter (ransac.cpp:175-189), std::sort replay (:199, quirk Q6), gather of the sorted 3D-3D
+//             pairs into a packed array, glibc-rand sample table (SampleMatches :269-293, quirk Q5);
+//   hyp     : ONE WARP PER HYPOTHESIS.  Each executed iteration of the reference depends only on its own sample,
+//             so all `iterations` hypotheses run concurrently: up to 19 refit rounds of
+//               T = weighted Kabsch(inliers)  — pcl::TransformationFromCorrespondences restated: the f32
+//                   incremental mean/covariance recurrence is replayed in match order (lane-uniform), then a
+//                   3x3 two-sided Jacobi SVD in registers, R = U diag(1,1,sign(det U det V)) V^T;
+//               (err, inliers) = Mahalanobis scoring of ALL good pairs (ErrorFunction2 :350-414, f64, closed
+//                   form 3x3 Cholesky), lanes striding over pairs, inlier mask by __ballot_sync, error summed in
+//                   match order;
+//   select  : the sequential accept / skip-ahead / early-exit rule (:233-249) replayed over the hypothesis
+//             results in sample order, identity fallback (:252-264), inlier list of the winner re-scored.
+// All float/double arithmetic is written in the oracle's operation order and compiled with -fmad=false, so
+// inlier sets, errors and poses are bit-identical to the oracle's.
+#include <cfloat>
+#include <cmath>
+
+#include "orbf_internal.h"
+#include "replay.h"
+
+namespace {
+
+struct Pt6 { float sx, sy, sz, tx, ty, tz; float pad0, pad1; };   // 32 B: one sorted good correspondence
+
+struct RansacParams {
+    RansacSet rs;
+    orbf_ransac_config cfg;
+    orbf_dmatch* good; int* goodCount; Pt6* pts;
+    int* samples; const int* userSamples;
+    orbf_hyp_trace* hyp; orbf_ransac_result* res; orbf_dmatch* inliers;
+    double* depthCov;
+    int K, iters, S;
+    double covX, covY;
+};
+
+struct DLess { ORBF_HD bool operator()(const orbf_dmatch& a, const orbf_dmatch& b) const { return a.distance < b.distance; } };
+
+// ------------------------------------------------------------------------------------------------------
+constexpr int PR_THREADS = 128;
+
+__global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    orbf_dmatch* sm = reinterpret_cast<orbf_dmatch*>(smem);     // K entries
+    __shared__ int sWarp[PR_THREADS / 32];
+    __shared__ int sBase;
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int qs = 0, ts = 0;
+    if (P.rs.pairs) { qs = P.rs.pairs[2 * pair]; ts = P.rs.pairs[2 * pair + 1]; }
+    const float* sz = P.rs.sz + (long long)qs * P.rs.slotStride;
+    const float* tz = P.rs.tz + (long long)ts * P.rs.slotStride;
+    const orbf_dmatch* m12 = P.rs.matches + (long long)pair * P.K;
+    const int nm = P.rs.matchCount[pair];
+    if (tid == 0) sBase = 0;
+    __syncthreads();
+    if ((unsigned)nm >= P.cfg.min_inlier_th) {
+        for (int base = 0; base < nm; base += PR_THREADS) {
+            const int i = base + tid;
+            bool keep = false;
+            orbf_dmatch m;
+            if (i < nm) {
+                m = m12[i];
+                keep = true;
+                if (P.cfg.check_depth) {
+                    const float a = sz[m.queryIdx], b = tz[m.trainIdx];
+                    if (isnan(a) || isnan(b) || a <= 0 || b <= 0) keep = false;
+                }
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) sWarp[warp] = __popc(mk);
+            __syncthreads();
+            int off = sBase;
+            for (int w = 0; w < warp; ++w) off += sWarp[w];
+            if (keep) sm[off + __popc(mk & ((1u << lane) - 1))] = m;
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int w = 0; w < PR_THREADS / 32; ++w) t += sWarp[w]; sBase += t; }
+            __syncthreads();
+        }
+    }
+    const int M = sBase;
+    orbf_dmatch* good = P.good + (long long)pair * P.K;
+    if (P.cfg.sort_mode == 0) {
+        if (tid == 0) { replay::IntroSort<orbf_dmatch, DLess> s{ sm, DLess() }; s.sort(M); }
+        __syncthreads();
+        for (int i = tid; i < M; i += PR_THREADS) good[i] = sm[i];
+    } else if (P.cfg.sort_mode == 2) {   // stable: rank = #{j : d_j < d_i or (d_j == d_i and j < i)}
+        for (int i = tid; i < M; i += PR_THREADS) {
+            const float d = sm[i].distance;
+            int r = 0;
+            for (int j = 0; j < M; ++j) { const float e = sm[j].distance; r += (e < d) || (e == d && j < i); }
+            good[r] = sm[i];
+        }
+    } else for (int i = tid; i < M; i += PR_THREADS) good[i] = sm[i];
+    __syncthreads();
+    // packed, sorted 3D-3D pairs
+    const float* sx = P.rs.sx + (long long)qs * P.rs.slotStride; const float* sy = P.rs.sy + (long long)qs * P.rs.slotStride;
+    const float* tx = P.rs.tx + (long long)ts * P.rs.slotStride; const float* ty = P.rs.ty + (long long)ts * P.rs.slotStride;
+    Pt6* pts = P.pts + (long long)pair * P.K;
+    for (int i = tid; i < M; i += PR_THREADS) {
+        const orbf_dmatch m = good[i];
+        Pt6 p;
+        p.sx = sx[m.queryIdx]; p.sy = sy[m.queryIdx]; p.sz = sz[m.queryIdx];
+        p.tx = tx[m.trainIdx]; p.ty = ty[m.trainIdx]; p.tz = tz[m.trainIdx];
+        p.pad0 = p.pad1 = 0.f;
+        pts[i] = p;
+    }
+    // sample table
+    int* tab = P.samples + (long long)pair * P.iters * P.S;
+    if (P.userSamples) {
+        for (int i = tid; i < P.iters * P.S; i += PR_THREADS) tab[i] = P.userSamples[i];
+    } else if (tid == 0) {
+        if (M >= P.S) {
+            replay::GlibcRand g;
+            g.seed(P.cfg.seed + (uint32_t)pair);
+            for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
+        } else for (int i = 0; i < P.iters * P.S; ++i) tab[i] = -1;
+    }
+    if (tid == 0) P.goodCount[pair] = M;
+}
+
+// depth covariance latch (quirk Q7: static local initialised by the first DepthCovariance() call of the process)
+__global__ void ransac_latch_kernel(RansacParams P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double cz = P.cfg.depth_cov;
+    if (!(cz >= 0.0)) {
+        cz = *P.depthCov;                       // value latched by an earlier call on this context (negative if none)
+        if (!(cz >= 0.0)) {
+            const int M = P.goodCount[0];
+            const Pt6* pts = P.pts;
+            if ((unsigned)M >= P.cfg.min_inlier_th && M >= P.S)
+                for (int i = 0; i < M; ++i) {
+                    const Pt6 p = pts[i];
+                    if (p.sz == 0.0f || p.tx == 0.0f) continue;
+                    if (isnan(p.sz) || isnan(p.tz)) continue;
+                    const double sd = 0.01 * (double)p.sz * (double)p.sz;
+                    cz = sd * sd;
+                    break;
+                }
+        }
+    }
+    *P.depthCov = cz;
+}
+
+// ---- 3x3 SVD (two-sided Jacobi), same operation order as the oracle ---------------------------------------
+struct M3 { float m[3][3]; };
+
+__device__ __forceinline__ void rot_rows(M3& a, int p, int q, float c, float s)
+{
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const float x = a.m[p][j], y = a.m[q][j]; a.m[p][j] = c * x + s * y; a.m[q][j] = c * y - s * x; }
+}
+__device__ __forceinline__ void rot_cols(M3& a, int p, int q, float c, float s)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const float x = a.m[i][p], y = a.m[i][q]; a.m[i][p] = c * x - s * y; a.m[i][q] = s * x + c * y; }
+}
+
+__device__ void svd3(const float* A, M3& U, float S[3], M3& V)
+{
+    M3 M;
+    float scale = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(A[i]));
+    if (!(scale > 0.f)) scale = 1.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { M.m[i][j] = A[3 * i + j] / scale; U.m[i][j] = V.m[i][j] = (i == j) ? 1.f : 0.f; }
+    const float precision = 2.f * FLT_EPSILON, tiny = FLT_MIN;
+    float maxDiag = fmaxf(fabsf(M.m[0][0]), fmaxf(fabsf(M.m[1][1]), fabsf(M.m[2][2])));
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool finished = true;
+#pragma unroll
+        for (int p = 1; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < p; ++q) {
+                const float thr = fmaxf(tiny, precision * maxDiag);
+                if (!(fabsf(M.m[p][q]) > thr || fabsf(M.m[q][p]) > thr)) continue;
+                finished = false;
+                const float m00 = M.m[p][p], m01 = M.m[p][q], m10 = M.m[q][p], m11 = M.m[q][q];
+                float c1 = 1.f, s1 = 0.f;
+                const float t = m00 + m11, d = m10 - m01;
+                if (fabsf(d) >= tiny) {
+                    const float u = t / d;
+                    const float tmp = sqrtf(1.f + u * u);
+                    s1 = 1.f / tmp;
+                    c1 = u / tmp;
+                }
+                const float x = c1 * m00 + s1 * m10;
+                const float y = c1 * m01 + s1 * m11;
+                const float z = c1 * m11 - s1 * m01;
+                float c2 = 1.f, s2 = 0.f;
+                if (fabsf(y) >= tiny) {
+                    const float tau = (x - z) / (2.f * y);
+                    const float w = sqrtf(tau * tau + 1.f);
+                    const float tt = (tau > 0.f) ? -1.f / (tau + w) : -1.f / (tau - w);
+                    c2 = 1.f / sqrtf(tt * tt + 1.f);
+                    s2 = tt * c2;
+                }
+                const float cL = c1 * c2 + s1 * s2, sL = s1 * c2 - c1 * s2;
+                rot_rows(M, p, q, cL, sL);
+                rot_cols(M, p, q, c2, s2);
+                rot_cols(U, p, q, cL, -sL);
+                rot_cols(V, p, q, c2, s2);
+                maxDiag = fmaxf(maxDiag, fmaxf(fabsf(M.m[p][p]), fabsf(M.m[q][q])));
+            }
+        if (finished) break;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = M.m[i][i];
+        S[i] = fabsf(a);
+        if (a < 0.f) for (int r = 0; r < 3; ++r) U.m[r][i] = -U.m[r][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int k = i;
+        for (int j = i + 1; j < 3; ++j) if (S[j] > S[k]) k = j;
+        if (k != i) {
+            float t = S[i]; S[i] = S[k]; S[k] = t;
+            for (int r = 0; r < 3; ++r) {
+                t = U.m[r][i]; U.m[r][i] = U.m[r][k]; U.m[r][k] = t;
+                t = V.m[r][i]; V.m[r][i] = V.m[r][k]; V.m[r][k] = t;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S[i] *= scale;
+}
+
+__device__ __forceinline__ float det3(const M3& a)
+{
+    return a.m[0][0] * (a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1]) - a.m[0][1] * (a.m[1][0] * a.m[2][2] - a.m[1][2] * a.m[2][0])
+        + a.m[0][2] * (a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0]);
+}
+
+struct Tfc {   // pcl::TransformationFromCorrespondences
+    float accW, m1[3], m2[3], C[3][3];
+    __device__ void reset()
+    {
+        accW = 0.f;
+        for (int i = 0; i < 3; ++i) { m1[i] = m2[i] = 0.f; for (int j = 0; j < 3; ++j) C[i][j] = 0.f; }
+    }
+    __device__ void add(const float p[3], const float q[3], float w)
+    {
+        if (w == 0.0f) return;
+        accW += w;
+        const float alpha = w / accW;
+        float d1[3], d2[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { d1[i] = p[i] - m1[i]; d2[i] = q[i] - m2[i]; }
+        const float oma = 1.0f - alpha;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float outer = d2[r] * d1[c]; C[r][c] = oma * (C[r][c] + alpha * outer); }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { m1[i] += alpha * d1[i]; m2[i] += alpha * d2[i]; }
+    }
+    __device__ void transform(float* T) const
+    {
+        M3 U, V; float S[3];
+        svd3(&C[0][0], U, S, V);
+        const float s22 = (det3(U) * det3(V) < 0.0f) ? -1.0f : 1.0f;
+        float R[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const float us = U.m[i][2] * s22;
+                R[i][j] = (U.m[i][0] * V.m[j][0] + U.m[i][1] * V.m[j][1]) + us * V.m[j][2];
+            }
+        for (int i = 0; i < 3; ++i) {
+            const float rm = (R[i][0] * m1[0] + R[i][1] * m1[1]) + R[i][2] * m1[2];
+            T[4 * i + 0] = R[i][0]; T[4 * i + 1] = R[i][1]; T[4 * i + 2] = R[i][2];
+            T[4 * i + 3] = m2[i] - rm;
+        }
+        T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+    }
+};
+
+// ErrorFunction2 (ransac.cpp:350-414); cz = depth covariance (explicit, quirk Q7)
+__device__ double mahal2(const Pt6& p, const double* T, double cz, double covX, double covY)
+{
+    const double dmax = DBL_MAX;
+    if (isnan(p.sz) || isnan(p.tz)) return dmax;
+    const double a[3] = { (double)p.sx, (double)p.sy, (double)p.sz }, b[3] = { (double)p.tx, (double)p.ty, (double)p.tz };
+    double dl[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double mu = ((T[4 * i] * a[0] + T[4 * i + 1] * a[1]) + T[4 * i + 2] * a[2]) + T[4 * i + 3];
+        dl[i] = mu - b[i];
+    }
+    {
+        const double sq = (dl[0] * dl[0] + dl[1] * dl[1]) + dl[2] * dl[2];
+        const double s1 = fmax(covX, cz), s2 = fmax(covX, cz);
+        if (sq > 2.0 * (s1 + s2)) return dmax;
+    }
+    const double c1[3] = { covX * a[2], covY * a[2], cz };
+    const double c2[3] = { covX * b[2], covY * b[2], cz };
+    double S[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double v = ((T[i] * c1[0]) * T[j] + (T[4 + i] * c1[1]) * T[4 + j]) + (T[8 + i] * c1[2]) * T[8 + j];
+            S[i][j] = v + ((i == j) ? c2[i] : 0.0);
+        }
+    if (isnan(dl[2])) return dmax;
+    double L[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double x = S[k][k];
+        for (int j = 0; j < k; ++j) x -= L[k][j] * L[k][j];
+        if (!(x > 0.0)) return dmax;
+        const double lkk = sqrt(x);
+        L[k][k] = lkk;
+        for (int i = k + 1; i < 3; ++i) {
+            double v = S[i][k];
+            for (int j = 0; j < k; ++j) v -= L[i][j] * L[k][j];
+            L[i][k] = v / lkk;
+        }
+    }
+    double y[3], xs[3];
+    y[0] = dl[0] / L[0][0];
+    y[1] = (dl[1] - L[1][0] * y[0]) / L[1][1];
+    y[2] = ((dl[2] - L[2][0] * y[0]) - L[2][1] * y[1]) / L[2][2];
+    xs[2] = y[2] / L[2][2];
+    xs[1] = (y[1] - L[2][1] * xs[2]) / L[1][1];
+    xs[0] = ((y[0] - L[1][0] * xs[1]) - L[2][0] * xs[2]) / L[0][0];
+    const double d2 = (dl[0] * xs[0] + dl[1] * xs[1]) + dl[2] * xs[2];
+    if (!(d2 >= 0.0)) return dmax;
+    return d2;
+}
+
+constexpr int HY_WARPS = 4;
+constexpr int MAX_WORDS = 64;   // supports up to 2048 good matches per pair
+
+// ComputeInliersAndError (ransac.cpp:315-348) by one warp: fills mask[] (bit i of word i/32), returns error
+__device__ double score_all(const Pt6* pts, int M, const float* T4f, double cz, const RansacParams& P, uint32_t* mask, int& nInl)
+{
+    const int lane = threadIdx.x & 31;
+    double T[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) T[i] = (double)T4f[i];
+    const double thr = (double)(P.cfg.max_mahal * P.cfg.max_mahal);
+    double mean = 0.0;
+    int cnt = 0;
+    for (int b = 0; b < M; b += 32) {
+        const int i = b + lane;
+        bool in = false;
+        double d = 0.0;
+        if (i < M) {
+            const Pt6 p = pts[i];
+            if (!(p.sz == 0.0f || p.tx == 0.0f)) {            // sic: target.x (quirk Q8)
+                d = mahal2(p, T, cz, P.covX, P.covY);
+                in = !(d > thr) && (d >= 0.0);
+            }
+        }
+        unsigned mk = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) mask[b >> 5] = mk;
+        cnt += __popc(mk);
+        while (mk) {                                           // meanError += mahalDist, in match order
+            const int src = __ffs(mk) - 1;
+            mk &= mk - 1;
+            mean += __shfl_sync(0xffffffffu, d, src);
+        }
+    }
+    __syncwarp();
+    nInl = cnt;
+    if (cnt < 3) return 1e9;
+    mean /= (double)cnt;
+    return sqrt(mean);
+}
+
+__global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams P)
+{
+    __shared__ uint32_t sMask[HY_WARPS][MAX_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.y;
+    const int k = blockIdx.x * HY_WARPS + warp;
+    if (k >= P.iters) return;
+    const int M = P.goodCount[pair];
+    orbf_hyp_trace* tr = P.hyp + (long long)pair * P.iters + k;
+    const float I16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    float refT[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) refT[i] = I16[i];
+    int nRefined = 0, rounds = -1;
+    double refErr = 1e6;
+    if ((unsigned)M >= P.cfg.min_inlier_th && M >= P.S && M <= MAX_WORDS * 32) {
+        const Pt6* pts = P.pts + (long long)pair * P.K;
+        const int* row = P.samples + ((long long)pair * P.iters + k) * P.S;
+        const double cz = *P.depthCov;
+        uint32_t* mask = sMask[warp];
+        const int words = (M + 31) >> 5;
+        for (int w = lane; w < words; w += 32) mask[w] = 0;
+        __syncwarp();
+        if (lane == 0) for (int s = 0; s < P.S; ++s) { const int id = row[s]; if (id >= 0 && id < M) mask[id >> 5] |= 1u << (id & 31); }
+        __syncwarp();
+        rounds = 0;
+        for (int refinements = 1; refinements < 20; ++refinements) {
+            // GetTransformFromMatches (ransac.cpp:295-313): lane-uniform replay of the incremental recurrence
+            Tfc tfc; tfc.reset();
+            for (int w = 0; w < words; ++w) {
+                uint32_t mk = mask[w];
+                while (mk) {
+                    const int i = (w << 5) + __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const Pt6 p = pts[i];
+                    if (isnan(p.sz) || isnan(p.tz)) continue;
+                    const float from[3] = { p.sx, p.sy, p.sz }, to[3] = { p.tx, p.ty, p.tz };
+                    tfc.add(from, to, 1.0f / (p.sz * p.tz));
+                }
+            }
+            float T[16];
+            tfc.transform(T);
+            ++rounds;
+            __syncwarp();
+            int nInl;
+            const double err = score_all(pts, M, T, cz, P, mask, nInl);
+            if ((unsigned)nInl < P.cfg.min_inlier_th || err > (double)P.cfg.max_mahal) break;
+            if (nInl >= nRefined && err <= refErr) {
+                const int prev = nRefined;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) refT[i] = T[i];
+                nRefined = nInl;
+                refErr = err;
+                if (nInl == prev) break;
+            } else break;
+        }
+    }
+    if (lane == 0) {
+        tr->n_refined = nRefined; tr->rounds = rounds; tr->refined_error = refErr;
+        for (int i = 0; i < 16; ++i) tr->T[i] = refT[i];
+    }
+}
+
+__global__ void __launch_bounds__(32) ransac_select_kernel(RansacParams P)
+{
+    __shared__ uint32_t sMask[MAX_WORDS];
+    __shared__ int sWin, sIdentity;
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    const int M = P.goodCount[pair];
+    const int nm = P.rs.matchCount[pair];
+    orbf_ransac_result* res = P.res + pair;
+    const orbf_hyp_trace* hyp = P.hyp + (long long)pair * P.iters;
+    const orbf_dmatch* good = P.good + (long long)pair * P.K;
+    const Pt6* pts = P.pts + (long long)pair * P.K;
+    orbf_dmatch* inl = P.inliers + (long long)pair * P.K;
+    const double cz = *P.depthCov;
+    const unsigned minInl = P.cfg.min_inlier_th;
+    float rmse = 1e6f;
+    int win = -1, nBest = 0, realIters = 0, validIters = 0, usedIdentity = 0;
+    const bool runnable = (unsigned)nm >= minInl && (unsigned)M >= minInl && M <= MAX_WORDS * 32;
+    if (runnable && lane == 0) {
+        for (int n = 0; n < P.iters && M >= P.S; ++n) {
+            const orbf_hyp_trace h = hyp[realIters];
+            realIters++;
+            if (h.n_refined > 0) {
+                validIters++;
+                if (h.refined_error <= (double)rmse && h.n_refined >= nBest && (unsigned)h.n_refined >= minInl) {
+                    rmse = (float)h.refined_error;
+                    win = realIters - 1;
+                    nBest = h.n_refined;
+                    if ((double)h.n_refined > (double)M * 0.5) n += 10;
+                    if ((double)h.n_refined > (double)M * 0.75) n += 10;
+                    if ((double)h.n_refined > (double)M * 0.8) break;
+                }
+            }
+        }
+    }
+    if (lane == 0) sWin = win;
+    __syncwarp();
+    win = sWin;
+    validIters = __shfl_sync(0xffffffffu, validIters, 0);
+    float T[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    int nInl = 0;
+    bool haveMask = false;
+    if (runnable && win >= 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) T[i] = hyp[win].T[i];
+        score_all(pts, M, T, cz, P, sMask, nInl);          // vRefinedMatches of the winner, recomputed
+        haveMask = true;
+    } else if (runnable && validIters == 0) {
+        const double err = score_all(pts, M, T, cz, P, sMask, nInl);
+        int ok = ((unsigned)nInl > minInl && err < (double)P.cfg.max_mahal) ? 1 : 0;
+        if (lane == 0) sIdentity = ok;
+        __syncwarp();
+        if (sIdentity) {
+            haveMask = true; usedIdentity = 1;
+            rmse = (float)((double)rmse + err);
+            validIters = 1;
+        } else nInl = 0;
+    }
+    int outCount = 0;
+    if (haveMask) {
+        __syncwarp();
+        for (int b = 0; b < M; b += 32) {
+            const uint32_t mk = sMask[b >> 5];
+            const int i = b + lane;
+            if (mk & (1u << lane)) inl[outCount + __popc(mk & ((1u << lane) - 1))] = good[i];
+            outCount += __popc(mk);
+        }
+    }
+    if (lane == 0) {
+        orbf_ransac_result r;
+        r.ok = ((unsigned)outCount >= minInl) ? 1 : 0;
+        r.rmse = rmse;
+        for (int i = 0; i < 16; ++i) r.T12[i] = T[i];
+        r.n_inliers = outCount; r.n_good = ((unsigned)nm >= minInl) ? M : 0;
+        r.real_iters = realIters; r.valid_iters = validIters; r.used_identity = usedIdentity;
+        r.depth_cov_used = cz;
+        *res = r;
+    }
+}
+
+// Kabsch::Compute (kabsch.cpp:14-57), single thread (the reference never calls it on the hot path)
+__global__ void kabsch_kernel(const float* A, const float* B, int n, float* T)
+{
+    if (threadIdx.x != 0) return;
+    const float I16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    for (int i = 0; i < 16; ++i) T[i] = I16[i];
+    if (n == 0) return;
+    float ca[3] = { 0, 0, 0 }, cb[3] = { 0, 0, 0 };
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { ca[k] += A[3 * i + k]; cb[k] += B[3 * i + k]; }
+    for (int k = 0; k < 3; ++k) { ca[k] /= (float)n; cb[k] /= (float)n; }
+    float H[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int i = 0; i < n; ++i)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) H[3 * r + c] += (A[3 * i + r] - ca[r]) * (B[3 * i + c] - cb[c]);
+    M3 V, W; float S[3];
+    svd3(H, V, S, W);
+    M3 Hm;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Hm.m[i][j] = H[3 * i + j];
+    const float det = det3(Hm);
+    const float d = (det != 0.f) ? (float)((det > 0.f) - (det < 0.f)) : 1.f;
+    float R[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i][j] = (W.m[i][0] * V.m[j][0] + W.m[i][1] * V.m[j][1]) + (W.m[i][2] * d) * V.m[j][2];
+    for (int i = 0; i < 3; ++i) {
+        const float rc = (R[i][0] * ca[0] + R[i][1] * ca[1]) + R[i][2] * ca[2];
+        T[4 * i] = R[i][0]; T[4 * i + 1] = R[i][1]; T[4 * i + 2] = R[i][2];
+        T[4 * i + 3] = cb[i] - rc;
+    }
+}
+
+}  // namespace
+
+int orbf_launch_kabsch(orbf_context* c, const float* dA, const float* dB, int n, float* dT)
+{
+    kabsch_kernel<<<1, 32, 0, c->stream>>>(dA, dB, n, dT);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int npairs, const orbf_ransac_config& cfg, const int* d_userSamples)
+{
+    if (npairs <= 0) return ORBF_OK;
+    if (cfg.iterations < 1 || cfg.sample_size < 1 || cfg.sample_size > ORBF_MAX_SAMPLE || cfg.iterations > 100000) return ORBF_ERR_ARG;
+    const int iters = cfg.iterations, S = (int)cfg.sample_size;
+    const size_t needHyp = (size_t)c->P * iters;
+    if ((size_t)c->hypCap < needHyp || !c->d_hyp) {
+        if (c->d_hyp) cudaFree(c->d_hyp);
+        if (c->d_samples) cudaFree(c->d_samples);
+        c->d_hyp = nullptr; c->d_samples = nullptr;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_hyp, needHyp * sizeof(orbf_hyp_trace)));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_samples, needHyp * ORBF_MAX_SAMPLE * sizeof(int)));
+        c->hypCap = (int)needHyp;
+    }
+    if (c->K > MAX_WORDS * 32) return ORBF_ERR_ARG;
+    const size_t needPts = (size_t)c->P * c->K;
+    if (c->ptsCap < needPts) {
+        if (c->d_pts) cudaFree(c->d_pts);
+        c->d_pts = nullptr; c->ptsCap = 0;
+        ORBF_CUDA(c, cudaMalloc(&c->d_pts, needPts * sizeof(Pt6)));
+        c->ptsCap = needPts;
+    }
+    RansacParams P;
+    P.rs = rs; P.cfg = cfg; P.good = c->d_good; P.goodCount = c->d_goodCount; P.pts = reinterpret_cast<Pt6*>(c->d_pts);
+    P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
+    P.depthCov = c->d_depthCov; P.K = c->K; P.iters = iters; P.S = S;
+    {   // raster covariances of ErrorFunction2 (ransac.cpp:352-359), host libm like the reference
+        const double ax = 58.0 / 180.0 * M_PI, ay = 45.0 / 180.0 * M_PI;
+        const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
+        P.covX = sx * sx; P.covY = sy * sy;
+    }
+    const size_t smem = (size_t)c->K * sizeof(orbf_dmatch);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ransac_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac smem attr", __FILE__, __LINE__);
+    }
+    ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    dim3 grid((iters + HY_WARPS - 1) / HY_WARPS, npairs);
+    ransac_hyp_kernel<<<grid, HY_WARPS * 32, 0, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    ransac_select_kernel<<<npairs, 32, 0, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}

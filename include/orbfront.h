@@ -1,0 +1,178 @@
+/* include/orbfront.h — C ABI of the B200-native ORB front end (liborbfront_b200.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of ttwang0303/Adaptive-RGBD-Localization-Mappig:
+ *   ORB extraction -> brute-force Hamming kNN-2 matching -> RANSAC-Kabsch 3D-3D.
+ * Plain pointers, sizes and POD structs only: no OpenCV / Eigen / PCL / torch types cross this line.
+ * Every entry point returns an orbf_status (0 = OK), never throws, and is thread-safe per context.
+ * There is NO CPU fallback: without a CUDA device orbf_create() fails with ORBF_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   orbf_create/orbf_get_tables      ORBextractor::ORBextractor + Get* getters   Features/orbextractor.cpp:346-404, orbextractor.h:44-55
+ *   orbf_extract                      ORBextractor::operator()                    Features/orbextractor.cpp:756-815 (orbextractor.h:37)
+ *                                     Extractor::Extract (ORB_SLAM2 route)        Features/extractor.cpp:39-42
+ *   orbf_extract_batch*               the same, batched + Frame::ExtractFeatures' depth gather   Core/frame.cpp:135-170
+ *   orbf_pyramid_level                public member mvImagePyramid                Features/orbextractor.h:57
+ *   orbf_knn2 / orbf_knn_match        cv::BFMatcher::knnMatch(k=2) + ratio test in Matcher::KnnMatch   Features/matcher.cpp:55-66 (23-35)
+ *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
+ *   orbf_match_pairs                  Tracking::TrackFrame's matcher call, batched  System/tracking.cpp:197-199
+ *   orbf_ransac_iterate               Ransac::Iterate(Frame*,Frame*,m12)          Odometry/ransac.cpp:155-267
+ *   orbf_ransac_pairs                 Odometry::Compute -> Ransac::Iterate, batched   Odometry/odometry.cpp:48
+ *   orbf_kabsch                       Kabsch::Compute                             Odometry/kabsch.cpp:14-57
+ *   orbf_kfdb_*                       keyframe descriptor storage of Core/keyframedatabase (config 5 many-to-many matching)
+ */
+#ifndef ORBFRONT_H
+#define ORBFRONT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBF_MAX_LEVELS 16
+#define ORBF_ABI_VERSION 1
+
+typedef enum {
+    ORBF_OK = 0,
+    ORBF_ERR_ARG = 1,        /* null pointer / out-of-range argument                          */
+    ORBF_ERR_CAPACITY = 2,   /* caller buffer too small; required size is still reported       */
+    ORBF_ERR_GEOMETRY = 3,   /* image too small for the pyramid / patch borders                */
+    ORBF_ERR_CUDA = 4,       /* CUDA runtime error or no device (see orbf_last_error)          */
+    ORBF_ERR_ALIGNMENT = 5,  /* device pointer / pitch not 16-byte aligned                     */
+    ORBF_ERR_STATE = 6       /* call order violated (e.g. match before extract)                */
+} orbf_status;
+
+/* POD mirrors of cv::KeyPoint (28 B) and cv::DMatch (16 B): same field order and sizes, so a
+ * std::vector<cv::KeyPoint> / std::vector<cv::DMatch> can be filled with one memcpy.          */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } orbf_keypoint;
+typedef struct { int32_t queryIdx, trainIdx, imgIdx; float distance; } orbf_dmatch;
+/* FAST candidate before quadtree distribution: coordinates relative to minBorder (16), cv::FAST response */
+typedef struct { int32_t x, y, score; } orbf_cand;
+
+typedef struct {
+    int32_t width, height;             /* frame size in pixels                                   */
+    int32_t nfeatures, nlevels;        /* ORBextractor(nfeatures, scaleFactor, nlevels, iniTh, minTh) */
+    float scale_factor;
+    int32_t ini_th_fast, min_th_fast;
+    int32_t max_frames;                /* frame slots kept device-resident (batch capacity)      */
+    int32_t max_pairs;                 /* frame-pair slots for matching / RANSAC (0 = max_frames)*/
+    int32_t device;                    /* CUDA device ordinal                                    */
+    float fx, fy, cx, cy, mbf;         /* Calibration:: (Utils/common.h:35-38,71)               */
+    float depth_factor;                /* Calibration::depthFactor = 1/5000 (Utils/common.h:67) */
+} orbf_config;
+
+typedef struct {
+    int32_t iterations;                /* Ransac(iters, minInlierTh, maxMahalanobisDist, sampleSize) */
+    uint32_t min_inlier_th;
+    float max_mahal;
+    uint32_t sample_size;              /* <= 8 */
+    int32_t check_depth;
+    int32_t sort_mode;                 /* 0 = libstdc++ std::sort replay (reference), 1 = keep order, 2 = stable */
+    double depth_cov;                  /* quirk Q7: process-wide depth covariance; < 0 => latch from the first
+                                          scored pair of the call (batched: of pair 0) and return it            */
+    uint32_t seed;                     /* sample tables: glibc srand(seed + pair_index) / rand() restated      */
+} orbf_ransac_config;
+
+typedef struct {
+    int32_t ok;                        /* Ransac::Iterate's bool                                  */
+    float rmse;
+    float T12[16];                     /* row-major 4x4 (mT12)                                    */
+    int32_t n_inliers, n_good, real_iters, valid_iters, used_identity;
+    double depth_cov_used;
+} orbf_ransac_result;
+
+typedef struct {                       /* per-hypothesis trace (row k of the sample table), parity tests */
+    int32_t n_refined, rounds;
+    double refined_error;
+    float T[16];
+} orbf_hyp_trace;
+
+typedef struct orbf_context orbf_context;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int orbf_abi_version(void);
+void orbf_default_config(orbf_config* cfg);                 /* 640x480, 1000 kp, 1.2, 8, 20, 7, FR1 intrinsics */
+void orbf_default_ransac_config(orbf_ransac_config* cfg);   /* Ransac(200, 20, 3.0f, 4)                        */
+int orbf_create(const orbf_config* cfg, orbf_context** out);
+int orbf_destroy(orbf_context* ctx);
+const char* orbf_status_string(int status);
+const char* orbf_last_error(const orbf_context* ctx);       /* detail of the last ORBF_ERR_CUDA             */
+int orbf_set_stream(orbf_context* ctx, void* cuda_stream);  /* run on a caller-owned cudaStream_t            */
+int orbf_synchronize(orbf_context* ctx);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+int orbf_launch_count(const orbf_context* ctx, int64_t* n);
+
+/* ---- extractor tables: GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / ... ---- */
+int orbf_get_tables(const orbf_context* ctx, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+    int32_t* nfeat_per_level, int32_t* level_w, int32_t* level_h);
+int orbf_keypoint_capacity(const orbf_context* ctx, int32_t* cap);   /* max keypoints one frame can yield */
+
+/* ---- extraction ------------------------------------------------------------------------------ */
+/* Single frame, host in / host out (ORBextractor::operator()).  img may be pageable.  n_out always
+ * receives the keypoint count; ORBF_ERR_CAPACITY if cap is too small.  Uses frame slot 0.          */
+int orbf_extract(orbf_context* ctx, const uint8_t* img, int32_t width, int32_t height, int32_t stride,
+    orbf_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* n_out);
+/* Batched, host input: copies n gray frames (+ optional u16 depth) into slots [slot0, slot0+n) on the
+ * context stream and extracts them.  Asynchronous; results stay device-resident.                    */
+int orbf_extract_batch(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems);
+/* Batched, device input (already in HBM): pointers must be 16-byte aligned, gray pitch a multiple of 16. */
+int orbf_extract_batch_device(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems);
+/* Results of one slot -> host (synchronises the stream). xyz = mvKeys3Dc (N x 3 floats), may be NULL. */
+int orbf_download_frame(orbf_context* ctx, int32_t slot, orbf_keypoint* kps, uint8_t* desc, float* xyz,
+    int32_t cap, int32_t* n_out);
+int orbf_frame_counts(orbf_context* ctx, int32_t slot0, int32_t n, int32_t* counts);
+/* Parity / mvImagePyramid access: level image, blurred level, FAST candidates (reference order). */
+int orbf_pyramid_level(orbf_context* ctx, int32_t slot, int32_t level, int32_t blurred, uint8_t* out, int32_t out_stride);
+int orbf_level_candidates(orbf_context* ctx, int32_t slot, int32_t level, orbf_cand* out, int32_t cap, int32_t* n_out);
+int orbf_level_keypoint_counts(orbf_context* ctx, int32_t slot, int32_t* counts /* [nlevels] */);
+
+/* ---- matching -------------------------------------------------------------------------------- */
+/* Raw kNN-2 on host descriptor matrices (rows of 32 bytes): BFMatcher(NORM_HAMMING).knnMatch(k=2).
+ * idx2/d2 = -1 when the train set has fewer than 2 rows.                                          */
+int orbf_knn2(orbf_context* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx1, int32_t* d1,
+    int32_t* idx2, int32_t* d2);
+/* kNN-2 + ratio test (m1.distance < ratio * m2.distance, float) + optional mutual-NN cross-check;
+ * survivors in query order, as Matcher::KnnMatch builds them before its host-side landmark filter. */
+int orbf_knn_match(orbf_context* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, float ratio,
+    int32_t cross_check, orbf_dmatch* out, int32_t cap, int32_t* n_out);
+int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes, int32_t* dist);  /* host helper */
+/* Device-resident: match frame slot pairs (query_slot, train_slot); results live in pair slots 0..npairs-1. */
+int orbf_match_pairs(orbf_context* ctx, const int32_t* pairs /* 2*npairs */, int32_t npairs, float ratio,
+    int32_t cross_check);
+int orbf_download_matches(orbf_context* ctx, int32_t pair, orbf_dmatch* out, int32_t cap, int32_t* n_out);
+int orbf_download_knn(orbf_context* ctx, int32_t pair, int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t cap,
+    int32_t* nq_out);
+int orbf_match_counts(orbf_context* ctx, int32_t npairs, int32_t* counts);
+
+/* ---- RANSAC / Kabsch ------------------------------------------------------------------------- */
+/* Host in / host out Ransac::Iterate.  sample_table: iterations x sample_size ascending ids into the
+ * sorted good-match list (-1 padded) or NULL => glibc rand() restated from cfg->seed.
+ * Optional traces (may be NULL): per-hypothesis, the sorted good matches, the sample table used.   */
+int orbf_ransac_iterate(orbf_context* ctx, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc,
+    const float* dst_xyz, int32_t ndst, const orbf_dmatch* m12, int32_t nm, const int32_t* sample_table,
+    orbf_dmatch* inliers_out, int32_t cap, orbf_ransac_result* out, orbf_hyp_trace* hyp_trace,
+    orbf_dmatch* good_sorted_out, int32_t* sample_table_out);
+/* Device-resident: RANSAC on the pairs last matched by orbf_match_pairs. */
+int orbf_ransac_pairs(orbf_context* ctx, int32_t npairs, const orbf_ransac_config* cfg);
+int orbf_download_ransac(orbf_context* ctx, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap);
+int orbf_download_ransac_summary(orbf_context* ctx, int32_t npairs, orbf_ransac_result* out /* [npairs] */);
+int orbf_kabsch(orbf_context* ctx, const float* setA, const float* setB, int32_t n, float* T16);
+
+/* ---- keyframe descriptor store (Core/keyframedatabase, BASELINE config 5) --------------------- */
+/* Copies the descriptors of frame slot `slot` into keyframe entry `kf` of the device-resident store
+ * (capacity max_keyframes, set on first use); many-to-many matching runs a-16 against every entry.  */
+int orbf_kfdb_reserve(orbf_context* ctx, int32_t max_keyframes);
+int orbf_kfdb_add_from_slot(orbf_context* ctx, int32_t kf, int32_t slot);
+int orbf_kfdb_add_host(orbf_context* ctx, int32_t kf, const uint8_t* desc, int32_t n);
+int orbf_kfdb_device_buffers(orbf_context* ctx, uint8_t** d_desc, int32_t** d_counts, int32_t* rows_per_kf,
+    int32_t* n_kf);
+/* query (host, nq x 32) against keyframes [kf0, kf0+nkf): per keyframe top-2 per query and the number of
+ * ratio survivors (out arrays sized nkf x nq, counts sized nkf).                                      */
+int orbf_kfdb_match(orbf_context* ctx, const uint8_t* q, int32_t nq, int32_t kf0, int32_t nkf, float ratio,
+    int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBFRONT_H */

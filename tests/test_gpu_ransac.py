@@ -1,0 +1,96 @@
+"""GPU parity: RANSAC-Kabsch through the C ABI vs the oracle.  Bars: identical sorted good-match list
+(std::sort replay), identical sample table (glibc rand replay), identical per-hypothesis inlier counts and
+errors, identical final inlier set; pose within 1e-5 (in fact bit-equal: same f32/f64 operation order)."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(ob):
+    c = ob.Context(max_frames=2)
+    yield c
+    c.close()
+
+
+def _compare(g, r):
+    assert g["n_good"] == r["n_good"]
+    assert g["good_sorted"].tobytes() == r["good_sorted"].tobytes(), "std::sort replay differs"
+    assert np.array_equal(g["sample_table"], r["sample_table"]), "sample table differs"
+    assert g["depth_cov"] == r["depth_cov"]
+    hg, hr = g["hyp"], r["hyp"]
+    run = hr["rounds"] >= 0                 # hypotheses the (sequential) oracle actually executed
+    assert np.array_equal(hg["n_refined"][run], hr["n_refined"][run]), "per-hypothesis inlier counts differ"
+    assert np.array_equal(hg["rounds"][run], hr["rounds"][run])
+    assert np.array_equal(hg["refined_error"][run], hr["refined_error"][run])
+    assert np.allclose(hg["T"][run], hr["T"][run], atol=1e-5)
+    assert g["ok"] == r["ok"] and g["real_iters"] == r["real_iters"] and g["valid_iters"] == r["valid_iters"]
+    assert g["used_identity"] == r["used_identity"]
+    assert g["inliers"].tobytes() == r["inliers"].tobytes(), "final inlier set differs"
+    assert np.abs(g["T12"] - r["T12"]).max() <= 1e-5
+    assert np.array_equal(g["T12"], r["T12"])
+    assert g["rmse"] == r["rmse"]
+
+
+@pytest.mark.parametrize("seed", [42, 7, 1234])
+@pytest.mark.parametrize("outliers", [0.3, 0.6, 0.05])
+def test_iterate_matches_oracle(ctx, orc, seed, outliers):
+    src, dst, m, R, t = synth.rigid_pairs(seed=seed, outlier_frac=outliers)
+    g = ctx.ransac_iterate(src, dst, m, seed=seed)
+    r = orc.ransac_iterate(src, dst, m, seed=seed)
+    _compare(g, r)
+    if outliers < 0.5:
+        assert r["ok"]
+        assert np.abs(r["T12"][:3, :3] - R).max() < 5e-3 and np.abs(r["T12"][:3, 3] - t).max() < 2e-2
+
+
+def test_explicit_sample_table_and_depth_cov(ctx, orc):
+    src, dst, m, _, _ = synth.rigid_pairs(seed=5)
+    r0 = orc.ransac_iterate(src, dst, m, seed=1)
+    tab = orc.sample_table_libc(99, r0["n_good"])
+    g = ctx.ransac_iterate(src, dst, m, sample_table=tab, depth_cov=2.5e-4)
+    r = orc.ransac_iterate(src, dst, m, sample_table=tab, depth_cov=2.5e-4)
+    _compare(g, r)
+
+
+def test_too_few_matches_and_all_outliers(ctx, orc):
+    src, dst, m, _, _ = synth.rigid_pairs(seed=6)
+    g = ctx.ransac_iterate(src, dst, m[:10]); r = orc.ransac_iterate(src, dst, m[:10])
+    assert not g["ok"] and not r["ok"] and g["rmse"] == r["rmse"] == 1e6 and len(g["inliers"]) == 0
+    src2, dst2, m2, _, _ = synth.rigid_pairs(seed=8, outlier_frac=1.0)
+    _compare(ctx.ransac_iterate(src2, dst2, m2, seed=3), orc.ransac_iterate(src2, dst2, m2, seed=3))
+
+
+def test_identity_motion_uses_fallback_or_hypothesis(ctx, orc):
+    """dst == src: whichever path the reference takes (hypothesis or identity fallback), both agree."""
+    src, _, m, _, _ = synth.rigid_pairs(seed=10, outlier_frac=0.0)
+    dst = np.zeros_like(src)
+    dst[m["trainIdx"]] = src[m["queryIdx"]]
+    _compare(ctx.ransac_iterate(src, dst, m, seed=2), orc.ransac_iterate(src, dst, m, seed=2))
+
+
+def test_sort_modes(ctx, orc):
+    src, dst, m, _, _ = synth.rigid_pairs(seed=12)
+    for mode in (0, 1, 2):
+        _compare(ctx.ransac_iterate(src, dst, m, seed=4, sort_mode=mode), orc.ransac_iterate(src, dst, m, seed=4, sort_mode=mode))
+
+
+def test_other_parameters(ctx, orc):
+    src, dst, m, _, _ = synth.rigid_pairs(seed=13, outlier_frac=0.4)
+    kw = dict(iterations=50, min_inlier_th=30, max_mahal=2.0, sample_size=3, seed=17)
+    _compare(ctx.ransac_iterate(src, dst, m, **kw), orc.ransac_iterate(src, dst, m, **kw))
+
+
+def test_kabsch(ctx, orc):
+    rng = np.random.default_rng(3)
+    src, dst, m, R, t = synth.rigid_pairs(seed=14, outlier_frac=0.0)
+    A = src[m["queryIdx"]][20:200]; B = (A.astype(np.float64) @ R.T + t).astype(np.float32)
+    T = ctx.kabsch(A, B)
+    assert np.abs(T - orc.kabsch(A, B)).max() <= 1e-5
+    assert np.abs(T[:3, :3] - R).max() < 1e-4 and np.abs(T[:3, 3] - t).max() < 1e-4
+    assert np.array_equal(ctx.kabsch(np.zeros((0, 3)), np.zeros((0, 3))), np.eye(4, dtype=np.float32))   # N = 0 -> identity
+    Bm = A * np.array([1, 1, -1], np.float32)                                                           # reflection case
+    assert np.abs(ctx.kabsch(A, Bm) - orc.kabsch(A, Bm)).max() <= 1e-5
