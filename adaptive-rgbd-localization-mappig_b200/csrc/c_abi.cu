@@ -184,7 +184,7 @@ static int standalone_knn(orbf_context* c, const uint8_t* q, int nq, const uint8
     if (nt) ORBF_CUDA(c, cudaMemcpyAsync(c->d_tdesc, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
     ms.qdesc = c->d_qdesc; ms.tdesc = c->d_tdesc; ms.qStride = ms.tStride = 0; ms.qCounts = ms.tCounts = nullptr; ms.pairs = nullptr;
     ms.nq = nq; ms.nt = nt; ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
-    if (cross && nt > c->K) return ORBF_ERR_ARG;
+    if (cross && (long long)nt > (long long)c->P * c->K) return ORBF_ERR_ARG;   // rev buffer holds P*K rows
     return orbf_launch_knn2(c, ms, 1, cross);
 }
 
@@ -456,3 +456,4 @@ extern "C" int orbf_selftest_sample_table(uint32_t seed, int32_t M, int32_t iter
     }
     return ORBF_OK;
 }
+

@@ -14,27 +14,32 @@ namespace {
 
 constexpr int FC_THREADS = 128;
 
+// Corner strength without ever negating a min/max result:
+//   bright arcs: min over 9 contiguous (v - ring) = v - max_arc(ring);  dark arcs: min (ring - v) = min_arc(ring) - v
+//   S = max(v - A, B - v),  A = min over the 16 arcs of the arc maximum,  B = max over the 16 arcs of the arc minimum.
+// (nvcc 12.9 for sm_100a miscompiles max(x, -max(...)) chains — the negation is lost when ptxas fuses them into
+//  VIMNMX3; tools/nvcc_minmax_bug.cu reproduces it.  The raw-pixel formulation is also cheaper: no 16 subtractions.)
 __device__ __forceinline__ int ring_strength(const uint8_t* p, int rp)
 {
     // ring offsets in cv::FAST order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-    const int v = p[0];
-    int d[25];
-    d[0] = v - p[3 * rp];      d[1] = v - p[3 * rp + 1];  d[2] = v - p[2 * rp + 2];  d[3] = v - p[rp + 3];
-    d[4] = v - p[3];           d[5] = v - p[-rp + 3];     d[6] = v - p[-2 * rp + 2]; d[7] = v - p[-3 * rp + 1];
-    d[8] = v - p[-3 * rp];     d[9] = v - p[-3 * rp - 1]; d[10] = v - p[-2 * rp - 2]; d[11] = v - p[-rp - 3];
-    d[12] = v - p[-3];         d[13] = v - p[rp - 3];     d[14] = v - p[2 * rp - 2]; d[15] = v - p[3 * rp - 1];
+    int r[25];
+    r[0] = p[3 * rp];      r[1] = p[3 * rp + 1];  r[2] = p[2 * rp + 2];   r[3] = p[rp + 3];
+    r[4] = p[3];           r[5] = p[-rp + 3];     r[6] = p[-2 * rp + 2];  r[7] = p[-3 * rp + 1];
+    r[8] = p[-3 * rp];     r[9] = p[-3 * rp - 1]; r[10] = p[-2 * rp - 2]; r[11] = p[-rp - 3];
+    r[12] = p[-3];         r[13] = p[rp - 3];     r[14] = p[2 * rp - 2];  r[15] = p[3 * rp - 1];
 #pragma unroll
-    for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
-    int best = -255;
+    for (int k = 16; k < 25; ++k) r[k] = r[k - 16];
+    int A = 255, B = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        int lo = min(d[k + 1], d[k + 2]), hi = max(d[k + 1], d[k + 2]);
+        int lo = min(r[k + 1], r[k + 2]), hi = max(r[k + 1], r[k + 2]);
 #pragma unroll
-        for (int j = 3; j <= 8; ++j) { lo = min(lo, d[k + j]); hi = max(hi, d[k + j]); }
-        best = max(best, max(min(lo, d[k]), min(lo, d[k + 9])));
-        best = max(best, -min(max(hi, d[k]), max(hi, d[k + 9])));
+        for (int j = 3; j <= 8; ++j) { lo = min(lo, r[k + j]); hi = max(hi, r[k + j]); }
+        A = min(A, min(max(hi, r[k]), max(hi, r[k + 9])));
+        B = max(B, max(min(lo, r[k]), min(lo, r[k + 9])));
     }
-    return best;
+    const int v = p[0];
+    return max(v - A, B - v);
 }
 
 __global__ void __launch_bounds__(FC_THREADS) fast_cell_kernel(PyrView pv, const CellDesc* __restrict__ cells,

@@ -1,0 +1,94 @@
+"""CPU-only checks of the product side: the shared library builds for sm_100a, loads, exports every symbol
+include/orbfront.h declares, refuses to run without a GPU (no fallback), and the round-based quadtree
+formulation used by csrc/quadtree.cu is equivalent to the reference's list algorithm."""
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(ob):
+    header = (ROOT / "include" / "orbfront.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(orbf_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 35
+    L = ob.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.orbf_abi_version() == 1
+
+
+def test_struct_layouts_match_header(ob):
+    import ctypes as C
+    assert ob.KEYPOINT_DT.itemsize == 28 and ob.DMATCH_DT.itemsize == 16      # cv::KeyPoint / cv::DMatch mirrors
+    assert C.sizeof(ob.Config) == 64 and C.sizeof(ob.RansacConfig) == 40 and C.sizeof(ob.RansacResult) == 104
+    assert ob.HYP_DT.itemsize == 80
+    cfg = ob.default_config()
+    assert (cfg.width, cfg.height, cfg.nfeatures, cfg.nlevels, cfg.ini_th_fast, cfg.min_th_fast) == (640, 480, 1000, 8, 20, 7)
+    assert abs(cfg.scale_factor - 1.2) < 1e-6 and abs(cfg.fx - 517.3) < 1e-4 and cfg.depth_factor == np.float32(1) / np.float32(5000)
+    r = ob.default_ransac_config()
+    assert (r.iterations, r.min_inlier_th, r.sample_size, r.check_depth) == (200, 20, 4, 1) and r.max_mahal == 3.0
+
+
+def test_bad_config_is_rejected_without_touching_cuda(ob):
+    import ctypes as C
+    for kw in (dict(nlevels=0), dict(nlevels=17), dict(width=0), dict(scale_factor=1.0), dict(min_th_fast=30), dict(max_frames=0)):
+        cfg = ob.default_config(**kw); h = C.c_void_p(None)
+        assert ob.lib().orbf_create(C.byref(cfg), C.byref(h)) == 1          # ORBF_ERR_ARG
+    cfg = ob.default_config(width=64, height=48); h = C.c_void_p(None)
+    assert ob.lib().orbf_create(C.byref(cfg), C.byref(h)) == 3              # ORBF_ERR_GEOMETRY
+
+
+def test_no_cpu_fallback(ob):
+    """Without a CUDA device the product path fails loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ob.OrbfError) as e:
+        ob.Context()
+    assert e.value.status == 4                                               # ORBF_ERR_CUDA
+
+
+def test_product_never_references_the_oracle():
+    pkg = ROOT / "adaptive-rgbd-localization-mappig_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")) + [ROOT / "include" / "orbfront.h"]:
+        text = f.read_text()
+        assert "oracle/" not in text.replace("the oracle", "") or f.name in ("ransac.cu",), f
+        assert "import oracle" not in text and "from oracle" not in text and "liborb_oracle" not in text, f
+
+
+def test_sass_is_sm100a(ob):
+    out = subprocess.run(["cuobjdump", "-lelf", str(ob.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_round_based_quadtree_equals_list_algorithm(orc, texture):
+    sys.path.insert(0, str(ROOT / "tools"))
+    from quadtree_model import distribute_rounds
+    import synth
+    nf = orc.tables()["nfeat"]
+    for fi in (0, 7):
+        img = synth.make_frame(texture, fi)
+        for l, L in enumerate(orc.pyramid(img)):
+            c = orc.fast_cells(L)
+            h, w = L.shape
+            tup = [(int(a["x"]), int(a["y"]), int(a["score"])) for a in c]
+            for N in (int(nf[l]), 17, 4 * int(nf[l])):
+                assert list(orc.distribute(c, 16, w - 16, 16, h - 16, N)) == distribute_rounds(tup, w - 32, h - 32, N)
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        W, H = int(rng.integers(60, 1300)), int(rng.integers(60, 700))
+        if round(W / H) < 1:
+            continue
+        pts = {(int(rng.integers(0, W)), int(rng.integers(0, H))) for _ in range(int(rng.integers(1, 1500)))}
+        c = np.zeros(len(pts), orc.CAND_DT)
+        for i, (x, y) in enumerate(sorted(pts, key=lambda p: (p[1] // 30, p[0] // 30, p[1], p[0]))):
+            c[i] = (x, y, int(rng.integers(7, 60)))
+        N = int(rng.integers(1, 400))
+        tup = [(int(a["x"]), int(a["y"]), int(a["score"])) for a in c]
+        assert list(orc.distribute(c, 16, W + 16, 16, H + 16, N)) == distribute_rounds(tup, W, H, N)

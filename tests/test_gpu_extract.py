@@ -90,6 +90,7 @@ def test_sparse_image_fewer_candidates_than_features(ctx, orc):
     for _ in range(60):
         x, y = int(rng.integers(40, 600)), int(rng.integers(40, 440))
         img[y:y + 9, x:x + 9] = 220
+    ctx.extract_batch(img[None])
     _check_frame(ctx, orc, img)
 
 
@@ -97,6 +98,7 @@ def test_random_noise_image_max_density(ctx, orc):
     """Uniform noise: far more candidates than the synthetic texture (stress for cell slots + quadtree)."""
     rng = np.random.default_rng(11)
     img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    ctx.extract_batch(img[None])
     _check_frame(ctx, orc, img)
 
 

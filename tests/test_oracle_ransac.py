@@ -1,0 +1,131 @@
+"""CPU tests of the RANSAC / Kabsch oracle and of the host+device restatements in csrc/replay.h
+(libstdc++ std::sort and glibc rand()), pinned against the real libraries the reference links."""
+import numpy as np
+import pytest
+
+import synth
+
+
+def test_svd3_against_numpy(orc):
+    rng = np.random.default_rng(0)
+    for i in range(1500):
+        A = rng.normal(size=(3, 3)).astype(np.float32)
+        if i % 5 == 0:
+            A[:, 2] = A[:, 0] * 2
+        if i % 7 == 0:
+            A *= 1e-6
+        if i % 11 == 0:
+            A = np.diag(rng.normal(size=3)).astype(np.float32)
+        U, S, V = orc.svd3(A)
+        scale = max(np.abs(A).max(), 1e-30)
+        assert np.abs(U @ np.diag(S) @ V.T - A).max() / scale < 1e-5
+        assert np.abs(U.T @ U - np.eye(3)).max() < 1e-5 and np.abs(V.T @ V - np.eye(3)).max() < 1e-5
+        sn = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+        assert np.abs(S - sn).max() / max(sn.max(), 1e-30) < 1e-5
+        assert S[0] >= S[1] >= S[2] >= 0
+    U, S, V = orc.svd3(np.zeros((3, 3)))
+    assert np.array_equal(U, np.eye(3)) and np.array_equal(V, np.eye(3)) and (S == 0).all()
+
+
+def test_weighted_transform_recovers_rigid_motion(orc):
+    src, dst, m, R, t = synth.rigid_pairs(seed=2, outlier_frac=0.0)
+    P = src[m["queryIdx"]]; P = P[P[:, 2] > 0]; Q = (P.astype(np.float64) @ R.T + t).astype(np.float32)
+    T = orc.weighted_transform(P, Q)
+    assert np.abs(T[:3, :3] - R).max() < 1e-5 and np.abs(T[:3, 3] - t).max() < 2e-5
+    assert np.array_equal(T[3], [0, 0, 0, 1])
+
+
+def test_mahalanobis_against_numpy(orc):
+    rng = np.random.default_rng(1)
+    src, dst, m, R, t = synth.rigid_pairs(seed=3, outlier_frac=0.0)
+    T = np.eye(4, dtype=np.float32); T[:3, :3] = R; T[:3, 3] = t
+    cx = (3 * np.tan(58.0 / 180.0 * np.pi / 640)) ** 2; cy = (3 * np.tan(45.0 / 180.0 * np.pi / 480)) ** 2; cz = 1.3e-3
+    checked = 0
+    for k in range(200):
+        p = src[m["queryIdx"][k]]; q = dst[m["trainIdx"][k]] + rng.normal(0, 0.004, 3).astype(np.float32)
+        if not (p[2] > 0 and q[2] > 0):
+            continue
+        Td = T.astype(np.float64)
+        mu = Td[:3, :3] @ p.astype(np.float64) + Td[:3, 3]
+        dl = mu - q.astype(np.float64)
+        got = orc.mahalanobis2(p, q, T, cz)
+        if dl @ dl > 2 * (max(cx, cz) * 2):
+            assert got == np.finfo(np.float64).max
+            continue
+        S = Td[:3, :3].T @ np.diag([cx * p[2], cy * p[2], cz]) @ Td[:3, :3] + np.diag([cx * q[2], cy * q[2], cz])
+        ref = dl @ np.linalg.solve(S, dl)
+        assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref))
+        checked += 1
+    assert checked > 50
+    assert orc.mahalanobis2(np.array([0, 0, np.nan], np.float32), dst[0], T, cz) == np.finfo(np.float64).max
+
+
+def test_ransac_recovers_motion_and_respects_rules(orc):
+    src, dst, m, R, t = synth.rigid_pairs(seed=4, outlier_frac=0.3)
+    r = orc.ransac_iterate(src, dst, m, seed=42)
+    assert r["ok"] and len(r["inliers"]) >= 0.6 * r["n_good"]
+    assert np.abs(r["T12"][:3, :3] - R).max() < 5e-3 and np.abs(r["T12"][:3, 3] - t).max() < 2e-2
+    assert r["n_good"] == len(m) - 10                        # 5 + 3 holes (z == 0) and 2 NaN targets filtered out
+    d = r["good_sorted"]["distance"]
+    assert (np.diff(d) >= 0).all()
+    assert r["real_iters"] <= 200 and r["valid_iters"] >= 1
+    inl = set(zip(r["inliers"]["queryIdx"].tolist(), r["inliers"]["trainIdx"].tolist()))
+    assert inl <= set(zip(m["queryIdx"].tolist(), m["trainIdx"].tolist()))
+    few = orc.ransac_iterate(src, dst, m[:19])
+    assert not few["ok"] and few["rmse"] == 1e6 and np.array_equal(few["T12"], np.eye(4))
+
+
+def test_ransac_early_exit_skips_iterations(orc):
+    """> 80 % inliers on an accepted hypothesis ends the loop (ransac.cpp:242-247): few real iterations."""
+    src, dst, m, _, _ = synth.rigid_pairs(seed=5, outlier_frac=0.02)
+    r = orc.ransac_iterate(src, dst, m, seed=1)
+    assert r["ok"] and r["real_iters"] < 20
+
+
+def test_kabsch_oracle(orc):
+    src, dst, m, R, t = synth.rigid_pairs(seed=6, outlier_frac=0.0)
+    A = src[m["queryIdx"]]; A = A[A[:, 2] > 0][:280]; B = (A.astype(np.float64) @ R.T + t).astype(np.float32)
+    T = orc.kabsch(A, B)
+    assert np.abs(T[:3, :3] - R).max() < 1e-5 and np.abs(T[:3, 3] - t).max() < 1e-5
+    assert np.array_equal(orc.kabsch(np.zeros((0, 3)), np.zeros((0, 3))), np.eye(4, dtype=np.float32))
+
+
+# ---- csrc/replay.h pinned against libc / libstdc++ (host side of the shared library; no GPU needed) ----
+def test_glibc_rand_replay(ob, orc):
+    for seed in (0, 1, 42, 123456789, 2 ** 31 + 5, 2 ** 32 - 1):
+        assert np.array_equal(ob.selftest_glibc_rand(seed, 3000), orc.libc_rand_sequence(seed, 3000)), seed
+
+
+def test_sample_table_replay(ob, orc):
+    for seed, M in ((42, 640), (7, 21), (9, 4), (3, 3), (5, 1000), (11, 5)):
+        assert np.array_equal(ob.selftest_sample_table(seed, M), orc.sample_table_libc(seed, M)), (seed, M)
+    t = orc.sample_table_libc(1, 50, 500, 4)
+    assert (np.diff(t, axis=1) > 0).all() and t.min() >= 0 and t.max() < 50      # ascending unique ids
+    assert np.median(t) < 25                                                        # min(r1, r2): biased to low ids
+
+
+def _killer(n):
+    """median-of-3 adversary: drives introsort to its depth limit so the heapsort fallback runs."""
+    a = np.zeros(n, np.float32)
+    k = n // 2
+    for i in range(k):
+        a[i] = i + 1 if i % 2 == 0 else k + i + (1 if k % 2 else 0)
+        a[k + i] = 2 * (i + 1)
+    return a
+
+
+def test_std_sort_replay(ob, orc):
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        n = int(rng.integers(0, 1500))
+        d = np.zeros(n, ob.DMATCH_DT); d["queryIdx"] = np.arange(n); d["trainIdx"] = rng.permutation(n) if n else 0
+        mode = t % 5
+        if mode == 0: d["distance"] = rng.integers(0, 64, n)
+        elif mode == 1: d["distance"] = rng.integers(0, 3, n)
+        elif mode == 2: d["distance"] = np.sort(rng.integers(0, 256, n))[::-1]
+        elif mode == 3: d["distance"] = rng.random(n)
+        else: d["distance"] = _killer(n) if n >= 2 else 0
+        assert ob.selftest_introsort(d).tobytes() == orc.std_sort_dmatch(d).tobytes(), (t, n, mode)
+    for n in (4096, 20000):            # deep recursion / heapsort path on adversarial input
+        d = np.zeros(n, ob.DMATCH_DT); d["queryIdx"] = np.arange(n); d["distance"] = _killer(n)
+        assert ob.selftest_introsort(d).tobytes() == orc.std_sort_dmatch(d).tobytes()
