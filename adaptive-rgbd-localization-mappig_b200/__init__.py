@@ -77,6 +77,7 @@ def lib():
         L.orbf_status_string.restype = C.c_char_p
         L.orbf_last_error.restype = C.c_char_p
         L.orbf_last_error.argtypes = [C.c_void_p]
+        L.orbf_profile_stage_name.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -155,6 +156,17 @@ class Context:
         n = C.c_int64(0)
         self._chk(lib().orbf_launch_count(self._h, C.byref(n)), "launch_count")
         return n.value
+
+    def profile_enable(self, on=True):
+        self._chk(lib().orbf_profile_enable(self._h, int(on)), "profile_enable")
+
+    def profile_collect(self):
+        self._chk(lib().orbf_profile_collect(self._h), "profile_collect")
+
+    def profile_read(self):
+        ms = np.zeros(10, np.float64); calls = np.zeros(10, np.int64)
+        self._chk(lib().orbf_profile_read(self._h, _p(ms), _p(calls), 10), "profile_read")
+        return {lib().orbf_profile_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(10)}
 
     def tables(self):
         L = self.L

@@ -19,11 +19,11 @@ struct DistanceLess { ORBF_HD bool operator()(const orbf_dmatch& a, const orbf_d
 
 static int run_extract(orbf_context* c, int slot0, int n)
 {
-    TRY(orbf_launch_pyramid(c, slot0, n));
-    TRY(orbf_launch_fast(c, slot0, n));
-    TRY(orbf_launch_quadtree(c, slot0, n));
-    TRY(orbf_launch_blur(c, slot0, n));
-    TRY(orbf_launch_describe(c, slot0, n));
+    orbf_prof_begin(c, ST_PYRAMID); TRY(orbf_launch_pyramid(c, slot0, n)); orbf_prof_end(c, ST_PYRAMID);
+    orbf_prof_begin(c, ST_FAST); TRY(orbf_launch_fast(c, slot0, n)); orbf_prof_end(c, ST_FAST);
+    orbf_prof_begin(c, ST_QUADTREE); TRY(orbf_launch_quadtree(c, slot0, n)); orbf_prof_end(c, ST_QUADTREE);
+    orbf_prof_begin(c, ST_BLUR); TRY(orbf_launch_blur(c, slot0, n)); orbf_prof_end(c, ST_BLUR);
+    orbf_prof_begin(c, ST_DESCRIBE); TRY(orbf_launch_describe(c, slot0, n)); orbf_prof_end(c, ST_DESCRIBE);
     return ORBF_OK;
 }
 
@@ -254,8 +254,8 @@ extern "C" int orbf_match_pairs(orbf_context* c, const int32_t* pairs, int32_t n
     for (int i = 0; i < 2 * npairs; ++i) if (pairs[i] < 0 || pairs[i] >= c->B) return ORBF_ERR_ARG;
     ORBF_CUDA(c, cudaMemcpyAsync(c->d_pairs, pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     MatchSet ms = slot_match_set(c);
-    TRY(orbf_launch_knn2(c, ms, npairs, cross_check != 0));
-    TRY(orbf_launch_match_select(c, ms, npairs, ratio, cross_check != 0));
+    orbf_prof_begin(c, ST_KNN2); TRY(orbf_launch_knn2(c, ms, npairs, cross_check != 0)); orbf_prof_end(c, ST_KNN2);
+    orbf_prof_begin(c, ST_MATCH_SELECT); TRY(orbf_launch_match_select(c, ms, npairs, ratio, cross_check != 0)); orbf_prof_end(c, ST_MATCH_SELECT);
     c->lastNPairs = npairs; c->pairsFromSlots = true;
     return ORBF_OK;
 }

@@ -203,7 +203,8 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->cfg = *cfg;
     c->B = cfg->max_frames;
     c->P = cfg->max_pairs > 0 ? cfg->max_pairs : cfg->max_frames;
-    c->launches = 0; c->stream = nullptr; c->ownStream = false;
+    c->launches = 0; c->stream = nullptr; c->ownStream = false; c->profiling = false;
+    for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;
     std::vector<ResizeCoef> tab; std::vector<CellDesc> cells;
@@ -298,6 +299,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (c->h_desc) cudaFreeHost(c->h_desc);
     if (c->h_xyz) cudaFreeHost(c->h_xyz);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    for (int i = 0; i < ST_COUNT; ++i) { if (c->evA[i]) cudaEventDestroy(c->evA[i]); if (c->evB[i]) cudaEventDestroy(c->evB[i]); }
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ORBF_OK;
@@ -366,4 +368,48 @@ PyrView orbf_pyr_view(const orbf_context* c, bool blurred)
         } else { q.base = c->d_pyr[l]; q.pitch = c->lg[l].pitch; q.frameStride = (long long)c->lg[l].plane; }
     }
     return v;
+}
+
+// ---- per-stage device timing (CUDA events on the context stream; bench.py's roofline numbers) ----------------
+void orbf_prof_begin(orbf_context* c, int st) { if (c->profiling && c->evA[st]) cudaEventRecord(c->evA[st], c->stream); }
+void orbf_prof_end(orbf_context* c, int st) { if (c->profiling && c->evB[st]) { cudaEventRecord(c->evB[st], c->stream); c->evPending[st] = true; } }
+
+extern "C" int orbf_profile_enable(orbf_context* c, int32_t on)
+{
+    if (!c) return ORBF_ERR_ARG;
+    if (on) for (int i = 0; i < ST_COUNT; ++i) {
+        if (!c->evA[i]) ORBF_CUDA(c, cudaEventCreate(&c->evA[i]));
+        if (!c->evB[i]) ORBF_CUDA(c, cudaEventCreate(&c->evB[i]));
+    }
+    c->profiling = on != 0;
+    for (int i = 0; i < ST_COUNT; ++i) { c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
+    return ORBF_OK;
+}
+
+// Synchronises the stream and folds the last recorded interval of every stage into the totals.
+extern "C" int orbf_profile_collect(orbf_context* c)
+{
+    if (!c) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < ST_COUNT; ++i)
+        if (c->evPending[i]) {
+            float ms = 0.f;
+            ORBF_CUDA(c, cudaEventElapsedTime(&ms, c->evA[i], c->evB[i]));
+            c->stageMs[i] += ms; c->stageCalls[i]++; c->evPending[i] = false;
+        }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_profile_read(const orbf_context* c, double* total_ms, int64_t* calls, int32_t cap)
+{
+    if (!c || cap < ST_COUNT) return ORBF_ERR_ARG;
+    for (int i = 0; i < ST_COUNT; ++i) { if (total_ms) total_ms[i] = c->stageMs[i]; if (calls) calls[i] = c->stageCalls[i]; }
+    return ORBF_OK;
+}
+
+extern "C" const char* orbf_profile_stage_name(int32_t i)
+{
+    static const char* n[ST_COUNT] = { "pyr_resize", "fast_cell", "quadtree", "blur7", "describe", "hamming_knn2", "match_select",
+        "ransac_prepare", "ransac_hyp", "ransac_select" };
+    return (i >= 0 && i < ST_COUNT) ? n[i] : "";
 }

@@ -51,6 +51,9 @@ struct LevelGeom {
     int tabX, tabY;           // offsets into d_resizeTab of the x / y coefficient tables (level l from l-1)
 };
 
+enum OrbfStage { ST_PYRAMID = 0, ST_FAST, ST_QUADTREE, ST_BLUR, ST_DESCRIBE, ST_KNN2, ST_MATCH_SELECT, ST_RANSAC_PREPARE,
+    ST_RANSAC_HYP, ST_RANSAC_SELECT, ST_COUNT };
+
 struct orbf_context {
     orbf_config cfg;
     int L;
@@ -63,6 +66,7 @@ struct orbf_context {
     cudaStream_t stream;
     bool ownStream;
     int64_t launches;
+    bool profiling; cudaEvent_t evA[ST_COUNT], evB[ST_COUNT]; bool evPending[ST_COUNT]; double stageMs[ST_COUNT]; int64_t stageCalls[ST_COUNT];
     std::string lastError;
 
     // inputs
@@ -129,6 +133,9 @@ int orbf_cuda_fail(orbf_context* ctx, cudaError_t e, const char* what, const cha
     } while (0)
 
 __host__ __device__ static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+void orbf_prof_begin(orbf_context* c, int stage);
+void orbf_prof_end(orbf_context* c, int stage);
 
 // ---- stage launchers (each enqueues on ctx->stream for slots [slot0, slot0+n)) ---------------------
 PyrView orbf_pyr_view(const orbf_context* ctx, bool blurred);

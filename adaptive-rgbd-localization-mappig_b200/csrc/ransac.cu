@@ -594,14 +594,20 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int npairs, const o
         cudaError_t e = cudaFuncSetAttribute(ransac_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac smem attr", __FILE__, __LINE__);
     }
+    orbf_prof_begin(c, ST_RANSAC_PREPARE);
     ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
     ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
+    orbf_prof_end(c, ST_RANSAC_PREPARE);
+    orbf_prof_begin(c, ST_RANSAC_HYP);
     dim3 grid((iters + HY_WARPS - 1) / HY_WARPS, npairs);
     ransac_hyp_kernel<<<grid, HY_WARPS * 32, 0, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
+    orbf_prof_end(c, ST_RANSAC_HYP);
+    orbf_prof_begin(c, ST_RANSAC_SELECT);
     ransac_select_kernel<<<npairs, 32, 0, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
+    orbf_prof_end(c, ST_RANSAC_SELECT);
     return ORBF_OK;
 }

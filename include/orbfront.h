@@ -101,6 +101,12 @@ int orbf_synchronize(orbf_context* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 int orbf_launch_count(const orbf_context* ctx, int64_t* n);
 
+/* per-stage device timing with CUDA events on the context stream (off by default) */
+int orbf_profile_enable(orbf_context* ctx, int32_t on);
+int orbf_profile_collect(orbf_context* ctx);                 /* synchronises; call once per batch step */
+int orbf_profile_read(const orbf_context* ctx, double* total_ms, int64_t* calls, int32_t cap /* >= 10 */);
+const char* orbf_profile_stage_name(int32_t stage);
+
 /* ---- extractor tables: GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / ... ---- */
 int orbf_get_tables(const orbf_context* ctx, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
     int32_t* nfeat_per_level, int32_t* level_w, int32_t* level_h);

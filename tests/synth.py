@@ -57,7 +57,7 @@ def make_frame(tex, i, w=640, h=480, seed=0, pad=128, noise_sigma=2.0, low_contr
     val = val + rng.normal(0.0, noise_sigma, size=val.shape)
     if low_contrast_every and i % low_contrast_every == low_contrast_every - 1:
         band = slice(h // 3, h // 3 + h // 4)
-        val[band] = 128.0 + (val[band] - 128.0) * 0.12   # exercises the th=7 fallback cells
+        val[band] = 128.0 + (val[band] - 128.0) * 0.35   # exercises the th=7 fallback cells
     return np.clip(np.rint(val), 0, 255).astype(np.uint8)
 
 
