@@ -256,6 +256,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     TRY(dalloc(c, &c->d_good, P * K));
     TRY(dalloc(c, &c->d_goodCount, P));
     TRY(dalloc(c, &c->d_rres, P));
+    { uint8_t* t = nullptr; TRY(dalloc(c, &t, P * 32)); c->d_rstate = t; }
     TRY(dalloc(c, &c->d_inliers, P * K));
     TRY(dalloc(c, &c->d_depthCov, 1));
     c->d_samples = nullptr; c->d_hyp = nullptr;
@@ -290,7 +291,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
-        c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_inliers, c->d_depthCov,
+        c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,
         c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts,
         c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount };
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -1,7 +1,7 @@
 // csrc/fast.cu — per-cell FAST-9/16 with non-max suppression and the iniTh -> minTh fallback
 // (reference ComputeKeyPointsOctTree, Features/orbextractor.cpp:665-723, calling cv::FAST(roi, th, true)).
 //
-// One CTA per (cell, frame).  The cell's scored interior plus a 3-px ring halo is staged in shared memory;
+// One warp per (cell, frame).  The cell's scored interior plus a 3-px ring halo is staged in shared memory;
 // corner strength S(p) = max over the 16 arcs of 9 contiguous ring pixels of min(centre - ring) for both
 // polarities (cv::FAST response = S - 1, corner iff S > th); NMS is strict '>' against the 8 neighbours
 // *inside the same cell interior* (quirk Q1: each cell is its own cv::FAST call, so neighbours in an
@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int FC_THREADS = 128;
+constexpr int FC_WARPS = 4, FC_THREADS = FC_WARPS * 32;
 
 // Corner strength without ever negating a min/max result:
 //   bright arcs: min over 9 contiguous (v - ring) = v - max_arc(ring);  dark arcs: min (ring - v) = min_arc(ring) - v
@@ -42,109 +42,94 @@ __device__ __forceinline__ int ring_strength(const uint8_t* p, int rp)
     return max(v - A, B - v);
 }
 
+// One WARP per (cell, frame); FC_WARPS cells per CTA.  No block barriers: the three phases (quick test ->
+// dense strength -> NMS + ordered write) only need __syncwarp.  Because a single warp walks the cell in
+// row-major chunks of 32 pixels, one ballot per chunk yields the reference's output order directly.
 __global__ void __launch_bounds__(FC_THREADS) fast_cell_kernel(PyrView pv, const CellDesc* __restrict__ cells,
     int nCellsTotal, uint32_t* __restrict__ cellCand, int* __restrict__ cellCount, int cellSlotTotal, int iniTh, int minTh,
-    int slot0, int regPitch, int maxW, int maxH)
+    int slot0, int regPitch, int regBytes, int scoreBytes, int warpBytes)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* reg = smem;                                        // (maxH+6) x regPitch : level pixels
-    uint8_t* score = reg + (maxH + 6) * regPitch;               // (maxH+2) x (maxW+2)  : response, zero border
-    uint16_t* list = reinterpret_cast<uint16_t*>(score + align_up((maxH + 2) * (maxW + 2), 16));   // quick-test survivors
-    __shared__ int sListCount;
-    __shared__ int sWarpCount[FC_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cellIdx = blockIdx.x * FC_WARPS + warp;
+    if (cellIdx >= nCellsTotal) return;
+    uint8_t* reg = smem + warp * warpBytes;                       // (h+6) x regPitch : level pixels, word-aligned columns
+    uint8_t* score = reg + regBytes;                              // (h+2) x (w+2)    : response, zero border
+    uint16_t* list = reinterpret_cast<uint16_t*>(score + scoreBytes);   // quick-test survivors
 
-    const CellDesc cd = cells[blockIdx.x];
+    const CellDesc cd = cells[cellIdx];
     const int slot = slot0 + blockIdx.y;
     const LevelView lv = pv.lv[cd.level];
-    const uint8_t* img = lv.base + (long long)slot * lv.frameStride;
-    const int w = cd.w, h = cd.h, sp = w + 2;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (int i = tid; i < (h + 6) * (w + 6); i += FC_THREADS) {
-        const int r = i / (w + 6), c = i - r * (w + 6);
-        reg[r * regPitch + c] = __ldg(img + (long long)(cd.y0 - 3 + r) * lv.pitch + cd.x0 - 3 + c);
+    const int w = cd.w, h = cd.h, sp = w + 2, npix = w * h;
+    const uint32_t rcpW = ((1u << 20) + w - 1) / w;               // y = (p * rcpW) >> 20 is exact for p < 2^20 / w
+    // stage (h+6) rows of (w+6) pixels with aligned 32-bit loads; ax = misalignment of the first column
+    const int gx0 = cd.x0 - 3, ax = gx0 & 3, wordsPerRow = (ax + w + 6 + 3) >> 2;
+    const uint8_t* img = lv.base + (long long)slot * lv.frameStride + (long long)(cd.y0 - 3) * lv.pitch + (gx0 - ax);
+    {
+        const uint32_t rcpR = ((1u << 20) + wordsPerRow - 1) / wordsPerRow;
+        const int nWords = (h + 6) * wordsPerRow;
+        for (int i = lane; i < nWords; i += 32) {
+            const int r = (int)(((uint32_t)i * rcpR) >> 20), c = i - r * wordsPerRow;
+            *reinterpret_cast<uint32_t*>(reg + r * regPitch + 4 * c) = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)r * lv.pitch) + c);
+        }
     }
+    const uint8_t* org = reg + 3 * regPitch + 3 + ax;             // interior pixel (0,0)
     uint32_t* out = cellCand + (long long)slot * cellSlotTotal + cd.slotOff;
     int total = 0;
     int th = iniTh;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        for (int i = tid; i < (h + 2) * sp; i += FC_THREADS) score[i] = 0;
-        if (tid == 0) sListCount = 0;
-        __syncthreads();
-        // 1. cheap necessary condition (an arc of 9 contains one pixel of every opposite pair), compacted
-        for (int base = 0; base < w * h; base += FC_THREADS) {
-            const int p = base + tid;
+        for (int i = lane; i < (h + 2) * sp; i += 32) score[i] = 0;
+        __syncwarp();
+        // 1. cheap necessary condition (an arc of 9 contains one pixel of every opposite pair, all of one polarity), compacted
+        int nList = 0;
+        for (int base = 0; base < npix; base += 32) {
+            const int p = base + lane;
             bool pass = false;
-            if (p < w * h) {
-                const int y = p / w, x = p - y * w;
-                const uint8_t* c = reg + (y + 3) * regPitch + x + 3;
+            if (p < npix) {
+                const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * w;
+                const uint8_t* c = org + y * regPitch + x;
                 const int v = c[0], hiT = v + th, loT = v - th;
                 const int p0 = c[3 * regPitch], p8 = c[-3 * regPitch], p4 = c[3], p12 = c[-3];
-                pass = ((p0 > hiT) | (p8 > hiT) | (p0 < loT) | (p8 < loT)) & ((p4 > hiT) | (p12 > hiT) | (p4 < loT) | (p12 < loT));
+                pass = (((p0 > hiT) | (p8 > hiT)) & ((p4 > hiT) | (p12 > hiT))) | (((p0 < loT) | (p8 < loT)) & ((p4 < loT) | (p12 < loT)));
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
-            int wbase = 0;
-            if (lane == 0 && m) wbase = atomicAdd(&sListCount, __popc(m));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (pass) list[wbase + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+            if (pass) list[nList + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+            nList += __popc(m);
         }
-        __syncthreads();
+        __syncwarp();
         // 2. full strength on the dense survivor list
-        const int nList = sListCount;
-        for (int i = tid; i < nList; i += FC_THREADS) {
+        for (int i = lane; i < nList; i += 32) {
             const int p = list[i];
-            const int y = p / w, x = p - y * w;
-            const int s = ring_strength(reg + (y + 3) * regPitch + x + 3, regPitch);
+            const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * w;
+            const int s = ring_strength(org + y * regPitch + x, regPitch);
             if (s > th) score[(y + 1) * sp + x + 1] = (uint8_t)(s - 1);
         }
-        __syncthreads();
-        // 3. NMS + row-major ordered compaction: each warp owns a contiguous quarter of the pixel range
-        const int per = (w * h + FC_THREADS / 32 - 1) / (FC_THREADS / 32);
-        const int pBeg = warp * per, pEnd = min(pBeg + per, w * h);
-        int cnt = 0;
-        for (int base = pBeg; base < pEnd; base += 32) {
+        __syncwarp();
+        // 3. NMS + row-major ordered compaction
+        total = 0;
+        for (int base = 0; base < npix; base += 32) {
             const int p = base + lane;
             bool keep = false;
-            if (p < pEnd) {
-                const int y = p / w, x = p - y * w;
+            int v = 0, x = 0, y = 0;
+            if (p < npix) {
+                y = (int)(((uint32_t)p * rcpW) >> 20); x = p - y * w;
                 const uint8_t* s = score + (y + 1) * sp + x + 1;
-                const int v = s[0];
+                v = s[0];
                 keep = v > 0 && v > s[-1] && v > s[1] && v > s[-sp - 1] && v > s[-sp] && v > s[-sp + 1] && v > s[sp - 1]
                     && v > s[sp] && v > s[sp + 1];
             }
-            cnt += __popc(__ballot_sync(0xffffffffu, keep));
-        }
-        if (lane == 0) sWarpCount[warp] = cnt;
-        __syncthreads();
-        int off = 0;
-        total = 0;
-        for (int k = 0; k < FC_THREADS / 32; ++k) { if (k < warp) off += sWarpCount[k]; total += sWarpCount[k]; }
-        if (total > 0) {
-            for (int base = pBeg; base < pEnd; base += 32) {
-                const int p = base + lane;
-                bool keep = false;
-                int v = 0, x = 0, y = 0;
-                if (p < pEnd) {
-                    y = p / w; x = p - y * w;
-                    const uint8_t* s = score + (y + 1) * sp + x + 1;
-                    v = s[0];
-                    keep = v > 0 && v > s[-1] && v > s[1] && v > s[-sp - 1] && v > s[-sp] && v > s[-sp + 1] && v > s[sp - 1]
-                        && v > s[sp] && v > s[sp + 1];
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const int xr = cd.x0 + x + cd.relx, yr = cd.y0 + y + cd.rely;
-                    out[off + __popc(m & ((1u << lane) - 1))] = (uint32_t)xr | ((uint32_t)yr << 11) | ((uint32_t)v << 22);
-                }
-                off += __popc(m);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int xr = cd.x0 + x + cd.relx, yr = cd.y0 + y + cd.rely;
+                out[total + __popc(m & ((1u << lane) - 1))] = (uint32_t)xr | ((uint32_t)yr << 11) | ((uint32_t)v << 22);
             }
-            break;
+            total += __popc(m);
         }
-        if (minTh >= th) break;
+        if (total > 0 || minTh >= th) break;
         th = minTh;   // empty cell at iniTh: rerun at minTh (orbextractor.cpp:709-712)
-        __syncthreads();
+        __syncwarp();
     }
-    if (tid == 0) cellCount[(long long)slot * nCellsTotal + blockIdx.x] = total;
+    if (lane == 0) cellCount[(long long)slot * nCellsTotal + cellIdx] = total;
 }
 
 }  // namespace
@@ -152,16 +137,19 @@ __global__ void __launch_bounds__(FC_THREADS) fast_cell_kernel(PyrView pv, const
 int orbf_launch_fast(orbf_context* c, int slot0, int n)
 {
     PyrView pv = orbf_pyr_view(c, false);
-    const int regPitch = align_up(c->maxCellW + 6, 4) + 4;
-    const size_t smem = (size_t)(c->maxCellH + 6) * regPitch + align_up((c->maxCellH + 2) * (c->maxCellW + 2), 16)
-        + (size_t)c->maxCellW * c->maxCellH * sizeof(uint16_t) + 16;
+    const int regPitch = align_up(c->maxCellW + 6 + 3, 4);
+    const int regBytes = (c->maxCellH + 6) * regPitch;
+    const int scoreBytes = align_up((c->maxCellH + 2) * (c->maxCellW + 2), 4);
+    const int warpBytes = align_up(regBytes + scoreBytes + c->maxCellW * c->maxCellH * (int)sizeof(uint16_t), 16);
+    const size_t smem = (size_t)warpBytes * FC_WARPS;
+    if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(fast_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "fast smem attr", __FILE__, __LINE__);
     }
-    dim3 grid(c->nCellsTotal, n);
+    dim3 grid((c->nCellsTotal + FC_WARPS - 1) / FC_WARPS, n);
     fast_cell_kernel<<<grid, FC_THREADS, smem, c->stream>>>(pv, c->d_cells, c->nCellsTotal, c->d_cellCand, c->d_cellCount,
-        c->cellSlotTotal, c->cfg.ini_th_fast, c->cfg.min_th_fast, slot0, regPitch, c->maxCellW, c->maxCellH);
+        c->cellSlotTotal, c->cfg.ini_th_fast, c->cfg.min_th_fast, slot0, regPitch, regBytes, scoreBytes, warpBytes);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }

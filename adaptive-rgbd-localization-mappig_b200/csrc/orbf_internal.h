@@ -104,6 +104,7 @@ struct orbf_context {
     int* d_samples;                               // [P][iters][S]
     orbf_hyp_trace* d_hyp; int hypCap;            // [P][iters]
     orbf_ransac_result* d_rres;                   // [P]
+    void* d_rstate;                               // [P] sequential accept-rule state (ransac.cu: RState, 28 B)
     orbf_dmatch* d_inliers;                       // [P][K]
     double* d_depthCov;                           // [1] latched covariance
     float* d_sxyz; float* d_txyz;                 // standalone staging: SoA x|y|z, grown on demand

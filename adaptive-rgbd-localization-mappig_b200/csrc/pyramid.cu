@@ -1,5 +1,5 @@
 // csrc/pyramid.cu — image pyramid (reference ComputePyramid, Features/orbextractor.cpp:833-857) and the
-// 7x7 sigma-2 Gaussian blur (orbextractor.cpp:795-796) as shared-memory-staged stencils.
+// 7x7 sigma-2 Gaussian blur (orbextractor.cpp:795-796) as register-blocked stencils (coalesced 32-bit row reads).
 //
 // Level l is cv::resize(level l-1, INTER_LINEAR) — OpenCV's fixed-point bilinear: horizontal
 // S[sx]*a0 + S[sx+1]*a1 with 11-bit coefficients, vertical (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2.
@@ -11,59 +11,57 @@
 
 namespace {
 
-constexpr int RS_TW = 64, RS_TH = 16, RS_THREADS = 256;
+// ---- bilinear resize, register-blocked: a lane owns 4 adjacent dst columns x RS_ROWS dst rows ------------------------
+// The x coefficients (source offset, a0, a1) of the 4 columns are loaded once and reused down the rows; source pixels
+// are read straight through L1 (byte loads: neighbouring lanes hit the same 128-byte lines), the 4 results of a row
+// leave as one aligned 32-bit store.  No shared memory, no barriers.
+constexpr int RS_WARPS = 4, RS_THREADS = RS_WARPS * 32, RS_ROWS = 4, RS_COLS = 128;
 
 __global__ void __launch_bounds__(RS_THREADS) resize_kernel(LevelView src, uint8_t* __restrict__ dstBase,
     long long dstFrameStride, int dstPitch, int dw, int dh, const ResizeCoef* __restrict__ tx,
-    const ResizeCoef* __restrict__ ty, int slot0, int regPitch, int regRows)
+    const ResizeCoef* __restrict__ ty, int slot0)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = slot0 + blockIdx.z;
     const uint8_t* sImg = src.base + (long long)slot * src.frameStride;
     uint8_t* dImg = dstBase + (long long)slot * dstFrameStride;
-    const int x0 = blockIdx.x * RS_TW, y0 = blockIdx.y * RS_TH;
-    const int x1 = min(x0 + RS_TW, dw) - 1, y1 = min(y0 + RS_TH, dh) - 1;
-    const int sxFirst = tx[x0].ofs, sxLast = min(tx[x1].ofs + 1, src.w - 1);
-    const int syFirst = ty[y0].ofs, syLast = min(ty[y1].ofs + 1, src.h - 1);
-    const int sxA = sxFirst & ~15;                       // 16-byte aligned start column
-    const int vecPerRow = (sxLast - sxA) / 16 + 1;
-    const int rows = syLast - syFirst + 1;
-    // stage the source footprint with 16-byte vector loads (rows are 16-byte aligned: pitch % 16 == 0)
-    for (int i = threadIdx.x; i < rows * vecPerRow; i += RS_THREADS) {
-        const int r = i / vecPerRow, v = i - r * vecPerRow;
-        const int gx = sxA + v * 16;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (gx + 16 <= src.pitch) val = __ldg(reinterpret_cast<const uint4*>(sImg + (long long)(syFirst + r) * src.pitch + gx));
-        else for (int b = 0; b < 16 && gx + b < src.pitch; ++b)
-            reinterpret_cast<uint8_t*>(&val)[b] = sImg[(long long)(syFirst + r) * src.pitch + gx + b];
-        *reinterpret_cast<uint4*>(smem + r * regPitch + v * 16) = val;
-    }
-    __syncthreads();
-    const int ly = threadIdx.x / (RS_TW / 4), lx = (threadIdx.x % (RS_TW / 4)) * 4;
-    const int y = y0 + ly, xb = x0 + lx;
-    if (y >= dh || xb >= dw) return;
-    const ResizeCoef cy = ty[y];
-    const uint8_t* r0 = smem + (cy.ofs - syFirst) * regPitch - sxA;
-    const uint8_t* r1 = smem + (min(cy.ofs + 1, src.h - 1) - syFirst) * regPitch - sxA;
-    const int b0 = cy.a0, b1 = cy.a1;
-    uint32_t packed = 0;
+    const int xb = blockIdx.x * RS_COLS + lane * 4;
+    const int y0 = (blockIdx.y * RS_WARPS + warp) * RS_ROWS;
+    if (xb >= dw || y0 >= dh) return;
+    int sx0[4], sx1[4], a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = xb + k;
-        if (x < dw) {
-            const ResizeCoef cx = tx[x];
-            const int sx = cx.ofs, sx1 = min(sx + 1, src.w - 1);
-            const int h0 = r0[sx] * cx.a0 + r0[sx1] * cx.a1;
-            const int h1 = r1[sx] * cx.a0 + r1[sx1] * cx.a1;
+        const int x = min(xb + k, dw - 1);                      // columns past the edge recompute the last one (never stored as valid)
+        const ResizeCoef cx = tx[x];
+        sx0[k] = cx.ofs; sx1[k] = min(cx.ofs + 1, src.w - 1); a0[k] = cx.a0; a1[k] = cx.a1;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= dh) break;
+        const ResizeCoef cy = ty[y];
+        const uint8_t* r0 = sImg + (long long)cy.ofs * src.pitch;
+        const uint8_t* r1 = sImg + (long long)min(cy.ofs + 1, src.h - 1) * src.pitch;
+        const int b0 = cy.a0, b1 = cy.a1;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h0 = __ldg(r0 + sx0[k]) * a0[k] + __ldg(r0 + sx1[k]) * a1[k];
+            const int h1 = __ldg(r1 + sx0[k]) * a0[k] + __ldg(r1 + sx1[k]) * a1[k];
             const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
             packed |= (uint32_t)(v & 255) << (8 * k);
         }
+        *reinterpret_cast<uint32_t*>(dImg + (long long)y * dstPitch + xb) = packed;   // pitch % 128 == 0: aligned, in-plane
     }
-    *reinterpret_cast<uint32_t*>(dImg + (long long)y * dstPitch + xb) = packed;   // pitch % 128 == 0: aligned, in-plane
 }
 
-constexpr int BL_TW = 64, BL_TH = 32, BL_THREADS = 256;
-constexpr int BL_RW = BL_TW + 6, BL_RH = BL_TH + 6, BL_RP = 72;
+// ---- 7x7 Gaussian, register-blocked, no shared memory ---------------------------------------------------------
+// The fixed-point result (sum_ij k_i k_j p_ij + 32768) >> 16 is exact integer arithmetic, so pass order is free.
+// A lane owns 4 adjacent columns (one aligned 32-bit word per row; the neighbouring words come from __shfl, so a
+// warp reads each row as one coalesced 128-byte segment).  Horizontal pass: two IDP4A per pixel on byte windows
+// cut out with funnel shifts (taps 18,34,48,56 | 48,34,18,0).  Vertical pass: 7-row ring of the 32-bit row sums in
+// registers, walked down a strip of BL_ROWS rows.  BORDER_REFLECT_101 at the true level edge (orbextractor.cpp:796).
+constexpr int BL_WARPS = 4, BL_THREADS = BL_WARPS * 32, BL_ROWS = 16, BL_COLS = 128;
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -72,45 +70,90 @@ __device__ __forceinline__ int reflect101(int p, int n)
     return p;
 }
 
+__device__ __forceinline__ uint32_t load_word_reflect(const uint8_t* __restrict__ row, int xw, int w)
+{
+    if (xw >= 0 && xw + 3 < w) return __ldg(reinterpret_cast<const uint32_t*>(row + xw));
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + reflect101(xw + k, w)) << (8 * k);
+    return v;
+}
+
+__device__ __forceinline__ void hrow7(uint32_t W1, uint32_t edge, int lane, uint32_t out[4])
+{
+    uint32_t W0 = __shfl_up_sync(0xffffffffu, W1, 1), W2 = __shfl_down_sync(0xffffffffu, W1, 1);
+    if (lane == 0) W0 = edge;
+    if (lane == 31) W2 = edge;
+    const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24), kB = 48u | (34u << 8) | (18u << 16);
+    // output i uses bytes [i-3, i+3]: window A = bytes i-3..i, window B = bytes i+1..i+4 (last tap weight 0)
+    out[0] = __dp4a(__funnelshift_r(W0, W1, 8), kA, __dp4a(__funnelshift_r(W1, W2, 8), kB, 0u));
+    out[1] = __dp4a(__funnelshift_r(W0, W1, 16), kA, __dp4a(__funnelshift_r(W1, W2, 16), kB, 0u));
+    out[2] = __dp4a(__funnelshift_r(W0, W1, 24), kA, __dp4a(__funnelshift_r(W1, W2, 24), kB, 0u));
+    out[3] = __dp4a(W1, kA, __dp4a(W2, kB, 0u));
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ sImg, uint8_t* __restrict__ dImg, int pitch, int dstPitch,
+    int w, int h, int x, int y0, int lane)
+{
+    // stage all BL_ROWS + 6 source rows of the strip first: every load of the strip is in flight at once
+    // (lane 0 / lane 31 also fetch the word left / right of the warp's 128-byte segment)
+    uint32_t w1[BL_ROWS + 6], ed[BL_ROWS + 6];
+    const int xe = (lane == 0) ? x - 4 : x + 4;
+    const bool edgeLane = lane == 0 || lane == 31;
+    if (INTERIOR) {     // warp-uniform: all 32 words of every row of the strip lie inside the level, no row reflection
+        const uint8_t* p = sImg + (long long)(y0 - 3) * pitch + x;
+        // edge word: loaded when it is inside the level; at the level's left / right edge (w % 4 == 0 there) it is the
+        // REFLECT_101 image of the lane's own word: b[-1..-3] = b[1..3] and b[w..w+2] = b[w-2..w-4]
+        const bool loadEdge = edgeLane && xe >= 0 && xe + 3 < w;
+        const uint32_t perm = (lane == 0) ? 0x1230u : 0x0012u;
+#pragma unroll
+        for (int r = 0; r < BL_ROWS + 6; ++r) {
+            w1[r] = __ldg(reinterpret_cast<const uint32_t*>(p));
+            ed[r] = loadEdge ? __ldg(reinterpret_cast<const uint32_t*>(p + (xe - x))) : __byte_perm(w1[r], 0u, perm);
+            p += pitch;
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < BL_ROWS + 6; ++r) {
+            const uint8_t* row = sImg + (long long)reflect101(y0 - 3 + r, h) * pitch;
+            w1[r] = load_word_reflect(row, x, w);
+            ed[r] = edgeLane ? load_word_reflect(row, xe, w) : 0u;
+        }
+    }
+    uint32_t ring[7][4];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) hrow7(w1[r], ed[r], lane, ring[r]);
+    uint8_t* q = dImg + (long long)y0 * dstPitch + x;
+#pragma unroll
+    for (int i = 0; i < BL_ROWS; ++i) {
+        hrow7(w1[i + 6], ed[i + 6], lane, ring[(i + 6) % 7]);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = 18u * (ring[i % 7][k] + ring[(i + 6) % 7][k]) + 34u * (ring[(i + 1) % 7][k] + ring[(i + 5) % 7][k])
+                + 48u * (ring[(i + 2) % 7][k] + ring[(i + 4) % 7][k]) + 56u * ring[(i + 3) % 7][k];
+            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        if (INTERIOR || (x < w && y0 + i < h)) *reinterpret_cast<uint32_t*>(q) = packed;
+        q += dstPitch;
+    }
+}
+
 __global__ void __launch_bounds__(BL_THREADS) blur7_kernel(LevelView src, uint8_t* __restrict__ dstBase,
     long long dstFrameStride, int dstPitch, int slot0)
 {
-    __shared__ uint8_t sIn[BL_RH][BL_RP];
-    __shared__ uint16_t sH[BL_RH][BL_TW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = slot0 + blockIdx.z;
     const uint8_t* sImg = src.base + (long long)slot * src.frameStride;
     uint8_t* dImg = dstBase + (long long)slot * dstFrameStride;
     const int w = src.w, h = src.h;
-    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
-    for (int i = threadIdx.x; i < BL_RH * BL_RW; i += BL_THREADS) {
-        const int r = i / BL_RW, c = i - r * BL_RW;
-        const int gy = reflect101(y0 - 3 + r, h), gx = reflect101(x0 - 3 + c, w);
-        sIn[r][c] = __ldg(sImg + (long long)gy * src.pitch + gx);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < BL_RH * BL_TW; i += BL_THREADS) {
-        const int r = i / BL_TW, c = i - r * BL_TW;
-        const uint8_t* p = &sIn[r][c];
-        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        sH[r][c] = (uint16_t)acc;
-    }
-    __syncthreads();
-    // each thread: 4 adjacent columns x 2 rows -> two aligned 32-bit stores
-    const int cx = (threadIdx.x % 16) * 4, ry = (threadIdx.x / 16) * 2;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int y = y0 + ry + rr;
-        if (y >= h) break;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = cx + k;
-            const uint32_t acc = 18u * (sH[ry + rr][c] + sH[ry + rr + 6][c]) + 34u * (sH[ry + rr + 1][c] + sH[ry + rr + 5][c])
-                + 48u * (sH[ry + rr + 2][c] + sH[ry + rr + 4][c]) + 56u * sH[ry + rr + 3][c];
-            packed |= ((acc + 32768u) >> 16) << (8 * k);
-        }
-        if (x0 + cx < dstPitch) *reinterpret_cast<uint32_t*>(dImg + (long long)y * dstPitch + x0 + cx) = packed;
-    }
+    const int xb = blockIdx.x * BL_COLS, x = xb + lane * 4;
+    const int y0 = (blockIdx.y * BL_WARPS + warp) * BL_ROWS;
+    if (y0 >= h) return;
+    const bool interior = (xb + BL_COLS + 4 <= w || xb + BL_COLS == w) && y0 >= 3 && y0 + BL_ROWS + 3 <= h;
+    if (interior) blur_strip<true>(sImg, dImg, src.pitch, dstPitch, w, h, x, y0, lane);
+    else blur_strip<false>(sImg, dImg, src.pitch, dstPitch, w, h, x, y0, lane);
 }
 
 }  // namespace
@@ -120,14 +163,9 @@ int orbf_launch_pyramid(orbf_context* c, int slot0, int n)
     PyrView pv = orbf_pyr_view(c, false);
     for (int l = 1; l < c->L; ++l) {
         const LevelGeom& g = c->lg[l];
-        const LevelGeom& s = c->lg[l - 1];
-        const double sx = (double)s.w / g.w, sy = (double)s.h / g.h;
-        const int regPitch = align_up((int)(RS_TW * sx) + 4 + 16, 16) + 16;
-        const int regRows = (int)(RS_TH * sy) + 4;
-        const size_t smem = (size_t)regPitch * regRows;
-        dim3 grid((g.w + RS_TW - 1) / RS_TW, (g.h + RS_TH - 1) / RS_TH, n);
-        resize_kernel<<<grid, RS_THREADS, smem, c->stream>>>(pv.lv[l - 1], c->d_pyr[l], (long long)g.plane, g.pitch, g.w, g.h,
-            c->d_resizeTab + g.tabX, c->d_resizeTab + g.tabY, slot0, regPitch, regRows);
+        dim3 grid((g.w + RS_COLS - 1) / RS_COLS, (g.h + RS_WARPS * RS_ROWS - 1) / (RS_WARPS * RS_ROWS), n);
+        resize_kernel<<<grid, RS_THREADS, 0, c->stream>>>(pv.lv[l - 1], c->d_pyr[l], (long long)g.plane, g.pitch, g.w, g.h,
+            c->d_resizeTab + g.tabX, c->d_resizeTab + g.tabY, slot0);
         ORBF_LAUNCH_CHECK(c);
     }
     return ORBF_OK;
@@ -138,7 +176,7 @@ int orbf_launch_blur(orbf_context* c, int slot0, int n)
     PyrView pv = orbf_pyr_view(c, false);
     for (int l = 0; l < c->L; ++l) {
         const LevelGeom& g = c->lg[l];
-        dim3 grid((g.w + BL_TW - 1) / BL_TW, (g.h + BL_TH - 1) / BL_TH, n);
+        dim3 grid((g.w + BL_COLS - 1) / BL_COLS, (g.h + BL_WARPS * BL_ROWS - 1) / (BL_WARPS * BL_ROWS), n);
         blur7_kernel<<<grid, BL_THREADS, 0, c->stream>>>(pv.lv[l], c->d_blur[l], (long long)g.plane, g.pitch, slot0);
         ORBF_LAUNCH_CHECK(c);
     }

@@ -26,8 +26,11 @@ namespace {
 
 struct Pt6 { float sx, sy, sz, tx, ty, tz; float pad0, pad1; };   // 32 B: one sorted good correspondence
 
+struct RState { float rmse; int win, nBest, n, realIters, validIters, done; };   // sequential accept-rule state of one pair
+
 struct RansacParams {
     RansacSet rs;
+    RState* state; int hypLo, hypHi;
     orbf_ransac_config cfg;
     orbf_dmatch* good; int* goodCount; Pt6* pts;
     int* samples; const int* userSamples;
@@ -84,6 +87,17 @@ __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams
     }
     const int M = sBase;
     orbf_dmatch* good = P.good + (long long)pair * P.K;
+    // sample table (needs only M): warp 1 draws it while warp 0 replays std::sort
+    int* tab = P.samples + (long long)pair * P.iters * P.S;
+    if (P.userSamples) {
+        for (int i = tid; i < P.iters * P.S; i += PR_THREADS) tab[i] = P.userSamples[i];
+    } else if (tid == 32) {
+        if (M >= P.S) {
+            replay::GlibcRand g;
+            g.seed(P.cfg.seed + (uint32_t)pair);
+            for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
+        } else for (int i = 0; i < P.iters * P.S; ++i) tab[i] = -1;
+    }
     if (P.cfg.sort_mode == 0) {
         if (tid == 0) { replay::IntroSort<orbf_dmatch, DLess> s{ sm, DLess() }; s.sort(M); }
         __syncthreads();
@@ -109,18 +123,15 @@ __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams
         p.pad0 = p.pad1 = 0.f;
         pts[i] = p;
     }
-    // sample table
-    int* tab = P.samples + (long long)pair * P.iters * P.S;
-    if (P.userSamples) {
-        for (int i = tid; i < P.iters * P.S; i += PR_THREADS) tab[i] = P.userSamples[i];
-    } else if (tid == 0) {
-        if (M >= P.S) {
-            replay::GlibcRand g;
-            g.seed(P.cfg.seed + (uint32_t)pair);
-            for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
-        } else for (int i = 0; i < P.iters * P.S; ++i) tab[i] = -1;
+    orbf_hyp_trace* tr = P.hyp + (long long)pair * P.iters;
+    for (int k = tid; k < P.iters; k += PR_THREADS) { tr[k].n_refined = 0; tr[k].rounds = -1; tr[k].refined_error = 1e6; }
+    if (tid == 0) {
+        P.goodCount[pair] = M;
+        RState st;
+        st.rmse = 1e6f; st.win = -1; st.nBest = 0; st.n = 0; st.realIters = 0; st.validIters = 0;
+        st.done = ((unsigned)nm >= P.cfg.min_inlier_th && (unsigned)M >= P.cfg.min_inlier_th && M >= P.S && M <= 2048) ? 0 : 1;
+        P.state[pair] = st;
     }
-    if (tid == 0) P.goodCount[pair] = M;
 }
 
 // depth covariance latch (quirk Q7: static local initialised by the first DepthCovariance() call of the process)
@@ -382,8 +393,9 @@ __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams 
     __shared__ uint32_t sMask[HY_WARPS][MAX_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = blockIdx.y;
-    const int k = blockIdx.x * HY_WARPS + warp;
-    if (k >= P.iters) return;
+    const int k = P.hypLo + blockIdx.x * HY_WARPS + warp;
+    if (k >= P.hypHi) return;
+    if (P.state[pair].done) return;          // the sequential loop already ended before this wave (early exit / skip-ahead)
     const int M = P.goodCount[pair];
     orbf_hyp_trace* tr = P.hyp + (long long)pair * P.iters + k;
     const float I16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
@@ -440,6 +452,39 @@ __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams 
     }
 }
 
+// The reference's accept / skip-ahead / early-exit rule (ransac.cpp:233-249), continued over the hypotheses of the
+// wave that just finished: one thread per pair, hypotheses consumed strictly in sample order.
+__global__ void ransac_replay_kernel(RansacParams P, int npairs)
+{
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= npairs) return;
+    RState st = P.state[pair];
+    if (st.done) return;
+    const int M = P.goodCount[pair];
+    const unsigned minInl = P.cfg.min_inlier_th;
+    const orbf_hyp_trace* hyp = P.hyp + (long long)pair * P.iters;
+    while (st.n < P.iters && st.realIters < P.hypHi) {
+        const orbf_hyp_trace h = hyp[st.realIters];
+        st.realIters++;
+        bool brk = false;
+        if (h.n_refined > 0) {
+            st.validIters++;
+            if (h.refined_error <= (double)st.rmse && h.n_refined >= st.nBest && (unsigned)h.n_refined >= minInl) {
+                st.rmse = (float)h.refined_error;
+                st.win = st.realIters - 1;
+                st.nBest = h.n_refined;
+                if ((double)h.n_refined > (double)M * 0.5) st.n += 10;
+                if ((double)h.n_refined > (double)M * 0.75) st.n += 10;
+                if ((double)h.n_refined > (double)M * 0.8) brk = true;
+            }
+        }
+        if (brk) { st.done = 1; break; }
+        st.n++;
+    }
+    if (st.n >= P.iters) st.done = 1;
+    P.state[pair] = st;
+}
+
 __global__ void __launch_bounds__(32) ransac_select_kernel(RansacParams P)
 {
     __shared__ uint32_t sMask[MAX_WORDS];
@@ -454,30 +499,13 @@ __global__ void __launch_bounds__(32) ransac_select_kernel(RansacParams P)
     orbf_dmatch* inl = P.inliers + (long long)pair * P.K;
     const double cz = *P.depthCov;
     const unsigned minInl = P.cfg.min_inlier_th;
-    float rmse = 1e6f;
-    int win = -1, nBest = 0, realIters = 0, validIters = 0, usedIdentity = 0;
+    const RState st = P.state[pair];
+    float rmse = st.rmse;
+    int win = st.win, realIters = st.realIters, validIters = st.validIters, usedIdentity = 0;
     const bool runnable = (unsigned)nm >= minInl && (unsigned)M >= minInl && M <= MAX_WORDS * 32;
-    if (runnable && lane == 0) {
-        for (int n = 0; n < P.iters && M >= P.S; ++n) {
-            const orbf_hyp_trace h = hyp[realIters];
-            realIters++;
-            if (h.n_refined > 0) {
-                validIters++;
-                if (h.refined_error <= (double)rmse && h.n_refined >= nBest && (unsigned)h.n_refined >= minInl) {
-                    rmse = (float)h.refined_error;
-                    win = realIters - 1;
-                    nBest = h.n_refined;
-                    if ((double)h.n_refined > (double)M * 0.5) n += 10;
-                    if ((double)h.n_refined > (double)M * 0.75) n += 10;
-                    if ((double)h.n_refined > (double)M * 0.8) break;
-                }
-            }
-        }
-    }
     if (lane == 0) sWin = win;
     __syncwarp();
     win = sWin;
-    validIters = __shfl_sync(0xffffffffu, validIters, 0);
     float T[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
     int nInl = 0;
     bool haveMask = false;
@@ -584,6 +612,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int npairs, const o
     P.rs = rs; P.cfg = cfg; P.good = c->d_good; P.goodCount = c->d_goodCount; P.pts = reinterpret_cast<Pt6*>(c->d_pts);
     P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
     P.depthCov = c->d_depthCov; P.K = c->K; P.iters = iters; P.S = S;
+    P.state = reinterpret_cast<RState*>(c->d_rstate); P.hypLo = 0; P.hypHi = iters;
     {   // raster covariances of ErrorFunction2 (ransac.cpp:352-359), host libm like the reference
         const double ax = 58.0 / 180.0 * M_PI, ay = 45.0 / 180.0 * M_PI;
         const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
@@ -601,9 +630,21 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int npairs, const o
     ORBF_LAUNCH_CHECK(c);
     orbf_prof_end(c, ST_RANSAC_PREPARE);
     orbf_prof_begin(c, ST_RANSAC_HYP);
-    dim3 grid((iters + HY_WARPS - 1) / HY_WARPS, npairs);
-    ransac_hyp_kernel<<<grid, HY_WARPS * 32, 0, c->stream>>>(P);
-    ORBF_LAUNCH_CHECK(c);
+    // waves of hypotheses: the reference usually stops after a handful of iterations (> 80 % inliers ends the loop,
+    // accepted hypotheses skip 10-20 iterations ahead), so later waves find their pair already done and exit at once
+    const int waveEnd[4] = { 8, 32, 96, iters };
+    int lo = 0;
+    for (int w = 0; w < 4 && lo < iters; ++w) {
+        const int hi = std::min(waveEnd[w], iters);
+        if (hi <= lo) continue;
+        P.hypLo = lo; P.hypHi = hi;
+        dim3 grid((hi - lo + HY_WARPS - 1) / HY_WARPS, npairs);
+        ransac_hyp_kernel<<<grid, HY_WARPS * 32, 0, c->stream>>>(P);
+        ORBF_LAUNCH_CHECK(c);
+        ransac_replay_kernel<<<(npairs + 127) / 128, 128, 0, c->stream>>>(P, npairs);
+        ORBF_LAUNCH_CHECK(c);
+        lo = hi;
+    }
     orbf_prof_end(c, ST_RANSAC_HYP);
     orbf_prof_begin(c, ST_RANSAC_SELECT);
     ransac_select_kernel<<<npairs, 32, 0, c->stream>>>(P);
