@@ -34,7 +34,7 @@ class Config(C.Structure):
                 ("scale_factor", C.c_float), ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
                 ("max_frames", C.c_int32), ("max_pairs", C.c_int32), ("device", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
-                ("depth_factor", C.c_float)]
+                ("depth_factor", C.c_float), ("pipeline_chunk", C.c_int32), ("pipeline_streams", C.c_int32)]
 
 
 class RansacConfig(C.Structure):
@@ -197,6 +197,27 @@ class Context:
         self._chk(lib().orbf_extract_batch_device(self._h, slot0, n, C.c_void_p(d_gray_ptr), C.c_int64(pitch), C.c_int64(frame_stride),
                                                   C.c_void_p(d_depth_ptr) if d_depth_ptr else None, C.c_int64(depth_pitch),
                                                   C.c_int64(depth_frame_stride)), "extract_batch_device")
+
+    def track_sequence(self, frames, depths, ratio, cross_check=False, ransac=True, slot0=0, **kw):
+        """Tracking::Track over a host sequence: extract all frames, match + RANSAC consecutive pairs (pipelined, async)."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+        n, h, w = frames.shape
+        if depths is not None:
+            assert depths.dtype == np.uint16 and depths.shape == frames.shape and depths.flags.c_contiguous
+        cfg = default_ransac_config(**kw)
+        self._chk(lib().orbf_track_sequence(self._h, slot0, n, _p(frames), C.c_int64(w), C.c_int64(w * h), _p(depths), C.c_int64(w),
+                                            C.c_int64(w * h), C.c_float(ratio), int(cross_check), C.byref(cfg) if ransac else None),
+                  "track_sequence")
+        return n - 1
+
+    def track_sequence_device(self, d_gray_ptr, pitch, frame_stride, n, d_depth_ptr, depth_pitch, depth_frame_stride, ratio,
+                              cross_check=False, ransac=True, slot0=0, **kw):
+        cfg = default_ransac_config(**kw)
+        self._chk(lib().orbf_track_sequence_device(self._h, slot0, n, C.c_void_p(d_gray_ptr), C.c_int64(pitch), C.c_int64(frame_stride),
+                                                   C.c_void_p(d_depth_ptr) if d_depth_ptr else None, C.c_int64(depth_pitch),
+                                                   C.c_int64(depth_frame_stride), C.c_float(ratio), int(cross_check),
+                                                   C.byref(cfg) if ransac else None), "track_sequence_device")
+        return n - 1
 
     def frame_counts(self, n, slot0=0):
         out = np.zeros(n, np.int32)

@@ -27,49 +27,214 @@ static int run_extract(orbf_context* c, int slot0, int n)
     return ORBF_OK;
 }
 
-extern "C" int orbf_extract_batch_device(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
-    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems)
+// ------------------------------------------------------------------------------------------------------
+// chunked multi-stream pipeline
+// ------------------------------------------------------------------------------------------------------
+// A batch call forks the caller-visible stream into the context's worker streams and joins them before it returns
+// (everything stays asynchronous with respect to the host).  Chunk k runs on worker k % nWork: its H2D copies, every
+// extraction stage of its frames and — for the sequence calls — matching + RANSAC of its consecutive frame pairs.
+// The copy of chunk k+1 therefore overlaps the kernels of chunk k, and the latency-bound stages of one chunk
+// (quadtree, sort replay, hypothesis scoring) overlap the throughput-bound stages (FAST, blur, Hamming) of another.
+// With per-stage profiling on, or pipeline_chunk < 0, everything runs as one chunk on the caller-visible stream.
+struct Pipeline {
+    orbf_context* c;
+    cudaStream_t main;
+    bool used[ORBF_MAX_WORKERS];
+    bool active;
+    explicit Pipeline(orbf_context* ctx) : c(ctx), main(ctx->stream), active(false) { for (bool& u : used) u = false; }
+    ~Pipeline() { c->stream = main; }
+    int begin(bool wanted)
+    {
+        active = wanted && c->nWork > 0 && c->chunkFrames > 0 && !c->profiling;
+        if (active) ORBF_CUDA(c, cudaEventRecord(c->evFork, main));
+        return ORBF_OK;
+    }
+    int enter(int k)   // make worker k % nWork the current stream
+    {
+        if (!active) return ORBF_OK;
+        const int s = k % c->nWork;
+        if (!used[s]) { ORBF_CUDA(c, cudaStreamWaitEvent(c->work[s], c->evFork, 0)); used[s] = true; }
+        c->stream = c->work[s];
+        return ORBF_OK;
+    }
+    int end()
+    {
+        c->stream = main;
+        if (!active) return ORBF_OK;
+        for (int s = 0; s < c->nWork; ++s)
+            if (used[s]) {
+                ORBF_CUDA(c, cudaEventRecord(c->evDone[s], c->work[s]));
+                ORBF_CUDA(c, cudaStreamWaitEvent(main, c->evDone[s], 0));
+            }
+        return ORBF_OK;
+    }
+};
+
+struct HostFrames {    // host-side input of a batched call (NULL gray => inputs are already on the device)
+    const uint8_t* gray; int64_t grayStride, grayFrameStride;
+    const uint16_t* depth; int64_t depthStride, depthFrameStride;
+};
+
+static int upload_chunk(orbf_context* c, const HostFrames& hf, int slotA, int first, int n)
 {
-    CTX_ENTER(c);
+    const int w = c->cfg.width, h = c->cfg.height;
+    uint8_t* dIn = c->d_in + (size_t)slotA * c->inPlane;
+    const uint8_t* g = hf.gray + (size_t)first * hf.grayFrameStride;
+    if (hf.grayFrameStride == hf.grayStride * h) {
+        ORBF_CUDA(c, cudaMemcpy2DAsync(dIn, c->inPitch, g, hf.grayStride, w, (size_t)h * n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            ORBF_CUDA(c, cudaMemcpy2DAsync(dIn + (size_t)i * c->inPlane, c->inPitch, g + (size_t)i * hf.grayFrameStride, hf.grayStride, w, h,
+                cudaMemcpyHostToDevice, c->stream));
+    }
+    if (hf.depth) {
+        uint16_t* dDepth = c->d_depthIn + (size_t)slotA * w * h;
+        const uint16_t* d = hf.depth + (size_t)first * hf.depthFrameStride;
+        if (hf.depthStride == w && hf.depthFrameStride == (int64_t)w * h) {
+            ORBF_CUDA(c, cudaMemcpyAsync(dDepth, d, (size_t)n * w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        } else {
+            for (int i = 0; i < n; ++i)
+                ORBF_CUDA(c, cudaMemcpy2DAsync(dDepth + (size_t)i * w * h, (size_t)w * 2, d + (size_t)i * hf.depthFrameStride,
+                    (size_t)hf.depthStride * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    return ORBF_OK;
+}
+
+static MatchSet slot_match_set(orbf_context* c)
+{
+    MatchSet ms;
+    ms.qdesc = c->d_desc; ms.tdesc = c->d_desc; ms.qStride = ms.tStride = (long long)c->K * 32;
+    ms.qCounts = ms.tCounts = c->d_count; ms.pairs = c->d_pairs; ms.pair0 = 0; ms.nq = 0; ms.nt = 0;
+    ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
+    return ms;
+}
+
+static RansacSet slot_ransac_set(orbf_context* c)
+{
+    RansacSet rs;
+    rs.sx = c->d_ptx; rs.sy = c->d_pty; rs.sz = c->d_ptz; rs.tx = c->d_ptx; rs.ty = c->d_pty; rs.tz = c->d_ptz;
+    rs.slotStride = c->K; rs.pairs = c->d_pairs; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount;
+    rs.nsrc = rs.ndst = c->K;
+    return rs;
+}
+
+static int run_match_group(orbf_context* c, int pair0, int npairs, float ratio, bool cross)
+{
+    MatchSet ms = slot_match_set(c);
+    ms.pair0 = pair0;
+    orbf_prof_begin(c, ST_KNN2); TRY(orbf_launch_knn2(c, ms, npairs, cross)); orbf_prof_end(c, ST_KNN2);
+    orbf_prof_begin(c, ST_MATCH_SELECT); TRY(orbf_launch_match_select(c, ms, npairs, ratio, cross)); orbf_prof_end(c, ST_MATCH_SELECT);
+    return ORBF_OK;
+}
+
+// Extraction of frames [slot0, slot0+n) and, when `track` is set, matching + RANSAC of the n-1 consecutive pairs
+// (pair slot p = (slot0+p, slot0+p+1)), chunk by chunk.  The pair that straddles two chunks runs with the later chunk,
+// after an event says the earlier chunk's extraction is complete.
+struct TrackArgs { float ratio; bool cross; const orbf_ransac_config* rcfg; };
+
+static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, const TrackArgs* track)
+{
+    const int npairs = track ? n - 1 : 0;
+    if (track && npairs > 0) {
+        if (npairs > c->P) return ORBF_ERR_ARG;
+        if (track->rcfg) TRY(orbf_ransac_reserve(c, *track->rcfg));
+        std::vector<int> pr(2 * (size_t)npairs);
+        for (int p = 0; p < npairs; ++p) { pr[2 * p] = slot0 + p; pr[2 * p + 1] = slot0 + p + 1; }
+        ORBF_CUDA(c, cudaMemcpyAsync(c->d_pairs, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->lastNPairs = npairs; c->pairsFromSlots = true;
+    }
+    // Measured on B200 (profiles/r1d_pipeline_sweep.txt): the stages are instruction-issue bound, so running chunks on
+    // concurrent streams buys nothing when the inputs are already in HBM (7.36 ms/512 frames on one stream vs 7.4-9.5 ms
+    // chunked) — the pipeline exists to hide the PCIe copies of host inputs (16.0 -> 10.9 ms end to end).
+    Pipeline pl(c);
+    TRY(pl.begin(hf && hf->gray));
+    const int chunk = pl.active ? c->chunkFrames : n;
+    int prevWorker = -1;
+    for (int k = 0, a = 0; a < n; ++k, a += chunk) {
+        const int b = std::min(a + chunk, n);
+        TRY(pl.enter(k));
+        if (hf && hf->gray) TRY(upload_chunk(c, *hf, slot0 + a, a, b - a));
+        TRY(run_extract(c, slot0 + a, b - a));
+        const int wk = pl.active ? k % c->nWork : -1;
+        if (pl.active && track) ORBF_CUDA(c, cudaEventRecord(c->evExtract[wk], c->stream));
+        if (track && npairs > 0) {
+            const int pa = std::max(a - 1, 0), pb = b - 1;          // pairs [pa, pb): the straddling pair a-1 belongs to this chunk
+            if (pb > pa) {
+                if (pl.active && a > 0 && prevWorker != wk) ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evExtract[prevWorker], 0));
+                TRY(run_match_group(c, pa, pb - pa, track->ratio, track->cross));
+                if (track->rcfg) TRY(orbf_launch_ransac(c, slot_ransac_set(c), pa, pb - pa, *track->rcfg, nullptr, pa == 0 ? 0 : 1));
+            }
+        }
+        prevWorker = wk;
+    }
+    return pl.end();
+}
+
+static int set_device_inputs(orbf_context* c, int slot0, int n, const uint8_t* d_gray, int64_t gray_pitch, int64_t gray_frame_stride,
+    const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems)
+{
     if (!d_gray || n < 1 || slot0 < 0 || slot0 + n > c->B || gray_pitch < c->cfg.width) return ORBF_ERR_ARG;
     if (((uintptr_t)d_gray & 15) || (gray_pitch & 15) || (gray_frame_stride & 15)) return ORBF_ERR_ALIGNMENT;
     if (d_depth && depth_pitch_elems < c->cfg.width) return ORBF_ERR_ARG;
     c->cur_gray = d_gray; c->cur_grayPitch = (int)gray_pitch; c->cur_grayFrameStride = gray_frame_stride;
     c->cur_depth = d_depth; c->cur_depthPitch = (int)depth_pitch_elems; c->cur_depthFrameStride = depth_frame_stride_elems;
     c->cur_slot0 = slot0; c->cur_n = n;
-    return run_extract(c, slot0, n);
+    return ORBF_OK;
+}
+
+static int set_host_inputs(orbf_context* c, int slot0, int n, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
+    const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, HostFrames& hf)
+{
+    if (!gray || n < 1 || slot0 < 0 || slot0 + n > c->B || gray_stride < c->cfg.width) return ORBF_ERR_ARG;
+    if (depth && depth_stride_elems < c->cfg.width) return ORBF_ERR_ARG;
+    const int w = c->cfg.width, h = c->cfg.height;
+    hf.gray = gray; hf.grayStride = gray_stride; hf.grayFrameStride = gray_frame_stride;
+    hf.depth = depth; hf.depthStride = depth_stride_elems; hf.depthFrameStride = depth_frame_stride_elems;
+    c->cur_gray = c->d_in + (size_t)slot0 * c->inPlane; c->cur_grayPitch = c->inPitch; c->cur_grayFrameStride = (long long)c->inPlane;
+    c->cur_depth = depth ? c->d_depthIn + (size_t)slot0 * w * h : nullptr; c->cur_depthPitch = w; c->cur_depthFrameStride = (long long)w * h;
+    c->cur_slot0 = slot0; c->cur_n = n;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_extract_batch_device(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems)
+{
+    CTX_ENTER(c);
+    TRY(set_device_inputs(c, slot0, n, d_gray, gray_pitch, gray_frame_stride, d_depth, depth_pitch_elems, depth_frame_stride_elems));
+    return run_batch(c, slot0, n, nullptr, nullptr);
 }
 
 extern "C" int orbf_extract_batch(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
     int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems)
 {
     CTX_ENTER(c);
-    if (!gray || n < 1 || slot0 < 0 || slot0 + n > c->B || gray_stride < c->cfg.width) return ORBF_ERR_ARG;
-    const int w = c->cfg.width, h = c->cfg.height;
-    uint8_t* dIn = c->d_in + (size_t)slot0 * c->inPlane;
-    if (gray_frame_stride == gray_stride * h) {
-        ORBF_CUDA(c, cudaMemcpy2DAsync(dIn, c->inPitch, gray, gray_stride, w, (size_t)h * n, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        for (int i = 0; i < n; ++i)
-            ORBF_CUDA(c, cudaMemcpy2DAsync(dIn + (size_t)i * c->inPlane, c->inPitch, gray + (size_t)i * gray_frame_stride, gray_stride,
-                w, h, cudaMemcpyHostToDevice, c->stream));
-    }
-    uint16_t* dDepth = nullptr;
-    if (depth) {
-        if (depth_stride_elems < w) return ORBF_ERR_ARG;
-        dDepth = c->d_depthIn + (size_t)slot0 * w * h;
-        if (depth_stride_elems == w && depth_frame_stride_elems == (int64_t)w * h) {
-            ORBF_CUDA(c, cudaMemcpyAsync(dDepth, depth, (size_t)n * w * h * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-        } else {
-            for (int i = 0; i < n; ++i)
-                ORBF_CUDA(c, cudaMemcpy2DAsync(dDepth + (size_t)i * w * h, (size_t)w * 2, depth + (size_t)i * depth_frame_stride_elems,
-                    (size_t)depth_stride_elems * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, c->stream));
-        }
-    }
-    c->cur_gray = dIn; c->cur_grayPitch = c->inPitch; c->cur_grayFrameStride = (long long)c->inPlane;
-    c->cur_depth = dDepth; c->cur_depthPitch = w; c->cur_depthFrameStride = (long long)w * h;
-    c->cur_slot0 = slot0; c->cur_n = n;
-    return run_extract(c, slot0, n);
+    HostFrames hf;
+    TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
+    return run_batch(c, slot0, n, &hf, nullptr);
+}
+
+// Tracking::Track's per-frame loop over a sequence (System/tracking.cpp:38-46, 193-208): extract every frame, then
+// Matcher(ratio).KnnMatch(last, cur) and Ransac::Iterate(last, cur) for each consecutive pair, pipelined by chunk.
+extern "C" int orbf_track_sequence(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg)
+{
+    CTX_ENTER(c);
+    HostFrames hf;
+    TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
+    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg };
+    return run_batch(c, slot0, n, &hf, &ta);
+}
+
+extern "C" int orbf_track_sequence_device(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg)
+{
+    CTX_ENTER(c);
+    TRY(set_device_inputs(c, slot0, n, d_gray, gray_pitch, gray_frame_stride, d_depth, depth_pitch_elems, depth_frame_stride_elems));
+    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg };
+    return run_batch(c, slot0, n, nullptr, &ta);
 }
 
 extern "C" int orbf_frame_counts(orbf_context* c, int32_t slot0, int32_t n, int32_t* counts)
@@ -183,6 +348,7 @@ static int standalone_knn(orbf_context* c, const uint8_t* q, int nq, const uint8
     if (nq) ORBF_CUDA(c, cudaMemcpyAsync(c->d_qdesc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
     if (nt) ORBF_CUDA(c, cudaMemcpyAsync(c->d_tdesc, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
     ms.qdesc = c->d_qdesc; ms.tdesc = c->d_tdesc; ms.qStride = ms.tStride = 0; ms.qCounts = ms.tCounts = nullptr; ms.pairs = nullptr;
+    ms.pair0 = 0;
     ms.nq = nq; ms.nt = nt; ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
     if (cross && (long long)nt > (long long)c->P * c->K) return ORBF_ERR_ARG;   // rev buffer holds P*K rows
     return orbf_launch_knn2(c, ms, 1, cross);
@@ -238,14 +404,6 @@ extern "C" int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int3
     return ORBF_OK;
 }
 
-static MatchSet slot_match_set(orbf_context* c)
-{
-    MatchSet ms;
-    ms.qdesc = c->d_desc; ms.tdesc = c->d_desc; ms.qStride = ms.tStride = (long long)c->K * 32;
-    ms.qCounts = ms.tCounts = c->d_count; ms.pairs = c->d_pairs; ms.nq = 0; ms.nt = 0;
-    ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
-    return ms;
-}
 
 extern "C" int orbf_match_pairs(orbf_context* c, const int32_t* pairs, int32_t npairs, float ratio, int32_t cross_check)
 {
@@ -253,11 +411,8 @@ extern "C" int orbf_match_pairs(orbf_context* c, const int32_t* pairs, int32_t n
     if (!pairs || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
     for (int i = 0; i < 2 * npairs; ++i) if (pairs[i] < 0 || pairs[i] >= c->B) return ORBF_ERR_ARG;
     ORBF_CUDA(c, cudaMemcpyAsync(c->d_pairs, pairs, (size_t)npairs * 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    MatchSet ms = slot_match_set(c);
-    orbf_prof_begin(c, ST_KNN2); TRY(orbf_launch_knn2(c, ms, npairs, cross_check != 0)); orbf_prof_end(c, ST_KNN2);
-    orbf_prof_begin(c, ST_MATCH_SELECT); TRY(orbf_launch_match_select(c, ms, npairs, ratio, cross_check != 0)); orbf_prof_end(c, ST_MATCH_SELECT);
     c->lastNPairs = npairs; c->pairsFromSlots = true;
-    return ORBF_OK;
+    return run_match_group(c, 0, npairs, ratio, cross_check != 0);
 }
 
 extern "C" int orbf_download_matches(orbf_context* c, int32_t pair, orbf_dmatch* out, int32_t cap, int32_t* n_out)
@@ -312,11 +467,8 @@ extern "C" int orbf_ransac_pairs(orbf_context* c, int32_t npairs, const orbf_ran
     CTX_ENTER(c);
     if (!cfg || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
     if (!c->pairsFromSlots || npairs > c->lastNPairs) return ORBF_ERR_STATE;
-    RansacSet rs;
-    rs.sx = c->d_ptx; rs.sy = c->d_pty; rs.sz = c->d_ptz; rs.tx = c->d_ptx; rs.ty = c->d_pty; rs.tz = c->d_ptz;
-    rs.slotStride = c->K; rs.pairs = c->d_pairs; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount;
-    rs.nsrc = rs.ndst = c->K;
-    return orbf_launch_ransac(c, rs, npairs, *cfg, nullptr);
+    TRY(orbf_ransac_reserve(c, *cfg));
+    return orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *cfg, nullptr, 0);
 }
 
 extern "C" int orbf_download_ransac(orbf_context* c, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap)
@@ -395,7 +547,7 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
     rs.sx = c->d_sxyz; rs.sy = c->d_sxyz + R; rs.sz = c->d_sxyz + 2 * (size_t)R;
     rs.tx = c->d_txyz; rs.ty = c->d_txyz + R; rs.tz = c->d_txyz + 2 * (size_t)R;
     rs.slotStride = 0; rs.pairs = nullptr; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount; rs.nsrc = nsrc; rs.ndst = ndst;
-    TRY(orbf_launch_ransac(c, rs, 1, cf, dTab));
+    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, 0));
     TRY(orbf_download_ransac(c, 0, out, inliers_out, cap));
     if (hyp_trace) ORBF_CUDA(c, cudaMemcpyAsync(hyp_trace, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
     if (good_sorted_out && out->n_good > 0)

@@ -3,6 +3,7 @@
 // sizes ComputePyramid (:833-838), the FAST cell grid ComputeKeyPointsOctTree (:665-703), the quadtree
 // roots DistributeOctTree (:470-489) and the resize coefficients cv::resize(INTER_LINEAR, 8U) as
 // called at :846 (OpenCV fixed-point bilinear, 11-bit coefficients).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -60,6 +61,7 @@ extern "C" void orbf_default_config(orbf_config* c)
     c->fx = 517.3f; c->fy = 516.5f; c->cx = 318.6f; c->cy = 255.3f;   // Utils/common.h:35-38 (FR1)
     c->mbf = 40.0f;
     c->depth_factor = 1.0f / 5000.0f;
+    c->pipeline_chunk = 0; c->pipeline_streams = 0;
 }
 
 extern "C" void orbf_default_ransac_config(orbf_ransac_config* c)
@@ -204,6 +206,9 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->B = cfg->max_frames;
     c->P = cfg->max_pairs > 0 ? cfg->max_pairs : cfg->max_frames;
     c->launches = 0; c->stream = nullptr; c->ownStream = false; c->profiling = false;
+    c->nWork = 0; c->evFork = nullptr; c->evLatch = nullptr;
+    for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
+    c->chunkFrames = cfg->pipeline_chunk == 0 ? 64 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;
@@ -218,6 +223,14 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
         cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e2 != cudaSuccess) { orbf_cuda_fail(c, e2, "cudaStreamCreate", __FILE__, __LINE__); return fail(ORBF_ERR_CUDA); }
         c->ownStream = true;
+        const int nw = cfg->pipeline_streams <= 0 ? 4 : std::min(cfg->pipeline_streams, ORBF_MAX_WORKERS);
+        auto ev = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+        bool ok = ev(&c->evFork) && ev(&c->evLatch);
+        for (int i = 0; ok && i < nw; ++i) {
+            ok = cudaStreamCreateWithFlags(&c->work[i], cudaStreamNonBlocking) == cudaSuccess && ev(&c->evDone[i]) && ev(&c->evExtract[i]);
+            if (ok) c->nWork = i + 1;
+        }
+        if (!ok) { orbf_cuda_fail(c, cudaGetLastError(), "worker streams", __FILE__, __LINE__); return fail(ORBF_ERR_CUDA); }
     }
     const size_t B = c->B, K = c->K, P = c->P;
     c->inPitch = align_up(cfg->width, 128);
@@ -301,6 +314,13 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (c->h_xyz) cudaFreeHost(c->h_xyz);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (int i = 0; i < ST_COUNT; ++i) { if (c->evA[i]) cudaEventDestroy(c->evA[i]); if (c->evB[i]) cudaEventDestroy(c->evB[i]); }
+    for (int i = 0; i < ORBF_MAX_WORKERS; ++i) {
+        if (c->work[i]) { cudaStreamSynchronize(c->work[i]); cudaStreamDestroy(c->work[i]); }
+        if (c->evDone[i]) cudaEventDestroy(c->evDone[i]);
+        if (c->evExtract[i]) cudaEventDestroy(c->evExtract[i]);
+    }
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evLatch) cudaEventDestroy(c->evLatch);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ORBF_OK;

@@ -101,7 +101,7 @@ extern "C" int orbf_kfdb_match(orbf_context* c, const uint8_t* q, int32_t nq, in
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     MatchSet ms;
     ms.qdesc = c->d_qdesc; ms.tdesc = c->d_kfDesc; ms.qStride = 0; ms.tStride = (long long)c->K * 32;
-    ms.qCounts = c->d_kfQCount; ms.tCounts = c->d_kfCount; ms.pairs = c->d_kfPairs; ms.nq = nq; ms.nt = 0;
+    ms.qCounts = c->d_kfQCount; ms.tCounts = c->d_kfCount; ms.pairs = c->d_kfPairs; ms.pair0 = 0; ms.nq = nq; ms.nt = 0;
     ms.knn = c->d_kfKnn; ms.rev = nullptr; ms.matches = nullptr; ms.matchCount = c->d_kfSurv;
     TRY(orbf_launch_knn2(c, ms, nkf, false));
     TRY(orbf_launch_match_select(c, ms, nkf, ratio, false));

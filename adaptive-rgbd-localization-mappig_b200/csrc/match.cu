@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(KN_THREADS) knn2_kernel(MatchSet ms, int K)
     __shared__ __align__(16) uint32_t sT[KN_CHUNK * 8];
     __shared__ uint32_t sRev[CROSS ? KN_CHUNK : 1];
     __shared__ uint32_t sMerge[KN_WARPS][KN_R][2][32];
-    const int pair = blockIdx.y;
+    const int pair = ms.pair0 + blockIdx.y;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
     const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq, nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(MS_THREADS) match_select_kernel(MatchSet ms, i
     int* __restrict__ matchCount = ms.matchCount;
     __shared__ int sWarp[MS_THREADS / 32];
     __shared__ int sBase;
-    const int pair = blockIdx.x;
+    const int pair = ms.pair0 + blockIdx.x;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
     const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq, nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
@@ -159,7 +159,7 @@ int orbf_launch_knn2(orbf_context* c, const MatchSet& ms, int npairs, bool cross
     if (maxNq <= 0 || npairs <= 0) return ORBF_OK;
     dim3 grid((maxNq + KN_QT - 1) / KN_QT, npairs);
     if (cross) {
-        ORBF_CUDA(c, cudaMemsetAsync(ms.rev, 0xFF, (size_t)npairs * c->K * sizeof(uint32_t), c->stream));
+        ORBF_CUDA(c, cudaMemsetAsync(ms.rev + (size_t)ms.pair0 * c->K, 0xFF, (size_t)npairs * c->K * sizeof(uint32_t), c->stream));
         knn2_kernel<true><<<grid, KN_THREADS, 0, c->stream>>>(ms, c->K);
     } else knn2_kernel<false><<<grid, KN_THREADS, 0, c->stream>>>(ms, c->K);
     ORBF_LAUNCH_CHECK(c);

@@ -20,6 +20,7 @@
 #define ORBF_MINB 16          // EDGE_THRESHOLD - 3 (orbextractor.cpp:672)
 #define ORBF_HALF_PATCH 15
 #define ORBF_MAX_SAMPLE 8
+#define ORBF_MAX_WORKERS 4    // internal worker streams of the chunked pipeline (c_abi.cu)
 
 struct LevelView {
     const uint8_t* base;      // address of slot 0's plane
@@ -63,8 +64,13 @@ struct orbf_context {
     int B, P;                 // frame slots, pair slots
     int K;                    // keypoint capacity per frame (multiple of 32)
     int nCellsTotal, cellSlotTotal, candTotal, kpStageTotal, maxCellW, maxCellH;
-    cudaStream_t stream;
+    cudaStream_t stream;      // stream every launcher enqueues on: the caller-visible stream, or (inside a pipelined
+                              // batch call) the worker stream of the chunk being enqueued
     bool ownStream;
+    // chunked multi-stream pipeline: a batch call forks the caller-visible stream into nWork worker streams, enqueues
+    // chunk k (H2D copies + all stages of its frames and frame pairs) on worker k % nWork, and joins them again
+    cudaStream_t work[ORBF_MAX_WORKERS]; int nWork, chunkFrames;
+    cudaEvent_t evFork, evDone[ORBF_MAX_WORKERS], evExtract[ORBF_MAX_WORKERS], evLatch;
     int64_t launches;
     bool profiling; cudaEvent_t evA[ST_COUNT], evB[ST_COUNT]; bool evPending[ST_COUNT]; double stageMs[ST_COUNT]; int64_t stageCalls[ST_COUNT];
     std::string lastError;
@@ -152,6 +158,7 @@ struct MatchSet {
     long long qStride, tStride;                    // bytes per slot (K*32), 0 when every pair uses slot 0
     const int* qCounts; const int* tCounts;        // per-slot row counts (NULL => nq / nt)
     const int* pairs;                              // [npairs][2] (query slot, train slot); NULL => slots (0, 0)
+    int pair0;                                     // first pair slot of this launch (pair = pair0 + blockIdx)
     int nq, nt;
     uint32_t* knn;                                 // out [npairs][K][2] packed (dist<<16 | trainIdx): best, second
     uint32_t* rev;                                 // out [npairs][K]    packed (dist<<16 | queryIdx): best query per train row
@@ -168,5 +175,8 @@ struct RansacSet {
     int nsrc, ndst;
 };
 int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int n, float* dT);
-int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples);
+// pairs [pair0, pair0 + npairs).  latchMode 0: this group owns pair 0 — latch the depth covariance (quirk Q7) after
+// its prepare kernel and record ctx->evLatch; 1: wait for ctx->evLatch before scoring hypotheses.
+int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);
+int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
+    const int* d_userSamples, int latchMode);

@@ -30,7 +30,7 @@ struct RState { float rmse; int win, nBest, n, realIters, validIters, done; };  
 
 struct RansacParams {
     RansacSet rs;
-    RState* state; int hypLo, hypHi;
+    RState* state; int hypLo, hypHi, pair0;
     orbf_ransac_config cfg;
     orbf_dmatch* good; int* goodCount; Pt6* pts;
     int* samples; const int* userSamples;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams
     orbf_dmatch* sm = reinterpret_cast<orbf_dmatch*>(smem);     // K entries
     __shared__ int sWarp[PR_THREADS / 32];
     __shared__ int sBase;
-    const int pair = blockIdx.x;
+    const int pair = P.pair0 + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int qs = 0, ts = 0;
     if (P.rs.pairs) { qs = P.rs.pairs[2 * pair]; ts = P.rs.pairs[2 * pair + 1]; }
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams 
 {
     __shared__ uint32_t sMask[HY_WARPS][MAX_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair = blockIdx.y;
+    const int pair = P.pair0 + blockIdx.y;
     const int k = P.hypLo + blockIdx.x * HY_WARPS + warp;
     if (k >= P.hypHi) return;
     if (P.state[pair].done) return;          // the sequential loop already ended before this wave (early exit / skip-ahead)
@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams 
 // wave that just finished: one thread per pair, hypotheses consumed strictly in sample order.
 __global__ void ransac_replay_kernel(RansacParams P, int npairs)
 {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pair >= npairs) return;
+    if (blockIdx.x * blockDim.x + threadIdx.x >= npairs) return;
+    const int pair = P.pair0 + blockIdx.x * blockDim.x + threadIdx.x;
     RState st = P.state[pair];
     if (st.done) return;
     const int M = P.goodCount[pair];
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(32) ransac_select_kernel(RansacParams P)
 {
     __shared__ uint32_t sMask[MAX_WORDS];
     __shared__ int sWin, sIdentity;
-    const int pair = blockIdx.x, lane = threadIdx.x;
+    const int pair = P.pair0 + blockIdx.x, lane = threadIdx.x;
     const int M = P.goodCount[pair];
     const int nm = P.rs.matchCount[pair];
     orbf_ransac_result* res = P.res + pair;
@@ -586,13 +586,13 @@ int orbf_launch_kabsch(orbf_context* c, const float* dA, const float* dB, int n,
     return ORBF_OK;
 }
 
-int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int npairs, const orbf_ransac_config& cfg, const int* d_userSamples)
+int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
 {
-    if (npairs <= 0) return ORBF_OK;
     if (cfg.iterations < 1 || cfg.sample_size < 1 || cfg.sample_size > ORBF_MAX_SAMPLE || cfg.iterations > 100000) return ORBF_ERR_ARG;
-    const int iters = cfg.iterations, S = (int)cfg.sample_size;
-    const size_t needHyp = (size_t)c->P * iters;
+    if (c->K > MAX_WORDS * 32) return ORBF_ERR_ARG;
+    const size_t needHyp = (size_t)c->P * cfg.iterations;
     if ((size_t)c->hypCap < needHyp || !c->d_hyp) {
+        ORBF_CUDA(c, cudaDeviceSynchronize());
         if (c->d_hyp) cudaFree(c->d_hyp);
         if (c->d_samples) cudaFree(c->d_samples);
         c->d_hyp = nullptr; c->d_samples = nullptr;
@@ -600,34 +600,50 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int npairs, const o
         ORBF_CUDA(c, cudaMalloc((void**)&c->d_samples, needHyp * ORBF_MAX_SAMPLE * sizeof(int)));
         c->hypCap = (int)needHyp;
     }
-    if (c->K > MAX_WORDS * 32) return ORBF_ERR_ARG;
     const size_t needPts = (size_t)c->P * c->K;
     if (c->ptsCap < needPts) {
+        ORBF_CUDA(c, cudaDeviceSynchronize());
         if (c->d_pts) cudaFree(c->d_pts);
         c->d_pts = nullptr; c->ptsCap = 0;
         ORBF_CUDA(c, cudaMalloc(&c->d_pts, needPts * sizeof(Pt6)));
         c->ptsCap = needPts;
-    }
-    RansacParams P;
-    P.rs = rs; P.cfg = cfg; P.good = c->d_good; P.goodCount = c->d_goodCount; P.pts = reinterpret_cast<Pt6*>(c->d_pts);
-    P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
-    P.depthCov = c->d_depthCov; P.K = c->K; P.iters = iters; P.S = S;
-    P.state = reinterpret_cast<RState*>(c->d_rstate); P.hypLo = 0; P.hypHi = iters;
-    {   // raster covariances of ErrorFunction2 (ransac.cpp:352-359), host libm like the reference
-        const double ax = 58.0 / 180.0 * M_PI, ay = 45.0 / 180.0 * M_PI;
-        const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
-        P.covX = sx * sx; P.covY = sy * sy;
     }
     const size_t smem = (size_t)c->K * sizeof(orbf_dmatch);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ransac_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac smem attr", __FILE__, __LINE__);
     }
+    return ORBF_OK;
+}
+
+int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
+    const int* d_userSamples, int latchMode)
+{
+    if (npairs <= 0) return ORBF_OK;
+    {
+        const int r = orbf_ransac_reserve(c, cfg);
+        if (r != ORBF_OK) return r;
+    }
+    const int iters = cfg.iterations, S = (int)cfg.sample_size;
+    RansacParams P;
+    P.rs = rs; P.cfg = cfg; P.good = c->d_good; P.goodCount = c->d_goodCount; P.pts = reinterpret_cast<Pt6*>(c->d_pts);
+    P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
+    P.depthCov = c->d_depthCov; P.K = c->K; P.iters = iters; P.S = S;
+    P.state = reinterpret_cast<RState*>(c->d_rstate); P.hypLo = 0; P.hypHi = iters; P.pair0 = pair0;
+    {   // raster covariances of ErrorFunction2 (ransac.cpp:352-359), host libm like the reference
+        const double ax = 58.0 / 180.0 * M_PI, ay = 45.0 / 180.0 * M_PI;
+        const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
+        P.covX = sx * sx; P.covY = sy * sy;
+    }
+    const size_t smem = (size_t)c->K * sizeof(orbf_dmatch);
     orbf_prof_begin(c, ST_RANSAC_PREPARE);
     ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
-    ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P);
-    ORBF_LAUNCH_CHECK(c);
+    if (latchMode == 0) {
+        ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P);
+        ORBF_LAUNCH_CHECK(c);
+        ORBF_CUDA(c, cudaEventRecord(c->evLatch, c->stream));
+    } else ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evLatch, 0));
     orbf_prof_end(c, ST_RANSAC_PREPARE);
     orbf_prof_begin(c, ST_RANSAC_HYP);
     // waves of hypotheses: the reference usually stops after a handful of iterations (> 80 % inliers ends the loop,

@@ -170,7 +170,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=192, help="frames of the cpu_baseline sample (rank 0, N=1)")
+    ap.add_argument("--cpu-sample", type=int, default=192, help="frames of the cpu_baseline sample (rank 0, N=1; 0 = skip)")
+    ap.add_argument("--chunk", type=int, default=0, help="pipeline chunk in frames (0 = library default, <0 = no chunking)")
+    ap.add_argument("--streams", type=int, default=0, help="pipeline worker streams (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,7 +189,7 @@ def main():
     ob = load_pkg()
     F = args.frames
     frames, depths = make_inputs(F, seed=rank)            # each rank its own shard of the sequence (weak scaling)
-    ctx = ob.Context(max_frames=F, max_pairs=F, device=local)
+    ctx = ob.Context(max_frames=F, max_pairs=F, device=local, pipeline_chunk=args.chunk, pipeline_streams=args.streams)
     stream = torch.cuda.Stream(device=local)
     ctx.set_stream(stream.cuda_stream)
     pairs = np.array([[i, i + 1] for i in range(F - 1)], np.int32)
@@ -199,14 +201,10 @@ def main():
     torch.cuda.synchronize()
 
     def step_device():
-        ctx.extract_batch_device(d_gray.data_ptr(), W, W * H, F, d_depth.data_ptr(), W, W * H)
-        ctx.match_pairs(pairs, RATIO, CROSS)
-        ctx.ransac_pairs(F - 1, seed=42)
+        ctx.track_sequence_device(d_gray.data_ptr(), W, W * H, F, d_depth.data_ptr(), W, W * H, RATIO, CROSS, seed=42)
 
     def step_e2e():
-        ctx.extract_batch(hg, hd)
-        ctx.match_pairs(pairs, RATIO, CROSS)
-        ctx.ransac_pairs(F - 1, seed=42)
+        ctx.track_sequence(hg, hd, RATIO, CROSS, seed=42)   # pinned host frames -> chunked H2D overlapped with the kernels
         summ = ctx.download_ransac_summary(F - 1)           # poses + inlier counts
         mc = ctx.match_counts(F - 1); fc = ctx.frame_counts(F)
         return summ, mc, fc
@@ -243,7 +241,7 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     barrier()
-    h2d = int(frames.nbytes + depths.nbytes + pairs.nbytes)
+    h2d = int(frames.nbytes + depths.nbytes)
     d2h = int(summ.nbytes + mc.nbytes + fc.nbytes)
     # ---- per-stage times (CUDA events inside the library, on the launching stream) ----
     ctx.profile_enable(True)
@@ -288,7 +286,7 @@ def main():
                     "hamming_knn2": {"pairs_per_s": float(sum(int(a) * int(b) for a, b in zip(fc[:-1], fc[1:]))) / (stage_ms["hamming_knn2"] * 1e-3),
                                      "popc32_per_pair": 8, "nominal_popc_peak_per_s": 16 * 148 * 1.965e9}}
         cpu = None
-        if world == 1:
+        if world == 1 and args.cpu_sample > 0:
             from oracle import oracle as orc
             orc.build()
             ns = min(args.cpu_sample, F)
@@ -302,7 +300,8 @@ def main():
                "config": {"workload": "ORB extract (1000 kp, 8 levels, 1.2) + kNN-2 Hamming match (ratio 0.8, cross-check) + RANSAC(200,20,3.0,4), "
                                       "640x480 RGB-D, consecutive pairs", "frames_per_step_per_gpu": F, "pairs_per_step_per_gpu": F - 1,
                           "l2": f"no flush needed: per-step input {(frames.nbytes + depths.nbytes) / 1e6:.0f} MB > 126 MB L2",
-                          "sharding": "frames partitioned per rank, no data-path collective"},
+                          "sharding": "frames partitioned per rank, no data-path collective",
+                          "pipeline": f"e2e arm: orbf_track_sequence, chunks of {ctx.cfg.pipeline_chunk or 64} frames over {ctx.cfg.pipeline_streams or 4} worker streams; device arm: one stream"},
                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

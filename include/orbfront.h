@@ -15,6 +15,8 @@
  *   orbf_knn2 / orbf_knn_match        cv::BFMatcher::knnMatch(k=2) + ratio test in Matcher::KnnMatch   Features/matcher.cpp:55-66 (23-35)
  *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
  *   orbf_match_pairs                  Tracking::TrackFrame's matcher call, batched  System/tracking.cpp:197-199
+ *   orbf_track_sequence*              Tracking::Track's per-frame loop (extract, match with the last frame, RANSAC)
+ *                                     over a whole sequence, pipelined            System/tracking.cpp:38-46,193-208
  *   orbf_ransac_iterate               Ransac::Iterate(Frame*,Frame*,m12)          Odometry/ransac.cpp:155-267
  *   orbf_ransac_pairs                 Odometry::Compute -> Ransac::Iterate, batched   Odometry/odometry.cpp:48
  *   orbf_kabsch                       Kabsch::Compute                             Odometry/kabsch.cpp:14-57
@@ -29,7 +31,7 @@ extern "C" {
 #endif
 
 #define ORBF_MAX_LEVELS 16
-#define ORBF_ABI_VERSION 1
+#define ORBF_ABI_VERSION 2
 
 typedef enum {
     ORBF_OK = 0,
@@ -58,6 +60,8 @@ typedef struct {
     int32_t device;                    /* CUDA device ordinal                                    */
     float fx, fy, cx, cy, mbf;         /* Calibration:: (Utils/common.h:35-38,71)               */
     float depth_factor;                /* Calibration::depthFactor = 1/5000 (Utils/common.h:67) */
+    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default 64, < 0 = no chunking) */
+    int32_t pipeline_streams;          /* internal worker streams, 1..4 (0 = default 4)           */
 } orbf_config;
 
 typedef struct {
@@ -124,6 +128,17 @@ int orbf_extract_batch(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_
 /* Batched, device input (already in HBM): pointers must be 16-byte aligned, gray pitch a multiple of 16. */
 int orbf_extract_batch_device(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
     int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems);
+/* A whole sequence in one call: extraction of n frames plus, for each consecutive pair p = (slot0+p, slot0+p+1),
+ * Matcher(ratio).KnnMatch and (ransac_cfg != NULL) Ransac::Iterate; results land in pair slots 0..n-2.  The call is
+ * asynchronous and internally pipelined: frames are processed in chunks of orbf_config.pipeline_chunk on
+ * orbf_config.pipeline_streams worker streams, so the H2D copy of one chunk overlaps the kernels of another (host
+ * inputs only: with inputs already in HBM the stages run back to back on the context stream).                     */
+int orbf_track_sequence(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg);
+int orbf_track_sequence_device(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg);
 /* Results of one slot -> host (synchronises the stream). xyz = mvKeys3Dc (N x 3 floats), may be NULL. */
 int orbf_download_frame(orbf_context* ctx, int32_t slot, orbf_keypoint* kps, uint8_t* desc, float* xyz,
     int32_t cap, int32_t* n_out);

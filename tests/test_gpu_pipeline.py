@@ -48,6 +48,39 @@ def test_sequence_extract_match_ransac(ob, orc, texture):
         ctx.close()
 
 
+@pytest.mark.parametrize("chunk,streams", [(2, 3), (3, 2), (4, 1), (-1, 3)])
+def test_track_sequence_pipelined_equals_staged(ob, orc, texture, chunk, streams):
+    """orbf_track_sequence (chunked over worker streams, pairs straddling chunks, depth covariance latched by pair 0)
+    gives the same bytes as extract_batch + match_pairs + ransac_pairs on one stream, and as the oracle."""
+    n = 9
+    frames = np.stack([synth.make_frame(texture, 40 + i) for i in range(n)])
+    depths = np.stack([synth.make_depth(40 + i) for i in range(n)])
+    ref = ob.Context(max_frames=n, pipeline_chunk=-1)
+    ctx = ob.Context(max_frames=n, pipeline_chunk=chunk, pipeline_streams=streams)
+    try:
+        ref.extract_batch(frames, depths)
+        pairs = np.array([[i, i + 1] for i in range(n - 1)], np.int32)
+        ref.match_pairs(pairs, 0.8, cross_check=True)
+        ref.ransac_pairs(n - 1, seed=7)
+        for rep in range(2):                      # second pass: worker streams / events are reused, covariance stays latched
+            assert ctx.track_sequence(frames, depths, 0.8, cross_check=True, seed=7) == n - 1
+            for s in range(n):
+                a, b = ctx.download_frame(s), ref.download_frame(s)
+                assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b)), f"frame {s}"
+            for p in range(n - 1):
+                assert ctx.download_matches(p).tobytes() == ref.download_matches(p).tobytes(), f"pair {p}"
+                g, r = ctx.download_ransac(p), ref.download_ransac(p)
+                assert g["inliers"].tobytes() == r["inliers"].tobytes() and g["T12"].tobytes() == r["T12"].tobytes()
+                assert g["rmse"] == r["rmse"] and g["depth_cov"] == r["depth_cov"] and g["real_iters"] == r["real_iters"]
+        k0, d0 = orc.extract(frames[0]); k1, d1 = orc.extract(frames[1])
+        m = orc.knn_match(d0, d1, 0.8, True)
+        assert ctx.download_matches(0).tobytes() == m.tobytes()
+        r = orc.ransac_iterate(orc.unproject(k0, depths[0])[0], orc.unproject(k1, depths[1])[0], m, seed=7)
+        assert ctx.download_ransac(0)["inliers"].tobytes() == r["inliers"].tobytes()
+    finally:
+        ctx.close(); ref.close()
+
+
 def test_device_input_path(ob, orc, texture):
     """Frames already resident in HBM (torch tensors): extract_batch_device reads level 0 in place."""
     import torch
