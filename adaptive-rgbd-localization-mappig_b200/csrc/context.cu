@@ -22,6 +22,38 @@ int orbf_cuda_fail(orbf_context* ctx, cudaError_t e, const char* what, const cha
 static inline int cv_round_f(float v) { return (int)nearbyintf(v); }
 static inline int cv_round_d(double v) { return (int)nearbyint(v); }
 
+// ---- TMA descriptor encoding (driver entry point fetched through the runtime: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int orbf_tma_encode_u8(orbf_context* ctx, CUtensorMap* out, const void* base, int w, int h, int frames, long long pitch,
+    long long frameStride, int boxW, int boxH)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return orbf_cuda_fail(ctx, e != cudaSuccess ? e : cudaErrorNotSupported, "cuTensorMapEncodeTiled lookup", __FILE__, __LINE__);
+        fn = (EncodeTiledFn)p;
+    }
+    if (((uintptr_t)base & 15) || (pitch & 15) || (frameStride & 15) || (boxW & 15) || boxW > 256 || boxH > 256) return ORBF_ERR_ALIGNMENT;
+    const cuuint64_t gdim[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames };
+    const cuuint64_t gstride[2] = { (cuuint64_t)pitch, (cuuint64_t)frameStride };
+    const cuuint32_t box[3] = { (cuuint32_t)boxW, (cuuint32_t)boxH, 1u };
+    const cuuint32_t estr[3] = { 1u, 1u, 1u };
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        if (ctx) ctx->lastError = buf;
+        return ORBF_ERR_CUDA;
+    }
+    return ORBF_OK;
+}
+
 static void build_resize_tab(int src, int dst, ResizeCoef* out)
 {
     const double inv_scale = (double)dst / src;
@@ -88,7 +120,7 @@ extern "C" const char* orbf_status_string(int s)
 
 extern "C" const char* orbf_last_error(const orbf_context* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
 
-static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::vector<CellDesc>& cells)
+static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::vector<CellDesc>& cells, std::vector<StripDesc>& strips)
 {
     const orbf_config& g = c->cfg;
     const int L = g.nlevels;
@@ -149,8 +181,9 @@ static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::ve
         q.wCell = (int)ceilf(width / q.cellsX); q.hCell = (int)ceilf(height / q.cellsY);
         q.cell0 = (int)cells.size();
         q.candOff = candOff;
-        int cap = 0;
+        int cap = 0, levelMaxW = 0, levelMaxH = 0;
         for (int i = 0; i < q.cellsY; ++i) {
+            int inRow = 0;
             const float iniY = (float)(minB + i * q.hCell);
             float maxY = iniY + q.hCell + 6;
             if (iniY >= maxBY - 3) continue;
@@ -170,10 +203,23 @@ static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::ve
                 d.cap = ((cw + 1) / 2) * ((ch + 1) / 2);   // strict 8-neighbour maxima: <= 1 per 2x2 block
                 cellSlot += d.cap; cap += d.cap;
                 c->maxCellW = std::max(c->maxCellW, cw); c->maxCellH = std::max(c->maxCellH, ch);
+                // strips of up to ORBF_STRIP_CELLS adjacent cells (their scored interiors tile the row without gaps)
+                if (inRow % ORBF_STRIP_CELLS == 0) {
+                    StripDesc sd;
+                    sd.level = (short)l; sd.nCells = 0; sd.x0 = d.x0; sd.y0 = d.y0; sd.w = 0; sd.h = d.h; sd.firstCell = (int)cells.size();
+                    strips.push_back(sd);
+                }
+                StripDesc& sd = strips.back();
+                sd.nCells++; sd.w = (short)(d.x0 + d.w - sd.x0);
+                levelMaxW = std::max(levelMaxW, (int)sd.w); levelMaxH = std::max(levelMaxH, ch);
+                ++inRow;
                 cells.push_back(d);
             }
         }
         q.nCells = (int)cells.size() - q.cell0;
+        c->fastBW[l] = align_up(15 + 3 + levelMaxW + 3, 16);   // box starts on a 16-byte boundary <= x0 - 3, ends >= 3 px past the strip
+        c->fastBH[l] = levelMaxH + 6;
+        if (c->fastBW[l] > 256 || c->fastBH[l] > 256) return ORBF_ERR_GEOMETRY;
         q.candCap = cap;
         candOff += cap;
         // quadtree roots (orbextractor.cpp:470-472)
@@ -212,8 +258,10 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;
-    std::vector<ResizeCoef> tab; std::vector<CellDesc> cells;
-    int rc = build_geometry(c, tab, cells);
+    std::vector<ResizeCoef> tab; std::vector<CellDesc> cells; std::vector<StripDesc> strips;
+    c->tmFastReady = false; c->tm0Base = nullptr; c->tm0Pitch = c->tm0FrameStride = 0; c->tm0Frames = 0;
+    int rc = build_geometry(c, tab, cells, strips);
+    c->nStrips = (int)strips.size();
     if (rc != ORBF_OK) { delete c; return rc; }
 
     cudaError_t e = cudaSetDevice(cfg->device);
@@ -245,6 +293,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     }
     TRY(dalloc(c, &c->d_resizeTab, tab.size()));
     TRY(dalloc(c, &c->d_cells, cells.size()));
+    TRY(dalloc(c, &c->d_strips, strips.size()));
     TRY(dalloc(c, &c->d_lg, (size_t)ORBF_MAX_LEVELS));
     TRY(dalloc(c, &c->d_cellCand, B * c->cellSlotTotal));
     TRY(dalloc(c, &c->d_cellCount, B * c->nCellsTotal));
@@ -281,6 +330,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     auto cu = [&](cudaError_t e3, const char* w) { if (e3 != cudaSuccess) { orbf_cuda_fail(c, e3, w, __FILE__, __LINE__); return false; } return true; };
     if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice), "cells")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemcpy(c->d_strips, strips.data(), strips.size() * sizeof(StripDesc), cudaMemcpyHostToDevice), "strips")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_lg, c->lg, sizeof(LevelGeom) * ORBF_MAX_LEVELS, cudaMemcpyHostToDevice), "lg")) return fail(ORBF_ERR_CUDA);
     { const double neg = -1.0; if (!cu(cudaMemcpy(c->d_depthCov, &neg, sizeof(double), cudaMemcpyHostToDevice), "depthCov")) return fail(ORBF_ERR_CUDA); }
     if (!cu(cudaMemset(c->d_count, 0, B * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
@@ -301,7 +351,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (!c) return ORBF_ERR_ARG;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
+    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,

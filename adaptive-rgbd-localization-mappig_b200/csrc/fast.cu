@@ -1,24 +1,37 @@
 // csrc/fast.cu — per-cell FAST-9/16 with non-max suppression and the iniTh -> minTh fallback
 // (reference ComputeKeyPointsOctTree, Features/orbextractor.cpp:665-723, calling cv::FAST(roi, th, true)).
 //
-// One warp per (cell, frame).  The cell's scored interior plus a 3-px ring halo is staged in shared memory;
-// corner strength S(p) = max over the 16 arcs of 9 contiguous ring pixels of min(centre - ring) for both
-// polarities (cv::FAST response = S - 1, corner iff S > th); NMS is strict '>' against the 8 neighbours
-// *inside the same cell interior* (quirk Q1: each cell is its own cv::FAST call, so neighbours in an
-// adjacent cell count as 0); a cell with no survivor at iniTh is redone at minTh.  Survivors are written
-// row-major (warp-ballot compaction) to the cell's private slot range, so the candidate list a later stage
-// gathers cell by cell is in exactly the reference's push_back order.
+// Work unit = a STRIP of up to 4 adjacent cells of one cell row (their scored interiors tile the row without gaps),
+// one CTA of 4 warps per (strip, frame), all levels in one launch:
+//   0. one thread fetches the strip + 3-px ring halo with a single TMA box load (cp.async.bulk.tensor.3d -> UTMALDG);
+//      a u8 box must start on a 16-byte boundary of the level row, so the interior begins at tile column ax in [3, 18];
+//   1. pretest, 4 pixels per thread on packed u16x2 lanes (VIMNMX.U16x2): a 9-arc contains one pixel of each opposite
+//      pair, so min(max(p0,p8), max(p4,p12)) > v+th or max(min(p0,p8), min(p4,p12)) < v-th is necessary; survivors
+//      (17 % of the pixels on the bench texture) are compacted into a CTA-wide list with warp ballots;
+//   2. corner strength of two survivors at a time on packed u16x2 lanes with 3-input min/max (VIMNMX3.U16x2):
+//      S = max(v - A, B - v), A = min over the 16 arcs of the arc maximum, B = max over the arcs of the arc minimum
+//      (cv::FAST response = S - 1, corner iff S > th); 80 packed ops per pixel pair;
+//   3. one warp per cell: strict '>' NMS against the 8 neighbours *inside the same cell interior* (quirk Q1: each cell
+//      is its own cv::FAST call, so neighbours in an adjacent cell count as 0), row-major ordered compaction (ballot
+//      prefix sums) into the cell's private slot range = the reference's push_back order;
+//   4. a cell with no survivor at iniTh is redone by its warp at minTh (orbextractor.cpp:709-712; rare, scalar path).
+// Arithmetic is all integer min/max/compare: bit-exact by construction.  Bound by the integer ALU pipe, not by HBM.
 #include "orbf_internal.h"
 
 namespace {
 
-constexpr int FC_WARPS = 4, FC_THREADS = FC_WARPS * 32;
+constexpr int FS_WARPS = ORBF_STRIP_CELLS, FS_THREADS = FS_WARPS * 32;
 
-// Corner strength without ever negating a min/max result:
-//   bright arcs: min over 9 contiguous (v - ring) = v - max_arc(ring);  dark arcs: min (ring - v) = min_arc(ring) - v
-//   S = max(v - A, B - v),  A = min over the 16 arcs of the arc maximum,  B = max over the 16 arcs of the arc minimum.
-// (nvcc 12.9 for sm_100a miscompiles max(x, -max(...)) chains — the negation is lost when ptxas fuses them into
-//  VIMNMX3; tools/nvcc_minmax_bug.cu reproduces it.  The raw-pixel formulation is also cheaper: no 16 subtractions.)
+struct FastParams {
+    CUtensorMap maps[ORBF_MAX_LEVELS];
+    const StripDesc* strips; const CellDesc* cells;
+    uint32_t* cellCand; int* cellCount;
+    int cellSlotTotal, nCellsTotal, iniTh, minTh, slot0, z0;   // z coordinate of a slot: slot - z0 on level 0, slot elsewhere
+    short BW[ORBF_MAX_LEVELS], BH[ORBF_MAX_LEVELS];
+};
+
+// Corner strength without ever negating a min/max result (nvcc 12.9 for sm_100a loses the negation when ptxas fuses
+// max(x, -max(...)) chains into VIMNMX3; tools/nvcc_minmax_bug.cu reproduces it).  Scalar form: fallback path only.
 __device__ __forceinline__ int ring_strength(const uint8_t* p, int rp)
 {
     // ring offsets in cv::FAST order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
@@ -42,114 +55,249 @@ __device__ __forceinline__ int ring_strength(const uint8_t* p, int rp)
     return max(v - A, B - v);
 }
 
-// One WARP per (cell, frame); FC_WARPS cells per CTA.  No block barriers: the three phases (quick test ->
-// dense strength -> NMS + ordered write) only need __syncwarp.  Because a single warp walks the cell in
-// row-major chunks of 32 pixels, one ballot per chunk yields the reference's output order directly.
-__global__ void __launch_bounds__(FC_THREADS) fast_cell_kernel(PyrView pv, const CellDesc* __restrict__ cells,
-    int nCellsTotal, uint32_t* __restrict__ cellCand, int* __restrict__ cellCount, int cellSlotTotal, int iniTh, int minTh,
-    int slot0, int regPitch, int regBytes, int scoreBytes, int warpBytes)
+// Strength of two pixels at once: lane halves hold pixel a (low) and pixel b (high), every value <= 255.
+__device__ __forceinline__ uint32_t ring_strength_x2(const uint8_t* pa, const uint8_t* pb, int rp)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cellIdx = blockIdx.x * FC_WARPS + warp;
-    if (cellIdx >= nCellsTotal) return;
-    uint8_t* reg = smem + warp * warpBytes;                       // (h+6) x regPitch : level pixels, word-aligned columns
-    uint8_t* score = reg + regBytes;                              // (h+2) x (w+2)    : response, zero border
-    uint16_t* list = reinterpret_cast<uint16_t*>(score + scoreBytes);   // quick-test survivors
+    const int o[16] = { 3 * rp, 3 * rp + 1, 2 * rp + 2, rp + 3, 3, -rp + 3, -2 * rp + 2, -3 * rp + 1,
+        -3 * rp, -3 * rp - 1, -2 * rp - 2, -rp - 3, -3, rp - 3, 2 * rp - 2, 3 * rp - 1 };
+    uint32_t r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = (uint32_t)pa[o[k]] + ((uint32_t)pb[o[k]] << 16);
+    uint32_t mx3[16], mn3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    uint32_t mx9[16], mn9[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {      // arc k = ring pixels k .. k+8
+        mx9[k] = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+        mn9[k] = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+    }
+    uint32_t A = __vimin3_u16x2(mx9[0], mx9[1], mx9[2]), B = __vimax3_u16x2(mn9[0], mn9[1], mn9[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) { A = __vimin3_u16x2(A, mx9[k], mx9[k + 1]); B = __vimax3_u16x2(B, mn9[k], mn9[k + 1]); }
+    A = __vminu2(A, mx9[15]); B = __vmaxu2(B, mn9[15]);
+    const uint32_t v = (uint32_t)pa[0] + ((uint32_t)pb[0] << 16);
+    // max(v - A, 0) and max(B - v, 0) per half: both differences are formed on values ordered first, so no borrow crosses halves
+    return __vmaxu2(__vmaxu2(v, A) - A, __vmaxu2(B, v) - v);
+}
 
-    const CellDesc cd = cells[cellIdx];
-    const int slot = slot0 + blockIdx.y;
-    const LevelView lv = pv.lv[cd.level];
-    const int w = cd.w, h = cd.h, sp = w + 2, npix = w * h;
-    const uint32_t rcpW = ((1u << 20) + w - 1) / w;               // y = (p * rcpW) >> 20 is exact for p < 2^20 / w
-    // stage (h+6) rows of (w+6) pixels with aligned 32-bit loads; ax = misalignment of the first column
-    const int gx0 = cd.x0 - 3, ax = gx0 & 3, wordsPerRow = (ax + w + 6 + 3) >> 2;
-    const uint8_t* img = lv.base + (long long)slot * lv.frameStride + (long long)(cd.y0 - 3) * lv.pitch + (gx0 - ax);
-    {
-        const uint32_t rcpR = ((1u << 20) + wordsPerRow - 1) / wordsPerRow;
-        const int nWords = (h + 6) * wordsPerRow;
-        for (int i = lane; i < nWords; i += 32) {
-            const int r = (int)(((uint32_t)i * rcpR) >> 20), c = i - r * wordsPerRow;
-            *reinterpret_cast<uint32_t*>(reg + r * regPitch + 4 * c) = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)r * lv.pitch) + c);
-        }
-    }
-    const uint8_t* org = reg + 3 * regPitch + 3 + ax;             // interior pixel (0,0)
-    uint32_t* out = cellCand + (long long)slot * cellSlotTotal + cd.slotOff;
+// pass flags of one pixel pair (halves = two adjacent pixels): a half of the result is 0 iff that pixel passes
+__device__ __forceinline__ uint32_t pretest_x2(uint32_t v, uint32_t p0, uint32_t p8, uint32_t p4, uint32_t p12, uint32_t th1)
+{
+    const uint32_t mb = __vminu2(__vmaxu2(p0, p8), __vmaxu2(p4, p12));     // bright: both opposite pairs hold a pixel > v + th
+    const uint32_t md = __vmaxu2(__vminu2(p0, p8), __vminu2(p4, p12));     // dark:   both opposite pairs hold a pixel < v - th
+    const uint32_t vh = v + th1, dh = md + th1;                           // th1 = (th + 1) in both halves; sums < 2^16
+    const uint32_t fb = __vminu2(mb, vh) ^ vh;                            // 0 iff mb >= v + th + 1
+    const uint32_t fd = __vmaxu2(dh, v) ^ v;                              // 0 iff md + th + 1 <= v
+    return __vminu2(fb, fd);
+}
+
+// NMS + row-major ordered compaction of one cell by one warp; returns the number of keypoints written
+// (c0 = tile column of the cell's first pixel)
+__device__ int nms_cell(const uint8_t* score, int BW, int c0, int cw, int h, uint32_t* out, int outX0, int outY0, int lane)
+{
+    const int w0 = c0 >> 2, w1 = (c0 + cw - 1) >> 2, nw = w1 - w0 + 1;
+    const uint32_t rcp = ((1u << 20) + nw - 1) / nw;
+    const int nTasks = h * nw;
+    const uint32_t lt = (1u << lane) - 1;
     int total = 0;
-    int th = iniTh;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        for (int i = lane; i < (h + 2) * sp; i += 32) score[i] = 0;
-        __syncwarp();
-        // 1. cheap necessary condition (an arc of 9 contains one pixel of every opposite pair, all of one polarity), compacted
-        int nList = 0;
-        for (int base = 0; base < npix; base += 32) {
-            const int p = base + lane;
-            bool pass = false;
-            if (p < npix) {
-                const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * w;
-                const uint8_t* c = org + y * regPitch + x;
-                const int v = c[0], hiT = v + th, loT = v - th;
-                const int p0 = c[3 * regPitch], p8 = c[-3 * regPitch], p4 = c[3], p12 = c[-3];
-                pass = (((p0 > hiT) | (p8 > hiT)) & ((p4 > hiT) | (p12 > hiT))) | (((p0 < loT) | (p8 < loT)) & ((p4 < loT) | (p12 < loT)));
+    for (int base = 0; base < nTasks; base += 32) {
+        const int t = base + lane;
+        uint32_t keep = 0, word = 0;
+        int row = 0, xw = 0;
+        if (t < nTasks) {
+            row = (int)(((uint32_t)t * rcp) >> 20);
+            const int wi = w0 + (t - row * nw);
+            xw = 4 * wi - c0;                                              // cell-local x of byte 0
+            word = *reinterpret_cast<const uint32_t*>(score + (row + 1) * BW + 4 * wi);
+            if (word) {
+                const uint8_t* s0 = score + (row + 1) * BW + 4 * wi;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int x = xw + b;
+                    const int v = (word >> (8 * b)) & 255;
+                    if (v && (unsigned)x < (unsigned)cw) {
+                        const uint8_t* s = s0 + b;
+                        const bool l = x > 0, r = x < cw - 1;              // neighbours in the adjacent cell do not exist for this cell
+                        bool k = v > s[-BW] && v > s[BW];
+                        if (l) k = k && v > s[-1] && v > s[-BW - 1] && v > s[BW - 1];
+                        if (r) k = k && v > s[1] && v > s[-BW + 1] && v > s[BW + 1];
+                        if (k) keep |= 1u << b;
+                    }
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (pass) list[nList + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
-            nList += __popc(m);
         }
-        __syncwarp();
-        // 2. full strength on the dense survivor list
-        for (int i = lane; i < nList; i += 32) {
-            const int p = list[i];
-            const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * w;
-            const int s = ring_strength(org + y * regPitch + x, regPitch);
-            if (s > th) score[(y + 1) * sp + x + 1] = (uint8_t)(s - 1);
-        }
-        __syncwarp();
-        // 3. NMS + row-major ordered compaction
-        total = 0;
-        for (int base = 0; base < npix; base += 32) {
-            const int p = base + lane;
-            bool keep = false;
-            int v = 0, x = 0, y = 0;
-            if (p < npix) {
-                y = (int)(((uint32_t)p * rcpW) >> 20); x = p - y * w;
-                const uint8_t* s = score + (y + 1) * sp + x + 1;
-                v = s[0];
-                keep = v > 0 && v > s[-1] && v > s[1] && v > s[-sp - 1] && v > s[-sp] && v > s[-sp + 1] && v > s[sp - 1]
-                    && v > s[sp] && v > s[sp + 1];
+        if (!__any_sync(0xffffffffu, keep != 0)) continue;
+        const int cnt = __popc(keep);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2), b2 = __ballot_sync(0xffffffffu, cnt & 4);
+        int pos = total + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        total += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (keep & (1u << b)) {
+                const uint32_t v = (word >> (8 * b)) & 255;
+                out[pos++] = (uint32_t)(outX0 + xw + b) | ((uint32_t)(outY0 + row) << 11) | (v << 22);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int xr = cd.x0 + x + cd.relx, yr = cd.y0 + y + cd.rely;
-                out[total + __popc(m & ((1u << lane) - 1))] = (uint32_t)xr | ((uint32_t)yr << 11) | ((uint32_t)v << 22);
-            }
-            total += __popc(m);
-        }
-        if (total > 0 || minTh >= th) break;
-        th = minTh;   // empty cell at iniTh: rerun at minTh (orbextractor.cpp:709-712)
-        __syncwarp();
     }
-    if (lane == 0) cellCount[(long long)slot * nCellsTotal + cellIdx] = total;
+    return total;
+}
+
+__global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_constant__ FastParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int sCount;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const StripDesc sd = P.strips[blockIdx.x];
+    const int slot = P.slot0 + blockIdx.y;
+    const int level = sd.level, BW = P.BW[level], BH = P.BH[level];
+    const int W = sd.w, h = sd.h;
+    const int xs = (sd.x0 - 3) & ~15, ax = sd.x0 - xs;                      // TMA boxes of bytes start on 16-byte boundaries
+    uint8_t* tile = smem;                                                   // BH x BW level pixels, interior (0,0) at [3][ax]
+    uint8_t* score = smem + align_up(BW * BH, 128);                         // (h + 2) x BW responses, interior (0,0) at [1][ax], zero elsewhere
+    uint16_t* list = reinterpret_cast<uint16_t*>(score + align_up(BW * (BH - 4), 16));   // pretest survivors: y * BW + tile column
+
+    if (tid == 0) { mbar_init(&bar, 1); sCount = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(BW * BH));
+        tma_load_3d(tile, &P.maps[level], xs, sd.y0 - 3, level == 0 ? slot - P.z0 : slot, &bar);
+    }
+    for (int i = tid; i < (BW * (h + 2)) >> 2; i += FS_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    mbar_wait(&bar, 0);
+    __syncthreads();
+
+    const int th = P.iniTh;
+    // ---- 1. pretest: 4 pixels (one aligned word of the centre row) per thread -------------------------------------
+    {
+        const int wFirst = ax >> 2, wpr = ((ax + W + 3) >> 2) - wFirst, nTasks = h * wpr;
+        const uint32_t rcp = ((1u << 20) + wpr - 1) / wpr;
+        const uint32_t th1 = (uint32_t)(th + 1) * 0x00010001u;
+        const uint32_t lt = (1u << lane) - 1;
+        for (int base = 0; base < nTasks; base += FS_THREADS) {
+            const int t = base + tid;
+            uint32_t flags = 0;
+            int e = 0;
+            if (t < nTasks) {
+                const int row = (int)(((uint32_t)t * rcp) >> 20), wi = wFirst + (t - row * wpr);
+                e = row * BW + 4 * wi;
+                const uint32_t* c = reinterpret_cast<const uint32_t*>(tile + (row + 3) * BW) + wi;
+                const uint32_t Cp = c[-1], C = c[0], Cn = c[1];             // word -1 of tile row >= 3 is still inside the tile
+                const uint32_t U = *reinterpret_cast<const uint32_t*>(tile + row * BW + 4 * wi);
+                const uint32_t D = *reinterpret_cast<const uint32_t*>(tile + (row + 6) * BW + 4 * wi);
+                const uint32_t L = __funnelshift_r(Cp, C, 8), R = __funnelshift_r(C, Cn, 24);      // pixels x-3 / x+3 of the 4 centres
+                const uint32_t f01 = pretest_x2(__byte_perm(C, 0, 0x4140), __byte_perm(D, 0, 0x4140), __byte_perm(U, 0, 0x4140),
+                    __byte_perm(R, 0, 0x4140), __byte_perm(L, 0, 0x4140), th1);
+                const uint32_t f23 = pretest_x2(__byte_perm(C, 0, 0x4342), __byte_perm(D, 0, 0x4342), __byte_perm(U, 0, 0x4342),
+                    __byte_perm(R, 0, 0x4342), __byte_perm(L, 0, 0x4342), th1);
+                flags = ((f01 & 0xFFFFu) == 0 ? 1u : 0u) | ((f01 >> 16) == 0 ? 2u : 0u) | ((f23 & 0xFFFFu) == 0 ? 4u : 0u) | ((f23 >> 16) == 0 ? 8u : 0u);
+                const int xi = 4 * wi - ax;                                 // interior x of byte 0: mask pixels outside [0, W)
+                if (xi < 0) flags &= 0xFu << (-xi);
+                if (W - xi < 4) flags &= (1u << (W - xi)) - 1;
+            }
+            if (!__any_sync(0xffffffffu, flags != 0)) continue;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, flags & 1), m1 = __ballot_sync(0xffffffffu, flags & 2);
+            const uint32_t m2 = __ballot_sync(0xffffffffu, flags & 4), m3 = __ballot_sync(0xffffffffu, flags & 8);
+            const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3);
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&sCount, n0 + n1 + n2 + n3);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (flags & 1) list[wbase + __popc(m0 & lt)] = (uint16_t)e;
+            if (flags & 2) list[wbase + n0 + __popc(m1 & lt)] = (uint16_t)(e + 1);
+            if (flags & 4) list[wbase + n0 + n1 + __popc(m2 & lt)] = (uint16_t)(e + 2);
+            if (flags & 8) list[wbase + n0 + n1 + n2 + __popc(m3 & lt)] = (uint16_t)(e + 3);
+        }
+    }
+    __syncthreads();
+    // ---- 2. corner strength, two survivors per thread --------------------------------------------------------------
+    {
+        const int n = sCount;
+        const uint8_t* org = tile + 3 * BW;
+        uint8_t* sorg = score + BW;
+        for (int i = tid; 2 * i < n; i += FS_THREADS) {
+            const int ea = list[2 * i], eb = list[min(2 * i + 1, n - 1)];
+            const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
+            const int sa = (int)(s & 0xFFFFu), sb = (int)(s >> 16);
+            if (sa > th) sorg[ea] = (uint8_t)(sa - 1);
+            if (sb > th) sorg[eb] = (uint8_t)(sb - 1);
+        }
+    }
+    __syncthreads();
+    // ---- 3./4. one warp per cell: NMS + ordered output, minTh fallback ---------------------------------------------
+    if (warp < sd.nCells) {
+        const int cellIdx = sd.firstCell + warp;
+        const CellDesc cd = P.cells[cellIdx];
+        const int c0 = ax + cd.x0 - sd.x0, cw = cd.w;
+        uint32_t* out = P.cellCand + (long long)slot * P.cellSlotTotal + cd.slotOff;
+        const int outX0 = cd.x0 + cd.relx, outY0 = cd.y0 + cd.rely;
+        int total = nms_cell(score, BW, c0, cw, h, out, outX0, outY0, lane);
+        if (total == 0 && P.minTh < th) {
+            // no corner at iniTh in this cell, so its score columns are still all zero: rescore the cell at minTh
+            const int t2 = P.minTh, npix = cw * h;
+            const uint32_t rcpW = ((1u << 20) + cw - 1) / cw;
+            const uint8_t* org = tile + 3 * BW + c0;
+            uint8_t* sorg = score + BW + c0;
+            for (int p = lane; p < npix; p += 32) {
+                const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
+                const uint8_t* c = org + y * BW + x;
+                const int v = c[0], hiT = v + t2, loT = v - t2;
+                const int p0 = c[3 * BW], p8 = c[-3 * BW], p4 = c[3], p12 = c[-3];
+                const bool pass = (((p0 > hiT) | (p8 > hiT)) & ((p4 > hiT) | (p12 > hiT))) | (((p0 < loT) | (p8 < loT)) & ((p4 < loT) | (p12 < loT)));
+                if (pass) {
+                    const int s = ring_strength(c, BW);
+                    if (s > t2) sorg[y * BW + x] = (uint8_t)(s - 1);
+                }
+            }
+            __syncwarp();
+            total = nms_cell(score, BW, c0, cw, h, out, outX0, outY0, lane);
+        }
+        if (lane == 0) P.cellCount[(long long)slot * P.nCellsTotal + cellIdx] = total;
+    }
 }
 
 }  // namespace
 
 int orbf_launch_fast(orbf_context* c, int slot0, int n)
 {
+    // level-0 map follows the caller's input plane; levels >= 1 are the context's own pyramid planes
     PyrView pv = orbf_pyr_view(c, false);
-    const int regPitch = align_up(c->maxCellW + 6 + 3, 4);
-    const int regBytes = (c->maxCellH + 6) * regPitch;
-    const int scoreBytes = align_up((c->maxCellH + 2) * (c->maxCellW + 2), 4);
-    const int warpBytes = align_up(regBytes + scoreBytes + c->maxCellW * c->maxCellH * (int)sizeof(uint16_t), 16);
-    const size_t smem = (size_t)warpBytes * FC_WARPS;
+    if (!c->tmFastReady) {
+        for (int l = 1; l < c->L; ++l) {
+            const int r = orbf_tma_encode_u8(c, &c->tmFast[l], c->d_pyr[l], c->lg[l].w, c->lg[l].h, c->B, c->lg[l].pitch, (long long)c->lg[l].plane,
+                c->fastBW[l], c->fastBH[l]);
+            if (r != ORBF_OK) return r;
+        }
+        c->tmFastReady = true;
+    }
+    if (c->tm0Base != c->cur_gray || c->tm0Pitch != c->cur_grayPitch || c->tm0FrameStride != c->cur_grayFrameStride || c->tm0Frames != c->cur_n) {
+        const int r = orbf_tma_encode_u8(c, &c->tmFast[0], c->cur_gray, c->lg[0].w, c->lg[0].h, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride,
+            c->fastBW[0], c->fastBH[0]);
+        if (r != ORBF_OK) return r;
+        c->tm0Base = c->cur_gray; c->tm0Pitch = c->cur_grayPitch; c->tm0FrameStride = c->cur_grayFrameStride; c->tm0Frames = c->cur_n;
+    }
+    (void)pv;
+    FastParams P;
+    size_t smem = 0;
+    for (int l = 0; l < c->L; ++l) {
+        P.maps[l] = c->tmFast[l];
+        P.BW[l] = (short)c->fastBW[l]; P.BH[l] = (short)c->fastBH[l];
+        const int BW = c->fastBW[l], BH = c->fastBH[l];
+        const size_t need = (size_t)align_up(BW * BH, 128) + align_up(BW * (BH - 4), 16) + (size_t)BW * (BH - 6) * sizeof(uint16_t) + 16;
+        smem = std::max(smem, need);
+    }
+    P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
+    P.cellSlotTotal = c->cellSlotTotal; P.nCellsTotal = c->nCellsTotal; P.iniTh = c->cfg.ini_th_fast; P.minTh = c->cfg.min_th_fast;
+    P.slot0 = slot0; P.z0 = c->cur_slot0;
     if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(fast_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "fast smem attr", __FILE__, __LINE__);
     }
-    dim3 grid((c->nCellsTotal + FC_WARPS - 1) / FC_WARPS, n);
-    fast_cell_kernel<<<grid, FC_THREADS, smem, c->stream>>>(pv, c->d_cells, c->nCellsTotal, c->d_cellCand, c->d_cellCount,
-        c->cellSlotTotal, c->cfg.ini_th_fast, c->cfg.min_th_fast, slot0, regPitch, regBytes, scoreBytes, warpBytes);
+    dim3 grid(c->nStrips, n);
+    fast_strip_kernel<<<grid, FS_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }

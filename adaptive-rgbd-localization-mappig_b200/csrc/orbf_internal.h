@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/orbfront.h"
+#include "tma.h"
 
 #define ORBF_EDGE 19
 #define ORBF_MINB 16          // EDGE_THRESHOLD - 3 (orbextractor.cpp:672)
@@ -38,6 +39,14 @@ struct CellDesc {             // one FAST cell (orbextractor.cpp:688-723): score
     int slotOff;              // offset of this cell's slots inside a frame's cell-candidate buffer
     int cap;
 };
+
+struct StripDesc {            // FAST work unit: up to ORBF_STRIP_CELLS adjacent cells of one cell row (fast.cu)
+    short level, nCells;
+    short x0, y0;             // first scored pixel (level coordinates) = interior origin of its first cell
+    short w, h;               // scored width over all its cells, scored rows
+    int firstCell;            // index of its first cell in the CellDesc table (the others follow)
+};
+#define ORBF_STRIP_CELLS 4
 
 struct LevelGeom {
     int w, h, pitch;
@@ -85,6 +94,9 @@ struct orbf_context {
     uint8_t* d_blur[ORBF_MAX_LEVELS];
     ResizeCoef* d_resizeTab;
     CellDesc* d_cells;
+    StripDesc* d_strips; int nStrips; int fastBW[ORBF_MAX_LEVELS], fastBH[ORBF_MAX_LEVELS];   // TMA box per level (fast.cu)
+    CUtensorMap tmFast[ORBF_MAX_LEVELS]; bool tmFastReady;
+    const void* tm0Base; long long tm0Pitch, tm0FrameStride; int tm0Frames;                  // what the level-0 maps were encoded for
     LevelGeom* d_lg;
     uint32_t* d_cellCand; int* d_cellCount;
     uint32_t* d_cand; int* d_candCount;
