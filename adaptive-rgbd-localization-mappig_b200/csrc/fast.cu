@@ -7,14 +7,15 @@
 //      a u8 box must start on a 16-byte boundary of the level row, so the interior begins at tile column ax in [3, 18];
 //   1. pretest, 4 pixels per thread on packed u16x2 lanes (VIMNMX.U16x2): a 9-arc contains one pixel of each opposite
 //      pair, so min(max(p0,p8), max(p4,p12)) > v+th or max(min(p0,p8), min(p4,p12)) < v-th is necessary; survivors
-//      (17 % of the pixels on the bench texture) are compacted into a CTA-wide list with warp ballots;
+//      (17 % of the pixels on the bench texture) are appended to a CTA-wide list (shared-memory atomics);
 //   2. corner strength of two survivors at a time on packed u16x2 lanes with 3-input min/max (VIMNMX3.U16x2):
 //      S = max(v - A, B - v), A = min over the 16 arcs of the arc maximum, B = max over the arcs of the arc minimum
 //      (cv::FAST response = S - 1, corner iff S > th); 80 packed ops per pixel pair;
-//   3. one warp per cell: strict '>' NMS against the 8 neighbours *inside the same cell interior* (quirk Q1: each cell
-//      is its own cv::FAST call, so neighbours in an adjacent cell count as 0), row-major ordered compaction (ballot
-//      prefix sums) into the cell's private slot range = the reference's push_back order;
-//   4. a cell with no survivor at iniTh is redone by its warp at minTh (orbextractor.cpp:709-712; rare, scalar path).
+//   3. NMS over the survivor list: strict '>' against the 8 neighbours *inside the same cell interior* (quirk Q1: each
+//      cell is its own cv::FAST call, so neighbours in an adjacent cell count as 0); kept corners go to their cell's list;
+//   4. one warp per cell ranks its kept corners by tile offset (= row-major order inside the cell) and writes them to
+//      the cell's private slot range in exactly the reference's push_back order;
+//   5. a cell with no survivor at iniTh is redone by its warp at minTh (orbextractor.cpp:709-712; rare, scalar path).
 // Arithmetic is all integer min/max/compare: bit-exact by construction.  Bound by the integer ALU pipe, not by HBM.
 #include "orbf_internal.h"
 
@@ -27,6 +28,7 @@ struct FastParams {
     const StripDesc* strips; const CellDesc* cells;
     uint32_t* cellCand; int* cellCount;
     int cellSlotTotal, nCellsTotal, iniTh, minTh, slot0, z0;   // z coordinate of a slot: slot - z0 on level 0, slot elsewhere
+    int keptCap;                                                // capacity of a cell's kept-corner list (max CellDesc::cap)
     short BW[ORBF_MAX_LEVELS], BH[ORBF_MAX_LEVELS];
 };
 
@@ -95,54 +97,25 @@ __device__ __forceinline__ uint32_t pretest_x2(uint32_t v, uint32_t p0, uint32_t
     return __vminu2(fb, fd);
 }
 
-// NMS + row-major ordered compaction of one cell by one warp; returns the number of keypoints written
-// (c0 = tile column of the cell's first pixel)
-__device__ int nms_cell(const uint8_t* score, int BW, int c0, int cw, int h, uint32_t* out, int outX0, int outY0, int lane)
+// strict 8-neighbour maximum test of score byte *s (value v > 0); l / r: a left / right neighbour column exists in this cell
+__device__ __forceinline__ bool nms_keep(const uint8_t* s, int v, int BW, bool l, bool r)
 {
-    const int w0 = c0 >> 2, w1 = (c0 + cw - 1) >> 2, nw = w1 - w0 + 1;
-    const uint32_t rcp = ((1u << 20) + nw - 1) / nw;
-    const int nTasks = h * nw;
-    const uint32_t lt = (1u << lane) - 1;
-    int total = 0;
-    for (int base = 0; base < nTasks; base += 32) {
-        const int t = base + lane;
-        uint32_t keep = 0, word = 0;
-        int row = 0, xw = 0;
-        if (t < nTasks) {
-            row = (int)(((uint32_t)t * rcp) >> 20);
-            const int wi = w0 + (t - row * nw);
-            xw = 4 * wi - c0;                                              // cell-local x of byte 0
-            word = *reinterpret_cast<const uint32_t*>(score + (row + 1) * BW + 4 * wi);
-            if (word) {
-                const uint8_t* s0 = score + (row + 1) * BW + 4 * wi;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int x = xw + b;
-                    const int v = (word >> (8 * b)) & 255;
-                    if (v && (unsigned)x < (unsigned)cw) {
-                        const uint8_t* s = s0 + b;
-                        const bool l = x > 0, r = x < cw - 1;              // neighbours in the adjacent cell do not exist for this cell
-                        bool k = v > s[-BW] && v > s[BW];
-                        if (l) k = k && v > s[-1] && v > s[-BW - 1] && v > s[BW - 1];
-                        if (r) k = k && v > s[1] && v > s[-BW + 1] && v > s[BW + 1];
-                        if (k) keep |= 1u << b;
-                    }
-                }
-            }
-        }
-        if (!__any_sync(0xffffffffu, keep != 0)) continue;
-        const int cnt = __popc(keep);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2), b2 = __ballot_sync(0xffffffffu, cnt & 4);
-        int pos = total + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-        total += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (keep & (1u << b)) {
-                const uint32_t v = (word >> (8 * b)) & 255;
-                out[pos++] = (uint32_t)(outX0 + xw + b) | ((uint32_t)(outY0 + row) << 11) | (v << 22);
-            }
+    bool k = v > s[-BW] && v > s[BW];
+    if (l) k = k && v > s[-1] && v > s[-BW - 1] && v > s[BW - 1];
+    if (r) k = k && v > s[1] && v > s[-BW + 1] && v > s[BW + 1];
+    return k;
+}
+
+// One warp orders a cell's kept corners (key = tile offset << 8 | response; offsets are distinct) and writes them out.
+__device__ __forceinline__ void emit_cell(const uint32_t* kept, int n, int BW, int c0, uint32_t* out, int outX0, int outY0, int lane)
+{
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t key = kept[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += kept[j] < key;
+        const int e = (int)(key >> 8), row = e / BW, col = e - row * BW;
+        out[rank] = (uint32_t)(outX0 + col - c0) | ((uint32_t)(outY0 + row) << 11) | ((key & 255u) << 22);
     }
-    return total;
 }
 
 __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_constant__ FastParams P)
@@ -159,8 +132,13 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     uint8_t* tile = smem;                                                   // BH x BW level pixels, interior (0,0) at [3][ax]
     uint8_t* score = smem + align_up(BW * BH, 128);                         // (h + 2) x BW responses, interior (0,0) at [1][ax], zero elsewhere
     uint16_t* list = reinterpret_cast<uint16_t*>(score + align_up(BW * (BH - 4), 16));   // pretest survivors: y * BW + tile column
+    uint32_t* kept = reinterpret_cast<uint32_t*>(list + align_up(BW * (BH - 6), 8));     // [cell][keptCap] NMS survivors
+    __shared__ int sKept[FS_WARPS];
+    __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
 
     if (tid == 0) { mbar_init(&bar, 1); sCount = 0; }
+    if (tid < FS_WARPS) sKept[tid] = 0;
+    if (tid <= FS_WARPS) sC0[tid] = tid < sd.nCells ? ax + P.cells[sd.firstCell + tid].x0 - sd.x0 : ax + W + (tid > sd.nCells ? 4096 : 0);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, (uint32_t)(BW * BH));
@@ -171,89 +149,105 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     __syncthreads();
 
     const int th = P.iniTh;
+    const int keptCap = P.keptCap;
     // ---- 1. pretest: 4 pixels (one aligned word of the centre row) per thread -------------------------------------
     {
         const int wFirst = ax >> 2, wpr = ((ax + W + 3) >> 2) - wFirst, nTasks = h * wpr;
         const uint32_t rcp = ((1u << 20) + wpr - 1) / wpr;
         const uint32_t th1 = (uint32_t)(th + 1) * 0x00010001u;
-        const uint32_t lt = (1u << lane) - 1;
-        for (int base = 0; base < nTasks; base += FS_THREADS) {
-            const int t = base + tid;
-            uint32_t flags = 0;
-            int e = 0;
-            if (t < nTasks) {
-                const int row = (int)(((uint32_t)t * rcp) >> 20), wi = wFirst + (t - row * wpr);
-                e = row * BW + 4 * wi;
-                const uint32_t* c = reinterpret_cast<const uint32_t*>(tile + (row + 3) * BW) + wi;
-                const uint32_t Cp = c[-1], C = c[0], Cn = c[1];             // word -1 of tile row >= 3 is still inside the tile
-                const uint32_t U = *reinterpret_cast<const uint32_t*>(tile + row * BW + 4 * wi);
-                const uint32_t D = *reinterpret_cast<const uint32_t*>(tile + (row + 6) * BW + 4 * wi);
-                const uint32_t L = __funnelshift_r(Cp, C, 8), R = __funnelshift_r(C, Cn, 24);      // pixels x-3 / x+3 of the 4 centres
-                const uint32_t f01 = pretest_x2(__byte_perm(C, 0, 0x4140), __byte_perm(D, 0, 0x4140), __byte_perm(U, 0, 0x4140),
-                    __byte_perm(R, 0, 0x4140), __byte_perm(L, 0, 0x4140), th1);
-                const uint32_t f23 = pretest_x2(__byte_perm(C, 0, 0x4342), __byte_perm(D, 0, 0x4342), __byte_perm(U, 0, 0x4342),
-                    __byte_perm(R, 0, 0x4342), __byte_perm(L, 0, 0x4342), th1);
-                flags = ((f01 & 0xFFFFu) == 0 ? 1u : 0u) | ((f01 >> 16) == 0 ? 2u : 0u) | ((f23 & 0xFFFFu) == 0 ? 4u : 0u) | ((f23 >> 16) == 0 ? 8u : 0u);
-                const int xi = 4 * wi - ax;                                 // interior x of byte 0: mask pixels outside [0, W)
-                if (xi < 0) flags &= 0xFu << (-xi);
-                if (W - xi < 4) flags &= (1u << (W - xi)) - 1;
+        for (int t = tid; t < nTasks; t += FS_THREADS) {
+            const int row = (int)(((uint32_t)t * rcp) >> 20), wi = wFirst + (t - row * wpr);
+            const uint32_t* c = reinterpret_cast<const uint32_t*>(tile + (row + 3) * BW) + wi;
+            const uint32_t Cp = c[-1], C = c[0], Cn = c[1];                 // word -1 of tile row >= 3 is still inside the tile
+            const uint32_t U = *reinterpret_cast<const uint32_t*>(tile + row * BW + 4 * wi);
+            const uint32_t D = *reinterpret_cast<const uint32_t*>(tile + (row + 6) * BW + 4 * wi);
+            const uint32_t L = __funnelshift_r(Cp, C, 8), R = __funnelshift_r(C, Cn, 24);          // pixels x-3 / x+3 of the 4 centres
+            const uint32_t f01 = pretest_x2(__byte_perm(C, 0, 0x4140), __byte_perm(D, 0, 0x4140), __byte_perm(U, 0, 0x4140),
+                __byte_perm(R, 0, 0x4140), __byte_perm(L, 0, 0x4140), th1);
+            const uint32_t f23 = pretest_x2(__byte_perm(C, 0, 0x4342), __byte_perm(D, 0, 0x4342), __byte_perm(U, 0, 0x4342),
+                __byte_perm(R, 0, 0x4342), __byte_perm(L, 0, 0x4342), th1);
+            uint32_t flags = ((f01 & 0xFFFFu) == 0 ? 1u : 0u) | ((f01 >> 16) == 0 ? 2u : 0u) | ((f23 & 0xFFFFu) == 0 ? 4u : 0u) | ((f23 >> 16) == 0 ? 8u : 0u);
+            const int xi = 4 * wi - ax;                                     // interior x of byte 0: mask pixels outside [0, W)
+            if (xi < 0) flags &= 0xFu << (-xi);
+            if (W - xi < 4) flags &= (1u << (W - xi)) - 1;
+            if (flags) {
+                int pos = atomicAdd(&sCount, __popc(flags));
+                const int e = row * BW + 4 * wi;
+                if (flags & 1) list[pos++] = (uint16_t)e;
+                if (flags & 2) list[pos++] = (uint16_t)(e + 1);
+                if (flags & 4) list[pos++] = (uint16_t)(e + 2);
+                if (flags & 8) list[pos] = (uint16_t)(e + 3);
             }
-            if (!__any_sync(0xffffffffu, flags != 0)) continue;
-            const uint32_t m0 = __ballot_sync(0xffffffffu, flags & 1), m1 = __ballot_sync(0xffffffffu, flags & 2);
-            const uint32_t m2 = __ballot_sync(0xffffffffu, flags & 4), m3 = __ballot_sync(0xffffffffu, flags & 8);
-            const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3);
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&sCount, n0 + n1 + n2 + n3);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (flags & 1) list[wbase + __popc(m0 & lt)] = (uint16_t)e;
-            if (flags & 2) list[wbase + n0 + __popc(m1 & lt)] = (uint16_t)(e + 1);
-            if (flags & 4) list[wbase + n0 + n1 + __popc(m2 & lt)] = (uint16_t)(e + 2);
-            if (flags & 8) list[wbase + n0 + n1 + n2 + __popc(m3 & lt)] = (uint16_t)(e + 3);
         }
     }
     __syncthreads();
+    const int n = sCount;
+    const uint8_t* org = tile + 3 * BW;
+    uint8_t* sorg = score + BW;
     // ---- 2. corner strength, two survivors per thread --------------------------------------------------------------
+    for (int i = tid; 2 * i < n; i += FS_THREADS) {
+        const int ea = list[2 * i], eb = list[min(2 * i + 1, n - 1)];
+        const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
+        const int sa = (int)(s & 0xFFFFu), sb = (int)(s >> 16);
+        if (sa > th) sorg[ea] = (uint8_t)(sa - 1);
+        if (sb > th) sorg[eb] = (uint8_t)(sb - 1);
+    }
+    __syncthreads();
+    // ---- 3. NMS over the survivor list, kept corners appended to their cell's list ----------------------------------
     {
-        const int n = sCount;
-        const uint8_t* org = tile + 3 * BW;
-        uint8_t* sorg = score + BW;
-        for (int i = tid; 2 * i < n; i += FS_THREADS) {
-            const int ea = list[2 * i], eb = list[min(2 * i + 1, n - 1)];
-            const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
-            const int sa = (int)(s & 0xFFFFu), sb = (int)(s >> 16);
-            if (sa > th) sorg[ea] = (uint8_t)(sa - 1);
-            if (sb > th) sorg[eb] = (uint8_t)(sb - 1);
+        const int b1 = sC0[1], b2 = sC0[2], b3 = sC0[3];
+        for (int i = tid; i < n; i += FS_THREADS) {
+            const int e = list[i];
+            const int v = sorg[e];
+            if (v) {
+                const int row = e / BW, col = e - row * BW;
+                const int k = (col >= b1) + (col >= b2) + (col >= b3);
+                if (nms_keep(sorg + e, v, BW, col > sC0[k], col < sC0[k + 1] - 1)) {
+                    const int pos = atomicAdd(&sKept[k], 1);
+                    if (pos < keptCap) kept[k * keptCap + pos] = ((uint32_t)e << 8) | (uint32_t)v;
+                }
+            }
         }
     }
     __syncthreads();
-    // ---- 3./4. one warp per cell: NMS + ordered output, minTh fallback ---------------------------------------------
+    // ---- 4./5. one warp per cell: ordered output, minTh fallback ------------------------------------------------------
     if (warp < sd.nCells) {
         const int cellIdx = sd.firstCell + warp;
         const CellDesc cd = P.cells[cellIdx];
-        const int c0 = ax + cd.x0 - sd.x0, cw = cd.w;
+        const int c0 = sC0[warp], cw = cd.w;
         uint32_t* out = P.cellCand + (long long)slot * P.cellSlotTotal + cd.slotOff;
         const int outX0 = cd.x0 + cd.relx, outY0 = cd.y0 + cd.rely;
-        int total = nms_cell(score, BW, c0, cw, h, out, outX0, outY0, lane);
+        uint32_t* myKept = kept + warp * keptCap;
+        int total = min(sKept[warp], keptCap);
         if (total == 0 && P.minTh < th) {
             // no corner at iniTh in this cell, so its score columns are still all zero: rescore the cell at minTh
             const int t2 = P.minTh, npix = cw * h;
             const uint32_t rcpW = ((1u << 20) + cw - 1) / cw;
-            const uint8_t* org = tile + 3 * BW + c0;
-            uint8_t* sorg = score + BW + c0;
             for (int p = lane; p < npix; p += 32) {
                 const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
-                const uint8_t* c = org + y * BW + x;
+                const uint8_t* c = org + y * BW + c0 + x;
                 const int v = c[0], hiT = v + t2, loT = v - t2;
                 const int p0 = c[3 * BW], p8 = c[-3 * BW], p4 = c[3], p12 = c[-3];
                 const bool pass = (((p0 > hiT) | (p8 > hiT)) & ((p4 > hiT) | (p12 > hiT))) | (((p0 < loT) | (p8 < loT)) & ((p4 < loT) | (p12 < loT)));
                 if (pass) {
                     const int s = ring_strength(c, BW);
-                    if (s > t2) sorg[y * BW + x] = (uint8_t)(s - 1);
+                    if (s > t2) sorg[y * BW + c0 + x] = (uint8_t)(s - 1);
                 }
             }
             __syncwarp();
-            total = nms_cell(score, BW, c0, cw, h, out, outX0, outY0, lane);
+            for (int p = lane; p < npix; p += 32) {
+                const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
+                const int e = y * BW + c0 + x;
+                const int v = sorg[e];
+                if (v && nms_keep(sorg + e, v, BW, x > 0, x < cw - 1)) {
+                    const int pos = atomicAdd(&sKept[warp], 1);
+                    if (pos < keptCap) myKept[pos] = ((uint32_t)e << 8) | (uint32_t)v;
+                }
+            }
+            __syncwarp();
+            total = min(sKept[warp], keptCap);
         }
+        emit_cell(myKept, total, BW, c0, out, outX0, outY0, lane);
         if (lane == 0) P.cellCount[(long long)slot * P.nCellsTotal + cellIdx] = total;
     }
 }
@@ -281,11 +275,14 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n)
     (void)pv;
     FastParams P;
     size_t smem = 0;
+    const int keptCap = ((c->maxCellW + 1) / 2) * ((c->maxCellH + 1) / 2);     // strict 8-neighbour maxima: <= 1 per 2x2 block
+    P.keptCap = keptCap;
     for (int l = 0; l < c->L; ++l) {
         P.maps[l] = c->tmFast[l];
         P.BW[l] = (short)c->fastBW[l]; P.BH[l] = (short)c->fastBH[l];
         const int BW = c->fastBW[l], BH = c->fastBH[l];
-        const size_t need = (size_t)align_up(BW * BH, 128) + align_up(BW * (BH - 4), 16) + (size_t)BW * (BH - 6) * sizeof(uint16_t) + 16;
+        const size_t need = (size_t)align_up(BW * BH, 128) + align_up(BW * (BH - 4), 16) + (size_t)align_up(BW * (BH - 6), 8) * sizeof(uint16_t)
+            + (size_t)FS_WARPS * keptCap * sizeof(uint32_t) + 16;
         smem = std::max(smem, need);
     }
     P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
