@@ -120,8 +120,11 @@ extern "C" const char* orbf_status_string(int s)
 
 extern "C" const char* orbf_last_error(const orbf_context* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
 
-static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::vector<CellDesc>& cells, std::vector<StripDesc>& strips)
+static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::vector<CellDesc>& cells, std::vector<StripDesc>& strips,
+    std::vector<TileDesc>& blTiles, std::vector<TileDesc>& rsTiles)
 {
+    int tileW, blurH, blurBW, blurBH, resizeH;
+    orbf_stage_tile_geometry(&tileW, &blurH, &blurBW, &blurBH, &resizeH);
     const orbf_config& g = c->cfg;
     const int L = g.nlevels;
     c->L = L;
@@ -172,6 +175,23 @@ static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::ve
             q.tabY = (int)tab.size(); tab.resize(tab.size() + q.h);
             build_resize_tab(c->lg[l - 1].h, q.h, &tab[q.tabY]);
         } else q.tabX = q.tabY = 0;
+        // destination tiles of the blur (every level) and resize (levels >= 1) stages, and the resize source box
+        for (int y0 = 0; y0 < q.h; y0 += blurH)
+            for (int x0 = 0; x0 < q.w; x0 += tileW) { TileDesc t = { (short)l, (short)x0, (short)y0, 0 }; blTiles.push_back(t); }
+        c->rsTile0[l] = (int)rsTiles.size(); c->rsBW[l] = c->rsBH[l] = 16;
+        if (l > 0) {
+            const ResizeCoef* tx = &tab[q.tabX]; const ResizeCoef* ty = &tab[q.tabY];
+            for (int y0 = 0; y0 < q.h; y0 += resizeH)
+                for (int x0 = 0; x0 < q.w; x0 += tileW) {
+                    TileDesc t = { (short)l, (short)x0, (short)y0, 0 };
+                    rsTiles.push_back(t);
+                    const int xs = tx[x0].ofs & ~15, xe = tx[std::min(x0 + tileW, q.w) - 1].ofs + 2;
+                    const int ys = ty[y0].ofs, ye = ty[std::min(y0 + resizeH, q.h) - 1].ofs + 2;
+                    c->rsBW[l] = std::max(c->rsBW[l], align_up(xe - xs, 16)); c->rsBH[l] = std::max(c->rsBH[l], ye - ys);
+                }
+            if (c->rsBW[l] > 256 || c->rsBH[l] > 256) return ORBF_ERR_GEOMETRY;
+        }
+        c->rsTileN[l] = (int)rsTiles.size() - c->rsTile0[l];
         // FAST cell grid
         const int minB = ORBF_MINB, maxBX = q.w - ORBF_EDGE + 3, maxBY = q.h - ORBF_EDGE + 3;
         const float W = 30;
@@ -258,10 +278,10 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;
-    std::vector<ResizeCoef> tab; std::vector<CellDesc> cells; std::vector<StripDesc> strips;
-    c->tmFastReady = false; c->tm0Base = nullptr; c->tm0Pitch = c->tm0FrameStride = 0; c->tm0Frames = 0;
-    int rc = build_geometry(c, tab, cells, strips);
-    c->nStrips = (int)strips.size();
+    std::vector<ResizeCoef> tab; std::vector<CellDesc> cells; std::vector<StripDesc> strips; std::vector<TileDesc> blTiles, rsTiles;
+    c->tmStaticReady = false; c->tm0Base = nullptr; c->tm0Pitch = c->tm0FrameStride = 0; c->tm0Frames = 0;
+    int rc = build_geometry(c, tab, cells, strips, blTiles, rsTiles);
+    c->nStrips = (int)strips.size(); c->nBlTiles = (int)blTiles.size();
     if (rc != ORBF_OK) { delete c; return rc; }
 
     cudaError_t e = cudaSetDevice(cfg->device);
@@ -294,6 +314,8 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     TRY(dalloc(c, &c->d_resizeTab, tab.size()));
     TRY(dalloc(c, &c->d_cells, cells.size()));
     TRY(dalloc(c, &c->d_strips, strips.size()));
+    TRY(dalloc(c, &c->d_blTiles, blTiles.size()));
+    TRY(dalloc(c, &c->d_rsTiles, rsTiles.size()));
     TRY(dalloc(c, &c->d_lg, (size_t)ORBF_MAX_LEVELS));
     TRY(dalloc(c, &c->d_cellCand, B * c->cellSlotTotal));
     TRY(dalloc(c, &c->d_cellCount, B * c->nCellsTotal));
@@ -331,6 +353,9 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice), "cells")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_strips, strips.data(), strips.size() * sizeof(StripDesc), cudaMemcpyHostToDevice), "strips")) return fail(ORBF_ERR_CUDA);
+    if (!cu(cudaMemcpy(c->d_blTiles, blTiles.data(), blTiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice), "blur tiles")) return fail(ORBF_ERR_CUDA);
+    if (!rsTiles.empty() && !cu(cudaMemcpy(c->d_rsTiles, rsTiles.data(), rsTiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice), "resize tiles"))
+        return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_lg, c->lg, sizeof(LevelGeom) * ORBF_MAX_LEVELS, cudaMemcpyHostToDevice), "lg")) return fail(ORBF_ERR_CUDA);
     { const double neg = -1.0; if (!cu(cudaMemcpy(c->d_depthCov, &neg, sizeof(double), cudaMemcpyHostToDevice), "depthCov")) return fail(ORBF_ERR_CUDA); }
     if (!cu(cudaMemset(c->d_count, 0, B * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
@@ -351,7 +376,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (!c) return ORBF_ERR_ARG;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
+    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_blTiles, c->d_rsTiles, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,
@@ -420,6 +445,37 @@ extern "C" int orbf_keypoint_capacity(const orbf_context* c, int32_t* cap)
 {
     if (!c || !cap) return ORBF_ERR_ARG;
     *cap = c->K;
+    return ORBF_OK;
+}
+
+// (Re-)encodes the TMA descriptors: the ones over the context's own pyramid planes once, the ones over the caller's
+// input plane whenever that plane changes.
+int orbf_refresh_maps(orbf_context* c)
+{
+    int tileW, blurH, blurBW, blurBH, resizeH;
+    orbf_stage_tile_geometry(&tileW, &blurH, &blurBW, &blurBH, &resizeH);
+#define ENC(map, base, lv, frames, pitch, stride, bw, bh)                                                               \
+    do {                                                                                                               \
+        const int r__ = orbf_tma_encode_u8(c, &(map), (base), c->lg[lv].w, c->lg[lv].h, (frames), (pitch), (stride), (bw), (bh)); \
+        if (r__ != ORBF_OK) return r__;                                                                                \
+    } while (0)
+    if (!c->tmStaticReady) {
+        for (int l = 1; l < c->L; ++l) {
+            ENC(c->tmFast[l], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, c->fastBW[l], c->fastBH[l]);
+            ENC(c->tmBlur[l], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, blurBW, blurBH);
+            if (l + 1 < c->L)
+                ENC(c->tmResize[l + 1], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, c->rsBW[l + 1], c->rsBH[l + 1]);
+        }
+        c->tmStaticReady = true;
+    }
+    if (c->tm0Base != c->cur_gray || c->tm0Pitch != c->cur_grayPitch || c->tm0FrameStride != c->cur_grayFrameStride || c->tm0Frames != c->cur_n) {
+        if (!c->cur_gray) return ORBF_ERR_STATE;
+        ENC(c->tmFast[0], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, c->fastBW[0], c->fastBH[0]);
+        ENC(c->tmBlur[0], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, blurBW, blurBH);
+        if (c->L > 1) ENC(c->tmResize[1], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, c->rsBW[1], c->rsBH[1]);
+        c->tm0Base = c->cur_gray; c->tm0Pitch = c->cur_grayPitch; c->tm0FrameStride = c->cur_grayFrameStride; c->tm0Frames = c->cur_n;
+    }
+#undef ENC
     return ORBF_OK;
 }
 

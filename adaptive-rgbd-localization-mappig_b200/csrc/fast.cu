@@ -256,23 +256,10 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
 
 int orbf_launch_fast(orbf_context* c, int slot0, int n)
 {
-    // level-0 map follows the caller's input plane; levels >= 1 are the context's own pyramid planes
-    PyrView pv = orbf_pyr_view(c, false);
-    if (!c->tmFastReady) {
-        for (int l = 1; l < c->L; ++l) {
-            const int r = orbf_tma_encode_u8(c, &c->tmFast[l], c->d_pyr[l], c->lg[l].w, c->lg[l].h, c->B, c->lg[l].pitch, (long long)c->lg[l].plane,
-                c->fastBW[l], c->fastBH[l]);
-            if (r != ORBF_OK) return r;
-        }
-        c->tmFastReady = true;
-    }
-    if (c->tm0Base != c->cur_gray || c->tm0Pitch != c->cur_grayPitch || c->tm0FrameStride != c->cur_grayFrameStride || c->tm0Frames != c->cur_n) {
-        const int r = orbf_tma_encode_u8(c, &c->tmFast[0], c->cur_gray, c->lg[0].w, c->lg[0].h, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride,
-            c->fastBW[0], c->fastBH[0]);
+    {
+        const int r = orbf_refresh_maps(c);
         if (r != ORBF_OK) return r;
-        c->tm0Base = c->cur_gray; c->tm0Pitch = c->cur_grayPitch; c->tm0FrameStride = c->cur_grayFrameStride; c->tm0Frames = c->cur_n;
     }
-    (void)pv;
     FastParams P;
     size_t smem = 0;
     const int keptCap = ((c->maxCellW + 1) / 2) * ((c->maxCellH + 1) / 2);     // strict 8-neighbour maxima: <= 1 per 2x2 block

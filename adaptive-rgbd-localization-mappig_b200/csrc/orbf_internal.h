@@ -47,6 +47,7 @@ struct StripDesc {            // FAST work unit: up to ORBF_STRIP_CELLS adjacent
     int firstCell;            // index of its first cell in the CellDesc table (the others follow)
 };
 #define ORBF_STRIP_CELLS 4
+struct TileDesc { short level, x0, y0, pad; };    // destination tile of the resize / blur stages (pyramid.cu)
 
 struct LevelGeom {
     int w, h, pitch;
@@ -95,8 +96,13 @@ struct orbf_context {
     ResizeCoef* d_resizeTab;
     CellDesc* d_cells;
     StripDesc* d_strips; int nStrips; int fastBW[ORBF_MAX_LEVELS], fastBH[ORBF_MAX_LEVELS];   // TMA box per level (fast.cu)
-    CUtensorMap tmFast[ORBF_MAX_LEVELS]; bool tmFastReady;
-    const void* tm0Base; long long tm0Pitch, tm0FrameStride; int tm0Frames;                  // what the level-0 maps were encoded for
+    TileDesc* d_blTiles; int nBlTiles;                                                       // blur tiles of all levels
+    TileDesc* d_rsTiles; int rsTile0[ORBF_MAX_LEVELS], rsTileN[ORBF_MAX_LEVELS];             // resize tiles per destination level
+    int rsBW[ORBF_MAX_LEVELS], rsBH[ORBF_MAX_LEVELS];                                        // resize source box per destination level
+    // TMA descriptors: FAST / blur read level l, resize reads level l-1; those over the caller's input plane (FAST 0, blur 0,
+    // resize 1) are re-encoded whenever the input pointer / pitch / frame count changes
+    CUtensorMap tmFast[ORBF_MAX_LEVELS], tmBlur[ORBF_MAX_LEVELS], tmResize[ORBF_MAX_LEVELS]; bool tmStaticReady;
+    const void* tm0Base; long long tm0Pitch, tm0FrameStride; int tm0Frames;                  // what the input-plane maps were encoded for
     LevelGeom* d_lg;
     uint32_t* d_cellCand; int* d_cellCount;
     uint32_t* d_cand; int* d_candCount;
@@ -158,6 +164,8 @@ void orbf_prof_end(orbf_context* c, int stage);
 
 // ---- stage launchers (each enqueues on ctx->stream for slots [slot0, slot0+n)) ---------------------
 PyrView orbf_pyr_view(const orbf_context* ctx, bool blurred);
+int orbf_refresh_maps(orbf_context* ctx);
+void orbf_stage_tile_geometry(int* tileW, int* blurH, int* blurBW, int* blurBH, int* resizeH);
 int orbf_launch_pyramid(orbf_context* ctx, int slot0, int n);
 int orbf_launch_blur(orbf_context* ctx, int slot0, int n);
 int orbf_launch_fast(orbf_context* ctx, int slot0, int n);

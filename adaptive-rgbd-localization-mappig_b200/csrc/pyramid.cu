@@ -1,171 +1,230 @@
-// csrc/pyramid.cu — image pyramid (reference ComputePyramid, Features/orbextractor.cpp:833-857) and the
-// 7x7 sigma-2 Gaussian blur (orbextractor.cpp:795-796) as register-blocked stencils (coalesced 32-bit row reads).
+// csrc/pyramid.cu — image pyramid (reference ComputePyramid, Features/orbextractor.cpp:833-857) and the 7x7 sigma-2
+// Gaussian blur (orbextractor.cpp:795-796) as TMA-fed tile stencils: ONE WARP PER TILE, four tiles per CTA.
 //
-// Level l is cv::resize(level l-1, INTER_LINEAR) — OpenCV's fixed-point bilinear: horizontal
-// S[sx]*a0 + S[sx+1]*a1 with 11-bit coefficients, vertical (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2.
-// The 19-px copyMakeBorder frame of the reference is never read downstream and is not materialised.
-// The blur is OpenCV's fixed-point Gaussian: taps [18,34,48,56,48,34,18]/256, horizontal Q8.8 (u16),
-// vertical Q16.16, (v + 32768) >> 16, BORDER_REFLECT_101 at the true level edge.
-// HBM-bound: algorithmic bytes per 640x480 frame = 926,546 rd + 643,332 wr (resize), 950,532 rd + wr (blur).
+// Each warp fetches its source box (tile + halo) with one cp.async.bulk.tensor.3d (UTMALDG) into shared memory, waits
+// on its own mbarrier, and walks down the tile with every lane owning 4 adjacent output columns, so each output row
+// leaves as one coalesced 128-byte store.  Out-of-image box elements arrive as zeros; BORDER_REFLECT_101 is patched
+// into the halo of edge tiles only.  All levels of all frames run in one launch per stage (tile tables).
+//
+// Level l is cv::resize(level l-1, INTER_LINEAR) — OpenCV's fixed-point bilinear: horizontal S[sx]*a0 + S[sx+1]*a1 with
+// 11-bit coefficients (one IDP.2A per pixel and source row), vertical (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2;
+// horizontally interpolated source rows are reused between consecutive output rows.  The 19-px copyMakeBorder frame of
+// the reference is never read downstream and is not materialised.
+// The blur is OpenCV's fixed-point Gaussian: taps [18,34,48,56,48,34,18]/256, horizontal Q8.8, vertical Q16.16,
+// (v + 32768) >> 16 — exact integer arithmetic, so the pass order is free: horizontal pass = 10 IDP.4A per 4 pixels with
+// the taps pre-shifted into byte-coefficient words (no data shifts), vertical pass on a 7-row register ring.
+// HBM-bound by design: algorithmic bytes per 640x480 frame = 926,546 rd + 643,332 wr (resize), 950,532 rd + wr (blur).
 #include "orbf_internal.h"
 
 namespace {
 
-// ---- bilinear resize, register-blocked: a lane owns 4 adjacent dst columns x RS_ROWS dst rows ------------------------
-// The x coefficients (source offset, a0, a1) of the 4 columns are loaded once and reused down the rows; source pixels
-// are read straight through L1 (byte loads: neighbouring lanes hit the same 128-byte lines), the 4 results of a row
-// leave as one aligned 32-bit store.  No shared memory, no barriers.
-constexpr int RS_WARPS = 4, RS_THREADS = RS_WARPS * 32, RS_ROWS = 4, RS_COLS = 128;
+constexpr int TL_W = 128, TL_WARPS = 4, TL_THREADS = TL_WARPS * 32;
+constexpr int BL_H = 35, BL_BW = 160, BL_BH = BL_H + 6, BL_TILE_BYTES = ((BL_BW * BL_BH + 127) / 128) * 128;   // 5 x 7-row ring turns
+constexpr int RS_H = 32;
 
-__global__ void __launch_bounds__(RS_THREADS) resize_kernel(LevelView src, uint8_t* __restrict__ dstBase,
-    long long dstFrameStride, int dstPitch, int dw, int dh, const ResizeCoef* __restrict__ tx,
-    const ResizeCoef* __restrict__ ty, int slot0)
+struct StageParams {
+    CUtensorMap maps[ORBF_MAX_LEVELS];          // source of level l's stage (blur: level l; resize: level l-1)
+    const TileDesc* tiles; int nTiles;
+    uint8_t* dst[ORBF_MAX_LEVELS]; long long dstFrameStride[ORBF_MAX_LEVELS];
+    int dstPitch[ORBF_MAX_LEVELS];
+    short w[ORBF_MAX_LEVELS], h[ORBF_MAX_LEVELS];      // destination size (blur: = source size)
+    short BW[ORBF_MAX_LEVELS], BH[ORBF_MAX_LEVELS];    // source box (resize)
+    int tabX[ORBF_MAX_LEVELS], tabY[ORBF_MAX_LEVELS];
+    const ResizeCoef* tab;
+    int slot0, z0, srcLevel0;                    // z of a slot in maps[l]: slot - z0 when the source is the caller's input plane
+    int tileStride;                              // bytes of shared memory per warp (resize)
+};
+
+// ---- 7x7 Gaussian ------------------------------------------------------------------------------------------------------
+// horizontal 7-tap sums of the 4 pixels whose first byte is byte 4 of the 12-byte window (W0, W1, W2)
+__device__ __forceinline__ void hrow7(const uint32_t* p, uint32_t out[4])
 {
+    const uint32_t W0 = p[0], W1 = p[1], W2 = p[2];
+    out[0] = __dp4a(W0, 0x30221200u, __dp4a(W1, 0x12223038u, 0u));                              // bytes 1..7
+    out[1] = __dp4a(W0, 0x22120000u, __dp4a(W1, 0x22303830u, __dp4a(W2, 0x00000012u, 0u)));      // bytes 2..8
+    out[2] = __dp4a(W0, 0x12000000u, __dp4a(W1, 0x30383022u, __dp4a(W2, 0x00001222u, 0u)));      // bytes 3..9
+    out[3] = __dp4a(W1, 0x38302212u, __dp4a(W2, 0x00122230u, 0u));                              // bytes 4..10
+}
+
+__global__ void __launch_bounds__(TL_THREADS) blur_tile_kernel(const __grid_constant__ StageParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[TL_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = slot0 + blockIdx.z;
-    const uint8_t* sImg = src.base + (long long)slot * src.frameStride;
-    uint8_t* dImg = dstBase + (long long)slot * dstFrameStride;
-    const int xb = blockIdx.x * RS_COLS + lane * 4;
-    const int y0 = (blockIdx.y * RS_WARPS + warp) * RS_ROWS;
-    if (xb >= dw || y0 >= dh) return;
-    int sx0[4], sx1[4], a0[4], a1[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = min(xb + k, dw - 1);                      // columns past the edge recompute the last one (never stored as valid)
-        const ResizeCoef cx = tx[x];
-        sx0[k] = cx.ofs; sx1[k] = min(cx.ofs + 1, src.w - 1); a0[k] = cx.a0; a1[k] = cx.a1;
+    const int tileIdx = blockIdx.x * TL_WARPS + warp;
+    if (tileIdx >= P.nTiles) return;
+    const TileDesc td = P.tiles[tileIdx];
+    const int level = td.level, x0 = td.x0, y0 = td.y0;
+    const int slot = P.slot0 + blockIdx.y;
+    const int w = P.w[level], h = P.h[level];
+    uint8_t* tile = smem + warp * BL_TILE_BYTES;                    // BL_BH x BL_BW; image (x0, y0) at tile [3][16]
+    if (lane == 0) {
+        mbar_init(&bars[warp], 1);
+        mbar_expect_tx(&bars[warp], BL_BW * BL_BH);
+        tma_load_3d(tile, &P.maps[level], x0 - 16, y0 - 3, level == P.srcLevel0 ? slot - P.z0 : slot, &bars[warp]);
     }
+    __syncwarp();
+    mbar_wait(&bars[warp], 0);
+    // BORDER_REFLECT_101 at the true level edges: rows first, then columns (corners inherit both)
+    if (y0 == 0 || y0 + BL_H + 3 > h) {
+        uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
 #pragma unroll
-    for (int r = 0; r < RS_ROWS; ++r) {
-        const int y = y0 + r;
-        if (y >= dh) break;
-        const ResizeCoef cy = ty[y];
-        const uint8_t* r0 = sImg + (long long)cy.ofs * src.pitch;
-        const uint8_t* r1 = sImg + (long long)min(cy.ofs + 1, src.h - 1) * src.pitch;
-        const int b0 = cy.a0, b1 = cy.a1;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int h0 = __ldg(r0 + sx0[k]) * a0[k] + __ldg(r0 + sx1[k]) * a1[k];
-            const int h1 = __ldg(r1 + sx0[k]) * a0[k] + __ldg(r1 + sx1[k]) * a1[k];
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            packed |= (uint32_t)(v & 255) << (8 * k);
+        for (int k = 1; k <= 3; ++k) {
+            if (y0 == 0)
+                for (int i = lane; i < BL_BW / 4; i += 32) t32[(3 - k) * (BL_BW / 4) + i] = t32[(3 + k) * (BL_BW / 4) + i];
+            const int tr = h - 1 + k - y0 + 3, sr = h - 1 - k - y0 + 3;     // image rows h-1+k <- h-1-k
+            if (tr < BL_BH && sr >= 0)
+                for (int i = lane; i < BL_BW / 4; i += 32) t32[tr * (BL_BW / 4) + i] = t32[sr * (BL_BW / 4) + i];
         }
-        *reinterpret_cast<uint32_t*>(dImg + (long long)y * dstPitch + xb) = packed;   // pitch % 128 == 0: aligned, in-plane
+        __syncwarp();
     }
-}
-
-// ---- 7x7 Gaussian, register-blocked, no shared memory ---------------------------------------------------------
-// The fixed-point result (sum_ij k_i k_j p_ij + 32768) >> 16 is exact integer arithmetic, so pass order is free.
-// A lane owns 4 adjacent columns (one aligned 32-bit word per row; the neighbouring words come from __shfl, so a
-// warp reads each row as one coalesced 128-byte segment).  Horizontal pass: two IDP4A per pixel on byte windows
-// cut out with funnel shifts (taps 18,34,48,56 | 48,34,18,0).  Vertical pass: 7-row ring of the 32-bit row sums in
-// registers, walked down a strip of BL_ROWS rows.  BORDER_REFLECT_101 at the true level edge (orbextractor.cpp:796).
-constexpr int BL_WARPS = 4, BL_THREADS = BL_WARPS * 32, BL_ROWS = 16, BL_COLS = 128;
-
-__device__ __forceinline__ int reflect101(int p, int n)
-{
-    if (n == 1) return 0;
-    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
-    return p;
-}
-
-__device__ __forceinline__ uint32_t load_word_reflect(const uint8_t* __restrict__ row, int xw, int w)
-{
-    if (xw >= 0 && xw + 3 < w) return __ldg(reinterpret_cast<const uint32_t*>(row + xw));
-    uint32_t v = 0;
+    if (x0 == 0 || x0 + TL_W + 3 > w) {
+        const int cR = 16 + (w - 1 - x0);
+        for (int r = lane; r < BL_BH; r += 32) {
+            uint8_t* t = tile + r * BL_BW;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + reflect101(xw + k, w)) << (8 * k);
-    return v;
-}
-
-__device__ __forceinline__ void hrow7(uint32_t W1, uint32_t edge, int lane, uint32_t out[4])
-{
-    uint32_t W0 = __shfl_up_sync(0xffffffffu, W1, 1), W2 = __shfl_down_sync(0xffffffffu, W1, 1);
-    if (lane == 0) W0 = edge;
-    if (lane == 31) W2 = edge;
-    const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24), kB = 48u | (34u << 8) | (18u << 16);
-    // output i uses bytes [i-3, i+3]: window A = bytes i-3..i, window B = bytes i+1..i+4 (last tap weight 0)
-    out[0] = __dp4a(__funnelshift_r(W0, W1, 8), kA, __dp4a(__funnelshift_r(W1, W2, 8), kB, 0u));
-    out[1] = __dp4a(__funnelshift_r(W0, W1, 16), kA, __dp4a(__funnelshift_r(W1, W2, 16), kB, 0u));
-    out[2] = __dp4a(__funnelshift_r(W0, W1, 24), kA, __dp4a(__funnelshift_r(W1, W2, 24), kB, 0u));
-    out[3] = __dp4a(W1, kA, __dp4a(W2, kB, 0u));
-}
-
-template <bool INTERIOR>
-__device__ __forceinline__ void blur_strip(const uint8_t* __restrict__ sImg, uint8_t* __restrict__ dImg, int pitch, int dstPitch,
-    int w, int h, int x, int y0, int lane)
-{
-    // stage all BL_ROWS + 6 source rows of the strip first: every load of the strip is in flight at once
-    // (lane 0 / lane 31 also fetch the word left / right of the warp's 128-byte segment)
-    uint32_t w1[BL_ROWS + 6], ed[BL_ROWS + 6];
-    const int xe = (lane == 0) ? x - 4 : x + 4;
-    const bool edgeLane = lane == 0 || lane == 31;
-    if (INTERIOR) {     // warp-uniform: all 32 words of every row of the strip lie inside the level, no row reflection
-        const uint8_t* p = sImg + (long long)(y0 - 3) * pitch + x;
-        // edge word: loaded when it is inside the level; at the level's left / right edge (w % 4 == 0 there) it is the
-        // REFLECT_101 image of the lane's own word: b[-1..-3] = b[1..3] and b[w..w+2] = b[w-2..w-4]
-        const bool loadEdge = edgeLane && xe >= 0 && xe + 3 < w;
-        const uint32_t perm = (lane == 0) ? 0x1230u : 0x0012u;
-#pragma unroll
-        for (int r = 0; r < BL_ROWS + 6; ++r) {
-            w1[r] = __ldg(reinterpret_cast<const uint32_t*>(p));
-            ed[r] = loadEdge ? __ldg(reinterpret_cast<const uint32_t*>(p + (xe - x))) : __byte_perm(w1[r], 0u, perm);
-            p += pitch;
+            for (int k = 1; k <= 3; ++k) {
+                if (x0 == 0) t[16 - k] = t[16 + k];
+                if (cR + k < BL_BW && cR - k >= 0) t[cR + k] = t[cR - k];
+            }
         }
-    } else {
-#pragma unroll 1
-        for (int r = 0; r < BL_ROWS + 6; ++r) {
-            const uint8_t* row = sImg + (long long)reflect101(y0 - 3 + r, h) * pitch;
-            w1[r] = load_word_reflect(row, x, w);
-            ed[r] = edgeLane ? load_word_reflect(row, xe, w) : 0u;
-        }
+        __syncwarp();
     }
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(tile) + 3 + lane;     // words of tile columns 12 + 4*lane ..
+    const int x = x0 + 4 * lane;
+    uint8_t* q = P.dst[level] + (long long)slot * P.dstFrameStride[level] + (long long)y0 * P.dstPitch[level] + x;
+    const int pitch = P.dstPitch[level];
+    const bool colOk = x < w;
     uint32_t ring[7][4];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) hrow7(w1[r], ed[r], lane, ring[r]);
-    uint8_t* q = dImg + (long long)y0 * dstPitch + x;
+    for (int r = 0; r < 6; ++r) hrow7(rowp + r * (BL_BW / 4), ring[r]);
+#pragma unroll 1
+    for (int turn = 0; turn < BL_H / 7; ++turn) {
 #pragma unroll
-    for (int i = 0; i < BL_ROWS; ++i) {
-        hrow7(w1[i + 6], ed[i + 6], lane, ring[(i + 6) % 7]);
-        uint32_t packed = 0;
+        for (int i = 0; i < 7; ++i) {
+            const int row = turn * 7 + i;
+            hrow7(rowp + (row + 6) * (BL_BW / 4), ring[(i + 6) % 7]);
+            uint32_t acc[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = 18u * (ring[i % 7][k] + ring[(i + 6) % 7][k]) + 34u * (ring[(i + 1) % 7][k] + ring[(i + 5) % 7][k])
-                + 48u * (ring[(i + 2) % 7][k] + ring[(i + 4) % 7][k]) + 56u * ring[(i + 3) % 7][k];
-            packed |= ((acc + 32768u) >> 16) << (8 * k);
+            for (int k = 0; k < 4; ++k)
+                acc[k] = 18u * (ring[i % 7][k] + ring[(i + 6) % 7][k]) + 34u * (ring[(i + 1) % 7][k] + ring[(i + 5) % 7][k])
+                    + 48u * (ring[(i + 2) % 7][k] + ring[(i + 4) % 7][k]) + 56u * ring[(i + 3) % 7][k] + 32768u;
+            // acc < 2^24: the rounded result is byte 2 of each accumulator
+            const uint32_t packed = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+            if (colOk && y0 + row < h) *reinterpret_cast<uint32_t*>(q) = packed;
+            q += pitch;
         }
-        if (INTERIOR || (x < w && y0 + i < h)) *reinterpret_cast<uint32_t*>(q) = packed;
-        q += dstPitch;
     }
 }
 
-__global__ void __launch_bounds__(BL_THREADS) blur7_kernel(LevelView src, uint8_t* __restrict__ dstBase,
-    long long dstFrameStride, int dstPitch, int slot0)
+// ---- bilinear resize -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TL_THREADS) resize_tile_kernel(const __grid_constant__ StageParams P)
 {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[TL_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = slot0 + blockIdx.z;
-    const uint8_t* sImg = src.base + (long long)slot * src.frameStride;
-    uint8_t* dImg = dstBase + (long long)slot * dstFrameStride;
-    const int w = src.w, h = src.h;
-    const int xb = blockIdx.x * BL_COLS, x = xb + lane * 4;
-    const int y0 = (blockIdx.y * BL_WARPS + warp) * BL_ROWS;
-    if (y0 >= h) return;
-    const bool interior = (xb + BL_COLS + 4 <= w || xb + BL_COLS == w) && y0 >= 3 && y0 + BL_ROWS + 3 <= h;
-    if (interior) blur_strip<true>(sImg, dImg, src.pitch, dstPitch, w, h, x, y0, lane);
-    else blur_strip<false>(sImg, dImg, src.pitch, dstPitch, w, h, x, y0, lane);
+    const int tileIdx = blockIdx.x * TL_WARPS + warp;
+    if (tileIdx >= P.nTiles) return;
+    const TileDesc td = P.tiles[tileIdx];
+    const int level = td.level, x0 = td.x0, y0 = td.y0;
+    const int slot = P.slot0 + blockIdx.y;
+    const int w = P.w[level], h = P.h[level], BW = P.BW[level], BH = P.BH[level];
+    const ResizeCoef* tx = P.tab + P.tabX[level];
+    const ResizeCoef* ty = P.tab + P.tabY[level];
+    const int xs = tx[x0].ofs & ~15, ys = ty[y0].ofs;               // source box origin (x on a 16-byte boundary)
+    uint8_t* tile = smem + warp * P.tileStride;
+    if (lane == 0) {
+        mbar_init(&bars[warp], 1);
+        mbar_expect_tx(&bars[warp], (uint32_t)(BW * BH));
+        tma_load_3d(tile, &P.maps[level], xs, ys, level == P.srcLevel0 ? slot - P.z0 : slot, &bars[warp]);
+    }
+    // per-lane column coefficients: 4 adjacent destination columns
+    const int x = x0 + 4 * lane;
+    int o[4];
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const ResizeCoef c = tx[min(x + k, w - 1)];                 // columns past the edge recompute the last one (never stored)
+        o[k] = c.ofs - xs;
+        pk[k] = (uint32_t)(uint16_t)c.a0 | ((uint32_t)(uint16_t)c.a1 << 16);
+    }
+    const int wi0 = o[0] >> 2, sh = 8 * (o[0] & 3);
+    uint32_t sel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int d = o[k] - o[0]; sel[k] = (uint32_t)d | ((uint32_t)(d + 1) << 4); }
+    __syncwarp();
+    mbar_wait(&bars[warp], 0);
+
+    const uint8_t* tcol = tile + 4 * wi0;
+#define RS_HROW(r, out)                                                                                             \
+    do {   /* horizontally interpolated row r of the tile, already >> 4 (the vertical pass consumes h >> 4) */      \
+        const uint32_t* p_ = reinterpret_cast<const uint32_t*>(tcol + (r) * BW);                                    \
+        const uint32_t Wa_ = p_[0], Wb_ = p_[1], Wc_ = p_[2];                                                        \
+        const uint32_t T0_ = __funnelshift_r(Wa_, Wb_, sh), T1_ = __funnelshift_r(Wb_, Wc_, sh);  /* 8 bytes from column o[0] */ \
+        _Pragma("unroll") for (int k = 0; k < 4; ++k) out[k] = __dp2a_lo(pk[k], __byte_perm(T0_, T1_, sel[k]), 0u) >> 4; \
+    } while (0)
+    uint8_t* q = P.dst[level] + (long long)slot * P.dstFrameStride[level] + (long long)y0 * P.dstPitch[level] + x;
+    const int pitch = P.dstPitch[level];
+    const bool colOk = x < w;
+    uint32_t hA[4], hB[4];
+    int rowB = -1;                                                   // tile row held in hB
+    const int rows = min(RS_H, h - y0);
+#pragma unroll 1
+    for (int i = 0; i < rows; ++i) {
+        const ResizeCoef cy = ty[y0 + i];
+        const int r = cy.ofs - ys;
+        if (r == rowB) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hA[k] = hB[k];
+        } else RS_HROW(r, hA);
+        RS_HROW(r + 1, hB);                                            // r + 1 is inside the box; past the source edge its weight is 0
+        rowB = r + 1;
+        const uint32_t b0 = (uint32_t)cy.a0 << 16, b1 = (uint32_t)cy.a1 << 16;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (__umulhi(hA[k], b0) + __umulhi(hB[k], b1) + 2u) >> 2;     // (b*(h>>4))>>16 == umulhi(h>>4, b<<16)
+        const uint32_t packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        if (colOk) *reinterpret_cast<uint32_t*>(q) = packed;         // pitch % 128 == 0: aligned, in-plane
+        q += pitch;
+    }
+#undef RS_HROW
+}
+
+void fill_common(orbf_context* c, StageParams& P, int slot0)
+{
+    for (int l = 0; l < c->L; ++l) { P.w[l] = (short)c->lg[l].w; P.h[l] = (short)c->lg[l].h; P.tabX[l] = c->lg[l].tabX; P.tabY[l] = c->lg[l].tabY; }
+    P.tab = c->d_resizeTab; P.slot0 = slot0; P.z0 = c->cur_slot0;
 }
 
 }  // namespace
 
 int orbf_launch_pyramid(orbf_context* c, int slot0, int n)
 {
-    PyrView pv = orbf_pyr_view(c, false);
+    if (c->L < 2) return ORBF_OK;
+    int r = orbf_refresh_maps(c);
+    if (r != ORBF_OK) return r;
+    StageParams P;
+    fill_common(c, P, slot0);
+    P.srcLevel0 = 1;                                                 // level 1 reads the caller's input plane
+    int maxBytes = 0;
     for (int l = 1; l < c->L; ++l) {
-        const LevelGeom& g = c->lg[l];
-        dim3 grid((g.w + RS_COLS - 1) / RS_COLS, (g.h + RS_WARPS * RS_ROWS - 1) / (RS_WARPS * RS_ROWS), n);
-        resize_kernel<<<grid, RS_THREADS, 0, c->stream>>>(pv.lv[l - 1], c->d_pyr[l], (long long)g.plane, g.pitch, g.w, g.h,
-            c->d_resizeTab + g.tabX, c->d_resizeTab + g.tabY, slot0);
+        P.maps[l] = c->tmResize[l];
+        P.dst[l] = c->d_pyr[l]; P.dstFrameStride[l] = (long long)c->lg[l].plane; P.dstPitch[l] = c->lg[l].pitch;
+        P.BW[l] = (short)c->rsBW[l]; P.BH[l] = (short)c->rsBH[l];
+        maxBytes = std::max(maxBytes, align_up(c->rsBW[l] * c->rsBH[l], 128));
+    }
+    P.tileStride = maxBytes;
+    const size_t smem = (size_t)maxBytes * TL_WARPS + 16;            // + slack: a lane reads up to 11 bytes past its last column
+    if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(resize_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return orbf_cuda_fail(c, e, "resize smem attr", __FILE__, __LINE__);
+    }
+    // the chain level l-1 -> l is a true dependency: one launch per level, each covering every frame of the batch
+    for (int l = 1; l < c->L; ++l) {
+        P.tiles = c->d_rsTiles + c->rsTile0[l]; P.nTiles = c->rsTileN[l];
+        dim3 grid((P.nTiles + TL_WARPS - 1) / TL_WARPS, n);
+        resize_tile_kernel<<<grid, TL_THREADS, smem, c->stream>>>(P);
         ORBF_LAUNCH_CHECK(c);
     }
     return ORBF_OK;
@@ -173,12 +232,26 @@ int orbf_launch_pyramid(orbf_context* c, int slot0, int n)
 
 int orbf_launch_blur(orbf_context* c, int slot0, int n)
 {
-    PyrView pv = orbf_pyr_view(c, false);
+    int r = orbf_refresh_maps(c);
+    if (r != ORBF_OK) return r;
+    StageParams P;
+    fill_common(c, P, slot0);
+    P.srcLevel0 = 0; P.tileStride = BL_TILE_BYTES;
     for (int l = 0; l < c->L; ++l) {
-        const LevelGeom& g = c->lg[l];
-        dim3 grid((g.w + BL_COLS - 1) / BL_COLS, (g.h + BL_WARPS * BL_ROWS - 1) / (BL_WARPS * BL_ROWS), n);
-        blur7_kernel<<<grid, BL_THREADS, 0, c->stream>>>(pv.lv[l], c->d_blur[l], (long long)g.plane, g.pitch, slot0);
-        ORBF_LAUNCH_CHECK(c);
+        P.maps[l] = c->tmBlur[l];
+        P.dst[l] = c->d_blur[l]; P.dstFrameStride[l] = (long long)c->lg[l].plane; P.dstPitch[l] = c->lg[l].pitch;
+        P.BW[l] = BL_BW; P.BH[l] = BL_BH;
     }
+    P.tiles = c->d_blTiles; P.nTiles = c->nBlTiles;
+    const size_t smem = (size_t)BL_TILE_BYTES * TL_WARPS;
+    dim3 grid((P.nTiles + TL_WARPS - 1) / TL_WARPS, n);
+    blur_tile_kernel<<<grid, TL_THREADS, smem, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
+}
+
+// geometry constants the context needs to build tile tables and TMA boxes
+void orbf_stage_tile_geometry(int* tileW, int* blurH, int* blurBW, int* blurBH, int* resizeH)
+{
+    *tileW = TL_W; *blurH = BL_H; *blurBW = BL_BW; *blurBH = BL_BH; *resizeH = RS_H;
 }
