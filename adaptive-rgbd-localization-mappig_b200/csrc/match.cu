@@ -3,9 +3,13 @@
 // (reference Features/matcher.cpp:55-66, :23-35); result order = (distance asc, trainIdx asc), which the
 // packed key (dist << 16 | trainIdx) reproduces under unsigned min.
 //
-// Register-tiled POPC/LOP3 kernel, integer-ALU bound (8 POPC32 per descriptor pair), no tensor cores:
-// each thread keeps R query descriptors (R x 8 words) in registers; a warp walks its share of the train
-// descriptors staged in shared memory with broadcast 128-bit loads, so one LDS pair feeds 32*R pairs.
+// Register-tiled POPC/LOP3 kernel, integer-ALU bound, no tensor cores: each thread keeps R query descriptors
+// (R x 8 words) in registers; a warp walks its share of the train descriptors staged in shared memory with
+// broadcast 128-bit loads, so one LDS pair feeds 32*R pairs.  The 256-bit popcount runs through a carry-save
+// adder tree (4 CSAs = 8 LOP3 turn the 8 XOR words into words of weight 1,1,2,4), so a pair costs 4 POPC
+// instead of 8: B200's POPC pipe issues 16 lanes/clk/SM against 64 for LOP3 (profiles/int_pipe_peaks.json), which
+// moves the bound from the POPC pipe (0.5 clk/pair/SM) to the ALU pipe (~0.27).  The running top-2 is only
+// touched when a pair beats the current second best (one ISETP per pair on the common path).
 // Cross-check (north-star extension, quirk Q10) reuses the same distances: per train row the warp takes
 // REDUX.MIN over (dist << 16 | queryIdx) and folds it into a shared / global atomicMin.
 #include "orbf_internal.h"
@@ -19,6 +23,32 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
 {
     m2 = min(m2, max(m1, key));
     m1 = min(m1, key);
+}
+
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Hamming distance of two 256-bit rows, returned as (popc(w1a) + popc(w1b)) and the weight-2 / weight-4 words' counts
+// folded by the caller with IMADs (FMA pipe): d = p1a + p1b + 2*p2 + 4*p4.
+__device__ __forceinline__ uint32_t hamming256_csa(const uint32_t q[8], const uint4& ta, const uint4& tb)
+{
+    const uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, x2 = q[2] ^ ta.z, x3 = q[3] ^ ta.w;
+    const uint32_t x4 = q[4] ^ tb.x, x5 = q[5] ^ tb.y, x6 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
+    const uint32_t s1 = lop3_xor3(x0, x1, x2), c1 = lop3_maj(x0, x1, x2);
+    const uint32_t s2 = lop3_xor3(x3, x4, x5), c2 = lop3_maj(x3, x4, x5);
+    const uint32_t s3 = lop3_xor3(s1, s2, x6), c3 = lop3_maj(s1, s2, x6);
+    const uint32_t s4 = lop3_xor3(c1, c2, c3), c4 = lop3_maj(c1, c2, c3);
+    return (uint32_t)__popc(c4) * 4u + ((uint32_t)__popc(s4) * 2u + (uint32_t)(__popc(s3) + __popc(x7)));
 }
 
 template <bool CROSS>
@@ -53,6 +83,10 @@ __global__ void __launch_bounds__(KN_THREADS) knn2_kernel(MatchSet ms, int K)
             for (int i = 0; i < 8; ++i) q[r][i] = 0;
         }
     }
+    static_assert(KN_R == 4, "cross-check reduction is written for 4 queries per thread");
+    uint32_t qkey[KN_R];                    // query index = low half of the reverse key; rows past nq get a key above every valid one
+#pragma unroll
+    for (int r = 0; r < KN_R; ++r) { const int qi = qBase + r * 32 + lane; qkey[r] = qi < nq ? (uint32_t)qi : 0xF0000000u; }   // d << 16 <= 0x01000000: no wrap
     for (int c0 = 0; c0 < nt; c0 += KN_CHUNK) {
         const int cn = min(KN_CHUNK, nt - c0);
         __syncthreads();
@@ -62,20 +96,23 @@ __global__ void __launch_bounds__(KN_THREADS) knn2_kernel(MatchSet ms, int K)
         __syncthreads();
         for (int j = warp; j < cn; j += KN_WARPS) {
             const uint4 ta = reinterpret_cast<const uint4*>(sT)[2 * j], tb = reinterpret_cast<const uint4*>(sT)[2 * j + 1];
-            uint32_t kmin = KEY_NONE;
+            const uint32_t idx = (uint32_t)(c0 + j);
+            uint32_t key[KN_R];
 #pragma unroll
-            for (int r = 0; r < KN_R; ++r) {
-                const int d = __popc(q[r][0] ^ ta.x) + __popc(q[r][1] ^ ta.y) + __popc(q[r][2] ^ ta.z) + __popc(q[r][3] ^ ta.w)
-                    + __popc(q[r][4] ^ tb.x) + __popc(q[r][5] ^ tb.y) + __popc(q[r][6] ^ tb.z) + __popc(q[r][7] ^ tb.w);
-                top2_insert(m1[r], m2[r], ((uint32_t)d << 16) | (uint32_t)(c0 + j));
-                if (CROSS) {
-                    const int qi = qBase + r * 32 + lane;
-                    if (qi < nq) kmin = min(kmin, ((uint32_t)d << 16) | (uint32_t)qi);
-                }
+            for (int r = 0; r < KN_R; ++r) key[r] = hamming256_csa(q[r], ta, tb) * 65536u + idx;
+            // train rows arrive in ascending index order, so a pair enters the top-2 iff its key is below the second best
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < KN_R; ++r) any |= key[r] < m2[r];
+            if (any) {
+#pragma unroll
+                for (int r = 0; r < KN_R; ++r) top2_insert(m1[r], m2[r], key[r]);
             }
             if (CROSS) {
-                const uint32_t wmin = __reduce_min_sync(0xffffffffu, kmin);
-                if (lane == 0 && wmin != KEY_NONE) atomicMin(&sRev[j], wmin);
+                // per train row: best query of this warp's 128 (rows past nq carry an all-ones query key)
+                const uint32_t a = min(key[0] - idx + qkey[0], key[1] - idx + qkey[1]), b = min(key[2] - idx + qkey[2], key[3] - idx + qkey[3]);
+                const uint32_t wmin = __reduce_min_sync(0xffffffffu, min(a, b));
+                if (lane == 0 && wmin < 0xF0000000u) atomicMin(&sRev[j], wmin);
             }
         }
         if (CROSS) {
