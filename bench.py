@@ -267,18 +267,22 @@ def main():
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
         hbm_stages = {k: stage_ms[k] for k in STAGE_BYTES}
         dom = max(hbm_stages, key=hbm_stages.get)
-        launches_per_step = {"pyr_resize": 7, "fast_cell": 1, "blur7": 8}[dom]
+        launches_per_step = {"pyr_resize": 7, "fast_cell": 1, "blur7": 1}[dom]
         bytes_per_launch = STAGE_BYTES[dom] * F / launches_per_step
         achieved = STAGE_BYTES[dom] * F / (stage_ms[dom] * 1e-3) / 1e9
-        traffic = None
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant stage from the committed ncu --set full capture
+        # (profiles/traffic.json: bytes per frame, measured at 128 frames per launch), scaled to this run's launch
+        traffic = None; traffic_note = None
         tfile = ROOT / "profiles" / "traffic.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get(dom)
+                tj = json.loads(tfile.read_text())
+                traffic = tj[dom]["dram_bytes_per_frame"] * F / launches_per_step
+                traffic_note = tj["source"]
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step,
+                    "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step,
                     "avg_launch_ms": stage_ms[dom] / launches_per_step, "peak_source": peak_src,
                     "stage_ms_per_step": stage_ms,
                     "whole_path": {"algorithmic_bytes_per_frame": FRAME_BYTES, "achieved_GBps": FRAME_BYTES * F / (ms * 1e-3) / 1e9,
