@@ -199,12 +199,14 @@ def test_cuda_ransac_matches_goldens(ob, g_ransac, tag):
     ctx = ob.Context(max_frames=1)
     try:
         r = ctx.ransac_iterate(src, dst, matches, seed=42)
-        assert r["good_sorted"].tobytes() == g_ransac[tag + "_good_sorted"].tobytes()
-        assert np.array_equal(r["sample_table"], g_ransac[tag + "_sample_table"])
+        if r["n_good"] >= 20:    # below minInlierTh Ransac::Iterate returns before it sorts or samples (ransac.cpp:191-192)
+            assert r["good_sorted"].tobytes() == g_ransac[tag + "_good_sorted"].tobytes()
+            assert np.array_equal(r["sample_table"], g_ransac[tag + "_sample_table"])
         assert r["inliers"].tobytes() == g_ransac[tag + "_inliers"].tobytes()
         assert np.abs(r["T12"] - g_ransac[tag + "_T12"]).max() <= POSE_TOL
         assert [int(r["ok"]), r["n_good"], r["real_iters"], r["valid_iters"], int(r["used_identity"])] == list(g_ransac[tag + "_scalars"])
-        assert np.array_equal(r["hyp"]["n_refined"], g_ransac[tag + "_hyp_n"])
+        n = r["real_iters"]      # the GPU scores whole waves of hypotheses; only the rows the sequential loop consumed are defined
+        assert np.array_equal(r["hyp"]["n_refined"][:n], g_ransac[tag + "_hyp_n"][:n])
     finally:
         ctx.close()
 
