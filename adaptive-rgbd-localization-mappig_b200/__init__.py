@@ -339,6 +339,10 @@ class Context:
         self._chk(lib().orbf_kfdb_device_buffers(self._h, C.byref(d), C.byref(cnt), C.byref(rows), C.byref(n)), "kfdb_device_buffers")
         return d.value, cnt.value, rows.value, n.value
 
+    def kfdb_attach_device(self, d_desc_ptr, d_counts_ptr, n_kf):
+        self._chk(lib().orbf_kfdb_attach_device(self._h, C.c_void_p(d_desc_ptr) if d_desc_ptr else None,
+                                                C.c_void_p(d_counts_ptr) if d_counts_ptr else None, n_kf), "kfdb_attach_device")
+
     def kfdb_match(self, q, kf0, nkf, ratio):
         q = np.ascontiguousarray(q, np.uint8)
         o = [np.zeros((nkf, len(q)), np.int32) for _ in range(4)]; surv = np.zeros(nkf, np.int32)

@@ -345,7 +345,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     TRY(dalloc(c, &c->d_depthCov, 1));
     c->d_samples = nullptr; c->d_hyp = nullptr;
     c->d_qdesc = c->d_tdesc = nullptr; c->d_sxyz = c->d_txyz = nullptr;
-    c->d_kfDesc = nullptr; c->d_kfCount = nullptr;
+    c->d_kfDesc = nullptr; c->d_kfCount = nullptr; c->d_kfExtDesc = nullptr; c->d_kfExtCount = nullptr; c->kfExtN = 0;
     c->d_pts = nullptr; c->ptsCap = 0; c->d_userSamples = nullptr; c->userSamplesCap = 0; c->d_kabsch = nullptr; c->kabschCap = 0;
     c->d_kfKnn = nullptr; c->d_kfSurv = nullptr; c->d_kfPairs = nullptr; c->d_kfQCount = nullptr; c->kfOutCap = 0;
     c->h_kp = nullptr; c->h_desc = nullptr; c->h_xyz = nullptr; c->h_counts = nullptr;

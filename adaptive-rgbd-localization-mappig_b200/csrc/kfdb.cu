@@ -58,6 +58,17 @@ extern "C" int orbf_kfdb_add_host(orbf_context* c, int32_t kf, const uint8_t* de
     return ORBF_OK;
 }
 
+// Match against a caller-owned store instead (e.g. the NCCL all-gather of every rank's shard): same [n_kf][K][32] + [n_kf]
+// layout.  The context does not take ownership; attach NULL to return to its own store.
+extern "C" int orbf_kfdb_attach_device(orbf_context* c, const uint8_t* d_desc, const int32_t* d_counts, int32_t n_kf)
+{
+    CTX_ENTER(c);
+    if ((d_desc == nullptr) != (d_counts == nullptr) || (d_desc && n_kf < 1)) return ORBF_ERR_ARG;
+    if (d_desc && ((uintptr_t)d_desc & 15)) return ORBF_ERR_ALIGNMENT;
+    c->d_kfExtDesc = d_desc; c->d_kfExtCount = d_counts; c->kfExtN = d_desc ? n_kf : 0;
+    return ORBF_OK;
+}
+
 extern "C" int orbf_kfdb_device_buffers(orbf_context* c, uint8_t** d_desc, int32_t** d_counts, int32_t* rows_per_kf, int32_t* n_kf)
 {
     if (!c) return ORBF_ERR_ARG;
@@ -72,7 +83,8 @@ extern "C" int orbf_kfdb_match(orbf_context* c, const uint8_t* q, int32_t nq, in
     int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors)
 {
     CTX_ENTER(c);
-    if (!q || nq < 1 || nq > c->K || kf0 < 0 || nkf < 1 || kf0 + nkf > c->kfCap) return ORBF_ERR_ARG;
+    const bool ext = c->d_kfExtDesc != nullptr;
+    if (!q || nq < 1 || nq > c->K || kf0 < 0 || nkf < 1 || kf0 + nkf > (ext ? c->kfExtN : c->kfCap)) return ORBF_ERR_ARG;
     if (nkf > c->kfOutCap) {
         if (c->d_kfKnn) cudaFree(c->d_kfKnn);
         if (c->d_kfSurv) cudaFree(c->d_kfSurv);
@@ -100,8 +112,8 @@ extern "C" int orbf_kfdb_match(orbf_context* c, const uint8_t* q, int32_t nq, in
     ORBF_CUDA(c, cudaMemcpyAsync(c->d_kfQCount, &nq, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     MatchSet ms;
-    ms.qdesc = c->d_qdesc; ms.tdesc = c->d_kfDesc; ms.qStride = 0; ms.tStride = (long long)c->K * 32;
-    ms.qCounts = c->d_kfQCount; ms.tCounts = c->d_kfCount; ms.pairs = c->d_kfPairs; ms.pair0 = 0; ms.nq = nq; ms.nt = 0;
+    ms.qdesc = c->d_qdesc; ms.tdesc = ext ? c->d_kfExtDesc : c->d_kfDesc; ms.qStride = 0; ms.tStride = (long long)c->K * 32;
+    ms.qCounts = c->d_kfQCount; ms.tCounts = ext ? c->d_kfExtCount : c->d_kfCount; ms.pairs = c->d_kfPairs; ms.pair0 = 0; ms.nq = nq; ms.nt = 0;
     ms.knn = c->d_kfKnn; ms.rev = nullptr; ms.matches = nullptr; ms.matchCount = c->d_kfSurv;
     TRY(orbf_launch_knn2(c, ms, nkf, false));
     TRY(orbf_launch_match_select(c, ms, nkf, ratio, false));

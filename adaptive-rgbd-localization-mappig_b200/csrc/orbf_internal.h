@@ -140,6 +140,7 @@ struct orbf_context {
 
     // keyframe store
     uint8_t* d_kfDesc; int* d_kfCount; int kfCap;
+    const uint8_t* d_kfExtDesc; const int* d_kfExtCount; int kfExtN;   // caller-owned store (orbf_kfdb_attach_device)
     uint32_t* d_kfKnn; int* d_kfSurv; int* d_kfPairs; int* d_kfQCount; int kfOutCap;
 };
 

@@ -188,6 +188,9 @@ int orbf_kfdb_add_from_slot(orbf_context* ctx, int32_t kf, int32_t slot);
 int orbf_kfdb_add_host(orbf_context* ctx, int32_t kf, const uint8_t* desc, int32_t n);
 int orbf_kfdb_device_buffers(orbf_context* ctx, uint8_t** d_desc, int32_t** d_counts, int32_t* rows_per_kf,
     int32_t* n_kf);
+/* Match against a caller-owned device store with the same layout ([n_kf][rows_per_kf][32] u8 + [n_kf] i32) — the
+ * NCCL all-gather of every rank's shard (BASELINE config 5).  Not owned by the context; NULL detaches.           */
+int orbf_kfdb_attach_device(orbf_context* ctx, const uint8_t* d_desc, const int32_t* d_counts, int32_t n_kf);
 /* query (host, nq x 32) against keyframes [kf0, kf0+nkf): per keyframe top-2 per query and the number of
  * ratio survivors (out arrays sized nkf x nq, counts sized nkf).                                      */
 int orbf_kfdb_match(orbf_context* ctx, const uint8_t* q, int32_t nq, int32_t kf0, int32_t nkf, float ratio,

@@ -1,0 +1,392 @@
+// include/orbfront_host.hpp — C++ host mirror of the reference's operator interface for the hot path, header-only,
+// on top of the C ABI in orbfront.h (liborbfront_b200.so).  Same class names, method names, argument meaning and
+// error behaviour as the reference, so the reference's call sites compile against it unchanged:
+//
+//   ORBextractor   Features/orbextractor.h:24-84     ctor, operator(), detect/compute/detectAndCompute, Get* getters
+//   Extractor      Features/extractor.h:6-48         Extract(), mNorm (ORB_SLAM2 route; the OpenCV-contrib routes are out of scope)
+//   Frame          Core/frame.h:82-87, frame.cpp:135-170   mvKeys / mvKeysUn / mvKeys3Dc / mvuRight / mDescriptors / N, ExtractFeatures()
+//   Matcher        Features/matcher.h:10-18          Matcher(nnratio), KnnMatch(Frame&, Frame&, matches), DescriptorDistance
+//   Ransac         Odometry/ransac.h:13-69           ctor, setters, Iterate(F1, F2, m12), rmse / mvInliers / mT12
+//   Kabsch         Odometry/kabsch.h:6-15            Compute(setA, setB)
+//   Odometry       Odometry/odometry.h:24            Compute(F1, F2, matches), RANSAC strategy
+//
+// Types: with OpenCV present (define ORBF_WITH_OPENCV) cv::KeyPoint / cv::DMatch / cv::Point3f / cv::Mat are used directly
+// (orbf_keypoint and orbf_dmatch have their exact layout); without it the PODs below stand in.  Eigen is never required:
+// Matrix4f is a 16-float row-major POD with operator()(r, c) (INTEGRATION.md shows the one-line Eigen::Map).
+// Every object shares one process-wide device context (Runtime), created on first use: Matcher is constructed per call on
+// the reference's stack (System/tracking.cpp:197), so its constructor allocates nothing.
+// No CPU fallback: without a CUDA device the first call throws orbf::Error(ORBF_ERR_CUDA).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "orbfront.h"
+
+#ifdef ORBF_WITH_OPENCV
+#include <opencv2/core.hpp>
+#endif
+
+namespace orbf {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& what) : std::runtime_error(what + ": " + orbf_status_string(s)), status(s) {}
+};
+
+#ifdef ORBF_WITH_OPENCV
+using KeyPoint = cv::KeyPoint;
+using DMatch = cv::DMatch;
+using Point3f = cv::Point3f;
+#else
+struct Point2f { float x, y; };
+struct Point3f { float x, y, z; Point3f(float a = 0, float b = 0, float c = 0) : x(a), y(b), z(c) {} };
+struct KeyPoint { Point2f pt; float size, angle, response; int octave, class_id; };             // cv::KeyPoint, 28 bytes
+struct DMatch {                                                                              // cv::DMatch, 16 bytes
+    int queryIdx, trainIdx, imgIdx; float distance;
+    bool operator<(const DMatch& m) const { return distance < m.distance; }
+};
+#endif
+static_assert(sizeof(KeyPoint) == sizeof(orbf_keypoint) && sizeof(DMatch) == sizeof(orbf_dmatch), "POD mirrors must match the C ABI");
+
+// Row-major image / descriptor matrix view-or-owner (the subset of cv::Mat the path touches).
+template <typename T>
+struct Mat_ {
+    int rows = 0, cols = 0; size_t step = 0;          // step in elements
+    T* data = nullptr; std::vector<T> owned;
+    Mat_() {}
+    Mat_(const Mat_& o) { *this = o; }
+    Mat_& operator=(const Mat_& o)
+    {
+        rows = o.rows; cols = o.cols; step = o.step; owned = o.owned;
+        data = o.owned.empty() ? o.data : owned.data();      // owners deep-copy, views stay views
+        return *this;
+    }
+    Mat_(int r, int c) { create(r, c); }
+    Mat_(int r, int c, T* external, size_t stepElems = 0) : rows(r), cols(c), step(stepElems ? stepElems : (size_t)c), data(external) {}
+    void create(int r, int c) { rows = r; cols = c; step = (size_t)c; owned.assign((size_t)r * c, T()); data = owned.data(); }
+    void release() { rows = cols = 0; step = 0; owned.clear(); data = nullptr; }
+    bool empty() const { return rows == 0 || cols == 0 || !data; }
+    T* ptr(int r) { return data + (size_t)r * step; }
+    const T* ptr(int r) const { return data + (size_t)r * step; }
+};
+using Mat8u = Mat_<uint8_t>;
+using Mat16u = Mat_<uint16_t>;
+
+struct Matrix4f {                                      // row-major; Eigen::Map<Eigen::Matrix<float,4,4,Eigen::RowMajor>>(m) on the Eigen side
+    float m[16];
+    Matrix4f() { setIdentity(); }
+    void setIdentity() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.f : 0.f; }
+    float& operator()(int r, int c) { return m[4 * r + c]; }
+    float operator()(int r, int c) const { return m[4 * r + c]; }
+};
+
+// ---- process-wide device context ---------------------------------------------------------------------------------------
+class Runtime {
+public:
+    // (Re)creates the shared context when the extractor parameters or frame size change; cheap otherwise.
+    static orbf_context* Get(int width, int height, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh)
+    {
+        Runtime& r = inst();
+        std::lock_guard<std::mutex> g(r.mu);
+        orbf_config c;
+        orbf_default_config(&c);
+        c.width = width; c.height = height; c.nfeatures = nfeatures; c.scale_factor = scaleFactor; c.nlevels = nlevels;
+        c.ini_th_fast = iniTh; c.min_th_fast = minTh; c.max_frames = 2; c.max_pairs = 2; c.device = r.device;
+        if (r.ctx && std::memcmp(&c, &r.cfg, sizeof(c)) == 0) return r.ctx;
+        if (r.ctx) { orbf_destroy(r.ctx); r.ctx = nullptr; }
+        orbf_context* h = nullptr;
+        const int rc = orbf_create(&c, &h);
+        if (rc != ORBF_OK) {
+            const std::string detail = h ? orbf_last_error(h) : "";
+            if (h) orbf_destroy(h);
+            throw Error(rc, "orbf_create " + detail);
+        }
+        r.ctx = h; r.cfg = c;
+        return h;
+    }
+    // The context of the last extractor configuration (Matcher / Ransac / Kabsch do not depend on the image geometry).
+    static orbf_context* Current()
+    {
+        Runtime& r = inst();
+        { std::lock_guard<std::mutex> g(r.mu); if (r.ctx) return r.ctx; }
+        return Get(640, 480, 1000, 1.2f, 8, 20, 7);      // Utils/common.h:77, Features/extractor.cpp:86
+    }
+    static void SetDevice(int dev) { inst().device = dev; }
+    static void Shutdown() { Runtime& r = inst(); std::lock_guard<std::mutex> g(r.mu); if (r.ctx) { orbf_destroy(r.ctx); r.ctx = nullptr; } }
+    static std::mutex& Lock() { return inst().call; }    // serialises calls: a context is thread-safe per handle, not per call
+private:
+    static Runtime& inst() { static Runtime r; return r; }
+    ~Runtime() { if (ctx) orbf_destroy(ctx); }
+    orbf_context* ctx = nullptr; orbf_config cfg; int device = 0; std::mutex mu, call;
+};
+
+inline void check(int rc, const char* what) { if (rc != ORBF_OK) throw Error(rc, what); }
+
+// ---- ORBextractor ------------------------------------------------------------------------------------------------------
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures_, float scaleFactor_, int nlevels_, int iniThFAST_, int minThFAST_)
+        : nfeatures(nfeatures_), scaleFactor(scaleFactor_), nlevels(nlevels_), iniThFAST(iniThFAST_), minThFAST(minThFAST_)
+    {
+        // scale tables as in orbextractor.cpp:346-381 (float * double(scaleFactor) -> float); device tables are identical
+        mvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+        mvScaleFactor[0] = 1.0f; mvLevelSigma2[0] = 1.0f;
+        for (int i = 1; i < nlevels; i++) {
+            mvScaleFactor[i] = (float)((double)mvScaleFactor[i - 1] * (double)scaleFactor_);
+            mvLevelSigma2[i] = mvScaleFactor[i] * mvScaleFactor[i];
+        }
+        for (int i = 0; i < nlevels; i++) { mvInvScaleFactor[i] = 1.0f / mvScaleFactor[i]; mvInvLevelSigma2[i] = 1.0f / mvLevelSigma2[i]; }
+    }
+
+    // Compute the ORB features and descriptors on an image.  Mask is ignored, as in the reference (orbextractor.h:36).
+    void operator()(const Mat8u& image, const Mat8u& /*mask*/, std::vector<KeyPoint>& keypoints, Mat8u& descriptors)
+    {
+        if (image.empty()) return;                                           // orbextractor.cpp:758-759: outputs untouched
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        orbf_context* ctx = Runtime::Get(image.cols, image.rows, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST);
+        int cap = 0, n = 0;
+        check(orbf_keypoint_capacity(ctx, &cap), "orbf_keypoint_capacity");
+        keypoints.resize((size_t)cap);
+        std::vector<uint8_t> desc((size_t)cap * 32);
+        check(orbf_extract(ctx, image.data, image.cols, image.rows, (int)image.step, reinterpret_cast<orbf_keypoint*>(keypoints.data()),
+                  desc.data(), cap, &n), "orbf_extract");
+        keypoints.resize((size_t)n);
+        if (n == 0) { descriptors.release(); return; }                       // orbextractor.cpp:776-777
+        descriptors.create(n, 32);
+        std::memcpy(descriptors.data, desc.data(), (size_t)n * 32);
+        lastW = image.cols; lastH = image.rows;
+    }
+    void detectAndCompute(const Mat8u& image, const Mat8u& mask, std::vector<KeyPoint>& keypoints, Mat8u& descriptors,
+        bool /*useProvidedKeypoints*/ = false) { (*this)(image, mask, keypoints, descriptors); }      // orbextractor.cpp:828-831
+    void detect(const Mat8u& image, std::vector<KeyPoint>& keypoints, const Mat8u& mask = Mat8u()) { Mat8u d; (*this)(image, mask, keypoints, d); }
+    void compute(const Mat8u& image, std::vector<KeyPoint>& keypoints, Mat8u& descriptors) { (*this)(image, Mat8u(), keypoints, descriptors); }
+
+    int GetLevels() { return nlevels; }
+    float GetScaleFactor() { return (float)scaleFactor; }
+    std::vector<float> GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    // mvImagePyramid[level] of the last extracted image (public member in the reference, orbextractor.h:57); fetched on demand
+    Mat8u ImagePyramidLevel(int level, bool blurred = false)
+    {
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        orbf_context* ctx = Runtime::Get(lastW, lastH, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST);
+        std::vector<int32_t> w(nlevels), h(nlevels);
+        check(orbf_get_tables(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, w.data(), h.data()), "orbf_get_tables");
+        Mat8u m(h[level], w[level]);
+        check(orbf_pyramid_level(ctx, 0, level, blurred ? 1 : 0, m.data, w[level]), "orbf_pyramid_level");
+        return m;
+    }
+
+protected:
+    int nfeatures; double scaleFactor; int nlevels, iniThFAST, minThFAST;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    int lastW = 640, lastH = 480;
+};
+
+// ---- Extractor facade ----------------------------------------------------------------------------------------------------
+enum { NORM_HAMMING = 6 };                                // cv::NORM_HAMMING
+class Extractor {
+public:
+    enum eAlgorithm { ORB = 0, ORB_SLAM2, FAST, GFTT, STAR, BRISK, FREAK, BRIEF, LATCH, SURF, SIFT };
+    enum eMode { NORMAL = 0, ADAPTIVE };
+    eAlgorithm mDetectorAlgorithm, mDescriptorAlgorithm; eMode mMode;
+
+    Extractor(const eAlgorithm& detector = ORB_SLAM2, const eAlgorithm& descriptor = ORB_SLAM2, const eMode& mode = NORMAL, int nFeatures = 1000)
+        : mDetectorAlgorithm(detector), mDescriptorAlgorithm(descriptor), mMode(mode)
+    {
+        // the reference terminates on an unknown enum (extractor.cpp:27,108,132); the OpenCV-contrib routes are out of scope here
+        if (detector != ORB_SLAM2 || descriptor != ORB_SLAM2) throw std::invalid_argument("orbf::Extractor: only the ORB_SLAM2 route runs on the GPU");
+        mpDetector.reset(new ORBextractor(nFeatures, 1.2f, 8, 20, 7));       // extractor.cpp:86
+        mNorm() = NORM_HAMMING;                                              // defaultNorm() of ORB (extractor.cpp:35)
+    }
+    void Extract(const Mat8u& image, const Mat8u& mask, std::vector<KeyPoint>& keypoints, Mat8u& descriptors)
+    {
+        mpDetector->detectAndCompute(image, mask, keypoints, descriptors);  // extractor.cpp:41-42
+    }
+    static int& mNorm() { static int n = NORM_HAMMING; return n; }
+    ORBextractor* detector() { return mpDetector.get(); }
+private:
+    std::unique_ptr<ORBextractor> mpDetector;
+};
+
+// ---- Frame: the storage the path reads and writes ----------------------------------------------------------------------
+struct Calibration {                                      // Utils/common.h:35-38,67,71 (FR1)
+    float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f, mbf = 40.0f, depthFactor = 1.0f / 5000.0f;
+};
+
+class Frame {
+public:
+    Frame() {}
+    Frame(const Mat8u& imGray, const Mat16u& imDepthRaw, double timestamp = 0.0) : mImGray(imGray), mImDepthRaw(imDepthRaw), mTimestamp(timestamp) {}
+
+    // Frame::ExtractFeatures (frame.cpp:135-170): extract, undistort (k1 == 0 => mvKeysUn = mvKeys), depth gather, unprojection
+    void ExtractFeatures(Extractor* pExtractor)
+    {
+        pExtractor->Extract(mImGray, Mat8u(), mvKeys, mDescriptors);
+        N = mvKeys.size();
+        mvKeysUn = mvKeys;
+        mvKeys3Dc.assign(N, Point3f(0, 0, 0));
+        mvuRight.assign(N, -1.f);
+        const Calibration K;
+        const float invfx = 1.0f / K.fx, invfy = 1.0f / K.fy;
+        for (size_t i = 0; i < N; ++i) {
+            const KeyPoint& kp = mvKeys[i];
+            const int v = (int)kp.pt.y, u = (int)kp.pt.x;                    // float -> int truncation (frame.cpp:155)
+            if (mImDepthRaw.empty() || u < 0 || v < 0 || u >= mImDepthRaw.cols || v >= mImDepthRaw.rows) continue;
+            const float z = (float)mImDepthRaw.ptr(v)[u] * K.depthFactor;    // depth image converted with depthFactor (frame.cpp:24)
+            if (z > 0) {
+                mvuRight[i] = kp.pt.x - K.mbf / z;
+                const float x = (kp.pt.x - K.cx) * z * invfx;                // products only: nothing for an FMA to contract (quirk Q4)
+                const float y = (kp.pt.y - K.cy) * z * invfy;
+                mvKeys3Dc[i] = Point3f(x, y, z);
+            }
+        }
+    }
+
+    Mat8u mImGray; Mat16u mImDepthRaw; double mTimestamp = 0.0;
+    std::vector<KeyPoint> mvKeys, mvKeysUn;
+    std::vector<Point3f> mvKeys3Dc;
+    std::vector<float> mvuRight;
+    Mat8u mDescriptors;
+    size_t N = 0;
+};
+
+// ---- Matcher -----------------------------------------------------------------------------------------------------------
+class Matcher {
+public:
+    Matcher(float nnratio = 0.6f) : mfNNratio(nnratio), TH_LOW(50), TH_HIGH(100) {}     // matcher.cpp:10-21; allocates nothing
+
+    static double DescriptorDistance(const Mat8u& a, const Mat8u& b)                    // matcher.cpp:355-358
+    {
+        int d = 0;
+        check(orbf_descriptor_distance(a.data, b.data, a.cols, &d), "orbf_descriptor_distance");
+        return (double)d;
+    }
+
+    // kNN-2 + Lowe ratio on the frames' descriptors (matcher.cpp:55-66).  The reference then filters on Landmark* state
+    // (matcher.cpp:70-83: F1 holds a live landmark at queryIdx, F2's slot is free) — pointer-graph bookkeeping that stays on
+    // the host: pass it as `accept`; without it every ratio survivor is returned, in query order.
+    template <typename Accept>
+    size_t KnnMatch(Frame& pF1, Frame& pF2, std::vector<DMatch>& vMatches12, Accept accept, bool crossCheck = false)
+    {
+        vMatches12.clear();
+        const int nq = pF1.mDescriptors.rows, nt = pF2.mDescriptors.rows;
+        if (nq == 0 || nt < 2) return 0;                                     // matchesKnn[i][1] needs two train rows (matcher.cpp:65)
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        orbf_context* ctx = Runtime::Current();
+        std::vector<DMatch> all((size_t)nq);
+        int n = 0;
+        check(orbf_knn_match(ctx, pF1.mDescriptors.data, nq, pF2.mDescriptors.data, nt, mfNNratio, crossCheck ? 1 : 0,
+                  reinterpret_cast<orbf_dmatch*>(all.data()), nq, &n), "orbf_knn_match");
+        for (int i = 0; i < n; ++i) if (accept(all[i])) vMatches12.push_back(all[i]);
+        return vMatches12.size();
+    }
+    size_t KnnMatch(Frame& pF1, Frame& pF2, std::vector<DMatch>& vMatches12, bool crossCheck = false)
+    {
+        return KnnMatch(pF1, pF2, vMatches12, [](const DMatch&) { return true; }, crossCheck);
+    }
+
+private:
+    float mfNNratio; double TH_LOW, TH_HIGH;
+};
+
+// ---- Ransac ------------------------------------------------------------------------------------------------------------
+class Ransac {
+public:
+    Ransac() : Ransac(200, 20, 3.0f, 4) {}                                               // ransac.cpp:8-17
+    Ransac(int iters, unsigned minInlierTh, float maxMahalanobisDist, unsigned sampleSize) { SetParameters(iters, minInlierTh, maxMahalanobisDist, sampleSize); }
+    void SetParameters(int iters, unsigned minInlierTh, float maxMahalanobisDist, unsigned sampleSize)
+    {
+        mIterations = iters; mMinInlierTh = minInlierTh; mMaxMahalanobisDistance = maxMahalanobisDist; mSampleSize = sampleSize;
+    }
+    void SetIterations(int iters) { mIterations = iters; }
+    void SetMaxMahalanobisDistance(float dist) { mMaxMahalanobisDistance = dist; }
+    void SetSampleSize(unsigned sampleSize) { mSampleSize = sampleSize; }
+    void SetInlierThreshold(unsigned th) { mMinInlierTh = th; }
+    void CheckDepth(bool check_) { mCheckDepth = check_; }
+    // The reference draws from libc rand() seeded with srand(clock()) (main.cpp:27, quirk Q5): the seed is explicit here and
+    // advances by one per call, so a run is reproducible.
+    static unsigned& Seed() { static unsigned s = 42; return s; }
+    // DepthCovariance's static local (ransac.cpp:416-421, quirk Q7): latched by the first scored pair of the process.
+    static double& LatchedDepthCovariance() { static double c = -1.0; return c; }
+
+    bool Iterate(Frame* pF1, Frame* pF2, const std::vector<DMatch>& m12)                  // ransac.cpp:155-267
+    {
+        rmse = 1e6f; mvInliers.clear(); mT12.setIdentity();
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        orbf_context* ctx = Runtime::Current();
+        orbf_ransac_config cfg;
+        orbf_default_ransac_config(&cfg);
+        cfg.iterations = mIterations; cfg.min_inlier_th = mMinInlierTh; cfg.max_mahal = mMaxMahalanobisDistance; cfg.sample_size = mSampleSize;
+        cfg.check_depth = mCheckDepth ? 1 : 0; cfg.depth_cov = LatchedDepthCovariance(); cfg.seed = Seed()++;
+        orbf_ransac_result res;
+        std::vector<DMatch> inl(m12.size() ? m12.size() : 1);
+        static_assert(sizeof(Point3f) == 12, "Point3f must be three packed floats");
+        check(orbf_ransac_iterate(ctx, &cfg, reinterpret_cast<const float*>(pF1->mvKeys3Dc.data()), (int)pF1->mvKeys3Dc.size(),
+                  reinterpret_cast<const float*>(pF2->mvKeys3Dc.data()), (int)pF2->mvKeys3Dc.size(),
+                  reinterpret_cast<const orbf_dmatch*>(m12.data()), (int)m12.size(), nullptr, reinterpret_cast<orbf_dmatch*>(inl.data()),
+                  (int)inl.size(), &res, nullptr, nullptr, nullptr), "orbf_ransac_iterate");
+        if (LatchedDepthCovariance() < 0.0 && res.depth_cov_used >= 0.0) LatchedDepthCovariance() = res.depth_cov_used;
+        rmse = res.rmse;
+        std::memcpy(mT12.m, res.T12, sizeof(res.T12));
+        mvInliers.assign(inl.begin(), inl.begin() + res.n_inliers);
+        return res.ok != 0;
+    }
+
+    float rmse = 1e6f;
+    std::vector<DMatch> mvInliers;
+    Matrix4f mT12;
+
+private:
+    int mIterations = 200; unsigned mMinInlierTh = 20; float mMaxMahalanobisDistance = 3.0f; unsigned mSampleSize = 4; bool mCheckDepth = true;
+};
+
+// ---- Kabsch ------------------------------------------------------------------------------------------------------------
+class Kabsch {
+public:
+    // setA / setB: N x 3 row-major (Eigen::MatrixXf rows = points in the reference, kabsch.cpp:14-57)
+    Matrix4f Compute(const std::vector<Point3f>& setA, const std::vector<Point3f>& setB)
+    {
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        Matrix4f T;
+        const int n = (int)std::min(setA.size(), setB.size());
+        check(orbf_kabsch(Runtime::Current(), reinterpret_cast<const float*>(setA.data()), reinterpret_cast<const float*>(setB.data()), n, T.m),
+            "orbf_kabsch");
+        return T;
+    }
+};
+
+// ---- Odometry (RANSAC strategy only; the ICP / bundle-adjustment strategies are out of scope) ------------------------------
+class Odometry {
+public:
+    enum eAlgorithm { RANSAC = 0, ADAPTIVE_RICP, MOTION_ONLY_BA, ADAPTIVE_RBA };
+    Odometry(const eAlgorithm& algorithm = RANSAC) : mOdometryAlgorithm(algorithm), mpRansac(new Ransac(200, 20, 3.0f, 4)) {}   // odometry.cpp:14
+    // Runs Ransac::Iterate and keeps T12 + the inlier matches (odometry.cpp:43-52); pose composition with the frame's
+    // pose is one 4x4 product and stays with the caller's pose type.
+    bool Compute(Frame* pF1, Frame* pF2, const std::vector<DMatch>& vMatches12)
+    {
+        if (mOdometryAlgorithm != RANSAC) throw std::invalid_argument("orbf::Odometry: only the RANSAC strategy is on the GPU path");
+        const bool ok = mpRansac->Iterate(pF1, pF2, vMatches12);
+        mT12 = mpRansac->mT12; mvInliers = mpRansac->mvInliers;
+        return ok;
+    }
+    eAlgorithm mOdometryAlgorithm;
+    Matrix4f mT12;
+    std::vector<DMatch> mvInliers;
+    Ransac* ransac() { return mpRansac.get(); }
+private:
+    std::unique_ptr<Ransac> mpRansac;
+};
+
+}  // namespace orbf

@@ -122,3 +122,73 @@ def test_keyframe_store_many_to_many(ob, orc, texture):
             assert surv[k] == len(orc.knn_match(q, descs[k], 0.8))
     finally:
         ctx.close()
+
+
+def _load_sharding():
+    import importlib.util
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("orbf_sharding", root / "adaptive-rgbd-localization-mappig_b200" / "sharding.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_sharded_sequence_equals_whole_sequence(ob, texture):
+    """Two ranks' shards (run one after the other on this GPU: halo frame, global pair seeds, broadcast depth covariance)
+    reproduce the single-context run of the whole sequence byte for byte."""
+    sh = _load_sharding()
+    n = 7
+    frames = np.stack([synth.make_frame(texture, 60 + i) for i in range(n)])
+    depths = np.stack([synth.make_depth(60 + i) for i in range(n)])
+    whole = ob.Context(max_frames=n)
+    try:
+        _, ref, cov = sh.run_sequence_shard(whole, frames, depths, n, 0, 1, seed=11)
+    finally:
+        whole.close()
+    got = []
+    for rank in range(2):
+        s = sh.frame_shard(n, 2, rank)
+        ctx = ob.Context(max_frames=n)
+        try:
+            _, res, c = sh.run_sequence_shard(ctx, frames[s["first"]:s["stop"]], depths[s["first"]:s["stop"]], n, rank, 2, seed=11,
+                                              first_pair_cov=None if rank == 0 else cov)
+            assert c == cov
+            got += res
+        finally:
+            ctx.close()
+    assert [r["pair"] for r in got] == list(range(n - 1))
+    for g, r in zip(got, ref):
+        assert g["inliers"].tobytes() == r["inliers"].tobytes() and g["T12"].tobytes() == r["T12"].tobytes() and g["rmse"] == r["rmse"]
+
+
+def test_keyframe_shards_gathered_into_one_store(ob, orc, texture):
+    """Config 5: the per-rank keyframe shard is viewed as a torch tensor (zero copy), 'gathered' (here: two shards
+    concatenated on one GPU, the layout NCCL all_gather_into_tensor produces) and attached as an external store."""
+    import torch
+    sh = _load_sharding()
+    frames = np.stack([synth.make_frame(texture, 70 + 3 * i) for i in range(4)])
+    ctx = ob.Context(max_frames=4)
+    try:
+        ctx.extract_batch(frames)
+        ctx.kfdb_reserve(2)
+        shards, descs = [], []
+        for r in range(2):
+            for j in range(2):
+                ctx.kfdb_add_from_slot(j, 2 * r + j)
+                descs.append(orc.extract(frames[2 * r + j])[1])
+            ctx.synchronize()
+            d_ptr, c_ptr, rows, nkf = ctx.kfdb_device_buffers()
+            shards.append((sh.device_tensor(d_ptr, (nkf, rows, 32)).clone(), sh.device_tensor(c_ptr, (nkf,), "i4").clone()))
+        gd = torch.cat([s[0] for s in shards]).contiguous(); gc = torch.cat([s[1] for s in shards]).contiguous()
+        torch.cuda.synchronize()
+        ctx.kfdb_attach_device(gd.data_ptr(), gc.data_ptr(), 4)
+        q = orc.extract(synth.make_frame(texture, 75))[1]
+        i1, d1, i2, d2, surv = ctx.kfdb_match(q, 0, 4, 0.8)
+        for k in range(4):
+            r = orc.knn2(q, descs[k])
+            assert np.array_equal(i1[k], r[0]) and np.array_equal(d1[k], r[1]) and np.array_equal(i2[k], r[2]) and np.array_equal(d2[k], r[3])
+            assert surv[k] == len(orc.knn_match(q, descs[k], 0.8))
+        ctx.kfdb_attach_device(0, 0, 0)
+    finally:
+        ctx.close()
