@@ -56,10 +56,11 @@ constexpr int DS_WARPS = 4;
 
 __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(DescParams P)
 {
-    __shared__ int sPat[32 * 9];   // byte row i at words [9i, 9i+8): 9-word stride keeps lanes on distinct banks
+    // test pattern as floats, test (lane, k) at float4 index k * 32 + lane: conflict-free 128-bit reads, no I2F in the loop
+    __shared__ float4 sPat[256];
     for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) {
         const int row = i >> 3, k = i & 7;
-        sPat[row * 9 + k] = *reinterpret_cast<const int*>(&c_pattern[4 * i]);
+        sPat[k * 32 + row] = make_float4((float)c_pattern[4 * i], (float)c_pattern[4 * i + 1], (float)c_pattern[4 * i + 2], (float)c_pattern[4 * i + 3]);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -101,19 +102,22 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(DescParams P)
     // ---- steered BRIEF ------------------------------------------------------------------------------
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float ar = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)ar), b = (float)sin((double)ar);
+    double sn, cs;
+    sincos((double)ar, &sn, &cs);
+    const float a = (float)cs, b = (float)sn;
     const LevelView bv = P.blur.lv[level];
     const uint8_t* cb = bv.base + (long long)slot * bv.frameStride + (long long)y * bv.pitch + x;
     int val = 0;
+    // cvRound (round-half-even) without the conversion pipe: |v| <= 13 * sqrt(2) * 2 << 2^22, so adding 1.5 * 2^23 leaves the
+    // rounded integer in the low mantissa bits (FADD on the FMA pipe + IADD instead of F2I on the quarter-rate XU pipe)
+    const float kMagic = 12582912.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int w = sPat[lane * 9 + k];
-        const float x0 = (float)(int8_t)(w & 0xFF), y0 = (float)(int8_t)((w >> 8) & 0xFF);
-        const float x1 = (float)(int8_t)((w >> 16) & 0xFF), y1 = (float)(int8_t)((w >> 24) & 0xFF);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const float4 w = sPat[k * 32 + lane];
+        const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.x, b), __fmul_rn(w.y, a)), kMagic)) - 0x4B400000;
+        const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.x, a), __fmul_rn(w.y, b)), kMagic)) - 0x4B400000;
+        const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.z, b), __fmul_rn(w.w, a)), kMagic)) - 0x4B400000;
+        const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.z, a), __fmul_rn(w.w, b)), kMagic)) - 0x4B400000;
         const int t0 = __ldg(cb + r0 * bv.pitch + c0), t1 = __ldg(cb + r1 * bv.pitch + c1);
         val |= (t0 < t1) << k;
     }

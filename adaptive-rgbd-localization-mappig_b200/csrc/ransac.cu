@@ -45,6 +45,141 @@ struct DLess { ORBF_HD bool operator()(const orbf_dmatch& a, const orbf_dmatch& 
 // ------------------------------------------------------------------------------------------------------
 constexpr int PR_THREADS = 128;
 
+// ---- std::sort replay, parallel over the independent sub-ranges of the introsort recursion ---------------------------
+// libstdc++'s __introsort_loop partitions [first, last) around a median-of-3 pivot and then treats [first, cut) and
+// [cut, last) independently, so the ranges alive at one recursion depth can be partitioned concurrently (one thread each)
+// without changing a single comparison or swap inside any range.  The __final_insertion_sort that follows is a stable
+// insertion sort over the whole array; since every element of an earlier leaf is <= every element of a later one, it never
+// moves an element across a leaf boundary, i.e. it stably sorts each leaf (<= 16 elements) in place — done here by rank
+// counting, one thread per element.  Ranges that exhaust the depth limit are heap-sorted by their thread exactly as the
+// library does (already sorted, so the final pass leaves them alone).  Keys: ordered float bits << 32 | position.
+struct HiLess { ORBF_HD bool operator()(unsigned long long a, unsigned long long b) const { return (a >> 32) < (b >> 32); } };
+constexpr int SORT_QCAP = 128;
+
+constexpr int SORT_THREADS = PR_THREADS - 32;     // warp 1 draws the sample table meanwhile
+__device__ __forceinline__ void sort_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SORT_THREADS) : "memory"); }
+
+__device__ void parallel_std_sort(unsigned long long* keys, unsigned long long* keys2, uint16_t* leafStart, uint16_t* leafEnd, int M, int tid)
+{
+    __shared__ int qF[2][SORT_QCAP], qL[2][SORT_QCAP], qD[2][SORT_QCAP];
+    __shared__ int qN[2];
+    replay::IntroSort<unsigned long long, HiLess> S{ keys, HiLess() };
+    for (int i = tid; i < M; i += SORT_THREADS) { leafStart[i] = (uint16_t)i; leafEnd[i] = (uint16_t)(i + 1); }
+    if (tid == 0) {
+        int lg = 0;
+        for (int t = M; t > 1; t >>= 1) ++lg;
+        qN[0] = 0; qN[1] = 0;
+        if (M > 16) { qF[0][0] = 0; qL[0][0] = M; qD[0][0] = 2 * lg; qN[0] = 1; }
+    }
+    sort_barrier();
+    if (M <= 16) {
+        for (int i = tid; i < M; i += SORT_THREADS) { leafStart[i] = 0; leafEnd[i] = (uint16_t)M; }
+    }
+    int cur = 0;
+    while (true) {
+        const int n = qN[cur];
+        if (n == 0) break;
+        for (int t = tid; t < n; t += SORT_THREADS) {
+            const int first = qF[cur][t], last = qL[cur][t];
+            int depth = qD[cur][t];
+            if (depth == 0) { S.heap_sort(first, last); continue; }      // leaf of singletons: already in final order
+            --depth;
+            const int mid = first + (last - first) / 2;
+            S.move_median_to_first(first, first + 1, mid, last - 1);
+            const int cut = S.unguarded_partition(first + 1, last, first);
+            const int lo[2] = { cut, first }, hi[2] = { last, cut };
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (hi[c] - lo[c] > 16) {
+                    const int slot = atomicAdd(&qN[cur ^ 1], 1);
+                    qF[cur ^ 1][slot] = lo[c]; qL[cur ^ 1][slot] = hi[c]; qD[cur ^ 1][slot] = depth;
+                } else
+                    for (int i = lo[c]; i < hi[c]; ++i) { leafStart[i] = (uint16_t)lo[c]; leafEnd[i] = (uint16_t)hi[c]; }
+            }
+        }
+        sort_barrier();
+        if (tid == 0) qN[cur] = 0;
+        cur ^= 1;
+        sort_barrier();
+    }
+    sort_barrier();
+    for (int i = tid; i < M; i += SORT_THREADS) {
+        const int s0 = leafStart[i], e0 = leafEnd[i];
+        const unsigned long long k = keys[i];
+        const uint32_t ki = (uint32_t)(k >> 32);
+        int rank = s0;
+        for (int j = s0; j < e0; ++j) { const uint32_t kj = (uint32_t)(keys[j] >> 32); rank += (kj < ki) || (kj == ki && j < i); }
+        keys2[rank] = k;
+    }
+    sort_barrier();
+}
+
+// ---- glibc rand() replay by one warp ---------------------------------------------------------------------------------
+// glibc's TYPE_3 generator is x[i] = x[i-31] + x[i-3] (mod 2^32) with x[0..30] from the 16807 LCG, x[31..33] = x[0..2], 310
+// discarded values and output x[i] >> 1 (csrc/replay.h holds the circular-buffer form the library uses).  A block of 31
+// consecutive values follows from the previous block P as N[j] = sum_k P[j-3k] + P[28 + j % 3]: a stride-3 inclusive scan,
+// i.e. four shuffle steps for 31 values instead of 31 dependent steps.  The warp fills a buffer of `rand() % M` values;
+// lane 0 then runs SampleMatches' duplicate-rejecting loop (ransac.cpp:269-293) over it, which no longer contains any
+// generator or modulo arithmetic.  Returns false when the buffer was too short (caller falls back to the scalar replay).
+constexpr int RAND_BUF = 4096;
+
+__device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* tab, uint16_t* ids, int lane)
+{
+    uint32_t P = 0;
+    {
+        if (seed == 0) seed = 1;
+        int32_t word = (int32_t)seed;
+        for (int i = 0; i < 31; ++i) {
+            if (i > 0) {
+                const int32_t hi = word / 127773, lo = word % 127773;
+                word = 16807 * lo - 2836 * hi;
+                if (word < 0) word += 2147483647;
+            }
+            if (lane == (i >= 3 ? i - 3 : 28 + i)) P = (uint32_t)word;    // lane j holds x[3 + j]; x[31..33] = x[0..2]
+        }
+    }
+    const int base = 28 + lane % 3;
+    for (int blk = 0; (blk - 10) * 31 < RAND_BUF; ++blk) {
+        uint32_t v = P;
+#pragma unroll
+        for (int off = 3; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += t;
+        }
+        v += __shfl_sync(0xffffffffu, P, base);
+        P = v;
+        if (blk >= 10) {
+            const int n = (blk - 10) * 31 + lane;
+            if (lane < 31 && n < RAND_BUF) ids[n] = (uint16_t)((int)(v >> 1) % M);
+        }
+    }
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
+        int pos = 0;
+        for (int k = 0; k < iters && ok; ++k) {
+            int sel[ORBF_MAX_SAMPLE];
+            int cnt = 0, safety = 0;
+            while (cnt < S) {
+                if (pos + 2 > RAND_BUF) { ok = false; break; }
+                const int id = min((int)ids[pos], (int)ids[pos + 1]);
+                pos += 2;
+                int p = 0;
+                bool dup = false;
+                while (p < cnt && sel[p] <= id) { if (sel[p] == id) dup = true; ++p; }
+                if (!dup) {
+                    for (int j = cnt; j > p; --j) sel[j] = sel[j - 1];
+                    sel[p] = id;
+                    ++cnt;
+                }
+                if (++safety > 10000) break;
+            }
+            for (int j = 0; j < S; ++j) tab[(long long)k * S + j] = (j < cnt) ? sel[j] : -1;
+        }
+    }
+    return __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+}
+
 __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -87,29 +222,48 @@ __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams
     }
     const int M = sBase;
     orbf_dmatch* good = P.good + (long long)pair * P.K;
-    // sample table (needs only M): warp 1 draws it while warp 0 replays std::sort
+    // sample table (needs only M): warp 1 draws it while the other three warps replay std::sort
     int* tab = P.samples + (long long)pair * P.iters * P.S;
-    if (P.userSamples) {
+    if (P.userSamples)
         for (int i = tid; i < P.iters * P.S; i += PR_THREADS) tab[i] = P.userSamples[i];
-    } else if (tid == 32) {
-        if (M >= P.S) {
-            replay::GlibcRand g;
-            g.seed(P.cfg.seed + (uint32_t)pair);
-            for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
-        } else for (int i = 0; i < P.iters * P.S; ++i) tab[i] = -1;
-    }
-    if (P.cfg.sort_mode == 0) {
-        if (tid == 0) { replay::IntroSort<orbf_dmatch, DLess> s{ sm, DLess() }; s.sort(M); }
-        __syncthreads();
-        for (int i = tid; i < M; i += PR_THREADS) good[i] = sm[i];
-    } else if (P.cfg.sort_mode == 2) {   // stable: rank = #{j : d_j < d_i or (d_j == d_i and j < i)}
-        for (int i = tid; i < M; i += PR_THREADS) {
-            const float d = sm[i].distance;
-            int r = 0;
-            for (int j = 0; j < M; ++j) { const float e = sm[j].distance; r += (e < d) || (e == d && j < i); }
-            good[r] = sm[i];
+    __syncthreads();
+    if (warp == 1) {
+        if (!P.userSamples) {
+            uint16_t* ids = reinterpret_cast<uint16_t*>(smem + (size_t)P.K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)));
+            bool done = false;
+            if (M >= P.S) done = warp_sample_table(P.cfg.seed + (uint32_t)pair, M, P.S, P.iters, tab, ids, lane);
+            if (!done && lane == 0) {
+                if (M >= P.S) {     // buffer exhausted (tiny M, many duplicate draws): scalar replay from the start
+                    replay::GlibcRand g;
+                    g.seed(P.cfg.seed + (uint32_t)pair);
+                    for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
+                } else for (int i = 0; i < P.iters * P.S; ++i) tab[i] = -1;
+            }
         }
-    } else for (int i = tid; i < M; i += PR_THREADS) good[i] = sm[i];
+    } else {
+        const int st = tid < 32 ? tid : tid - 32;                              // 0..SORT_THREADS-1
+        if (P.cfg.sort_mode == 0) {
+            unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm + P.K);
+            unsigned long long* keys2 = keys + P.K;
+            uint16_t* leafStart = reinterpret_cast<uint16_t*>(keys2 + P.K);
+            uint16_t* leafEnd = leafStart + P.K;
+            for (int i = st; i < M; i += SORT_THREADS) {
+                uint32_t b = __float_as_uint(sm[i].distance);
+                b ^= (b >> 31) ? 0xFFFFFFFFu : 0x80000000u;                 // float order -> unsigned order
+                keys[i] = ((unsigned long long)b << 32) | (unsigned)i;
+            }
+            sort_barrier();
+            parallel_std_sort(keys, keys2, leafStart, leafEnd, M, st);
+            for (int i = st; i < M; i += SORT_THREADS) good[i] = sm[(uint32_t)keys2[i]];
+        } else if (P.cfg.sort_mode == 2) {   // stable: rank = #{j : d_j < d_i or (d_j == d_i and j < i)}
+            for (int i = st; i < M; i += SORT_THREADS) {
+                const float d = sm[i].distance;
+                int r = 0;
+                for (int j = 0; j < M; ++j) { const float e = sm[j].distance; r += (e < d) || (e == d && j < i); }
+                good[r] = sm[i];
+            }
+        } else for (int i = st; i < M; i += SORT_THREADS) good[i] = sm[i];
+    }
     __syncthreads();
     // packed, sorted 3D-3D pairs
     const float* sx = P.rs.sx + (long long)qs * P.rs.slotStride; const float* sy = P.rs.sy + (long long)qs * P.rs.slotStride;
@@ -608,7 +762,7 @@ int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
         ORBF_CUDA(c, cudaMalloc(&c->d_pts, needPts * sizeof(Pt6)));
         c->ptsCap = needPts;
     }
-    const size_t smem = (size_t)c->K * sizeof(orbf_dmatch);
+    const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + RAND_BUF * sizeof(uint16_t);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ransac_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac smem attr", __FILE__, __LINE__);
@@ -635,7 +789,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
         const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
         P.covX = sx * sx; P.covY = sy * sy;
     }
-    const size_t smem = (size_t)c->K * sizeof(orbf_dmatch);
+    const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + RAND_BUF * sizeof(uint16_t);
     orbf_prof_begin(c, ST_RANSAC_PREPARE);
     ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
