@@ -12,8 +12,11 @@
 
 namespace {
 
-__constant__ int c_umax[16];
-__constant__ __align__(16) int8_t c_pattern[1024];
+// Device tables, filled once per device by orbf_launch_describe:
+//   g_patF  : rBRIEF test t = 8 * byte + bit as floats (x0, y0, x1, y1) at index bit * 32 + byte (lane-major: conflict-free)
+//   g_icCoef: umax[0..15], the half-width of the circular patch per |row| (= half-height per |column|: the disc is symmetric)
+__device__ float4 g_patF[256];
+__device__ uint32_t g_icCoef[16];
 const int8_t h_pattern[1024] = {
 #include "rbrief_pattern.inc"
 };
@@ -56,12 +59,10 @@ constexpr int DS_WARPS = 4;
 
 __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(DescParams P)
 {
-    // test pattern as floats, test (lane, k) at float4 index k * 32 + lane: conflict-free 128-bit reads, no I2F in the loop
     __shared__ float4 sPat[256];
-    for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) {
-        const int row = i >> 3, k = i & 7;
-        sPat[k * 32 + row] = make_float4((float)c_pattern[4 * i], (float)c_pattern[4 * i + 1], (float)c_pattern[4 * i + 2], (float)c_pattern[4 * i + 3]);
-    }
+    __shared__ uint32_t sCoef[16];
+    for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) sPat[i] = g_patF[i];
+    if (threadIdx.x < 16) sCoef[threadIdx.x] = g_icCoef[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = P.slot0 + blockIdx.y;
@@ -79,21 +80,26 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(DescParams P)
     const int x = (int)(key & 0x7FF) + ORBF_MINB, y = (int)((key >> 11) & 0x7FF) + ORBF_MINB;
     const int score = (int)(key >> 22);
 
-    // ---- orientation ---------------------------------------------------------------------------------
+    // ---- orientation: lane = patch column u = lane - 15 (each row is one coalesced <= 31-byte read) --------------------
+    // The patch is a disc, so column u spans rows |v| <= umax[|u|]: one compare against a per-lane bound, no table reads;
+    // sum(u * I) is u * (column sum), formed once after the loop.
     const LevelView rv = P.raw.lv[level];
-    const uint8_t* c = rv.base + (long long)slot * rv.frameStride + (long long)y * rv.pitch + x;
-    const int u = lane - ORBF_HALF_PATCH;
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int au = abs(u);
+    {
+        const int u = lane - ORBF_HALF_PATCH;
+        const int dv = lane < 31 ? (int)(sCoef[min(abs(u), ORBF_HALF_PATCH)]) : -1;    // sCoef[0..15] = umax
+        const uint8_t* p = rv.base + (long long)slot * rv.frameStride + (long long)(y - ORBF_HALF_PATCH) * rv.pitch + (x + u);
+        int colSum = 0;
 #pragma unroll
         for (int v = -ORBF_HALF_PATCH; v <= ORBF_HALF_PATCH; ++v) {
-            if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = __ldg(c + v * rv.pitch + u);
-                m10 += u * val;
+            if ((v < 0 ? -v : v) <= dv) {
+                const int val = __ldg(p);
+                colSum += val;
                 m01 += v * val;
             }
+            p += rv.pitch;
         }
+        m10 = u * colSum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
@@ -168,8 +174,13 @@ int orbf_launch_describe(orbf_context* c, int slot0, int n)
 {
     const int dev = c->cfg.device;
     if (dev < 64 && !g_constReady[dev]) {
-        ORBF_CUDA(c, cudaMemcpyToSymbol(c_umax, c->umax, sizeof(int) * 16));
-        ORBF_CUDA(c, cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+        float4 patF[256];
+        for (int t = 0; t < 256; ++t)
+            patF[(t & 7) * 32 + (t >> 3)] = make_float4((float)h_pattern[4 * t], (float)h_pattern[4 * t + 1], (float)h_pattern[4 * t + 2], (float)h_pattern[4 * t + 3]);
+        uint32_t coef[16];
+        for (int v = 0; v < 16; ++v) coef[v] = (uint32_t)c->umax[v];
+        ORBF_CUDA(c, cudaMemcpyToSymbol(g_patF, patF, sizeof(patF)));
+        ORBF_CUDA(c, cudaMemcpyToSymbol(g_icCoef, coef, sizeof(coef)));
         g_constReady[dev] = true;
     }
     DescParams P;
