@@ -43,6 +43,12 @@ class RansacConfig(C.Structure):
                 ("depth_cov", C.c_double), ("seed", C.c_uint32)]
 
 
+class AdaptiveConfig(C.Structure):
+    _fields_ = [("min_features", C.c_int32), ("max_features", C.c_int32), ("max_iters", C.c_int32), ("max_per_cell", C.c_int32),
+                ("grid", C.c_int32), ("edge", C.c_int32), ("init_th", C.c_double), ("min_th", C.c_double), ("max_th", C.c_double),
+                ("inc", C.c_double), ("dec", C.c_double), ("retain_best", C.c_int32)]
+
+
 class RansacResult(C.Structure):
     _fields_ = [("ok", C.c_int32), ("rmse", C.c_float), ("T12", C.c_float * 16), ("n_inliers", C.c_int32),
                 ("n_good", C.c_int32), ("real_iters", C.c_int32), ("valid_iters", C.c_int32), ("used_identity", C.c_int32),
@@ -322,6 +328,25 @@ class Context:
         T = np.zeros(16, np.float32)
         self._chk(lib().orbf_kabsch(self._h, _p(A) if len(A) else None, _p(B) if len(B) else None, len(A), _p(T)), "kabsch")
         return T.reshape(4, 4)
+
+    # ---- adaptive-threshold FAST detector (Extractor ADAPTIVE mode, BASELINE config 4) ----
+    def adaptive_detect(self, frames, thresh, **kw):
+        """frames [n, H, W] u8; thresh [grid*grid] float64 state, updated in place.  Returns (list of keypoint arrays,
+        cell_thresh [n, cells], cell_found [n, cells])."""
+        cfg = AdaptiveConfig()
+        lib().orbf_default_adaptive_config(C.byref(cfg))
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        cells = cfg.grid * cfg.grid
+        assert thresh.dtype == np.float64 and len(thresh) == cells
+        cap = cfg.max_per_cell * cells
+        out = np.zeros((n, cap), KEYPOINT_DT); counts = np.zeros(n, np.int32)
+        used = np.zeros((n, cells), np.int32); found = np.zeros((n, cells), np.int32)
+        self._chk(lib().orbf_adaptive_detect(self._h, C.byref(cfg), _p(frames), n, w, C.c_int64(w * h), _p(thresh), _p(out), _p(counts), cap,
+                                             _p(used), _p(found)), "adaptive_detect")
+        return [out[i, :counts[i]].copy() for i in range(n)], used, found
 
     # ---- keyframe store ----
     def kfdb_reserve(self, n):

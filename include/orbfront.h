@@ -21,6 +21,9 @@
  *   orbf_ransac_pairs                 Odometry::Compute -> Ransac::Iterate, batched   Odometry/odometry.cpp:48
  *   orbf_kabsch                       Kabsch::Compute                             Odometry/kabsch.cpp:14-57
  *   orbf_kfdb_*                       keyframe descriptor storage of Core/keyframedatabase (config 5 many-to-many matching)
+ *   orbf_adaptive_detect              Extractor(FAST, ., ADAPTIVE): VideoGridAdaptedFeatureDetector over VideoDynamicAdaptedFeatureDetector
+ *                                     over DetectorAdjuster(FAST)  Features/extractor.cpp:52-77, videogridadaptedfeaturedetector.cpp:52-84,
+ *                                     videodynamicadaptedfeaturedetector.cpp:24-44, detectoradjuster.cpp:22-59 (BASELINE config 4)
  */
 #ifndef ORBFRONT_H
 #define ORBFRONT_H
@@ -195,6 +198,20 @@ int orbf_kfdb_attach_device(orbf_context* ctx, const uint8_t* d_desc, const int3
  * ratio survivors (out arrays sized nkf x nq, counts sized nkf).                                      */
 int orbf_kfdb_match(orbf_context* ctx, const uint8_t* q, int32_t nq, int32_t kf0, int32_t nkf, float ratio,
     int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors);
+
+/* ---- adaptive-threshold FAST detector (Extractor mode ADAPTIVE with the FAST detector) ---------- */
+typedef struct {
+    int32_t min_features, max_features, max_iters, max_per_cell, grid, edge;   /* 67, 113, 5, 113, 3, 31 (extractor.cpp:65-77)   */
+    double init_th, min_th, max_th, inc, dec;                                  /* 20, 2, 10000, 1.3, 0.7 (extractor.cpp:56)      */
+    int32_t retain_best;                                                        /* Extract(): retainBest(nFeatures); 0 = off      */
+} orbf_adaptive_config;
+void orbf_default_adaptive_config(orbf_adaptive_config* cfg);
+/* n host frames (gray, context width x height) through the grid of stateful detectors, in order: `thresh` [grid*grid] is
+ * the per-cell threshold state (<= 0 => init_th), updated in place so the next call continues the video.  out [n][cap]
+ * keypoints (cv::FAST KeyPoint fields: size 7, angle -1, octave 0), counts [n]; optional per-frame, per-cell integer
+ * threshold of the final detection and number of keypoints it found (before keepStrongest).                         */
+int orbf_adaptive_detect(orbf_context* ctx, const orbf_adaptive_config* cfg, const uint8_t* gray, int32_t n, int32_t stride,
+    int64_t frame_stride, double* thresh, orbf_keypoint* out, int32_t* counts, int32_t cap, int32_t* cell_thresh, int32_t* cell_found);
 
 #ifdef __cplusplus
 }

@@ -203,21 +203,42 @@ public:
     eAlgorithm mDetectorAlgorithm, mDescriptorAlgorithm; eMode mMode;
 
     Extractor(const eAlgorithm& detector = ORB_SLAM2, const eAlgorithm& descriptor = ORB_SLAM2, const eMode& mode = NORMAL, int nFeatures = 1000)
-        : mDetectorAlgorithm(detector), mDescriptorAlgorithm(descriptor), mMode(mode)
+        : mDetectorAlgorithm(detector), mDescriptorAlgorithm(descriptor), mMode(mode), mnFeatures(nFeatures)
     {
-        // the reference terminates on an unknown enum (extractor.cpp:27,108,132); the OpenCV-contrib routes are out of scope here
-        if (detector != ORB_SLAM2 || descriptor != ORB_SLAM2) throw std::invalid_argument("orbf::Extractor: only the ORB_SLAM2 route runs on the GPU");
-        mpDetector.reset(new ORBextractor(nFeatures, 1.2f, 8, 20, 7));       // extractor.cpp:86
-        mNorm() = NORM_HAMMING;                                              // defaultNorm() of ORB (extractor.cpp:35)
+        // the reference terminates on an unknown enum (extractor.cpp:27,108,132).  On the GPU: the ORB_SLAM2 route, and the
+        // adaptive FAST detector of CreateAdaptiveDetector (extractor.cpp:52-77); the OpenCV-contrib routes are out of scope
+        if (detector == ORB_SLAM2 && descriptor == ORB_SLAM2) {
+            mpDetector.reset(new ORBextractor(nFeatures, 1.2f, 8, 20, 7));   // extractor.cpp:86
+            mNorm() = NORM_HAMMING;                                          // defaultNorm() of ORB (extractor.cpp:35)
+        } else if (detector == FAST && mode == ADAPTIVE) {
+            orbf_default_adaptive_config(&mAdaptive);
+            mAdaptive.retain_best = nFeatures;
+            mAdaptiveState.assign((size_t)mAdaptive.grid * mAdaptive.grid, 0.0);    // <= 0: start from init_th (20)
+        } else throw std::invalid_argument("orbf::Extractor: only the ORB_SLAM2 and adaptive-FAST routes run on the GPU");
     }
     void Extract(const Mat8u& image, const Mat8u& mask, std::vector<KeyPoint>& keypoints, Mat8u& descriptors)
     {
-        mpDetector->detectAndCompute(image, mask, keypoints, descriptors);  // extractor.cpp:41-42
+        if (mpDetector) { mpDetector->detectAndCompute(image, mask, keypoints, descriptors); return; }   // extractor.cpp:41-42
+        // adaptive route: detect -> retainBest(nFeatures) (extractor.cpp:44-46); the descriptor extractors of this route are
+        // OpenCV(-contrib) objects and stay with the caller
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        orbf_context* ctx = Runtime::Get(image.cols, image.rows, mnFeatures, 1.2f, 8, 20, 7);
+        const int cap = mAdaptive.max_per_cell * mAdaptive.grid * mAdaptive.grid;
+        keypoints.resize((size_t)cap);
+        int n = 0;
+        check(orbf_adaptive_detect(ctx, &mAdaptive, image.data, 1, (int)image.step, (int64_t)image.step * image.rows, mAdaptiveState.data(),
+                  reinterpret_cast<orbf_keypoint*>(keypoints.data()), &n, cap, nullptr, nullptr), "orbf_adaptive_detect");
+        keypoints.resize((size_t)n);
+        descriptors.release();
     }
+    const std::vector<double>& AdaptiveThresholds() const { return mAdaptiveState; }   // DetectorAdjuster::mThresh of the 3x3 cells
     static int& mNorm() { static int n = NORM_HAMMING; return n; }
     ORBextractor* detector() { return mpDetector.get(); }
 private:
     std::unique_ptr<ORBextractor> mpDetector;
+    int mnFeatures;
+    orbf_adaptive_config mAdaptive;
+    std::vector<double> mAdaptiveState;
 };
 
 // ---- Frame: the storage the path reads and writes ----------------------------------------------------------------------

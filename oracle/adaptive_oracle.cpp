@@ -1,0 +1,100 @@
+// oracle/adaptive_oracle.cpp — CPU restatement of the reference's adaptive FAST detector route (TEST INFRASTRUCTURE ONLY).
+// Follows /root/reference:
+//   Extractor::CreateAdaptiveDetector   Features/extractor.cpp:52-77     FAST adjuster (20, 2, 10000, 1.3, 0.7), 3x3 grid,
+//                                                                         min 600/9 = 67, max 1020/9 = 113, 5 iterations, edge 31
+//   VideoGridAdaptedFeatureDetector::detect   Features/videogridadaptedfeaturedetector.cpp:52-84  overlapping sub-images, keepStrongest
+//   VideoDynamicAdaptedFeatureDetector::detect Features/videodynamicadaptedfeaturedetector.cpp:24-44 the per-cell threshold loop
+//   DetectorAdjuster::detect/tooFew/tooMany/good  Features/detectoradjuster.cpp:22-59            cv::FastFeatureDetector::create(int(mThresh))
+//   Extractor::Extract (non-ORB_SLAM2 route)  Features/extractor.cpp:44-46                      KeyPointsFilter::retainBest(nFeatures)
+// cv::FAST on a sub-image view = orc_fast_roi (pinned against cv2 in tests/test_oracle_vs_cv2.py).
+// Definitions where the reference is unspecified (std::nth_element leaves both the order and, among equal responses at the
+// cut, the kept subset implementation-defined; quirk Q15): keepStrongest keeps the N largest responses, equal responses in
+// detection (row-major) order, and the survivors stay in detection order.  retainBest keeps every keypoint whose response is
+// >= the N-th largest (OpenCV keeps all ties), in aggregate order.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "oracle_api.h"
+
+int orc_adaptive_default(orc_adaptive_cfg* c)
+{
+    if (!c) return ORC_ERR_ARG;
+    c->grid = 3; c->edge = 31; c->max_iters = 5;
+    const int minFeatures = 600, maxFeatures = (int)(minFeatures * 1.7);          // extractor.cpp:65-66
+    c->min_features = (int)std::round(minFeatures / 9.0f);                        // :71
+    c->max_features = (int)std::round(maxFeatures / 9.0f);                        // :72
+    c->max_per_cell = maxFeatures / 9;                                            // videogridadaptedfeaturedetector.cpp:58
+    c->init_th = 20; c->min_th = 2; c->max_th = 10000; c->inc = 1.3; c->dec = 0.7;   // extractor.cpp:56
+    return ORC_OK;
+}
+
+static void keep_strongest(std::vector<orc_cand>& v, int N)
+{
+    if ((int)v.size() <= N) return;
+    std::vector<int> idx(v.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return v[a].score > v[b].score; });
+    std::vector<char> keep(v.size(), 0);
+    for (int i = 0; i < N; ++i) keep[idx[i]] = 1;
+    std::vector<orc_cand> out;
+    for (size_t i = 0; i < v.size(); ++i) if (keep[i]) out.push_back(v[i]);
+    v.swap(out);
+}
+
+int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, int h, int stride, double* thresh, int retain_best,
+    orc_keypoint* out, int cap, int* n_out, int* cell_found, int* cell_thresh)
+{
+    if (!cfg || !img || !thresh || !n_out || cfg->grid < 1 || cfg->grid > 5) return ORC_ERR_ARG;
+    const int g = cfg->grid;
+    std::vector<orc_keypoint> all;
+    std::vector<orc_cand> kps;
+    for (int i = 0; i < g; ++i) {
+        const int rowstart = std::max((i * h) / g - cfg->edge, 0), rowend = std::min(h, ((i + 1) * h) / g + cfg->edge);
+        for (int j = 0; j < g; ++j) {
+            const int colstart = std::max((j * w) / g - cfg->edge, 0), colend = std::min(w, ((j + 1) * w) / g + cfg->edge);
+            double& th = thresh[i * g + j];
+            int iterCount = cfg->max_iters, usedTh = 0;
+            const int sw = colend - colstart, sh = rowend - rowstart;
+            do {
+                usedTh = (int)th;                                                  // FastFeatureDetector::create(int threshold)
+                int n = 0;
+                kps.assign((size_t)sw * sh / 4 + 16, orc_cand());
+                const int rc = orc_fast_roi(img + (size_t)rowstart * stride + colstart, stride, sw, sh, usedTh, kps.data(), (int)kps.size(), &n);
+                if (rc != ORC_OK) return rc;
+                kps.resize(n);
+                if (n < cfg->min_features) {                                       // tooFew
+                    th *= cfg->dec;
+                    if (th < cfg->min_th) th = cfg->min_th;
+                } else if (n > cfg->max_features) {                                // tooMany
+                    th *= cfg->inc;
+                    if (th > cfg->max_th) th = cfg->max_th;
+                    break;
+                } else break;
+                iterCount--;
+            } while (iterCount > 0 && th > cfg->min_th && th < cfg->max_th);       // good()
+            if (cell_found) cell_found[i * g + j] = (int)kps.size();
+            if (cell_thresh) cell_thresh[i * g + j] = usedTh;
+            keep_strongest(kps, cfg->max_per_cell);
+            for (const orc_cand& c : kps) {
+                orc_keypoint k;
+                k.x = (float)(c.x + colstart); k.y = (float)(c.y + rowstart); k.size = 7.f; k.angle = -1.f;
+                k.response = (float)c.score; k.octave = 0; k.class_id = -1;
+                all.push_back(k);
+            }
+        }
+    }
+    if (retain_best > 0 && (int)all.size() > retain_best) {
+        std::vector<float> r(all.size());
+        for (size_t i = 0; i < all.size(); ++i) r[i] = all[i].response;
+        std::nth_element(r.begin(), r.begin() + (retain_best - 1), r.end(), std::greater<float>());
+        const float cut = r[retain_best - 1];
+        std::vector<orc_keypoint> keep;
+        for (const orc_keypoint& k : all) if (k.response >= cut) keep.push_back(k);
+        all.swap(keep);
+    }
+    *n_out = (int)all.size();
+    if ((int)all.size() > cap) return ORC_ERR_CAPACITY;
+    if (out) std::copy(all.begin(), all.end(), out);
+    return ORC_OK;
+}

@@ -223,6 +223,36 @@ def unproject(kps, depth, depth_factor=FR1["depth_factor"], fx=FR1["fx"], fy=FR1
     return xyz, ur
 
 
+class AdaptiveCfg(C.Structure):
+    _fields_ = [("min_features", C.c_int), ("max_features", C.c_int), ("max_iters", C.c_int), ("max_per_cell", C.c_int),
+                ("grid", C.c_int), ("edge", C.c_int), ("init_th", C.c_double), ("min_th", C.c_double), ("max_th", C.c_double),
+                ("inc", C.c_double), ("dec", C.c_double)]
+
+
+def adaptive_default(**kw):
+    cfg = AdaptiveCfg()
+    lib().orc_adaptive_default(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def adaptive_detect(img, thresh, retain_best=0, cfg=None):
+    """VideoGridAdaptedFeatureDetector::detect (+ retainBest) on one frame; `thresh` [grid*grid] float64 is updated in place.
+    Returns (kps, cell_found, cell_thresh)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cfg = cfg or adaptive_default()
+    g2 = cfg.grid * cfg.grid
+    assert thresh.dtype == np.float64 and len(thresh) == g2
+    cap = cfg.max_per_cell * g2 + 16
+    out = np.zeros(cap, KEYPOINT_DT); n = C.c_int(0)
+    found = np.zeros(g2, np.int32); used = np.zeros(g2, np.int32)
+    _chk(lib().orc_adaptive_detect(C.byref(cfg), _p(img), w, h, w, _p(thresh), int(retain_best), _p(out), cap, C.byref(n), _p(found),
+                                   _p(used)), "adaptive_detect")
+    return out[:n.value].copy(), found, used
+
+
 def knn2(q, t, speed=False):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     nq, nt = len(q), len(t)

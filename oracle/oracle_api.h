@@ -56,6 +56,17 @@ int orc_extract(const orc_extract_cfg* cfg, const uint8_t* img, int stride, orc_
 int orc_unproject(const orc_keypoint* kps, int n, const uint16_t* depth_u16, const float* depth_f32, int w, int h,
     int dstride_elems, float depth_factor, float fx, float fy, float cx, float cy, float mbf, float* xyz, float* uright);
 
+/* ---- adaptive FAST detector route (Features/video*adaptedfeaturedetector.cpp, detectoradjuster.cpp, extractor.cpp:52-77) ---- */
+typedef struct {
+    int min_features, max_features, max_iters, max_per_cell, grid, edge;
+    double init_th, min_th, max_th, inc, dec;
+} orc_adaptive_cfg;
+int orc_adaptive_default(orc_adaptive_cfg* cfg);
+/* thresh: [grid*grid] per-cell threshold state, in/out (persists from frame to frame like the stateful detectors).
+ * cell_found / cell_thresh (optional): keypoints found by, and integer threshold of, each cell's last detection.  */
+int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, int h, int stride, double* thresh, int retain_best,
+    orc_keypoint* out, int cap, int* n_out, int* cell_found, int* cell_thresh);
+
 /* ---- matching (Features/matcher.cpp:10-88,355-358) ---- */
 int orc_hamming(const uint8_t* a, const uint8_t* b);
 int orc_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx1, int* d1, int* idx2, int* d2);

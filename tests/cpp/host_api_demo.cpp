@@ -60,6 +60,15 @@ int main(int argc, char** argv)
         for (auto& p : B) { const float x = p.x; p.x = -p.y + 0.1f; p.y = x - 0.2f; p.z += 0.3f; }      // 90 deg about z + translation
         const Matrix4f T = Kabsch().Compute(A, B);
         put(out, T.m, sizeof(float) * 16);
+        // Extractor(FAST, ., ADAPTIVE): the stateful grid detector over the same frames (extractor.cpp:52-77)
+        Extractor adaptive(Extractor::FAST, Extractor::BRIEF, Extractor::ADAPTIVE);
+        for (int i = 0; i < n; ++i) {
+            std::vector<KeyPoint> kps; Mat8u none;
+            adaptive.Extract(Mat8u(h, w, gray.data() + (size_t)i * w * h), Mat8u(), kps, none);
+            puti(out, (int)kps.size());
+            put(out, kps.data(), kps.size() * sizeof(KeyPoint));
+        }
+        put(out, adaptive.AdaptiveThresholds().data(), 9 * sizeof(double));
         Runtime::Shutdown();
     } catch (const Error& e) {
         fprintf(stderr, "host_api_demo: %s\n", e.what());

@@ -82,4 +82,9 @@ def test_host_mirror_matches_oracle(demo, ob, orc, texture, tmp_path):
     T = take(np.float32, 16).reshape(4, 4)
     assert np.abs(T[:3, :3] - np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)).max() < 1e-4
     assert np.abs(T[:3, 3] - np.array([0.1, -0.2, 0.3], np.float32)).max() < 1e-4
+    th = np.full(9, 20.0)
+    for i in range(n):                                                                       # Extractor(FAST, ., ADAPTIVE)
+        N = int(take(np.int32, 1)[0]); k = take(ob.KEYPOINT_DT, N)
+        assert k.tobytes() == orc.adaptive_detect(frames[i], th, retain_best=1000)[0].tobytes(), f"adaptive frame {i}"
+    assert np.array_equal(take(np.float64, 9), th)
     assert pos == len(buf)
