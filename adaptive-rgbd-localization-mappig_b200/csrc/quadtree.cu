@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int QT_THREADS = 128;
+constexpr int QT_THREADS = 256;
 constexpr int QT_SMEM_KEYS = 16384;
 
 struct QtParams {
