@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(CC_THREADS) cell_collect_kernel(const __grid_c
 {
     __shared__ int rowCount[CC_MAX_ROWS];
     __shared__ int hist[256];
-    __shared__ int sTotal;
     const int cellIdx = blockIdx.x, f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const AdGeom g = P.cell[cellIdx];
@@ -185,7 +184,6 @@ __global__ void __launch_bounds__(CC_THREADS) cell_collect_kernel(const __grid_c
             if (tid == 0) {                                                 // exclusive prefix over rows (<= ~300 rows), suffix sums of the histogram
                 int acc = 0;
                 for (int r = 0; r < rows; ++r) { const int c = rowCount[r]; rowCount[r] = acc; acc += c; }
-                sTotal = acc;
                 int* ge = P.ge + ((long long)f * P.nCells + cellIdx) * 257;
                 int suf = 0;
                 ge[256] = 0;

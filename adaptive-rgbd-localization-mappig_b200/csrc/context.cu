@@ -272,7 +272,8 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->B = cfg->max_frames;
     c->P = cfg->max_pairs > 0 ? cfg->max_pairs : cfg->max_frames;
     c->launches = 0; c->stream = nullptr; c->ownStream = false; c->profiling = false;
-    c->nWork = 0; c->evFork = nullptr; c->evLatch = nullptr;
+    c->nWork = 0; c->evFork = nullptr; c->evLatch = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
+    for (int i = 0; i < 8; ++i) c->evHiGroup[i] = nullptr;
     for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
     c->chunkFrames = cfg->pipeline_chunk == 0 ? 64 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
@@ -298,6 +299,10 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
             ok = cudaStreamCreateWithFlags(&c->work[i], cudaStreamNonBlocking) == cudaSuccess && ev(&c->evDone[i]) && ev(&c->evExtract[i]);
             if (ok) c->nWork = i + 1;
         }
+        int prLo = 0, prHi = 0;
+        ok = ok && cudaDeviceGetStreamPriorityRange(&prLo, &prHi) == cudaSuccess
+            && cudaStreamCreateWithPriority(&c->hi, cudaStreamNonBlocking, prHi) == cudaSuccess && ev(&c->evHiA) && ev(&c->evHiB);
+        for (int i = 0; ok && i < 8; ++i) ok = ev(&c->evHiGroup[i]);
         if (!ok) { orbf_cuda_fail(c, cudaGetLastError(), "worker streams", __FILE__, __LINE__); return fail(ORBF_ERR_CUDA); }
     }
     const size_t B = c->B, K = c->K, P = c->P;
@@ -394,6 +399,10 @@ extern "C" int orbf_destroy(orbf_context* c)
         if (c->evDone[i]) cudaEventDestroy(c->evDone[i]);
         if (c->evExtract[i]) cudaEventDestroy(c->evExtract[i]);
     }
+    if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); }
+    if (c->evHiA) cudaEventDestroy(c->evHiA);
+    if (c->evHiB) cudaEventDestroy(c->evHiB);
+    for (int i = 0; i < 8; ++i) if (c->evHiGroup[i]) cudaEventDestroy(c->evHiGroup[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evLatch) cudaEventDestroy(c->evLatch);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);

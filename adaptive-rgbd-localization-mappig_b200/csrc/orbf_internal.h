@@ -81,6 +81,9 @@ struct orbf_context {
     // chunk k (H2D copies + all stages of its frames and frame pairs) on worker k % nWork, and joins them again
     cudaStream_t work[ORBF_MAX_WORKERS]; int nWork, chunkFrames;
     cudaEvent_t evFork, evDone[ORBF_MAX_WORKERS], evExtract[ORBF_MAX_WORKERS], evLatch;
+    // high-priority side stream for the latency-bound stages (quadtree, RANSAC): their few, long-running CTAs are placed as
+    // soon as SM resources free up and overlap the throughput-bound kernels (blur, Hamming) still running on the main stream
+    cudaStream_t hi; cudaEvent_t evHiA, evHiB, evHiGroup[8];
     int64_t launches;
     bool profiling; cudaEvent_t evA[ST_COUNT], evB[ST_COUNT]; bool evPending[ST_COUNT]; double stageMs[ST_COUNT]; int64_t stageCalls[ST_COUNT];
     std::string lastError;

@@ -40,7 +40,6 @@ struct RansacParams {
     double covX, covY;
 };
 
-struct DLess { ORBF_HD bool operator()(const orbf_dmatch& a, const orbf_dmatch& b) const { return a.distance < b.distance; } };
 
 // ------------------------------------------------------------------------------------------------------
 constexpr int PR_THREADS = 128;
@@ -407,11 +406,6 @@ __device__ __forceinline__ float det3(const M3& a)
 
 struct Tfc {   // pcl::TransformationFromCorrespondences
     float accW, m1[3], m2[3], C[3][3];
-    __device__ void reset()
-    {
-        accW = 0.f;
-        for (int i = 0; i < 3; ++i) { m1[i] = m2[i] = 0.f; for (int j = 0; j < 3; ++j) C[i][j] = 0.f; }
-    }
     __device__ void add(const float p[3], const float q[3], float w)
     {
         if (w == 0.0f) return;
@@ -447,6 +441,64 @@ struct Tfc {   // pcl::TransformationFromCorrespondences
         T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
     }
 };
+
+// GetTransformFromMatches (ransac.cpp:295-313) for the inlier set in mask[], by one warp, bit-identical to feeding the
+// points to Tfc::add in match order:
+//   (a) the inliers are compacted in order (ballot prefix) together with their weights w = 1 / (z_from * z_to);
+//   (b) accW is the sequential float prefix sum of w (one dependent FADD per point — the only truly serial part), and
+//       alpha_k = w_k / accW_k is then formed for 32 points at a time;
+//   (c) the recurrence C = (1-alpha)(C + alpha d2 d1^T), m += alpha d splits into independent scalar chains: lane (r, c)
+//       owns C[r][c] plus private copies of m1[c] and m2[r], so a point costs ~10 FP ops per lane instead of ~60 per warp.
+// idx / al: per-warp shared scratch of at least M entries.
+__device__ void tfc_from_mask(const Pt6* pts, const uint32_t* mask, int words, uint16_t* idx, float* al, Tfc& out, int lane)
+{
+    const uint32_t lt = (1u << lane) - 1;
+    int n = 0;
+    for (int w = 0; w < words; ++w) {
+        const uint32_t mk = mask[w];
+        const int i = (w << 5) + lane;
+        bool use = (mk >> lane) & 1u;
+        float wt = 0.f;
+        if (use) {
+            const Pt6 p = pts[i];
+            if (isnan(p.sz) || isnan(p.tz)) use = false;
+            else { wt = 1.0f / (p.sz * p.tz); if (wt == 0.0f) use = false; }
+        }
+        const uint32_t um = __ballot_sync(0xffffffffu, use);
+        if (use) { const int pos = n + __popc(um & lt); idx[pos] = (uint16_t)i; al[pos] = wt; }
+        n += __popc(um);
+    }
+    __syncwarp();
+    float acc = 0.f;
+    for (int base = 0; base < n; base += 32) {
+        const int cnt = min(32, n - base);
+        float myAcc = 1.f;
+        for (int j = 0; j < cnt; ++j) { acc += al[base + j]; if (lane == j) myAcc = acc; }
+        __syncwarp();
+        if (lane < cnt) al[base + lane] = al[base + lane] / myAcc;
+        __syncwarp();
+    }
+    const int r = (lane % 9) / 3, c = lane % 3;              // lanes 9..31 repeat the nine chains
+    float Cv = 0.f, m1c = 0.f, m2r = 0.f;
+    for (int k = 0; k < n; ++k) {
+        const float alpha = al[k], oma = 1.0f - alpha;
+        const float* pf = reinterpret_cast<const float*>(pts + idx[k]);
+        const float d1 = pf[c] - m1c, d2 = pf[3 + r] - m2r;
+        const float outer = d2 * d1;
+        Cv = oma * (Cv + alpha * outer);
+        m1c += alpha * d1;
+        m2r += alpha * d2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        out.m1[i] = __shfl_sync(0xffffffffu, m1c, i);
+        out.m2[i] = __shfl_sync(0xffffffffu, m2r, 3 * i);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) out.C[i][j] = __shfl_sync(0xffffffffu, Cv, 3 * i + j);
+    }
+    out.accW = acc;
+    __syncwarp();
+}
 
 // ErrorFunction2 (ransac.cpp:350-414); cz = depth covariance (explicit, quirk Q7)
 __device__ double mahal2(const Pt6& p, const double* T, double cz, double covX, double covY)
@@ -545,6 +597,9 @@ __device__ double score_all(const Pt6* pts, int M, const float* T4f, double cz, 
 __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams P)
 {
     __shared__ uint32_t sMask[HY_WARPS][MAX_WORDS];
+    extern __shared__ __align__(16) uint8_t hsmem[];             // per warp: K alpha floats + K inlier indices (tfc_from_mask)
+    float* sAl = reinterpret_cast<float*>(hsmem);
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sAl + HY_WARPS * P.K);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = P.pair0 + blockIdx.y;
     const int k = P.hypLo + blockIdx.x * HY_WARPS + warp;
@@ -570,19 +625,8 @@ __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams 
         __syncwarp();
         rounds = 0;
         for (int refinements = 1; refinements < 20; ++refinements) {
-            // GetTransformFromMatches (ransac.cpp:295-313): lane-uniform replay of the incremental recurrence
-            Tfc tfc; tfc.reset();
-            for (int w = 0; w < words; ++w) {
-                uint32_t mk = mask[w];
-                while (mk) {
-                    const int i = (w << 5) + __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    const Pt6 p = pts[i];
-                    if (isnan(p.sz) || isnan(p.tz)) continue;
-                    const float from[3] = { p.sx, p.sy, p.sz }, to[3] = { p.tx, p.ty, p.tz };
-                    tfc.add(from, to, 1.0f / (p.sz * p.tz));
-                }
-            }
+            Tfc tfc;
+            tfc_from_mask(pts, mask, words, sIdx + warp * P.K, sAl + warp * P.K, tfc, lane);
             float T[16];
             tfc.transform(T);
             ++rounds;
@@ -802,6 +846,11 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     orbf_prof_begin(c, ST_RANSAC_HYP);
     // waves of hypotheses: the reference usually stops after a handful of iterations (> 80 % inliers ends the loop,
     // accepted hypotheses skip 10-20 iterations ahead), so later waves find their pair already done and exit at once
+    const size_t hypSmem = (size_t)HY_WARPS * c->K * (sizeof(float) + sizeof(uint16_t));
+    if (hypSmem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hypSmem);
+        if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac hyp smem attr", __FILE__, __LINE__);
+    }
     const int waveEnd[4] = { 8, 32, 96, iters };
     int lo = 0;
     for (int w = 0; w < 4 && lo < iters; ++w) {
@@ -809,7 +858,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
         if (hi <= lo) continue;
         P.hypLo = lo; P.hypHi = hi;
         dim3 grid((hi - lo + HY_WARPS - 1) / HY_WARPS, npairs);
-        ransac_hyp_kernel<<<grid, HY_WARPS * 32, 0, c->stream>>>(P);
+        ransac_hyp_kernel<<<grid, HY_WARPS * 32, hypSmem, c->stream>>>(P);
         ORBF_LAUNCH_CHECK(c);
         ransac_replay_kernel<<<(npairs + 127) / 128, 128, 0, c->stream>>>(P, npairs);
         ORBF_LAUNCH_CHECK(c);
