@@ -1,0 +1,142 @@
+"""Full-size checks through size-independent properties (the oracle is too slow to replay BASELINE.json's largest
+configurations frame by frame): determinism across batch positions, permutation invariance, self-matching, symmetry of the
+mutual-NN filter, distances re-derived with numpy, rigid-motion recovery, and the oracle on a handful of distinct inputs.
+
+  config 1   256 frames 640x480            config 3   512-frame sequence shard, consecutive pairs
+  config 2   1000 x 1000 descriptors       config 5   1000-keypoint query vs 2048 keyframes"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def popcount_rows(x):
+    return np.unpackbits(x, axis=-1).sum(-1)
+
+
+def test_config1_batch_of_256_frames_is_position_independent(ob, orc, texture):
+    base = [synth.make_frame(texture, i) for i in (0, 3, 7, 11)]         # frame 7 carries the low-contrast band (minTh fallback cells)
+    n = 256
+    order = np.random.default_rng(0).integers(0, 4, n)
+    frames = np.stack([base[j] for j in order])
+    ctx = ob.Context(max_frames=n)
+    try:
+        ctx.extract_batch(frames)
+        counts = ctx.frame_counts(n)
+        ref = [orc.extract(b) for b in base]
+        first = {}
+        for s in range(n):
+            j = int(order[s])
+            assert counts[s] == len(ref[j][0])
+            if j not in first or s % 37 == 0:                           # full download for a sample of slots, incl. the first of each kind
+                k, d, _ = ctx.download_frame(s)
+                assert k.tobytes() == ref[j][0].tobytes() and np.array_equal(d, ref[j][1]), f"slot {s} (base {j})"
+                first.setdefault(j, s)
+        # permutation: the reversed batch gives the reversed results
+        ctx.extract_batch(np.ascontiguousarray(frames[::-1]))
+        assert np.array_equal(ctx.frame_counts(n), counts[::-1])
+        k, d, _ = ctx.download_frame(5)
+        assert k.tobytes() == ref[int(order[n - 6])][0].tobytes()
+    finally:
+        ctx.close()
+
+
+def test_config2_matching_properties_at_1000x1000(ob):
+    A, B = synth.descriptor_sets(1000, seed=21)
+    ctx = ob.Context(max_frames=1)
+    try:
+        i1, d1, i2, d2 = ctx.knn2(A, B)
+        # distances are the true Hamming distances, ordered, and nothing closer exists
+        D = popcount_rows(A[:, None, :] ^ B[None, :, :])                 # 1000 x 1000
+        assert np.array_equal(d1, D[np.arange(1000), i1]) and np.array_equal(d2, D[np.arange(1000), i2])
+        assert np.all(d1 <= d2) and np.all(i1 != i2)
+        srt = np.sort(D, axis=1)
+        assert np.array_equal(d1, srt[:, 0]) and np.array_equal(d2, srt[:, 1])
+        assert np.array_equal(i1, np.argmin(D, axis=1))                  # argmin = lowest index on ties (P5)
+        # self-matching: every row finds itself at distance 0 and survives ratio + cross-check
+        m = ctx.knn_match(A, A, 0.8, cross_check=True)
+        assert len(m) == 1000 and np.array_equal(m["queryIdx"], m["trainIdx"]) and np.all(m["distance"] == 0)
+        # mutual-NN symmetry: (i, j) kept from A->B iff j's best in B->A is i
+        fw = ctx.knn_match(A, B, 1.01, cross_check=True)                 # ratio > 1 keeps every mutual pair with d1 < 1.01 d2
+        bi1 = ctx.knn2(B, A)[0]
+        assert np.all(bi1[fw["trainIdx"]] == fw["queryIdx"])
+        # ratio monotonicity: survivors at 0.6 are a subset of those at 0.8, of those at 0.9
+        s6, s8, s9 = (set(ctx.knn_match(A, B, r)["queryIdx"].tolist()) for r in (0.6, 0.8, 0.9))
+        assert s6 <= s8 <= s9
+    finally:
+        ctx.close()
+
+
+def test_config3_sequence_shard_of_512_frames(ob, orc, texture):
+    base_f = [synth.make_frame(texture, i) for i in range(4)]
+    base_d = [synth.make_depth(i) for i in range(4)]
+    n = 512
+    seq = [0, 1, 2, 3, 2, 1]                                             # ping-pong: consecutive frames stay consecutive motions
+    ids = [seq[i % len(seq)] for i in range(n)]
+    frames = np.stack([base_f[j] for j in ids]); depths = np.stack([base_d[j] for j in ids])
+    ctx = ob.Context(max_frames=n, max_pairs=n)
+    try:
+        ctx.track_sequence(frames, depths, 0.8, cross_check=True, seed=42)           # pipelined host path, 8 chunks
+        summ = ctx.download_ransac_summary(n - 1)
+        mc = ctx.match_counts(n - 1)
+        assert np.all(summ["ok"] == 1), "every pair is a small rigid motion of the same scene"
+        assert len(set(summ["depth_cov_used"].tolist())) == 1, "one depth covariance for the whole sequence (quirk Q7)"
+        # pairs with the same (frame, frame) content have the same matches; RANSAC differs only through its per-pair seed
+        kind = {}
+        for p in range(n - 1):
+            key = (ids[p], ids[p + 1])
+            if key in kind:
+                assert mc[p] == mc[kind[key]], f"pair {p} vs {kind[key]}"
+            else:
+                kind[key] = p
+        # the recovered motion of (a, b) is the inverse of (b, a) up to RANSAC noise
+        Tab = summ["T12"][kind[(0, 1)]].reshape(4, 4).astype(np.float64); Tba = summ["T12"][kind[(1, 0)]].reshape(4, 4).astype(np.float64)
+        assert np.abs(Tab @ Tba - np.eye(4)).max() < 2e-2
+        # oracle on the first two pairs
+        k0, d0 = orc.extract(base_f[0]); k1, d1 = orc.extract(base_f[1])
+        m = orc.knn_match(d0, d1, 0.8, True)
+        assert ctx.download_matches(0).tobytes() == m.tobytes()
+        r = orc.ransac_iterate(orc.unproject(k0, base_d[0])[0], orc.unproject(k1, base_d[1])[0], m, seed=42)
+        assert ctx.download_ransac(0)["inliers"].tobytes() == r["inliers"].tobytes()
+    finally:
+        ctx.close()
+
+
+def test_config5_query_against_2048_keyframes(ob, orc, texture):
+    base = [orc.extract(synth.make_frame(texture, 2 * i))[1] for i in range(6)]
+    nkf = 2048
+    ctx = ob.Context(max_frames=1)
+    try:
+        ctx.kfdb_reserve(nkf)
+        for k in range(nkf):
+            ctx.kfdb_add_host(k, base[k % 6])
+        q = orc.extract(synth.make_frame(texture, 5))[1]
+        i1, d1, i2, d2, surv = ctx.kfdb_match(q, 0, nkf, 0.8)
+        for j in range(6):
+            r = orc.knn2(q, base[j])
+            rows = np.arange(j, nkf, 6)
+            assert np.all(i1[rows] == r[0]) and np.all(d1[rows] == r[1]) and np.all(i2[rows] == r[2]) and np.all(d2[rows] == r[3])
+            assert np.all(surv[rows] == len(orc.knn_match(q, base[j], 0.8)))
+    finally:
+        ctx.close()
+
+
+def test_ransac_recovers_a_known_rigid_motion_at_1000_matches(ob):
+    src, dst, matches, R, t = synth.rigid_pairs(m=1000, seed=31, outlier_frac=0.4, n_pts=1056)
+    ctx = ob.Context(max_frames=1)
+    try:
+        r = ctx.ransac_iterate(src, dst, matches, seed=5)
+        assert r["ok"]
+        assert np.abs(r["T12"][:3, :3] - R).max() < 5e-3 and np.abs(r["T12"][:3, 3] - t).max() < 5e-3
+        assert len(r["inliers"]) > 0.5 * r["n_good"]
+        # inliers are a subset of the sorted good matches, in their order
+        pos = {(int(m["queryIdx"]), int(m["trainIdx"])): i for i, m in enumerate(r["good_sorted"])}
+        seq = [pos[(int(m["queryIdx"]), int(m["trainIdx"]))] for m in r["inliers"]]
+        assert seq == sorted(seq)
+        # idempotence: the same call again gives the same bytes
+        r2 = ctx.ransac_iterate(src, dst, matches, seed=5)
+        assert r2["inliers"].tobytes() == r["inliers"].tobytes() and r2["T12"].tobytes() == r["T12"].tobytes()
+    finally:
+        ctx.close()
