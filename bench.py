@@ -245,11 +245,14 @@ def main():
     d2h = int(summ.nbytes + mc.nbytes + fc.nbytes)
     # ---- per-stage times (CUDA events inside the library, on the launching stream) ----
     ctx.profile_enable(True)
-    for _ in range(max(3, args.steps // 2)):
+    per_iter = []
+    prev = {k: 0.0 for k in ctx.profile_read()}
+    for _ in range(max(5, args.steps)):
         step_device(); ctx.profile_collect()
-    prof = ctx.profile_read()
+        cur = {k: v[0] for k, v in ctx.profile_read().items()}
+        per_iter.append({k: cur[k] - prev[k] for k in cur}); prev = cur
     ctx.profile_enable(False)
-    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items()}
+    stage_ms = {k: float(np.median([it[k] for it in per_iter])) for k in per_iter[0]}     # median over the profiled steps
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
