@@ -22,7 +22,8 @@ const int8_t h_pattern[1024] = {
 };
 
 struct DescParams {
-    PyrView raw, blur;
+    CUtensorMap mapRaw[ORBF_MAX_LEVELS], mapBlur[ORBF_MAX_LEVELS];    // 64 x 39 windows (raw level 0 = caller's plane: z = slot - z0)
+    int z0;
     const uint32_t* lkp; const int* lkpCount;
     int kpStageTotal, K, slot0, L;
     int kpOff[ORBF_MAX_LEVELS]; float scale[ORBF_MAX_LEVELS]; int scaledPatch[ORBF_MAX_LEVELS];
@@ -55,102 +56,130 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-constexpr int DS_WARPS = 4;
+constexpr int DS_WARPS = 4, DS_KPW = 8;     // keypoints per warp: window of keypoint k+1 is in flight while keypoint k is computed
+constexpr int DS_WIN_BYTES = (ORBF_PATCH_BW * ORBF_PATCH_BH + 127) / 128 * 128;     // TMA destinations: 128-byte aligned
 
-__global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(DescParams P)
+struct KpLoc { int level, x, y, score; };
+
+// keypoint i of the frame (level-major, quadtree list order inside a level): its level and integer level coordinates
+__device__ __forceinline__ KpLoc locate(const DescParams& P, const int* lc, int slot, int i, int& total)
+{
+    KpLoc k; k.level = -1; k.x = k.y = k.score = 0;
+    int before = 0; total = 0;
+    for (int l = 0; l < P.L; ++l) {
+        const int c = lc[l];
+        if (k.level < 0 && i < total + c) { k.level = l; before = total; }
+        total += c;
+    }
+    if (k.level >= 0) {
+        const uint32_t key = P.lkp[(long long)slot * P.kpStageTotal + P.kpOff[k.level] + (i - before)];
+        k.x = (int)(key & 0x7FF) + ORBF_MINB; k.y = (int)((key >> 11) & 0x7FF) + ORBF_MINB; k.score = (int)(key >> 22);
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_constant__ DescParams P)
 {
     __shared__ float4 sPat[256];
     __shared__ uint32_t sCoef[16];
+    // per warp, double buffered: the keypoint's 64 x 39 windows of the raw level (orientation) and the blurred level
+    // (descriptor), fetched by two TMA box loads — ~80 sectors per window instead of ~450 scattered byte gathers through L1
+    __shared__ __align__(128) uint8_t sWin[DS_WARPS][2][2][DS_WIN_BYTES];
+    __shared__ __align__(8) uint64_t sBar[DS_WARPS][2];
     for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) sPat[i] = g_patF[i];
     if (threadIdx.x < 16) sCoef[threadIdx.x] = g_icCoef[threadIdx.x];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { mbar_init(&sBar[warp][0], 1); mbar_init(&sBar[warp][1], 1); }
+    __syncthreads();
     const int slot = P.slot0 + blockIdx.y;
-    const int i = blockIdx.x * DS_WARPS + warp;
     const int* lc = P.lkpCount + slot * ORBF_MAX_LEVELS;
-    int level = -1, before = 0, total = 0;
-    for (int l = 0; l < P.L; ++l) {
-        const int c = lc[l];
-        if (level < 0 && i < total + c) { level = l; before = total; }
-        total += c;
-    }
-    if (i == 0 && lane == 0) P.count[slot] = total;
-    if (level < 0) return;
-    const uint32_t key = P.lkp[(long long)slot * P.kpStageTotal + P.kpOff[level] + (i - before)];
-    const int x = (int)(key & 0x7FF) + ORBF_MINB, y = (int)((key >> 11) & 0x7FF) + ORBF_MINB;
-    const int score = (int)(key >> 22);
-
-    // ---- orientation: lane = patch column u = lane - 15 (each row is one coalesced <= 31-byte read) --------------------
-    // The patch is a disc, so column u spans rows |v| <= umax[|u|]: one compare against a per-lane bound, no table reads;
-    // sum(u * I) is u * (column sum), formed once after the loop.
-    const LevelView rv = P.raw.lv[level];
-    int m10 = 0, m01 = 0;
-    {
-        const int u = lane - ORBF_HALF_PATCH;
-        const int dv = lane < 31 ? (int)(sCoef[min(abs(u), ORBF_HALF_PATCH)]) : -1;    // sCoef[0..15] = umax
-        const uint8_t* p = rv.base + (long long)slot * rv.frameStride + (long long)(y - ORBF_HALF_PATCH) * rv.pitch + (x + u);
-        int colSum = 0;
-#pragma unroll
-        for (int v = -ORBF_HALF_PATCH; v <= ORBF_HALF_PATCH; ++v) {
-            if ((v < 0 ? -v : v) <= dv) {
-                const int val = __ldg(p);
-                colSum += val;
-                m01 += v * val;
-            }
-            p += rv.pitch;
-        }
-        m10 = u * colSum;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- steered BRIEF ------------------------------------------------------------------------------
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    const float ar = __fmul_rn(angle, factorPI);
-    double sn, cs;
-    sincos((double)ar, &sn, &cs);
-    const float a = (float)cs, b = (float)sn;
-    const LevelView bv = P.blur.lv[level];
-    const uint8_t* cb = bv.base + (long long)slot * bv.frameStride + (long long)y * bv.pitch + x;
-    int val = 0;
-    // cvRound (round-half-even) without the conversion pipe: |v| <= 13 * sqrt(2) * 2 << 2^22, so adding 1.5 * 2^23 leaves the
-    // rounded integer in the low mantissa bits (FADD on the FMA pipe + IADD instead of F2I on the quarter-rate XU pipe)
+    const int base = (blockIdx.x * DS_WARPS + warp) * DS_KPW;
+    int total;
+    KpLoc cur = locate(P, lc, slot, base, total);
+    if (base == 0 && lane == 0) P.count[slot] = total;
+    auto fetch = [&](const KpLoc& k, int buf) {       // lane 0 only
+        const int xs = (k.x - ORBF_EDGE) & ~15;       // TMA boxes of bytes start on 16-byte boundaries
+        mbar_expect_tx(&sBar[warp][buf], 2 * ORBF_PATCH_BW * ORBF_PATCH_BH);
+        tma_load_3d(sWin[warp][buf][0], &P.mapRaw[k.level], xs, k.y - ORBF_EDGE, k.level == 0 ? slot - P.z0 : slot, &sBar[warp][buf]);
+        tma_load_3d(sWin[warp][buf][1], &P.mapBlur[k.level], xs, k.y - ORBF_EDGE, slot, &sBar[warp][buf]);
+    };
+    if (cur.level >= 0 && lane == 0) fetch(cur, 0);
     const float kMagic = 12582912.f;
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+#pragma unroll 1
+    for (int it = 0; it < DS_KPW && cur.level >= 0; ++it) {
+        const int i = base + it, buf = it & 1;
+        KpLoc nxt; nxt.level = -1;
+        if (it + 1 < DS_KPW) { int t2; nxt = locate(P, lc, slot, i + 1, t2); }
+        if (nxt.level >= 0 && lane == 0) fetch(nxt, buf ^ 1);
+        __syncwarp();
+        mbar_wait(&sBar[warp][buf], (it >> 1) & 1);
+        const int level = cur.level, x = cur.x, y = cur.y;
+        const int cx0 = x - ((x - ORBF_EDGE) & ~15);                      // window column of the keypoint
+        // ---- orientation: lane = patch column u = lane - 15; the disc spans rows |v| <= umax[|u|] in column u -------------
+        int m10 = 0, m01 = 0;
+        {
+            const int u = lane - ORBF_HALF_PATCH;
+            const int dv = lane < 31 ? (int)(sCoef[min(abs(u), ORBF_HALF_PATCH)]) : -1;
+            const uint8_t* p = sWin[warp][buf][0] + (ORBF_EDGE - ORBF_HALF_PATCH) * ORBF_PATCH_BW + cx0 + u;
+            int colSum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float4 w = sPat[k * 32 + lane];
-        const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.x, b), __fmul_rn(w.y, a)), kMagic)) - 0x4B400000;
-        const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.x, a), __fmul_rn(w.y, b)), kMagic)) - 0x4B400000;
-        const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.z, b), __fmul_rn(w.w, a)), kMagic)) - 0x4B400000;
-        const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.z, a), __fmul_rn(w.w, b)), kMagic)) - 0x4B400000;
-        const int t0 = __ldg(cb + r0 * bv.pitch + c0), t1 = __ldg(cb + r1 * bv.pitch + c1);
-        val |= (t0 < t1) << k;
-    }
-    const long long o = (long long)slot * P.K + i;
-    P.desc[o * 32 + lane] = (uint8_t)val;
-
-    // ---- keypoint record + depth unprojection ----------------------------------------------------------
-    if (lane == 0) {
-        float fx = (float)x, fy = (float)y;
-        if (level != 0) { fx = __fmul_rn(fx, P.scale[level]); fy = __fmul_rn(fy, P.scale[level]); }
-        P.kpx[o] = fx; P.kpy[o] = fy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
-        P.kpresp[o] = (float)score; P.kpoct[o] = level; P.kplxy[o] = (uint32_t)x | ((uint32_t)y << 16);
-        float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
-        if (P.depth) {
-            const int ui = (int)fx, vi = (int)fy;     // float -> int truncation of the (distorted) keypoint (frame.cpp:155)
-            if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
-                const float z = __fmul_rn((float)__ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui),
-                    P.depthFactor);
-                if (z > 0) {
-                    ur = __fsub_rn(fx, __fdiv_rn(P.mbf, z));
-                    X = __fmul_rn(__fmul_rn(__fsub_rn(fx, P.cx), z), P.invfx);
-                    Y = __fmul_rn(__fmul_rn(__fsub_rn(fy, P.cy), z), P.invfy);
-                    Z = z;
+            for (int v = -ORBF_HALF_PATCH; v <= ORBF_HALF_PATCH; ++v) {
+                if ((v < 0 ? -v : v) <= dv) {
+                    const int val = p[(v + ORBF_HALF_PATCH) * ORBF_PATCH_BW];
+                    colSum += val;
+                    m01 += v * val;
                 }
             }
+            m10 = u * colSum;
         }
-        P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // ---- steered BRIEF: (x*b + y*a, x*a - y*b) with separate mul / add, cvRound = round-half-even via the 1.5 * 2^23 trick
+        // (FADD on the FMA pipe + IADD instead of F2I on the quarter-rate XU pipe; |v| <= 19 << 2^22) ------------------------
+        const float ar = __fmul_rn(angle, factorPI);
+        double sn, cs;
+        sincos((double)ar, &sn, &cs);
+        const float a = (float)cs, b = (float)sn;
+        const uint8_t* cb = sWin[warp][buf][1] + ORBF_EDGE * ORBF_PATCH_BW + cx0;
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 w = sPat[k * 32 + lane];
+            const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.x, b), __fmul_rn(w.y, a)), kMagic)) - 0x4B400000;
+            const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.x, a), __fmul_rn(w.y, b)), kMagic)) - 0x4B400000;
+            const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.z, b), __fmul_rn(w.w, a)), kMagic)) - 0x4B400000;
+            const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.z, a), __fmul_rn(w.w, b)), kMagic)) - 0x4B400000;
+            const int t0 = cb[r0 * ORBF_PATCH_BW + c0], t1 = cb[r1 * ORBF_PATCH_BW + c1];
+            val |= (t0 < t1) << k;
+        }
+        const long long o = (long long)slot * P.K + i;
+        P.desc[o * 32 + lane] = (uint8_t)val;
+        // ---- keypoint record + depth unprojection ------------------------------------------------------------------------
+        if (lane == 0) {
+            float fx = (float)x, fy = (float)y;
+            if (level != 0) { fx = __fmul_rn(fx, P.scale[level]); fy = __fmul_rn(fy, P.scale[level]); }
+            P.kpx[o] = fx; P.kpy[o] = fy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
+            P.kpresp[o] = (float)cur.score; P.kpoct[o] = level; P.kplxy[o] = (uint32_t)x | ((uint32_t)y << 16);
+            float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
+            if (P.depth) {
+                const int ui = (int)fx, vi = (int)fy;     // float -> int truncation of the (distorted) keypoint (frame.cpp:155)
+                if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
+                    const float z = __fmul_rn((float)__ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui),
+                        P.depthFactor);
+                    if (z > 0) {
+                        ur = __fsub_rn(fx, __fdiv_rn(P.mbf, z));
+                        X = __fmul_rn(__fmul_rn(__fsub_rn(fx, P.cx), z), P.invfx);
+                        Y = __fmul_rn(__fmul_rn(__fsub_rn(fy, P.cy), z), P.invfy);
+                        Z = z;
+                    }
+                }
+            }
+            P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;
+        }
+        __syncwarp();                                   // every lane is done with this buffer before it is refilled
+        cur = nxt;
     }
 }
 
@@ -183,8 +212,13 @@ int orbf_launch_describe(orbf_context* c, int slot0, int n)
         ORBF_CUDA(c, cudaMemcpyToSymbol(g_icCoef, coef, sizeof(coef)));
         g_constReady[dev] = true;
     }
+    {
+        const int r = orbf_refresh_maps(c);
+        if (r != ORBF_OK) return r;
+    }
     DescParams P;
-    P.raw = orbf_pyr_view(c, false); P.blur = orbf_pyr_view(c, true);
+    for (int l = 0; l < c->L; ++l) { P.mapRaw[l] = c->tmPatchRaw[l]; P.mapBlur[l] = c->tmPatchBlur[l]; }
+    P.z0 = c->cur_slot0;
     P.lkp = c->d_lkp; P.lkpCount = c->d_lkpCount; P.kpStageTotal = c->kpStageTotal; P.K = c->K; P.slot0 = slot0; P.L = c->L;
     for (int l = 0; l < c->L; ++l) { P.kpOff[l] = c->lg[l].kpOff; P.scale[l] = c->scale[l]; P.scaledPatch[l] = c->lg[l].scaledPatch; }
     P.kpx = c->d_kpx; P.kpy = c->d_kpy; P.kpsize = c->d_kpsize; P.kpangle = c->d_kpangle; P.kpresp = c->d_kpresp;
@@ -197,7 +231,7 @@ int orbf_launch_describe(orbf_context* c, int slot0, int n)
     P.width = c->cfg.width; P.height = c->cfg.height;
     P.cx = c->cfg.cx; P.cy = c->cfg.cy; P.invfx = 1.0f / c->cfg.fx; P.invfy = 1.0f / c->cfg.fy;
     P.mbf = c->cfg.mbf; P.depthFactor = c->cfg.depth_factor;
-    dim3 grid((c->K + DS_WARPS - 1) / DS_WARPS, n);
+    dim3 grid((c->K + DS_WARPS * DS_KPW - 1) / (DS_WARPS * DS_KPW), n);
     describe_kernel<<<grid, DS_WARPS * 32, 0, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;

@@ -21,6 +21,8 @@
 #define ORBF_MINB 16          // EDGE_THRESHOLD - 3 (orbextractor.cpp:672)
 #define ORBF_HALF_PATCH 15
 #define ORBF_MAX_SAMPLE 8
+#define ORBF_PATCH_BW 64      // describe.cu: TMA box of a keypoint window, (2 * 19 + 1) rows x 64 bytes
+#define ORBF_PATCH_BH 39
 #define ORBF_MAX_WORKERS 4    // internal worker streams of the chunked pipeline (c_abi.cu)
 
 struct LevelView {
@@ -105,6 +107,7 @@ struct orbf_context {
     // TMA descriptors: FAST / blur read level l, resize reads level l-1; those over the caller's input plane (FAST 0, blur 0,
     // resize 1) are re-encoded whenever the input pointer / pitch / frame count changes
     CUtensorMap tmFast[ORBF_MAX_LEVELS], tmBlur[ORBF_MAX_LEVELS], tmResize[ORBF_MAX_LEVELS]; bool tmStaticReady;
+    CUtensorMap tmPatchRaw[ORBF_MAX_LEVELS], tmPatchBlur[ORBF_MAX_LEVELS];   // 64 x 39 keypoint windows of the raw / blurred levels (describe.cu)
     const void* tm0Base; long long tm0Pitch, tm0FrameStride; int tm0Frames;                  // what the input-plane maps were encoded for
     LevelGeom* d_lg;
     uint32_t* d_cellCand; int* d_cellCount;
