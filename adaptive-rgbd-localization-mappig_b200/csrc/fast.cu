@@ -5,9 +5,10 @@
 // one CTA of 4 warps per (strip, frame), all levels in one launch:
 //   0. one thread fetches the strip + 3-px ring halo with a single TMA box load (cp.async.bulk.tensor.3d -> UTMALDG);
 //      a u8 box must start on a 16-byte boundary of the level row, so the interior begins at tile column ax in [3, 18];
-//   1. pretest, 4 pixels per thread on packed u16x2 lanes (VIMNMX.U16x2): a 9-arc contains one pixel of each opposite
-//      pair, so min(max(p0,p8), max(p4,p12)) > v+th or max(min(p0,p8), min(p4,p12)) < v-th is necessary; survivors
-//      (17 % of the pixels on the bench texture) are appended to a CTA-wide list (shared-memory atomics);
+//   1. pretest, 4 pixels per thread, byte-parallel: a 9-arc contains one pixel of each opposite ring pair, so for the four
+//      pairs (0,8) (4,12) (2,10) (6,14) at least one member must differ from the centre by more than th.  |r - v| for 4
+//      pixels is one VABSDIFF4, "> th" a carry trick into bit 7 of each byte; 8 % of the pixels of the bench texture
+//      survive (true corners: 3.5 %) and are appended to a CTA-wide list (shared-memory atomics);
 //   2. corner strength of two survivors at a time on packed u16x2 lanes with 3-input min/max (VIMNMX3.U16x2):
 //      S = max(v - A, B - v), A = min over the 16 arcs of the arc maximum, B = max over the arcs of the arc minimum
 //      (cv::FAST response = S - 1, corner iff S > th); 80 packed ops per pixel pair;
@@ -90,29 +91,41 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     {
         const int wFirst = ax >> 2, wpr = ((ax + W + 3) >> 2) - wFirst, nTasks = h * wpr;
         const uint32_t rcp = ((1u << 20) + wpr - 1) / wpr;
-        const uint32_t th1 = (uint32_t)(th + 1) * 0x00010001u;
+        // per byte x = |r - v|: bit 7 of ((x & 0x7f) + K) | x (th < 128, K = 127 - th) or of ((x & 0x7f) + K) & x (th >= 128,
+        // K = 255 - th) is set iff x > th
+        const bool hiTh = th >= 128;
+        const uint32_t K = (uint32_t)(hiTh ? 255 - th : 127 - th) * 0x01010101u, M7 = 0x7F7F7F7Fu;
         for (int t = tid; t < nTasks; t += FS_THREADS) {
             const int row = (int)(((uint32_t)t * rcp) >> 20), wi = wFirst + (t - row * wpr);
             const uint32_t* c = reinterpret_cast<const uint32_t*>(tile + (row + 3) * BW) + wi;
-            const uint32_t Cp = c[-1], C = c[0], Cn = c[1];                 // word -1 of tile row >= 3 is still inside the tile
-            const uint32_t U = *reinterpret_cast<const uint32_t*>(tile + row * BW + 4 * wi);
-            const uint32_t D = *reinterpret_cast<const uint32_t*>(tile + (row + 6) * BW + 4 * wi);
-            const uint32_t L = __funnelshift_r(Cp, C, 8), R = __funnelshift_r(C, Cn, 24);          // pixels x-3 / x+3 of the 4 centres
-            const uint32_t f01 = pretest_x2(__byte_perm(C, 0, 0x4140), __byte_perm(D, 0, 0x4140), __byte_perm(U, 0, 0x4140),
-                __byte_perm(R, 0, 0x4140), __byte_perm(L, 0, 0x4140), th1);
-            const uint32_t f23 = pretest_x2(__byte_perm(C, 0, 0x4342), __byte_perm(D, 0, 0x4342), __byte_perm(U, 0, 0x4342),
-                __byte_perm(R, 0, 0x4342), __byte_perm(L, 0, 0x4342), th1);
-            uint32_t flags = ((f01 & 0xFFFFu) == 0 ? 1u : 0u) | ((f01 >> 16) == 0 ? 2u : 0u) | ((f23 & 0xFFFFu) == 0 ? 4u : 0u) | ((f23 >> 16) == 0 ? 8u : 0u);
+            const uint32_t C = c[0];
+            const uint32_t* u2 = reinterpret_cast<const uint32_t*>(tile + (row + 1) * BW) + wi;     // image row y - 2
+            const uint32_t* d2 = reinterpret_cast<const uint32_t*>(tile + (row + 5) * BW) + wi;     // image row y + 2
+            uint32_t ad[8];
+            ad[0] = __vabsdiffu4(*reinterpret_cast<const uint32_t*>(tile + (row + 6) * BW + 4 * wi), C);     // ring 0  ( 0, +3)
+            ad[1] = __vabsdiffu4(*reinterpret_cast<const uint32_t*>(tile + row * BW + 4 * wi), C);           // ring 8  ( 0, -3)
+            ad[2] = __vabsdiffu4(__funnelshift_r(C, c[1], 24), C);                                           // ring 4  (+3,  0)
+            ad[3] = __vabsdiffu4(__funnelshift_r(c[-1], C, 8), C);                                           // ring 12 (-3,  0); word -1 of tile row >= 3 is inside the tile
+            ad[4] = __vabsdiffu4(__funnelshift_r(d2[0], d2[1], 16), C);                                      // ring 2  (+2, +2)
+            ad[5] = __vabsdiffu4(__funnelshift_r(u2[-1], u2[0], 16), C);                                     // ring 10 (-2, -2)
+            ad[6] = __vabsdiffu4(__funnelshift_r(u2[0], u2[1], 16), C);                                      // ring 6  (+2, -2)
+            ad[7] = __vabsdiffu4(__funnelshift_r(d2[-1], d2[0], 16), C);                                     // ring 14 (-2, +2)
+            uint32_t all = 0x80808080u;
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const uint32_t ta = (ad[k] & M7) + K, tb = (ad[k + 1] & M7) + K;
+                all &= hiTh ? ((ta & ad[k]) | (tb & ad[k + 1])) : (ta | tb | ad[k] | ad[k + 1]);
+            }
             const int xi = 4 * wi - ax;                                     // interior x of byte 0: mask pixels outside [0, W)
-            if (xi < 0) flags &= 0xFu << (-xi);
-            if (W - xi < 4) flags &= (1u << (W - xi)) - 1;
-            if (flags) {
-                int pos = atomicAdd(&sCount, __popc(flags));
+            if (xi < 0) all &= 0xFFFFFFFFu << (8 * (-xi));
+            if (W - xi < 4) all &= 0xFFFFFFFFu >> (8 * (4 - (W - xi)));
+            if (all) {
+                int pos = atomicAdd(&sCount, __popc(all));
                 const int e = row * BW + 4 * wi;
-                if (flags & 1) list[pos++] = (uint16_t)e;
-                if (flags & 2) list[pos++] = (uint16_t)(e + 1);
-                if (flags & 4) list[pos++] = (uint16_t)(e + 2);
-                if (flags & 8) list[pos] = (uint16_t)(e + 3);
+                if (all & 0x80u) list[pos++] = (uint16_t)e;
+                if (all & 0x8000u) list[pos++] = (uint16_t)(e + 1);
+                if (all & 0x800000u) list[pos++] = (uint16_t)(e + 2);
+                if (all & 0x80000000u) list[pos] = (uint16_t)(e + 3);
             }
         }
     }
