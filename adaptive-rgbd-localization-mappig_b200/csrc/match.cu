@@ -52,13 +52,12 @@ __device__ __forceinline__ uint32_t hamming256_csa(const uint32_t q[8], const ui
 }
 
 template <bool CROSS>
-__global__ void __launch_bounds__(KN_THREADS) knn2_kernel(MatchSet ms, int K)
+__global__ void __launch_bounds__(KN_THREADS, 6) knn2_kernel(MatchSet ms, int K)
 {
     uint32_t* __restrict__ knn = ms.knn;
     uint32_t* __restrict__ rev = ms.rev;
     __shared__ __align__(16) uint32_t sT[KN_CHUNK * 8];
     __shared__ uint32_t sRev[CROSS ? KN_CHUNK : 1];
-    __shared__ uint32_t sMerge[KN_WARPS][KN_R][2][32];
     const int pair = ms.pair0 + blockIdx.y;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
@@ -121,7 +120,9 @@ __global__ void __launch_bounds__(KN_THREADS) knn2_kernel(MatchSet ms, int K)
                 if (sRev[i] != KEY_NONE) atomicMin(&rev[(long long)pair * K + c0 + i], sRev[i]);
         }
     }
-    // merge the warps' partial top-2 lists
+    // merge the warps' partial top-2 lists (the staging area aliases the train rows, which are no longer needed)
+    __syncthreads();
+    uint32_t (*sMerge)[KN_R][2][32] = reinterpret_cast<uint32_t (*)[KN_R][2][32]>(sT);
 #pragma unroll
     for (int r = 0; r < KN_R; ++r) { sMerge[warp][r][0][lane] = m1[r]; sMerge[warp][r][1][lane] = m2[r]; }
     __syncthreads();
