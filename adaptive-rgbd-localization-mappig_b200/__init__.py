@@ -34,7 +34,8 @@ class Config(C.Structure):
                 ("scale_factor", C.c_float), ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
                 ("max_frames", C.c_int32), ("max_pairs", C.c_int32), ("device", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
-                ("depth_factor", C.c_float), ("pipeline_chunk", C.c_int32), ("pipeline_streams", C.c_int32)]
+                ("depth_factor", C.c_float), ("pipeline_chunk", C.c_int32), ("pipeline_streams", C.c_int32),
+                ("depth_zero_copy", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class RansacConfig(C.Structure):

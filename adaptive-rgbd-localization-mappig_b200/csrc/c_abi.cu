@@ -94,6 +94,7 @@ struct Pipeline {
 struct HostFrames {    // host-side input of a batched call (NULL gray => inputs are already on the device)
     const uint8_t* gray; int64_t grayStride, grayFrameStride;
     const uint16_t* depth; int64_t depthStride, depthFrameStride;
+    bool depthInPlace;     // depth stays in pinned host memory and is sampled over PCIe (orbf_config.depth_zero_copy)
 };
 
 static int upload_chunk(orbf_context* c, const HostFrames& hf, int slotA, int first, int n)
@@ -108,7 +109,7 @@ static int upload_chunk(orbf_context* c, const HostFrames& hf, int slotA, int fi
             ORBF_CUDA(c, cudaMemcpy2DAsync(dIn + (size_t)i * c->inPlane, c->inPitch, g + (size_t)i * hf.grayFrameStride, hf.grayStride, w, h,
                 cudaMemcpyHostToDevice, c->stream));
     }
-    if (hf.depth) {
+    if (hf.depth && !hf.depthInPlace) {
         uint16_t* dDepth = c->d_depthIn + (size_t)slotA * w * h;
         const uint16_t* d = hf.depth + (size_t)first * hf.depthFrameStride;
         if (hf.depthStride == w && hf.depthFrameStride == (int64_t)w * h) {
@@ -184,12 +185,17 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
             if (pb > pa) {
                 if (pl.active && a > 0 && prevWorker != wk) ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evExtract[prevWorker], 0));
                 TRY(run_match_group(c, pa, pb - pa, track->ratio, track->cross));
-                if (track->rcfg) TRY(orbf_launch_ransac(c, slot_ransac_set(c), pa, pb - pa, *track->rcfg, nullptr, pa == 0 ? 0 : 1));
+                // RANSAC is a chain of ten latency-bound launches whose duration barely depends on the number of pairs: per
+                // chunk it would be paid once per chunk, so the pipelined path runs it once, after the join, for all pairs
+                if (track->rcfg && !pl.active) TRY(orbf_launch_ransac(c, slot_ransac_set(c), pa, pb - pa, *track->rcfg, nullptr, pa == 0 ? 0 : 1));
             }
         }
         prevWorker = wk;
     }
-    return pl.end();
+    const bool deferred = pl.active;
+    TRY(pl.end());
+    if (deferred && track && npairs > 0 && track->rcfg) TRY(orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *track->rcfg, nullptr, 0));
+    return ORBF_OK;
 }
 
 static int set_device_inputs(orbf_context* c, int slot0, int n, const uint8_t* d_gray, int64_t gray_pitch, int64_t gray_frame_stride,
@@ -214,6 +220,18 @@ static int set_host_inputs(orbf_context* c, int slot0, int n, const uint8_t* gra
     hf.depth = depth; hf.depthStride = depth_stride_elems; hf.depthFrameStride = depth_frame_stride_elems;
     c->cur_gray = c->d_in + (size_t)slot0 * c->inPlane; c->cur_grayPitch = c->inPitch; c->cur_grayFrameStride = (long long)c->inPlane;
     c->cur_depth = depth ? c->d_depthIn + (size_t)slot0 * w * h : nullptr; c->cur_depthPitch = w; c->cur_depthFrameStride = (long long)w * h;
+    hf.depthInPlace = false;
+    if (depth && c->cfg.depth_zero_copy >= 0) {
+        // A frame needs ~1000 of its 307,200 depth samples (Core/frame.cpp:155: one lookup per keypoint).  When the caller's
+        // plane is page-locked, the unprojection reads those samples in place through the unified address space instead of
+        // staging 614 KB per frame in HBM: the PCIe link carries 1/3 of the bytes.
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, depth) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            hf.depthInPlace = true;
+            c->cur_depth = static_cast<const uint16_t*>(at.devicePointer);
+            c->cur_depthPitch = (int)depth_stride_elems; c->cur_depthFrameStride = depth_frame_stride_elems;
+        } else cudaGetLastError();      // pageable memory: not an error, stage it
+    }
     c->cur_slot0 = slot0; c->cur_n = n;
     return ORBF_OK;
 }

@@ -93,7 +93,7 @@ extern "C" void orbf_default_config(orbf_config* c)
     c->fx = 517.3f; c->fy = 516.5f; c->cx = 318.6f; c->cy = 255.3f;   // Utils/common.h:35-38 (FR1)
     c->mbf = 40.0f;
     c->depth_factor = 1.0f / 5000.0f;
-    c->pipeline_chunk = 0; c->pipeline_streams = 0;
+    c->pipeline_chunk = 0; c->pipeline_streams = 0; c->depth_zero_copy = 0; c->reserved_ = 0;
 }
 
 extern "C" void orbf_default_ransac_config(orbf_ransac_config* c)
@@ -275,7 +275,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->nWork = 0; c->evFork = nullptr; c->evLatch = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
     for (int i = 0; i < 8; ++i) c->evHiGroup[i] = nullptr;
     for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
-    c->chunkFrames = cfg->pipeline_chunk == 0 ? 64 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
+    c->chunkFrames = cfg->pipeline_chunk == 0 ? 96 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;

@@ -116,6 +116,19 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         mbar_wait(&sBar[warp][buf], (it >> 1) & 1);
         const int level = cur.level, x = cur.x, y = cur.y;
         const int cx0 = x - ((x - ORBF_EDGE) & ~15);                      // window column of the keypoint
+        // depth sample of the keypoint (Core/frame.cpp:155), requested first: when the plane lives in pinned host memory the
+        // read crosses PCIe (~2 us) and completes behind the orientation / descriptor work below
+        float kfx = (float)x, kfy = (float)y;
+        if (level != 0) { kfx = __fmul_rn(kfx, P.scale[level]); kfy = __fmul_rn(kfy, P.scale[level]); }
+        unsigned short rawDepth = 0;
+        bool haveDepth = false;
+        if (lane == 0 && P.depth) {
+            const int ui = (int)kfx, vi = (int)kfy;     // float -> int truncation of the (distorted) keypoint
+            if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
+                rawDepth = __ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui);
+                haveDepth = true;
+            }
+        }
         // ---- orientation: lane = patch column u = lane - 15; the disc spans rows |v| <= umax[|u|] in column u -------------
         int m10 = 0, m01 = 0;
         {
@@ -158,22 +171,17 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         P.desc[o * 32 + lane] = (uint8_t)val;
         // ---- keypoint record + depth unprojection ------------------------------------------------------------------------
         if (lane == 0) {
-            float fx = (float)x, fy = (float)y;
-            if (level != 0) { fx = __fmul_rn(fx, P.scale[level]); fy = __fmul_rn(fy, P.scale[level]); }
+            const float fx = kfx, fy = kfy;
             P.kpx[o] = fx; P.kpy[o] = fy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
             P.kpresp[o] = (float)cur.score; P.kpoct[o] = level; P.kplxy[o] = (uint32_t)x | ((uint32_t)y << 16);
             float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
-            if (P.depth) {
-                const int ui = (int)fx, vi = (int)fy;     // float -> int truncation of the (distorted) keypoint (frame.cpp:155)
-                if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
-                    const float z = __fmul_rn((float)__ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui),
-                        P.depthFactor);
-                    if (z > 0) {
-                        ur = __fsub_rn(fx, __fdiv_rn(P.mbf, z));
-                        X = __fmul_rn(__fmul_rn(__fsub_rn(fx, P.cx), z), P.invfx);
-                        Y = __fmul_rn(__fmul_rn(__fsub_rn(fy, P.cy), z), P.invfy);
-                        Z = z;
-                    }
+            if (haveDepth) {
+                const float z = __fmul_rn((float)rawDepth, P.depthFactor);
+                if (z > 0) {
+                    ur = __fsub_rn(fx, __fdiv_rn(P.mbf, z));
+                    X = __fmul_rn(__fmul_rn(__fsub_rn(fx, P.cx), z), P.invfx);
+                    Y = __fmul_rn(__fmul_rn(__fsub_rn(fy, P.cy), z), P.invfy);
+                    Z = z;
                 }
             }
             P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;

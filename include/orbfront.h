@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define ORBF_MAX_LEVELS 16
-#define ORBF_ABI_VERSION 2
+#define ORBF_ABI_VERSION 3
 
 typedef enum {
     ORBF_OK = 0,
@@ -63,8 +63,12 @@ typedef struct {
     int32_t device;                    /* CUDA device ordinal                                    */
     float fx, fy, cx, cy, mbf;         /* Calibration:: (Utils/common.h:35-38,71)               */
     float depth_factor;                /* Calibration::depthFactor = 1/5000 (Utils/common.h:67) */
-    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default 64, < 0 = no chunking) */
+    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default 96, < 0 = no chunking) */
     int32_t pipeline_streams;          /* internal worker streams, 1..4 (0 = default 4)           */
+    int32_t depth_zero_copy;           /* host depth planes in pinned (page-locked) memory are not copied: the ~1000 depth
+                                          samples a frame needs are read in place over PCIe by the kernel that unprojects
+                                          the keypoints (0 = default on, -1 = always stage the whole plane in HBM)          */
+    int32_t reserved_;
 } orbf_config;
 
 typedef struct {

@@ -192,3 +192,30 @@ def test_keyframe_shards_gathered_into_one_store(ob, orc, texture):
         ctx.kfdb_attach_device(0, 0, 0)
     finally:
         ctx.close()
+
+
+def test_depth_sampled_in_place_from_pinned_memory_equals_staged_copy(ob, texture):
+    """orbf_config.depth_zero_copy: with page-locked host depth planes the unprojection reads its samples over PCIe instead
+    of staging the planes in HBM; results must be the same bytes as the staged path (and as pageable input)."""
+    import torch
+    n = 6
+    frames = np.stack([synth.make_frame(texture, 80 + i) for i in range(n)])
+    depths = np.stack([synth.make_depth(80 + i) for i in range(n)])
+    pg = torch.from_numpy(frames).pin_memory(); pd = torch.from_numpy(depths.view(np.int16)).pin_memory()
+    hg = pg.numpy(); hd = pd.numpy().view(np.uint16)
+    staged = ob.Context(max_frames=n, depth_zero_copy=-1, pipeline_chunk=2)
+    inplace = ob.Context(max_frames=n, pipeline_chunk=2)
+    try:
+        staged.track_sequence(hg, hd, 0.8, cross_check=True, seed=3)
+        inplace.track_sequence(hg, hd, 0.8, cross_check=True, seed=3)
+        for s in range(n):
+            a, b = inplace.download_frame(s), staged.download_frame(s)
+            assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b)), f"frame {s}"
+            assert np.any(a[2][:, 2] > 0), "depth must have been sampled"
+        for p in range(n - 1):
+            g, r = inplace.download_ransac(p), staged.download_ransac(p)
+            assert g["inliers"].tobytes() == r["inliers"].tobytes() and g["T12"].tobytes() == r["T12"].tobytes()
+        inplace.extract_batch(frames, depths)                       # pageable input on the same context: falls back to staging
+        assert all(x.tobytes() == y.tobytes() for x, y in zip(inplace.download_frame(1), staged.download_frame(1)))
+    finally:
+        staged.close(); inplace.close()

@@ -1,6 +1,6 @@
 #!/bin/bash
 # chunk / worker-stream sweep of the pipelined sequence call (authoring aid; run on the GPU box)
-for cs in "-1 1" "64 2" "64 3" "64 4" "128 2" "128 3" "128 4" "256 2" "256 4" "32 4"; do
+for cs in "64 2" "64 3" "64 4" "128 2" "128 3" "128 4" "256 2" "32 4" "96 4"; do
   set -- $cs
   python bench.py --steps 10 --warmup 3 --cpu-sample 0 --chunk $1 --streams $2 2>/dev/null | python -c "
 import json,sys
