@@ -347,10 +347,15 @@ extern "C" int orbf_adaptive_detect(orbf_context* c, const orbf_adaptive_config*
         rc = orbf_tma_encode_u8(c, &P.map, dIn, w, h, nb, pitch, (long long)pitch * h, SP_BW, SP_BH);
         if (rc != ORBF_OK) break;
         P.nFrames = nb;
+        // Floor of the response plane: one "too few" step below the lowest cell threshold covers almost every frame; a sub-batch
+        // whose controllers go lower is redone three steps down, then at the minimum threshold (each redo costs more: the
+        // lower the floor, the more pixels get a full corner score).
         const double minState = *std::min_element(st.begin(), st.end());
-        int floorTh = std::max((int)cfg->min_th, (int)(minState * cfg->dec * cfg->dec));      // covers two "too few" steps; retried below otherwise
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            P.floorTh = std::max(floorTh, 1);
+        const int floors[3] = { std::max((int)cfg->min_th, (int)(minState * cfg->dec)),
+            std::max((int)cfg->min_th, (int)(minState * cfg->dec * cfg->dec * cfg->dec)), (int)cfg->min_th };
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            if (attempt > 0 && floors[attempt] == floors[attempt - 1]) { if (attempt == 2) rc = ORBF_ERR_STATE; continue; }
+            P.floorTh = std::max(floors[attempt], 1);
             const int zero = 0;
             AD_CUDA(cudaMemcpyAsync(dUnder, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
             AD_CUDA(cudaMemcpyAsync(dThresh, st.data(), nCells * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -366,9 +371,8 @@ extern "C" int orbf_adaptive_detect(orbf_context* c, const orbf_adaptive_config*
             AD_CUDA(cudaMemcpyAsync(&under, dUnder, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             AD_CUDA(cudaStreamSynchronize(c->stream));
             AD_CUDA(cudaGetLastError());
-            if (!under) break;
-            if (attempt == 1) { rc = ORBF_ERR_STATE; break; }
-            floorTh = (int)cfg->min_th;                       // a cell went below the floor: redo the sub-batch at the minimum threshold
+            if (!under) { rc = ORBF_OK; break; }
+            rc = ORBF_ERR_STATE;                              // stays only if even the minimum-threshold plane was not enough
         }
         if (rc != ORBF_OK) break;
         std::vector<double> stNew(nCells);
