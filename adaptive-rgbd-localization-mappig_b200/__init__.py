@@ -369,6 +369,13 @@ class Context:
         self._chk(lib().orbf_kfdb_attach_device(self._h, C.c_void_p(d_desc_ptr) if d_desc_ptr else None,
                                                 C.c_void_p(d_counts_ptr) if d_counts_ptr else None, n_kf), "kfdb_attach_device")
 
+    def kfdb_survivors(self, q, kf0, nkf, ratio):
+        """Number of ratio-test survivors of the query against each keyframe (no top-2 tables downloaded)."""
+        q = np.ascontiguousarray(q, np.uint8)
+        surv = np.zeros(nkf, np.int32)
+        self._chk(lib().orbf_kfdb_match(self._h, _p(q), len(q), kf0, nkf, C.c_float(ratio), None, None, None, None, _p(surv)), "kfdb_match")
+        return surv
+
     def kfdb_match(self, q, kf0, nkf, ratio):
         q = np.ascontiguousarray(q, np.uint8)
         o = [np.zeros((nkf, len(q)), np.int32) for _ in range(4)]; surv = np.zeros(nkf, np.int32)

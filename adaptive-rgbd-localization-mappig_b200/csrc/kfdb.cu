@@ -117,10 +117,12 @@ extern "C" int orbf_kfdb_match(orbf_context* c, const uint8_t* q, int32_t nq, in
     ms.knn = c->d_kfKnn; ms.rev = nullptr; ms.matches = nullptr; ms.matchCount = c->d_kfSurv;
     TRY(orbf_launch_knn2(c, ms, nkf, false));
     TRY(orbf_launch_match_select(c, ms, nkf, ratio, false));
-    std::vector<uint32_t> kk((size_t)nkf * c->K * 2);
-    ORBF_CUDA(c, cudaMemcpyAsync(kk.data(), c->d_kfKnn, kk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    const bool wantTables = idx1 || d1 || idx2 || d2;       // survivor counts alone (keyframe ranking) skip the 8 KB-per-keyframe tables
+    std::vector<uint32_t> kk(wantTables ? (size_t)nkf * c->K * 2 : 0);
+    if (wantTables) ORBF_CUDA(c, cudaMemcpyAsync(kk.data(), c->d_kfKnn, kk.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     if (survivors) ORBF_CUDA(c, cudaMemcpyAsync(survivors, c->d_kfSurv, (size_t)nkf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!wantTables) return ORBF_OK;
     for (int k = 0; k < nkf; ++k)
         for (int i = 0; i < nq; ++i) {
             const uint32_t a = kk[((size_t)k * c->K + i) * 2], b = kk[((size_t)k * c->K + i) * 2 + 1];

@@ -199,7 +199,8 @@ int orbf_kfdb_device_buffers(orbf_context* ctx, uint8_t** d_desc, int32_t** d_co
  * NCCL all-gather of every rank's shard (BASELINE config 5).  Not owned by the context; NULL detaches.           */
 int orbf_kfdb_attach_device(orbf_context* ctx, const uint8_t* d_desc, const int32_t* d_counts, int32_t n_kf);
 /* query (host, nq x 32) against keyframes [kf0, kf0+nkf): per keyframe top-2 per query and the number of
- * ratio survivors (out arrays sized nkf x nq, counts sized nkf).                                      */
+ * ratio survivors (out arrays sized nkf x nq, counts sized nkf).  With all four table pointers NULL only the survivor
+ * counts are produced and downloaded (keyframe ranking).                                                */
 int orbf_kfdb_match(orbf_context* ctx, const uint8_t* q, int32_t nq, int32_t kf0, int32_t nkf, float ratio,
     int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors);
 

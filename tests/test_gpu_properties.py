@@ -119,6 +119,7 @@ def test_config5_query_against_2048_keyframes(ob, orc, texture):
             rows = np.arange(j, nkf, 6)
             assert np.all(i1[rows] == r[0]) and np.all(d1[rows] == r[1]) and np.all(i2[rows] == r[2]) and np.all(d2[rows] == r[3])
             assert np.all(surv[rows] == len(orc.knn_match(q, base[j], 0.8)))
+        assert np.array_equal(ctx.kfdb_survivors(q, 0, nkf, 0.8), surv)
     finally:
         ctx.close()
 

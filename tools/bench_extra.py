@@ -79,4 +79,14 @@ dt = timed(lambda: ctx.kfdb_match(q, 0, nkf, 0.8), reps=3, warm=1)
 out["kfdb_query_vs_2048_keyframes"] = {"ms_per_query_incl_d2h_of_top2_tables": dt * 1e3, "descriptor_pairs": pairs, "pairs_per_s": pairs / dt,
                                        "note": "includes the D2H of 2048 x 1056 x 2 top-2 entries (17 MB) and host unpacking"}
 ctx.close()
+ctx2 = ob.Context(max_frames=8)
+ctx2.extract_batch(fr)
+ctx2.kfdb_reserve(nkf)
+for k in range(nkf):
+    ctx2.kfdb_add_from_slot(k, k % 8)
+ctx2.synchronize()
+dt = timed(lambda: ctx2.kfdb_survivors(q, 0, nkf, 0.8), reps=5, warm=2)
+out["kfdb_query_vs_2048_keyframes_survivor_counts_only"] = {"ms_per_query": dt * 1e3, "descriptor_pairs": pairs, "pairs_per_s": pairs / dt,
+                                                            "note": "H2D of the 32 KB query + kernels + D2H of 2048 survivor counts"}
+ctx2.close()
 print(json.dumps(out, indent=1))
