@@ -200,6 +200,20 @@ class Context:
         self._chk(lib().orbf_extract_batch(self._h, slot0, n, _p(frames), C.c_int64(w), C.c_int64(w * h), _p(depths),
                                            C.c_int64(w), C.c_int64(w * h)), "extract_batch")
 
+    def extract_batch_bgr(self, bgr, depths=None, slot0=0):
+        """bgr: [n, H, W, 3] u8 host frames (Frame::Frame's cvtColor runs on the device); depths as in extract_batch."""
+        assert bgr.dtype == np.uint8 and bgr.ndim == 4 and bgr.shape[3] == 3 and bgr.flags.c_contiguous
+        n, h, w, _ = bgr.shape
+        if depths is not None:
+            assert depths.dtype == np.uint16 and depths.shape == bgr.shape[:3] and depths.flags.c_contiguous
+        self._chk(lib().orbf_extract_batch_bgr(self._h, slot0, n, _p(bgr), C.c_int64(3 * w), C.c_int64(3 * w * h), _p(depths), C.c_int64(w),
+                                               C.c_int64(w * h)), "extract_batch_bgr")
+
+    def download_gray(self, slot):
+        out = np.zeros((self.cfg.height, self.cfg.width), np.uint8)
+        self._chk(lib().orbf_download_gray(self._h, slot, _p(out), self.cfg.width), "download_gray")
+        return out
+
     def extract_batch_device(self, d_gray_ptr, pitch, frame_stride, n, d_depth_ptr=0, depth_pitch=0, depth_frame_stride=0, slot0=0):
         self._chk(lib().orbf_extract_batch_device(self._h, slot0, n, C.c_void_p(d_gray_ptr), C.c_int64(pitch), C.c_int64(frame_stride),
                                                   C.c_void_p(d_depth_ptr) if d_depth_ptr else None, C.c_int64(depth_pitch),

@@ -253,6 +253,56 @@ extern "C" int orbf_extract_batch(orbf_context* c, int32_t slot0, int32_t n, con
     return run_batch(c, slot0, n, &hf, nullptr);
 }
 
+// Frame::Frame + Frame::ExtractFeatures from the colour image (Core/frame.cpp:18-45, 135-170): interleaved 8-bit BGR host
+// frames are copied to HBM, converted to gray on the device (cv::cvtColor CV_BGR2GRAY, fixed point) into the frame slots,
+// and extracted.  orbf_download_gray returns mImGray of a slot.
+extern "C" int orbf_extract_batch_bgr(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* bgr, int64_t bgr_stride,
+    int64_t bgr_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems)
+{
+    CTX_ENTER(c);
+    const int w = c->cfg.width, h = c->cfg.height;
+    if (!bgr || n < 1 || slot0 < 0 || slot0 + n > c->B || bgr_stride < 3 * (int64_t)w) return ORBF_ERR_ARG;
+    if (c->bgrSlots < n) {
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_bgr) cudaFree(c->d_bgr);
+        c->d_bgr = nullptr; c->bgrSlots = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_bgr, (size_t)n * h * w * 3));
+        c->bgrSlots = n;
+    }
+    const size_t rowBytes = (size_t)w * 3;
+    if (bgr_frame_stride == bgr_stride * h) {
+        ORBF_CUDA(c, cudaMemcpy2DAsync(c->d_bgr, rowBytes, bgr, bgr_stride, rowBytes, (size_t)h * n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            ORBF_CUDA(c, cudaMemcpy2DAsync(c->d_bgr + (size_t)i * h * rowBytes, rowBytes, bgr + (size_t)i * bgr_frame_stride, bgr_stride, rowBytes, h,
+                cudaMemcpyHostToDevice, c->stream));
+    }
+    TRY(orbf_launch_bgr2gray(c, c->d_bgr, (int)rowBytes, (long long)h * rowBytes, slot0, n));
+    HostFrames hf;
+    // the gray planes are already in the frame slots: reuse the host-input bookkeeping for depth, skip the gray upload
+    uint8_t dummy = 0;
+    TRY(set_host_inputs(c, slot0, n, &dummy, w, (int64_t)w * h, depth, depth_stride_elems, depth_frame_stride_elems, hf));
+    if (depth && !hf.depthInPlace) {
+        hf.gray = nullptr;
+        const uint16_t* d = depth;
+        uint16_t* dDepth = c->d_depthIn + (size_t)slot0 * w * h;
+        for (int i = 0; i < n; ++i)
+            ORBF_CUDA(c, cudaMemcpy2DAsync(dDepth + (size_t)i * w * h, (size_t)w * 2, d + (size_t)i * depth_frame_stride_elems,
+                (size_t)depth_stride_elems * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, c->stream));
+    }
+    return run_batch(c, slot0, n, nullptr, nullptr);
+}
+
+extern "C" int orbf_download_gray(orbf_context* c, int32_t slot, uint8_t* out, int32_t out_stride)
+{
+    CTX_ENTER(c);
+    if (!out || slot < 0 || slot >= c->B || out_stride < c->cfg.width) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpy2DAsync(out, out_stride, c->d_in + (size_t)slot * c->inPlane, c->inPitch, c->cfg.width, c->cfg.height,
+        cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
 // Tracking::Track's per-frame loop over a sequence (System/tracking.cpp:38-46, 193-208): extract every frame, then
 // Matcher(ratio).KnnMatch(last, cur) and Ransac::Iterate(last, cur) for each consecutive pair, pipelined by chunk.
 extern "C" int orbf_track_sequence(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,

@@ -350,6 +350,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     TRY(dalloc(c, &c->d_depthCov, 1));
     c->d_samples = nullptr; c->d_hyp = nullptr;
     c->d_qdesc = c->d_tdesc = nullptr; c->d_sxyz = c->d_txyz = nullptr;
+    c->d_bgr = nullptr; c->bgrSlots = 0;
     c->d_kfDesc = nullptr; c->d_kfCount = nullptr; c->d_kfExtDesc = nullptr; c->d_kfExtCount = nullptr; c->kfExtN = 0;
     c->d_pts = nullptr; c->ptsCap = 0; c->d_userSamples = nullptr; c->userSamplesCap = 0; c->d_kabsch = nullptr; c->kabschCap = 0;
     c->d_kfKnn = nullptr; c->d_kfSurv = nullptr; c->d_kfPairs = nullptr; c->d_kfQCount = nullptr; c->kfOutCap = 0;
@@ -381,7 +382,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (!c) return ORBF_ERR_ARG;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_blTiles, c->d_rsTiles, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
+    void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_blTiles, c->d_rsTiles, c->d_bgr, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,

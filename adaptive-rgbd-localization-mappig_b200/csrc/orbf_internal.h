@@ -92,6 +92,7 @@ struct orbf_context {
 
     // inputs
     uint8_t* d_in; int inPitch; size_t inPlane;
+    uint8_t* d_bgr; int bgrSlots;                  // staging of interleaved BGR frames (orbf_extract_batch_bgr), allocated on first use
     uint16_t* d_depthIn;
     const uint8_t* cur_gray; long long cur_grayFrameStride; int cur_grayPitch; int cur_slot0, cur_n;
     const uint16_t* cur_depth; long long cur_depthFrameStride; int cur_depthPitch;
@@ -179,6 +180,7 @@ int orbf_launch_fast(orbf_context* ctx, int slot0, int n);
 int orbf_launch_quadtree(orbf_context* ctx, int slot0, int n);
 int orbf_launch_describe(orbf_context* ctx, int slot0, int n);
 int orbf_launch_pack_aos(orbf_context* ctx, int slot0, int n);
+int orbf_launch_bgr2gray(orbf_context* ctx, const uint8_t* d_bgr, int bgrPitch, long long bgrFrameStride, int slot0, int n);
 // matching: query/train descriptor matrices addressed per pair
 struct MatchSet {
     const uint8_t* qdesc; const uint8_t* tdesc;   // base of slot 0 (row stride 32 B)

@@ -190,6 +190,34 @@ __global__ void __launch_bounds__(TL_THREADS) resize_tile_kernel(const __grid_co
 #undef RS_HROW
 }
 
+// ---- BGR -> gray (Frame::Frame, Core/frame.cpp:23: cv::cvtColor(imColor, mImGray, CV_BGR2GRAY)) ------------------------------
+// OpenCV's 8-bit path is fixed point with 15 fractional bits: (B*3735 + G*19235 + R*9798 + 16384) >> 15 (pinned against
+// cv2 4.13.0 in tests/test_ingest.py).  A thread converts 4 pixels: three aligned word reads, one word write.
+__global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict__ bgr, int bgrPitch, long long bgrFrameStride,
+    uint8_t* __restrict__ gray, int grayPitch, long long grayFrameStride, int w, int h, int slot0)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= w) return;
+    const uint8_t* src = bgr + (long long)f * bgrFrameStride + (long long)y * bgrPitch + 3 * x4;
+    uint8_t* dst = gray + (long long)(slot0 + f) * grayFrameStride + (long long)y * grayPitch + x4;
+    uint8_t px[12];
+    if (x4 + 3 < w && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        *reinterpret_cast<uint32_t*>(px) = __ldg(s32); *reinterpret_cast<uint32_t*>(px + 4) = __ldg(s32 + 1); *reinterpret_cast<uint32_t*>(px + 8) = __ldg(s32 + 2);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) px[i] = (x4 + i / 3 < w) ? __ldg(src + i) : 0;
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t v = (px[3 * k] * 3735u + px[3 * k + 1] * 19235u + px[3 * k + 2] * 9798u + 16384u) >> 15;
+        out |= v << (8 * k);
+    }
+    if (x4 + 3 < w) *reinterpret_cast<uint32_t*>(dst) = out;
+    else for (int k = 0; x4 + k < w; ++k) dst[k] = (uint8_t)(out >> (8 * k));
+}
+
 void fill_common(orbf_context* c, StageParams& P, int slot0)
 {
     for (int l = 0; l < c->L; ++l) { P.w[l] = (short)c->lg[l].w; P.h[l] = (short)c->lg[l].h; P.tabX[l] = c->lg[l].tabX; P.tabY[l] = c->lg[l].tabY; }
@@ -246,6 +274,15 @@ int orbf_launch_blur(orbf_context* c, int slot0, int n)
     const size_t smem = (size_t)BL_TILE_BYTES * TL_WARPS;
     dim3 grid((P.nTiles + TL_WARPS - 1) / TL_WARPS, n);
     blur_tile_kernel<<<grid, TL_THREADS, smem, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+int orbf_launch_bgr2gray(orbf_context* c, const uint8_t* d_bgr, int bgrPitch, long long bgrFrameStride, int slot0, int n)
+{
+    const int w = c->cfg.width, h = c->cfg.height;
+    dim3 grid(((w + 3) / 4 + 255) / 256, h, n);
+    bgr2gray_kernel<<<grid, 256, 0, c->stream>>>(d_bgr, bgrPitch, bgrFrameStride, c->d_in, c->inPitch, (long long)c->inPlane, w, h, slot0);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }

@@ -11,6 +11,7 @@
  *   orbf_extract                      ORBextractor::operator()                    Features/orbextractor.cpp:756-815 (orbextractor.h:37)
  *                                     Extractor::Extract (ORB_SLAM2 route)        Features/extractor.cpp:39-42
  *   orbf_extract_batch*               the same, batched + Frame::ExtractFeatures' depth gather   Core/frame.cpp:135-170
+ *   orbf_extract_batch_bgr            Frame::Frame (cvtColor BGR2GRAY) + ExtractFeatures   Core/frame.cpp:18-45,135-170
  *   orbf_pyramid_level                public member mvImagePyramid                Features/orbextractor.h:57
  *   orbf_knn2 / orbf_knn_match        cv::BFMatcher::knnMatch(k=2) + ratio test in Matcher::KnnMatch   Features/matcher.cpp:55-66 (23-35)
  *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
@@ -135,6 +136,11 @@ int orbf_extract_batch(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_
 /* Batched, device input (already in HBM): pointers must be 16-byte aligned, gray pitch a multiple of 16. */
 int orbf_extract_batch_device(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
     int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems);
+/* Frame::Frame + ExtractFeatures from the colour image (Core/frame.cpp:18-45,135-170): n interleaved 8-bit BGR host frames
+ * (row stride in bytes) -> gray on the device (cv::cvtColor CV_BGR2GRAY, OpenCV's fixed-point arithmetic) -> extraction.     */
+int orbf_extract_batch_bgr(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* bgr, int64_t bgr_stride,
+    int64_t bgr_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems);
+int orbf_download_gray(orbf_context* ctx, int32_t slot, uint8_t* out, int32_t out_stride);   /* mImGray of a slot (host-input paths) */
 /* A whole sequence in one call: extraction of n frames plus, for each consecutive pair p = (slot0+p, slot0+p+1),
  * Matcher(ratio).KnnMatch and (ransac_cfg != NULL) Ransac::Iterate; results land in pair slots 0..n-2.  The call is
  * asynchronous and internally pipelined: frames are processed in chunks of orbf_config.pipeline_chunk on

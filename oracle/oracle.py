@@ -223,6 +223,13 @@ def unproject(kps, depth, depth_factor=FR1["depth_factor"], fx=FR1["fx"], fy=FR1
     return xyz, ur
 
 
+def bgr2gray(bgr):
+    """Frame::Frame's cv::cvtColor(imColor, mImGray, CV_BGR2GRAY) (Core/frame.cpp:23) for 8-bit images: OpenCV's fixed-point
+    path with 15 fractional bits (pinned against cv2 4.13.0 in tests/test_ingest.py)."""
+    b, g, r = (bgr[..., i].astype(np.uint32) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
+
+
 class AdaptiveCfg(C.Structure):
     _fields_ = [("min_features", C.c_int), ("max_features", C.c_int), ("max_iters", C.c_int), ("max_per_cell", C.c_int),
                 ("grid", C.c_int), ("edge", C.c_int), ("init_th", C.c_double), ("min_th", C.c_double), ("max_th", C.c_double),
