@@ -286,6 +286,15 @@ class Context:
                                        C.byref(n)), "knn_match")
         return out[:n.value].copy()
 
+    def distinctive_descriptors(self, desc, offsets):
+        """Landmark::ComputeDistinctiveDescriptors for a batch of landmarks: (best row per landmark, its median distance)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); offsets = np.ascontiguousarray(offsets, np.int32)
+        n = len(offsets) - 1
+        best = np.zeros(max(n, 1), np.int32); med = np.zeros(max(n, 1), np.int32)
+        self._chk(lib().orbf_distinctive_descriptors(self._h, _p(desc) if len(desc) else None, _p(offsets), n, _p(best), _p(med)),
+                  "distinctive_descriptors")
+        return best[:n], med[:n]
+
     def match_pairs(self, pairs, ratio, cross_check=False):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         self._chk(lib().orbf_match_pairs(self._h, _p(pairs), len(pairs), C.c_float(ratio), int(cross_check)), "match_pairs")

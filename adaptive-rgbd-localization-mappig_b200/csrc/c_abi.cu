@@ -484,6 +484,35 @@ extern "C" int orbf_knn_match(orbf_context* c, const uint8_t* q, int32_t nq, con
     return orbf_download_matches(c, 0, out, cap, n_out);
 }
 
+// Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks: desc holds every landmark's
+// observed descriptors back to back, offsets [n+1] delimits them; best[l] = row (inside landmark l) with the least median
+// Hamming distance to the others (-1 without observations), median[l] optional.  At most 128 observations per landmark count.
+extern "C" int orbf_distinctive_descriptors(orbf_context* c, const uint8_t* desc, const int32_t* offsets, int32_t n_landmarks, int32_t* best,
+    int32_t* median)
+{
+    CTX_ENTER(c);
+    if (!offsets || !best || n_landmarks < 0 || (n_landmarks > 0 && offsets[n_landmarks] > 0 && !desc)) return ORBF_ERR_ARG;
+    if (n_landmarks == 0) return ORBF_OK;
+    for (int l = 0; l < n_landmarks; ++l) if (offsets[l + 1] < offsets[l] || offsets[l] < 0) return ORBF_ERR_ARG;
+    const size_t rows = (size_t)offsets[n_landmarks];
+    uint8_t* dDesc = nullptr; int *dOff = nullptr, *dBest = nullptr;
+    auto freeAll = [&]() { if (dDesc) cudaFree(dDesc); if (dOff) cudaFree(dOff); if (dBest) cudaFree(dBest); };
+#define DD_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeAll(); return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } } while (0)
+    DD_CUDA(cudaMalloc((void**)&dDesc, std::max<size_t>(rows, 1) * 32));
+    DD_CUDA(cudaMalloc((void**)&dOff, ((size_t)n_landmarks + 1) * sizeof(int)));
+    DD_CUDA(cudaMalloc((void**)&dBest, (size_t)n_landmarks * 2 * sizeof(int)));
+    if (rows) DD_CUDA(cudaMemcpyAsync(dDesc, desc, rows * 32, cudaMemcpyHostToDevice, c->stream));
+    DD_CUDA(cudaMemcpyAsync(dOff, offsets, ((size_t)n_landmarks + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const int rc = orbf_launch_distinctive(c, dDesc, dOff, n_landmarks, dBest, dBest + n_landmarks);
+    if (rc != ORBF_OK) { freeAll(); return rc; }
+    DD_CUDA(cudaMemcpyAsync(best, dBest, (size_t)n_landmarks * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (median) DD_CUDA(cudaMemcpyAsync(median, dBest + n_landmarks, (size_t)n_landmarks * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    DD_CUDA(cudaStreamSynchronize(c->stream));
+#undef DD_CUDA
+    freeAll();
+    return ORBF_OK;
+}
+
 extern "C" int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes, int32_t* dist)
 {
     if (!a || !b || !dist || nbytes < 0) return ORBF_ERR_ARG;

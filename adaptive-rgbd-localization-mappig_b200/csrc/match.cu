@@ -189,7 +189,57 @@ __global__ void __launch_bounds__(MS_THREADS) match_select_kernel(MatchSet ms, i
     if (threadIdx.x == 0) matchCount[pair] = sBase;
 }
 
+// ---- Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273): one warp per landmark ------------------------------
+// Lane j holds observation j's descriptor (chunks of 32 observations); for every row i the distances to all observations are
+// formed with the same XOR/POPC arithmetic, the row median sorted[(size_t)(0.5 * (N - 1))] is found by rank counting over
+// shuffles, and the first row with the strictly smallest median wins.
+constexpr int DD_MAX_OBS = 128;
+
+__global__ void __launch_bounds__(128) distinctive_kernel(const uint8_t* __restrict__ desc, const int* __restrict__ offsets, int nLandmarks,
+    int* __restrict__ best, int* __restrict__ bestMedian)
+{
+    __shared__ uint16_t sDist[4][DD_MAX_OBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = blockIdx.x * 4 + warp;
+    if (l >= nLandmarks) return;
+    const int a = offsets[l], N = min(offsets[l + 1] - a, DD_MAX_OBS);
+    if (N <= 0) { if (lane == 0) { best[l] = -1; if (bestMedian) bestMedian[l] = -1; } return; }
+    const int m = (int)(0.5 * (double)(N - 1));
+    int bestIdx = 0, bestMed = 0x7fffffff;
+    uint16_t* dist = sDist[warp];
+    for (int i = 0; i < N; ++i) {
+        const uint4 ia = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(a + i) * 32)), ib = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(a + i) * 32) + 1);
+        for (int j = lane; j < N; j += 32) {
+            const uint4 ja = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(a + j) * 32)), jb = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)(a + j) * 32) + 1);
+            dist[j] = (uint16_t)(__popc(ia.x ^ ja.x) + __popc(ia.y ^ ja.y) + __popc(ia.z ^ ja.z) + __popc(ia.w ^ ja.w)
+                + __popc(ib.x ^ jb.x) + __popc(ib.y ^ jb.y) + __popc(ib.z ^ jb.z) + __popc(ib.w ^ jb.w));
+        }
+        __syncwarp();
+        // the m-th smallest: the value v with #{< v} <= m < #{<= v}
+        int med = -1;
+        for (int j = lane; j < N; j += 32) {
+            const int v = dist[j];
+            int less = 0, leq = 0;
+            for (int k = 0; k < N; ++k) { const int u = dist[k]; less += u < v; leq += u <= v; }
+            if (less <= m && m < leq) med = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) med = max(med, __shfl_xor_sync(0xffffffffu, med, o));
+        if (med < bestMed) { bestMed = med; bestIdx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) { best[l] = bestIdx; if (bestMedian) bestMedian[l] = bestMed; }
+}
+
 }  // namespace
+
+int orbf_launch_distinctive(orbf_context* c, const uint8_t* d_desc, const int* d_offsets, int nLandmarks, int* d_best, int* d_median)
+{
+    if (nLandmarks <= 0) return ORBF_OK;
+    distinctive_kernel<<<(nLandmarks + 3) / 4, 128, 0, c->stream>>>(d_desc, d_offsets, nLandmarks, d_best, d_median);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
 
 int orbf_launch_knn2(orbf_context* c, const MatchSet& ms, int npairs, bool cross)
 {

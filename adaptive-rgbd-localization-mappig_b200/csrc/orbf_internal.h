@@ -194,6 +194,7 @@ struct MatchSet {
     orbf_dmatch* matches; int* matchCount;         // out [npairs][K], [npairs]   (matches may be NULL: count only)
 };
 int orbf_launch_knn2(orbf_context* ctx, const MatchSet& ms, int npairs, bool cross);
+int orbf_launch_distinctive(orbf_context* ctx, const uint8_t* d_desc, const int* d_offsets, int nLandmarks, int* d_best, int* d_median);
 int orbf_launch_match_select(orbf_context* ctx, const MatchSet& ms, int npairs, float ratio, bool cross);
 // RANSAC
 struct RansacSet {

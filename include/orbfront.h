@@ -15,6 +15,7 @@
  *   orbf_pyramid_level                public member mvImagePyramid                Features/orbextractor.h:57
  *   orbf_knn2 / orbf_knn_match        cv::BFMatcher::knnMatch(k=2) + ratio test in Matcher::KnnMatch   Features/matcher.cpp:55-66 (23-35)
  *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
+ *   orbf_distinctive_descriptors      Landmark::ComputeDistinctiveDescriptors     Core/landmark.cpp:219-273
  *   orbf_match_pairs                  Tracking::TrackFrame's matcher call, batched  System/tracking.cpp:197-199
  *   orbf_track_sequence*              Tracking::Track's per-frame loop (extract, match with the last frame, RANSAC)
  *                                     over a whole sequence, pipelined            System/tracking.cpp:38-46,193-208
@@ -171,6 +172,11 @@ int orbf_knn2(orbf_context* ctx, const uint8_t* q, int32_t nq, const uint8_t* t,
 int orbf_knn_match(orbf_context* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, float ratio,
     int32_t cross_check, orbf_dmatch* out, int32_t cap, int32_t* n_out);
 int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes, int32_t* dist);  /* host helper */
+/* Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks: desc = every landmark's observed
+ * descriptors back to back (rows of 32 bytes), offsets [n_landmarks + 1]; best[l] = row inside landmark l with the least median
+ * Hamming distance to the others (first wins ties, -1 without observations); median[l] optional (may be NULL).          */
+int orbf_distinctive_descriptors(orbf_context* ctx, const uint8_t* desc, const int32_t* offsets, int32_t n_landmarks, int32_t* best,
+    int32_t* median);
 /* Device-resident: match frame slot pairs (query_slot, train_slot); results live in pair slots 0..npairs-1. */
 int orbf_match_pairs(orbf_context* ctx, const int32_t* pairs /* 2*npairs */, int32_t npairs, float ratio,
     int32_t cross_check);

@@ -98,3 +98,31 @@ int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, 
     if (out) std::copy(all.begin(), all.end(), out);
     return ORC_OK;
 }
+
+// ---- Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273), SURVEY.md §8f rank 1 ----------------------------
+// For every landmark: all-pairs Hamming distances of its observed descriptors, per row the median sorted[(size_t)(0.5*(N-1))],
+// the first row with the strictly smallest median is the landmark's descriptor.  offsets[l]..offsets[l+1] delimit landmark l's
+// rows in `desc`; best[l] = chosen row index inside the landmark (-1 for a landmark without observations).
+int orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_landmarks, int* best, int* best_median)
+{
+    if (!desc || !offsets || !best || n_landmarks < 0) return ORC_ERR_ARG;
+    std::vector<double> row;
+    for (int l = 0; l < n_landmarks; ++l) {
+        const int a = offsets[l], N = offsets[l + 1] - a;
+        best[l] = -1;
+        if (best_median) best_median[l] = -1;
+        if (N <= 0) continue;
+        double bestMedian = 1e300;
+        int bestIdx = 0;
+        for (int i = 0; i < N; ++i) {
+            row.assign(N, 0.0);
+            for (int j = 0; j < N; ++j) row[j] = (i == j) ? 0.0 : (double)orc_hamming(desc + (size_t)(a + i) * 32, desc + (size_t)(a + j) * 32);
+            std::sort(row.begin(), row.end());
+            const double median = row[(size_t)(0.5 * (N - 1))];
+            if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+        }
+        best[l] = bestIdx;
+        if (best_median) best_median[l] = (int)bestMedian;
+    }
+    return ORC_OK;
+}

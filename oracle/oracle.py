@@ -223,6 +223,15 @@ def unproject(kps, depth, depth_factor=FR1["depth_factor"], fx=FR1["fx"], fy=FR1
     return xyz, ur
 
 
+def distinctive_descriptors(desc, offsets):
+    """Landmark::ComputeDistinctiveDescriptors (landmark.cpp:219-273) per landmark: (best row index, its median distance)."""
+    desc = np.ascontiguousarray(desc, np.uint8); offsets = np.ascontiguousarray(offsets, np.int32)
+    n = len(offsets) - 1
+    best = np.zeros(n, np.int32); med = np.zeros(n, np.int32)
+    _chk(lib().orc_distinctive_descriptors(_p(desc), _p(offsets), n, _p(best), _p(med)), "distinctive_descriptors")
+    return best, med
+
+
 def bgr2gray(bgr):
     """Frame::Frame's cv::cvtColor(imColor, mImGray, CV_BGR2GRAY) (Core/frame.cpp:23) for 8-bit images: OpenCV's fixed-point
     path with 15 fractional bits (pinned against cv2 4.13.0 in tests/test_ingest.py)."""

@@ -67,6 +67,9 @@ int orc_adaptive_default(orc_adaptive_cfg* cfg);
 int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, int h, int stride, double* thresh, int retain_best,
     orc_keypoint* out, int cap, int* n_out, int* cell_found, int* cell_thresh);
 
+/* Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks */
+int orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_landmarks, int* best, int* best_median);
+
 /* ---- matching (Features/matcher.cpp:10-88,355-358) ---- */
 int orc_hamming(const uint8_t* a, const uint8_t* b);
 int orc_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx1, int* d1, int* idx2, int* d2);
