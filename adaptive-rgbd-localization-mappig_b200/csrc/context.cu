@@ -223,8 +223,10 @@ static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::ve
                 d.cap = ((cw + 1) / 2) * ((ch + 1) / 2);   // strict 8-neighbour maxima: <= 1 per 2x2 block
                 cellSlot += d.cap; cap += d.cap;
                 c->maxCellW = std::max(c->maxCellW, cw); c->maxCellH = std::max(c->maxCellH, ch);
-                // strips of up to ORBF_STRIP_CELLS adjacent cells (their scored interiors tile the row without gaps)
-                if (inRow % ORBF_STRIP_CELLS == 0) {
+                // strips of up to ORBF_STRIP_CELLS adjacent cells (their scored interiors tile the row without gaps), no wider than
+                // the fixed tile pitch allows
+                if (cw > ORBF_STRIP_MAX_W) return ORBF_ERR_GEOMETRY;
+                if (inRow == 0 || strips.back().nCells >= ORBF_STRIP_CELLS || d.x0 + d.w - strips.back().x0 > ORBF_STRIP_MAX_W) {
                     StripDesc sd;
                     sd.level = (short)l; sd.nCells = 0; sd.x0 = d.x0; sd.y0 = d.y0; sd.w = 0; sd.h = d.h; sd.firstCell = (int)cells.size();
                     strips.push_back(sd);
@@ -237,7 +239,8 @@ static int build_geometry(orbf_context* c, std::vector<ResizeCoef>& tab, std::ve
             }
         }
         q.nCells = (int)cells.size() - q.cell0;
-        c->fastBW[l] = align_up(15 + 3 + levelMaxW + 3, 16);   // box starts on a 16-byte boundary <= x0 - 3, ends >= 3 px past the strip
+        c->fastBW[l] = ORBF_FAST_BW;                             // box starts on a 16-byte boundary <= x0 - 3, ends >= 3 px past the strip
+        (void)levelMaxW;
         c->fastBH[l] = levelMaxH + 6;
         if (c->fastBW[l] > 256 || c->fastBH[l] > 256) return ORBF_ERR_GEOMETRY;
         q.candCap = cap;

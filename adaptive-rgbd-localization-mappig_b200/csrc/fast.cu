@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StripDesc sd = P.strips[blockIdx.x];
     const int slot = P.slot0 + blockIdx.y;
-    const int level = sd.level, BW = P.BW[level], BH = P.BH[level];
+    constexpr int BW = ORBF_FAST_BW;                                       // compile-time pitch: every tile offset is an immediate
+    const int level = sd.level, BH = P.BH[level];
     const int W = sd.w, h = sd.h;
     const int xs = (sd.x0 - 3) & ~15, ax = sd.x0 - xs;                      // TMA boxes of bytes start on 16-byte boundaries
     uint8_t* tile = smem;                                                   // BH x BW level pixels, interior (0,0) at [3][ax]

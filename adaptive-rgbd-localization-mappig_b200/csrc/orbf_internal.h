@@ -49,6 +49,8 @@ struct StripDesc {            // FAST work unit: up to ORBF_STRIP_CELLS adjacent
     int firstCell;            // index of its first cell in the CellDesc table (the others follow)
 };
 #define ORBF_STRIP_CELLS 4
+#define ORBF_FAST_BW 176       // fast.cu: fixed row pitch of the strip tile in shared memory (= TMA box width): 18 + 155 + 3
+#define ORBF_STRIP_MAX_W (ORBF_FAST_BW - 21)
 struct TileDesc { short level, x0, y0, pad; };    // destination tile of the resize / blur stages (pyramid.cu)
 
 struct LevelGeom {
