@@ -20,7 +20,7 @@ namespace {
 
 constexpr int TL_W = 128, TL_WARPS = 4, TL_THREADS = TL_WARPS * 32;
 constexpr int BL_H = 35, BL_BW = 160, BL_BH = BL_H + 6, BL_TILE_BYTES = ((BL_BW * BL_BH + 127) / 128) * 128;   // 5 x 7-row ring turns
-constexpr int RS_H = 32;
+constexpr int RS_H = 16;
 
 struct StageParams {
     CUtensorMap maps[ORBF_MAX_LEVELS];          // source of level l's stage (blur: level l; resize: level l-1)
