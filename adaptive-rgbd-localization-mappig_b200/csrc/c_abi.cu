@@ -168,7 +168,8 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
     }
     // Measured on B200 (profiles/r1d_pipeline_sweep.txt): the stages are instruction-issue bound, so running chunks on
     // concurrent streams buys nothing when the inputs are already in HBM (7.36 ms/512 frames on one stream vs 7.4-9.5 ms
-    // chunked) — the pipeline exists to hide the PCIe copies of host inputs (16.0 -> 10.9 ms end to end).
+    // chunked; re-measured after the kernel rewrites: 4.09 ms vs 4.06 ms) — the pipeline exists to hide the PCIe copies of
+    // host inputs.
     Pipeline pl(c);
     TRY(pl.begin(hf && hf->gray));
     const int chunk = pl.active ? c->chunkFrames : n;

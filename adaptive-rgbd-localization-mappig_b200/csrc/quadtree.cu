@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int QT_THREADS = 256;
-constexpr int QT_SMEM_KEYS = 16384;
+constexpr int QT_SMEM_KEYS = 8192;
 
 struct QtParams {
     const LevelGeom* lg; const CellDesc* cells;
