@@ -292,6 +292,7 @@ def main():
                     "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step,
                     "avg_launch_ms": stage_ms[dom] / launches_per_step, "peak_source": peak_src,
                     "stage_ms_per_step": stage_ms,
+                    "stage_hbm_frac": {k: STAGE_BYTES[k] * F / (stage_ms[k] * 1e-3) / 1e9 / peak for k in STAGE_BYTES},
                     "whole_path": {"algorithmic_bytes_per_frame": FRAME_BYTES, "achieved_GBps": FRAME_BYTES * F / (ms * 1e-3) / 1e9,
                                    "frac_of_hbm": FRAME_BYTES * F / (ms * 1e-3) / 1e9 / peak},
                     "hamming_knn2": {"pairs_per_s": float(sum(int(a) * int(b) for a, b in zip(fc[:-1], fc[1:]))) / (stage_ms["hamming_knn2"] * 1e-3),
