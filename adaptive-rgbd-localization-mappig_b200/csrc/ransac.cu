@@ -118,12 +118,56 @@ __device__ void parallel_std_sort(unsigned long long* keys, unsigned long long* 
 // discarded values and output x[i] >> 1 (csrc/replay.h holds the circular-buffer form the library uses).  A block of 31
 // consecutive values follows from the previous block P as N[j] = sum_k P[j-3k] + P[28 + j % 3]: a stride-3 inclusive scan,
 // i.e. four shuffle steps for 31 values instead of 31 dependent steps.  The warp fills a buffer of `rand() % M` values;
-// lane 0 then runs SampleMatches' duplicate-rejecting loop (ransac.cpp:269-293) over it, which no longer contains any
+// the duplicate-rejecting loop of SampleMatches (ransac.cpp:269-293) then streams over it (rows_from_stream) without any
 // generator or modulo arithmetic.  Returns false when the buffer was too short (caller falls back to the scalar replay).
-constexpr int RAND_BUF = 4096;
+constexpr int RAND_BUF = 3072;     // rand() values buffered per pair: 1536 draws of SampleMatches (a 200 x 4 table needs ~860)
+
+__device__ __forceinline__ void cas(int& a, int& b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+
+// SampleMatches' duplicate-rejecting loop (ransac.cpp:269-293) as a streaming state machine over the id stream: the ids arrive
+// by shuffle, 32 at a time, and every lane runs the same register-resident state (no divergence, no local memory, no
+// dependent shared-memory loads on the critical path).  A row closes when it holds S distinct ids; they are emitted ascending.
+template <int SMAX>
+__device__ bool rows_from_stream(const uint16_t* pid, int np, int S, int iters, int* tab, int lane)
+{
+    int sel[SMAX];
+#pragma unroll
+    for (int q = 0; q < SMAX; ++q) sel[q] = 0x7fffffff;
+    int cnt = 0, row = 0;
+    for (int base = 0; base < np && row < iters; base += 32) {
+        const int mine = (base + lane < np) ? (int)pid[base + lane] : 0;
+        const int lim = min(32, np - base);
+        for (int j = 0; j < lim && row < iters; ++j) {
+            const int id = __shfl_sync(0xffffffffu, mine, j);
+            bool dup = false;
+#pragma unroll
+            for (int q = 0; q < SMAX; ++q) dup |= sel[q] == id;          // unused slots hold INT_MAX
+            if (dup) continue;
+#pragma unroll
+            for (int q = 0; q < SMAX; ++q) if (q == cnt) sel[q] = id;
+            if (++cnt < S) continue;
+            if (SMAX == 4) { cas(sel[0], sel[1]); cas(sel[2], sel[3]); cas(sel[0], sel[2]); cas(sel[1], sel[3]); cas(sel[1], sel[2]); }
+            else {
+#pragma unroll
+                for (int pass = 0; pass < SMAX; ++pass)
+#pragma unroll
+                    for (int q = pass & 1; q + 1 < SMAX; q += 2) cas(sel[q], sel[q + 1]);
+            }
+            int v = sel[0];
+#pragma unroll
+            for (int q = 1; q < SMAX; ++q) if (lane == q) v = sel[q];
+            if (lane < S) tab[(long long)row * S + lane] = v;
+            ++row; cnt = 0;
+#pragma unroll
+            for (int q = 0; q < SMAX; ++q) sel[q] = 0x7fffffff;
+        }
+    }
+    return row == iters;
+}
 
 __device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* tab, uint16_t* ids, int lane)
 {
+    uint16_t* pid = ids + RAND_BUF;                 // [RAND_BUF / 2] min of each rand pair = the id SampleMatches draws
     uint32_t P = 0;
     {
         if (seed == 0) seed = 1;
@@ -153,30 +197,9 @@ __device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* t
         }
     }
     __syncwarp();
-    bool ok = true;
-    if (lane == 0) {
-        int pos = 0;
-        for (int k = 0; k < iters && ok; ++k) {
-            int sel[ORBF_MAX_SAMPLE];
-            int cnt = 0, safety = 0;
-            while (cnt < S) {
-                if (pos + 2 > RAND_BUF) { ok = false; break; }
-                const int id = min((int)ids[pos], (int)ids[pos + 1]);
-                pos += 2;
-                int p = 0;
-                bool dup = false;
-                while (p < cnt && sel[p] <= id) { if (sel[p] == id) dup = true; ++p; }
-                if (!dup) {
-                    for (int j = cnt; j > p; --j) sel[j] = sel[j - 1];
-                    sel[p] = id;
-                    ++cnt;
-                }
-                if (++safety > 10000) break;
-            }
-            for (int j = 0; j < S; ++j) tab[(long long)k * S + j] = (j < cnt) ? sel[j] : -1;
-        }
-    }
-    return __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    for (int k = lane; k < RAND_BUF / 2; k += 32) pid[k] = (uint16_t)min((int)ids[2 * k], (int)ids[2 * k + 1]);
+    __syncwarp();
+    return S <= 4 ? rows_from_stream<4>(pid, RAND_BUF / 2, S, iters, tab, lane) : rows_from_stream<8>(pid, RAND_BUF / 2, S, iters, tab, lane);
 }
 
 __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams P)
@@ -806,8 +829,8 @@ int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
         ORBF_CUDA(c, cudaMalloc(&c->d_pts, needPts * sizeof(Pt6)));
         c->ptsCap = needPts;
     }
-    const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + RAND_BUF * sizeof(uint16_t);
-    if (smem > 48 * 1024) {
+    const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + (RAND_BUF + RAND_BUF / 2) * sizeof(uint16_t);
+    {   // static (sort queues) + dynamic shared memory exceed the 48 KB default: always opt in
         cudaError_t e = cudaFuncSetAttribute(ransac_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac smem attr", __FILE__, __LINE__);
     }
@@ -833,7 +856,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
         const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
         P.covX = sx * sx; P.covY = sy * sy;
     }
-    const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + RAND_BUF * sizeof(uint16_t);
+    const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + (RAND_BUF + RAND_BUF / 2) * sizeof(uint16_t);
     orbf_prof_begin(c, ST_RANSAC_PREPARE);
     ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
