@@ -3,21 +3,33 @@
 // (reference Features/matcher.cpp:55-66, :23-35); result order = (distance asc, trainIdx asc), which the
 // packed key (dist << 16 | trainIdx) reproduces under unsigned min.
 //
-// Register-tiled POPC/LOP3 kernel, integer-ALU bound, no tensor cores: each thread keeps R query descriptors
-// (R x 8 words) in registers; a warp walks its share of the train descriptors staged in shared memory with
-// broadcast 128-bit loads, so one LDS pair feeds 32*R pairs.  The 256-bit popcount runs through a carry-save
-// adder tree (4 CSAs = 8 LOP3 turn the 8 XOR words into words of weight 1,1,2,4), so a pair costs 4 POPC
-// instead of 8: B200's POPC pipe issues 16 lanes/clk/SM against 64 for LOP3 (profiles/int_pipe_peaks.json), which
-// moves the bound from the POPC pipe (0.5 clk/pair/SM) to the ALU pipe (~0.27).  The running top-2 is only
-// touched when a pair beats the current second best (one ISETP per pair on the common path).
-// Cross-check (north-star extension, quirk Q10) reuses the same distances: per train row the warp takes
-// REDUX.MIN over (dist << 16 | queryIdx) and folds it into a shared / global atomicMin.
+// The O(nq * nt * 256) distance matrix is the one compute-bound piece of the path (64 KB of descriptors per pair, 2.6e8 bit
+// operations), so it runs on the tensor cores as an exact integer GEMM: every descriptor bit becomes a signed byte (1 -> +1,
+// 0 -> -1), dot(a, b) over the 256 bytes = 256 - 2 * hamming(a, b), and IMMA (mma.sync m16n8k32 s8*s8 -> s32) produces
+// 16 x 8 distances per 8 instructions.  The previous POPC/LOP3 kernel needed ~100 warp instructions for the same 128
+// distances and was bound by the integer ALU pipe (0.63e12 distances/s); B200's s8 mma.sync path sustains 0.48 IMMA/clk/SM
+// = 2.2e12 distances/s (tools/bmma_probe.cu).  The bit -> byte expansion is one PRMT per 4 bytes (the selector nibbles are the
+// bits, the pool bytes are 0xFF / 0x01); the order of the 256 dimensions is irrelevant as long as both operands use the
+// same one, so the expansion is laid out to make the fragment loads contiguous.
+//
+// CTA = 8 warps = 256 query rows (two m16 tiles per warp, A fragments resident in 64 registers); train rows are expanded in
+// chunks of 256 into shared memory as [k-step pair][column][lane-in-group][4 words], which makes every B-fragment load a
+// conflict-free LDS.128.  The epilogue is branch-free and packed two columns per register (VIMNMX.U16x2): per n8 tile and
+// row slot a running top-2 of 15-bit (256 - distance, tile) codes, decoded into (distance << 16 | trainIdx) keys once per
+// chunk; for the cross-check, the maximum over the thread's rows and 3 shuffles over the 8 row groups give the warp's best
+// (256 - distance, row) per column, stored per warp and folded over the 8 warps at the end of the chunk.
 #include "orbf_internal.h"
 
 namespace {
 
-constexpr int KN_R = 4, KN_WARPS = 4, KN_THREADS = KN_WARPS * 32, KN_QT = 32 * KN_R, KN_CHUNK = 1024;
+constexpr int KM_WARPS = 8, KM_THREADS = KM_WARPS * 32, KM_ROWS = KM_WARPS * 32, KM_CHUNK = 256;
+constexpr size_t KM_SMEM = (size_t)4 * KM_CHUNK * 16 * sizeof(uint32_t) + KM_WARPS * (KM_CHUNK / 2) * sizeof(uint32_t);
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+// Accumulator encoding: train bytes are +-32 and query bytes +-1, so an accumulator that starts at 32 * 256 + rc holds
+// v = 64 * h + rc with h = 256 - hamming (0..256) and rc = 32 - (row within the warp's 32) in the low 6 bits: one 15-bit
+// value that orders a column's candidates by (distance asc, query asc) and still tells which row it came from.  Rows past nq
+// have all-zero bytes and start at 0 (v = 0, rc = 0 marks them).
+constexpr int V_SHIFT = 6, V_START = 32 * 256;
 
 __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t key)
 {
@@ -25,118 +37,182 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
     m1 = min(m1, key);
 }
 
-__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
+// 4 descriptor bits (bits s, s+4, s+8, s+12 of `half`) -> 4 signed bytes (+MAG / -MAG)
+template <int MAG>
+__device__ __forceinline__ uint32_t expand4(uint32_t half, int s)
 {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+    constexpr uint32_t pool = ((uint32_t)MAG << 8) | (uint32_t)((256 - MAG) & 0xFF);          // byte 0 = -MAG (bit clear), byte 1 = +MAG (bit set)
+    return __byte_perm(pool, 0u, (half >> s) & 0x1111u);
 }
 
-// Hamming distance of two 256-bit rows, returned as (popc(w1a) + popc(w1b)) and the weight-2 / weight-4 words' counts
-// folded by the caller with IMADs (FMA pipe): d = p1a + p1b + 2*p2 + 4*p4.
-__device__ __forceinline__ uint32_t hamming256_csa(const uint32_t q[8], const uint4& ta, const uint4& tb)
+__device__ __forceinline__ uint32_t pack16(int lo, int hi)           // lo | hi << 16 on the FMA pipe (the ALU pipe is the busy one)
 {
-    const uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, x2 = q[2] ^ ta.z, x3 = q[3] ^ ta.w;
-    const uint32_t x4 = q[4] ^ tb.x, x5 = q[5] ^ tb.y, x6 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
-    const uint32_t s1 = lop3_xor3(x0, x1, x2), c1 = lop3_maj(x0, x1, x2);
-    const uint32_t s2 = lop3_xor3(x3, x4, x5), c2 = lop3_maj(x3, x4, x5);
-    const uint32_t s3 = lop3_xor3(s1, s2, x6), c3 = lop3_maj(s1, s2, x6);
-    const uint32_t s4 = lop3_xor3(c1, c2, c3), c4 = lop3_maj(c1, c2, c3);
-    return (uint32_t)__popc(c4) * 4u + ((uint32_t)__popc(s4) * 2u + (uint32_t)(__popc(s3) + __popc(x7)));
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+}
+
+__device__ __forceinline__ void imma_first(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int c01, int c23)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};\n"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c01), "r"(c23));
+}
+__device__ __forceinline__ void imma_acc(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 template <bool CROSS>
-__global__ void __launch_bounds__(KN_THREADS, 6) knn2_kernel(MatchSet ms, int K)
+__global__ void __launch_bounds__(KM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
 {
+    extern __shared__ __align__(16) uint32_t kmSmem[];
+    uint4* sB4 = reinterpret_cast<uint4*>(kmSmem);                 // [4][KM_CHUNK][4] uint4
+    uint32_t* sCol = kmSmem + 4 * KM_CHUNK * 16;                   // [KM_WARPS][KM_CHUNK / 2] per-warp column maxima, two columns per word
     uint32_t* __restrict__ knn = ms.knn;
     uint32_t* __restrict__ rev = ms.rev;
-    __shared__ __align__(16) uint32_t sT[KN_CHUNK * 8];
-    __shared__ uint32_t sRev[CROSS ? KN_CHUNK : 1];
     const int pair = ms.pair0 + blockIdx.y;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
     const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq, nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
-    const int qBase = blockIdx.x * KN_QT;
+    const int qBase = blockIdx.x * KM_ROWS;
     if (qBase >= nq) return;
-    const uint8_t* Q = ms.qdesc + (long long)qs * ms.qStride;
-    const uint8_t* T = ms.tdesc + (long long)ts * ms.tStride;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t* Q = reinterpret_cast<const uint32_t*>(ms.qdesc + (long long)qs * ms.qStride);
+    const uint32_t* T = reinterpret_cast<const uint32_t*>(ms.tdesc + (long long)ts * ms.tStride);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
 
-    uint32_t q[KN_R][8], m1[KN_R], m2[KN_R];
+    // row slot r = 2 * mtile + half: row-in-warp (r >> 1) * 16 + (r & 1) * 8 + g
+    uint32_t A[2][8][4];                     // [mtile][k-step][a0..a3]
+    int cinit[4];
 #pragma unroll
-    for (int r = 0; r < KN_R; ++r) {
-        const int qi = qBase + r * 32 + lane;
-        m1[r] = m2[r] = KEY_NONE;
-        if (qi < nq) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(Q + (long long)qi * 32));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(Q + (long long)qi * 32 + 16));
-            q[r][0] = a.x; q[r][1] = a.y; q[r][2] = a.z; q[r][3] = a.w; q[r][4] = b.x; q[r][5] = b.y; q[r][6] = b.z; q[r][7] = b.w;
-        } else {
+    for (int r = 0; r < 4; ++r) {
+        const int inWarp = (r >> 1) * 16 + (r & 1) * 8 + g, row = qBase + warp * 32 + inWarp;
+        const bool valid = row < nq;
+        cinit[r] = valid ? V_START + 32 - inWarp : 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[r][i] = 0;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w = valid ? __ldg(Q + (long long)row * 8 + 2 * q + (t >> 1)) : 0u;
+            const uint32_t half = (t & 1) ? (w >> 16) : (w & 0xFFFFu);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                // k-step 2q + e: a0/a1 (rows g / g+8) pair with b0, a2/a3 with b1
+                A[r >> 1][2 * q + e][(r & 1)] = valid ? expand4<1>(half, 2 * e) : 0u;
+                A[r >> 1][2 * q + e][2 + (r & 1)] = valid ? expand4<1>(half, 2 * e + 1) : 0u;
+            }
         }
     }
-    static_assert(KN_R == 4, "cross-check reduction is written for 4 queries per thread");
-    uint32_t qkey[KN_R];                    // query index = low half of the reverse key; rows past nq get a key above every valid one
+    uint32_t k1[4], k2[4];
 #pragma unroll
-    for (int r = 0; r < KN_R; ++r) { const int qi = qBase + r * 32 + lane; qkey[r] = qi < nq ? (uint32_t)qi : 0xF0000000u; }   // d << 16 <= 0x01000000: no wrap
-    for (int c0 = 0; c0 < nt; c0 += KN_CHUNK) {
-        const int cn = min(KN_CHUNK, nt - c0);
+    for (int r = 0; r < 4; ++r) k1[r] = k2[r] = KEY_NONE;
+
+    for (int c0 = 0; c0 < nt; c0 += KM_CHUNK) {
+        const int cn = min(KM_CHUNK, nt - c0);
         __syncthreads();
-        for (int i = threadIdx.x; i < cn * 2; i += KN_THREADS)
-            reinterpret_cast<uint4*>(sT)[i] = __ldg(reinterpret_cast<const uint4*>(T + (long long)c0 * 32) + i);
-        if (CROSS) for (int i = threadIdx.x; i < cn; i += KN_THREADS) sRev[i] = KEY_NONE;
+        // expand the chunk: item e = ((q * KM_CHUNK + col) * 4 + tt) -> one 16-byte store, consecutive threads consecutive addresses
+        for (int e = threadIdx.x; e < 4 * KM_CHUNK * 4; e += KM_THREADS) {
+            const int q = e >> 10, col = (e >> 2) & (KM_CHUNK - 1), tt = e & 3;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (col < cn) {
+                const uint32_t w = __ldg(T + (long long)(c0 + col) * 8 + 2 * q + (tt >> 1));
+                const uint32_t half = (tt & 1) ? (w >> 16) : (w & 0xFFFFu);
+                o = make_uint4(expand4<32>(half, 0), expand4<32>(half, 1), expand4<32>(half, 2), expand4<32>(half, 3));
+            }
+            sB4[e] = o;
+        }
         __syncthreads();
-        for (int j = warp; j < cn; j += KN_WARPS) {
-            const uint4 ta = reinterpret_cast<const uint4*>(sT)[2 * j], tb = reinterpret_cast<const uint4*>(sT)[2 * j + 1];
-            const uint32_t idx = (uint32_t)(c0 + j);
-            uint32_t key[KN_R];
+
+        // per chunk and row slot: packed running top-2 of each of the thread's two column streams (low half = column 2t of every
+        // tile, high half = 2t + 1); the row code in the low 6 bits is replaced by 32 - tile, so ties keep the earlier column
+        uint32_t b1[4] = {0u, 0u, 0u, 0u}, b2[4] = {0u, 0u, 0u, 0u};
+        uint32_t tcode = 32u * 0x10001u;
+        const int ntiles = (cn + 7) >> 3;
+        for (int tile = 0; tile < ntiles; ++tile, tcode -= 0x10001u) {
+            const int colB = tile * 8;
+            uint4 b[4];
 #pragma unroll
-            for (int r = 0; r < KN_R; ++r) key[r] = hamming256_csa(q[r], ta, tb) * 65536u + idx;
-            // train rows arrive in ascending index order, so a pair enters the top-2 iff its key is below the second best
-            bool any = false;
+            for (int q = 0; q < 4; ++q) b[q] = sB4[(q * KM_CHUNK + colB + g) * 4 + t];
+            int acc[2][4];
+            imma_first(acc[0], A[0][0], b[0].x, b[0].y, cinit[0], cinit[1]);
+            imma_first(acc[1], A[1][0], b[0].x, b[0].y, cinit[2], cinit[3]);
+            imma_acc(acc[0], A[0][1], b[0].z, b[0].w);
+            imma_acc(acc[1], A[1][1], b[0].z, b[0].w);
 #pragma unroll
-            for (int r = 0; r < KN_R; ++r) any |= key[r] < m2[r];
-            if (any) {
+            for (int q = 1; q < 4; ++q) {
+                imma_acc(acc[0], A[0][2 * q], b[q].x, b[q].y);
+                imma_acc(acc[1], A[1][2 * q], b[q].x, b[q].y);
+                imma_acc(acc[0], A[0][2 * q + 1], b[q].z, b[q].w);
+                imma_acc(acc[1], A[1][2 * q + 1], b[q].z, b[q].w);
+            }
+            if (colB + 8 > cn) {
+                // ragged last tile: columns past nt score hamming 256 and carry an index >= nt, so every valid column beats them
+                const bool v0 = colB + 2 * t < cn, v1 = colB + 2 * t + 1 < cn;
 #pragma unroll
-                for (int r = 0; r < KN_R; ++r) top2_insert(m1[r], m2[r], key[r]);
+                for (int m = 0; m < 2; ++m) {
+                    if (!v0) acc[m][0] = acc[m][2] = 0;
+                    if (!v1) acc[m][1] = acc[m][3] = 0;
+                }
+            }
+            uint32_t P[4];                    // row slot r: columns 2t (low half) and 2t + 1 (high half)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) P[r] = pack16(acc[r >> 1][2 * (r & 1)], acc[r >> 1][2 * (r & 1) + 1]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t e = (P[r] & 0xFFC0FFC0u) | tcode;
+                b2[r] = __vmaxu2(b2[r], __vminu2(b1[r], e));
+                b1[r] = __vmaxu2(b1[r], e);
             }
             if (CROSS) {
-                // per train row: best query of this warp's 128 (rows past nq carry an all-ones query key)
-                const uint32_t a = min(key[0] - idx + qkey[0], key[1] - idx + qkey[1]), b = min(key[2] - idx + qkey[2], key[3] - idx + qkey[3]);
-                const uint32_t wmin = __reduce_min_sync(0xffffffffu, min(a, b));
-                if (lane == 0 && wmin < 0xF0000000u) atomicMin(&sRev[j], wmin);
+                // columns: best (h, lowest query) of the warp's 32 rows; every (warp, column) is visited once, so a plain store
+                uint32_t m = __vmaxu2(__vimax3_u16x2(P[0], P[1], P[2]), P[3]);
+                m = __vmaxu2(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                m = __vmaxu2(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                m = __vmaxu2(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                if (g == 0) sCol[warp * (KM_CHUNK / 2) + tile * 4 + t] = m;
+            }
+        }
+        // fold the chunk's candidates into the rows' (distance << 16 | trainIdx) top-2
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = ((k & 2) ? b2[r] : b1[r]) >> ((k & 1) * 16) & 0xFFFFu;
+                if (e) {
+                    const uint32_t col = (uint32_t)c0 + (32u - (e & 63u)) * 8u + 2u * t + (k & 1);
+                    top2_insert(k1[r], k2[r], ((256u - (e >> V_SHIFT)) << 16) | col);
+                }
             }
         }
         if (CROSS) {
             __syncthreads();
-            for (int i = threadIdx.x; i < cn; i += KN_THREADS)
-                if (sRev[i] != KEY_NONE) atomicMin(&rev[(long long)pair * K + c0 + i], sRev[i]);
+            for (int i = threadIdx.x; i < cn; i += KM_THREADS) {
+                uint32_t best = 0u;           // h << 9 | (7 - warp) << 6 | rc: highest h, then lowest row
+#pragma unroll
+                for (int w = 0; w < KM_WARPS; ++w) {
+                    const uint32_t v = (sCol[w * (KM_CHUNK / 2) + (i >> 1)] >> ((i & 1) * 16)) & 0xFFFFu;
+                    if (v & 63u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(KM_WARPS - 1 - w) << V_SHIFT) | (v & 63u));
+                }
+                if (best) {
+                    const uint32_t row = (uint32_t)qBase + (KM_WARPS - 1 - ((best >> V_SHIFT) & 7u)) * 32u + 32u - (best & 63u);
+                    atomicMin(&rev[(long long)pair * K + c0 + i], (256u - (best >> 9)) * 65536u + row);
+                }
+            }
         }
     }
-    // merge the warps' partial top-2 lists (the staging area aliases the train rows, which are no longer needed)
-    __syncthreads();
-    uint32_t (*sMerge)[KN_R][2][32] = reinterpret_cast<uint32_t (*)[KN_R][2][32]>(sT);
+    // merge the 4 lanes of each row group; lane t == 0 writes
 #pragma unroll
-    for (int r = 0; r < KN_R; ++r) { sMerge[warp][r][0][lane] = m1[r]; sMerge[warp][r][1][lane] = m2[r]; }
-    __syncthreads();
-    if (warp == 0) {
+    for (int r = 0; r < 4; ++r) {
 #pragma unroll
-        for (int r = 0; r < KN_R; ++r) {
-            uint32_t a = KEY_NONE, b = KEY_NONE;
-#pragma unroll
-            for (int w = 0; w < KN_WARPS; ++w) { top2_insert(a, b, sMerge[w][r][0][lane]); top2_insert(a, b, sMerge[w][r][1][lane]); }
-            const int qi = qBase + r * 32 + lane;
-            if (qi < nq) {
-                uint2* o = reinterpret_cast<uint2*>(knn + ((long long)pair * K + qi) * 2);
-                *o = make_uint2(a, b);
-            }
+        for (int o = 1; o <= 2; o <<= 1) {
+            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1[r], o), o2 = __shfl_xor_sync(0xffffffffu, k2[r], o);
+            top2_insert(k1[r], k2[r], o1);
+            top2_insert(k1[r], k2[r], o2);
+        }
+        const int row = qBase + warp * 32 + (r >> 1) * 16 + (r & 1) * 8 + g;
+        if (t == 0 && row < nq) {
+            const uint32_t a = (int)(k1[r] & 0xFFFFu) < nt ? k1[r] : KEY_NONE, b = (int)(k2[r] & 0xFFFFu) < nt ? k2[r] : KEY_NONE;
+            *reinterpret_cast<uint2*>(knn + ((long long)pair * K + row) * 2) = make_uint2(a, b);
         }
     }
 }
@@ -245,11 +321,13 @@ int orbf_launch_knn2(orbf_context* c, const MatchSet& ms, int npairs, bool cross
 {
     const int maxNq = ms.qCounts ? c->K : ms.nq;
     if (maxNq <= 0 || npairs <= 0) return ORBF_OK;
-    dim3 grid((maxNq + KN_QT - 1) / KN_QT, npairs);
+    dim3 grid((maxNq + KM_ROWS - 1) / KM_ROWS, npairs);
+    if (cross) ORBF_CUDA(c, cudaFuncSetAttribute(knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KM_SMEM));
+    else ORBF_CUDA(c, cudaFuncSetAttribute(knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KM_SMEM));
     if (cross) {
         ORBF_CUDA(c, cudaMemsetAsync(ms.rev + (size_t)ms.pair0 * c->K, 0xFF, (size_t)npairs * c->K * sizeof(uint32_t), c->stream));
-        knn2_kernel<true><<<grid, KN_THREADS, 0, c->stream>>>(ms, c->K);
-    } else knn2_kernel<false><<<grid, KN_THREADS, 0, c->stream>>>(ms, c->K);
+        knn2_kernel<true><<<grid, KM_THREADS, KM_SMEM, c->stream>>>(ms, c->K);
+    } else knn2_kernel<false><<<grid, KM_THREADS, KM_SMEM, c->stream>>>(ms, c->K);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }
