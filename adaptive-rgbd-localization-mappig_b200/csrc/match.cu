@@ -4,32 +4,34 @@
 // packed key (dist << 16 | trainIdx) reproduces under unsigned min.
 //
 // The O(nq * nt * 256) distance matrix is the one compute-bound piece of the path (64 KB of descriptors per pair, 2.6e8 bit
-// operations), so it runs on the tensor cores as an exact integer GEMM: every descriptor bit becomes a signed byte (1 -> +1,
-// 0 -> -1), dot(a, b) over the 256 bytes = 256 - 2 * hamming(a, b), and IMMA (mma.sync m16n8k32 s8*s8 -> s32) produces
-// 16 x 8 distances per 8 instructions.  The previous POPC/LOP3 kernel needed ~100 warp instructions for the same 128
-// distances and was bound by the integer ALU pipe (0.63e12 distances/s); B200's s8 mma.sync path sustains 0.48 IMMA/clk/SM
-// = 2.2e12 distances/s (tools/bmma_probe.cu).  The bit -> byte expansion is one PRMT per 4 bytes (the selector nibbles are the
-// bits, the pool bytes are 0xFF / 0x01); the order of the 256 dimensions is irrelevant as long as both operands use the
-// same one, so the expansion is laid out to make the fragment loads contiguous.
-//
-// CTA = 8 warps = 256 query rows (two m16 tiles per warp, A fragments resident in 64 registers); train rows are expanded in
-// chunks of 256 into shared memory as [k-step pair][column][lane-in-group][4 words], which makes every B-fragment load a
-// conflict-free LDS.128.  The epilogue is branch-free and packed two columns per register (VIMNMX.U16x2): per n8 tile and
-// row slot a running top-2 of 15-bit (256 - distance, tile) codes, decoded into (distance << 16 | trainIdx) keys once per
-// chunk; for the cross-check, the maximum over the thread's rows and 3 shuffles over the 8 row groups give the warp's best
-// (256 - distance, row) per column, stored per warp and folded over the 8 warps at the end of the chunk.
+// operations), so it runs on the 5th-generation tensor cores as an exact integer GEMM: every descriptor bit becomes a signed
+// byte (query: 1 -> +1, 0 -> -1; train: +-64), dot(a, b) over the 256 bytes = 64 * (256 - 2 * hamming(a, b)), computed by
+// tcgen05.mma kind::i8 (s8 x s8 -> s32) with the 128 x 256 accumulator tile in tensor memory.
+//   * CTA = 128 query rows (one TMEM lane each) x the pair's train rows in chunks of 256; two CTAs share an SM (2 x 256 TMEM
+//     columns, 2 x 98 KB of shared memory), so one CTA's epilogue runs under the other's MMAs.
+//   * Operands are expanded in the kernel, straight into the no-swizzle K-major canonical layout (8-row x 16-byte core
+//     matrices, LBO 128 B, SBO 2 KB): one PRMT turns 4 descriptor bits into 4 bytes (selector nibbles = the bits, pool bytes =
+//     the two codes).  The order of the 256 dimensions is irrelevant as long as both operands use the same one.
+//   * One thread issues the 8 K-steps (UTCIMMA 128 x 256 x 32) and commits to an mbarrier; every thread then reads its own
+//     row with tcgen05.ld (32x32b.x32) and works on two columns per register (VIMNMX.U16x2):
+//       value v = accumulator + 64 * 256 + rc = 128 * (256 - hamming) + rc, rc = 32 - lane in the low 7 bits;
+//       rows:    per 128 columns a packed running top-2 of (v with rc replaced by 64 - pair index), decoded into
+//                (distance << 16 | trainIdx) keys once per 128 columns;
+//       columns (cross-check, quirk Q10): a 31-shuffle halving butterfly leaves lane L with the best (256 - hamming, row) of the
+//                warp's 32 rows for column pair L; the 4 warps are folded through shared memory once per chunk.
+// History: a POPC/LOP3 kernel (integer-ALU bound, 0.81 ms per 511 pairs), then mma.sync IMMA s8 (0.43 ms; warp-level MMAs block
+// the issue port ~6 of every 8.3 clk, tools/bmma_probe.cu), now tcgen05 (tools/umma_probe.cu pins the descriptor fields).
 #include "orbf_internal.h"
 
 namespace {
 
-constexpr int KM_WARPS = 8, KM_THREADS = KM_WARPS * 32, KM_ROWS = KM_WARPS * 32, KM_CHUNK = 256;
-constexpr size_t KM_SMEM = (size_t)4 * KM_CHUNK * 16 * sizeof(uint32_t) + KM_WARPS * (KM_CHUNK / 2) * sizeof(uint32_t);
+constexpr int UM_THREADS = 128, UM_ROWS = 128, UM_CHUNK = 256;
+constexpr uint32_t UM_LBO = 128, UM_SBO = 16 * 128;             // bytes: next 16-byte K chunk / next 8-row group
+constexpr size_t UM_SMEM_A = (size_t)UM_ROWS * 256, UM_SMEM_B = (size_t)UM_CHUNK * 256, UM_SMEM_COL = 4 * (UM_CHUNK / 2) * sizeof(uint32_t);
+constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + 1024;   // + slack to align the operand tiles
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
-// Accumulator encoding: train bytes are +-32 and query bytes +-1, so an accumulator that starts at 32 * 256 + rc holds
-// v = 64 * h + rc with h = 256 - hamming (0..256) and rc = 32 - (row within the warp's 32) in the low 6 bits: one 15-bit
-// value that orders a column's candidates by (distance asc, query asc) and still tells which row it came from.  Rows past nq
-// have all-zero bytes and start at 0 (v = 0, rc = 0 marks them).
-constexpr int V_SHIFT = 6, V_START = 32 * 256;
+constexpr int V_SHIFT = 7;
+constexpr uint32_t V_BIAS = 64 * 256;
 
 __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t key)
 {
@@ -37,184 +39,202 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
     m1 = min(m1, key);
 }
 
-// 4 descriptor bits (bits s, s+4, s+8, s+12 of `half`) -> 4 signed bytes (+MAG / -MAG)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 4 descriptor bits (bits s, s+4, s+8, s+12 of `half`) -> 4 signed bytes (+MAG where the bit is 1, -MAG where it is 0)
 template <int MAG>
 __device__ __forceinline__ uint32_t expand4(uint32_t half, int s)
 {
-    constexpr uint32_t pool = ((uint32_t)MAG << 8) | (uint32_t)((256 - MAG) & 0xFF);          // byte 0 = -MAG (bit clear), byte 1 = +MAG (bit set)
+    constexpr uint32_t pool = ((uint32_t)MAG << 8) | (uint32_t)((256 - MAG) & 0xFF);
     return __byte_perm(pool, 0u, (half >> s) & 0x1111u);
 }
 
-__device__ __forceinline__ uint32_t pack16(int lo, int hi)           // lo | hi << 16 on the FMA pipe (the ALU pipe is the busy one)
+// one descriptor word -> 32 operand bytes = K chunks 2w and 2w + 1 of `row` in the canonical layout
+template <int MAG>
+__device__ __forceinline__ void expand_word(uint8_t* tile, int row, int w, uint32_t bits, bool valid)
 {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(hi), "r"(lo));
-    return r;
+    uint8_t* dst = tile + (row >> 3) * UM_SBO + (2 * w) * UM_LBO + (row & 7) * 16;
+    const uint32_t lo = bits & 0xFFFFu, hi = bits >> 16;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (valid) {
+        a = make_uint4(expand4<MAG>(lo, 0), expand4<MAG>(lo, 1), expand4<MAG>(lo, 2), expand4<MAG>(lo, 3));
+        b = make_uint4(expand4<MAG>(hi, 0), expand4<MAG>(hi, 1), expand4<MAG>(hi, 2), expand4<MAG>(hi, 3));
+    }
+    *reinterpret_cast<uint4*>(dst) = a;
+    *reinterpret_cast<uint4*>(dst + UM_LBO) = b;
 }
 
-__device__ __forceinline__ void imma_first(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int c01, int c23)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr)
 {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};\n"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c01), "r"(c23));
+    // start address, leading / stride byte offsets (all >> 4), descriptor version 1 (sm_100), layout type 0 = no swizzle
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | (uint64_t)(UM_LBO >> 4) << 16 | (uint64_t)(UM_SBO >> 4) << 32 | (uint64_t)1 << 46;
 }
-__device__ __forceinline__ void imma_acc(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                   "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                   "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Halving butterfly: lanes with bit HALF set keep the upper half of P[0 .. 2 * HALF) and send the lower one, and vice versa.
+template <int HALF>
+__device__ __forceinline__ void bfly_max(uint32_t (&P)[32], int lane)
+{
+    const bool up = (lane & HALF) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        const uint32_t send = up ? P[i] : P[i + HALF], keep = up ? P[i + HALF] : P[i];
+        P[i] = __vmaxu2(keep, __shfl_xor_sync(0xffffffffu, send, HALF));
+    }
 }
 
 template <bool CROSS>
-__global__ void __launch_bounds__(KM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
+__global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
 {
-    extern __shared__ __align__(16) uint32_t kmSmem[];
-    uint4* sB4 = reinterpret_cast<uint4*>(kmSmem);                 // [4][KM_CHUNK][4] uint4
-    uint32_t* sCol = kmSmem + 4 * KM_CHUNK * 16;                   // [KM_WARPS][KM_CHUNK / 2] per-warp column maxima, two columns per word
+    extern __shared__ uint8_t umSmemRaw[];
+    __shared__ uint32_t sTmem;
+    __shared__ __align__(8) uint64_t sBar;
     uint32_t* __restrict__ knn = ms.knn;
     uint32_t* __restrict__ rev = ms.rev;
     const int pair = ms.pair0 + blockIdx.y;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
     const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq, nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
-    const int qBase = blockIdx.x * KM_ROWS;
+    const int qBase = blockIdx.x * UM_ROWS;
     if (qBase >= nq) return;
     const uint32_t* Q = reinterpret_cast<const uint32_t*>(ms.qdesc + (long long)qs * ms.qStride);
     const uint32_t* T = reinterpret_cast<const uint32_t*>(ms.tdesc + (long long)ts * ms.tStride);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* sA = umSmemRaw + ((1024u - (smem_u32(umSmemRaw) & 1023u)) & 1023u);
+    uint8_t* sB = sA + UM_SMEM_A;
+    uint32_t* sCol = reinterpret_cast<uint32_t*>(sB + UM_SMEM_B);           // [4 warps][UM_CHUNK / 2] packed per-warp column maxima
 
-    // row slot r = 2 * mtile + half: row-in-warp (r >> 1) * 16 + (r & 1) * 8 + g
-    uint32_t A[2][8][4];                     // [mtile][k-step][a0..a3]
-    int cinit[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int inWarp = (r >> 1) * 16 + (r & 1) * 8 + g, row = qBase + warp * 32 + inWarp;
-        const bool valid = row < nq;
-        cinit[r] = valid ? V_START + 32 - inWarp : 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t w = valid ? __ldg(Q + (long long)row * 8 + 2 * q + (t >> 1)) : 0u;
-            const uint32_t half = (t & 1) ? (w >> 16) : (w & 0xFFFFu);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                // k-step 2q + e: a0/a1 (rows g / g+8) pair with b0, a2/a3 with b1
-                A[r >> 1][2 * q + e][(r & 1)] = valid ? expand4<1>(half, 2 * e) : 0u;
-                A[r >> 1][2 * q + e][2 + (r & 1)] = valid ? expand4<1>(half, 2 * e + 1) : 0u;
-            }
-        }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "n"(UM_CHUNK));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    uint32_t k1[4], k2[4];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    // this thread's query row = TMEM lane tid
+    const int row = qBase + tid;
+    const bool rowValid = row < nq;
+    {
+        uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;
+        if (rowValid) { d0 = __ldg(reinterpret_cast<const uint4*>(Q + (long long)row * 8)); d1 = __ldg(reinterpret_cast<const uint4*>(Q + (long long)row * 8) + 1); }
+        const uint32_t w[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-    for (int r = 0; r < 4; ++r) k1[r] = k2[r] = KEY_NONE;
+        for (int i = 0; i < 8; ++i) expand_word<1>(sA, tid, i, w[i], rowValid);
+    }
+    const uint32_t vadd = rowValid ? (V_BIAS + 32u - (uint32_t)lane) * 0x10001u : 0u;   // both halves: + 64 * 256 + rc
+    uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+    // instruction descriptor: D s32 (2 @ bit 4), A / B signed 8-bit (1 @ 7, 1 @ 10), both K-major, N >> 3 @ 17, M >> 4 @ 24
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UM_CHUNK >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+    uint32_t tmem = 0;
+    uint32_t phase = 0;
 
-    for (int c0 = 0; c0 < nt; c0 += KM_CHUNK) {
-        const int cn = min(KM_CHUNK, nt - c0);
-        __syncthreads();
-        // expand the chunk: item e = ((q * KM_CHUNK + col) * 4 + tt) -> one 16-byte store, consecutive threads consecutive addresses
-        for (int e = threadIdx.x; e < 4 * KM_CHUNK * 4; e += KM_THREADS) {
-            const int q = e >> 10, col = (e >> 2) & (KM_CHUNK - 1), tt = e & 3;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (col < cn) {
-                const uint32_t w = __ldg(T + (long long)(c0 + col) * 8 + 2 * q + (tt >> 1));
-                const uint32_t half = (tt & 1) ? (w >> 16) : (w & 0xFFFFu);
-                o = make_uint4(expand4<32>(half, 0), expand4<32>(half, 1), expand4<32>(half, 2), expand4<32>(half, 3));
-            }
-            sB4[e] = o;
+    for (int c0 = 0; c0 < nt; c0 += UM_CHUNK) {
+        const int cn = min(UM_CHUNK, nt - c0);
+        // the previous chunk's MMAs are complete (every thread waited on the barrier), so the train tile can be overwritten
+        for (int i = tid; i < UM_CHUNK * 8; i += UM_THREADS) {
+            const int col = i & (UM_CHUNK - 1), w = i >> 8;
+            const bool valid = col < cn;
+            const uint32_t bits = valid ? __ldg(T + (long long)(c0 + col) * 8 + w) : 0u;
+            expand_word<64>(sB, col, w, bits, valid);
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> the tensor core's async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // orders the previous chunk's tcgen05.ld before the MMAs
         __syncthreads();
-
-        // per chunk and row slot: packed running top-2 of each of the thread's two column streams (low half = column 2t of every
-        // tile, high half = 2t + 1); the row code in the low 6 bits is replaced by 32 - tile, so ties keep the earlier column
-        uint32_t b1[4] = {0u, 0u, 0u, 0u}, b2[4] = {0u, 0u, 0u, 0u};
-        uint32_t tcode = 32u * 0x10001u;
-        const int ntiles = (cn + 7) >> 3;
-        for (int tile = 0; tile < ntiles; ++tile, tcode -= 0x10001u) {
-            const int colB = tile * 8;
-            uint4 b[4];
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem = sTmem;
+        if (tid == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) b[q] = sB4[(q * KM_CHUNK + colB + g) * 4 + t];
-            int acc[2][4];
-            imma_first(acc[0], A[0][0], b[0].x, b[0].y, cinit[0], cinit[1]);
-            imma_first(acc[1], A[1][0], b[0].x, b[0].y, cinit[2], cinit[3]);
-            imma_acc(acc[0], A[0][1], b[0].z, b[0].w);
-            imma_acc(acc[1], A[1][1], b[0].z, b[0].w);
-#pragma unroll
-            for (int q = 1; q < 4; ++q) {
-                imma_acc(acc[0], A[0][2 * q], b[q].x, b[q].y);
-                imma_acc(acc[1], A[1][2 * q], b[q].x, b[q].y);
-                imma_acc(acc[0], A[0][2 * q + 1], b[q].z, b[q].w);
-                imma_acc(acc[1], A[1][2 * q + 1], b[q].z, b[q].w);
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t da = umma_desc(smem_u32(sA) + ks * 2 * UM_LBO), db = umma_desc(smem_u32(sB) + ks * 2 * UM_LBO);
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
             }
-            if (colB + 8 > cn) {
-                // ragged last tile: columns past nt score hamming 256 and carry an index >= nt, so every valid column beats them
-                const bool v0 = colB + 2 * t < cn, v1 = colB + 2 * t + 1 < cn;
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sBar)) : "memory");
+        }
+        {
+            uint32_t done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&sBar)), "r"(phase) : "memory");
+                if (!done && ++spins > (1u << 26)) __trap();                   // a lost commit must fail loudly, not hang the device
+            }
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int seg = 0; seg < 2; ++seg) {                    // 128 columns = 64 column pairs per segment
+            uint32_t b1 = 0u, b2 = 0u;                         // packed running top-2 of the even / odd column streams
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    if (!v0) acc[m][0] = acc[m][2] = 0;
-                    if (!v1) acc[m][1] = acc[m][3] = 0;
+            for (int bt = 0; bt < 2; ++bt) {                   // 64 columns = 32 pairs per batch
+                const int colBase = seg * 128 + bt * 64;
+                uint32_t P[32];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld32(tbase + colBase + hf * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) P[hf * 16 + j] = v[2 * j] + (v[2 * j + 1] << 16) + vadd;
+                }
+                if (colBase + 64 > cn) {
+                    // columns past nt (zero operand rows) must lose against every real column: v = 0
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        P[j] &= (colBase + 2 * j < cn ? 0x0000FFFFu : 0u) | (colBase + 2 * j + 1 < cn ? 0xFFFF0000u : 0u);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t e = (P[j] & 0xFF80FF80u) | ((uint32_t)(64 - (bt * 32 + j)) * 0x10001u);
+                    b2 = __vmaxu2(b2, __vminu2(b1, e));
+                    b1 = __vmaxu2(b1, e);
+                }
+                if (CROSS) {
+                    bfly_max<16>(P, lane); bfly_max<8>(P, lane); bfly_max<4>(P, lane); bfly_max<2>(P, lane); bfly_max<1>(P, lane);
+                    sCol[warp * (UM_CHUNK / 2) + (colBase >> 1) + lane] = P[0];
                 }
             }
-            uint32_t P[4];                    // row slot r: columns 2t (low half) and 2t + 1 (high half)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) P[r] = pack16(acc[r >> 1][2 * (r & 1)], acc[r >> 1][2 * (r & 1) + 1]);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t e = (P[r] & 0xFFC0FFC0u) | tcode;
-                b2[r] = __vmaxu2(b2[r], __vminu2(b1[r], e));
-                b1[r] = __vmaxu2(b1[r], e);
-            }
-            if (CROSS) {
-                // columns: best (h, lowest query) of the warp's 32 rows; every (warp, column) is visited once, so a plain store
-                uint32_t m = __vmaxu2(__vimax3_u16x2(P[0], P[1], P[2]), P[3]);
-                m = __vmaxu2(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                m = __vmaxu2(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                m = __vmaxu2(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                if (g == 0) sCol[warp * (KM_CHUNK / 2) + tile * 4 + t] = m;
-            }
-        }
-        // fold the chunk's candidates into the rows' (distance << 16 | trainIdx) top-2
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t e = ((k & 2) ? b2[r] : b1[r]) >> ((k & 1) * 16) & 0xFFFFu;
-                if (e) {
-                    const uint32_t col = (uint32_t)c0 + (32u - (e & 63u)) * 8u + 2u * t + (k & 1);
-                    top2_insert(k1[r], k2[r], ((256u - (e >> V_SHIFT)) << 16) | col);
-                }
+                const uint32_t e = ((k & 2) ? b2 : b1) >> ((k & 1) * 16) & 0xFFFFu;
+                const uint32_t col = (uint32_t)(c0 + seg * 128) + (64u - (e & 127u)) * 2u + (k & 1);
+                if (e && (int)col < nt) top2_insert(k1, k2, ((256u - (e >> V_SHIFT)) << 16) | col);
             }
         }
         if (CROSS) {
             __syncthreads();
-            for (int i = threadIdx.x; i < cn; i += KM_THREADS) {
-                uint32_t best = 0u;           // h << 9 | (7 - warp) << 6 | rc: highest h, then lowest row
+            const uint32_t both[4] = {sCol[tid], sCol[UM_CHUNK / 2 + tid], sCol[2 * (UM_CHUNK / 2) + tid], sCol[3 * (UM_CHUNK / 2) + tid]};
 #pragma unroll
-                for (int w = 0; w < KM_WARPS; ++w) {
-                    const uint32_t v = (sCol[w * (KM_CHUNK / 2) + (i >> 1)] >> ((i & 1) * 16)) & 0xFFFFu;
-                    if (v & 63u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(KM_WARPS - 1 - w) << V_SHIFT) | (v & 63u));
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t best = 0u;                            // h << 9 | (3 - warp) << 7 | rc: highest h, then lowest row
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t v = (both[w] >> (hf * 16)) & 0xFFFFu;
+                    if (v & 127u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(3 - w) << V_SHIFT) | (v & 127u));
                 }
-                if (best) {
-                    const uint32_t row = (uint32_t)qBase + (KM_WARPS - 1 - ((best >> V_SHIFT) & 7u)) * 32u + 32u - (best & 63u);
-                    atomicMin(&rev[(long long)pair * K + c0 + i], (256u - (best >> 9)) * 65536u + row);
+                const int col = 2 * tid + hf;
+                if (best && col < cn) {
+                    const uint32_t r = (uint32_t)qBase + (3u - ((best >> V_SHIFT) & 3u)) * 32u + 32u - (best & 127u);
+                    atomicMin(&rev[(long long)pair * K + c0 + col], (256u - (best >> 9)) * 65536u + r);
                 }
             }
         }
     }
-    // merge the 4 lanes of each row group; lane t == 0 writes
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1[r], o), o2 = __shfl_xor_sync(0xffffffffu, k2[r], o);
-            top2_insert(k1[r], k2[r], o1);
-            top2_insert(k1[r], k2[r], o2);
-        }
-        const int row = qBase + warp * 32 + (r >> 1) * 16 + (r & 1) * 8 + g;
-        if (t == 0 && row < nq) {
-            const uint32_t a = (int)(k1[r] & 0xFFFFu) < nt ? k1[r] : KEY_NONE, b = (int)(k2[r] & 0xFFFFu) < nt ? k2[r] : KEY_NONE;
-            *reinterpret_cast<uint2*>(knn + ((long long)pair * K + row) * 2) = make_uint2(a, b);
-        }
-    }
+    if (rowValid) *reinterpret_cast<uint2*>(knn + ((long long)pair * K + row) * 2) = make_uint2(k1, k2);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sTmem), "n"(UM_CHUNK));
 }
 
 constexpr int MS_THREADS = 256;
@@ -321,13 +341,13 @@ int orbf_launch_knn2(orbf_context* c, const MatchSet& ms, int npairs, bool cross
 {
     const int maxNq = ms.qCounts ? c->K : ms.nq;
     if (maxNq <= 0 || npairs <= 0) return ORBF_OK;
-    dim3 grid((maxNq + KM_ROWS - 1) / KM_ROWS, npairs);
-    if (cross) ORBF_CUDA(c, cudaFuncSetAttribute(knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KM_SMEM));
-    else ORBF_CUDA(c, cudaFuncSetAttribute(knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KM_SMEM));
+    dim3 grid((maxNq + UM_ROWS - 1) / UM_ROWS, npairs);
+    if (cross) ORBF_CUDA(c, cudaFuncSetAttribute(knn2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
+    else ORBF_CUDA(c, cudaFuncSetAttribute(knn2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
     if (cross) {
         ORBF_CUDA(c, cudaMemsetAsync(ms.rev + (size_t)ms.pair0 * c->K, 0xFF, (size_t)npairs * c->K * sizeof(uint32_t), c->stream));
-        knn2_kernel<true><<<grid, KM_THREADS, KM_SMEM, c->stream>>>(ms, c->K);
-    } else knn2_kernel<false><<<grid, KM_THREADS, KM_SMEM, c->stream>>>(ms, c->K);
+        knn2_kernel<true><<<grid, UM_THREADS, UM_SMEM, c->stream>>>(ms, c->K);
+    } else knn2_kernel<false><<<grid, UM_THREADS, UM_SMEM, c->stream>>>(ms, c->K);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }

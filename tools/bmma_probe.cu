@@ -45,6 +45,71 @@ __global__ void imma_tput_kernel(int iters, int* sink)
     if (s == 0x7fffffff) sink[0] = s;
 }
 
+__device__ __forceinline__ void qmma_e4m3(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.f32.e4m3.e4m3.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int ILP>
+__global__ void qmma_tput_kernel(int iters, int* sink)
+{
+    uint32_t a[4] = {0x38383838u, 0x38003838u, 0x00383800u, 0x38380038u};     // 1.0 in e4m3 = 0x38
+    uint32_t b[2] = {0x38383800u, (blockIdx.x & 1u) * 0x38383838u};
+    float d[ILP][4];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) d[k][0] = d[k][1] = d[k][2] = d[k][3] = 0.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) qmma_e4m3(d[k], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += d[k][0] + d[k][1] + d[k][2] + d[k][3];
+    if (s == 12345.f) sink[0] = (int)s;
+}
+
+
+// does IMMA issue overlap with integer ALU work of the same / other warps?  NALU independent LOP3-class ops per 8 IMMAs
+template <int NALU>
+__global__ void mix_kernel(int iters, int* sink)
+{
+    uint32_t a[4] = {threadIdx.x & 0x01010101u, 0x01000101u, 0x00010100u, 0x01010001u};
+    uint32_t b[2] = {0x01010100u, (blockIdx.x & 1u) * 0x01010101u};
+    int d[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k][0] = d[k][1] = d[k][2] = d[k][3] = 0;
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = threadIdx.x * 77u + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            imma_u8(d[k], a, b);
+#pragma unroll
+            for (int j = 0; j < NALU / 8; ++j) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[(k + j) & 7]) : "r"(x[(k + j + 3) & 7]), "r"(x[(k + j + 5) & 7]));
+        }
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += d[k][0] + d[k][1] + d[k][2] + d[k][3] + (int)x[k];
+    if (s == 0x7fffffff) sink[0] = s;
+}
+
+template <int NALU>
+static void run_mix(int* dO, cudaDeviceProp& p, int clk, cudaEvent_t e0, cudaEvent_t e1)
+{
+    const int iters = 50000, warps = 16;
+    int blocks = p.multiProcessorCount;
+    mix_kernel<NALU><<<blocks, warps * 32>>>(100, dO); cudaDeviceSynchronize();
+    cudaEventRecord(e0); mix_kernel<NALU><<<blocks, warps * 32>>>(iters, dO); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double clkPerIter = ms * 1e-3 * clk * 1e3 / iters;          // SM clocks per loop iteration (all 16 warps run one iteration each)
+    printf("mix: 8 IMMA + %3d ALU per warp-iteration, 16 warps/SM: %.1f clk per iteration-round  (IMMA alone would be %.1f, ALU alone %.1f)\n", NALU, clkPerIter,
+           16 * 8 / 0.48, 16.0 * NALU / 2.0);
+}
+
 // correctness: one warp, 16 descriptors x 8 descriptors
 __global__ void check_kernel(const uint32_t* A, const uint32_t* B, int* out, int useXor)
 {
@@ -131,5 +196,26 @@ int main()
         printf("IMMA.16832.U8 warps/CTA %2d: %.1f G imma/s = %.3f imma/clk/SM (nominal %d MHz) = %.1f dense int8 TOP/s; 256-bit pair-distances: %.1f T/s\n", warps,
                n / ms * 1e-6, n / (ms * 1e-3) / p.multiProcessorCount / (clk * 1e3), clk / 1000, n * 4096 * 2 / ms * 1e-9, n * 16 / ms * 1e-9);
     }
+    for (int warps = 4; warps <= 16; warps *= 2) {
+        const int iters = 100000, ILP = 8;
+        int blocks = p.multiProcessorCount * 2;
+        qmma_tput_kernel<ILP><<<blocks, warps * 32>>>(100, dO); cudaDeviceSynchronize();
+        cudaEventRecord(e0); qmma_tput_kernel<ILP><<<blocks, warps * 32>>>(iters, dO); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double n = (double)blocks * warps * iters * ILP;
+        printf("QMMA.16832.E4M3 (f32 acc) warps/CTA %2d: %.1f G mma/s = %.3f mma/clk/SM = %.1f dense fp8 TFLOP/s\n", warps,
+               n / ms * 1e-6, n / (ms * 1e-3) / p.multiProcessorCount / (clk * 1e3), n * 4096 * 2 / ms * 1e-9);
+    }
+    run_mix<0>(dO, p, clk, e0, e1); run_mix<16>(dO, p, clk, e0, e1); run_mix<32>(dO, p, clk, e0, e1); run_mix<64>(dO, p, clk, e0, e1); run_mix<128>(dO, p, clk, e0, e1);
     return 0;
+}
+// (s4 probe, compile-only check) -----------------------------------------------------------------------------------------
+__global__ void s4_probe_kernel(int* out)
+{
+    uint32_t a[4] = {threadIdx.x, 1, 2, 3}, b[2] = {5, threadIdx.x};
+    int d[4] = {0, 0, 0, 0};
+    asm volatile("mma.sync.aligned.m16n8k64.row.col.s32.s4.s4.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    out[threadIdx.x] = d[0] + d[1] + d[2] + d[3];
 }
