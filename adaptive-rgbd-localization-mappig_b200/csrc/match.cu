@@ -5,13 +5,14 @@
 //
 // The O(nq * nt * 256) distance matrix is the one compute-bound piece of the path (64 KB of descriptors per pair, 2.6e8 bit
 // operations), so it runs on the 5th-generation tensor cores as an exact integer GEMM: every descriptor bit becomes a signed
-// byte (query: 1 -> +1, 0 -> -1; train: +-64), dot(a, b) over the 256 bytes = 64 * (256 - 2 * hamming(a, b)), computed by
+// byte (1 -> +8, 0 -> -8), dot(a, b) over the 256 bytes = 64 * (256 - 2 * hamming(a, b)), computed by
 // tcgen05.mma kind::i8 (s8 x s8 -> s32) with the 128 x 256 accumulator tile in tensor memory.
-//   * CTA = 128 query rows (one TMEM lane each) x the pair's train rows in chunks of 256; two CTAs share an SM (2 x 256 TMEM
-//     columns, 2 x 98 KB of shared memory), so one CTA's epilogue runs under the other's MMAs.
+//   * CTA = 128 query rows (one TMEM lane each) x the pair's train rows in chunks of 256; 8 warps = 4 lane quarters x 2 column
+//     halves; two CTAs share an SM (2 x 256 TMEM columns, 2 x 100 KB of shared memory), so one CTA's epilogue runs under the
+//     other's MMAs.
 //   * Operands are expanded in the kernel, straight into the no-swizzle K-major canonical layout (8-row x 16-byte core
-//     matrices, LBO 128 B, SBO 2 KB): one PRMT turns 4 descriptor bits into 4 bytes (selector nibbles = the bits, pool bytes =
-//     the two codes).  The order of the 256 dimensions is irrelevant as long as both operands use the same one.
+//     matrices, LBO 128 B, SBO 2 KB), through a 2 KB shared-memory table descriptor byte -> 8 operand bytes (LSU work, the ALU
+//     pipe belongs to the epilogue).  The order of the 256 dimensions is irrelevant as long as both operands use the same one.
 //   * One thread issues the 8 K-steps (UTCIMMA 128 x 256 x 32) and commits to an mbarrier; every thread then reads its own
 //     row with tcgen05.ld (32x32b.x32) and works on two columns per register (VIMNMX.U16x2):
 //       value v = accumulator + 64 * 256 + rc = 128 * (256 - hamming) + rc, rc = 32 - lane in the low 7 bits;
@@ -25,13 +26,15 @@
 
 namespace {
 
-constexpr int UM_THREADS = 128, UM_ROWS = 128, UM_CHUNK = 256;
+constexpr int UM_THREADS = 256, UM_ROWS = 128, UM_CHUNK = 256;
 constexpr uint32_t UM_LBO = 128, UM_SBO = 16 * 128;             // bytes: next 16-byte K chunk / next 8-row group
 constexpr size_t UM_SMEM_A = (size_t)UM_ROWS * 256, UM_SMEM_B = (size_t)UM_CHUNK * 256, UM_SMEM_COL = 4 * (UM_CHUNK / 2) * sizeof(uint32_t);
-constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + 1024;   // + slack to align the operand tiles
+constexpr size_t UM_SMEM_LUT = 256 * 8;
+constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + UM_SMEM_LUT + 1024;   // + slack to align the operand tiles
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr int V_SHIFT = 7;
 constexpr uint32_t V_BIAS = 64 * 256;
+constexpr int OPERAND_MAG = 8;                                  // both operands are +-8: a product of two equal bits is +64
 
 __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t key)
 {
@@ -41,24 +44,17 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 4 descriptor bits (bits s, s+4, s+8, s+12 of `half`) -> 4 signed bytes (+MAG where the bit is 1, -MAG where it is 0)
-template <int MAG>
-__device__ __forceinline__ uint32_t expand4(uint32_t half, int s)
-{
-    constexpr uint32_t pool = ((uint32_t)MAG << 8) | (uint32_t)((256 - MAG) & 0xFF);
-    return __byte_perm(pool, 0u, (half >> s) & 0x1111u);
-}
-
-// one descriptor word -> 32 operand bytes = K chunks 2w and 2w + 1 of `row` in the canonical layout
-template <int MAG>
-__device__ __forceinline__ void expand_word(uint8_t* tile, int row, int w, uint32_t bits, bool valid)
+// one descriptor word -> 32 operand bytes = K chunks 2w and 2w + 1 of `row` in the canonical layout; the table maps a
+// descriptor byte to its 8 operand bytes
+__device__ __forceinline__ void expand_word(uint8_t* tile, const uint8_t* lut, int row, int w, uint32_t bits, bool valid)
 {
     uint8_t* dst = tile + (row >> 3) * UM_SBO + (2 * w) * UM_LBO + (row & 7) * 16;
-    const uint32_t lo = bits & 0xFFFFu, hi = bits >> 16;
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
     if (valid) {
-        a = make_uint4(expand4<MAG>(lo, 0), expand4<MAG>(lo, 1), expand4<MAG>(lo, 2), expand4<MAG>(lo, 3));
-        b = make_uint4(expand4<MAG>(hi, 0), expand4<MAG>(hi, 1), expand4<MAG>(hi, 2), expand4<MAG>(hi, 3));
+        const uint2 e0 = *reinterpret_cast<const uint2*>(lut + ((bits << 3) & 0x7F8u)), e1 = *reinterpret_cast<const uint2*>(lut + ((bits >> 5) & 0x7F8u));
+        const uint2 e2 = *reinterpret_cast<const uint2*>(lut + ((bits >> 13) & 0x7F8u)), e3 = *reinterpret_cast<const uint2*>(lut + ((bits >> 21) & 0x7F8u));
+        a = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        b = make_uint4(e2.x, e2.y, e3.x, e3.y);
     }
     *reinterpret_cast<uint4*>(dst) = a;
     *reinterpret_cast<uint4*>(dst + UM_LBO) = b;
@@ -109,9 +105,11 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
     const uint32_t* Q = reinterpret_cast<const uint32_t*>(ms.qdesc + (long long)qs * ms.qStride);
     const uint32_t* T = reinterpret_cast<const uint32_t*>(ms.tdesc + (long long)ts * ms.tStride);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quarter = warp & 3, colHalf = warp >> 2;         // TMEM lanes 32 * quarter .. + 31, chunk columns 128 * colHalf .. + 127
     uint8_t* sA = umSmemRaw + ((1024u - (smem_u32(umSmemRaw) & 1023u)) & 1023u);
     uint8_t* sB = sA + UM_SMEM_A;
-    uint32_t* sCol = reinterpret_cast<uint32_t*>(sB + UM_SMEM_B);           // [4 warps][UM_CHUNK / 2] packed per-warp column maxima
+    uint32_t* sCol = reinterpret_cast<uint32_t*>(sB + UM_SMEM_B);           // [4 quarters][UM_CHUNK / 2] packed per-warp column maxima
+    uint8_t* sLut = reinterpret_cast<uint8_t*>(sCol) + UM_SMEM_COL;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "n"(UM_CHUNK));
@@ -121,21 +119,29 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    // this thread's query row = TMEM lane tid
-    const int row = qBase + tid;
-    const bool rowValid = row < nq;
     {
-        uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;
-        if (rowValid) { d0 = __ldg(reinterpret_cast<const uint4*>(Q + (long long)row * 8)); d1 = __ldg(reinterpret_cast<const uint4*>(Q + (long long)row * 8) + 1); }
-        const uint32_t w[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        // descriptor byte tid -> 8 operand bytes (bit i -> byte i)
+        uint32_t lo = 0u, hi = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) expand_word<1>(sA, tid, i, w[i], rowValid);
+        for (int i = 0; i < 4; ++i) {
+            lo |= (((tid >> i) & 1) ? (uint32_t)OPERAND_MAG : (uint32_t)(256 - OPERAND_MAG)) << (8 * i);
+            hi |= (((tid >> (4 + i)) & 1) ? (uint32_t)OPERAND_MAG : (uint32_t)(256 - OPERAND_MAG)) << (8 * i);
+        }
+        *reinterpret_cast<uint2*>(sLut + tid * 8) = make_uint2(lo, hi);
     }
+    __syncthreads();
+    for (int i = tid; i < UM_ROWS * 8; i += UM_THREADS) {
+        const int r = i & (UM_ROWS - 1), w = i >> 7;
+        const bool valid = qBase + r < nq;
+        expand_word(sA, sLut, r, w, valid ? __ldg(Q + (long long)(qBase + r) * 8 + w) : 0u, valid);
+    }
+    // this thread's query row = TMEM lane 32 * quarter + lane; two threads (colHalf 0 / 1) share a row
+    const int row = qBase + quarter * 32 + lane;
+    const bool rowValid = row < nq;
     const uint32_t vadd = rowValid ? (V_BIAS + 32u - (uint32_t)lane) * 0x10001u : 0u;   // both halves: + 64 * 256 + rc
     uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
     // instruction descriptor: D s32 (2 @ bit 4), A / B signed 8-bit (1 @ 7, 1 @ 10), both K-major, N >> 3 @ 17, M >> 4 @ 24
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UM_CHUNK >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
-    uint32_t tmem = 0;
     uint32_t phase = 0;
 
     for (int c0 = 0; c0 < nt; c0 += UM_CHUNK) {
@@ -144,14 +150,13 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         for (int i = tid; i < UM_CHUNK * 8; i += UM_THREADS) {
             const int col = i & (UM_CHUNK - 1), w = i >> 8;
             const bool valid = col < cn;
-            const uint32_t bits = valid ? __ldg(T + (long long)(c0 + col) * 8 + w) : 0u;
-            expand_word<64>(sB, col, w, bits, valid);
+            expand_word(sB, sLut, col, w, valid ? __ldg(T + (long long)(c0 + col) * 8 + w) : 0u, valid);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> the tensor core's async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // orders the previous chunk's tcgen05.ld before the MMAs
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem = sTmem;
+        const uint32_t tmem = sTmem;
         if (tid == 0) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -173,67 +178,79 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-        for (int seg = 0; seg < 2; ++seg) {                    // 128 columns = 64 column pairs per segment
-            uint32_t b1 = 0u, b2 = 0u;                         // packed running top-2 of the even / odd column streams
+        // this warp's 32 rows x 128 columns = 64 column pairs: two batches of 32 pairs
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + colHalf * 128;
+        uint32_t b1 = 0u, b2 = 0u;                             // packed running top-2 of the even / odd column streams
 #pragma unroll
-            for (int bt = 0; bt < 2; ++bt) {                   // 64 columns = 32 pairs per batch
-                const int colBase = seg * 128 + bt * 64;
-                uint32_t P[32];
+        for (int bt = 0; bt < 2; ++bt) {
+            const int colBase = colHalf * 128 + bt * 64;
+            uint32_t P[32];                                    // raw pair = acc(2j) + (acc(2j + 1) << 16): multiples of 128 in both halves
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[32];
-                    tmem_ld32(tbase + colBase + hf * 32, v);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) P[hf * 16 + j] = v[2 * j] + (v[2 * j + 1] << 16) + vadd;
-                }
-                if (colBase + 64 > cn) {
-                    // columns past nt (zero operand rows) must lose against every real column: v = 0
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld32(tbase + bt * 64 + hf * 32, v);
+                if (colBase + hf * 32 + 32 > cn) {
+                    // columns past nt (zero operand rows) must lose against every real column: hamming 256
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        P[j] &= (colBase + 2 * j < cn ? 0x0000FFFFu : 0u) | (colBase + 2 * j + 1 < cn ? 0xFFFF0000u : 0u);
+                        if (colBase + hf * 32 + j >= cn) v[j] = 0u - V_BIAS;
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t e = (P[j] & 0xFF80FF80u) | ((uint32_t)(64 - (bt * 32 + j)) * 0x10001u);
-                    b2 = __vmaxu2(b2, __vminu2(b1, e));
-                    b1 = __vmaxu2(b1, e);
-                }
-                if (CROSS) {
-                    bfly_max<16>(P, lane); bfly_max<8>(P, lane); bfly_max<4>(P, lane); bfly_max<2>(P, lane); bfly_max<1>(P, lane);
-                    sCol[warp * (UM_CHUNK / 2) + (colBase >> 1) + lane] = P[0];
-                }
+                for (int j = 0; j < 16; ++j) P[hf * 16 + j] = v[2 * j] + (v[2 * j + 1] << 16);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t e = ((k & 2) ? b2 : b1) >> ((k & 1) * 16) & 0xFFFFu;
-                const uint32_t col = (uint32_t)(c0 + seg * 128) + (64u - (e & 127u)) * 2u + (k & 1);
-                if (e && (int)col < nt) top2_insert(k1, k2, ((256u - (e >> V_SHIFT)) << 16) | col);
+            for (int j = 0; j < 32; ++j) {
+                // + 64 * 256 leaves 128 * (256 - hamming) with clear low 7 bits, which take the code 64 - pair index
+                const uint32_t e = P[j] + ((V_BIAS + 64u - (uint32_t)(bt * 32 + j)) * 0x10001u);
+                b2 = __vmaxu2(b2, __vminu2(b1, e));
+                b1 = __vmaxu2(b1, e);
             }
+            if (CROSS) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) P[j] += vadd;
+                bfly_max<16>(P, lane); bfly_max<8>(P, lane); bfly_max<4>(P, lane); bfly_max<2>(P, lane); bfly_max<1>(P, lane);
+                sCol[quarter * (UM_CHUNK / 2) + (colBase >> 1) + lane] = P[0];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = ((k & 2) ? b2 : b1) >> ((k & 1) * 16) & 0xFFFFu;
+            const uint32_t col = (uint32_t)(c0 + colHalf * 128) + (64u - (e & 127u)) * 2u + (k & 1);
+            if (e && (int)col < nt) top2_insert(k1, k2, ((256u - (e >> V_SHIFT)) << 16) | col);
         }
         if (CROSS) {
             __syncthreads();
-            const uint32_t both[4] = {sCol[tid], sCol[UM_CHUNK / 2 + tid], sCol[2 * (UM_CHUNK / 2) + tid], sCol[3 * (UM_CHUNK / 2) + tid]};
+            if (tid < UM_CHUNK / 2) {
+                const uint32_t both[4] = {sCol[tid], sCol[UM_CHUNK / 2 + tid], sCol[2 * (UM_CHUNK / 2) + tid], sCol[3 * (UM_CHUNK / 2) + tid]};
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t best = 0u;                            // h << 9 | (3 - warp) << 7 | rc: highest h, then lowest row
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t best = 0u;                        // h << 9 | (3 - quarter) << 7 | rc: highest h, then lowest row
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t v = (both[w] >> (hf * 16)) & 0xFFFFu;
-                    if (v & 127u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(3 - w) << V_SHIFT) | (v & 127u));
-                }
-                const int col = 2 * tid + hf;
-                if (best && col < cn) {
-                    const uint32_t r = (uint32_t)qBase + (3u - ((best >> V_SHIFT) & 3u)) * 32u + 32u - (best & 127u);
-                    atomicMin(&rev[(long long)pair * K + c0 + col], (256u - (best >> 9)) * 65536u + r);
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t v = (both[w] >> (hf * 16)) & 0xFFFFu;
+                        if (v & 127u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(3 - w) << V_SHIFT) | (v & 127u));
+                    }
+                    const int col = 2 * tid + hf;
+                    if (best && col < cn) {
+                        const uint32_t r = (uint32_t)qBase + (3u - ((best >> V_SHIFT) & 3u)) * 32u + 32u - (best & 127u);
+                        atomicMin(&rev[(long long)pair * K + c0 + col], (256u - (best >> 9)) * 65536u + r);
+                    }
                 }
             }
         }
     }
-    if (rowValid) *reinterpret_cast<uint2*>(knn + ((long long)pair * K + row) * 2) = make_uint2(k1, k2);
+    // the two threads of a row merge through shared memory (the column staging area is free now)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    uint2* sMerge = reinterpret_cast<uint2*>(sCol);
+    if (colHalf == 1) sMerge[quarter * 32 + lane] = make_uint2(k1, k2);
+    __syncthreads();
+    if (colHalf == 0 && rowValid) {
+        const uint2 o = sMerge[quarter * 32 + lane];
+        top2_insert(k1, k2, o.x);
+        top2_insert(k1, k2, o.y);
+        *reinterpret_cast<uint2*>(knn + ((long long)pair * K + row) * 2) = make_uint2(k1, k2);
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sTmem), "n"(UM_CHUNK));
 }
 
