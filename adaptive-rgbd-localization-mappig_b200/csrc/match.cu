@@ -34,6 +34,7 @@ constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + UM_SMEM_LUT + 1
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr int V_SHIFT = 7;
 constexpr uint32_t V_BIAS = 64 * 256;
+static_assert(UM_THREADS == UM_CHUNK && UM_THREADS == 2 * UM_ROWS, "operand expansion maps one train row / half a query row to a thread");
 constexpr int OPERAND_MAG = 8;                                  // both operands are +-8: a product of two equal bits is +64
 
 __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t key)
@@ -44,20 +45,24 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// one descriptor word -> 32 operand bytes = K chunks 2w and 2w + 1 of `row` in the canonical layout; the table maps a
-// descriptor byte to its 8 operand bytes
-__device__ __forceinline__ void expand_word(uint8_t* tile, const uint8_t* lut, int row, int w, uint32_t bits, bool valid)
+// Half a descriptor (4 words = 128 bits) -> 128 operand bytes = K chunks 8 * half .. 8 * half + 7 of `row` in the canonical
+// layout; the table maps a descriptor byte to its 8 operand bytes.
+__device__ __forceinline__ void expand_half(uint8_t* tile, const uint8_t* lut, int row, int half, uint4 bits, bool valid)
 {
-    uint8_t* dst = tile + (row >> 3) * UM_SBO + (2 * w) * UM_LBO + (row & 7) * 16;
-    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-    if (valid) {
-        const uint2 e0 = *reinterpret_cast<const uint2*>(lut + ((bits << 3) & 0x7F8u)), e1 = *reinterpret_cast<const uint2*>(lut + ((bits >> 5) & 0x7F8u));
-        const uint2 e2 = *reinterpret_cast<const uint2*>(lut + ((bits >> 13) & 0x7F8u)), e3 = *reinterpret_cast<const uint2*>(lut + ((bits >> 21) & 0x7F8u));
-        a = make_uint4(e0.x, e0.y, e1.x, e1.y);
-        b = make_uint4(e2.x, e2.y, e3.x, e3.y);
+    uint8_t* dst = tile + (row >> 3) * UM_SBO + (8 * half) * UM_LBO + (row & 7) * 16;
+    const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        if (valid) {
+            const uint2 e0 = *reinterpret_cast<const uint2*>(lut + ((w[k] << 3) & 0x7F8u)), e1 = *reinterpret_cast<const uint2*>(lut + ((w[k] >> 5) & 0x7F8u));
+            const uint2 e2 = *reinterpret_cast<const uint2*>(lut + ((w[k] >> 13) & 0x7F8u)), e3 = *reinterpret_cast<const uint2*>(lut + ((w[k] >> 21) & 0x7F8u));
+            a = make_uint4(e0.x, e0.y, e1.x, e1.y);
+            b = make_uint4(e2.x, e2.y, e3.x, e3.y);
+        }
+        *reinterpret_cast<uint4*>(dst + (2 * k) * UM_LBO) = a;
+        *reinterpret_cast<uint4*>(dst + (2 * k + 1) * UM_LBO) = b;
     }
-    *reinterpret_cast<uint4*>(dst) = a;
-    *reinterpret_cast<uint4*>(dst + UM_LBO) = b;
 }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr)
@@ -130,10 +135,10 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         *reinterpret_cast<uint2*>(sLut + tid * 8) = make_uint2(lo, hi);
     }
     __syncthreads();
-    for (int i = tid; i < UM_ROWS * 8; i += UM_THREADS) {
-        const int r = i & (UM_ROWS - 1), w = i >> 7;
+    {
+        const int r = tid & (UM_ROWS - 1), half = tid >> 7;
         const bool valid = qBase + r < nq;
-        expand_word(sA, sLut, r, w, valid ? __ldg(Q + (long long)(qBase + r) * 8 + w) : 0u, valid);
+        expand_half(sA, sLut, r, half, valid ? __ldg(reinterpret_cast<const uint4*>(Q + (long long)(qBase + r) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
     }
     // this thread's query row = TMEM lane 32 * quarter + lane; two threads (colHalf 0 / 1) share a row
     const int row = qBase + quarter * 32 + lane;
@@ -147,10 +152,10 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
     for (int c0 = 0; c0 < nt; c0 += UM_CHUNK) {
         const int cn = min(UM_CHUNK, nt - c0);
         // the previous chunk's MMAs are complete (every thread waited on the barrier), so the train tile can be overwritten
-        for (int i = tid; i < UM_CHUNK * 8; i += UM_THREADS) {
-            const int col = i & (UM_CHUNK - 1), w = i >> 8;
-            const bool valid = col < cn;
-            expand_word(sB, sLut, col, w, valid ? __ldg(T + (long long)(c0 + col) * 8 + w) : 0u, valid);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const bool valid = tid < cn;                       // UM_THREADS == UM_CHUNK: one train row per thread
+            expand_half(sB, sLut, tid, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + tid) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> the tensor core's async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // orders the previous chunk's tcgen05.ld before the MMAs
