@@ -11,8 +11,8 @@
 //     halves; two CTAs share an SM (2 x 256 TMEM columns, 2 x 100 KB of shared memory), so one CTA's epilogue runs under the
 //     other's MMAs.
 //   * Operands are expanded in the kernel, straight into the no-swizzle K-major canonical layout (8-row x 16-byte core
-//     matrices, LBO 128 B, SBO 2 KB), through a 2 KB shared-memory table descriptor byte -> 8 operand bytes (LSU work, the ALU
-//     pipe belongs to the epilogue).  The order of the 256 dimensions is irrelevant as long as both operands use the same one.
+//     matrices, LBO 128 B, SBO 2 KB): one PRMT turns 4 descriptor bits into 4 bytes.  The order of the 256 dimensions is
+//     irrelevant as long as both operands use the same one.
 //   * One thread issues the 8 K-steps (UTCIMMA 128 x 256 x 32) and commits to an mbarrier; every thread then reads its own
 //     row with tcgen05.ld (32x32b.x32) and works on two columns per register (VIMNMX.U16x2):
 //       value v = accumulator + 64 * 256 + rc = 128 * (256 - hamming) + rc, rc = 32 - lane in the low 7 bits;
@@ -29,8 +29,7 @@ namespace {
 constexpr int UM_THREADS = 256, UM_ROWS = 128, UM_CHUNK = 256;
 constexpr uint32_t UM_LBO = 128, UM_SBO = 16 * 128;             // bytes: next 16-byte K chunk / next 8-row group
 constexpr size_t UM_SMEM_A = (size_t)UM_ROWS * 256, UM_SMEM_B = (size_t)UM_CHUNK * 256, UM_SMEM_COL = 4 * (UM_CHUNK / 2) * sizeof(uint32_t);
-constexpr size_t UM_SMEM_LUT = 256 * 8;
-constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + UM_SMEM_LUT + 1024;   // + slack to align the operand tiles
+constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + 1024;   // + slack to align the operand tiles
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr int V_SHIFT = 7;
 constexpr uint32_t V_BIAS = 64 * 256;
@@ -45,9 +44,18 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 4 descriptor bits (bits s, s+4, s+8, s+12 of `half`) -> 4 signed operand bytes: one PRMT whose selector nibbles are the bits
+// and whose pool bytes are the two codes.  (A shared-memory table byte -> 8 bytes costs fewer instructions but its random
+// 8-byte reads take ~6.5 wavefronts each, and the L1 / shared-memory data pipe is what this kernel saturates first.)
+__device__ __forceinline__ uint32_t expand4(uint32_t half, int s)
+{
+    constexpr uint32_t pool = ((uint32_t)OPERAND_MAG << 8) | (uint32_t)(256 - OPERAND_MAG);
+    return __byte_perm(pool, 0u, (half >> s) & 0x1111u);
+}
+
 // Half a descriptor (4 words = 128 bits) -> 128 operand bytes = K chunks 8 * half .. 8 * half + 7 of `row` in the canonical
-// layout; the table maps a descriptor byte to its 8 operand bytes.
-__device__ __forceinline__ void expand_half(uint8_t* tile, const uint8_t* lut, int row, int half, uint4 bits, bool valid)
+// layout.  The order of the bits within a word is irrelevant as long as both operands use the same one.
+__device__ __forceinline__ void expand_half(uint8_t* tile, int row, int half, uint4 bits, bool valid)
 {
     uint8_t* dst = tile + (row >> 3) * UM_SBO + (8 * half) * UM_LBO + (row & 7) * 16;
     const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
@@ -55,10 +63,9 @@ __device__ __forceinline__ void expand_half(uint8_t* tile, const uint8_t* lut, i
     for (int k = 0; k < 4; ++k) {
         uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
         if (valid) {
-            const uint2 e0 = *reinterpret_cast<const uint2*>(lut + ((w[k] << 3) & 0x7F8u)), e1 = *reinterpret_cast<const uint2*>(lut + ((w[k] >> 5) & 0x7F8u));
-            const uint2 e2 = *reinterpret_cast<const uint2*>(lut + ((w[k] >> 13) & 0x7F8u)), e3 = *reinterpret_cast<const uint2*>(lut + ((w[k] >> 21) & 0x7F8u));
-            a = make_uint4(e0.x, e0.y, e1.x, e1.y);
-            b = make_uint4(e2.x, e2.y, e3.x, e3.y);
+            const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+            a = make_uint4(expand4(lo, 0), expand4(lo, 1), expand4(lo, 2), expand4(lo, 3));
+            b = make_uint4(expand4(hi, 0), expand4(hi, 1), expand4(hi, 2), expand4(hi, 3));
         }
         *reinterpret_cast<uint4*>(dst + (2 * k) * UM_LBO) = a;
         *reinterpret_cast<uint4*>(dst + (2 * k + 1) * UM_LBO) = b;
@@ -114,7 +121,6 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
     uint8_t* sA = umSmemRaw + ((1024u - (smem_u32(umSmemRaw) & 1023u)) & 1023u);
     uint8_t* sB = sA + UM_SMEM_A;
     uint32_t* sCol = reinterpret_cast<uint32_t*>(sB + UM_SMEM_B);           // [4 quarters][UM_CHUNK / 2] packed per-warp column maxima
-    uint8_t* sLut = reinterpret_cast<uint8_t*>(sCol) + UM_SMEM_COL;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTmem)), "n"(UM_CHUNK));
@@ -125,20 +131,9 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     {
-        // descriptor byte tid -> 8 operand bytes (bit i -> byte i)
-        uint32_t lo = 0u, hi = 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            lo |= (((tid >> i) & 1) ? (uint32_t)OPERAND_MAG : (uint32_t)(256 - OPERAND_MAG)) << (8 * i);
-            hi |= (((tid >> (4 + i)) & 1) ? (uint32_t)OPERAND_MAG : (uint32_t)(256 - OPERAND_MAG)) << (8 * i);
-        }
-        *reinterpret_cast<uint2*>(sLut + tid * 8) = make_uint2(lo, hi);
-    }
-    __syncthreads();
-    {
         const int r = tid & (UM_ROWS - 1), half = tid >> 7;
         const bool valid = qBase + r < nq;
-        expand_half(sA, sLut, r, half, valid ? __ldg(reinterpret_cast<const uint4*>(Q + (long long)(qBase + r) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
+        expand_half(sA, r, half, valid ? __ldg(reinterpret_cast<const uint4*>(Q + (long long)(qBase + r) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
     }
     // this thread's query row = TMEM lane 32 * quarter + lane; two threads (colHalf 0 / 1) share a row
     const int row = qBase + quarter * 32 + lane;
@@ -155,7 +150,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const bool valid = tid < cn;                       // UM_THREADS == UM_CHUNK: one train row per thread
-            expand_half(sB, sLut, tid, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + tid) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
+            expand_half(sB, tid, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + tid) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> the tensor core's async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // orders the previous chunk's tcgen05.ld before the MMAs
