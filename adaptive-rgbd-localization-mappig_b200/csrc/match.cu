@@ -44,13 +44,17 @@ __device__ __forceinline__ void top2_insert(uint32_t& m1, uint32_t& m2, uint32_t
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 4 descriptor bits (bits s, s+4, s+8, s+12 of `half`) -> 4 signed operand bytes: one PRMT whose selector nibbles are the bits
-// and whose pool bytes are the two codes.  (A shared-memory table byte -> 8 bytes costs fewer instructions but its random
-// 8-byte reads take ~6.5 wavefronts each, and the L1 / shared-memory data pipe is what this kernel saturates first.)
-__device__ __forceinline__ uint32_t expand4(uint32_t half, int s)
+// 16 descriptor bits -> 16 signed operand bytes with PRMT: the selector nibbles are the bits themselves.  A nibble may carry its
+// bit at position 0, 1 or 2 (values 0 / 1, 0 / 2, 0 / 4 all index a +MAG byte of the pool, 0 the -MAG byte), so three of the four
+// bit phases need only a mask; the fourth (bit 3 would select PRMT's sign-replicate mode) comes from the word shifted by one.
+// (A shared-memory table byte -> 8 bytes costs fewer instructions, but its random 8-byte reads take ~6.5 wavefronts each and
+// the L1 / shared-memory data pipe is what this kernel saturates first.)
+__device__ __forceinline__ uint4 expand16(uint32_t x, uint32_t xShifted1)
 {
-    constexpr uint32_t pool = ((uint32_t)OPERAND_MAG << 8) | (uint32_t)(256 - OPERAND_MAG);
-    return __byte_perm(pool, 0u, (half >> s) & 0x1111u);
+    constexpr uint32_t P = (uint32_t)OPERAND_MAG, N = (uint32_t)(256 - OPERAND_MAG);
+    constexpr uint32_t poolLo = N | (P << 8) | (P << 16), poolHi = P;       // bytes 0..7: -M +M +M . +M . . .
+    return make_uint4(__byte_perm(poolLo, poolHi, x & 0x1111u), __byte_perm(poolLo, poolHi, x & 0x2222u), __byte_perm(poolLo, poolHi, x & 0x4444u),
+                      __byte_perm(poolLo, poolHi, xShifted1 & 0x4444u));
 }
 
 // Half a descriptor (4 words = 128 bits) -> 128 operand bytes = K chunks 8 * half .. 8 * half + 7 of `row` in the canonical
@@ -63,9 +67,8 @@ __device__ __forceinline__ void expand_half(uint8_t* tile, int row, int half, ui
     for (int k = 0; k < 4; ++k) {
         uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
         if (valid) {
-            const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
-            a = make_uint4(expand4(lo, 0), expand4(lo, 1), expand4(lo, 2), expand4(lo, 3));
-            b = make_uint4(expand4(hi, 0), expand4(hi, 1), expand4(hi, 2), expand4(hi, 3));
+            a = expand16(w[k], w[k] >> 1);
+            b = expand16(w[k] >> 16, w[k] >> 17);
         }
         *reinterpret_cast<uint4*>(dst + (2 * k) * UM_LBO) = a;
         *reinterpret_cast<uint4*>(dst + (2 * k + 1) * UM_LBO) = b;
@@ -100,12 +103,32 @@ __device__ __forceinline__ void bfly_max(uint32_t (&P)[32], int lane)
     }
 }
 
+// Cross-check: fold one chunk's per-warp column maxima over the 4 lane quarters; thread `pairIdx` owns two columns.
+__device__ __forceinline__ void fold_columns(const uint32_t* sCol, uint32_t* revChunk, int cn, int qBase, int pairIdx)
+{
+    const uint32_t both[4] = {sCol[pairIdx], sCol[UM_CHUNK / 2 + pairIdx], sCol[2 * (UM_CHUNK / 2) + pairIdx], sCol[3 * (UM_CHUNK / 2) + pairIdx]};
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        uint32_t best = 0u;                                    // h << 9 | (3 - quarter) << 7 | rc: highest h, then lowest row
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t v = (both[w] >> (hf * 16)) & 0xFFFFu;
+            if (v & 127u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(3 - w) << V_SHIFT) | (v & 127u));
+        }
+        const int col = 2 * pairIdx + hf;
+        if (best && col < cn) {
+            const uint32_t r = (uint32_t)qBase + (3u - ((best >> V_SHIFT) & 3u)) * 32u + 32u - (best & 127u);
+            atomicMin(&revChunk[col], (256u - (best >> 9)) * 65536u + r);
+        }
+    }
+}
+
 template <bool CROSS>
 __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
 {
     extern __shared__ uint8_t umSmemRaw[];
     __shared__ uint32_t sTmem;
-    __shared__ __align__(8) uint64_t sBar;
+    __shared__ __align__(8) uint64_t sBar[2];
     uint32_t* __restrict__ knn = ms.knn;
     uint32_t* __restrict__ rev = ms.rev;
     const int pair = ms.pair0 + blockIdx.y;
@@ -127,7 +150,8 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     {
@@ -141,37 +165,45 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
     const uint32_t vadd = rowValid ? (V_BIAS + 32u - (uint32_t)lane) * 0x10001u : 0u;   // both halves: + 64 * 256 + rc
     uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
     // instruction descriptor: D s32 (2 @ bit 4), A / B signed 8-bit (1 @ 7, 1 @ 10), both K-major, N >> 3 @ 17, M >> 4 @ 24
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UM_CHUNK >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+    const uint32_t idescHalf = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((UM_CHUNK / 2) >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
     uint32_t phase = 0;
 
+    // Per chunk the train tile is expanded and multiplied in two halves of 128 rows: the MMAs of half 0 run under the expansion of
+    // half 1, and the warps of column half 0 start their epilogue while half 1 is still in the tensor core.
     for (int c0 = 0; c0 < nt; c0 += UM_CHUNK) {
         const int cn = min(UM_CHUNK, nt - c0);
-        // the previous chunk's MMAs are complete (every thread waited on the barrier), so the train tile can be overwritten
+        uint32_t tmem = 0;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const bool valid = tid < cn;                       // UM_THREADS == UM_CHUNK: one train row per thread
-            expand_half(sB, tid, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + tid) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> the tensor core's async proxy
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // orders the previous chunk's tcgen05.ld before the MMAs
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem = sTmem;
-        if (tid == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t da = umma_desc(smem_u32(sA) + ks * 2 * UM_LBO), db = umma_desc(smem_u32(sB) + ks * 2 * UM_LBO);
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+        for (int part = 0; part < 2; ++part) {
+            // every thread that gets here has seen the MMAs that read this half of the tile complete (see the syncs below)
+            {
+                const int col = part * (UM_CHUNK / 2) + (tid & (UM_CHUNK / 2 - 1)), half = tid >> 7;
+                const bool valid = col < cn;
+                expand_half(sB, col, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + col) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sBar)) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> the tensor core's async proxy
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // orders the previous chunk's tcgen05.ld before the MMAs
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tmem = sTmem;
+            if (tid == 0) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t da = umma_desc(smem_u32(sA) + ks * 2 * UM_LBO);
+                    const uint64_t db = umma_desc(smem_u32(sB) + part * (UM_CHUNK / 2 / 8) * UM_SBO + ks * 2 * UM_LBO);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem + part * (UM_CHUNK / 2)), "l"(da), "l"(db), "r"(idescHalf), "r"((uint32_t)(ks > 0)) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sBar[part])) : "memory");
+            }
+            if (CROSS && part == 0 && c0 > 0 && tid < UM_CHUNK / 2) fold_columns(sCol, rev + (long long)pair * K + (c0 - UM_CHUNK), UM_CHUNK, qBase, tid);
         }
         {
             uint32_t done = 0, spins = 0;
             while (!done) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(smem_u32(&sBar)), "r"(phase) : "memory");
+                             : "=r"(done) : "r"(smem_u32(&sBar[colHalf])), "r"(phase) : "memory");
                 if (!done && ++spins > (1u << 26)) __trap();                   // a lost commit must fail loudly, not hang the device
             }
             phase ^= 1u;
@@ -218,30 +250,15 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
             const uint32_t col = (uint32_t)(c0 + colHalf * 128) + (64u - (e & 127u)) * 2u + (k & 1);
             if (e && (int)col < nt) top2_insert(k1, k2, ((256u - (e >> V_SHIFT)) << 16) | col);
         }
-        if (CROSS) {
-            __syncthreads();
-            if (tid < UM_CHUNK / 2) {
-                const uint32_t both[4] = {sCol[tid], sCol[UM_CHUNK / 2 + tid], sCol[2 * (UM_CHUNK / 2) + tid], sCol[3 * (UM_CHUNK / 2) + tid]};
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t best = 0u;                        // h << 9 | (3 - quarter) << 7 | rc: highest h, then lowest row
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const uint32_t v = (both[w] >> (hf * 16)) & 0xFFFFu;
-                        if (v & 127u) best = max(best, ((v >> V_SHIFT) << 9) | ((uint32_t)(3 - w) << V_SHIFT) | (v & 127u));
-                    }
-                    const int col = 2 * tid + hf;
-                    if (best && col < cn) {
-                        const uint32_t r = (uint32_t)qBase + (3u - ((best >> V_SHIFT) & 3u)) * 32u + 32u - (best & 127u);
-                        atomicMin(&rev[(long long)pair * K + c0 + col], (256u - (best >> 9)) * 65536u + r);
-                    }
-                }
-            }
-        }
     }
-    // the two threads of a row merge through shared memory (the column staging area is free now)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CROSS && nt > 0 && tid < UM_CHUNK / 2) {
+        const int cLast = ((nt - 1) / UM_CHUNK) * UM_CHUNK;
+        fold_columns(sCol, rev + (long long)pair * K + cLast, nt - cLast, qBase, tid);
+    }
+    __syncthreads();
+    // the two threads of a row merge through shared memory (the column staging area is free now)
     uint2* sMerge = reinterpret_cast<uint2*>(sCol);
     if (colHalf == 1) sMerge[quarter * 32 + lane] = make_uint2(k1, k2);
     __syncthreads();
