@@ -295,6 +295,28 @@ class Context:
                   "distinctive_descriptors")
         return best[:n], med[:n]
 
+    def projection_match(self, lm_desc, proj_x, proj_y, lm_flags, slot=-1, kp_x=None, kp_y=None, kp_octave=None, desc=None, feat_taken=None,
+                         radius=8.0, nn_ratio=0.8, th_high=100):
+        """Matcher::ProjectionMatch (Features/matcher.cpp:90-143): (feature matched to each landmark or -1, number of matches).
+        slot >= 0 uses that frame slot's keypoints / descriptors on the device; otherwise pass kp_x, kp_y, kp_octave, desc."""
+        lm_desc = np.ascontiguousarray(lm_desc, np.uint8).reshape(-1, 32)
+        proj_x = np.ascontiguousarray(proj_x, np.float32); proj_y = np.ascontiguousarray(proj_y, np.float32)
+        lm_flags = np.ascontiguousarray(lm_flags, np.uint8)
+        L = len(lm_flags)
+        n = 0
+        if slot < 0:
+            kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32)
+            kp_octave = np.ascontiguousarray(kp_octave, np.int32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+            n = len(kp_x)
+        taken = None if feat_taken is None else np.ascontiguousarray(feat_taken, np.uint8)
+        best = np.full(max(L, 1), -1, np.int32); nm = C.c_int32(0)
+        opt = lambda a: _p(a) if a is not None and len(a) else None
+        self._chk(lib().orbf_projection_match(self._h, int(slot), opt(kp_x) if slot < 0 else None, opt(kp_y) if slot < 0 else None,
+                                              opt(kp_octave) if slot < 0 else None, opt(desc) if slot < 0 else None, n, opt(lm_desc), opt(proj_x), opt(proj_y),
+                                              opt(lm_flags), L, opt(taken), C.c_float(radius), C.c_float(nn_ratio), int(th_high), _p(best), C.byref(nm)),
+                  "projection_match")
+        return best[:L], nm.value
+
     def match_pairs(self, pairs, ratio, cross_check=False):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         self._chk(lib().orbf_match_pairs(self._h, _p(pairs), len(pairs), C.c_float(ratio), int(cross_check)), "match_pairs")

@@ -514,6 +514,64 @@ extern "C" int orbf_distinctive_descriptors(orbf_context* c, const uint8_t* desc
     return ORBF_OK;
 }
 
+extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
+    int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
+    const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches)
+{
+    CTX_ENTER(c);
+    if (!best_idx || !n_matches || n_landmarks < 0) return ORBF_ERR_ARG;
+    if (n_landmarks > 0 && (!lm_desc || !proj_x || !proj_y || !lm_flags)) return ORBF_ERR_ARG;
+    if (slot >= c->B) return ORBF_ERR_ARG;
+    if (slot < 0 && (n_feat < 0 || n_feat > 65535 || (n_feat > 0 && (!kp_x || !kp_y || !kp_octave || !desc)))) return ORBF_ERR_ARG;
+    *n_matches = 0;
+    if (n_landmarks == 0) return ORBF_OK;
+    int nFeat = n_feat;
+    if (slot >= 0) {
+        if (cudaMemcpyAsync(&nFeat, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return orbf_cuda_fail(c, cudaGetLastError(), "projection_match: frame count", __FILE__, __LINE__);
+    }
+    if (feat_taken == nullptr && nFeat == 0) { for (int i = 0; i < n_landmarks; ++i) best_idx[i] = -1; return ORBF_OK; }
+    const size_t L = (size_t)n_landmarks, F = (size_t)std::max(nFeat, 1);
+    // one allocation: landmark inputs | frame inputs (host route) | scratch | outputs
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t oLmDesc = take(L * 32), oPx = take(L * 4), oPy = take(L * 4), oFlags = take(L), oTakenIn = take(F), oTaken = take(F);
+    const size_t oKx = take(F * 4), oKy = take(F * 4), oOct = take(F * 4), oDesc = take(F * 32);
+    const size_t oCand = take(L * F * 4), oCnt = take(L * 4), oBest = take((L + 1) * 4);
+    uint8_t* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, off);
+    if (e != cudaSuccess) return orbf_cuda_fail(c, e, "projection_match: scratch", __FILE__, __LINE__);
+#define PJ_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaFree(d); return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } } while (0)
+    PJ_CUDA(cudaMemcpyAsync(d + oLmDesc, lm_desc, L * 32, cudaMemcpyHostToDevice, c->stream));
+    PJ_CUDA(cudaMemcpyAsync(d + oPx, proj_x, L * 4, cudaMemcpyHostToDevice, c->stream));
+    PJ_CUDA(cudaMemcpyAsync(d + oPy, proj_y, L * 4, cudaMemcpyHostToDevice, c->stream));
+    PJ_CUDA(cudaMemcpyAsync(d + oFlags, lm_flags, L, cudaMemcpyHostToDevice, c->stream));
+    if (feat_taken && nFeat > 0) PJ_CUDA(cudaMemcpyAsync(d + oTakenIn, feat_taken, (size_t)nFeat, cudaMemcpyHostToDevice, c->stream));
+    const float *dKx, *dKy; const int* dOct; const uint8_t* dDesc;
+    if (slot >= 0) {
+        dKx = c->d_kpx + (size_t)slot * c->K; dKy = c->d_kpy + (size_t)slot * c->K; dOct = c->d_kpoct + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
+    } else {
+        if (nFeat > 0) {
+            PJ_CUDA(cudaMemcpyAsync(d + oKx, kp_x, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
+            PJ_CUDA(cudaMemcpyAsync(d + oKy, kp_y, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
+            PJ_CUDA(cudaMemcpyAsync(d + oOct, kp_octave, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
+            PJ_CUDA(cudaMemcpyAsync(d + oDesc, desc, (size_t)nFeat * 32, cudaMemcpyHostToDevice, c->stream));
+        }
+        dKx = reinterpret_cast<const float*>(d + oKx); dKy = reinterpret_cast<const float*>(d + oKy); dOct = reinterpret_cast<const int*>(d + oOct); dDesc = d + oDesc;
+    }
+    int* dBest = reinterpret_cast<int*>(d + oBest);
+    const int rc = orbf_launch_projection_match(c, dKx, dKy, dOct, dDesc, nFeat, d + oLmDesc, reinterpret_cast<const float*>(d + oPx), reinterpret_cast<const float*>(d + oPy),
+        d + oFlags, n_landmarks, (feat_taken && nFeat > 0) ? d + oTakenIn : nullptr, radius, nn_ratio, th_high, reinterpret_cast<uint32_t*>(d + oCand),
+        reinterpret_cast<int*>(d + oCnt), d + oTaken, dBest, dBest + L);
+    if (rc != ORBF_OK) { cudaFree(d); return rc; }
+    PJ_CUDA(cudaMemcpyAsync(best_idx, dBest, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PJ_CUDA(cudaMemcpyAsync(n_matches, dBest + L, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PJ_CUDA(cudaStreamSynchronize(c->stream));
+#undef PJ_CUDA
+    cudaFree(d);
+    return ORBF_OK;
+}
+
 extern "C" int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes, int32_t* dist)
 {
     if (!a || !b || !dist || nbytes < 0) return ORBF_ERR_ARG;

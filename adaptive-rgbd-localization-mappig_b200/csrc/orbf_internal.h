@@ -197,6 +197,9 @@ struct MatchSet {
 };
 int orbf_launch_knn2(orbf_context* ctx, const MatchSet& ms, int npairs, bool cross);
 int orbf_launch_distinctive(orbf_context* ctx, const uint8_t* d_desc, const int* d_offsets, int nLandmarks, int* d_best, int* d_median);
+int orbf_launch_projection_match(orbf_context* ctx, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat,
+    const uint8_t* d_lmDesc, const float* d_projX, const float* d_projY, const uint8_t* d_lmFlags, int nLm, const uint8_t* d_featTaken, float radius, float nnRatio,
+    int thHigh, uint32_t* d_cand, int* d_candCount, uint8_t* d_taken, int* d_bestIdx, int* d_nMatches);
 int orbf_launch_match_select(orbf_context* ctx, const MatchSet& ms, int npairs, float ratio, bool cross);
 // RANSAC
 struct RansacSet {

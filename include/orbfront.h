@@ -16,6 +16,7 @@
  *   orbf_knn2 / orbf_knn_match        cv::BFMatcher::knnMatch(k=2) + ratio test in Matcher::KnnMatch   Features/matcher.cpp:55-66 (23-35)
  *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
  *   orbf_distinctive_descriptors      Landmark::ComputeDistinctiveDescriptors     Core/landmark.cpp:219-273
+ *   orbf_projection_match             Matcher::ProjectionMatch + Frame::GetFeaturesInArea   Features/matcher.cpp:90-143, Core/frame.cpp:258-274
  *   orbf_match_pairs                  Tracking::TrackFrame's matcher call, batched  System/tracking.cpp:197-199
  *   orbf_track_sequence*              Tracking::Track's per-frame loop (extract, match with the last frame, RANSAC)
  *                                     over a whole sequence, pipelined            System/tracking.cpp:38-46,193-208
@@ -177,6 +178,16 @@ int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes,
  * Hamming distance to the others (first wins ties, -1 without observations); median[l] optional (may be NULL).          */
 int orbf_distinctive_descriptors(orbf_context* ctx, const uint8_t* desc, const int32_t* offsets, int32_t n_landmarks, int32_t* best,
     int32_t* median);
+/* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) for one frame: landmarks projected into the frame are matched, in order,
+ * to the features inside the square window |dx| < radius && |dy| < radius; best <= th_high, and rejected when best and second best
+ * share an octave and best > nn_ratio * second; a feature given to a landmark with Observations() > 0 is skipped by later landmarks.
+ * Frame side: slot >= 0 takes keypoints / descriptors of that frame slot (output of orbf_extract_batch*; kp_* / desc ignored),
+ * slot < 0 takes n_feat host rows kp_x / kp_y / kp_octave / desc.
+ * lm_flags[i]: bit 0 = candidate (mbTrackInView && !isBad()), bit 1 = Observations() > 0.  feat_taken[j] (may be NULL) = feature j
+ * already holds a landmark with Observations() > 0.  best_idx[i] = feature matched to landmark i or -1.                     */
+int orbf_projection_match(orbf_context* ctx, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
+    int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
+    const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches);
 /* Device-resident: match frame slot pairs (query_slot, train_slot); results live in pair slots 0..npairs-1. */
 int orbf_match_pairs(orbf_context* ctx, const int32_t* pairs /* 2*npairs */, int32_t npairs, float ratio,
     int32_t cross_check);

@@ -318,6 +318,38 @@ public:
         return KnnMatch(pF1, pF2, vMatches12, [](const DMatch&) { return true; }, crossCheck);
     }
 
+    // One projected landmark as Matcher::ProjectionMatch reads it (matcher.cpp:94-103): the Landmark* graph stays with the caller.
+    struct ProjectedLandmark {
+        const uint8_t* descriptor;          // Landmark::GetDescriptor(), 32 bytes
+        float projX, projY;                 // mTrackProjX / mTrackProjY
+        bool inView;                        // mbTrackInView && !isBad()
+        bool observed;                      // Observations() > 0
+    };
+    // Matcher::ProjectionMatch (matcher.cpp:90-143).  featureTaken[j] = pFrame->GetLandmark(j) exists and has Observations() > 0.
+    // bestIdx[i] = feature the reference would pass to pFrame->AddLandmark(vpLandmarks[i], .) or -1; returns nmatches.
+    size_t ProjectionMatch(Frame& frame, const std::vector<ProjectedLandmark>& landmarks, const std::vector<uint8_t>& featureTaken, float th,
+        std::vector<int>& bestIdx)
+    {
+        const int L = (int)landmarks.size(), N = (int)frame.mvKeys.size();
+        bestIdx.assign((size_t)L, -1);
+        if (L == 0) return 0;
+        std::vector<uint8_t> d((size_t)L * 32), flags((size_t)L);
+        std::vector<float> px((size_t)L), py((size_t)L), kx((size_t)N), ky((size_t)N);
+        std::vector<int32_t> oct((size_t)N);
+        for (int i = 0; i < L; ++i) {
+            std::copy(landmarks[i].descriptor, landmarks[i].descriptor + 32, d.begin() + (size_t)i * 32);
+            px[i] = landmarks[i].projX; py[i] = landmarks[i].projY;
+            flags[i] = (uint8_t)((landmarks[i].inView ? 1 : 0) | (landmarks[i].observed ? 2 : 0));
+        }
+        for (int j = 0; j < N; ++j) { kx[j] = frame.mvKeys[j].pt.x; ky[j] = frame.mvKeys[j].pt.y; oct[j] = frame.mvKeys[j].octave; }
+        int n = 0;
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        check(orbf_projection_match(Runtime::Current(), -1, kx.data(), ky.data(), oct.data(), frame.mDescriptors.data, N, d.data(), px.data(), py.data(),
+                  flags.data(), L, featureTaken.empty() ? nullptr : featureTaken.data(), th, mfNNratio, (int)TH_HIGH, bestIdx.data(), &n),
+            "orbf_projection_match");
+        return (size_t)n;
+    }
+
 private:
     float mfNNratio; double TH_LOW, TH_HIGH;
 };

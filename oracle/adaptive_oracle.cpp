@@ -126,3 +126,51 @@ int orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_l
     }
     return ORC_OK;
 }
+
+// ---- Matcher::ProjectionMatch (Features/matcher.cpp:90-143), SURVEY.md §8f rank 1 ---------------------------------------------
+// Landmarks already projected into the frame are matched IN ORDER: Frame::GetFeaturesInArea (Core/frame.cpp:258-274) is a linear
+// scan in feature order over the square window |dx| < r && |dy| < r (float); a feature whose slot holds a landmark with
+// Observations() > 0 is skipped; best / second best by strict '<' on the double-valued Hamming distance; accepted when
+// best <= TH_HIGH unless both come from the same octave and best > ratio * second (float ratio promoted to double);
+// Frame::AddLandmark then puts the landmark into the slot, which later landmarks see.
+//   lm_flags[i] bit 0: mbTrackInView && !isBad();  bit 1: Observations() > 0.
+//   feat_taken[j] (may be NULL): slot j initially holds a landmark with Observations() > 0.
+int orc_projection_match(const float* kp_x, const float* kp_y, const int* kp_octave, const uint8_t* desc, int n_feat, const uint8_t* lm_desc,
+    const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int n_landmarks, const uint8_t* feat_taken, float radius, float nn_ratio,
+    double th_high, int* best_idx, int* n_matches)
+{
+    if (n_feat < 0 || n_landmarks < 0 || !best_idx || !n_matches) return ORC_ERR_ARG;
+    if (n_landmarks > 0 && (!lm_desc || !proj_x || !proj_y || !lm_flags)) return ORC_ERR_ARG;
+    if (n_feat > 0 && (!kp_x || !kp_y || !kp_octave || !desc)) return ORC_ERR_ARG;
+    std::vector<uint8_t> taken(std::max(n_feat, 1), 0);
+    if (feat_taken) std::copy(feat_taken, feat_taken + n_feat, taken.begin());
+    int nm = 0;
+    for (int i = 0; i < n_landmarks; ++i) {
+        best_idx[i] = -1;
+        if (!(lm_flags[i] & 1)) continue;
+        double bestDist1 = 1.7976931348623157e308, bestDist2 = 1.7976931348623157e308;
+        int bestLevel = -1, bestLevel2 = -1, bestIdx = -1;
+        bool any = false;
+        for (int j = 0; j < n_feat; ++j) {
+            const float distx = kp_x[j] - proj_x[i], disty = kp_y[j] - proj_y[i];
+            if (!(std::fabs(distx) < radius && std::fabs(disty) < radius)) continue;
+            any = true;
+            if (taken[j]) continue;
+            const double dist = (double)orc_hamming(lm_desc + (size_t)i * 32, desc + (size_t)j * 32);
+            if (dist < bestDist1) {
+                bestDist2 = bestDist1; bestDist1 = dist; bestLevel2 = bestLevel; bestLevel = kp_octave[j]; bestIdx = j;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kp_octave[j]; bestDist2 = dist;
+            }
+        }
+        if (!any) continue;
+        if (bestDist1 <= th_high) {
+            if (bestLevel == bestLevel2 && bestDist1 > nn_ratio * bestDist2) continue;
+            best_idx[i] = bestIdx;
+            if (lm_flags[i] & 2) taken[bestIdx] = 1;
+            ++nm;
+        }
+    }
+    *n_matches = nm;
+    return ORC_OK;
+}

@@ -269,6 +269,23 @@ def adaptive_detect(img, thresh, retain_best=0, cfg=None):
     return out[:n.value].copy(), found, used
 
 
+def projection_match(kp_x, kp_y, kp_octave, desc, lm_desc, proj_x, proj_y, lm_flags, feat_taken=None, radius=8.0, nn_ratio=0.8, th_high=100.0):
+    """Matcher::ProjectionMatch (Features/matcher.cpp:90-143): (best feature per landmark or -1, number of matches)."""
+    kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32)
+    kp_octave = np.ascontiguousarray(kp_octave, np.int32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    lm_desc = np.ascontiguousarray(lm_desc, np.uint8).reshape(-1, 32)
+    proj_x = np.ascontiguousarray(proj_x, np.float32); proj_y = np.ascontiguousarray(proj_y, np.float32)
+    lm_flags = np.ascontiguousarray(lm_flags, np.uint8)
+    taken = None if feat_taken is None else np.ascontiguousarray(feat_taken, np.uint8)
+    n, L = len(kp_x), len(lm_flags)
+    best = np.full(max(L, 1), -1, np.int32); nm = C.c_int(0)
+    _chk(lib().orc_projection_match(_p(kp_x) if n else None, _p(kp_y) if n else None, _p(kp_octave) if n else None, _p(desc) if n else None, n,
+                                    _p(lm_desc) if L else None, _p(proj_x) if L else None, _p(proj_y) if L else None, _p(lm_flags) if L else None, L,
+                                    _p(taken) if taken is not None else None, C.c_float(radius), C.c_float(nn_ratio), C.c_double(th_high), _p(best),
+                                    C.byref(nm)), "projection_match")
+    return best[:L], nm.value
+
+
 def knn2(q, t, speed=False):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     nq, nt = len(q), len(t)

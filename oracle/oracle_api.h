@@ -69,6 +69,10 @@ int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, 
 
 /* Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks */
 int orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_landmarks, int* best, int* best_median);
+/* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) */
+int orc_projection_match(const float* kp_x, const float* kp_y, const int* kp_octave, const uint8_t* desc, int n_feat, const uint8_t* lm_desc,
+    const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int n_landmarks, const uint8_t* feat_taken, float radius, float nn_ratio,
+    double th_high, int* best_idx, int* n_matches);
 
 /* ---- matching (Features/matcher.cpp:10-88,355-358) ---- */
 int orc_hamming(const uint8_t* a, const uint8_t* b);
