@@ -84,9 +84,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """windows: [(t0, t1)] perf_counter intervals of the timed regions; samples inside them are the ones reported (a 100 ms
+        sampling period against steps of a few ms: when no sample falls inside, the samples taken under load between the first
+        warm-up step and the end of the last timed region are used and the line says so)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -97,7 +100,17 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        scope = "timed regions"
+        if windows:
+            inside = [r for r in rows if any(a <= r[0] <= b for a, b in windows)]
+            if inside:
+                rows = inside
+            else:
+                lo = getattr(self, "load_t0", None); hi = max(b for _, b in windows)
+                rows = [r for r in rows if (lo is None or r[0] >= lo) and r[0] <= hi]
+                scope = "under load (warm-up .. end of timed regions; no sample fell inside a timed region)"
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -109,7 +122,7 @@ class ClockSampler:
                 if f[4 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def cpu_pipeline(orc, frames, depths, speed=True):
@@ -178,7 +191,7 @@ def knn2_view(frame_counts, ms):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -229,22 +242,25 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(local); sampler.start()             # started early: nvidia-smi needs ~100 ms before its first row
+    step_device(); torch.cuda.synchronize()
+    t_load0 = time.perf_counter(); sampler.load_t0 = t_load0
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     l0 = ctx.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.perf_counter()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
             step_device()
         ev1.record(stream)
     barrier()
+    tw1 = time.perf_counter()
     launches = ctx.launch_count() - l0
     ms = ev0.elapsed_time(ev1) / args.steps
-    clocks = sampler.stop()
     # ---- end-to-end timing (host buffers, copies inside the timed region) ----
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -253,8 +269,11 @@ def main():
     for _ in range(args.steps):
         summ, mc, fc = step_e2e()
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t1 = time.perf_counter()
+    e2e_ms = (t1 - t0) * 1e3 / args.steps
     barrier()
+    clocks = sampler.stop([(tw0, tw1), (t0, t1)])
+    clocks["load_window_s"] = round(t1 - t_load0, 3)
     # depth: either the whole u16 planes are staged, or (pinned host memory, the default) only the 32-byte sectors holding the
     # one sample each keypoint needs cross PCIe, read in place by the unprojection kernel
     h2d = int(frames.nbytes + (depths.nbytes if args.depth_copy else 32 * int(np.sum(fc))))

@@ -20,7 +20,7 @@ for line in txt.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", line)
     if m and kern:
         counts[kern][m.group(1)] += 1
-want = ["UTMALDG.3D", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "VIMNMX3.U16x2", "VIMNMX.U16x2", "VABSDIFF4.U8", "IDP.4A", "IDP.2A",
+want = ["UTCIMMA", "LDTM.x32", "UTCBAR", "UTMALDG.3D", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "VIMNMX3.U16x2", "VIMNMX.U16x2", "VABSDIFF4.U8", "IDP.4A", "IDP.2A",
         "POPC", "LOP3.LUT", "CREDUX.MIN", "ATOMS", "DFMA", "SHFL", "VOTE", "BAR.SYNC"]
 lines = ["# SASS evidence (cuobjdump -sass liborbfront_b200.so, sm_100a): instruction counts per kernel", "",
          "TMA = `UTMALDG.3D` (+ mbarrier `SYNCS.*`); packed 16x2 integer min/max = `VIMNMX(3).U16x2`; byte SIMD = `VABSDIFF4`, `IDP.4A`, "
