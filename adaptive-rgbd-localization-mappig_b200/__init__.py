@@ -317,6 +317,36 @@ class Context:
                   "projection_match")
         return best[:L], nm.value
 
+    def fuse_search(self, Rcw, tcw, camera, lm_pos, lm_desc, lm_valid, slot=-1, kp_x=None, kp_y=None, u_right=None, desc=None, radius=3.0, th_low=50):
+        """Matcher::Fuse, projection + windowed search (Features/matcher.cpp:212-296): (best feature or -1, its distance or -1) per landmark.
+        camera = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+        Rcw = np.ascontiguousarray(Rcw, np.float32).reshape(9); tcw = np.ascontiguousarray(tcw, np.float32).reshape(3)
+        camera = np.ascontiguousarray(camera, np.float32).reshape(9)
+        lm_pos = np.ascontiguousarray(lm_pos, np.float32).reshape(-1, 3); lm_desc = np.ascontiguousarray(lm_desc, np.uint8).reshape(-1, 32)
+        lm_valid = np.ascontiguousarray(lm_valid, np.uint8)
+        L = len(lm_valid); n = 0
+        if slot < 0:
+            kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32)
+            u_right = np.ascontiguousarray(u_right, np.float32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+            n = len(kp_x)
+        opt = lambda a: _p(a) if a is not None and len(a) else None
+        best = np.full(max(L, 1), -1, np.int32); dist = np.full(max(L, 1), -1, np.int32)
+        self._chk(lib().orbf_fuse_search(self._h, int(slot), _p(Rcw), _p(tcw), _p(camera), opt(kp_x) if slot < 0 else None, opt(kp_y) if slot < 0 else None,
+                                         opt(u_right) if slot < 0 else None, opt(desc) if slot < 0 else None, n, opt(lm_pos), opt(lm_desc), opt(lm_valid), L,
+                                         C.c_float(radius), int(th_low), _p(best), _p(dist)), "fuse_search")
+        return best[:L], dist[:L]
+
+    def bow_match(self, words1, off1, idx1, desc1, words2, off2, idx2, desc2, nn_ratio=0.6, th_low=50):
+        """Matcher::BoWMatch (Features/matcher.cpp:145-209) on flattened DBoW3 feature vectors: DMatch array in the reference's order."""
+        w1 = np.ascontiguousarray(words1, np.int32); o1 = np.ascontiguousarray(off1, np.int32); i1 = np.ascontiguousarray(idx1, np.int32)
+        w2 = np.ascontiguousarray(words2, np.int32); o2 = np.ascontiguousarray(off2, np.int32); i2 = np.ascontiguousarray(idx2, np.int32)
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        opt = lambda a: _p(a) if len(a) else None
+        out = np.zeros(max(len(i1), 1), DMATCH_DT); n = C.c_int32(0)
+        self._chk(lib().orbf_bow_match(self._h, opt(w1), _p(o1), opt(i1), len(w1), opt(d1), len(d1), opt(w2), _p(o2), opt(i2), len(w2), opt(d2), len(d2),
+                                       C.c_float(nn_ratio), int(th_low), _p(out), len(out), C.byref(n)), "bow_match")
+        return out[:n.value].copy()
+
     def match_pairs(self, pairs, ratio, cross_check=False):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         self._chk(lib().orbf_match_pairs(self._h, _p(pairs), len(pairs), C.c_float(ratio), int(cross_check)), "match_pairs")

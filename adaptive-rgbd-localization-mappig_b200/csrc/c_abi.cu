@@ -514,6 +514,86 @@ extern "C" int orbf_distinctive_descriptors(orbf_context* c, const uint8_t* desc
     return ORBF_OK;
 }
 
+// One device allocation carved into 256-byte aligned pieces, freed on scope exit (the §8f matcher entry points stage host arrays).
+namespace {
+struct Scratch {
+    uint8_t* base = nullptr; size_t size = 0;
+    size_t take(size_t bytes) { const size_t o = size; size = (size + std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; return o; }
+    cudaError_t alloc() { return cudaMalloc((void**)&base, std::max<size_t>(size, 256)); }
+    template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
+    ~Scratch() { if (base) cudaFree(base); }
+};
+}  // namespace
+#define SC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } while (0)
+#define SC_H2D(off, src, bytes) do { if ((bytes) > 0) SC_CUDA(cudaMemcpyAsync(sc.base + (off), (src), (bytes), cudaMemcpyHostToDevice, c->stream)); } while (0)
+
+extern "C" int orbf_fuse_search(orbf_context* c, int32_t slot, const float* Rcw, const float* tcw, const float* camera, const float* kp_x, const float* kp_y,
+    const float* u_right, const uint8_t* desc, int32_t n_feat, const float* lm_pos, const uint8_t* lm_desc, const uint8_t* lm_valid, int32_t n_landmarks,
+    float radius, int32_t th_low, int32_t* best_idx, int32_t* best_dist)
+{
+    CTX_ENTER(c);
+    if (!Rcw || !tcw || !camera || !best_idx || n_landmarks < 0 || slot >= c->B) return ORBF_ERR_ARG;
+    if (n_landmarks > 0 && (!lm_pos || !lm_desc || !lm_valid)) return ORBF_ERR_ARG;
+    if (slot < 0 && (n_feat < 0 || n_feat > 65535 || (n_feat > 0 && (!kp_x || !kp_y || !u_right || !desc)))) return ORBF_ERR_ARG;
+    if (n_landmarks == 0) return ORBF_OK;
+    int nFeat = n_feat;
+    if (slot >= 0) { SC_CUDA(cudaMemcpyAsync(&nFeat, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); SC_CUDA(cudaStreamSynchronize(c->stream)); }
+    const size_t L = (size_t)n_landmarks, F = (size_t)std::max(nFeat, 0);
+    Scratch sc;
+    const size_t oPos = sc.take(L * 12), oLd = sc.take(L * 32), oVal = sc.take(L), oOut = sc.take(L * 8);
+    const size_t oKx = sc.take(F * 4), oKy = sc.take(F * 4), oUr = sc.take(F * 4), oDesc = sc.take(F * 32);
+    SC_CUDA(sc.alloc());
+    SC_H2D(oPos, lm_pos, L * 12); SC_H2D(oLd, lm_desc, L * 32); SC_H2D(oVal, lm_valid, L);
+    const float *dKx, *dKy, *dUr; const uint8_t* dDesc;
+    if (slot >= 0) {
+        dKx = c->d_kpx + (size_t)slot * c->K; dKy = c->d_kpy + (size_t)slot * c->K; dUr = c->d_uright + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
+    } else {
+        SC_H2D(oKx, kp_x, F * 4); SC_H2D(oKy, kp_y, F * 4); SC_H2D(oUr, u_right, F * 4); SC_H2D(oDesc, desc, F * 32);
+        dKx = sc.at<float>(oKx); dKy = sc.at<float>(oKy); dUr = sc.at<float>(oUr); dDesc = sc.at<uint8_t>(oDesc);
+    }
+    int* dOut = sc.at<int>(oOut);
+    TRY(orbf_launch_fuse_search(c, Rcw, tcw, camera, dKx, dKy, dUr, dDesc, nFeat, sc.at<float>(oPos), sc.at<uint8_t>(oLd), sc.at<uint8_t>(oVal), n_landmarks, radius,
+        th_low, dOut, dOut + L));
+    SC_CUDA(cudaMemcpyAsync(best_idx, dOut, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (best_dist) SC_CUDA(cudaMemcpyAsync(best_dist, dOut + L, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_bow_match(orbf_context* c, const int32_t* words1, const int32_t* off1, const int32_t* idx1, int32_t nw1, const uint8_t* desc1, int32_t n1,
+    const int32_t* words2, const int32_t* off2, const int32_t* idx2, int32_t nw2, const uint8_t* desc2, int32_t n2, float nn_ratio, int32_t th_low,
+    orbf_dmatch* out, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || nw1 < 0 || nw2 < 0 || n1 < 0 || n2 < 0 || n2 > 65535 || cap < 0 || (cap > 0 && !out)) return ORBF_ERR_ARG;
+    *n_out = 0;
+    if (nw1 == 0 || nw2 == 0) return ORBF_OK;
+    if (!words1 || !off1 || !words2 || !off2) return ORBF_ERR_ARG;
+    const int e1 = off1[nw1], e2 = off2[nw2];
+    if (e1 < 0 || e2 < 0 || (e1 > 0 && (!idx1 || !desc1)) || (e2 > 0 && (!idx2 || !desc2))) return ORBF_ERR_ARG;
+    for (int a = 0; a < nw1; ++a) if (off1[a + 1] < off1[a] || (a > 0 && words1[a] <= words1[a - 1])) return ORBF_ERR_ARG;
+    for (int b = 0; b < nw2; ++b) if (off2[b + 1] < off2[b] || (b > 0 && words2[b] <= words2[b - 1]) || off2[b + 1] - off2[b] > 65535) return ORBF_ERR_ARG;
+    for (int e = 0; e < e1; ++e) if (idx1[e] < 0 || idx1[e] >= n1) return ORBF_ERR_ARG;
+    for (int e = 0; e < e2; ++e) if (idx2[e] < 0 || idx2[e] >= n2) return ORBF_ERR_ARG;
+    if (e1 == 0 || e2 == 0) return ORBF_OK;
+    Scratch sc;
+    const size_t oW1 = sc.take((size_t)nw1 * 4), oO1 = sc.take(((size_t)nw1 + 1) * 4), oI1 = sc.take((size_t)e1 * 4), oD1 = sc.take((size_t)n1 * 32);
+    const size_t oW2 = sc.take((size_t)nw2 * 4), oO2 = sc.take(((size_t)nw2 + 1) * 4), oI2 = sc.take((size_t)e2 * 4), oD2 = sc.take((size_t)n2 * 32);
+    const size_t oET = sc.take((size_t)e1 * 4), oED = sc.take((size_t)e1 * 4), oFU = sc.take((size_t)n2 * 4), oOut = sc.take((size_t)e1 * sizeof(orbf_dmatch)), oN = sc.take(4);
+    SC_CUDA(sc.alloc());
+    SC_H2D(oW1, words1, (size_t)nw1 * 4); SC_H2D(oO1, off1, ((size_t)nw1 + 1) * 4); SC_H2D(oI1, idx1, (size_t)e1 * 4); SC_H2D(oD1, desc1, (size_t)n1 * 32);
+    SC_H2D(oW2, words2, (size_t)nw2 * 4); SC_H2D(oO2, off2, ((size_t)nw2 + 1) * 4); SC_H2D(oI2, idx2, (size_t)e2 * 4); SC_H2D(oD2, desc2, (size_t)n2 * 32);
+    TRY(orbf_launch_bow_match(c, sc.at<int>(oW1), sc.at<int>(oO1), sc.at<int>(oI1), nw1, sc.at<uint8_t>(oD1), sc.at<int>(oW2), sc.at<int>(oO2), sc.at<int>(oI2), nw2,
+        sc.at<uint8_t>(oD2), n2, nn_ratio, th_low, e1, sc.at<int>(oET), sc.at<int>(oED), sc.at<int>(oFU), sc.at<orbf_dmatch>(oOut), sc.at<int>(oN)));
+    int n = 0;
+    SC_CUDA(cudaMemcpyAsync(&n, sc.at<int>(oN), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    if (n > cap) return ORBF_ERR_CAPACITY;
+    if (n > 0) { SC_CUDA(cudaMemcpyAsync(out, sc.at<orbf_dmatch>(oOut), (size_t)n * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream)); SC_CUDA(cudaStreamSynchronize(c->stream)); }
+    return ORBF_OK;
+}
+
 extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
     int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
     const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches)

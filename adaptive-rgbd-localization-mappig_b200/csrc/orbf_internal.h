@@ -197,6 +197,12 @@ struct MatchSet {
 };
 int orbf_launch_knn2(orbf_context* ctx, const MatchSet& ms, int npairs, bool cross);
 int orbf_launch_distinctive(orbf_context* ctx, const uint8_t* d_desc, const int* d_offsets, int nLandmarks, int* d_best, int* d_median);
+int orbf_launch_fuse_search(orbf_context* ctx, const float* Rcw, const float* tcw, const float* camera, const float* d_kpx, const float* d_kpy, const float* d_uright,
+    const uint8_t* d_desc, int nFeat, const float* d_lmPos, const uint8_t* d_lmDesc, const uint8_t* d_lmValid, int nLm, float radius, int thLow, int* d_bestIdx,
+    int* d_bestDist);
+int orbf_launch_bow_match(orbf_context* ctx, const int* d_words1, const int* d_off1, const int* d_idx1, int nw1, const uint8_t* d_desc1, const int* d_words2,
+    const int* d_off2, const int* d_idx2, int nw2, const uint8_t* d_desc2, int nTrain, float nnRatio, int thLow, int nEntries, int* d_entryTrain, int* d_entryDist,
+    int* d_firstUser, orbf_dmatch* d_out, int* d_nOut);
 int orbf_launch_projection_match(orbf_context* ctx, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat,
     const uint8_t* d_lmDesc, const float* d_projX, const float* d_projY, const uint8_t* d_lmFlags, int nLm, const uint8_t* d_featTaken, float radius, float nnRatio,
     int thHigh, uint32_t* d_cand, int* d_candCount, uint8_t* d_taken, int* d_bestIdx, int* d_nMatches);

@@ -1,4 +1,7 @@
-// csrc/projection.cu — Matcher::ProjectionMatch (reference Features/matcher.cpp:90-143): landmarks already
+// csrc/projection.cu — the windowed / word-bucketed Hamming searches of the reference matcher:
+// Matcher::ProjectionMatch (Features/matcher.cpp:90-143), the search of Matcher::Fuse (:212-296) and Matcher::BoWMatch (:145-209).
+//
+// ProjectionMatch: landmarks already
 // projected into a frame are matched to the frame's features inside a square window (Frame::GetFeaturesInArea,
 // Core/frame.cpp:258-274: a linear scan in feature order, |dx| < r && |dy| < r in float).
 //
@@ -98,6 +101,134 @@ __global__ void __launch_bounds__(32) proj_resolve_kernel(const uint32_t* __rest
     if (lane == 0) *nMatches = nm;
 }
 
+
+// ---- Matcher::Fuse, search part (Features/matcher.cpp:212-296): warp per landmark, landmarks independent ---------------------------
+// p3Dc = Rcw * p3Dw + tcw exactly as cv::gemm evaluates a 3x3 * 3x1 product (float, left to right) followed by the double
+// alpha / beta combination; projection with separate multiply and add (the library is built with -fmad=false, quirk Q4).
+struct FuseCamera { float R[9], t[3], fx, fy, cx, cy, mbf, minX, maxX, minY, maxY; };
+
+__global__ void __launch_bounds__(128) fuse_search_kernel(FuseCamera cam, const float* __restrict__ kpx, const float* __restrict__ kpy, const float* __restrict__ uRight,
+    const uint8_t* __restrict__ desc, int nFeat, const float* __restrict__ lmPos, const uint8_t* __restrict__ lmDesc, const uint8_t* __restrict__ lmValid, int nLm,
+    float radius, int thLow, int* __restrict__ bestIdx, int* __restrict__ bestDist)
+{
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= nLm) return;
+    uint32_t best = PJ_NONE;
+    if (lmValid[i]) {
+        float pc[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float t = __fmul_rn(cam.R[3 * r], lmPos[3 * i]);
+            t = __fadd_rn(t, __fmul_rn(cam.R[3 * r + 1], lmPos[3 * i + 1]));
+            t = __fadd_rn(t, __fmul_rn(cam.R[3 * r + 2], lmPos[3 * i + 2]));
+            pc[r] = __double2float_rn(__dadd_rn((double)t, (double)cam.t[r]));
+        }
+        if (!(pc[2] < 0.0f)) {
+            const float invz = __fdiv_rn(1.0f, pc[2]);
+            const float u = __fadd_rn(__fmul_rn(cam.fx, __fmul_rn(pc[0], invz)), cam.cx), v = __fadd_rn(__fmul_rn(cam.fy, __fmul_rn(pc[1], invz)), cam.cy);
+            if (u >= cam.minX && u < cam.maxX && v >= cam.minY && v < cam.maxY) {
+                const float ur = __fsub_rn(u, __fmul_rn(cam.mbf, invz));
+                const uint4 la = __ldg(reinterpret_cast<const uint4*>(lmDesc + (size_t)i * 32)), lb = __ldg(reinterpret_cast<const uint4*>(lmDesc + (size_t)i * 32) + 1);
+                for (int j = lane; j < nFeat; j += 32) {
+                    const float x = kpx[j], y = kpy[j];
+                    if (!(fabsf(__fsub_rn(x, u)) < radius && fabsf(__fsub_rn(y, v)) < radius)) continue;
+                    const float ex = __fsub_rn(u, x), ey = __fsub_rn(v, y), r = uRight[j];
+                    float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    if (r >= 0) {
+                        const float er = __fsub_rn(ur, r);
+                        e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                        if (e2 > 7.8f) continue;
+                    } else if (e2 > 5.99f) continue;
+                    const uint4 fa = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32)), fb = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32) + 1);
+                    const int d = __popc(la.x ^ fa.x) + __popc(la.y ^ fa.y) + __popc(la.z ^ fa.z) + __popc(la.w ^ fa.w)
+                                + __popc(lb.x ^ fb.x) + __popc(lb.y ^ fb.y) + __popc(lb.z ^ fb.z) + __popc(lb.w ^ fb.w);
+                    best = min(best, ((uint32_t)d << 16) | (uint32_t)j);          // strict '<' in feature order = smallest (distance, index)
+                }
+            }
+        }
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) {
+        const bool ok = best != PJ_NONE && (int)(best >> 16) <= thLow;
+        bestIdx[i] = ok ? (int)(best & 0xFFFFu) : -1;
+        bestDist[i] = ok ? (int)(best >> 16) : -1;
+    }
+}
+
+// ---- Matcher::BoWMatch (Features/matcher.cpp:145-209) --------------------------------------------------------------------------
+// Entry e of keyframe 1's flattened feature vector (= the reference's processing order: words ascending, bucket order) finds
+// its word in keyframe 2 by binary search, then its best / second best in that bucket; the std::set of used train indices is
+// "the first entry in processing order wins", i.e. an atomicMin of the entry number per train feature.
+__global__ void __launch_bounds__(128) bow_best_kernel(const int* __restrict__ words1, const int* __restrict__ off1, const int* __restrict__ idx1, int nw1,
+    const uint8_t* __restrict__ desc1, const int* __restrict__ words2, const int* __restrict__ off2, const int* __restrict__ idx2, int nw2,
+    const uint8_t* __restrict__ desc2, float nnRatio, int thLow, int nEntries, int* __restrict__ entryTrain, int* __restrict__ entryDist, int* __restrict__ firstUser)
+{
+    const int lane = threadIdx.x & 31, e = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= nEntries) return;
+    // word of entry e: last a with off1[a] <= e
+    int lo = 0, hi = nw1 - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off1[mid] <= e) lo = mid; else hi = mid - 1; }
+    const int w = words1[lo];
+    int l2 = 0, h2 = nw2;                                        // lower_bound of w in words2
+    while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (words2[mid] < w) l2 = mid + 1; else h2 = mid; }
+    int train = -1, dist = -1;
+    if (l2 < nw2 && words2[l2] == w) {
+        const int q = idx1[e], b0 = off2[l2], nb = off2[l2 + 1] - b0;
+        const uint4 qa = __ldg(reinterpret_cast<const uint4*>(desc1 + (size_t)q * 32)), qb = __ldg(reinterpret_cast<const uint4*>(desc1 + (size_t)q * 32) + 1);
+        uint32_t k1 = PJ_NONE, k2 = PJ_NONE;
+        for (int p = lane; p < nb; p += 32) {
+            const int t = idx2[b0 + p];
+            const uint4 ta = __ldg(reinterpret_cast<const uint4*>(desc2 + (size_t)t * 32)), tb = __ldg(reinterpret_cast<const uint4*>(desc2 + (size_t)t * 32) + 1);
+            const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                        + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            pj_insert(k1, k2, ((uint32_t)d << 16) | (uint32_t)p);          // position in the bucket: strict '<' keeps the earlier one
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+            pj_insert(k1, k2, o1);
+            pj_insert(k1, k2, o2);
+        }
+        if (k1 != PJ_NONE && (int)(k1 >> 16) <= thLow) {
+            const float d1 = (float)(k1 >> 16), d2 = k2 != PJ_NONE ? (float)(k2 >> 16) : __int_as_float(0x7f800000);   // (float)DBL_MAX = +inf
+            if (d1 < __fmul_rn(nnRatio, d2)) { train = idx2[b0 + (int)(k1 & 0xFFFFu)]; dist = (int)(k1 >> 16); }
+        }
+    }
+    if (lane == 0) {
+        entryTrain[e] = train; entryDist[e] = dist;
+        if (train >= 0) atomicMin(&firstUser[train], e);
+    }
+}
+
+// entries that own their train feature, compacted in processing order (single CTA: the lists are a few thousand entries)
+__global__ void __launch_bounds__(256) bow_emit_kernel(const int* __restrict__ idx1, const int* __restrict__ entryTrain, const int* __restrict__ entryDist,
+    const int* __restrict__ firstUser, int nEntries, orbf_dmatch* __restrict__ out, int* __restrict__ nOut)
+{
+    __shared__ int sWarp[8];
+    __shared__ int sBase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sBase = 0;
+    __syncthreads();
+    for (int base = 0; base < nEntries; base += 256) {
+        const int e = base + threadIdx.x;
+        const int t = e < nEntries ? entryTrain[e] : -1;
+        const bool keep = t >= 0 && firstUser[t] == e;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) sWarp[warp] = __popc(m);
+        __syncthreads();
+        int off = sBase;
+        for (int w = 0; w < warp; ++w) off += sWarp[w];
+        if (keep) {
+            orbf_dmatch dm; dm.queryIdx = idx1[e]; dm.trainIdx = t; dm.imgIdx = -1; dm.distance = (float)entryDist[e];
+            out[off + __popc(m & ((1u << lane) - 1))] = dm;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; ++w) s += sWarp[w]; sBase += s; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nOut = sBase;
+}
+
 }  // namespace
 
 int orbf_launch_projection_match(orbf_context* c, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat, const uint8_t* d_lmDesc,
@@ -108,6 +239,36 @@ int orbf_launch_projection_match(orbf_context* c, const float* d_kpx, const floa
     proj_candidates_kernel<<<(nLm + 3) / 4, 128, 0, c->stream>>>(d_kpx, d_kpy, d_desc, nFeat, d_lmDesc, d_projX, d_projY, d_lmFlags, nLm, radius, d_cand, d_candCount);
     ORBF_LAUNCH_CHECK(c);
     proj_resolve_kernel<<<1, 32, 0, c->stream>>>(d_cand, d_candCount, d_kpoct, nFeat, d_lmFlags, nLm, d_featTaken, nnRatio, thHigh, d_taken, d_bestIdx, d_nMatches);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+int orbf_launch_fuse_search(orbf_context* c, const float* Rcw, const float* tcw, const float* camera /* fx fy cx cy mbf minX maxX minY maxY */, const float* d_kpx,
+    const float* d_kpy, const float* d_uright, const uint8_t* d_desc, int nFeat, const float* d_lmPos, const uint8_t* d_lmDesc, const uint8_t* d_lmValid, int nLm,
+    float radius, int thLow, int* d_bestIdx, int* d_bestDist)
+{
+    if (nLm <= 0) return ORBF_OK;
+    FuseCamera cam;
+    for (int i = 0; i < 9; ++i) cam.R[i] = Rcw[i];
+    for (int i = 0; i < 3; ++i) cam.t[i] = tcw[i];
+    cam.fx = camera[0]; cam.fy = camera[1]; cam.cx = camera[2]; cam.cy = camera[3]; cam.mbf = camera[4];
+    cam.minX = camera[5]; cam.maxX = camera[6]; cam.minY = camera[7]; cam.maxY = camera[8];
+    fuse_search_kernel<<<(nLm + 3) / 4, 128, 0, c->stream>>>(cam, d_kpx, d_kpy, d_uright, d_desc, nFeat, d_lmPos, d_lmDesc, d_lmValid, nLm, radius, thLow, d_bestIdx, d_bestDist);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+int orbf_launch_bow_match(orbf_context* c, const int* d_words1, const int* d_off1, const int* d_idx1, int nw1, const uint8_t* d_desc1, const int* d_words2,
+    const int* d_off2, const int* d_idx2, int nw2, const uint8_t* d_desc2, int nTrain, float nnRatio, int thLow, int nEntries, int* d_entryTrain, int* d_entryDist,
+    int* d_firstUser, orbf_dmatch* d_out, int* d_nOut)
+{
+    ORBF_CUDA(c, cudaMemsetAsync(d_nOut, 0, sizeof(int), c->stream));
+    if (nEntries <= 0 || nw1 <= 0 || nw2 <= 0) return ORBF_OK;
+    ORBF_CUDA(c, cudaMemsetAsync(d_firstUser, 0x7F, (size_t)std::max(nTrain, 1) * sizeof(int), c->stream));
+    bow_best_kernel<<<(nEntries + 3) / 4, 128, 0, c->stream>>>(d_words1, d_off1, d_idx1, nw1, d_desc1, d_words2, d_off2, d_idx2, nw2, d_desc2, nnRatio, thLow, nEntries,
+        d_entryTrain, d_entryDist, d_firstUser);
+    ORBF_LAUNCH_CHECK(c);
+    bow_emit_kernel<<<1, 256, 0, c->stream>>>(d_idx1, d_entryTrain, d_entryDist, d_firstUser, nEntries, d_out, d_nOut);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }

@@ -17,6 +17,8 @@
  *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
  *   orbf_distinctive_descriptors      Landmark::ComputeDistinctiveDescriptors     Core/landmark.cpp:219-273
  *   orbf_projection_match             Matcher::ProjectionMatch + Frame::GetFeaturesInArea   Features/matcher.cpp:90-143, Core/frame.cpp:258-274
+ *   orbf_fuse_search                  Matcher::Fuse, projection + windowed search   Features/matcher.cpp:212-296
+ *   orbf_bow_match                    Matcher::BoWMatch                           Features/matcher.cpp:145-209
  *   orbf_match_pairs                  Tracking::TrackFrame's matcher call, batched  System/tracking.cpp:197-199
  *   orbf_track_sequence*              Tracking::Track's per-frame loop (extract, match with the last frame, RANSAC)
  *                                     over a whole sequence, pipelined            System/tracking.cpp:38-46,193-208
@@ -188,6 +190,22 @@ int orbf_distinctive_descriptors(orbf_context* ctx, const uint8_t* desc, const i
 int orbf_projection_match(orbf_context* ctx, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
     int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
     const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches);
+/* Matcher::Fuse (Features/matcher.cpp:212-296), the part that computes: landmark i (world position lm_pos[3i..], descriptor, lm_valid[i] =
+ * pLM && !isBad() && !IsInKeyFrame(pKF)) is transformed by Rcw (row-major 3x3) / tcw, projected with camera = {fx, fy, cx, cy, mbf, mnMinX,
+ * mnMaxX, mnMinY, mnMaxY}, and matched to the keyframe feature with the smallest Hamming distance inside the window that passes the
+ * stereo (u_right[j] >= 0) / mono reprojection gate; best_idx[i] = that feature when the distance is <= th_low, else -1 (best_dist may
+ * be NULL).  The Replace / AddObservation / AddLandmark that follows (matcher.cpp:297-311) edits the map graph and stays with the caller.
+ * slot >= 0: keyframe features from that frame slot (kp_x / kp_y / u_right / desc ignored); slot < 0: n_feat host rows.            */
+int orbf_fuse_search(orbf_context* ctx, int32_t slot, const float* Rcw, const float* tcw, const float* camera, const float* kp_x, const float* kp_y,
+    const float* u_right, const uint8_t* desc, int32_t n_feat, const float* lm_pos, const uint8_t* lm_desc, const uint8_t* lm_valid,
+    int32_t n_landmarks, float radius, int32_t th_low, int32_t* best_idx, int32_t* best_dist);
+/* Matcher::BoWMatch (Features/matcher.cpp:145-209).  The two DBoW3 feature vectors arrive flattened: words[nw] ascending node ids,
+ * off[nw + 1] bucket offsets, idx[off[nw]] feature indices in bucket order; desc1 / desc2 = the keyframes' descriptor matrices
+ * (n1 / n2 rows of 32 bytes).  Survivors (best <= th_low, (float)best < nn_ratio * (float)second, train feature not used by an earlier
+ * query) in the reference's order; imgIdx = -1 as a default-constructed cv::DMatch has it.                                     */
+int orbf_bow_match(orbf_context* ctx, const int32_t* words1, const int32_t* off1, const int32_t* idx1, int32_t nw1, const uint8_t* desc1, int32_t n1,
+    const int32_t* words2, const int32_t* off2, const int32_t* idx2, int32_t nw2, const uint8_t* desc2, int32_t n2, float nn_ratio, int32_t th_low,
+    orbf_dmatch* out, int32_t cap, int32_t* n_out);
 /* Device-resident: match frame slot pairs (query_slot, train_slot); results live in pair slots 0..npairs-1. */
 int orbf_match_pairs(orbf_context* ctx, const int32_t* pairs /* 2*npairs */, int32_t npairs, float ratio,
     int32_t cross_check);

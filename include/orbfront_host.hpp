@@ -350,6 +350,43 @@ public:
         return (size_t)n;
     }
 
+    // Matcher::Fuse (matcher.cpp:212-296), the computing half: projection of every landmark with the keyframe pose and the windowed
+    // search for its best feature.  lmValid[i] = pLM && !pLM->isBad() && !pLM->IsInKeyFrame(pKF); bestIdx[i] = feature or -1.  The
+    // caller then runs the reference's Replace / AddObservation / AddLandmark branch (matcher.cpp:297-311) on the survivors.
+    void FuseSearch(Frame& kf, const float Rcw[9], const float tcw[3], const float camera[9] /* fx fy cx cy mbf minX maxX minY maxY */,
+        const std::vector<Point3f>& worldPos, const std::vector<const uint8_t*>& descriptors, const std::vector<uint8_t>& lmValid, float th,
+        std::vector<int>& bestIdx)
+    {
+        const int L = (int)worldPos.size(), N = (int)kf.mvKeysUn.size();
+        bestIdx.assign((size_t)L, -1);
+        if (L == 0) return;
+        std::vector<uint8_t> d((size_t)L * 32);
+        std::vector<float> pos((size_t)L * 3), kx((size_t)N), ky((size_t)N);
+        for (int i = 0; i < L; ++i) {
+            std::copy(descriptors[i], descriptors[i] + 32, d.begin() + (size_t)i * 32);
+            pos[3 * i] = worldPos[i].x; pos[3 * i + 1] = worldPos[i].y; pos[3 * i + 2] = worldPos[i].z;
+        }
+        for (int j = 0; j < N; ++j) { kx[j] = kf.mvKeysUn[j].pt.x; ky[j] = kf.mvKeysUn[j].pt.y; }
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        check(orbf_fuse_search(Runtime::Current(), -1, Rcw, tcw, camera, kx.data(), ky.data(), kf.mvuRight.data(), kf.mDescriptors.data, N, pos.data(), d.data(),
+                  lmValid.data(), L, th, (int)TH_LOW, bestIdx.data(), nullptr), "orbf_fuse_search");
+    }
+
+    // Matcher::BoWMatch (matcher.cpp:145-209).  A DBoW3::FeatureVector is a std::map<NodeId, std::vector<unsigned>>: pass it flattened
+    // (words ascending, bucket offsets, feature indices in bucket order).
+    struct FlatFeatureVector { std::vector<int32_t> words, offsets, indices; };
+    int BoWMatch(const FlatFeatureVector& fv1, const Mat8u& desc1, const FlatFeatureVector& fv2, const Mat8u& desc2, std::vector<DMatch>& vMatches12)
+    {
+        vMatches12.assign(fv1.indices.size(), DMatch());
+        int n = 0;
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        check(orbf_bow_match(Runtime::Current(), fv1.words.data(), fv1.offsets.data(), fv1.indices.data(), (int)fv1.words.size(), desc1.data, desc1.rows,
+                  fv2.words.data(), fv2.offsets.data(), fv2.indices.data(), (int)fv2.words.size(), desc2.data, desc2.rows, mfNNratio, (int)TH_LOW,
+                  reinterpret_cast<orbf_dmatch*>(vMatches12.data()), (int)vMatches12.size(), &n), "orbf_bow_match");
+        vMatches12.resize((size_t)n);
+        return n;
+    }
+
 private:
     float mfNNratio; double TH_LOW, TH_HIGH;
 };

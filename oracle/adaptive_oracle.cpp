@@ -174,3 +174,107 @@ int orc_projection_match(const float* kp_x, const float* kp_y, const int* kp_oct
     *n_matches = nm;
     return ORC_OK;
 }
+
+// ---- Matcher::Fuse, search part (Features/matcher.cpp:212-296), SURVEY.md §8f rank 1 ---------------------------------------------
+// Per landmark (independent of the others): p3Dc = Rcw * p3Dw + tcw as cv::gemm evaluates it for 3x3 * 3x1 (float products summed
+// left to right in float, then (float)((double)t * 1.0 + (double)tcw * 1.0); pinned against cv2.gemm in tests/test_fuse_bow.py),
+// rejected for z < 0, pinhole projection with separate multiply and add, KeyFrame::IsInImage, ur = u - mbf / z;
+// Frame::GetFeaturesInArea window in feature order; stereo (mvuRight >= 0) / mono reprojection gates 7.8 / 5.99; strict '<' on the
+// Hamming distance; accepted when best <= TH_LOW.  What follows in the reference (Replace / AddObservation / AddLandmark,
+// matcher.cpp:297-311) edits the map graph and stays with the caller.
+//   lm_valid[i]: pLM && !pLM->isBad() && !pLM->IsInKeyFrame(pKF).   best_idx[i] = -1 when nothing is fused.
+int orc_fuse_search(const float* Rcw /* 9, row-major */, const float* tcw /* 3 */, float fx, float fy, float cx, float cy, float mbf, float min_x, float max_x,
+    float min_y, float max_y, const float* kp_x, const float* kp_y, const float* u_right, const uint8_t* desc, int n_feat, const float* lm_pos /* 3 per landmark */,
+    const uint8_t* lm_desc, const uint8_t* lm_valid, int n_landmarks, float radius, double th_low, int* best_idx, int* best_dist)
+{
+    if (n_feat < 0 || n_landmarks < 0 || !best_idx || !Rcw || !tcw) return ORC_ERR_ARG;
+    if (n_landmarks > 0 && (!lm_pos || !lm_desc || !lm_valid)) return ORC_ERR_ARG;
+    if (n_feat > 0 && (!kp_x || !kp_y || !u_right || !desc)) return ORC_ERR_ARG;
+    for (int i = 0; i < n_landmarks; ++i) {
+        best_idx[i] = -1;
+        if (best_dist) best_dist[i] = -1;
+        if (!lm_valid[i]) continue;
+        float pc[3];
+        for (int r = 0; r < 3; ++r) {
+            float t = Rcw[3 * r] * lm_pos[3 * i];
+            t = t + Rcw[3 * r + 1] * lm_pos[3 * i + 1];
+            t = t + Rcw[3 * r + 2] * lm_pos[3 * i + 2];
+            pc[r] = (float)((double)t * 1.0 + (double)tcw[r] * 1.0);
+        }
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        float u = fx * x; u = u + cx;
+        float v = fy * y; v = v + cy;
+        if (!(u >= min_x && u < max_x && v >= min_y && v < max_y)) continue;
+        float ur = mbf * invz; ur = u - ur;
+        double bestDist = 1.7976931348623157e308;
+        int bestIdx = -1;
+        for (int j = 0; j < n_feat; ++j) {
+            const float distx = kp_x[j] - u, disty = kp_y[j] - v;
+            if (!(std::fabs(distx) < radius && std::fabs(disty) < radius)) continue;
+            const float ex = u - kp_x[j], ey = v - kp_y[j];
+            if (u_right[j] >= 0) {
+                const float er = ur - u_right[j];
+                float e2 = ex * ex; e2 = e2 + ey * ey; e2 = e2 + er * er;
+                if (e2 > 7.8f) continue;
+            } else {
+                float e2 = ex * ex; e2 = e2 + ey * ey;
+                if (e2 > 5.99f) continue;
+            }
+            const double dist = (double)orc_hamming(lm_desc + (size_t)i * 32, desc + (size_t)j * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = j; }
+        }
+        if (bestDist <= th_low) {
+            best_idx[i] = bestIdx;
+            if (best_dist) best_dist[i] = (int)bestDist;
+        }
+    }
+    return ORC_OK;
+}
+
+// ---- Matcher::BoWMatch (Features/matcher.cpp:145-209), SURVEY.md §8f rank 1 -------------------------------------------------------
+// The DBoW3 feature vectors arrive as CSR: words1[nw1] ascending node ids, off1[nw1 + 1], idx1[...] feature indices in the
+// std::vector order (same for keyframe 2).  For every word present in both, every feature of keyframe 1 in that word looks for its
+// best / second best (strict '<', bucket order) among keyframe 2's features of the word; kept when best <= TH_LOW and
+// (float)best < ratio * (float)second, unless the train feature was already used by an earlier query (std::set trainIdxs).
+int orc_bow_match(const int* words1, const int* off1, const int* idx1, int nw1, const uint8_t* desc1, const int* words2, const int* off2, const int* idx2,
+    int nw2, const uint8_t* desc2, float nn_ratio, double th_low, orc_dmatch* out, int cap, int* n_out)
+{
+    if (nw1 < 0 || nw2 < 0 || !n_out) return ORC_ERR_ARG;
+    std::vector<orc_dmatch> res;
+    std::vector<int> used;
+    int a = 0, b = 0;
+    while (a < nw1 && b < nw2) {
+        if (words1[a] == words2[b]) {
+            for (int e1 = off1[a]; e1 < off1[a + 1]; ++e1) {
+                const int q = idx1[e1];
+                double bestDist1 = 1.7976931348623157e308, bestDist2 = 1.7976931348623157e308;
+                int bestTrain = -1;
+                for (int e2 = off2[b]; e2 < off2[b + 1]; ++e2) {
+                    const int t = idx2[e2];
+                    const double dist = (double)orc_hamming(desc1 + (size_t)q * 32, desc2 + (size_t)t * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestTrain = t; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= th_low) {
+                    if (static_cast<float>(bestDist1) < nn_ratio * static_cast<float>(bestDist2)) {
+                        if (std::find(used.begin(), used.end(), bestTrain) != used.end()) continue;
+                        orc_dmatch m; m.queryIdx = q; m.trainIdx = bestTrain; m.imgIdx = -1; m.distance = static_cast<float>(bestDist1);
+                        res.push_back(m);
+                        used.push_back(bestTrain);
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (words1[a] < words2[b]) {
+            while (a < nw1 && words1[a] < words2[b]) ++a;          // lower_bound on a sorted map
+        } else {
+            while (b < nw2 && words2[b] < words1[a]) ++b;
+        }
+    }
+    *n_out = (int)res.size();
+    if ((int)res.size() > cap) return ORC_ERR_CAPACITY;
+    if (out) std::copy(res.begin(), res.end(), out);
+    return ORC_OK;
+}

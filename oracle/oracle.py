@@ -286,6 +286,35 @@ def projection_match(kp_x, kp_y, kp_octave, desc, lm_desc, proj_x, proj_y, lm_fl
     return best[:L], nm.value
 
 
+def fuse_search(Rcw, tcw, camera, kp_x, kp_y, u_right, desc, lm_pos, lm_desc, lm_valid, radius=3.0, th_low=50.0):
+    """Matcher::Fuse, projection + windowed search (Features/matcher.cpp:212-296)."""
+    Rcw = np.ascontiguousarray(Rcw, np.float32).reshape(9); tcw = np.ascontiguousarray(tcw, np.float32).reshape(3)
+    fx, fy, cx, cy, mbf, x0, x1, y0, y1 = [float(v) for v in np.asarray(camera, np.float32)]
+    kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32); u_right = np.ascontiguousarray(u_right, np.float32)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    lm_pos = np.ascontiguousarray(lm_pos, np.float32).reshape(-1, 3); lm_desc = np.ascontiguousarray(lm_desc, np.uint8).reshape(-1, 32)
+    lm_valid = np.ascontiguousarray(lm_valid, np.uint8)
+    n, L = len(kp_x), len(lm_valid)
+    best = np.full(max(L, 1), -1, np.int32); dist = np.full(max(L, 1), -1, np.int32)
+    opt = lambda a: _p(a) if len(a) else None
+    _chk(lib().orc_fuse_search(_p(Rcw), _p(tcw), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(mbf), C.c_float(x0), C.c_float(x1),
+                               C.c_float(y0), C.c_float(y1), opt(kp_x), opt(kp_y), opt(u_right), opt(desc), n, opt(lm_pos), opt(lm_desc), opt(lm_valid), L,
+                               C.c_float(radius), C.c_double(th_low), _p(best), _p(dist)), "fuse_search")
+    return best[:L], dist[:L]
+
+
+def bow_match(words1, off1, idx1, desc1, words2, off2, idx2, desc2, nn_ratio=0.6, th_low=50.0):
+    """Matcher::BoWMatch (Features/matcher.cpp:145-209) on flattened feature vectors."""
+    w1 = np.ascontiguousarray(words1, np.int32); o1 = np.ascontiguousarray(off1, np.int32); i1 = np.ascontiguousarray(idx1, np.int32)
+    w2 = np.ascontiguousarray(words2, np.int32); o2 = np.ascontiguousarray(off2, np.int32); i2 = np.ascontiguousarray(idx2, np.int32)
+    d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+    out = np.zeros(max(len(i1), 1), DMATCH_DT); n = C.c_int(0)
+    opt = lambda a: _p(a) if len(a) else None
+    _chk(lib().orc_bow_match(opt(w1), _p(o1), opt(i1), len(w1), opt(d1), opt(w2), _p(o2), opt(i2), len(w2), opt(d2), C.c_float(nn_ratio), C.c_double(th_low),
+                             _p(out), len(out), C.byref(n)), "bow_match")
+    return out[:n.value].copy()
+
+
 def knn2(q, t, speed=False):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     nq, nt = len(q), len(t)

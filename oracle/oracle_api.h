@@ -69,6 +69,12 @@ int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, 
 
 /* Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks */
 int orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_landmarks, int* best, int* best_median);
+/* Matcher::Fuse, search part (Features/matcher.cpp:212-296) and Matcher::BoWMatch (Features/matcher.cpp:145-209) */
+int orc_fuse_search(const float* Rcw, const float* tcw, float fx, float fy, float cx, float cy, float mbf, float min_x, float max_x, float min_y, float max_y,
+    const float* kp_x, const float* kp_y, const float* u_right, const uint8_t* desc, int n_feat, const float* lm_pos, const uint8_t* lm_desc,
+    const uint8_t* lm_valid, int n_landmarks, float radius, double th_low, int* best_idx, int* best_dist);
+int orc_bow_match(const int* words1, const int* off1, const int* idx1, int nw1, const uint8_t* desc1, const int* words2, const int* off2, const int* idx2,
+    int nw2, const uint8_t* desc2, float nn_ratio, double th_low, orc_dmatch* out, int cap, int* n_out);
 /* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) */
 int orc_projection_match(const float* kp_x, const float* kp_y, const int* kp_octave, const uint8_t* desc, int n_feat, const uint8_t* lm_desc,
     const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int n_landmarks, const uint8_t* feat_taken, float radius, float nn_ratio,
