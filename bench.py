@@ -211,7 +211,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on fd 1 while the communicator comes up; the contract is ONE JSON line on stdout, so
+        # stdout points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     ob = load_pkg()
     F = args.frames
     frames, depths = make_inputs(F, seed=rank)            # each rank its own shard of the sequence (weak scaling)
