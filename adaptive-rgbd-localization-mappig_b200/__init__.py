@@ -317,6 +317,16 @@ class Context:
                   "projection_match")
         return best[:L], nm.value
 
+    def compose_trajectory(self, npairs, pose0=None, with_flags=True):
+        """Odometry::Compute's composition rule + inlier flags (Odometry/odometry.cpp:78-90) over the pairs last solved by ransac_pairs /
+        track_sequence: (poses [npairs + 1, 4, 4], outlier flags [npairs + 1, K] or None)."""
+        poses = np.zeros((npairs + 1, 16), np.float32)
+        flags = np.ones((npairs + 1, self.K), np.uint8) if with_flags else None
+        p0 = None if pose0 is None else np.ascontiguousarray(pose0, np.float32).reshape(16)
+        self._chk(lib().orbf_compose_trajectory(self._h, int(npairs), _p(p0) if p0 is not None else None, _p(poses), _p(flags) if with_flags else None),
+                  "compose_trajectory")
+        return poses.reshape(-1, 4, 4), flags
+
     def fuse_search(self, Rcw, tcw, camera, lm_pos, lm_desc, lm_valid, slot=-1, kp_x=None, kp_y=None, u_right=None, desc=None, radius=3.0, th_low=50):
         """Matcher::Fuse, projection + windowed search (Features/matcher.cpp:212-296): (best feature or -1, its distance or -1) per landmark.
         camera = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY)."""

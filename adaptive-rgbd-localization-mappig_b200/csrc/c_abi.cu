@@ -594,6 +594,22 @@ extern "C" int orbf_bow_match(orbf_context* c, const int32_t* words1, const int3
     return ORBF_OK;
 }
 
+extern "C" int orbf_compose_trajectory(orbf_context* c, int32_t npairs, const float* pose0, float* poses, uint8_t* outlier)
+{
+    CTX_ENTER(c);
+    if (!poses || npairs < 0 || npairs > c->P || npairs > c->lastNPairs) return ORBF_ERR_ARG;
+    static const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    Scratch sc;
+    const size_t oP0 = sc.take(64), oPoses = sc.take(((size_t)npairs + 1) * 64), oOut = sc.take(outlier ? ((size_t)npairs + 1) * c->K : 1);
+    SC_CUDA(sc.alloc());
+    SC_H2D(oP0, pose0 ? pose0 : eye, 64);
+    TRY(orbf_launch_compose(c, npairs, sc.at<float>(oP0), sc.at<float>(oPoses), outlier ? sc.at<uint8_t>(oOut) : nullptr));
+    SC_CUDA(cudaMemcpyAsync(poses, sc.at<float>(oPoses), ((size_t)npairs + 1) * 64, cudaMemcpyDeviceToHost, c->stream));
+    if (outlier) SC_CUDA(cudaMemcpyAsync(outlier, sc.at<uint8_t>(oOut), ((size_t)npairs + 1) * c->K, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
 extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
     int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
     const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches)

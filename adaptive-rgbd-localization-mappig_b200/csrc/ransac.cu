@@ -894,3 +894,49 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     orbf_prof_end(c, ST_RANSAC_SELECT);
     return ORBF_OK;
 }
+
+// ---- Odometry::Compute, RANSAC strategy (Odometry/odometry.cpp:78-90) along a device-resident sequence --------------------------
+// Composition rule pose[k + 1] = T12[k] * pose[k]: cv::Mat's 4x4 float product (every element = four products summed left to right
+// in float), inherently sequential in k; 16 lanes own one element each and pass the pose along through shared memory.
+// Inlier flags: Frame::mvbOutlier starts all-true, SetInlier(m.trainIdx) clears it for the winner's inliers.
+namespace {
+__global__ void __launch_bounds__(32) compose_kernel(const orbf_ransac_result* __restrict__ res, int npairs, const float* __restrict__ pose0, float* __restrict__ poses)
+{
+    __shared__ float sP[16];
+    const int lane = threadIdx.x, r = (lane >> 2) & 3, c = lane & 3;
+    if (lane < 16) { sP[lane] = pose0[lane]; poses[lane] = pose0[lane]; }
+    __syncwarp();
+    for (int k = 0; k < npairs; ++k) {
+        const float* A = res[k].T12;
+        float t = 0.f;
+        if (lane < 16) {
+            t = __fmul_rn(A[4 * r], sP[c]);
+            t = __fadd_rn(t, __fmul_rn(A[4 * r + 1], sP[4 + c]));
+            t = __fadd_rn(t, __fmul_rn(A[4 * r + 2], sP[8 + c]));
+            t = __fadd_rn(t, __fmul_rn(A[4 * r + 3], sP[12 + c]));
+        }
+        __syncwarp();
+        if (lane < 16) { sP[lane] = t; poses[(size_t)(k + 1) * 16 + lane] = t; }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) inlier_flag_kernel(const orbf_ransac_result* __restrict__ res, const orbf_dmatch* __restrict__ inliers, int K, int npairs,
+    uint8_t* __restrict__ outlier /* [npairs + 1][K], preset to 1 */)
+{
+    const int p = blockIdx.x;
+    const int n = res[p].n_inliers;
+    for (int i = threadIdx.x; i < n; i += 256) outlier[(size_t)(p + 1) * K + inliers[(size_t)p * K + i].trainIdx] = 0;
+}
+}  // namespace
+
+int orbf_launch_compose(orbf_context* c, int npairs, const float* d_pose0, float* d_poses, uint8_t* d_outlier)
+{
+    compose_kernel<<<1, 32, 0, c->stream>>>(c->d_rres, npairs, d_pose0, d_poses);
+    ORBF_LAUNCH_CHECK(c);
+    if (d_outlier) {
+        ORBF_CUDA(c, cudaMemsetAsync(d_outlier, 1, (size_t)(npairs + 1) * c->K, c->stream));
+        if (npairs > 0) { inlier_flag_kernel<<<npairs, 256, 0, c->stream>>>(c->d_rres, c->d_inliers, c->K, npairs, d_outlier); ORBF_LAUNCH_CHECK(c); }
+    }
+    return ORBF_OK;
+}

@@ -25,6 +25,7 @@
  *   orbf_ransac_iterate               Ransac::Iterate(Frame*,Frame*,m12)          Odometry/ransac.cpp:155-267
  *   orbf_ransac_pairs                 Odometry::Compute -> Ransac::Iterate, batched   Odometry/odometry.cpp:48
  *   orbf_kabsch                       Kabsch::Compute                             Odometry/kabsch.cpp:14-57
+ *   orbf_compose_trajectory           Odometry::Compute (RANSAC): composition rule + SetInlier   Odometry/odometry.cpp:78-90
  *   orbf_kfdb_*                       keyframe descriptor storage of Core/keyframedatabase (config 5 many-to-many matching)
  *   orbf_adaptive_detect              Extractor(FAST, ., ADAPTIVE): VideoGridAdaptedFeatureDetector over VideoDynamicAdaptedFeatureDetector
  *                                     over DetectorAdjuster(FAST)  Features/extractor.cpp:52-77, videogridadaptedfeaturedetector.cpp:52-84,
@@ -227,6 +228,11 @@ int orbf_ransac_pairs(orbf_context* ctx, int32_t npairs, const orbf_ransac_confi
 int orbf_download_ransac(orbf_context* ctx, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap);
 int orbf_download_ransac_summary(orbf_context* ctx, int32_t npairs, orbf_ransac_result* out /* [npairs] */);
 int orbf_kabsch(orbf_context* ctx, const float* setA, const float* setB, int32_t n, float* T16);
+/* Odometry::Compute, RANSAC strategy (Odometry/odometry.cpp:78-90) for the npairs consecutive pairs last solved by orbf_ransac_pairs /
+ * orbf_track_sequence: poses[0] = pose0 (row-major 4x4, NULL = identity), poses[k + 1] = T12[k] * poses[k] with cv::Mat's float product;
+ * outlier (may be NULL) = [npairs + 1][keypoint capacity] bytes, Frame::mvbOutlier after SetInlier(m.trainIdx) for the pair's inliers
+ * (row 0, the first frame, stays all 1).                                                                              */
+int orbf_compose_trajectory(orbf_context* ctx, int32_t npairs, const float* pose0, float* poses /* [(npairs + 1) * 16] */, uint8_t* outlier);
 
 /* ---- keyframe descriptor store (Core/keyframedatabase, BASELINE config 5) --------------------- */
 /* Copies the descriptors of frame slot `slot` into keyframe entry `kf` of the device-resident store

@@ -529,3 +529,25 @@ int orc_kabsch(const float* A, const float* B, int n, float* T)
 }
 
 }  // extern "C"
+
+// ---- Odometry::Compute, RANSAC strategy: composition rule + inlier flags (Odometry/odometry.cpp:78-90), SURVEY.md §8f rank 3 ----
+// pose[k + 1] = T12[k] * pose[k] as cv::Mat evaluates a 4x4 * 4x4 float product (cv::gemm's small-matrix path: every element is
+// the four products summed left to right in float; pinned against cv2.gemm in tests/test_trajectory.py), sequentially along
+// the sequence.  outlier[k + 1][j] starts true (Frame::mvbOutlier) and is cleared for every inlier's trainIdx (SetInlier).
+int orc_compose_trajectory(const float* T12 /* [npairs][16] */, int npairs, const float* pose0 /* 16 */, float* poses /* [npairs + 1][16] */)
+{
+    if (npairs < 0 || !pose0 || !poses || (npairs > 0 && !T12)) return ORC_ERR_ARG;
+    for (int i = 0; i < 16; ++i) poses[i] = pose0[i];
+    for (int k = 0; k < npairs; ++k) {
+        const float* A = T12 + (size_t)k * 16; const float* B = poses + (size_t)k * 16; float* D = poses + (size_t)(k + 1) * 16;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                float t = A[4 * r] * B[c];
+                t = t + A[4 * r + 1] * B[4 + c];
+                t = t + A[4 * r + 2] * B[8 + c];
+                t = t + A[4 * r + 3] * B[12 + c];
+                D[4 * r + c] = t;
+            }
+    }
+    return ORC_OK;
+}

@@ -315,6 +315,15 @@ def bow_match(words1, off1, idx1, desc1, words2, off2, idx2, desc2, nn_ratio=0.6
     return out[:n.value].copy()
 
 
+def compose_trajectory(T12, pose0=None):
+    """pose[k+1] = T12[k] * pose[k] (Odometry/odometry.cpp:82-84) for a whole sequence: [npairs + 1, 4, 4]."""
+    T12 = np.ascontiguousarray(T12, np.float32).reshape(-1, 16)
+    pose0 = np.eye(4, dtype=np.float32) if pose0 is None else np.ascontiguousarray(pose0, np.float32)
+    out = np.zeros((len(T12) + 1, 16), np.float32)
+    _chk(lib().orc_compose_trajectory(_p(T12) if len(T12) else None, len(T12), _p(pose0.reshape(16)), _p(out)), "compose_trajectory")
+    return out.reshape(-1, 4, 4)
+
+
 def knn2(q, t, speed=False):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     nq, nt = len(q), len(t)

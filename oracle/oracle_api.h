@@ -75,6 +75,8 @@ int orc_fuse_search(const float* Rcw, const float* tcw, float fx, float fy, floa
     const uint8_t* lm_valid, int n_landmarks, float radius, double th_low, int* best_idx, int* best_dist);
 int orc_bow_match(const int* words1, const int* off1, const int* idx1, int nw1, const uint8_t* desc1, const int* words2, const int* off2, const int* idx2,
     int nw2, const uint8_t* desc2, float nn_ratio, double th_low, orc_dmatch* out, int cap, int* n_out);
+/* Odometry::Compute composition rule (Odometry/odometry.cpp:82-84) along a sequence */
+int orc_compose_trajectory(const float* T12, int npairs, const float* pose0, float* poses);
 /* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) */
 int orc_projection_match(const float* kp_x, const float* kp_y, const int* kp_octave, const uint8_t* desc, int n_feat, const uint8_t* lm_desc,
     const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int n_landmarks, const uint8_t* feat_taken, float radius, float nn_ratio,
