@@ -327,6 +327,14 @@ class Context:
                   "compose_trajectory")
         return poses.reshape(-1, 4, 4), flags
 
+    def undistort_points(self, xy, fx, fy, cx, cy, dist):
+        """Frame::UndistortKeyPoints (Core/frame.cpp:286-313): cv::undistortPoints(pts, pts, K, dist, Mat(), K); dist = (k1, k2, p1, p2, k3)."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); dist = np.ascontiguousarray(dist, np.float32).reshape(5)
+        out = np.zeros_like(xy)
+        self._chk(lib().orbf_undistort_points(self._h, _p(xy) if len(xy) else None, len(xy), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                              _p(dist), _p(out) if len(xy) else None), "undistort_points")
+        return out
+
     def fuse_search(self, Rcw, tcw, camera, lm_pos, lm_desc, lm_valid, slot=-1, kp_x=None, kp_y=None, u_right=None, desc=None, radius=3.0, th_low=50):
         """Matcher::Fuse, projection + windowed search (Features/matcher.cpp:212-296): (best feature or -1, its distance or -1) per landmark.
         camera = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY)."""

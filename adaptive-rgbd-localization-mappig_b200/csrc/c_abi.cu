@@ -610,6 +610,21 @@ extern "C" int orbf_compose_trajectory(orbf_context* c, int32_t npairs, const fl
     return ORBF_OK;
 }
 
+extern "C" int orbf_undistort_points(orbf_context* c, const float* xy, int32_t n, float fx, float fy, float cx, float cy, const float* dist, float* out)
+{
+    CTX_ENTER(c);
+    if (n < 0 || !dist || (n > 0 && (!xy || !out))) return ORBF_ERR_ARG;
+    if (n == 0) return ORBF_OK;
+    Scratch sc;
+    const size_t oIn = sc.take((size_t)n * 8), oOut = sc.take((size_t)n * 8);
+    SC_CUDA(sc.alloc());
+    SC_H2D(oIn, xy, (size_t)n * 8);
+    TRY(orbf_launch_undistort(c, sc.at<float>(oIn), n, fx, fy, cx, cy, dist, sc.at<float>(oOut)));
+    SC_CUDA(cudaMemcpyAsync(out, sc.at<float>(oOut), (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
 extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
     int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
     const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches)

@@ -197,6 +197,7 @@ struct MatchSet {
 };
 int orbf_launch_knn2(orbf_context* ctx, const MatchSet& ms, int npairs, bool cross);
 int orbf_launch_distinctive(orbf_context* ctx, const uint8_t* d_desc, const int* d_offsets, int nLandmarks, int* d_best, int* d_median);
+int orbf_launch_undistort(orbf_context* ctx, const float* d_xy, int n, float fx, float fy, float cx, float cy, const float* dist5, float* d_out);
 int orbf_launch_compose(orbf_context* ctx, int npairs, const float* d_pose0, float* d_poses, uint8_t* d_outlier);
 int orbf_launch_fuse_search(orbf_context* ctx, const float* Rcw, const float* tcw, const float* camera, const float* d_kpx, const float* d_kpy, const float* d_uright,
     const uint8_t* d_desc, int nFeat, const float* d_lmPos, const uint8_t* d_lmDesc, const uint8_t* d_lmValid, int nLm, float radius, int thLow, int* d_bestIdx,

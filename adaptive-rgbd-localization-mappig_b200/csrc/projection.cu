@@ -229,6 +229,33 @@ __global__ void __launch_bounds__(256) bow_emit_kernel(const int* __restrict__ i
     if (threadIdx.x == 0) *nOut = sBase;
 }
 
+
+// ---- Frame::UndistortKeyPoints (Core/frame.cpp:286-313): cv::undistortPoints(pts, pts, K, dist, Mat(), K) --------------------------
+// cvUndistortPointsInternal with the default criteria (5 fixed iterations), every operation in double in OpenCV's order (the
+// library is compiled with -fmad=false, so nothing contracts); thread per point.
+struct UndistortParams { double fx, fy, cx, cy, k1, k2, p1, p2, k3; };
+
+__global__ void __launch_bounds__(128) undistort_kernel(UndistortParams U, const float* __restrict__ xy, int n, float* __restrict__ out)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const double px = xy[2 * i], py = xy[2 * i + 1], ifx = 1.0 / U.fx, ify = 1.0 / U.fy;
+    double x = (px - U.cx) * ifx, y = (py - U.cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((U.k3 * r2 + U.k2) * r2 + U.k1) * r2);
+        if (icdist < 0) { x = (px - U.cx) * ifx; y = (py - U.cy) * ify; break; }
+        const double deltaX = 2 * U.p1 * x * y + U.p2 * (r2 + 2 * x * x) + 0.0 * r2 + 0.0 * r2 * r2;
+        const double deltaY = U.p1 * (r2 + 2 * y * y) + 2 * U.p2 * x * y + 0.0 * r2 + 0.0 * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = U.fx * x + 0.0 * y + U.cx, yy = 0.0 * x + U.fy * y + U.cy, ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
+    out[2 * i] = (float)(xx * ww);
+    out[2 * i + 1] = (float)(yy * ww);
+}
+
 }  // namespace
 
 int orbf_launch_projection_match(orbf_context* c, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat, const uint8_t* d_lmDesc,
@@ -269,6 +296,15 @@ int orbf_launch_bow_match(orbf_context* c, const int* d_words1, const int* d_off
         d_entryTrain, d_entryDist, d_firstUser);
     ORBF_LAUNCH_CHECK(c);
     bow_emit_kernel<<<1, 256, 0, c->stream>>>(d_idx1, d_entryTrain, d_entryDist, d_firstUser, nEntries, d_out, d_nOut);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+int orbf_launch_undistort(orbf_context* c, const float* d_xy, int n, float fx, float fy, float cx, float cy, const float* dist5, float* d_out)
+{
+    if (n <= 0) return ORBF_OK;
+    UndistortParams U{(double)fx, (double)fy, (double)cx, (double)cy, (double)dist5[0], (double)dist5[1], (double)dist5[2], (double)dist5[3], (double)dist5[4]};
+    undistort_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(U, d_xy, n, d_out);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }

@@ -16,6 +16,7 @@
  *   orbf_knn2 / orbf_knn_match        cv::BFMatcher::knnMatch(k=2) + ratio test in Matcher::KnnMatch   Features/matcher.cpp:55-66 (23-35)
  *   orbf_descriptor_distance          Matcher::DescriptorDistance                 Features/matcher.cpp:355-358
  *   orbf_distinctive_descriptors      Landmark::ComputeDistinctiveDescriptors     Core/landmark.cpp:219-273
+ *   orbf_undistort_points             Frame::UndistortKeyPoints / ComputeImageBounds (cv::undistortPoints)   Core/frame.cpp:286-343
  *   orbf_projection_match             Matcher::ProjectionMatch + Frame::GetFeaturesInArea   Features/matcher.cpp:90-143, Core/frame.cpp:258-274
  *   orbf_fuse_search                  Matcher::Fuse, projection + windowed search   Features/matcher.cpp:212-296
  *   orbf_bow_match                    Matcher::BoWMatch                           Features/matcher.cpp:145-209
@@ -181,6 +182,10 @@ int orbf_descriptor_distance(const uint8_t* a, const uint8_t* b, int32_t nbytes,
  * Hamming distance to the others (first wins ties, -1 without observations); median[l] optional (may be NULL).          */
 int orbf_distinctive_descriptors(orbf_context* ctx, const uint8_t* desc, const int32_t* offsets, int32_t n_landmarks, int32_t* best,
     int32_t* median);
+/* Frame::UndistortKeyPoints (Core/frame.cpp:286-313): cv::undistortPoints(pts, pts, K, dist, Mat(), K) with OpenCV's default 5 iterations;
+ * xy / out = n interleaved (x, y) floats (may alias), dist = {k1, k2, p1, p2, k3}.  The same call on the four image corners gives
+ * ComputeImageBounds (frame.cpp:320-343).  The extraction entry points assume k1 == 0 (mvKeysUn = mvKeys, frame.cpp:288-291).      */
+int orbf_undistort_points(orbf_context* ctx, const float* xy, int32_t n, float fx, float fy, float cx, float cy, const float* dist, float* out);
 /* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) for one frame: landmarks projected into the frame are matched, in order,
  * to the features inside the square window |dx| < radius && |dy| < radius; best <= th_high, and rejected when best and second best
  * share an octave and best > nn_ratio * second; a feature given to a landmark with Observations() > 0 is skipped by later landmarks.

@@ -278,3 +278,32 @@ int orc_bow_match(const int* words1, const int* off1, const int* idx1, int nw1, 
     if (out) std::copy(res.begin(), res.end(), out);
     return ORC_OK;
 }
+
+// ---- Frame::UndistortKeyPoints (Core/frame.cpp:286-313) = cv::undistortPoints(pts, pts, K, dist, Mat(), K), SURVEY.md §8f rank 2 ---
+// OpenCV's cvUndistortPointsInternal with its default criteria (5 fixed iterations, no epsilon test), all in double: normalise,
+// iterate x = (x0 - deltaX) * icdist with the radial (k1 k2 k3) and tangential (p1 p2) terms, re-project with the same camera
+// matrix, round to float.  dist = {k1, k2, p1, p2, k3}.  Pinned against cv2.undistortPoints in tests/test_undistort.py.
+int orc_undistort_points(const float* xy /* n x 2 */, int n, float fx, float fy, float cx, float cy, const float* dist /* 5 */, float* out /* n x 2 */)
+{
+    if (n < 0 || !dist || (n > 0 && (!xy || !out))) return ORC_ERR_ARG;
+    const double k0 = dist[0], k1 = dist[1], p1 = dist[2], p2 = dist[3], k4 = dist[4];
+    const double dfx = fx, dfy = fy, dcx = cx, dcy = cy, ifx = 1.0 / dfx, ify = 1.0 / dfy;
+    for (int i = 0; i < n; ++i) {
+        const double px = xy[2 * i], py = xy[2 * i + 1];
+        double x = (px - dcx) * ifx, y = (py - dcy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+            if (icdist < 0) { x = (px - dcx) * ifx; y = (py - dcy) * ify; break; }
+            const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0.0 * r2 + 0.0 * r2 * r2;
+            const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0.0 * r2 + 0.0 * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = dfx * x + 0.0 * y + dcx, yy = 0.0 * x + dfy * y + dcy, ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+    return ORC_OK;
+}

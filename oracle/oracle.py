@@ -324,6 +324,15 @@ def compose_trajectory(T12, pose0=None):
     return out.reshape(-1, 4, 4)
 
 
+def undistort_points(xy, fx, fy, cx, cy, dist):
+    """cv::undistortPoints(pts, pts, K, dist, Mat(), K) (Core/frame.cpp:302), dist = (k1, k2, p1, p2, k3)."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); dist = np.ascontiguousarray(dist, np.float32).reshape(5)
+    out = np.zeros_like(xy)
+    _chk(lib().orc_undistort_points(_p(xy) if len(xy) else None, len(xy), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(dist),
+                                    _p(out) if len(xy) else None), "undistort_points")
+    return out
+
+
 def knn2(q, t, speed=False):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     nq, nt = len(q), len(t)

@@ -77,6 +77,8 @@ int orc_bow_match(const int* words1, const int* off1, const int* idx1, int nw1, 
     int nw2, const uint8_t* desc2, float nn_ratio, double th_low, orc_dmatch* out, int cap, int* n_out);
 /* Odometry::Compute composition rule (Odometry/odometry.cpp:82-84) along a sequence */
 int orc_compose_trajectory(const float* T12, int npairs, const float* pose0, float* poses);
+/* Frame::UndistortKeyPoints (Core/frame.cpp:286-313): cv::undistortPoints with P = K, dist = {k1, k2, p1, p2, k3} */
+int orc_undistort_points(const float* xy, int n, float fx, float fy, float cx, float cy, const float* dist, float* out);
 /* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) */
 int orc_projection_match(const float* kp_x, const float* kp_y, const int* kp_octave, const uint8_t* desc, int n_feat, const uint8_t* lm_desc,
     const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int n_landmarks, const uint8_t* feat_taken, float radius, float nn_ratio,

@@ -1,0 +1,37 @@
+"""Frame::UndistortKeyPoints / ComputeImageBounds (reference Core/frame.cpp:286-343): cv::undistortPoints with
+P = K.  The oracle restates OpenCV's cvUndistortPointsInternal and is pinned bit-exactly against cv2.undistortPoints; the CUDA kernel
+is compared bit-exactly with the oracle."""
+import numpy as np
+import pytest
+
+FX, FY, CX, CY = 517.3, 516.5, 318.6, 255.3                                  # TUM FR1 (common.h:35-38)
+DISTS = [np.array([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32),   # TUM FR1 distortion
+         np.array([0.2312, -0.7849, -0.0033, -0.0001, 0.9172], np.float32),  # TUM FR2
+         np.array([-0.3, 0.1, 0.001, -0.002, 0.0], np.float32)]
+
+
+def _points(seed, n=4000):
+    rng = np.random.default_rng(seed)
+    pts = np.stack([rng.uniform(-5, 645, n), rng.uniform(-5, 485, n)], 1).astype(np.float32)
+    pts[:4] = [[0, 0], [640, 0], [0, 480], [640, 480]]                         # the ComputeImageBounds corners
+    return pts
+
+
+@pytest.mark.parametrize("k", range(len(DISTS)))
+def test_oracle_is_cv2_undistort_points(orc, k):
+    import cv2
+    pts = _points(k)
+    K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1]], np.float32)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, DISTS[k], None, K).reshape(-1, 2)
+    got = orc.undistort_points(pts, FX, FY, CX, CY, DISTS[k])
+    assert np.array_equal(got, ref)
+    assert len(orc.undistort_points(pts[:0], FX, FY, CX, CY, DISTS[k])) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", range(len(DISTS)))
+def test_cuda_matches_oracle(ob, orc, k):
+    pts = _points(10 + k, 20000)
+    ctx = ob.Context(max_frames=2)
+    assert np.array_equal(ctx.undistort_points(pts, FX, FY, CX, CY, DISTS[k]), orc.undistort_points(pts, FX, FY, CX, CY, DISTS[k]))
+    assert len(ctx.undistort_points(pts[:0], FX, FY, CX, CY, DISTS[k])) == 0
