@@ -1,0 +1,61 @@
+"""TUM association / trajectory files (reference Utils/utils.cpp:16-38, System/tracking.cpp:544-580)."""
+import importlib.util
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+spec = importlib.util.spec_from_file_location("orbfront_tum", ROOT / "adaptive-rgbd-localization-mappig_b200" / "tum.py")
+tum = importlib.util.module_from_spec(spec); spec.loader.exec_module(tum)
+
+
+def test_associations_roundtrip(tmp_path):
+    p = tmp_path / "assoc.txt"
+    p.write_text("1305031102.175304 rgb/1305031102.175304.png 1305031102.160407 depth/1305031102.160407.png\n\n"
+                 "1305031102.211214 rgb/1305031102.211214.png 1305031102.226738 depth/1305031102.226738.png\n")
+    ts, rgb, dep = tum.load_associations(p)
+    assert ts.tolist() == [1305031102.175304, 1305031102.211214]
+    assert rgb == ["rgb/1305031102.175304.png", "rgb/1305031102.211214.png"] and dep[1] == "depth/1305031102.226738.png"
+
+
+def _rot(rng):
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def test_trajectory_format_and_values(tmp_path):
+    import cv2
+    rng = np.random.default_rng(0)
+    poses = []
+    for _ in range(50):
+        T = np.eye(4, dtype=np.float32); T[:3, :3] = _rot(rng).astype(np.float32); T[:3, 3] = rng.normal(size=3).astype(np.float32)
+        poses.append(T)
+    ts = 1305031102.0 + np.arange(50) * 0.0333
+    p = tmp_path / "traj.txt"
+    tum.save_trajectory(p, ts, poses)
+    t2, xyz, q = tum.load_trajectory(p)
+    assert np.allclose(t2, ts, atol=1e-6)
+    for k, T in enumerate(poses):
+        Rwc = np.ascontiguousarray(T[:3, :3].T)
+        twc = cv2.gemm(Rwc, np.ascontiguousarray(T[:3, 3:4]), -1.0, None, 0.0)[:, 0]          # -Rwc * tcw as cv::Mat evaluates it
+        assert np.array_equal(np.float32(xyz[k]), np.float32([float(f"{v:.9f}") for v in twc]))
+        # the quaternion rotates like Rwc (sign-free check) and has unit norm
+        x, y, z, w = q[k]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.allclose(R, Rwc, atol=2e-6) and abs(np.linalg.norm(q[k]) - 1) < 1e-6
+    line = p.read_text().splitlines()[0].split()
+    assert len(line) == 8 and len(line[0].split(".")[1]) == 6 and all(len(v.split(".")[1]) == 9 for v in line[1:])
+
+
+def test_quaternion_branches():
+    # trace <= 0 branches of Eigen's conversion: rotations by pi about each axis
+    for axis in range(3):
+        R = -np.eye(3); R[axis, axis] = 1
+        q = tum.quaternion_from_rotation(R)
+        want = np.zeros(4, np.float32); want[axis] = 1
+        assert np.array_equal(np.abs(q), want)
