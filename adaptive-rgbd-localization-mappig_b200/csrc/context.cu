@@ -476,7 +476,7 @@ int orbf_refresh_maps(orbf_context* c)
         for (int l = 1; l < c->L; ++l) {
             ENC(c->tmFast[l], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, c->fastBW[l], c->fastBH[l]);
             ENC(c->tmBlur[l], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, blurBW, blurBH);
-            ENC(c->tmPatchRaw[l], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, ORBF_PATCH_BW, ORBF_PATCH_BH);
+            ENC(c->tmPatchRaw[l], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, ORBF_RAW_BW, ORBF_RAW_BH);
             if (l + 1 < c->L)
                 ENC(c->tmResize[l + 1], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, c->rsBW[l + 1], c->rsBH[l + 1]);
         }
@@ -488,7 +488,7 @@ int orbf_refresh_maps(orbf_context* c)
         if (!c->cur_gray) return ORBF_ERR_STATE;
         ENC(c->tmFast[0], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, c->fastBW[0], c->fastBH[0]);
         ENC(c->tmBlur[0], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, blurBW, blurBH);
-        ENC(c->tmPatchRaw[0], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, ORBF_PATCH_BW, ORBF_PATCH_BH);
+        ENC(c->tmPatchRaw[0], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, ORBF_RAW_BW, ORBF_RAW_BH);
         if (c->L > 1) ENC(c->tmResize[1], c->cur_gray, 0, c->cur_n, c->cur_grayPitch, c->cur_grayFrameStride, c->rsBW[1], c->rsBH[1]);
         c->tm0Base = c->cur_gray; c->tm0Pitch = c->cur_grayPitch; c->tm0FrameStride = c->cur_grayFrameStride; c->tm0Frames = c->cur_n;
     }

@@ -78,13 +78,23 @@ __device__ __forceinline__ KpLoc locate(const DescParams& P, const int* lc, int 
     return k;
 }
 
+constexpr int DS_RAW_BYTES = (ORBF_RAW_BW * ORBF_RAW_BH + 127) / 128 * 128;
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)          // sum of u8(a) * s8(b) + c
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_constant__ DescParams P)
 {
     __shared__ float4 sPat[256];
     __shared__ uint32_t sCoef[16];
-    // per warp, double buffered: the keypoint's 64 x 39 windows of the raw level (orientation) and the blurred level
-    // (descriptor), fetched by two TMA box loads — ~80 sectors per window instead of ~450 scattered byte gathers through L1
-    __shared__ __align__(128) uint8_t sWin[DS_WARPS][2][2][DS_WIN_BYTES];
+    // per warp, double buffered: the keypoint's 31 x 48 window of the raw level (orientation disc) and its 39 x 64 window of the
+    // blurred level (descriptor), fetched by two TMA box loads — ~70 sectors instead of ~450 scattered byte gathers through L1
+    __shared__ __align__(128) uint8_t sRaw[DS_WARPS][2][DS_RAW_BYTES];
+    __shared__ __align__(128) uint8_t sBlur[DS_WARPS][2][DS_WIN_BYTES];
     __shared__ __align__(8) uint64_t sBar[DS_WARPS][2];
     for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) sPat[i] = g_patF[i];
     if (threadIdx.x < 16) sCoef[threadIdx.x] = g_icCoef[threadIdx.x];
@@ -94,60 +104,102 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     const int slot = P.slot0 + blockIdx.y;
     const int* lc = P.lkpCount + slot * ORBF_MAX_LEVELS;
     const int base = (blockIdx.x * DS_WARPS + warp) * DS_KPW;
+    // lanes 0..7 locate the warp's 8 keypoints once; each iteration takes its keypoint by shuffle
     int total;
-    KpLoc cur = locate(P, lc, slot, base, total);
+    const KpLoc mine = locate(P, lc, slot, base + (lane & (DS_KPW - 1)), total);
     if (base == 0 && lane == 0) P.count[slot] = total;
-    auto fetch = [&](const KpLoc& k, int buf) {       // lane 0 only
-        const int xs = (k.x - ORBF_EDGE) & ~15;       // TMA boxes of bytes start on 16-byte boundaries
-        mbar_expect_tx(&sBar[warp][buf], 2 * ORBF_PATCH_BW * ORBF_PATCH_BH);
-        tma_load_3d(sWin[warp][buf][0], &P.mapRaw[k.level], xs, k.y - ORBF_EDGE, k.level == 0 ? slot - P.z0 : slot, &sBar[warp][buf]);
-        tma_load_3d(sWin[warp][buf][1], &P.mapBlur[k.level], xs, k.y - ORBF_EDGE, slot, &sBar[warp][buf]);
+    auto take = [&](int it) {
+        KpLoc k;
+        k.level = __shfl_sync(0xffffffffu, mine.level, it); k.x = __shfl_sync(0xffffffffu, mine.x, it);
+        k.y = __shfl_sync(0xffffffffu, mine.y, it); k.score = __shfl_sync(0xffffffffu, mine.score, it);
+        return k;
     };
+    // orientation moments, lane = disc row v = lane - 15 (lane 31 idles): the row's 31 bytes against two constant coefficient
+    // words per 4 columns — u (signed) and 1, both zero outside |u| <= umax[|v|] — so a row costs 16 DP4A
+    uint32_t coefU[8], coefM[8];
+    {
+        const int v = lane - ORBF_HALF_PATCH, um = lane < 31 ? (int)sCoef[abs(v)] : -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t cu = 0, cm = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int u = 4 * k + j - ORBF_HALF_PATCH;
+                if (4 * k + j <= 2 * ORBF_HALF_PATCH && abs(u) <= um) { cu |= ((uint32_t)u & 0xFFu) << (8 * j); cm |= 1u << (8 * j); }
+            }
+            coefU[k] = cu; coefM[k] = cm;
+        }
+    }
+    auto fetch = [&](const KpLoc& k, int buf) {       // lane 0 only
+        // TMA boxes of bytes start on 16-byte boundaries
+        mbar_expect_tx(&sBar[warp][buf], ORBF_RAW_BW * ORBF_RAW_BH + ORBF_PATCH_BW * ORBF_PATCH_BH);
+        tma_load_3d(sRaw[warp][buf], &P.mapRaw[k.level], (k.x - ORBF_HALF_PATCH) & ~15, k.y - ORBF_HALF_PATCH, k.level == 0 ? slot - P.z0 : slot, &sBar[warp][buf]);
+        tma_load_3d(sBlur[warp][buf], &P.mapBlur[k.level], (k.x - ORBF_EDGE) & ~15, k.y - ORBF_EDGE, slot, &sBar[warp][buf]);
+    };
+    KpLoc cur = take(0);
     if (cur.level >= 0 && lane == 0) fetch(cur, 0);
     const float kMagic = 12582912.f;
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    // the record of keypoint k (lane 0) is written at the start of iteration k + 1, when its depth sample has long arrived
+    long long pendO = -1; float pendX = 0.f, pendY = 0.f; unsigned short pendRaw = 0; bool pendHave = false;
+    auto flush = [&]() {
+        if (lane == 0 && pendO >= 0) {
+            float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
+            if (pendHave) {
+                const float z = __fmul_rn((float)pendRaw, P.depthFactor);
+                if (z > 0) {
+                    ur = __fsub_rn(pendX, __fdiv_rn(P.mbf, z));
+                    X = __fmul_rn(__fmul_rn(__fsub_rn(pendX, P.cx), z), P.invfx);
+                    Y = __fmul_rn(__fmul_rn(__fsub_rn(pendY, P.cy), z), P.invfy);
+                    Z = z;
+                }
+            }
+            P.ptx[pendO] = X; P.pty[pendO] = Y; P.ptz[pendO] = Z; P.uright[pendO] = ur;
+        }
+    };
 #pragma unroll 1
     for (int it = 0; it < DS_KPW && cur.level >= 0; ++it) {
         const int i = base + it, buf = it & 1;
         KpLoc nxt; nxt.level = -1;
-        if (it + 1 < DS_KPW) { int t2; nxt = locate(P, lc, slot, i + 1, t2); }
+        if (it + 1 < DS_KPW) nxt = take(it + 1);
         if (nxt.level >= 0 && lane == 0) fetch(nxt, buf ^ 1);
         __syncwarp();
-        mbar_wait(&sBar[warp][buf], (it >> 1) & 1);
         const int level = cur.level, x = cur.x, y = cur.y;
-        const int cx0 = x - ((x - ORBF_EDGE) & ~15);                      // window column of the keypoint
         // depth sample of the keypoint (Core/frame.cpp:155), requested first: when the plane lives in pinned host memory the
-        // read crosses PCIe (~2 us) and completes behind the orientation / descriptor work below
+        // read crosses PCIe (~2 us) and completes behind the orientation / descriptor work
         float kfx = (float)x, kfy = (float)y;
         if (level != 0) { kfx = __fmul_rn(kfx, P.scale[level]); kfy = __fmul_rn(kfy, P.scale[level]); }
-        unsigned short rawDepth = 0;
-        bool haveDepth = false;
+        flush();
+        const long long o = (long long)slot * P.K + i;
+        pendO = o; pendX = kfx; pendY = kfy; pendHave = false; pendRaw = 0;
         if (lane == 0 && P.depth) {
             const int ui = (int)kfx, vi = (int)kfy;     // float -> int truncation of the (distorted) keypoint
             if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
-                rawDepth = __ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui);
-                haveDepth = true;
+                pendRaw = __ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui);
+                pendHave = true;
             }
         }
-        // ---- orientation: lane = patch column u = lane - 15; the disc spans rows |v| <= umax[|u|] in column u -------------
-        int m10 = 0, m01 = 0;
+        mbar_wait(&sBar[warp][buf], (it >> 1) & 1);
+        // ---- orientation -----------------------------------------------------------------------------------------------------
+        int m10, m01;
         {
-            const int u = lane - ORBF_HALF_PATCH;
-            const int dv = lane < 31 ? (int)(sCoef[min(abs(u), ORBF_HALF_PATCH)]) : -1;
-            const uint8_t* p = sWin[warp][buf][0] + (ORBF_EDGE - ORBF_HALF_PATCH) * ORBF_PATCH_BW + cx0 + u;
-            int colSum = 0;
+            const int off = (x - ORBF_HALF_PATCH) & 15;                   // column of u = -15 inside the raw window
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(sRaw[warp][buf] + min(lane, ORBF_RAW_BH - 1) * ORBF_RAW_BW) + (off >> 2);
+            const int sh = (off & 3) * 8;
+            uint32_t w[9];
 #pragma unroll
-            for (int v = -ORBF_HALF_PATCH; v <= ORBF_HALF_PATCH; ++v) {
-                if ((v < 0 ? -v : v) <= dv) {
-                    const int val = p[(v + ORBF_HALF_PATCH) * ORBF_PATCH_BW];
-                    colSum += val;
-                    m01 += v * val;
-                }
+            for (int k = 0; k < 9; ++k) w[k] = row[k];                    // (off >> 2) + 9 <= 12 words: inside the row
+            int su = 0, sm = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t bytes = __funnelshift_r(w[k], w[k + 1], sh);
+                su = dp4a_us(bytes, coefU[k], su);
+                sm = (int)__dp4a(bytes, coefM[k], (uint32_t)sm);
             }
-            m10 = u * colSum;
+            m10 = su; m01 = (lane - ORBF_HALF_PATCH) * sm;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o2); m01 += __shfl_xor_sync(0xffffffffu, m01, o2); }
         const float angle = fast_atan2_deg((float)m01, (float)m10);
         // ---- steered BRIEF: (x*b + y*a, x*a - y*b) with separate mul / add, cvRound = round-half-even via the 1.5 * 2^23 trick
         // (FADD on the FMA pipe + IADD instead of F2I on the quarter-rate XU pipe; |v| <= 19 << 2^22) ------------------------
@@ -155,7 +207,8 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         double sn, cs;
         sincos((double)ar, &sn, &cs);
         const float a = (float)cs, b = (float)sn;
-        const uint8_t* cb = sWin[warp][buf][1] + ORBF_EDGE * ORBF_PATCH_BW + cx0;
+        const int cx0 = x - ((x - ORBF_EDGE) & ~15);                      // window column of the keypoint
+        const uint8_t* cb = sBlur[warp][buf] + ORBF_EDGE * ORBF_PATCH_BW + cx0;
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -167,28 +220,16 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
             const int t0 = cb[r0 * ORBF_PATCH_BW + c0], t1 = cb[r1 * ORBF_PATCH_BW + c1];
             val |= (t0 < t1) << k;
         }
-        const long long o = (long long)slot * P.K + i;
         P.desc[o * 32 + lane] = (uint8_t)val;
-        // ---- keypoint record + depth unprojection ------------------------------------------------------------------------
+        // ---- keypoint record (the 3D point follows when the depth sample is in, see flush) --------------------------------
         if (lane == 0) {
-            const float fx = kfx, fy = kfy;
-            P.kpx[o] = fx; P.kpy[o] = fy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
+            P.kpx[o] = kfx; P.kpy[o] = kfy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
             P.kpresp[o] = (float)cur.score; P.kpoct[o] = level; P.kplxy[o] = (uint32_t)x | ((uint32_t)y << 16);
-            float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
-            if (haveDepth) {
-                const float z = __fmul_rn((float)rawDepth, P.depthFactor);
-                if (z > 0) {
-                    ur = __fsub_rn(fx, __fdiv_rn(P.mbf, z));
-                    X = __fmul_rn(__fmul_rn(__fsub_rn(fx, P.cx), z), P.invfx);
-                    Y = __fmul_rn(__fmul_rn(__fsub_rn(fy, P.cy), z), P.invfy);
-                    Z = z;
-                }
-            }
-            P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;
         }
         __syncwarp();                                   // every lane is done with this buffer before it is refilled
         cur = nxt;
     }
+    flush();
 }
 
 __global__ void pack_aos_kernel(const float* kpx, const float* kpy, const float* kpsize, const float* kpangle, const float* kpresp,

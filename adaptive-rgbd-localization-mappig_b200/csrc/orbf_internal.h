@@ -23,6 +23,8 @@
 #define ORBF_MAX_SAMPLE 8
 #define ORBF_PATCH_BW 64      // describe.cu: TMA box of a keypoint window, (2 * 19 + 1) rows x 64 bytes
 #define ORBF_PATCH_BH 39
+#define ORBF_RAW_BW 48        // describe.cu: TMA box of the orientation disc, (2 * 15 + 1) rows x 48 bytes of the raw level
+#define ORBF_RAW_BH 31
 #define ORBF_MAX_WORKERS 4    // internal worker streams of the chunked pipeline (c_abi.cu)
 
 struct LevelView {
