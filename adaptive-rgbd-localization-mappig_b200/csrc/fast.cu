@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int sCount;
+    __shared__ int sCount, sCorner;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StripDesc sd = P.strips[blockIdx.x];
     const int slot = P.slot0 + blockIdx.y;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     __shared__ int sKept[FS_WARPS];
     __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
 
-    if (tid == 0) { mbar_init(&bar, 1); sCount = 0; }
+    if (tid == 0) { mbar_init(&bar, 1); sCount = 0; sCorner = 0; }
     if (tid < FS_WARPS) sKept[tid] = 0;
     if (tid <= FS_WARPS) sC0[tid] = tid < sd.nCells ? ax + P.cells[sd.firstCell + tid].x0 - sd.x0 : ax + W + (tid > sd.nCells ? 4096 : 0);
     __syncthreads();
@@ -134,28 +134,40 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     const int n = sCount;
     const uint8_t* org = tile + 3 * BW;
     uint8_t* sorg = score + BW;
-    // ---- 2. corner strength, two survivors per thread --------------------------------------------------------------
-    for (int i = tid; 2 * i < n; i += FS_THREADS) {
-        const int ea = list[2 * i], eb = list[min(2 * i + 1, n - 1)];
-        const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
-        const int sa = (int)(s & 0xFFFFu), sb = (int)(s >> 16);
-        if (sa > th) sorg[ea] = (uint8_t)(sa - 1);
-        if (sb > th) sorg[eb] = (uint8_t)(sb - 1);
+    // ---- 2. corner strength, two survivors per thread; the corners (44 % of the survivors) are compacted in place at the front
+    // of the list so that the NMS pass runs with full warps.  A round reads 2 * FS_THREADS entries before anything is appended,
+    // and the appends of round k stay below the entries consumed so far, so the only hazard is inside a round (the barrier).
+    for (int base = 0; base < n; base += 2 * FS_THREADS) {
+        const int ia = base + 2 * tid;
+        int ea = 0, eb = 0, sa = 0, sb = 0;
+        if (ia < n) {
+            ea = list[ia]; eb = list[min(ia + 1, n - 1)];
+            const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
+            sa = (int)(s & 0xFFFFu); sb = ia + 1 < n ? (int)(s >> 16) : 0;
+            if (sa > th) sorg[ea] = (uint8_t)(sa - 1);
+            if (sb > th) sorg[eb] = (uint8_t)(sb - 1);
+        }
+        __syncthreads();
+        const int na = sa > th, nb = sb > th;
+        if (na + nb) {
+            int pos = atomicAdd(&sCorner, na + nb);
+            if (na) list[pos++] = (uint16_t)ea;
+            if (nb) list[pos] = (uint16_t)eb;
+        }
     }
     __syncthreads();
-    // ---- 3. NMS over the survivor list, kept corners appended to their cell's list ----------------------------------
+    // ---- 3. NMS over the corner list, kept corners appended to their cell's list -------------------------------------
     {
+        const int nc = sCorner;
         const int b1 = sC0[1], b2 = sC0[2], b3 = sC0[3];
-        for (int i = tid; i < n; i += FS_THREADS) {
+        for (int i = tid; i < nc; i += FS_THREADS) {
             const int e = list[i];
             const int v = sorg[e];
-            if (v) {
-                const int row = e / BW, col = e - row * BW;
-                const int k = (col >= b1) + (col >= b2) + (col >= b3);
-                if (nms_keep(sorg + e, v, BW, col > sC0[k], col < sC0[k + 1] - 1)) {
-                    const int pos = atomicAdd(&sKept[k], 1);
-                    if (pos < keptCap) kept[k * keptCap + pos] = ((uint32_t)e << 8) | (uint32_t)v;
-                }
+            const int row = e / BW, col = e - row * BW;
+            const int k = (col >= b1) + (col >= b2) + (col >= b3);
+            if (nms_keep(sorg + e, v, BW, col > sC0[k], col < sC0[k + 1] - 1)) {
+                const int pos = atomicAdd(&sKept[k], 1);
+                if (pos < keptCap) kept[k * keptCap + pos] = ((uint32_t)e << 8) | (uint32_t)v;
             }
         }
     }
