@@ -874,9 +874,11 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
         cudaError_t e = cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hypSmem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac hyp smem attr", __FILE__, __LINE__);
     }
-    const int waveEnd[4] = { 8, 32, 96, iters };
+    // (a first wave of 2 covers the common case — on well-matched consecutive frames the loop ends after its first accepted
+    // hypothesis — and keeps that wave inside one residency of the GPU; every later wave is a few microseconds when nothing is left)
+    const int waveEnd[5] = { 2, 8, 32, 96, iters };
     int lo = 0;
-    for (int w = 0; w < 4 && lo < iters; ++w) {
+    for (int w = 0; w < 5 && lo < iters; ++w) {
         const int hi = std::min(waveEnd[w], iters);
         if (hi <= lo) continue;
         P.hypLo = lo; P.hypHi = hi;
