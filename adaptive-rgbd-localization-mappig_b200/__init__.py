@@ -386,7 +386,9 @@ class Context:
         return out
 
     # ---- RANSAC / Kabsch ----
-    def ransac_iterate(self, src_xyz, dst_xyz, m12, sample_table=None, **kw):
+    def ransac_iterate(self, src_xyz, dst_xyz, m12, sample_table=None, want_table=True, **kw):
+        """want_table=False leaves sample_table_out NULL: the library then draws the sample table lazily (first rows in
+        ransac_prepare, the rest only if the loop gets that far), as the batched paths do; the returned table is all -1."""
         cfg = default_ransac_config(**kw)
         src = np.ascontiguousarray(src_xyz, np.float32); dst = np.ascontiguousarray(dst_xyz, np.float32)
         m12 = np.ascontiguousarray(m12, DMATCH_DT)
@@ -395,7 +397,7 @@ class Context:
         good = np.zeros(max(len(m12), 1), DMATCH_DT); tab_out = np.full((cfg.iterations, cfg.sample_size), -1, np.int32)
         tab = None if sample_table is None else np.ascontiguousarray(sample_table, np.int32)
         self._chk(lib().orbf_ransac_iterate(self._h, C.byref(cfg), _p(src), len(src), _p(dst), len(dst), _p(m12), len(m12), _p(tab),
-                                            _p(inl), len(inl), C.byref(res), _p(hyp), _p(good), _p(tab_out)), "ransac_iterate")
+                                            _p(inl), len(inl), C.byref(res), _p(hyp), _p(good), _p(tab_out) if want_table else None), "ransac_iterate")
         return dict(ok=bool(res.ok), rmse=float(res.rmse), T12=np.array(res.T12, np.float32).reshape(4, 4),
                     inliers=inl[:res.n_inliers].copy(), n_good=res.n_good, real_iters=res.real_iters, valid_iters=res.valid_iters,
                     used_identity=bool(res.used_identity), depth_cov=float(res.depth_cov_used), hyp=hyp,

@@ -835,7 +835,7 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
     rs.sx = c->d_sxyz; rs.sy = c->d_sxyz + R; rs.sz = c->d_sxyz + 2 * (size_t)R;
     rs.tx = c->d_txyz; rs.ty = c->d_txyz + R; rs.tz = c->d_txyz + 2 * (size_t)R;
     rs.slotStride = 0; rs.pairs = nullptr; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount; rs.nsrc = nsrc; rs.ndst = ndst;
-    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, 0));
+    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, 0, /*fullTable=*/sample_table_out != nullptr));
     TRY(orbf_download_ransac(c, 0, out, inliers_out, cap));
     if (hyp_trace) ORBF_CUDA(c, cudaMemcpyAsync(hyp_trace, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
     if (good_sorted_out && out->n_good > 0)

@@ -224,4 +224,4 @@ int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int 
 // its prepare kernel and record ctx->evLatch; 1: wait for ctx->evLatch before scoring hypotheses.
 int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);
 int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, int latchMode);
+    const int* d_userSamples, int latchMode, bool fullTable = false);

@@ -37,6 +37,7 @@ struct RansacParams {
     orbf_hyp_trace* hyp; orbf_ransac_result* res; orbf_dmatch* inliers;
     double* depthCov;
     int K, iters, S;
+    int tabRows;              // sample-table rows ransac_prepare draws itself; ransac_table_kernel completes the table for the pairs that go on
     double covX, covY;
 };
 
@@ -165,7 +166,8 @@ __device__ bool rows_from_stream(const uint16_t* pid, int np, int S, int iters, 
     return row == iters;
 }
 
-__device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* tab, uint16_t* ids, int lane)
+// nRand = how many rand() values to buffer (a multiple of 2, <= RAND_BUF): a full 200 x 4 table needs ~860, its first rows a few dozen
+__device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* tab, uint16_t* ids, int lane, int nRand = RAND_BUF)
 {
     uint16_t* pid = ids + RAND_BUF;                 // [RAND_BUF / 2] min of each rand pair = the id SampleMatches draws
     uint32_t P = 0;
@@ -182,7 +184,7 @@ __device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* t
         }
     }
     const int base = 28 + lane % 3;
-    for (int blk = 0; (blk - 10) * 31 < RAND_BUF; ++blk) {
+    for (int blk = 0; (blk - 10) * 31 < nRand; ++blk) {
         uint32_t v = P;
 #pragma unroll
         for (int off = 3; off < 32; off <<= 1) {
@@ -197,9 +199,9 @@ __device__ bool warp_sample_table(uint32_t seed, int M, int S, int iters, int* t
         }
     }
     __syncwarp();
-    for (int k = lane; k < RAND_BUF / 2; k += 32) pid[k] = (uint16_t)min((int)ids[2 * k], (int)ids[2 * k + 1]);
+    for (int k = lane; k < nRand / 2; k += 32) pid[k] = (uint16_t)min((int)ids[2 * k], (int)ids[2 * k + 1]);
     __syncwarp();
-    return S <= 4 ? rows_from_stream<4>(pid, RAND_BUF / 2, S, iters, tab, lane) : rows_from_stream<8>(pid, RAND_BUF / 2, S, iters, tab, lane);
+    return S <= 4 ? rows_from_stream<4>(pid, nRand / 2, S, iters, tab, lane) : rows_from_stream<8>(pid, nRand / 2, S, iters, tab, lane);
 }
 
 __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams P)
@@ -252,13 +254,15 @@ __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams
     if (warp == 1) {
         if (!P.userSamples) {
             uint16_t* ids = reinterpret_cast<uint16_t*>(smem + (size_t)P.K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)));
+            // the first tabRows rows only (the loop rarely gets further); ransac_table_kernel draws the rest for pairs that go on
+            const int rows = P.tabRows, nRand = rows < P.iters ? min(RAND_BUF, 64 * rows) : RAND_BUF;
             bool done = false;
-            if (M >= P.S) done = warp_sample_table(P.cfg.seed + (uint32_t)pair, M, P.S, P.iters, tab, ids, lane);
+            if (M >= P.S) done = warp_sample_table(P.cfg.seed + (uint32_t)pair, M, P.S, rows, tab, ids, lane, nRand);
             if (!done && lane == 0) {
                 if (M >= P.S) {     // buffer exhausted (tiny M, many duplicate draws): scalar replay from the start
                     replay::GlibcRand g;
                     g.seed(P.cfg.seed + (uint32_t)pair);
-                    for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
+                    for (int k = 0; k < rows; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
                 } else for (int i = 0; i < P.iters * P.S; ++i) tab[i] = -1;
             }
         }
@@ -311,6 +315,24 @@ __global__ void __launch_bounds__(PR_THREADS) ransac_prepare_kernel(RansacParams
 }
 
 // depth covariance latch (quirk Q7: static local initialised by the first DepthCovariance() call of the process)
+// The whole sample table for the pairs whose loop is still running after the first tabRows hypotheses (one warp per pair; the
+// rows prepare already drew come out identical: same seed, same stream).
+__global__ void __launch_bounds__(32) ransac_table_kernel(RansacParams P)
+{
+    __shared__ uint16_t ids[RAND_BUF + RAND_BUF / 2];
+    const int pair = P.pair0 + blockIdx.x, lane = threadIdx.x;
+    if (P.state[pair].done) return;
+    const int M = P.goodCount[pair];
+    int* tab = P.samples + (long long)pair * P.iters * P.S;
+    bool done = false;
+    if (M >= P.S) done = warp_sample_table(P.cfg.seed + (uint32_t)pair, M, P.S, P.iters, tab, ids, lane);
+    if (!done && lane == 0 && M >= P.S) {
+        replay::GlibcRand g;
+        g.seed(P.cfg.seed + (uint32_t)pair);
+        for (int k = 0; k < P.iters; ++k) replay::sample_row(g, M, P.S, tab + (long long)k * P.S);
+    }
+}
+
 __global__ void ransac_latch_kernel(RansacParams P)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -838,7 +860,7 @@ int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
 }
 
 int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, int latchMode)
+    const int* d_userSamples, int latchMode, bool fullTable)
 {
     if (npairs <= 0) return ORBF_OK;
     {
@@ -851,6 +873,8 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
     P.depthCov = c->d_depthCov; P.K = c->K; P.iters = iters; P.S = S;
     P.state = reinterpret_cast<RState*>(c->d_rstate); P.hypLo = 0; P.hypHi = iters; P.pair0 = pair0;
+    constexpr int LAZY_ROWS = 8;                     // = the end of the second hypothesis wave
+    P.tabRows = (fullTable || d_userSamples) ? iters : std::min(iters, LAZY_ROWS);
     {   // raster covariances of ErrorFunction2 (ransac.cpp:352-359), host libm like the reference
         const double ax = 58.0 / 180.0 * M_PI, ay = 45.0 / 180.0 * M_PI;
         const double sx = 3 * tan(ax / 640), sy = 3 * tan(ay / 480);
@@ -881,6 +905,11 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     for (int w = 0; w < 5 && lo < iters; ++w) {
         const int hi = std::min(waveEnd[w], iters);
         if (hi <= lo) continue;
+        if (hi > P.tabRows && lo <= P.tabRows && P.tabRows < iters) {          // this wave reads rows prepare did not draw
+            ransac_table_kernel<<<npairs, 32, 0, c->stream>>>(P);
+            ORBF_LAUNCH_CHECK(c);
+            P.tabRows = iters;
+        }
         P.hypLo = lo; P.hypHi = hi;
         dim3 grid((hi - lo + HY_WARPS - 1) / HY_WARPS, npairs);
         ransac_hyp_kernel<<<grid, HY_WARPS * 32, hypSmem, c->stream>>>(P);

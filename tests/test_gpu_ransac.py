@@ -47,6 +47,20 @@ def test_iterate_matches_oracle(ctx, orc, seed, outliers):
         assert np.abs(r["T12"][:3, :3] - R).max() < 5e-3 and np.abs(r["T12"][:3, 3] - t).max() < 2e-2
 
 
+@pytest.mark.parametrize("seed,outliers", [(21, 0.6), (22, 0.75), (23, 1.0), (24, 0.3)])
+def test_lazy_sample_table_matches_oracle(ctx, orc, seed, outliers):
+    """The batched paths draw only the first sample-table rows up front and complete the table for the pairs whose loop gets past
+    them (ransac_table_kernel).  Hard inputs (the loop runs tens to all 200 iterations) through that path: same result as the
+    oracle, hypothesis by hypothesis."""
+    src, dst, m, _, _ = synth.rigid_pairs(seed=seed, outlier_frac=outliers)
+    g = ctx.ransac_iterate(src, dst, m, seed=seed, want_table=False)
+    r = orc.ransac_iterate(src, dst, m, seed=seed)
+    if outliers >= 0.6:
+        assert r["real_iters"] > 8, "case is meant to outlast the eagerly drawn rows"
+    g["sample_table"] = r["sample_table"]          # not returned on this path
+    _compare(g, r)
+
+
 def test_explicit_sample_table_and_depth_cov(ctx, orc):
     src, dst, m, _, _ = synth.rigid_pairs(seed=5)
     r0 = orc.ransac_iterate(src, dst, m, seed=1)
