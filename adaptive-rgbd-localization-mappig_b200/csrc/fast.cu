@@ -43,15 +43,15 @@ __device__ __forceinline__ bool nms_keep(const uint8_t* s, int v, int BW, bool l
     return k;
 }
 
-// One warp orders a cell's kept corners (key = tile offset << 8 | response; offsets are distinct) and writes them out.
-__device__ __forceinline__ void emit_cell(const uint32_t* kept, int n, int BW, int c0, uint32_t* out, int outX0, int outY0, int lane)
+// One warp orders a cell's kept corners (by tile offset; offsets are distinct) and writes them out with their response.
+__device__ __forceinline__ void emit_cell(const uint16_t* kept, const uint8_t* sorg, int n, int BW, int c0, uint32_t* out, int outX0, int outY0, int lane)
 {
     for (int i = lane; i < n; i += 32) {
-        const uint32_t key = kept[i];
+        const uint32_t e = kept[i];
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += kept[j] < key;
-        const int e = (int)(key >> 8), row = e / BW, col = e - row * BW;
-        out[rank] = (uint32_t)(outX0 + col - c0) | ((uint32_t)(outY0 + row) << 11) | ((key & 255u) << 22);
+        for (int j = 0; j < n; ++j) rank += kept[j] < e;
+        const int row = (int)e / BW, col = (int)e - row * BW;
+        out[rank] = (uint32_t)(outX0 + col - c0) | ((uint32_t)(outY0 + row) << 11) | ((uint32_t)sorg[e] << 22);
     }
 }
 
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
     uint8_t* tile = smem;                                                   // BH x BW level pixels, interior (0,0) at [3][ax]
     uint8_t* score = smem + align_up(BW * BH, 128);                         // (h + 2) x BW responses, interior (0,0) at [1][ax], zero elsewhere
     uint16_t* list = reinterpret_cast<uint16_t*>(score + align_up(BW * (BH - 4), 16));   // pretest survivors: y * BW + tile column
-    uint32_t* kept = reinterpret_cast<uint32_t*>(list + align_up(BW * (BH - 6), 8));     // [cell][keptCap] NMS survivors
+    uint16_t* kept = list + align_up(ORBF_STRIP_MAX_W * (BH - 6), 8);                    // [cell][keptCap] NMS survivors (tile offsets)
     __shared__ int sKept[FS_WARPS];
     __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
 
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
             const int k = (col >= b1) + (col >= b2) + (col >= b3);
             if (nms_keep(sorg + e, v, BW, col > sC0[k], col < sC0[k + 1] - 1)) {
                 const int pos = atomicAdd(&sKept[k], 1);
-                if (pos < keptCap) kept[k * keptCap + pos] = ((uint32_t)e << 8) | (uint32_t)v;
+                if (pos < keptCap) kept[k * keptCap + pos] = (uint16_t)e;
             }
         }
     }
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
         const int c0 = sC0[warp], cw = cd.w;
         uint32_t* out = P.cellCand + (long long)slot * P.cellSlotTotal + cd.slotOff;
         const int outX0 = cd.x0 + cd.relx, outY0 = cd.y0 + cd.rely;
-        uint32_t* myKept = kept + warp * keptCap;
+        uint16_t* myKept = kept + warp * keptCap;
         int total = min(sKept[warp], keptCap);
         if (total == 0 && P.minTh < th) {
             // no corner at iniTh in this cell, so its score columns are still all zero: rescore the cell at minTh
@@ -203,13 +203,13 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_con
                 const int v = sorg[e];
                 if (v && nms_keep(sorg + e, v, BW, x > 0, x < cw - 1)) {
                     const int pos = atomicAdd(&sKept[warp], 1);
-                    if (pos < keptCap) myKept[pos] = ((uint32_t)e << 8) | (uint32_t)v;
+                    if (pos < keptCap) myKept[pos] = (uint16_t)e;
                 }
             }
             __syncwarp();
             total = min(sKept[warp], keptCap);
         }
-        emit_cell(myKept, total, BW, c0, out, outX0, outY0, lane);
+        emit_cell(myKept, sorg, total, BW, c0, out, outX0, outY0, lane);
         if (lane == 0) P.cellCount[(long long)slot * P.nCellsTotal + cellIdx] = total;
     }
 }
@@ -230,8 +230,9 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n)
         P.maps[l] = c->tmFast[l];
         P.BW[l] = (short)c->fastBW[l]; P.BH[l] = (short)c->fastBH[l];
         const int BW = c->fastBW[l], BH = c->fastBH[l];
-        const size_t need = (size_t)align_up(BW * BH, 128) + align_up(BW * (BH - 4), 16) + (size_t)align_up(BW * (BH - 6), 8) * sizeof(uint16_t)
-            + (size_t)FS_WARPS * keptCap * sizeof(uint32_t) + 16;
+        // 27.2 KB at 640x480: 8 CTAs per SM (the kernel gains ~6 % per extra resident CTA at this point)
+        const size_t need = (size_t)align_up(BW * BH, 128) + align_up(BW * (BH - 4), 16) + (size_t)align_up(ORBF_STRIP_MAX_W * (BH - 6), 8) * sizeof(uint16_t)
+            + (size_t)FS_WARPS * keptCap * sizeof(uint16_t) + 16;
         smem = std::max(smem, need);
     }
     P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
