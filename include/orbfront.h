@@ -41,7 +41,7 @@ extern "C" {
 #endif
 
 #define ORBF_MAX_LEVELS 16
-#define ORBF_ABI_VERSION 3
+#define ORBF_ABI_VERSION 4   /* 4: + projection_match, fuse_search, bow_match, compose_trajectory, undistort_points */
 
 typedef enum {
     ORBF_OK = 0,
