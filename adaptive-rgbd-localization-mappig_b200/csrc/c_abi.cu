@@ -173,9 +173,24 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
     Pipeline pl(c);
     TRY(pl.begin(hf && hf->gray));
     const int chunk = pl.active ? c->chunkFrames : n;
+    // chunk boundaries: quarter- and half-size chunks at both ends, so that the first kernels start after a short copy and the
+    // last copy is followed by a short tail of compute (the link, not the SMs, bounds this path)
+    std::vector<int> bounds{0};
+    if (pl.active && chunk >= 64 && n >= 4 * chunk) {
+        const int q = chunk / 4, h = chunk / 2;
+        bounds.push_back(q); bounds.push_back(q + h);
+        const int tailStart = n - q - h;
+        for (int a = q + h; a + chunk <= tailStart; a += chunk) bounds.push_back(a + chunk);
+        if (bounds.back() < tailStart) bounds.push_back(tailStart);
+        bounds.push_back(n - q); bounds.push_back(n);
+    } else {
+        for (int a = chunk; a < n; a += chunk) bounds.push_back(a);
+        bounds.push_back(n);
+    }
     int prevWorker = -1;
-    for (int k = 0, a = 0; a < n; ++k, a += chunk) {
-        const int b = std::min(a + chunk, n);
+    for (int k = 0; k + 1 < (int)bounds.size(); ++k) {
+        const int a = bounds[k], b = bounds[k + 1];
+        if (b <= a) continue;
         TRY(pl.enter(k));
         if (hf && hf->gray) TRY(upload_chunk(c, *hf, slot0 + a, a, b - a));
         TRY(run_extract(c, slot0 + a, b - a, !pl.active));

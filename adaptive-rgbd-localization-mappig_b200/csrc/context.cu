@@ -278,7 +278,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->nWork = 0; c->evFork = nullptr; c->evLatch = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
     for (int i = 0; i < 8; ++i) c->evHiGroup[i] = nullptr;
     for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
-    c->chunkFrames = cfg->pipeline_chunk == 0 ? 96 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
+    c->chunkFrames = cfg->pipeline_chunk == 0 ? 64 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;

@@ -140,23 +140,19 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     if (cur.level >= 0 && lane == 0) fetch(cur, 0);
     const float kMagic = 12582912.f;
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    // the record of keypoint k (lane 0) is written at the start of iteration k + 1, when its depth sample has long arrived
-    long long pendO = -1; float pendX = 0.f, pendY = 0.f; unsigned short pendRaw = 0; bool pendHave = false;
-    auto flush = [&]() {
-        if (lane == 0 && pendO >= 0) {
-            float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
-            if (pendHave) {
-                const float z = __fmul_rn((float)pendRaw, P.depthFactor);
-                if (z > 0) {
-                    ur = __fsub_rn(pendX, __fdiv_rn(P.mbf, z));
-                    X = __fmul_rn(__fmul_rn(__fsub_rn(pendX, P.cx), z), P.invfx);
-                    Y = __fmul_rn(__fmul_rn(__fsub_rn(pendY, P.cy), z), P.invfy);
-                    Z = z;
-                }
-            }
-            P.ptx[pendO] = X; P.pty[pendO] = Y; P.ptz[pendO] = Z; P.uright[pendO] = ur;
+    // depth sample of the keypoint (Core/frame.cpp:155): lanes 0..7 request the samples of the warp's 8 keypoints up front and
+    // unproject them after the loop, so the read — an HBM access, or a ~2 us PCIe round trip when the plane lives in pinned host
+    // memory — has the whole warp's work to hide behind
+    float myX = (float)mine.x, myY = (float)mine.y;
+    if (mine.level > 0) { myX = __fmul_rn(myX, P.scale[mine.level]); myY = __fmul_rn(myY, P.scale[mine.level]); }
+    unsigned short myRaw = 0; bool myHave = false;
+    if (lane < DS_KPW && mine.level >= 0 && P.depth) {
+        const int ui = (int)myX, vi = (int)myY;         // float -> int truncation of the (distorted) keypoint
+        if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
+            myRaw = __ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui);
+            myHave = true;
         }
-    };
+    }
 #pragma unroll 1
     for (int it = 0; it < DS_KPW && cur.level >= 0; ++it) {
         const int i = base + it, buf = it & 1;
@@ -165,20 +161,9 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         if (nxt.level >= 0 && lane == 0) fetch(nxt, buf ^ 1);
         __syncwarp();
         const int level = cur.level, x = cur.x, y = cur.y;
-        // depth sample of the keypoint (Core/frame.cpp:155), requested first: when the plane lives in pinned host memory the
-        // read crosses PCIe (~2 us) and completes behind the orientation / descriptor work
         float kfx = (float)x, kfy = (float)y;
         if (level != 0) { kfx = __fmul_rn(kfx, P.scale[level]); kfy = __fmul_rn(kfy, P.scale[level]); }
-        flush();
         const long long o = (long long)slot * P.K + i;
-        pendO = o; pendX = kfx; pendY = kfy; pendHave = false; pendRaw = 0;
-        if (lane == 0 && P.depth) {
-            const int ui = (int)kfx, vi = (int)kfy;     // float -> int truncation of the (distorted) keypoint
-            if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
-                pendRaw = __ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui);
-                pendHave = true;
-            }
-        }
         mbar_wait(&sBar[warp][buf], (it >> 1) & 1);
         // ---- orientation -----------------------------------------------------------------------------------------------------
         int m10, m01;
@@ -221,7 +206,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
             val |= (t0 < t1) << k;
         }
         P.desc[o * 32 + lane] = (uint8_t)val;
-        // ---- keypoint record (the 3D point follows when the depth sample is in, see flush) --------------------------------
+        // ---- keypoint record (the 3D points follow after the loop) -------------------------------------------------------
         if (lane == 0) {
             P.kpx[o] = kfx; P.kpy[o] = kfy; P.kpsize[o] = (float)P.scaledPatch[level]; P.kpangle[o] = angle;
             P.kpresp[o] = (float)cur.score; P.kpoct[o] = level; P.kplxy[o] = (uint32_t)x | ((uint32_t)y << 16);
@@ -229,7 +214,20 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         __syncwarp();                                   // every lane is done with this buffer before it is refilled
         cur = nxt;
     }
-    flush();
+    if (lane < DS_KPW && mine.level >= 0) {
+        float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
+        if (myHave) {
+            const float z = __fmul_rn((float)myRaw, P.depthFactor);
+            if (z > 0) {
+                ur = __fsub_rn(myX, __fdiv_rn(P.mbf, z));
+                X = __fmul_rn(__fmul_rn(__fsub_rn(myX, P.cx), z), P.invfx);
+                Y = __fmul_rn(__fmul_rn(__fsub_rn(myY, P.cy), z), P.invfy);
+                Z = z;
+            }
+        }
+        const long long o = (long long)slot * P.K + base + lane;
+        P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;
+    }
 }
 
 __global__ void pack_aos_kernel(const float* kpx, const float* kpy, const float* kpsize, const float* kpangle, const float* kpresp,

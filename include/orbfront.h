@@ -70,7 +70,7 @@ typedef struct {
     int32_t device;                    /* CUDA device ordinal                                    */
     float fx, fy, cx, cy, mbf;         /* Calibration:: (Utils/common.h:35-38,71)               */
     float depth_factor;                /* Calibration::depthFactor = 1/5000 (Utils/common.h:67) */
-    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default 96, < 0 = no chunking) */
+    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default 64, < 0 = no chunking) */
     int32_t pipeline_streams;          /* internal worker streams, 1..4 (0 = default 4)           */
     int32_t depth_zero_copy;           /* host depth planes in pinned (page-locked) memory are not copied: the ~1000 depth
                                           samples a frame needs are read in place over PCIe by the kernel that unprojects
