@@ -331,6 +331,9 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step,
                     "avg_launch_ms": stage_ms[dom] / launches_per_step, "peak_source": peak_src,
+                    "note": ("the dominant kernel by time (fast_cell) is bound by the integer ALU pipe, not by HBM (ncu, profiles/r1x_kernels.csv: "
+                             "ALU pipe 57 %, issue slots 67 %, DRAM 6 %): its HBM fraction is small by construction.  stage_hbm_frac has the "
+                             "HBM-class stages (pyramid resize, blur), hamming_knn2 the tensor-core view of the matcher."),
                     "stage_ms_per_step": stage_ms,
                     "stage_hbm_frac": {k: STAGE_BYTES[k] * F / (stage_ms[k] * 1e-3) / 1e9 / peak for k in STAGE_BYTES},
                     "whole_path": {"algorithmic_bytes_per_frame": FRAME_BYTES, "achieved_GBps": FRAME_BYTES * F / (ms * 1e-3) / 1e9,
