@@ -79,6 +79,26 @@ def run_sequence_shard(ctx, frames, depths, n_frames_total, rank, world, ratio=0
     return sh, results, cov
 
 
+def compose_trajectory_sharded(compose_local, npairs_local, rank, world, pose0=None, group=None, device="cpu"):
+    """Odometry::Compute's composition rule (pose[k+1] = T12[k] * pose[k], Odometry/odometry.cpp:82-84) over a sharded sequence.
+    The float products are not associative, so a shard cannot be composed from the identity and corrected afterwards: rank r
+    starts from the pose of its first frame — the halo frame, i.e. the last pose of rank r - 1 — which is passed down the ranks
+    (64 bytes per hop, the only exchange of the sharded path besides the depth covariance).  compose_local(npairs, pose0) ->
+    poses [npairs + 1, 4, 4] is Context.compose_trajectory (or the oracle's).  Returns this rank's poses, first = its first frame."""
+    import torch
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and world > 1
+    start = np.eye(4, dtype=np.float32) if pose0 is None else np.ascontiguousarray(pose0, np.float32).reshape(4, 4)
+    if multi and rank > 0:
+        t = torch.zeros(16, dtype=torch.float32, device=device)
+        dist.recv(t, src=rank - 1, group=group)
+        start = t.cpu().numpy().reshape(4, 4).copy()
+    poses = np.asarray(compose_local(npairs_local, start), np.float32).reshape(-1, 4, 4)
+    if multi and rank + 1 < world:
+        dist.send(torch.from_numpy(np.ascontiguousarray(poses[-1]).reshape(16)).to(device), dst=rank + 1, group=group)
+    return poses
+
+
 class _CudaArrayView:
     """Zero-copy torch view of a raw device pointer (the library's keyframe store) through __cuda_array_interface__."""
 

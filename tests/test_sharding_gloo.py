@@ -80,6 +80,11 @@ def _worker(rank, world, port, n_frames, out_dir):
         np.savez(Path(out_dir) / f"rank{rank}.npz", cov=cov, pairs=np.array([r["pair"] for r in results]),
                  T=np.stack([r["T12"] for r in results]), ninl=np.array([len(r["inliers"]) for r in results]),
                  inl=np.concatenate([r["inliers"] for r in results]), rmse=np.array([r["rmse"] for r in results]))
+        # trajectory: the composition rule chained rank to rank (each rank starts from the pose of its halo frame)
+        T12 = np.stack([r["T12"] for r in results]) if results else np.zeros((0, 4, 4), np.float32)
+        p0 = np.eye(4, dtype=np.float32); p0[:3, 3] = [0.5, -0.25, 0.125]
+        poses = sh_mod.compose_trajectory_sharded(lambda npairs, start: ctx.orc.compose_trajectory(T12[:npairs], start), len(T12), rank, world, pose0=p0)
+        np.save(Path(out_dir) / f"poses{rank}.npy", poses)
         # config 5: keyframe shards (2 keyframes per rank = this rank's first two frames), all-gather vs gather-top-2
         K = 1024
         local = torch.zeros((2, K, 32), dtype=torch.uint8); counts = torch.zeros(2, dtype=torch.int32)
@@ -138,6 +143,12 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path, orc, texture):
     assert list(pairs) == list(range(n - 1))
     T = np.concatenate([g["T"] for g in got]); ninl = np.concatenate([g["ninl"] for g in got]); rmse = np.concatenate([g["rmse"] for g in got])
     inl = np.concatenate([g["inl"] for g in got])
+    # sharded trajectory == the single-process composition, bit for bit (rank 1's first pose is the halo frame = rank 0's last)
+    p0 = np.eye(4, dtype=np.float32); p0[:3, 3] = [0.5, -0.25, 0.125]
+    ref_poses = ctx.orc.compose_trajectory(np.stack([r["T12"] for r in ref]), p0)
+    pr = [np.load(tmp_path / f"poses{r}.npy") for r in range(2)]
+    assert np.array_equal(pr[1][0], pr[0][-1])
+    assert np.array_equal(np.concatenate([pr[0], pr[1][1:]]), ref_poses)
     assert np.array_equal(T, np.stack([r["T12"] for r in ref])) and list(ninl) == [len(r["inliers"]) for r in ref]
     assert inl.tobytes() == np.concatenate([r["inliers"] for r in ref]).tobytes() and list(rmse) == [r["rmse"] for r in ref]
     kf = [np.load(tmp_path / f"kf{r}.npz") for r in range(2)]
