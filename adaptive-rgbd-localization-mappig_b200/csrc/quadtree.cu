@@ -95,10 +95,17 @@ __global__ void __launch_bounds__(QT_THREADS) quadtree_kernel(QtParams P)
     if (warp == 0) { const int t = scan_by_warp0(cellCnt, cellOff, g.nCells, lane); if (lane == 0) sN = t; }
     __syncthreads();
     const int n = sN;
-    for (int c = warp; c < g.nCells; c += QT_THREADS / 32) {
+    // one cell per thread: a warp per cell walked ~40 cells one after the other, each a chain of dependent global loads
+    // (descriptor -> candidates -> store); here every thread has at most two such chains and its loads are independent
+    for (int c = tid; c < g.nCells; c += QT_THREADS) {
         const int k = cellCnt[c], o = cellOff[c];
         const uint32_t* src = P.cellCand + (long long)slot * P.cellSlotTotal + P.cells[g.cell0 + c].slotOff;
-        for (int i = lane; i < k; i += 32) cand[o + i] = src[i];
+        int i = 0;
+        for (; i + 4 <= k; i += 4) {
+            const uint32_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
+            cand[o + i] = a0; cand[o + i + 1] = a1; cand[o + i + 2] = a2; cand[o + i + 3] = a3;
+        }
+        for (; i < k; ++i) cand[o + i] = src[i];
     }
     if (tid == 0) P.candCount[slot * ORBF_MAX_LEVELS + level] = n;
     if (n == 0) { if (tid == 0) P.lkpCount[slot * ORBF_MAX_LEVELS + level] = 0; return; }
