@@ -13,13 +13,15 @@
 //   * Operands are expanded in the kernel, straight into the no-swizzle K-major canonical layout (8-row x 16-byte core
 //     matrices, LBO 128 B, SBO 2 KB): one PRMT turns 4 descriptor bits into 4 bytes.  The order of the 256 dimensions is
 //     irrelevant as long as both operands use the same one.
-//   * One thread issues the 8 K-steps (UTCIMMA 128 x 256 x 32) and commits to an mbarrier; every thread then reads its own
-//     row with tcgen05.ld (32x32b.x32) and works on two columns per register (VIMNMX.U16x2):
+//   * The train tile is expanded and multiplied in two halves of 128 rows: one thread issues the 8 K-steps of a half
+//     (UTCIMMA 128 x 128 x 32) and commits to that half's mbarrier, so the first half is in the tensor core while the second is
+//     still being expanded and the warps of column half 0 start before half 1 is done.  Every thread then reads its own row
+//     with tcgen05.ld (32x32b.x32) and works on two columns per register (VIMNMX.U16x2):
 //       value v = accumulator + 64 * 256 + rc = 128 * (256 - hamming) + rc, rc = 32 - lane in the low 7 bits;
 //       rows:    per 128 columns a packed running top-2 of (v with rc replaced by 64 - pair index), decoded into
 //                (distance << 16 | trainIdx) keys once per 128 columns;
 //       columns (cross-check, quirk Q10): a 31-shuffle halving butterfly leaves lane L with the best (256 - hamming, row) of the
-//                warp's 32 rows for column pair L; the 4 warps are folded through shared memory once per chunk.
+//                warp's 32 rows for column pair L; the 4 lane quarters are folded through shared memory once per chunk.
 // History: a POPC/LOP3 kernel (integer-ALU bound, 0.81 ms per 511 pairs), then mma.sync IMMA s8 (0.43 ms; warp-level MMAs block
 // the issue port ~6 of every 8.3 clk, tools/bmma_probe.cu), now tcgen05 (tools/umma_probe.cu pins the descriptor fields).
 #include "orbf_internal.h"
