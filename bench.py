@@ -77,7 +77,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.gpu),
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
         except Exception:
             self.proc = None
@@ -191,7 +191,7 @@ def knn2_view(frame_counts, ms):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -251,8 +251,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
-    sampler = ClockSampler(local); sampler.start()             # started early: nvidia-smi needs ~100 ms before its first row
+    sampler = ClockSampler(local); sampler.start()             # started early: nvidia-smi needs 0.1-1 s before its first row
     step_device(); torch.cuda.synchronize()
+    t_wait = time.perf_counter()
+    while sampler.proc and not sampler.rows and time.perf_counter() - t_wait < 5.0:     # keep the GPU busy until the sampler is live
+        step_device(); torch.cuda.synchronize()
     t_load0 = time.perf_counter(); sampler.load_t0 = t_load0
     for _ in range(args.warmup):
         step_device()
