@@ -24,7 +24,7 @@ want = ["UTCIMMA", "LDTM.x32", "UTCBAR", "UTMALDG.3D", "SYNCS.ARRIVE.TRANS64", "
         "POPC", "LOP3.LUT", "CREDUX.MIN", "ATOMS", "DFMA", "SHFL", "VOTE", "BAR.SYNC"]
 lines = ["# SASS evidence (cuobjdump -sass liborbfront_b200.so, sm_100a): instruction counts per kernel", "",
          "TMA = `UTMALDG.3D` (+ mbarrier `SYNCS.*`); packed 16x2 integer min/max = `VIMNMX(3).U16x2`; byte SIMD = `VABSDIFF4`, `IDP.4A`, "
-         "`IDP.2A`; matcher = `LOP3` carry-save + `POPC`.", "Regenerate with `python tools/sass_evidence.py`.", "",
+         "`IDP.2A`; matcher = `UTCIMMA` (tcgen05.mma kind::i8), `LDTM` (tcgen05.ld), `UTCBAR` (tcgen05.commit) + packed `VIMNMX.U16x2` epilogue.", "Regenerate with `python tools/sass_evidence.py`.", "",
          "| kernel | total | " + " | ".join(want) + " |", "|---|---:|" + "---:|" * len(want)]
 for k in sorted(counts, key=lambda k: -sum(counts[k].values())):
     c = counts[k]
