@@ -5,6 +5,8 @@
 -fmad=false: the RANSAC / descriptor arithmetic must not contract a*b+c into FMA; the
 integer kernels are unaffected.  -lineinfo keeps ncu's source page mapped to these files.
 """
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -19,26 +21,52 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--threads", "0"]
 
 
+STAMP = HERE / "liborbfront_b200.so.stamp"          # sha256 of every input of the last build: travels with the .so to the GPU box
+
+
+def _deps():
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc"))) + [HERE.parent / "include" / "orbfront.h", Path(__file__)]
+
+
+def source_hash():
+    h = hashlib.sha256()
+    h.update(" ".join(FLAGS).encode())
+    for d in _deps():
+        h.update(d.name.encode()); h.update(d.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not OUT.exists():
+    """Content-based, not mtime-based: a snapshot copied to another machine must not look stale (N ranks started by torchrun
+    would otherwise all recompile, into the same file)."""
+    if not OUT.exists() or not STAMP.exists():
         return True
-    t = OUT.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "orbfront.h", Path(__file__)]
-    return any(d.stat().st_mtime > t for d in deps)
+    return STAMP.read_text().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return str(OUT)
-    cmd = [NVCC] + FLAGS + ["-shared", "-o", str(OUT)] + [str(CSRC / s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    log = r.stdout + r.stderr
-    (HERE / "build.log").write_text(log)
-    if r.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        print(log)
+    # one builder at a time (ranks of one node share the tree); the others wait for the lock, find the stamp current and return
+    with open(HERE / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return str(OUT)
+        want = source_hash()
+        tmp = HERE / f"liborbfront_b200.so.tmp.{os.getpid()}"
+        cmd = [NVCC] + FLAGS + ["-shared", "-o", str(tmp)] + [str(CSRC / s) for s in SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = r.stdout + r.stderr
+        (HERE / "build.log").write_text(log)
+        if r.returncode != 0:
+            if tmp.exists():
+                tmp.unlink()
+            sys.stderr.write(log)
+            raise RuntimeError("nvcc failed")
+        os.replace(tmp, OUT)                          # atomic: a concurrent dlopen sees the old or the new file, never half of one
+        STAMP.write_text(want + "\n")
+        if verbose:
+            print(log)
     return str(OUT)
 
 

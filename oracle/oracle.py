@@ -45,7 +45,10 @@ class RansacOut(C.Structure):
 
 def build(speed=False):
     """Compile the oracle with oracle/Makefile (g++ only; building the checker is not using it)."""
-    subprocess.run(["make", "-C", str(_DIR), "-s", "all"], check=True)
+    import fcntl
+    with open(_DIR / ".build.lock", "w") as lock:          # processes of one node share the tree
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        subprocess.run(["make", "-C", str(_DIR), "-s", "all"], check=True)
 
 
 _libs = {}
