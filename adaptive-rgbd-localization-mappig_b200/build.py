@@ -49,7 +49,10 @@ def build(force=False, verbose=False):
         return str(OUT)
     # one builder at a time (ranks of one node share the tree); the others wait for the lock, find the stamp current and return
     with open(HERE / ".build.lock", "w") as lock:
-        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+        except OSError:
+            pass                                      # a filesystem without flock: the atomic rename below still keeps the file whole
         if not force and not needs_build():
             return str(OUT)
         want = source_hash()
