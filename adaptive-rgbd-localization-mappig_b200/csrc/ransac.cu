@@ -451,6 +451,9 @@ __device__ __forceinline__ float det3(const M3& a)
 
 struct Tfc {   // pcl::TransformationFromCorrespondences
     float accW, m1[3], m2[3], C[3][3];
+    // The recurrence as PCL writes it (one correspondence at a time).  tfc_from_mask runs exactly these operations, split into
+    // nine per-lane chains; the scalar form is kept (not compiled) as the statement of what they compute.
+#if 0
     __device__ void add(const float p[3], const float q[3], float w)
     {
         if (w == 0.0f) return;
@@ -467,6 +470,7 @@ struct Tfc {   // pcl::TransformationFromCorrespondences
 #pragma unroll
         for (int i = 0; i < 3; ++i) { m1[i] += alpha * d1[i]; m2[i] += alpha * d2[i]; }
     }
+#endif
     __device__ void transform(float* T) const
     {
         M3 U, V; float S[3];
