@@ -92,3 +92,21 @@ def test_round_based_quadtree_equals_list_algorithm(orc, texture):
         N = int(rng.integers(1, 400))
         tup = [(int(a["x"]), int(a["y"]), int(a["score"])) for a in c]
         assert list(orc.distribute(c, 16, W + 16, 16, H + 16, N)) == distribute_rounds(tup, W, H, N)
+
+
+def test_build_is_content_stamped_not_mtime_based(tmp_path):
+    """A snapshot copied to another machine (fresh mtimes, N ranks starting at once) must not look stale: the rebuild decision
+    hashes the sources, and a build goes through a lock + atomic rename (build.py)."""
+    import importlib.util, os, time
+    spec = importlib.util.spec_from_file_location("orbf_build", ROOT / "adaptive-rgbd-localization-mappig_b200" / "build.py")
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    b.build()
+    assert b.OUT.exists() and b.STAMP.read_text().strip() == b.source_hash() and not b.needs_build()
+    src = next(iter(sorted(b.CSRC.glob("*.cu"))))
+    st = src.stat()
+    try:
+        os.utime(src, (time.time() + 3600, time.time() + 3600))      # a newer mtime alone changes nothing
+        assert not b.needs_build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    assert not list(b.HERE.glob("*.so.tmp.*"))
