@@ -56,7 +56,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
-constexpr int DS_WARPS = 4, DS_KPW = 8;     // keypoints per warp: window of keypoint k+1 is in flight while keypoint k is computed
+constexpr int DS_WARPS = 4, DS_KPW = 16;     // keypoints per warp: window of keypoint k+1 is in flight while keypoint k is computed
 constexpr int DS_WIN_BYTES = (ORBF_PATCH_BW * ORBF_PATCH_BH + 127) / 128 * 128;     // TMA destinations: 128-byte aligned
 
 struct KpLoc { int level, x, y, score; };
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     const int slot = P.slot0 + blockIdx.y;
     const int* lc = P.lkpCount + slot * ORBF_MAX_LEVELS;
     const int base = (blockIdx.x * DS_WARPS + warp) * DS_KPW;
-    // lanes 0..7 locate the warp's 8 keypoints once; each iteration takes its keypoint by shuffle
+    // lanes 0..DS_KPW-1 locate the warp's keypoints once; each iteration takes its keypoint by shuffle
     int total;
     const KpLoc mine = locate(P, lc, slot, base + (lane & (DS_KPW - 1)), total);
     if (base == 0 && lane == 0) P.count[slot] = total;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     if (cur.level >= 0 && lane == 0) fetch(cur, 0);
     const float kMagic = 12582912.f;
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    // depth sample of the keypoint (Core/frame.cpp:155): lanes 0..7 request the samples of the warp's 8 keypoints up front and
+    // depth sample of the keypoint (Core/frame.cpp:155): lanes 0..DS_KPW-1 request the samples of the warp's keypoints up front and
     // unproject them after the loop, so the read — an HBM access, or a ~2 us PCIe round trip when the plane lives in pinned host
     // memory — has the whole warp's work to hide behind
     float myX = (float)mine.x, myY = (float)mine.y;
