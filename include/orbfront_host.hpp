@@ -471,6 +471,21 @@ public:
         mT12 = mpRansac->mT12; mvInliers = mpRansac->mvInliers;
         return ok;
     }
+    // The rest of Odometry::Compute (odometry.cpp:82-90) for a device-resident sequence (after orbf_track_sequence /
+    // orbf_ransac_pairs on `npairs` consecutive pairs): poses[k + 1] = T12[k] * poses[k] with cv::Mat's float product, and the
+    // frames' mvbOutlier flags after SetInlier(m.trainIdx).  poses: (npairs + 1) row-major 4x4; outlier may be null.
+    static void ComposeTrajectory(int npairs, const Matrix4f* pose0, std::vector<Matrix4f>& poses, std::vector<uint8_t>* outlier = nullptr)
+    {
+        std::lock_guard<std::mutex> g(Runtime::Lock());
+        orbf_context* ctx = Runtime::Current();
+        static_assert(sizeof(Matrix4f) == 16 * sizeof(float), "poses are written as one contiguous block");
+        poses.assign((size_t)npairs + 1, Matrix4f());
+        int cap = 0;
+        check(orbf_keypoint_capacity(ctx, &cap), "orbf_keypoint_capacity");
+        if (outlier) outlier->assign(((size_t)npairs + 1) * (size_t)cap, 1);
+        check(orbf_compose_trajectory(ctx, npairs, pose0 ? pose0->m : nullptr, poses[0].m, outlier ? outlier->data() : nullptr),
+            "orbf_compose_trajectory");
+    }
     eAlgorithm mOdometryAlgorithm;
     Matrix4f mT12;
     std::vector<DMatch> mvInliers;
