@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
             while (!done) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(done) : "r"(smem_u32(&sBar[colHalf])), "r"(phase) : "memory");
-                if (!done && ++spins > (1u << 26)) __trap();                   // a lost commit must fail loudly, not hang the device
+                if (!done && ++spins > (1u << 22)) __trap();                   // a lost commit must fail loudly, not hang the device
             }
             phase ^= 1u;
         }
