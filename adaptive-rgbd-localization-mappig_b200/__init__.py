@@ -35,7 +35,8 @@ class Config(C.Structure):
                 ("max_frames", C.c_int32), ("max_pairs", C.c_int32), ("device", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
                 ("depth_factor", C.c_float), ("pipeline_chunk", C.c_int32), ("pipeline_streams", C.c_int32),
-                ("depth_zero_copy", C.c_int32), ("reserved_", C.c_int32)]
+                ("depth_zero_copy", C.c_int32), ("reserved_", C.c_int32),
+                ("k1", C.c_float), ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
 
 
 class RansacConfig(C.Structure):
@@ -251,6 +252,12 @@ class Context:
         self._chk(lib().orbf_download_frame(self._h, slot, _p(kps), _p(desc), _p(xyz), self.K, C.byref(n)), "download_frame")
         return kps[:n.value].copy(), desc[:n.value].copy(), xyz[:n.value].copy()
 
+    def download_keys_un(self, slot):
+        """Frame::mvKeysUn (undistorted keypoint positions, [n, 2]) and mvuRight of a slot."""
+        xy = np.zeros((self.K, 2), np.float32); ur = np.zeros(self.K, np.float32); n = C.c_int32(0)
+        self._chk(lib().orbf_download_keys_un(self._h, slot, _p(xy), _p(ur), self.K, C.byref(n)), "download_keys_un")
+        return xy[:n.value].copy(), ur[:n.value].copy()
+
     def pyramid_level(self, slot, level, blurred=False):
         t = self.tables()
         w, h = int(t["level_w"][level]), int(t["level_h"][level])
@@ -406,6 +413,12 @@ class Context:
     def ransac_pairs(self, npairs, **kw):
         cfg = default_ransac_config(**kw)
         self._chk(lib().orbf_ransac_pairs(self._h, npairs, C.byref(cfg)), "ransac_pairs")
+
+    def ransac_probe_depth_cov(self, npairs, **kw):
+        """The depth covariance (quirk Q7) the pairs last matched would latch on a fresh process, or -1."""
+        cfg = default_ransac_config(**kw); cov = C.c_double(-1.0)
+        self._chk(lib().orbf_ransac_probe_depth_cov(self._h, npairs, C.byref(cfg), C.byref(cov)), "ransac_probe_depth_cov")
+        return cov.value
 
     def download_ransac(self, pair):
         res = RansacResult(); inl = np.zeros(self.K, DMATCH_DT)

@@ -203,14 +203,14 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
                 TRY(run_match_group(c, pa, pb - pa, track->ratio, track->cross));
                 // RANSAC is a chain of ten latency-bound launches whose duration barely depends on the number of pairs: per
                 // chunk it would be paid once per chunk, so the pipelined path runs it once, after the join, for all pairs
-                if (track->rcfg && !pl.active) TRY(orbf_launch_ransac(c, slot_ransac_set(c), pa, pb - pa, *track->rcfg, nullptr, pa == 0 ? 0 : 1));
+                if (track->rcfg && !pl.active) TRY(orbf_launch_ransac(c, slot_ransac_set(c), pa, pb - pa, *track->rcfg, nullptr, false));
             }
         }
         prevWorker = wk;
     }
     const bool deferred = pl.active;
     TRY(pl.end());
-    if (deferred && track && npairs > 0 && track->rcfg) TRY(orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *track->rcfg, nullptr, 0));
+    if (deferred && track && npairs > 0 && track->rcfg) TRY(orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *track->rcfg, nullptr, false));
     return ORBF_OK;
 }
 
@@ -375,6 +375,28 @@ extern "C" int orbf_download_frame(orbf_context* c, int32_t slot, orbf_keypoint*
     if (kps) memcpy(kps, c->h_kp, n * sizeof(orbf_keypoint));
     if (desc) memcpy(desc, c->h_desc, (size_t)n * 32);
     if (xyz) for (int i = 0; i < n; ++i) { xyz[3 * i] = c->h_xyz[i]; xyz[3 * i + 1] = c->h_xyz[c->K + i]; xyz[3 * i + 2] = c->h_xyz[2 * c->K + i]; }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_download_keys_un(orbf_context* c, int32_t slot, float* xy, float* u_right, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || slot < 0 || slot >= c->B) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int n = c->h_counts[0];
+    *n_out = n;
+    if (n > cap) return ORBF_ERR_CAPACITY;
+    if (n == 0) return ORBF_OK;
+    const size_t o = (size_t)slot * c->K;
+    if (xy) {
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz, c->d_kpux + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + c->K, c->d_kpuy + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (u_right) ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + 2 * c->K, c->d_uright + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (xy) for (int i = 0; i < n; ++i) { xy[2 * i] = c->h_xyz[i]; xy[2 * i + 1] = c->h_xyz[c->K + i]; }
+    if (u_right) memcpy(u_right, c->h_xyz + 2 * c->K, n * sizeof(float));
     return ORBF_OK;
 }
 
@@ -561,7 +583,7 @@ extern "C" int orbf_fuse_search(orbf_context* c, int32_t slot, const float* Rcw,
     SC_H2D(oPos, lm_pos, L * 12); SC_H2D(oLd, lm_desc, L * 32); SC_H2D(oVal, lm_valid, L);
     const float *dKx, *dKy, *dUr; const uint8_t* dDesc;
     if (slot >= 0) {
-        dKx = c->d_kpx + (size_t)slot * c->K; dKy = c->d_kpy + (size_t)slot * c->K; dUr = c->d_uright + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
+        dKx = c->d_kpux + (size_t)slot * c->K; dKy = c->d_kpuy + (size_t)slot * c->K; dUr = c->d_uright + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
     } else {
         SC_H2D(oKx, kp_x, F * 4); SC_H2D(oKy, kp_y, F * 4); SC_H2D(oUr, u_right, F * 4); SC_H2D(oDesc, desc, F * 32);
         dKx = sc.at<float>(oKx); dKy = sc.at<float>(oKy); dUr = sc.at<float>(oUr); dDesc = sc.at<uint8_t>(oDesc);
@@ -675,7 +697,7 @@ extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float*
     if (feat_taken && nFeat > 0) PJ_CUDA(cudaMemcpyAsync(d + oTakenIn, feat_taken, (size_t)nFeat, cudaMemcpyHostToDevice, c->stream));
     const float *dKx, *dKy; const int* dOct; const uint8_t* dDesc;
     if (slot >= 0) {
-        dKx = c->d_kpx + (size_t)slot * c->K; dKy = c->d_kpy + (size_t)slot * c->K; dOct = c->d_kpoct + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
+        dKx = c->d_kpux + (size_t)slot * c->K; dKy = c->d_kpuy + (size_t)slot * c->K; dOct = c->d_kpoct + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
     } else {
         if (nFeat > 0) {
             PJ_CUDA(cudaMemcpyAsync(d + oKx, kp_x, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
@@ -771,7 +793,24 @@ extern "C" int orbf_ransac_pairs(orbf_context* c, int32_t npairs, const orbf_ran
     if (!cfg || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
     if (!c->pairsFromSlots || npairs > c->lastNPairs) return ORBF_ERR_STATE;
     TRY(orbf_ransac_reserve(c, *cfg));
-    return orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *cfg, nullptr, 0);
+    return orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *cfg, nullptr, false);
+}
+
+// The covariance the pairs last matched would latch (quirk Q7) if nothing had been latched before them: the value of the first pair, in
+// order, that reaches scoring, or -1.  Sharded sequences use it to agree on the globally first value before any rank scores (the
+// context's own latch is neither read nor written).
+extern "C" int orbf_ransac_probe_depth_cov(orbf_context* c, int32_t npairs, const orbf_ransac_config* cfg, double* cov)
+{
+    CTX_ENTER(c);
+    if (!cfg || !cov || npairs < 1 || npairs > c->P) return ORBF_ERR_ARG;
+    if (!c->pairsFromSlots || npairs > c->lastNPairs) return ORBF_ERR_STATE;
+    orbf_ransac_config cf = *cfg;
+    cf.depth_cov = -1.0;
+    TRY(orbf_ransac_reserve(c, cf));
+    TRY(orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, cf, nullptr, /*standalone=*/true, false, /*probeOnly=*/true));
+    ORBF_CUDA(c, cudaMemcpyAsync(cov, c->d_depthCov + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
 }
 
 extern "C" int orbf_download_ransac(orbf_context* c, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap)
@@ -780,7 +819,7 @@ extern "C" int orbf_download_ransac(orbf_context* c, int32_t pair, orbf_ransac_r
     if (!out || pair < 0 || pair >= c->P) return ORBF_ERR_ARG;
     ORBF_CUDA(c, cudaMemcpyAsync(out, c->d_rres + pair, sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (out->n_inliers > cap) return ORBF_ERR_CAPACITY;
+    if (inliers && out->n_inliers > cap) return ORBF_ERR_CAPACITY;
     if (inliers && out->n_inliers > 0) {
         ORBF_CUDA(c, cudaMemcpyAsync(inliers, c->d_inliers + (size_t)pair * c->K, out->n_inliers * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost,
             c->stream));
@@ -840,17 +879,12 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
         ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
         dTab = c->d_userSamples;
     }
-    orbf_ransac_config cf = *cfg;
-    if (cf.depth_cov < 0.0) {   // standalone call: latch within this call only (matches one oracle call with depth_cov < 0)
-        const double neg = -1.0;
-        ORBF_CUDA(c, cudaMemcpyAsync(c->d_depthCov, &neg, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
+    const orbf_ransac_config& cf = *cfg;     // standalone: depth_cov < 0 latches within this call only (one oracle call with depth_cov < 0)
     RansacSet rs;
     rs.sx = c->d_sxyz; rs.sy = c->d_sxyz + R; rs.sz = c->d_sxyz + 2 * (size_t)R;
     rs.tx = c->d_txyz; rs.ty = c->d_txyz + R; rs.tz = c->d_txyz + 2 * (size_t)R;
     rs.slotStride = 0; rs.pairs = nullptr; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount; rs.nsrc = nsrc; rs.ndst = ndst;
-    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, 0, /*fullTable=*/sample_table_out != nullptr));
+    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, /*standalone=*/true, /*fullTable=*/sample_table_out != nullptr));
     TRY(orbf_download_ransac(c, 0, out, inliers_out, cap));
     if (hyp_trace) ORBF_CUDA(c, cudaMemcpyAsync(hyp_trace, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
     if (good_sorted_out && out->n_good > 0)

@@ -94,6 +94,7 @@ extern "C" void orbf_default_config(orbf_config* c)
     c->mbf = 40.0f;
     c->depth_factor = 1.0f / 5000.0f;
     c->pipeline_chunk = 0; c->pipeline_streams = 0; c->depth_zero_copy = 0; c->reserved_ = 0;
+    c->k1 = c->k2 = c->p1 = c->p2 = c->k3 = 0.0f;               // the synthetic configurations zero the distortion (frame.cpp:288-291)
 }
 
 extern "C" void orbf_default_ransac_config(orbf_ransac_config* c)
@@ -275,7 +276,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->B = cfg->max_frames;
     c->P = cfg->max_pairs > 0 ? cfg->max_pairs : cfg->max_frames;
     c->launches = 0; c->stream = nullptr; c->ownStream = false; c->profiling = false;
-    c->nWork = 0; c->evFork = nullptr; c->evLatch = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
+    c->nWork = 0; c->evFork = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
     for (int i = 0; i < 8; ++i) c->evHiGroup[i] = nullptr;
     for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
     c->chunkFrames = cfg->pipeline_chunk == 0 ? 64 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
@@ -297,7 +298,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
         c->ownStream = true;
         const int nw = cfg->pipeline_streams <= 0 ? 4 : std::min(cfg->pipeline_streams, ORBF_MAX_WORKERS);
         auto ev = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-        bool ok = ev(&c->evFork) && ev(&c->evLatch);
+        bool ok = ev(&c->evFork);
         for (int i = 0; ok && i < nw; ++i) {
             ok = cudaStreamCreateWithFlags(&c->work[i], cudaStreamNonBlocking) == cudaSuccess && ev(&c->evDone[i]) && ev(&c->evExtract[i]);
             if (ok) c->nWork = i + 1;
@@ -335,7 +336,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     TRY(dalloc(c, &c->d_kpx, B * K)); TRY(dalloc(c, &c->d_kpy, B * K)); TRY(dalloc(c, &c->d_kpsize, B * K));
     TRY(dalloc(c, &c->d_kpangle, B * K)); TRY(dalloc(c, &c->d_kpresp, B * K));
     TRY(dalloc(c, &c->d_ptx, B * K)); TRY(dalloc(c, &c->d_pty, B * K)); TRY(dalloc(c, &c->d_ptz, B * K));
-    TRY(dalloc(c, &c->d_uright, B * K));
+    TRY(dalloc(c, &c->d_uright, B * K)); TRY(dalloc(c, &c->d_kpux, B * K)); TRY(dalloc(c, &c->d_kpuy, B * K));
     TRY(dalloc(c, &c->d_kpoct, B * K)); TRY(dalloc(c, &c->d_kplxy, B * K));
     TRY(dalloc(c, &c->d_desc, B * K * 32));
     TRY(dalloc(c, &c->d_count, B));
@@ -350,7 +351,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     TRY(dalloc(c, &c->d_rres, P));
     { uint8_t* t = nullptr; TRY(dalloc(c, &t, P * 32)); c->d_rstate = t; }
     TRY(dalloc(c, &c->d_inliers, P * K));
-    TRY(dalloc(c, &c->d_depthCov, 1));
+    TRY(dalloc(c, &c->d_depthCov, 2));
     c->d_samples = nullptr; c->d_hyp = nullptr;
     c->d_qdesc = c->d_tdesc = nullptr; c->d_sxyz = c->d_txyz = nullptr;
     c->d_bgr = nullptr; c->bgrSlots = 0;
@@ -366,7 +367,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     if (!rsTiles.empty() && !cu(cudaMemcpy(c->d_rsTiles, rsTiles.data(), rsTiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice), "resize tiles"))
         return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_lg, c->lg, sizeof(LevelGeom) * ORBF_MAX_LEVELS, cudaMemcpyHostToDevice), "lg")) return fail(ORBF_ERR_CUDA);
-    { const double neg = -1.0; if (!cu(cudaMemcpy(c->d_depthCov, &neg, sizeof(double), cudaMemcpyHostToDevice), "depthCov")) return fail(ORBF_ERR_CUDA); }
+    { const double neg[2] = { -1.0, -1.0 }; if (!cu(cudaMemcpy(c->d_depthCov, neg, sizeof(neg), cudaMemcpyHostToDevice), "depthCov")) return fail(ORBF_ERR_CUDA); }
     if (!cu(cudaMemset(c->d_count, 0, B * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemset(c->d_matchCount, 0, P * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemset(c->d_lkpCount, 0, B * ORBF_MAX_LEVELS * sizeof(int)), "memset")) return fail(ORBF_ERR_CUDA);
@@ -387,7 +388,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_blTiles, c->d_rsTiles, c->d_bgr, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
-        c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
+        c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpux, c->d_kpuy, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,
         c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts,
         c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount };
@@ -408,7 +409,6 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (c->evHiB) cudaEventDestroy(c->evHiB);
     for (int i = 0; i < 8; ++i) if (c->evHiGroup[i]) cudaEventDestroy(c->evHiGroup[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
-    if (c->evLatch) cudaEventDestroy(c->evLatch);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ORBF_OK;

@@ -9,6 +9,7 @@
 //     pt *= scale[level]; rows ordered level-major then quadtree list order;
 //   * Frame::ExtractFeatures' depth gather + unprojection (Core/frame.cpp:148-164) into SoA x/y/z.
 #include "orbf_internal.h"
+#include "undistort_device.h"
 
 namespace {
 
@@ -27,7 +28,8 @@ struct DescParams {
     const uint32_t* lkp; const int* lkpCount;
     int kpStageTotal, K, slot0, L;
     int kpOff[ORBF_MAX_LEVELS]; float scale[ORBF_MAX_LEVELS]; int scaledPatch[ORBF_MAX_LEVELS];
-    float *kpx, *kpy, *kpsize, *kpangle, *kpresp, *ptx, *pty, *ptz, *uright;
+    float *kpx, *kpy, *kpsize, *kpangle, *kpresp, *ptx, *pty, *ptz, *uright, *kpux, *kpuy;
+    int distorted; UndistortParams und;                                  // k1 != 0: mvKeysUn = cv::undistortPoints(mvKeys) (Core/frame.cpp:286-313)
     int* kpoct; uint32_t* kplxy; uint8_t* desc; int* count;
     const uint16_t* depth; long long depthFrameStride; int depthPitch;   // elements
     int width, height;
@@ -215,18 +217,21 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         cur = nxt;
     }
     if (lane < DS_KPW && mine.level >= 0) {
+        // mvKeysUn (frame.cpp:286-313): the depth was looked up at the distorted keypoint above, mvuRight and mvKeys3Dc use the undistorted one
+        float uX = myX, uY = myY;
+        if (P.distorted) undistort_point(P.und, myX, myY, &uX, &uY);
         float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
         if (myHave) {
             const float z = __fmul_rn((float)myRaw, P.depthFactor);
             if (z > 0) {
-                ur = __fsub_rn(myX, __fdiv_rn(P.mbf, z));
-                X = __fmul_rn(__fmul_rn(__fsub_rn(myX, P.cx), z), P.invfx);
-                Y = __fmul_rn(__fmul_rn(__fsub_rn(myY, P.cy), z), P.invfy);
+                ur = __fsub_rn(uX, __fdiv_rn(P.mbf, z));
+                X = __fmul_rn(__fmul_rn(__fsub_rn(uX, P.cx), z), P.invfx);
+                Y = __fmul_rn(__fmul_rn(__fsub_rn(uY, P.cy), z), P.invfy);
                 Z = z;
             }
         }
         const long long o = (long long)slot * P.K + base + lane;
-        P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur;
+        P.ptx[o] = X; P.pty[o] = Y; P.ptz[o] = Z; P.uright[o] = ur; P.kpux[o] = uX; P.kpuy[o] = uY;
     }
 }
 
@@ -269,7 +274,10 @@ int orbf_launch_describe(orbf_context* c, int slot0, int n)
     P.lkp = c->d_lkp; P.lkpCount = c->d_lkpCount; P.kpStageTotal = c->kpStageTotal; P.K = c->K; P.slot0 = slot0; P.L = c->L;
     for (int l = 0; l < c->L; ++l) { P.kpOff[l] = c->lg[l].kpOff; P.scale[l] = c->scale[l]; P.scaledPatch[l] = c->lg[l].scaledPatch; }
     P.kpx = c->d_kpx; P.kpy = c->d_kpy; P.kpsize = c->d_kpsize; P.kpangle = c->d_kpangle; P.kpresp = c->d_kpresp;
-    P.ptx = c->d_ptx; P.pty = c->d_pty; P.ptz = c->d_ptz; P.uright = c->d_uright;
+    P.ptx = c->d_ptx; P.pty = c->d_pty; P.ptz = c->d_ptz; P.uright = c->d_uright; P.kpux = c->d_kpux; P.kpuy = c->d_kpuy;
+    P.distorted = c->cfg.k1 != 0.0f ? 1 : 0;
+    P.und = UndistortParams{ (double)c->cfg.fx, (double)c->cfg.fy, (double)c->cfg.cx, (double)c->cfg.cy, (double)c->cfg.k1, (double)c->cfg.k2,
+        (double)c->cfg.p1, (double)c->cfg.p2, (double)c->cfg.k3 };
     P.kpoct = c->d_kpoct; P.kplxy = c->d_kplxy; P.desc = c->d_desc; P.count = c->d_count;
     if (c->cur_depth) {
         P.depth = c->cur_depth - (long long)c->cur_slot0 * c->cur_depthFrameStride;

@@ -239,7 +239,7 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n)
     P.cellSlotTotal = c->cellSlotTotal; P.nCellsTotal = c->nCellsTotal; P.iniTh = c->cfg.ini_th_fast; P.minTh = c->cfg.min_th_fast;
     P.slot0 = slot0; P.z0 = c->cur_slot0;
     if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
-    if (smem > 48 * 1024) {
+    {   // static + dynamic shared memory can exceed the 48 KB default while the dynamic part alone does not: always opt in
         cudaError_t e = cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "fast smem attr", __FILE__, __LINE__);
     }

@@ -6,7 +6,7 @@
 //   level candidates         : [B][candTotal] u32 in reference order + [B][L] counts
 //   level keypoints          : [B][kpStageTotal] u32 (quadtree output, list order) + [B][L] counts
 //   frame SoA                : kp_x,kp_y,kp_size,kp_angle,kp_resp [B][K] f32; kp_oct [B][K] i32; kp_lxy [B][K] u32;
-//                              desc [B][K][32] u8; pt_x,pt_y,pt_z,u_right [B][K] f32; count [B]
+//                              desc [B][K][32] u8; pt_x,pt_y,pt_z,u_right,kpu_x,kpu_y [B][K] f32; count [B]
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -86,7 +86,7 @@ struct orbf_context {
     // chunked multi-stream pipeline: a batch call forks the caller-visible stream into nWork worker streams, enqueues
     // chunk k (H2D copies + all stages of its frames and frame pairs) on worker k % nWork, and joins them again
     cudaStream_t work[ORBF_MAX_WORKERS]; int nWork, chunkFrames;
-    cudaEvent_t evFork, evDone[ORBF_MAX_WORKERS], evExtract[ORBF_MAX_WORKERS], evLatch;
+    cudaEvent_t evFork, evDone[ORBF_MAX_WORKERS], evExtract[ORBF_MAX_WORKERS];
     // high-priority side stream for the latency-bound stages (quadtree, RANSAC): their few, long-running CTAs are placed as
     // soon as SM resources free up and overlap the throughput-bound kernels (blur, Hamming) still running on the main stream
     cudaStream_t hi; cudaEvent_t evHiA, evHiB, evHiGroup[8];
@@ -119,7 +119,7 @@ struct orbf_context {
     uint32_t* d_cand; int* d_candCount;
     uint16_t* d_nodeScratch;
     uint32_t* d_lkp; int* d_lkpCount;
-    float *d_kpx, *d_kpy, *d_kpsize, *d_kpangle, *d_kpresp, *d_ptx, *d_pty, *d_ptz, *d_uright;
+    float *d_kpx, *d_kpy, *d_kpsize, *d_kpangle, *d_kpresp, *d_ptx, *d_pty, *d_ptz, *d_uright, *d_kpux, *d_kpuy;
     int* d_kpoct; uint32_t* d_kplxy; uint8_t* d_desc; int* d_count;
     orbf_keypoint* d_kpAos;   // staging for D2H in cv::KeyPoint layout
     // host staging (pinned)
@@ -141,7 +141,7 @@ struct orbf_context {
     orbf_ransac_result* d_rres;                   // [P]
     void* d_rstate;                               // [P] sequential accept-rule state (ransac.cu: RState, 28 B)
     orbf_dmatch* d_inliers;                       // [P][K]
-    double* d_depthCov;                           // [1] latched covariance
+    double* d_depthCov;                           // [2]: covariance latched on the context (quirk Q7), per-call value
     float* d_sxyz; float* d_txyz;                 // standalone staging: SoA x|y|z, grown on demand
     int xyzStageRows;
     void* d_pts; size_t ptsCap;                   // packed sorted correspondences [P][K] (ransac.cu: Pt6)
@@ -220,8 +220,8 @@ struct RansacSet {
     int nsrc, ndst;
 };
 int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int n, float* dT);
-// pairs [pair0, pair0 + npairs).  latchMode 0: this group owns pair 0 — latch the depth covariance (quirk Q7) after
-// its prepare kernel and record ctx->evLatch; 1: wait for ctx->evLatch before scoring hypotheses.
+// pairs [pair0, pair0 + npairs).  The depth covariance (quirk Q7) is latched by the first pair, in enqueue order, that reaches
+// scoring; standalone = the call neither sees nor replaces the value latched on the context (orbf_ransac_iterate).
 int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);
 int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, int latchMode, bool fullTable = false);
+    const int* d_userSamples, bool standalone, bool fullTable = false, bool probeOnly = false);

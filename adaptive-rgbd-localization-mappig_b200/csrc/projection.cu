@@ -15,6 +15,7 @@
 //      ratio test (double); the accepted feature is marked taken.  A window of 8 px holds ~1 candidate, so this pass is a few
 //      tens of instructions per landmark.
 #include "orbf_internal.h"
+#include "undistort_device.h"
 
 namespace {
 
@@ -233,27 +234,11 @@ __global__ void __launch_bounds__(256) bow_emit_kernel(const int* __restrict__ i
 // ---- Frame::UndistortKeyPoints (Core/frame.cpp:286-313): cv::undistortPoints(pts, pts, K, dist, Mat(), K) --------------------------
 // cvUndistortPointsInternal with the default criteria (5 fixed iterations), every operation in double in OpenCV's order (the
 // library is compiled with -fmad=false, so nothing contracts); thread per point.
-struct UndistortParams { double fx, fy, cx, cy, k1, k2, p1, p2, k3; };
-
 __global__ void __launch_bounds__(128) undistort_kernel(UndistortParams U, const float* __restrict__ xy, int n, float* __restrict__ out)
 {
     const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    const double px = xy[2 * i], py = xy[2 * i + 1], ifx = 1.0 / U.fx, ify = 1.0 / U.fy;
-    double x = (px - U.cx) * ifx, y = (py - U.cy) * ify;
-    const double x0 = x, y0 = y;
-    for (int j = 0; j < 5; ++j) {
-        const double r2 = x * x + y * y;
-        const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((U.k3 * r2 + U.k2) * r2 + U.k1) * r2);
-        if (icdist < 0) { x = (px - U.cx) * ifx; y = (py - U.cy) * ify; break; }
-        const double deltaX = 2 * U.p1 * x * y + U.p2 * (r2 + 2 * x * x) + 0.0 * r2 + 0.0 * r2 * r2;
-        const double deltaY = U.p1 * (r2 + 2 * y * y) + 2 * U.p2 * x * y + 0.0 * r2 + 0.0 * r2 * r2;
-        x = (x0 - deltaX) * icdist;
-        y = (y0 - deltaY) * icdist;
-    }
-    const double xx = U.fx * x + 0.0 * y + U.cx, yy = 0.0 * x + U.fy * y + U.cy, ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
-    out[2 * i] = (float)(xx * ww);
-    out[2 * i + 1] = (float)(yy * ww);
+    undistort_point(U, xy[2 * i], xy[2 * i + 1], &out[2 * i], &out[2 * i + 1]);
 }
 
 }  // namespace

@@ -244,7 +244,7 @@ int orbf_launch_pyramid(orbf_context* c, int slot0, int n)
     P.tileStride = maxBytes;
     const size_t smem = (size_t)maxBytes * TL_WARPS + 16;            // + slack: a lane reads up to 11 bytes past its last column
     if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
-    if (smem > 48 * 1024) {
+    {
         cudaError_t e = cudaFuncSetAttribute(resize_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "resize smem attr", __FILE__, __LINE__);
     }

@@ -37,6 +37,7 @@ struct RansacParams {
     orbf_hyp_trace* hyp; orbf_ransac_result* res; orbf_dmatch* inliers;
     double* depthCov;
     int K, iters, S;
+    int covReset;             // standalone call: ignore (and do not touch) the covariance latched on the context
     int tabRows;              // sample-table rows ransac_prepare draws itself; ransac_table_kernel completes the table for the pairs that go on
     double covX, covY;
 };
@@ -333,24 +334,28 @@ __global__ void __launch_bounds__(32) ransac_table_kernel(RansacParams P)
     }
 }
 
-__global__ void ransac_latch_kernel(RansacParams P)
+__global__ void ransac_latch_kernel(RansacParams P, int npairs)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double cz = P.cfg.depth_cov;
     if (!(cz >= 0.0)) {
-        cz = *P.depthCov;                       // value latched by an earlier call on this context (negative if none)
-        if (!(cz >= 0.0)) {
-            const int M = P.goodCount[0];
-            const Pt6* pts = P.pts;
-            if ((unsigned)M >= P.cfg.min_inlier_th && M >= P.S)
-                for (int i = 0; i < M; ++i) {
-                    const Pt6 p = pts[i];
-                    if (p.sz == 0.0f || p.tx == 0.0f) continue;
-                    if (isnan(p.sz) || isnan(p.tz)) continue;
-                    const double sd = 0.01 * (double)p.sz * (double)p.sz;
-                    cz = sd * sd;
-                    break;
-                }
+        cz = P.covReset ? -1.0 : *P.depthCov;   // value latched by an earlier call on this context (negative if none)
+        // The reference latches on the first ErrorFunction2 call of the process, i.e. in the first pair (in call order) that
+        // gets as far as scoring — Iterate returns early below minInlierTh matches / good matches (ransac.cpp:165,191) — at
+        // the first correspondence ComputeInliersAndError does not skip (:326) and ErrorFunction2 does not reject as NaN (:362).
+        for (int q = 0; q < npairs && !(cz >= 0.0); ++q) {
+            const int pair = P.pair0 + q;
+            const int M = P.goodCount[pair];
+            if ((unsigned)P.rs.matchCount[pair] < P.cfg.min_inlier_th || (unsigned)M < P.cfg.min_inlier_th || M > 2048) continue;
+            const Pt6* pts = P.pts + (long long)pair * P.K;
+            for (int i = 0; i < M; ++i) {
+                const Pt6 p = pts[i];
+                if (p.sz == 0.0f || p.tx == 0.0f) continue;
+                if (isnan(p.sz) || isnan(p.tz)) continue;
+                const double sd = 0.01 * (double)p.sz * (double)p.sz;
+                cz = sd * sd;
+                break;
+            }
         }
     }
     *P.depthCov = cz;
@@ -864,7 +869,7 @@ int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
 }
 
 int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, int latchMode, bool fullTable)
+    const int* d_userSamples, bool standalone, bool fullTable, bool probeOnly)
 {
     if (npairs <= 0) return ORBF_OK;
     {
@@ -875,7 +880,10 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     RansacParams P;
     P.rs = rs; P.cfg = cfg; P.good = c->d_good; P.goodCount = c->d_goodCount; P.pts = reinterpret_cast<Pt6*>(c->d_pts);
     P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
-    P.depthCov = c->d_depthCov; P.K = c->K; P.iters = iters; P.S = S;
+    // slot 0 = the covariance latched on the context (quirk Q7), written only while it is still negative; slot 1 = per-call value of
+    // standalone calls and of calls with an explicit covariance, which must neither see nor replace the latched one
+    P.covReset = standalone ? 1 : 0;
+    P.depthCov = c->d_depthCov + ((standalone || cfg.depth_cov >= 0.0) ? 1 : 0); P.K = c->K; P.iters = iters; P.S = S;
     P.state = reinterpret_cast<RState*>(c->d_rstate); P.hypLo = 0; P.hypHi = iters; P.pair0 = pair0;
     constexpr int LAZY_ROWS = 8;                     // = the end of the second hypothesis wave
     P.tabRows = (fullTable || d_userSamples) ? iters : std::min(iters, LAZY_ROWS);
@@ -888,17 +896,17 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     orbf_prof_begin(c, ST_RANSAC_PREPARE);
     ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
-    if (latchMode == 0) {
-        ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P);
-        ORBF_LAUNCH_CHECK(c);
-        ORBF_CUDA(c, cudaEventRecord(c->evLatch, c->stream));
-    } else ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evLatch, 0));
+    // every group runs the latch (a no-op once a value >= 0 is there): groups of one sequence are enqueued in pair order on one stream,
+    // so a group whose pairs never reach scoring leaves the latch to the next one
+    ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P, npairs);
+    ORBF_LAUNCH_CHECK(c);
     orbf_prof_end(c, ST_RANSAC_PREPARE);
+    if (probeOnly) return ORBF_OK;
     orbf_prof_begin(c, ST_RANSAC_HYP);
     // waves of hypotheses: the reference usually stops after a handful of iterations (> 80 % inliers ends the loop,
     // accepted hypotheses skip 10-20 iterations ahead), so later waves find their pair already done and exit at once
     const size_t hypSmem = (size_t)HY_WARPS * c->K * (sizeof(float) + sizeof(uint16_t));
-    if (hypSmem > 48 * 1024) {
+    {   // static (masks) + dynamic shared memory can exceed the 48 KB default while the dynamic part alone does not: always opt in
         cudaError_t e = cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hypSmem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac hyp smem attr", __FILE__, __LINE__);
     }

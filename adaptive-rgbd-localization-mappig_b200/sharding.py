@@ -4,8 +4,9 @@ SURVEY.md §8(e): extraction is independent per frame, matching + RANSAC per con
 n frames is cut into `world` contiguous chunks; rank r > 0 additionally extracts the last frame of rank r-1 (a halo
 frame: 300 KB of H2D and one extra extraction, instead of a 44 KB peer copy on the critical path) so that the pair that
 straddles two chunks has an owner.  The only scalar that crosses ranks is the depth covariance the reference latches in a
-function-local static on the first pair it ever scores (quirk Q7, Odometry/ransac.cpp:416-421): rank 0 computes it
-from pair 0 and broadcasts 8 bytes before any rank scores a hypothesis.
+function-local static on the first pair it ever scores (quirk Q7, Odometry/ransac.cpp:416-421): every rank probes the value its
+own pairs would latch (the first of them, in order, that reaches scoring — pair 0 of a shard may well have too few matches), the
+8-byte candidates are all-gathered, and the first valid one in rank order is what every rank scores with.
 
 BASELINE config 5 (keyframe-database many-to-many matching) is the one place with a real exchange step: every rank
 holds a shard of the keyframe descriptors; `gather_keyframes` all-gathers the shards over NCCL (NVLink 5 / NVSwitch) into
@@ -34,14 +35,18 @@ def frame_shard(n_frames, world, rank):
     return dict(start=start, stop=stop, halo=halo, first=first, pairs=(p0, p1))
 
 
-def broadcast_depth_cov(value, group=None, device="cpu"):
-    """Quirk Q7: rank 0's latched depth covariance (a Python float, < 0 if none yet) -> every rank."""
+def first_depth_cov(local_value, group=None, device="cpu"):
+    """Quirk Q7 across ranks: every rank contributes the covariance its own pairs would latch (< 0 if none of them reaches scoring);
+    the globally first pair that scores belongs to the lowest rank with a valid candidate."""
     import torch
     import torch.distributed as dist
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.broadcast(t, src=0, group=group)
-    return float(t.item())
+    t = torch.tensor([float(local_value)], dtype=torch.float64, device=device)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return float(t.item())
+    allv = torch.empty(dist.get_world_size(group), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(allv, t, group=group)
+    valid = [float(v) for v in allv.cpu() if float(v) >= 0.0]
+    return valid[0] if valid else -1.0
 
 
 def run_sequence_shard(ctx, frames, depths, n_frames_total, rank, world, ratio=0.8, cross_check=True, seed=42, group=None,
@@ -53,23 +58,19 @@ def run_sequence_shard(ctx, frames, depths, n_frames_total, rank, world, ratio=0
     sh = frame_shard(n_frames_total, world, rank)
     n_local = sh["stop"] - sh["first"]
     assert len(frames) == n_local, (len(frames), n_local)
-    # depth covariance of the globally first pair: computed by rank 0 on its first two frames, then broadcast
-    cov = -1.0
-    if first_pair_cov is not None:
-        cov = first_pair_cov
-    elif rank == 0 and n_local >= 2:
-        ctx.extract_batch(frames[:2], depths[:2])
-        ctx.match_pairs(np.array([[0, 1]], np.int32), ratio, cross_check)
-        ctx.ransac_pairs(1, seed=seed, depth_cov=-1.0)
-        cov = ctx.download_ransac(0)["depth_cov"]
-    cov = broadcast_depth_cov(cov, group, device)
-    if n_local == 0:
-        return sh, [], cov
-    ctx.extract_batch(frames, depths)
-    npairs = n_local - 1
-    results = []
+    npairs = max(n_local - 1, 0)
+    if n_local > 0:
+        ctx.extract_batch(frames, depths)
     if npairs > 0:
         ctx.match_pairs(np.array([[i, i + 1] for i in range(npairs)], np.int32), ratio, cross_check)
+    # depth covariance: the value latched by the globally first pair that reaches scoring, agreed on before any rank scores
+    if first_pair_cov is not None:
+        cov = first_pair_cov
+    else:
+        local = ctx.ransac_probe_depth_cov(npairs, seed=seed + sh["pairs"][0]) if npairs > 0 else -1.0
+        cov = first_depth_cov(local, group, device)
+    results = []
+    if npairs > 0:
         # the library seeds pair slot k with seed + k: offset so that global pair p gets seed + p
         ctx.ransac_pairs(npairs, seed=seed + sh["pairs"][0], depth_cov=cov)
         for k in range(npairs):

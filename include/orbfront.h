@@ -41,7 +41,8 @@ extern "C" {
 #endif
 
 #define ORBF_MAX_LEVELS 16
-#define ORBF_ABI_VERSION 4   /* 4: + projection_match, fuse_search, bow_match, compose_trajectory, undistort_points */
+#define ORBF_ABI_VERSION 5   /* 4: + projection_match, fuse_search, bow_match, compose_trajectory, undistort_points
+                                5: + distortion coefficients in orbf_config (mvKeysUn feeds the unprojection), orbf_download_keys_un */
 
 typedef enum {
     ORBF_OK = 0,
@@ -76,6 +77,12 @@ typedef struct {
                                           samples a frame needs are read in place over PCIe by the kernel that unprojects
                                           the keypoints (0 = default on, -1 = always stage the whole plane in HBM)          */
     int32_t reserved_;
+    float k1, k2, p1, p2, k3;          /* Calibration::k1.. (Utils/common.h:40-44) as Frame::Frame loads them into mDistCoef
+                                          (Core/frame.cpp:32-42).  k1 == 0 (the default, and what the synthetic benchmarks use)
+                                          is the reference's own shortcut mvKeysUn = mvKeys (frame.cpp:288-291); otherwise
+                                          every keypoint goes through cv::undistortPoints (frame.cpp:294-312) before mvuRight
+                                          and mvKeys3Dc are formed from it (frame.cpp:157-162); the depth sample is still
+                                          looked up at the distorted keypoint (frame.cpp:152-155, quirk Q11)              */
 } orbf_config;
 
 typedef struct {
@@ -162,6 +169,9 @@ int orbf_track_sequence_device(orbf_context* ctx, int32_t slot0, int32_t n, cons
 int orbf_download_frame(orbf_context* ctx, int32_t slot, orbf_keypoint* kps, uint8_t* desc, float* xyz,
     int32_t cap, int32_t* n_out);
 int orbf_frame_counts(orbf_context* ctx, int32_t slot0, int32_t n, int32_t* counts);
+/* Frame::mvKeysUn of a slot: n interleaved (x, y) floats, the undistorted keypoint positions (= the keypoints when k1 == 0);
+ * u_right (may be NULL) = Frame::mvuRight.                                                                              */
+int orbf_download_keys_un(orbf_context* ctx, int32_t slot, float* xy, float* u_right, int32_t cap, int32_t* n_out);
 /* Parity / mvImagePyramid access: level image, blurred level, FAST candidates (reference order). */
 int orbf_pyramid_level(orbf_context* ctx, int32_t slot, int32_t level, int32_t blurred, uint8_t* out, int32_t out_stride);
 int orbf_level_candidates(orbf_context* ctx, int32_t slot, int32_t level, orbf_cand* out, int32_t cap, int32_t* n_out);
@@ -184,7 +194,8 @@ int orbf_distinctive_descriptors(orbf_context* ctx, const uint8_t* desc, const i
     int32_t* median);
 /* Frame::UndistortKeyPoints (Core/frame.cpp:286-313): cv::undistortPoints(pts, pts, K, dist, Mat(), K) with OpenCV's default 5 iterations;
  * xy / out = n interleaved (x, y) floats (may alias), dist = {k1, k2, p1, p2, k3}.  The same call on the four image corners gives
- * ComputeImageBounds (frame.cpp:320-343).  The extraction entry points assume k1 == 0 (mvKeysUn = mvKeys, frame.cpp:288-291).      */
+ * ComputeImageBounds (frame.cpp:320-343).  The extraction entry points apply the same arithmetic to their keypoints when
+ * orbf_config.k1 != 0 (see there).                                                                                      */
 int orbf_undistort_points(orbf_context* ctx, const float* xy, int32_t n, float fx, float fy, float cx, float cy, const float* dist, float* out);
 /* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) for one frame: landmarks projected into the frame are matched, in order,
  * to the features inside the square window |dx| < radius && |dy| < radius; best <= th_high, and rejected when best and second best
@@ -230,6 +241,9 @@ int orbf_ransac_iterate(orbf_context* ctx, const orbf_ransac_config* cfg, const 
     orbf_dmatch* good_sorted_out, int32_t* sample_table_out);
 /* Device-resident: RANSAC on the pairs last matched by orbf_match_pairs. */
 int orbf_ransac_pairs(orbf_context* ctx, int32_t npairs, const orbf_ransac_config* cfg);
+/* Quirk Q7 across shards: the covariance these pairs would latch on a fresh process (first pair, in order, that reaches scoring;
+ * -1 if none does).  Neither reads nor writes the value latched on the context.                                              */
+int orbf_ransac_probe_depth_cov(orbf_context* ctx, int32_t npairs, const orbf_ransac_config* cfg, double* cov);
 int orbf_download_ransac(orbf_context* ctx, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap);
 int orbf_download_ransac_summary(orbf_context* ctx, int32_t npairs, orbf_ransac_result* out /* [npairs] */);
 int orbf_kabsch(orbf_context* ctx, const float* setA, const float* setB, int32_t n, float* T16);

@@ -212,9 +212,22 @@ FR1 = dict(fx=517.3, fy=516.5, cx=318.6, cy=255.3, mbf=40.0, depth_factor=np.flo
 
 
 def unproject(kps, depth, depth_factor=FR1["depth_factor"], fx=FR1["fx"], fy=FR1["fy"], cx=FR1["cx"], cy=FR1["cy"],
-              mbf=FR1["mbf"]):
-    """Frame::ExtractFeatures depth gather + unprojection (frame.cpp:148-164)."""
+              mbf=FR1["mbf"], dist=None):
+    """Frame::ExtractFeatures depth gather + unprojection (frame.cpp:148-164).  dist = (k1, k2, p1, p2, k3) with k1 != 0 runs
+    Frame::UndistortKeyPoints first (frame.cpp:286-313) and unprojects mvKeysUn; the depth lookup stays at the distorted keypoint."""
     kps = np.ascontiguousarray(kps, KEYPOINT_DT)
+    if dist is not None and float(dist[0]) != 0.0:
+        xy = np.stack([kps["x"], kps["y"]], 1).astype(np.float32) if len(kps) else np.zeros((0, 2), np.float32)
+        xy_un = undistort_points(xy, fx, fy, cx, cy, dist)
+        h, w = depth.shape
+        xyz = np.zeros((len(kps), 3), np.float32); ur = np.zeros(len(kps), np.float32)
+        if depth.dtype == np.uint16:
+            d = np.ascontiguousarray(depth); args = (_p(d), None)
+        else:
+            d = np.ascontiguousarray(depth, np.float32); args = (None, _p(d))
+        _chk(lib().orc_unproject_un(_p(kps), _p(xy_un), len(kps), args[0], args[1], w, h, w, C.c_float(depth_factor), C.c_float(fx),
+                                    C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(mbf), _p(xyz), _p(ur)), "unproject_un")
+        return xyz, ur
     h, w = depth.shape
     xyz = np.zeros((len(kps), 3), np.float32); ur = np.zeros(len(kps), np.float32)
     if depth.dtype == np.uint16:

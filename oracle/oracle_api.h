@@ -55,6 +55,8 @@ int orc_extract(const orc_extract_cfg* cfg, const uint8_t* img, int stride, orc_
     int* n_out, orc_extract_debug* dbg);
 int orc_unproject(const orc_keypoint* kps, int n, const uint16_t* depth_u16, const float* depth_f32, int w, int h,
     int dstride_elems, float depth_factor, float fx, float fy, float cx, float cy, float mbf, float* xyz, float* uright);
+int orc_unproject_un(const orc_keypoint* kps, const float* xy_un, int n, const uint16_t* depth_u16, const float* depth_f32, int w, int h,
+    int dstride_elems, float depth_factor, float fx, float fy, float cx, float cy, float mbf, float* xyz, float* uright);
 
 /* ---- adaptive FAST detector route (Features/video*adaptedfeaturedetector.cpp, detectoradjuster.cpp, extractor.cpp:52-77) ---- */
 typedef struct {

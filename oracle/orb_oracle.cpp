@@ -723,4 +723,31 @@ int orc_unproject(const orc_keypoint* kps, int n, const uint16_t* depth_u16, con
     return ORC_OK;
 }
 
+// The same with mvKeysUn (Core/frame.cpp:148-164): the depth is looked up at the distorted keypoint kp (:152-155), mvuRight and
+// mvKeys3Dc are formed from the undistorted kpU = xy_un[i] (:157-162).  xy_un == NULL is the k1 == 0 shortcut (frame.cpp:288-291).
+int orc_unproject_un(const orc_keypoint* kps, const float* xy_un, int n, const uint16_t* depth_u16, const float* depth_f32, int w, int h,
+    int dstride_elems, float depth_factor, float fx, float fy, float cx, float cy, float mbf, float* xyz, float* uright)
+{
+    if (!xy_un) return orc_unproject(kps, n, depth_u16, depth_f32, w, h, dstride_elems, depth_factor, fx, fy, cx, cy, mbf, xyz, uright);
+    const float invfx = 1.0f / fx, invfy = 1.0f / fy;
+    for (int i = 0; i < n; ++i) {
+        const int u = (int)kps[i].x, v = (int)kps[i].y;
+        const float xu = xy_un[2 * i], yu = xy_un[2 * i + 1];
+        float X = 0, Y = 0, Z = 0, ur = -1;
+        if (u >= 0 && v >= 0 && u < w && v < h) {
+            const float z = depth_f32 ? depth_f32[(size_t)v * dstride_elems + u]
+                                      : (float)depth_u16[(size_t)v * dstride_elems + u] * depth_factor;
+            if (z > 0) {
+                ur = xu - mbf / z;
+                X = (xu - cx) * z * invfx;
+                Y = (yu - cy) * z * invfy;
+                Z = z;
+            }
+        }
+        xyz[3 * i] = X; xyz[3 * i + 1] = Y; xyz[3 * i + 2] = Z;
+        if (uright) uright[i] = ur;
+    }
+    return ORC_OK;
+}
+
 }  // extern "C"

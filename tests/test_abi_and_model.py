@@ -20,13 +20,13 @@ def test_library_exports_every_declared_symbol(ob):
     L = ob.lib()
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.orbf_abi_version() == 4
+    assert L.orbf_abi_version() == 5
 
 
 def test_struct_layouts_match_header(ob):
     import ctypes as C
     assert ob.KEYPOINT_DT.itemsize == 28 and ob.DMATCH_DT.itemsize == 16      # cv::KeyPoint / cv::DMatch mirrors
-    assert C.sizeof(ob.Config) == 80 and C.sizeof(ob.RansacConfig) == 40 and C.sizeof(ob.RansacResult) == 104
+    assert C.sizeof(ob.Config) == 100 and C.sizeof(ob.RansacConfig) == 40 and C.sizeof(ob.RansacResult) == 104
     assert ob.HYP_DT.itemsize == 80
     cfg = ob.default_config()
     assert (cfg.width, cfg.height, cfg.nfeatures, cfg.nlevels, cfg.ini_th_fast, cfg.min_th_fast) == (640, 480, 1000, 8, 20, 7)

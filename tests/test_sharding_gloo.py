@@ -54,6 +54,14 @@ class OracleContext:
             self.results.append(r)
         self.latched = cov
 
+    def ransac_probe_depth_cov(self, npairs, seed=42, **kw):
+        for k in range(npairs):
+            a, b = self.pairs[k]
+            cov = self.orc.ransac_iterate(self.frames[a][2], self.frames[b][2], self.matches[k], seed=seed + k, depth_cov=-1.0)["depth_cov"]
+            if cov >= 0:
+                return cov
+        return -1.0
+
     def download_ransac(self, k):
         return dict(self.results[k])
 
@@ -63,7 +71,7 @@ def free_port():
     return p
 
 
-def _worker(rank, world, port, n_frames, out_dir):
+def _worker(rank, world, port, n_frames, out_dir, dead_first=False):
     import torch
     import torch.distributed as dist
     sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
@@ -75,6 +83,8 @@ def _worker(rank, world, port, n_frames, out_dir):
         sh = sh_mod.frame_shard(n_frames, world, rank)
         ids = range(sh["first"], sh["stop"])
         frames = np.stack([synth.make_frame(tex, i) for i in ids]); depths = np.stack([synth.make_depth(i) for i in ids])
+        if dead_first and rank == 0:
+            frames[0] = 128                     # rank 0's first pair has no matches: the covariance comes from a later pair
         ctx = OracleContext()
         shard, results, cov = sh_mod.run_sequence_shard(ctx, frames, depths, n_frames, rank, world, seed=42)
         np.savez(Path(out_dir) / f"rank{rank}.npz", cov=cov, pairs=np.array([r["pair"] for r in results]),
@@ -127,15 +137,17 @@ def test_frame_shard_partitions_every_pair_once():
         sh.frame_shard(4, 2, 2)
 
 
-def test_two_rank_gloo_run_equals_single_process(tmp_path, orc, texture):
+@pytest.mark.parametrize("n,dead_first", [(5, False), (4, True)])
+def test_two_rank_gloo_run_equals_single_process(tmp_path, orc, texture, n, dead_first):
     import torch.multiprocessing as mp
     import synth
-    n = 5
     port = free_port()
-    mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n, str(tmp_path), dead_first), nprocs=2, join=True)
     # single-process reference: the whole sequence on one rank
     ctx = OracleContext()
     frames = np.stack([synth.make_frame(texture, i) for i in range(n)]); depths = np.stack([synth.make_depth(i) for i in range(n)])
+    if dead_first:
+        frames[0] = 128
     _, ref, cov = load_sharding().run_sequence_shard(ctx, frames, depths, n, 0, 1, seed=42)
     got = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
     assert all(float(g["cov"]) == cov for g in got), "depth covariance must be the globally first pair's on every rank"

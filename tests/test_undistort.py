@@ -35,3 +35,29 @@ def test_cuda_matches_oracle(ob, orc, k):
     ctx = ob.Context(max_frames=2)
     assert np.array_equal(ctx.undistort_points(pts, FX, FY, CX, CY, DISTS[k]), orc.undistort_points(pts, FX, FY, CX, CY, DISTS[k]))
     assert len(ctx.undistort_points(pts[:0], FX, FY, CX, CY, DISTS[k])) == 0
+
+
+def test_oracle_unprojects_the_undistorted_keypoint(orc):
+    """Core/frame.cpp:148-164: depth at the truncated DISTORTED keypoint, mvuRight / mvKeys3Dc from mvKeysUn — restated here with numpy
+    float32 operations on top of cv2.undistortPoints."""
+    import cv2
+    rng = np.random.default_rng(3)
+    n = 500
+    kps = np.zeros(n, orc.KEYPOINT_DT)
+    kps["x"] = rng.uniform(19, 620, n).astype(np.float32); kps["y"] = rng.uniform(19, 460, n).astype(np.float32)
+    depth = rng.integers(0, 20000, size=(480, 640)).astype(np.uint16)
+    depth[rng.random((480, 640)) < 0.1] = 0
+    K = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1]], np.float32)
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    un = cv2.undistortPoints(xy.reshape(-1, 1, 2), K, DISTS[0], None, K).reshape(-1, 2)
+    f32 = np.float32
+    z = depth[kps["y"].astype(np.int64), kps["x"].astype(np.int64)].astype(f32) * f32(1.0 / 5000.0)
+    ok = z > 0
+    invfx, invfy = f32(1.0) / f32(FX), f32(1.0) / f32(FY)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        X = np.where(ok, (un[:, 0] - f32(CX)) * z * invfx, f32(0)); Y = np.where(ok, (un[:, 1] - f32(CY)) * z * invfy, f32(0))
+        ur = np.where(ok, un[:, 0] - f32(40.0) / z, f32(-1))
+    xyz, got_ur = orc.unproject(kps, depth, dist=DISTS[0])
+    assert np.array_equal(xyz, np.stack([X, Y, np.where(ok, z, f32(0))], 1).astype(f32)) and np.array_equal(got_ur, ur.astype(f32))
+    plain, _ = orc.unproject(kps, depth)                      # k1 == 0 shortcut
+    assert np.array_equal(plain, orc.unproject(kps, depth, dist=np.zeros(5, np.float32))[0]) and not np.array_equal(plain, xyz)
