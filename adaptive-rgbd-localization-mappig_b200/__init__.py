@@ -457,6 +457,12 @@ class Context:
                                              _p(used), _p(found)), "adaptive_detect")
         return [out[i, :counts[i]].copy() for i in range(n)], used, found
 
+    def selftest_sincosf_device(self, lo_bits, hi_bits):
+        """Device restatement of glibc sinf / cosf over the floats with bit patterns [lo, hi]: [n, 2] (sin, cos)."""
+        out = np.zeros((int(hi_bits) - int(lo_bits) + 1, 2), np.float32)
+        self._chk(lib().orbf_selftest_sincosf_device(self._h, C.c_uint32(lo_bits), C.c_uint32(hi_bits), _p(out)), "selftest_sincosf_device")
+        return out
+
     # ---- keyframe store ----
     def kfdb_reserve(self, n):
         self._chk(lib().orbf_kfdb_reserve(self._h, n), "kfdb_reserve")
@@ -515,3 +521,15 @@ def selftest_sample_table(seed, M, iterations=200, sample_size=4):
     if rc:
         raise OrbfError(rc, "selftest_sample_table")
     return out
+
+
+def selftest_sincosf(lo_bits, hi_bits, want_values=False):
+    """Host restatement of glibc sinf / cosf (csrc/glibc_sincosf.h) over the floats with bit patterns [lo, hi]:
+    (number of inputs where it differs from this machine's libm, values [n, 2] (sin, cos) or None)."""
+    n = int(hi_bits) - int(lo_bits) + 1
+    out = np.zeros((n, 2), np.float32) if want_values else None
+    nd = C.c_int64(0)
+    rc = lib().orbf_selftest_sincosf(C.c_uint32(lo_bits), C.c_uint32(hi_bits), _p(out), C.byref(nd))
+    if rc:
+        raise OrbfError(rc, "selftest_sincosf")
+    return nd.value, out

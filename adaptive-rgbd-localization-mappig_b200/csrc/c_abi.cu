@@ -7,6 +7,7 @@
 
 #include "orbf_internal.h"
 #include "replay.h"
+#include "glibc_sincosf.h"
 
 #define CTX_ENTER(c)                                                                   \
     do {                                                                               \
@@ -931,6 +932,45 @@ extern "C" int orbf_selftest_glibc_rand(uint32_t seed, int32_t n, int32_t* out)
     replay::GlibcRand g;
     g.seed(seed);
     for (int i = 0; i < n; ++i) out[i] = g.next();
+    return ORBF_OK;
+}
+
+// host restatement of glibc's sinf / cosf (csrc/glibc_sincosf.h) over the floats with bit patterns [lo, hi]: out (optional) receives
+// sin then cos of each; n_diff the number of inputs where either differs from THIS machine's libm sinf / cosf
+extern "C" int orbf_selftest_sincosf(uint32_t lo, uint32_t hi, float* out, int64_t* n_diff)
+{
+    if (hi < lo) return ORBF_ERR_ARG;
+    int64_t nd = 0;
+    for (uint64_t b = lo; b <= hi; ++b) {
+        float x; const uint32_t bb = (uint32_t)b; memcpy(&x, &bb, 4);
+        const float s = replay::glibc_sinf(x), c = replay::glibc_cosf(x);
+        if (out) { out[2 * (b - lo)] = s; out[2 * (b - lo) + 1] = c; }
+        if (n_diff) nd += (s != sinf(x)) || (c != cosf(x));
+    }
+    if (n_diff) *n_diff = nd;
+    return ORBF_OK;
+}
+
+// the device restatement over the same range: out = sin then cos of each input (device-computed, copied back)
+__global__ void selftest_sincosf_kernel(uint32_t lo, uint32_t count, float* out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float x = __uint_as_float(lo + i);
+    out[2 * (size_t)i] = replay::glibc_sinf(x); out[2 * (size_t)i + 1] = replay::glibc_cosf(x);
+}
+extern "C" int orbf_selftest_sincosf_device(orbf_context* c, uint32_t lo, uint32_t hi, float* out)
+{
+    CTX_ENTER(c);
+    if (hi < lo || !out || (uint64_t)hi - lo >= (1u << 28)) return ORBF_ERR_ARG;
+    const uint32_t count = hi - lo + 1;
+    float* d = nullptr;
+    ORBF_CUDA(c, cudaMalloc((void**)&d, (size_t)count * 2 * sizeof(float)));
+    selftest_sincosf_kernel<<<(count + 255) / 256, 256, 0, c->stream>>>(lo, count, d);
+    cudaError_t e = cudaMemcpyAsync(out, d, (size_t)count * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return orbf_cuda_fail(c, e, "selftest_sincosf", __FILE__, __LINE__);
     return ORBF_OK;
 }
 

@@ -10,6 +10,7 @@
 //   * Frame::ExtractFeatures' depth gather + unprojection (Core/frame.cpp:148-164) into SoA x/y/z.
 #include "orbf_internal.h"
 #include "undistort_device.h"
+#include "glibc_sincosf.h"
 
 namespace {
 
@@ -191,9 +192,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         // ---- steered BRIEF: (x*b + y*a, x*a - y*b) with separate mul / add, cvRound = round-half-even via the 1.5 * 2^23 trick
         // (FADD on the FMA pipe + IADD instead of F2I on the quarter-rate XU pipe; |v| <= 19 << 2^22) ------------------------
         const float ar = __fmul_rn(angle, factorPI);
-        double sn, cs;
-        sincos((double)ar, &sn, &cs);
-        const float a = (float)cs, b = (float)sn;
+        const float a = replay::glibc_cosf(ar), b = replay::glibc_sinf(ar);     // std::cos(float) / std::sin(float) of the reference: libm's cosf / sinf
         const int cx0 = x - ((x - ORBF_EDGE) & ~15);                      // window column of the keypoint
         const uint8_t* cb = sBlur[warp][buf] + ORBF_EDGE * ORBF_PATCH_BW + cx0;
         int val = 0;

@@ -474,7 +474,9 @@ void rbrief(const uint8_t* img, int stride, int x, int y, float angleDeg, uint8_
 {
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float angle = angleDeg * factorPI;
-    const float a = (float)std::cos((double)angle), b = (float)std::sin((double)angle);
+    // `(float)cos(angle)` with a float argument under `using namespace std` (orbextractor.cpp:7-8,45-46) is std::cos(float): libm's
+    // cosf / sinf, not the double functions (checked against the reference's own source in oracle/_ref)
+    const float a = cosf(angle), b = sinf(angle);
     const uint8_t* c = img + (size_t)y * stride + x;
     const int8_t* pat = kPattern;
     for (int i = 0; i < 32; ++i, pat += 32) {

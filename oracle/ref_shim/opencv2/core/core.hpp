@@ -1,0 +1,209 @@
+// oracle/ref_shim/opencv2/core/core.hpp — TEST INFRASTRUCTURE ONLY.
+// A minimal stand-in for the parts of OpenCV that /root/reference/Features/orbextractor.cpp (and the adaptive-detector sources
+// next to it) touch, so that those reference sources compile VERBATIM, from where they lie, with g++ alone (oracle/Makefile, target
+// _ref).  The container types (Mat with ROI views and reference counting, KeyPoint, Point, Size, Rect, Input/OutputArray) are
+// written here; the image-processing entry points (resize, FAST, GaussianBlur, fastAtan2) delegate to the routines of
+// oracle/orb_oracle.cpp that tests/test_oracle_vs_cv2.py pins bit for bit against the real library (cv2 4.13).  What the _ref build
+// therefore adds is the reference-AUTHORED logic run from the reference's own source: cell grid, FAST fallback, quadtree
+// distribution, orientation, steering, descriptor assembly, output order.
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../oracle_api.h"
+
+typedef unsigned char uchar;
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_32F 5
+#define CV_PI 3.1415926535897932384626433832795
+#define CV_WRAP
+#define CV_OUT
+#define CV_IN_OUT
+#define CV_EXPORTS
+#define CV_Assert(x) assert(x)
+
+inline int cvRound(double v) { return (int)std::nearbyint(v); }       // round half to even, like the SSE2 cvtsd2si OpenCV uses
+inline int cvRound(float v) { return (int)std::nearbyintf(v); }
+inline int cvRound(int v) { return v; }
+inline int cvFloor(double v) { return (int)std::floor(v); }
+inline int cvCeil(double v) { return (int)std::ceil(v); }
+
+namespace cv {
+
+template <typename T> struct Point_ {
+    T x, y;
+    Point_() : x(0), y(0) {}
+    Point_(T x_, T y_) : x(x_), y(y_) {}
+    template <typename U> Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
+    Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }
+};
+typedef Point_<int> Point2i;
+typedef Point_<int> Point;
+typedef Point_<float> Point2f;
+
+struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
+struct Rect { int x, y, width, height; Rect() : x(0), y(0), width(0), height(0) {} Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+struct Scalar { double v[4]; static Scalar all(double a) { Scalar s; s.v[0] = s.v[1] = s.v[2] = s.v[3] = a; return s; } };
+
+struct KeyPoint {
+    Point2f pt; float size, angle, response; int octave, class_id;
+    KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+    KeyPoint(float x, float y, float size_, float angle_ = -1, float response_ = 0, int octave_ = 0, int class_id_ = -1)
+        : pt(x, y), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
+};
+
+class Mat;
+struct MatZeros { int rows, cols, type; };            // what Mat::zeros returns: assigned INTO an existing Mat of the same shape
+
+class Mat {
+public:
+    int rows, cols; size_t step; uchar* data;
+    Mat() : rows(0), cols(0), step(0), data(nullptr), type_(0), esz_(1) {}
+    Mat(int r, int c, int type) : Mat() { create(r, c, type); }
+    Mat(Size sz, int type) : Mat() { create(sz.height, sz.width, type); }
+    Mat(int r, int c, int type, void* ext, size_t stp = 0) : rows(r), cols(c), step(stp ? stp : (size_t)c * esz(type)), data((uchar*)ext), type_(type), esz_(esz(type)) {}
+    Mat(const MatZeros& z) : Mat() { *this = z; }
+    static int esz(int type) { return type == CV_32F ? 4 : 1; }
+    void create(int r, int c, int type)
+    {
+        if (data && r == rows && c == cols && type == type_) return;       // cv::Mat::create: no reallocation for the same shape
+        buf_ = std::shared_ptr<uchar>(new uchar[(size_t)std::max(r, 0) * std::max(c, 0) * esz(type) + 64], std::default_delete<uchar[]>());
+        rows = r; cols = c; type_ = type; esz_ = esz(type); step = (size_t)c * esz_; data = buf_.get();
+    }
+    void release() { buf_.reset(); rows = cols = 0; step = 0; data = nullptr; }
+    bool empty() const { return !data || rows == 0 || cols == 0; }
+    int type() const { return type_; }
+    size_t step1() const { return step / esz_; }
+    Size size() const { return Size(cols, rows); }
+    Mat operator()(const Rect& r) const { Mat m(*this); m.data = data + (size_t)r.y * step + (size_t)r.x * esz_; m.rows = r.height; m.cols = r.width; return m; }
+    Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * esz_; m.cols = b - a; return m; }
+    Mat clone() const
+    {
+        Mat m(rows, cols, type_);
+        for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz_);
+        return m;
+    }
+    void copyTo(Mat& dst) const
+    {
+        dst.create(rows, cols, type_);
+        for (int r = 0; r < rows; ++r) std::memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz_);
+    }
+    template <typename T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <typename T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    uchar* ptr(int r = 0) { return data + (size_t)r * step; }
+    const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
+    static MatZeros zeros(int r, int c, int type) { MatZeros z = { r, c, type }; return z; }
+    // m = Mat::zeros(...): cv::MatExpr assignment creates (a no-op for an unchanged shape, so a rowRange view keeps pointing into its
+    // parent) and then clears in place
+    Mat& operator=(const MatZeros& z)
+    {
+        create(z.rows, z.cols, z.type);
+        for (int r = 0; r < rows; ++r) std::memset(data + (size_t)r * step, 0, (size_t)cols * esz_);
+        return *this;
+    }
+private:
+    int type_, esz_;
+    std::shared_ptr<uchar> buf_;
+};
+
+// cv::InputArray / cv::OutputArray: proxies around a Mat (all the reference passes through them)
+class _InputArray {
+public:
+    _InputArray() : m_(nullptr) {}
+    _InputArray(const Mat& m) : m_(const_cast<Mat*>(&m)) {}
+    bool empty() const { return !m_ || m_->empty(); }
+    Mat getMat() const { return m_ ? *m_ : Mat(); }
+protected:
+    Mat* m_;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray() {}
+    _OutputArray(Mat& m) : _InputArray(m) {}
+    void create(int r, int c, int type) const { if (m_) m_->create(r, c, type); }
+    void release() const { if (m_) m_->release(); }
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
+inline const _OutputArray& noArray() { static _OutputArray none; return none; }
+
+enum { BORDER_CONSTANT = 0, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
+enum { INTER_LINEAR = 1 };
+
+inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
+
+// cv::FAST(image, keypoints, threshold, nonmaxSuppression): FAST-9/16 on the matrix handed in (a view is its own image)
+inline void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true)
+{
+    const Mat m = image.getMat();
+    assert(nonmaxSuppression && m.type() == CV_8UC1);
+    keypoints.clear();
+    if (m.rows < 7 || m.cols < 7) return;
+    std::vector<orc_cand> out((size_t)m.rows * m.cols / 2 + 16);
+    int n = 0;
+    const int rc = orc_fast_roi(m.data, (int)m.step, m.cols, m.rows, threshold, out.data(), (int)out.size(), &n);
+    assert(rc == ORC_OK); (void)rc;
+    for (int i = 0; i < n; ++i) keypoints.push_back(KeyPoint((float)out[i].x, (float)out[i].y, 7.f, -1.f, (float)out[i].score));
+}
+
+inline void resize(InputArray src_, OutputArray dst_, Size dsize, double = 0, double = 0, int interpolation = INTER_LINEAR)
+{
+    assert(interpolation == INTER_LINEAR);
+    const Mat src = src_.getMat();
+    dst_.create(dsize.height, dsize.width, src.type());
+    Mat dst = dst_.getMat();
+    const int rc = orc_resize_linear(src.data, src.cols, src.rows, (int)src.step, dst.data, dst.cols, dst.rows, (int)dst.step);
+    assert(rc == ORC_OK); (void)rc;
+}
+
+// cv::copyMakeBorder, BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba).  src may be a view into dst (the reference builds its padded
+// pyramid that way, orbextractor.cpp:841-851): the interior is copied only when it lives elsewhere.
+inline void copyMakeBorder(InputArray src_, OutputArray dst_, int top, int bottom, int left, int right, int borderType)
+{
+    assert((borderType & ~BORDER_ISOLATED) == BORDER_REFLECT_101);
+    const Mat src = src_.getMat();
+    dst_.create(src.rows + top + bottom, src.cols + left + right, src.type());
+    Mat dst = dst_.getMat();
+    auto refl = [](int p, int n) { if (n == 1) return 0; while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p; return p; };
+    for (int r = 0; r < src.rows; ++r) {
+        uchar* d = dst.data + (size_t)(r + top) * dst.step;
+        const uchar* s = src.data + (size_t)r * src.step;
+        if (d + left != s) std::memmove(d + left, s, (size_t)src.cols);
+        for (int c = 0; c < left; ++c) d[c] = s[refl(c - left, src.cols)];
+        for (int c = 0; c < right; ++c) d[left + src.cols + c] = s[refl(src.cols + c, src.cols)];
+    }
+    for (int r = 0; r < top; ++r) std::memcpy(dst.data + (size_t)r * dst.step, dst.data + (size_t)(top + refl(r - top, src.rows)) * dst.step, (size_t)dst.cols);
+    for (int r = 0; r < bottom; ++r)
+        std::memcpy(dst.data + (size_t)(top + src.rows + r) * dst.step, dst.data + (size_t)(top + refl(src.rows + r, src.rows)) * dst.step, (size_t)dst.cols);
+}
+
+inline void GaussianBlur(InputArray src_, OutputArray dst_, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT)
+{
+    assert(ksize.width == 7 && ksize.height == 7 && sigmaX == 2 && sigmaY == 2 && borderType == BORDER_REFLECT_101);
+    const Mat src = src_.getMat();
+    Mat tmp = src.clone();                                             // the reference blurs in place
+    dst_.create(src.rows, src.cols, src.type());
+    Mat dst = dst_.getMat();
+    const int rc = orc_gaussian_blur7(tmp.data, tmp.cols, tmp.rows, (int)tmp.step, dst.data, (int)dst.step);
+    assert(rc == ORC_OK); (void)rc;
+}
+
+class Algorithm { public: virtual ~Algorithm() {} };
+class Feature2D : public Algorithm {
+public:
+    virtual ~Feature2D() {}
+    virtual void detect(InputArray, std::vector<KeyPoint>&, InputArray = noArray()) {}
+    virtual void compute(InputArray, std::vector<KeyPoint>&, OutputArray) {}
+    virtual void detectAndCompute(InputArray, InputArray, std::vector<KeyPoint>&, OutputArray, bool = false) {}
+};
+typedef Feature2D FeatureDetector;
+
+}  // namespace cv
