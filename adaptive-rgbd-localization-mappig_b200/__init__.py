@@ -80,8 +80,13 @@ def lib():
     """Load (building first if needed) the shared library.  Raises if it cannot be produced: no fallback."""
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(str(LIB_PATH))
+        import os
+        alt = os.environ.get("ORBF_LIB")             # tuning runs: load another build of the same sources (tools/fast_variants.sh)
+        if alt:
+            L = C.CDLL(alt)
+        else:
+            build()
+            L = C.CDLL(str(LIB_PATH))
         L.orbf_status_string.restype = C.c_char_p
         L.orbf_last_error.restype = C.c_char_p
         L.orbf_last_error.argtypes = [C.c_void_p]

@@ -5,211 +5,396 @@
 // one CTA of 4 warps per (strip, frame), all levels in one launch:
 //   0. one thread fetches the strip + 3-px ring halo with a single TMA box load (cp.async.bulk.tensor.3d -> UTMALDG);
 //      a u8 box must start on a 16-byte boundary of the level row, so the interior begins at tile column ax in [3, 18];
-//   1. pretest, 4 pixels per thread, byte-parallel: a 9-arc contains one pixel of each opposite ring pair, so for the four
+//   1. pretest, 8 pixels per thread, byte-parallel: a 9-arc contains one pixel of each opposite ring pair, so for the four
 //      pairs (0,8) (4,12) (2,10) (6,14) at least one member must differ from the centre by more than th.  |r - v| for 4
 //      pixels is one VABSDIFF4, "> th" a carry trick into bit 7 of each byte; 8 % of the pixels of the bench texture
-//      survive (true corners: 3.5 %) and are appended to a CTA-wide list (shared-memory atomics);
+//      survive (true corners: 3.5 %) and are appended to a CTA-wide list of bounded size;
 //   2. corner strength of two survivors at a time on packed u16x2 lanes with 3-input min/max (VIMNMX3.U16x2):
 //      S = max(v - A, B - v), A = min over the 16 arcs of the arc maximum, B = max over the arcs of the arc minimum
-//      (cv::FAST response = S - 1, corner iff S > th); 80 packed ops per pixel pair;
-//   3. NMS over the survivor list: strict '>' against the 8 neighbours *inside the same cell interior* (quirk Q1: each
-//      cell is its own cv::FAST call, so neighbours in an adjacent cell count as 0); kept corners go to their cell's list;
-//   4. one warp per cell ranks its kept corners by tile offset (= row-major order inside the cell) and writes them to
-//      the cell's private slot range in exactly the reference's push_back order;
-//   5. a cell with no survivor at iniTh is redone by its warp at minTh (orbextractor.cpp:709-712; rare, scalar path).
-// Arithmetic is all integer min/max/compare: bit-exact by construction.  Bound by the integer ALU pipe, not by HBM.
+//      (cv::FAST response = S - 1, corner iff S > th); 80 packed ops per pixel pair.  Responses go to a score plane in which
+//      the cells of the strip are one zero column apart, so that
+//   3. NMS over the corner list is eight unconditional strict compares (quirk Q1: each cell is its own cv::FAST call, so
+//      neighbours in an adjacent cell count as 0); a kept corner sets its bit in a per-row bitmap;
+//   4. one warp per cell turns the cell's bits into the reference's push_back order (row-major inside the cell) with a
+//      popcount prefix over the rows — no sorting — and writes the cell's private slot range;
+//   5. cells left empty after NMS are redone at minTh (orbextractor.cpp:709-712) through the same vector path, restricted to
+//      those cells.  A strip whose survivors exceed the list (noise-like content) takes the dense scalar path instead.
+// Arithmetic is all integer min/max/compare: bit-exact by construction.  Not HBM-bound: the binding resource is the shared-memory
+// data pipe (ncu: 83 % of the peak wavefront rate, 45 % of the wavefronts are the ring gathers of step 2 at ~2.7 wavefronts per
+// warp-wide byte gather), with instruction issue close behind (73 %) — profiles/r2c_fast_phases.txt, profiles/r2c_fast_smem.txt.
 #include "orbf_internal.h"
 #include "fast_device.h"
+
+// tuning switches (profiles/r2*_fast_variants.txt has the measurements behind the defaults)
+#ifndef FV_APPEND_COOP
+#define FV_APPEND_COOP 0        // pretest append: 1 = warp prefix + one atomic per warp, 0 = one atomic per task with survivors
+#endif
+#ifndef FV_CORNER_COOP
+#define FV_CORNER_COOP 1        // corner compaction in the strength rounds: 1 = ballot-aggregated, 0 = one atomic per thread
+#endif
+#ifndef FV_CELLTAB
+#define FV_CELLTAB 0            // cell index of a column: 1 = shared-memory table, 0 = three compares
+#endif
+#ifndef FV_LB
+#define FV_LB 10                // __launch_bounds__ minimum CTAs per SM (0 = unconstrained)
+#endif
 
 namespace {
 
 constexpr int FS_WARPS = ORBF_STRIP_CELLS, FS_THREADS = FS_WARPS * 32;
+constexpr int BW = ORBF_FAST_BW;                 // tile pitch (= TMA box width): every tile offset is an immediate
+constexpr int SP = BW + FS_WARPS;                // score-plane pitch: cell k of the strip is shifted right by k columns
+constexpr int BITW = (SP + 31) / 32;             // words of a row of the kept-corner bitmap
+constexpr int LIST_CAP = 2048;                   // pretest survivors a strip may hold (u16 tile offsets)
 
 struct FastParams {
     CUtensorMap maps[ORBF_MAX_LEVELS];
     const StripDesc* strips; const CellDesc* cells;
     uint32_t* cellCand; int* cellCount;
     int cellSlotTotal, nCellsTotal, iniTh, minTh, slot0, z0;   // z coordinate of a slot: slot - z0 on level 0, slot elsewhere
-    int keptCap;                                                // capacity of a cell's kept-corner list (max CellDesc::cap)
-    short BW[ORBF_MAX_LEVELS], BH[ORBF_MAX_LEVELS];
+    int scoreOff, listOff, bitsOff;                             // byte offsets of the shared-memory regions
+    short BH[ORBF_MAX_LEVELS];
 };
 
-// strict 8-neighbour maximum test of score byte *s (value v > 0); l / r: a left / right neighbour column exists in this cell
-__device__ __forceinline__ bool nms_keep(const uint8_t* s, int v, int BW, bool l, bool r)
+struct Strip { int W, h, ax; };      // scored width / rows of the strip, tile column of its first scored pixel
+
+// ---- 1. pretest over the strip interior; survivors (tile offsets row * BW + column) are appended to list -----------------------
+// sMask[w] = 0x80 in every byte of tile word w (columns 4w .. 4w + 3) that lies inside the scored interior — the start value of
+// the flag chain, so that pixels outside [ax, ax + W) never survive (no per-task edge arithmetic).
+// onlyEmpty: keep a survivor only if its cell has no kept corner yet (minTh pass)
+// cell index of tile column col
+__device__ __forceinline__ int cell_of(const uint8_t* sCellOf, const int* sC0, int col)
 {
-    bool k = v > s[-BW] && v > s[BW];
-    if (l) k = k && v > s[-1] && v > s[-BW - 1] && v > s[BW - 1];
-    if (r) k = k && v > s[1] && v > s[-BW + 1] && v > s[BW + 1];
-    return k;
+#if FV_CELLTAB
+    return sCellOf[col];
+#else
+    return (col >= sC0[1]) + (col >= sC0[2]) + (col >= sC0[3]);
+#endif
 }
 
-// One warp orders a cell's kept corners (by tile offset; offsets are distinct) and writes them out with their response.
-__device__ __forceinline__ void emit_cell(const uint16_t* kept, const uint8_t* sorg, int n, int BW, int c0, uint32_t* out, int outX0, int outY0, int lane)
+__device__ __forceinline__ void pretest(const uint8_t* tile, uint16_t* list, int* sCount, const Strip& S, int th, bool onlyEmpty, const uint32_t* sMask,
+    const uint8_t* sCellOf, const int* sC0, const int* sHas, int tid)
 {
-    for (int i = lane; i < n; i += 32) {
-        const uint32_t e = kept[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) rank += kept[j] < e;
-        const int row = (int)e / BW, col = (int)e - row * BW;
-        out[rank] = (uint32_t)(outX0 + col - c0) | ((uint32_t)(outY0 + row) << 11) | ((uint32_t)sorg[e] << 22);
+    const int lane = tid & 31;
+    const int wFirst = S.ax >> 3, wpr = ((S.ax + S.W + 7) >> 3) - wFirst, nTasks = S.h * wpr;
+    const uint32_t rcp = ((1u << 20) + wpr - 1) / wpr;
+    // per byte x = |r - v|: bit 7 of ((x & 0x7f) + K) | x (th < 128, K = 127 - th) or of ((x & 0x7f) + K) & x (th >= 128,
+    // K = 255 - th) is set iff x > th
+    const bool hiTh = th >= 128;
+    const uint32_t K = (uint32_t)(hiTh ? 255 - th : 127 - th) * 0x01010101u, M7 = 0x7F7F7F7Fu;
+#if FV_APPEND_COOP
+    const int nRounds = (nTasks + FS_THREADS - 1) / FS_THREADS;
+    for (int rd = 0; rd < nRounds; ++rd) {          // every thread runs every round: the append below is warp-cooperative
+        const int t = rd * FS_THREADS + tid;
+#else
+    for (int t = tid; t < nTasks; t += FS_THREADS) {
+#endif
+        uint32_t all[2] = { 0u, 0u };
+        int e = 0;
+        if (t < nTasks) {
+            const int row = (int)(((uint32_t)t * rcp) >> 20), x8 = 8 * (wFirst + (t - row * wpr));
+            e = row * BW + x8;
+            const uint8_t* p = tile + e;                                                 // image row y - 3 of the task's 8 columns
+            const uint2 r0 = *reinterpret_cast<const uint2*>(p + 6 * BW);                // ring 0  ( 0, +3)
+            const uint2 r8 = *reinterpret_cast<const uint2*>(p);                         // ring 8  ( 0, -3)
+            const uint2 c = *reinterpret_cast<const uint2*>(p + 3 * BW);
+            const uint32_t cl = *reinterpret_cast<const uint32_t*>(p + 3 * BW - 4), cr = *reinterpret_cast<const uint32_t*>(p + 3 * BW + 8);
+            const uint2 u = *reinterpret_cast<const uint2*>(p + BW);                      // image row y - 2
+            const uint32_t ul = *reinterpret_cast<const uint32_t*>(p + BW - 4), ur = *reinterpret_cast<const uint32_t*>(p + BW + 8);
+            const uint2 d = *reinterpret_cast<const uint2*>(p + 5 * BW);                  // image row y + 2
+            const uint32_t dl = *reinterpret_cast<const uint32_t*>(p + 5 * BW - 4), dr = *reinterpret_cast<const uint32_t*>(p + 5 * BW + 8);
+            const uint2 m0 = *reinterpret_cast<const uint2*>(sMask + (x8 >> 2));
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                // the word's own 4 bytes, the word left of it (.L) and right of it (.R), on the three rows that need shifted neighbours
+                const uint32_t C = w ? c.y : c.x, CL = w ? c.x : cl, CR = w ? cr : c.y;
+                const uint32_t U = w ? u.y : u.x, UL = w ? u.x : ul, UR = w ? ur : u.y;
+                const uint32_t D = w ? d.y : d.x, DL = w ? d.x : dl, DR = w ? dr : d.y;
+                uint32_t ad[8];
+                ad[0] = __vabsdiffu4(w ? r0.y : r0.x, C);
+                ad[1] = __vabsdiffu4(w ? r8.y : r8.x, C);
+                ad[2] = __vabsdiffu4(__funnelshift_r(C, CR, 24), C);                                             // ring 4  (+3,  0)
+                ad[3] = __vabsdiffu4(__funnelshift_r(CL, C, 8), C);                                              // ring 12 (-3,  0)
+                ad[4] = __vabsdiffu4(__funnelshift_r(D, DR, 16), C);                                             // ring 2  (+2, +2)
+                ad[5] = __vabsdiffu4(__funnelshift_r(UL, U, 16), C);                                             // ring 10 (-2, -2)
+                ad[6] = __vabsdiffu4(__funnelshift_r(U, UR, 16), C);                                             // ring 6  (+2, -2)
+                ad[7] = __vabsdiffu4(__funnelshift_r(DL, D, 16), C);                                             // ring 14 (-2, +2)
+                uint32_t a = w ? m0.y : m0.x;
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    const uint32_t ta = (ad[k] & M7) + K, tb = (ad[k + 1] & M7) + K;
+                    a &= hiTh ? ((ta & ad[k]) | (tb & ad[k + 1])) : (ta | tb | ad[k] | ad[k + 1]);
+                }
+                all[w] = a;
+            }
+            if (onlyEmpty && (all[0] | all[1])) {            // rare pass: drop survivors of cells that already have a kept corner
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    if (sHas[cell_of(sCellOf, sC0, x8 + b)]) all[b >> 2] &= ~(0x80u << (8 * (b & 3)));
+            }
+        }
+        const int cnt = __popc(all[0]) + __popc(all[1]);
+#if FV_APPEND_COOP
+        // warp-cooperative append: exclusive prefix of the survivor counts, one shared-memory atomic per warp
+        if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int base = 0;
+        if (lane == 31) base = atomicAdd(sCount, incl);
+        int pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+#else
+        if (cnt == 0) continue;
+        int pos = atomicAdd(sCount, cnt);
+#endif
+        if (pos <= LIST_CAP - 8) {          // a task that would cross the end writes nothing: the count alone says "overflow"
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                if (all[b >> 2] & (0x80u << (8 * (b & 3)))) list[pos++] = (uint16_t)(e + b);
+        }
+    }
+    (void)lane;
+}
+
+// ---- 2. corner strength, two survivors per thread; the corners (44 % of the survivors) are compacted in place at the front of
+// the list — as score-plane positions — so that the NMS pass runs with full warps.  A round reads 2 * FS_THREADS entries before
+// anything is appended, and the appends of round k stay below the entries consumed so far, so the only hazard is inside a round
+// (the barrier).  Ends with a barrier: *sCorner is the corner count.
+__device__ __forceinline__ void strengths(const uint8_t* org, uint8_t* sorg, uint16_t* list, int n, int* sCorner, int th, const uint8_t* sCellOf, const int* sC0, int tid)
+{
+    const int lane = tid & 31;
+#if !FV_CELLTAB
+    const int b1 = sC0[1], b2 = sC0[2], b3 = sC0[3];
+#endif
+    for (int base = 0; base < n; base += 2 * FS_THREADS) {
+        const int ia = base + 2 * tid;
+        int pa = 0, pb = 0, sa = 0, sb = 0;
+        if (ia < n) {
+            const int ea = list[ia], eb = list[min(ia + 1, n - 1)];
+            const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
+            sa = (int)(s & 0xFFFFu); sb = ia + 1 < n ? (int)(s >> 16) : 0;
+            const int ra = ea / BW, rb = eb / BW;                        // score-plane position = tile offset + (SP - BW) * row + cell index
+#if FV_CELLTAB
+            pa = ea + (SP - BW) * ra + sCellOf[ea - ra * BW];
+            pb = eb + (SP - BW) * rb + sCellOf[eb - rb * BW];
+#else
+            const int ca = ea - ra * BW, cb = eb - rb * BW;
+            pa = ea + (SP - BW) * ra + (ca >= b1) + (ca >= b2) + (ca >= b3);
+            pb = eb + (SP - BW) * rb + (cb >= b1) + (cb >= b2) + (cb >= b3);
+#endif
+            if (sa > th) sorg[pa] = (uint8_t)(sa - 1);
+            if (sb > th) sorg[pb] = (uint8_t)(sb - 1);
+        }
+        __syncthreads();
+        const int na = sa > th, nb = sb > th;
+#if FV_CORNER_COOP
+        // ballot-aggregated compaction: one shared-memory atomic per warp and round
+        const uint32_t ma = __ballot_sync(0xffffffffu, na), mb = __ballot_sync(0xffffffffu, nb);
+        if (ma | mb) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(sCorner, __popc(ma) + __popc(mb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (na) list[base + __popc(ma & lt)] = (uint16_t)pa;
+            if (nb) list[base + __popc(ma) + __popc(mb & lt)] = (uint16_t)pb;
+        }
+#else
+        if (na + nb) {
+            int pos = atomicAdd(sCorner, na + nb);
+            if (na) list[pos++] = (uint16_t)pa;
+            if (nb) list[pos] = (uint16_t)pb;
+        }
+#endif
+    }
+    __syncthreads();
+    (void)lane;
+}
+
+// ---- 3. NMS over the corner list: strict '>' against the 8 neighbours of the score plane (zero between cells and around the strip)
+__device__ __forceinline__ bool is_local_max(const uint8_t* s, int v)
+{
+    return (v > s[-1]) & (v > s[1]) & (v > s[-SP - 1]) & (v > s[-SP]) & (v > s[-SP + 1]) & (v > s[SP - 1]) & (v > s[SP]) & (v > s[SP + 1]);
+}
+
+__device__ __forceinline__ void nms(const uint8_t* sorg, const uint16_t* list, int nc, uint32_t* bits, int* sHas, const uint8_t* sCellOfG, const int* sC0, int tid)
+{
+    for (int i = tid; i < nc; i += FS_THREADS) {
+        const int p = list[i];
+        if (is_local_max(sorg + p, sorg[p])) {
+            const int row = p / SP, col = p - row * SP;                   // col = tile column + cell index
+            atomicOr(&bits[row * BITW + (col >> 5)], 1u << (col & 31));
+#if FV_CELLTAB
+            sHas[sCellOfG[col]] = 1;
+#else
+            sHas[(col > sC0[1]) + (col > sC0[2] + 1) + (col > sC0[3] + 2)] = 1;
+#endif
+        }
     }
 }
 
-__global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel(const __grid_constant__ FastParams P)
+// dense scalar path of one cell (one warp): every pixel scored at threshold th, NMS by scanning the cell.  Used when the
+// survivor list of the strip overflows (noise-like content); slow, exact, rare.  k = index of the cell in its strip, c0 = its
+// first tile column.
+__device__ void dense_cell(const uint8_t* org, uint8_t* sorg, uint32_t* bits, int* sHas, int k, int c0, int cw, int h, int th, int lane)
+{
+    const int npix = cw * h;
+    const uint32_t rcpW = ((1u << 20) + cw - 1) / cw;
+    for (int p = lane; p < npix; p += 32) {
+        const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
+        const uint8_t* c = org + y * BW + c0 + x;
+        const int v = c[0], hiT = v + th, loT = v - th;
+        const int p0 = c[3 * BW], p8 = c[-3 * BW], p4 = c[3], p12 = c[-3];
+        const bool pass = (((p0 > hiT) | (p8 > hiT)) & ((p4 > hiT) | (p12 > hiT))) | (((p0 < loT) | (p8 < loT)) & ((p4 < loT) | (p12 < loT)));
+        if (pass) {
+            const int s = ring_strength(c, BW);
+            if (s > th) sorg[y * SP + c0 + k + x] = (uint8_t)(s - 1);
+        }
+    }
+    __syncwarp();
+    for (int p = lane; p < npix; p += 32) {
+        const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
+        const int col = c0 + k + x;
+        const uint8_t* s = sorg + y * SP + col;
+        const int v = s[0];
+        if (v != 0 && is_local_max(s, v)) {
+            atomicOr(&bits[y * BITW + (col >> 5)], 1u << (col & 31));
+            sHas[k] = 1;
+        }
+    }
+    __syncwarp();
+}
+
+#if FV_LB
+__global__ void __launch_bounds__(FS_THREADS, FV_LB) fast_strip_kernel
+#else
+__global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
+#endif
+    (const __grid_constant__ FastParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int sCount, sCorner;
+    __shared__ int sCount, sCorner, sDense;
+    __shared__ int sHas[FS_WARPS];                                          // cell has a kept corner (cells the strip does not have: 1)
+    __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
+    __shared__ __align__(8) uint32_t sMask[BW / 4 + 2];                     // per tile word: 0x80 in the bytes inside the scored interior
+    __shared__ uint8_t sCellOf[BW], sCellOfG[SP];                           // cell index of a tile column / of a score-plane column
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StripDesc sd = P.strips[blockIdx.x];
     const int slot = P.slot0 + blockIdx.y;
-    constexpr int BW = ORBF_FAST_BW;                                       // compile-time pitch: every tile offset is an immediate
     const int level = sd.level, BH = P.BH[level];
-    const int W = sd.w, h = sd.h;
-    const int xs = (sd.x0 - 3) & ~15, ax = sd.x0 - xs;                      // TMA boxes of bytes start on 16-byte boundaries
+    Strip S;
+    S.W = sd.w; S.h = sd.h;
+    const int xs = (sd.x0 - 3) & ~15;                                       // TMA boxes of bytes start on 16-byte boundaries
+    S.ax = sd.x0 - xs;
     uint8_t* tile = smem;                                                   // BH x BW level pixels, interior (0,0) at [3][ax]
-    uint8_t* score = smem + align_up(BW * BH, 128);                         // (h + 2) x BW responses, interior (0,0) at [1][ax], zero elsewhere
-    uint16_t* list = reinterpret_cast<uint16_t*>(score + align_up(BW * (BH - 4), 16));   // pretest survivors: y * BW + tile column
-    uint16_t* kept = list + align_up(ORBF_STRIP_MAX_W * (BH - 6), 8);                    // [cell][keptCap] NMS survivors (tile offsets)
-    __shared__ int sKept[FS_WARPS];
-    __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
+    uint8_t* score = smem + P.scoreOff;                                     // (h + 2) x SP responses, interior (0,0) of cell k at [1][ax + k]
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smem + P.bitsOff);         // [h][BITW] kept corners, score-plane columns
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem + P.listOff);         // pretest survivors (tile offsets), then corners (score-plane positions)
 
-    if (tid == 0) { mbar_init(&bar, 1); sCount = 0; sCorner = 0; }
-    if (tid < FS_WARPS) sKept[tid] = 0;
-    if (tid <= FS_WARPS) sC0[tid] = tid < sd.nCells ? ax + P.cells[sd.firstCell + tid].x0 - sd.x0 : ax + W + (tid > sd.nCells ? 4096 : 0);
+    if (tid == 0) { mbar_init(&bar, 1); sCount = 0; sCorner = 0; sDense = 0; }
+    if (tid < FS_WARPS) sHas[tid] = tid < sd.nCells ? 0 : 1;
+    if (tid <= FS_WARPS) sC0[tid] = tid < sd.nCells ? S.ax + P.cells[sd.firstCell + tid].x0 - sd.x0 : S.ax + S.W + (tid > sd.nCells ? 4096 : 0);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, (uint32_t)(BW * BH));
         tma_load_3d(tile, &P.maps[level], xs, sd.y0 - 3, level == 0 ? slot - P.z0 : slot, &bar);
     }
-    for (int i = tid; i < (BW * (h + 2)) >> 2; i += FS_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    {   // score plane and bitmap (adjacent regions, multiples of 16 bytes) start at zero
+        uint4* z = reinterpret_cast<uint4*>(score);
+        const int n16 = (P.listOff - P.scoreOff) >> 4;
+        for (int i = tid; i < n16; i += FS_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    {
+        const int b1 = sC0[1], b2 = sC0[2], b3 = sC0[3], lo = S.ax, hi = S.ax + S.W;
+        if (tid < BW / 4 + 2) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int col = 4 * tid + j; if (col >= lo && col < hi) m |= 0x80u << (8 * j); }
+            sMask[tid] = m;
+        }
+#if FV_CELLTAB
+        for (int col = tid; col < SP; col += FS_THREADS) {
+            if (col < BW) sCellOf[col] = (uint8_t)((col >= b1) + (col >= b2) + (col >= b3));
+            sCellOfG[col] = (uint8_t)((col > b1) + (col > b2 + 1) + (col > b3 + 2));
+        }
+#else
+        (void)b1; (void)b2; (void)b3;
+#endif
+    }
     mbar_wait(&bar, 0);
     __syncthreads();
 
-    const int th = P.iniTh;
-    const int keptCap = P.keptCap;
-    // ---- 1. pretest: 4 pixels (one aligned word of the centre row) per thread -------------------------------------
-    {
-        const int wFirst = ax >> 2, wpr = ((ax + W + 3) >> 2) - wFirst, nTasks = h * wpr;
-        const uint32_t rcp = ((1u << 20) + wpr - 1) / wpr;
-        // per byte x = |r - v|: bit 7 of ((x & 0x7f) + K) | x (th < 128, K = 127 - th) or of ((x & 0x7f) + K) & x (th >= 128,
-        // K = 255 - th) is set iff x > th
-        const bool hiTh = th >= 128;
-        const uint32_t K = (uint32_t)(hiTh ? 255 - th : 127 - th) * 0x01010101u, M7 = 0x7F7F7F7Fu;
-        for (int t = tid; t < nTasks; t += FS_THREADS) {
-            const int row = (int)(((uint32_t)t * rcp) >> 20), wi = wFirst + (t - row * wpr);
-            const uint32_t* c = reinterpret_cast<const uint32_t*>(tile + (row + 3) * BW) + wi;
-            const uint32_t C = c[0];
-            const uint32_t* u2 = reinterpret_cast<const uint32_t*>(tile + (row + 1) * BW) + wi;     // image row y - 2
-            const uint32_t* d2 = reinterpret_cast<const uint32_t*>(tile + (row + 5) * BW) + wi;     // image row y + 2
-            uint32_t ad[8];
-            ad[0] = __vabsdiffu4(*reinterpret_cast<const uint32_t*>(tile + (row + 6) * BW + 4 * wi), C);     // ring 0  ( 0, +3)
-            ad[1] = __vabsdiffu4(*reinterpret_cast<const uint32_t*>(tile + row * BW + 4 * wi), C);           // ring 8  ( 0, -3)
-            ad[2] = __vabsdiffu4(__funnelshift_r(C, c[1], 24), C);                                           // ring 4  (+3,  0)
-            ad[3] = __vabsdiffu4(__funnelshift_r(c[-1], C, 8), C);                                           // ring 12 (-3,  0); word -1 of tile row >= 3 is inside the tile
-            ad[4] = __vabsdiffu4(__funnelshift_r(d2[0], d2[1], 16), C);                                      // ring 2  (+2, +2)
-            ad[5] = __vabsdiffu4(__funnelshift_r(u2[-1], u2[0], 16), C);                                     // ring 10 (-2, -2)
-            ad[6] = __vabsdiffu4(__funnelshift_r(u2[0], u2[1], 16), C);                                      // ring 6  (+2, -2)
-            ad[7] = __vabsdiffu4(__funnelshift_r(d2[-1], d2[0], 16), C);                                     // ring 14 (-2, +2)
-            uint32_t all = 0x80808080u;
-#pragma unroll
-            for (int k = 0; k < 8; k += 2) {
-                const uint32_t ta = (ad[k] & M7) + K, tb = (ad[k + 1] & M7) + K;
-                all &= hiTh ? ((ta & ad[k]) | (tb & ad[k + 1])) : (ta | tb | ad[k] | ad[k + 1]);
-            }
-            const int xi = 4 * wi - ax;                                     // interior x of byte 0: mask pixels outside [0, W)
-            if (xi < 0) all &= 0xFFFFFFFFu << (8 * (-xi));
-            if (W - xi < 4) all &= 0xFFFFFFFFu >> (8 * (4 - (W - xi)));
-            if (all) {
-                int pos = atomicAdd(&sCount, __popc(all));
-                const int e = row * BW + 4 * wi;
-                if (all & 0x80u) list[pos++] = (uint16_t)e;
-                if (all & 0x8000u) list[pos++] = (uint16_t)(e + 1);
-                if (all & 0x800000u) list[pos++] = (uint16_t)(e + 2);
-                if (all & 0x80000000u) list[pos] = (uint16_t)(e + 3);
-            }
-        }
-    }
-    __syncthreads();
-    const int n = sCount;
     const uint8_t* org = tile + 3 * BW;
-    uint8_t* sorg = score + BW;
-    // ---- 2. corner strength, two survivors per thread; the corners (44 % of the survivors) are compacted in place at the front
-    // of the list so that the NMS pass runs with full warps.  A round reads 2 * FS_THREADS entries before anything is appended,
-    // and the appends of round k stay below the entries consumed so far, so the only hazard is inside a round (the barrier).
-    for (int base = 0; base < n; base += 2 * FS_THREADS) {
-        const int ia = base + 2 * tid;
-        int ea = 0, eb = 0, sa = 0, sb = 0;
-        if (ia < n) {
-            ea = list[ia]; eb = list[min(ia + 1, n - 1)];
-            const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
-            sa = (int)(s & 0xFFFFu); sb = ia + 1 < n ? (int)(s >> 16) : 0;
-            if (sa > th) sorg[ea] = (uint8_t)(sa - 1);
-            if (sb > th) sorg[eb] = (uint8_t)(sb - 1);
-        }
+    uint8_t* sorg = score + SP;
+    int th = P.iniTh;
+    bool second = false;
+    while (true) {
+        pretest(tile, list, &sCount, S, th, second, sMask, sCellOf, sC0, sHas, tid);
         __syncthreads();
-        const int na = sa > th, nb = sb > th;
-        if (na + nb) {
-            int pos = atomicAdd(&sCorner, na + nb);
-            if (na) list[pos++] = (uint16_t)ea;
-            if (nb) list[pos] = (uint16_t)eb;
+        const int n = sCount;
+        if (n > LIST_CAP - 8) {            // dense path below; nothing was scored in this pass
+            if (tid == 0) sDense = 1;
+            break;
         }
+        strengths(org, sorg, list, n, &sCorner, th, sCellOf, sC0, tid);
+        nms(sorg, list, sCorner, bits, sHas, sCellOfG, sC0, tid);
+        __syncthreads();
+        if (second || P.minTh >= th || (sHas[0] & sHas[1] & sHas[2] & sHas[3])) break;
+        __syncthreads();
+        if (tid == 0) { sCount = 0; sCorner = 0; }
+        th = P.minTh; second = true;       // cells without a kept corner at iniTh: the same pass at minTh, restricted to them
+        __syncthreads();
     }
     __syncthreads();
-    // ---- 3. NMS over the corner list, kept corners appended to their cell's list -------------------------------------
-    {
-        const int nc = sCorner;
-        const int b1 = sC0[1], b2 = sC0[2], b3 = sC0[3];
-        for (int i = tid; i < nc; i += FS_THREADS) {
-            const int e = list[i];
-            const int v = sorg[e];
-            const int row = e / BW, col = e - row * BW;
-            const int k = (col >= b1) + (col >= b2) + (col >= b3);
-            if (nms_keep(sorg + e, v, BW, col > sC0[k], col < sC0[k + 1] - 1)) {
-                const int pos = atomicAdd(&sKept[k], 1);
-                if (pos < keptCap) kept[k * keptCap + pos] = (uint16_t)e;
-            }
-        }
-    }
-    __syncthreads();
-    // ---- 4./5. one warp per cell: ordered output, minTh fallback ------------------------------------------------------
+    // ---- 4. one warp per cell: dense passes if flagged, then the ordered output -----------------------------------------------
     if (warp < sd.nCells) {
         const int cellIdx = sd.firstCell + warp;
         const CellDesc cd = P.cells[cellIdx];
-        const int c0 = sC0[warp], cw = cd.w;
+        const int c0 = sC0[warp], cw = cd.w, h = S.h;
+        if (sDense) {
+            // overflow in the first pass: nothing is scored yet, every cell goes through iniTh and, if still empty, minTh; overflow in
+            // the second pass: only the cells the first pass left empty are redone, at minTh.  Responses do not depend on the
+            // threshold, so a dense pass over a cell that already holds some only adds to them.
+            if (!second) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, P.iniTh, lane);
+            if (!sHas[warp] && P.minTh < P.iniTh) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, P.minTh, lane);
+        }
         uint32_t* out = P.cellCand + (long long)slot * P.cellSlotTotal + cd.slotOff;
         const int outX0 = cd.x0 + cd.relx, outY0 = cd.y0 + cd.rely;
-        uint16_t* myKept = kept + warp * keptCap;
-        int total = min(sKept[warp], keptCap);
-        if (total == 0 && P.minTh < th) {
-            // no corner at iniTh in this cell, so its score columns are still all zero: rescore the cell at minTh
-            const int t2 = P.minTh, npix = cw * h;
-            const uint32_t rcpW = ((1u << 20) + cw - 1) / cw;
-            for (int p = lane; p < npix; p += 32) {
-                const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
-                const uint8_t* c = org + y * BW + c0 + x;
-                const int v = c[0], hiT = v + t2, loT = v - t2;
-                const int p0 = c[3 * BW], p8 = c[-3 * BW], p4 = c[3], p12 = c[-3];
-                const bool pass = (((p0 > hiT) | (p8 > hiT)) & ((p4 > hiT) | (p12 > hiT))) | (((p0 < loT) | (p8 < loT)) & ((p4 < loT) | (p12 < loT)));
-                if (pass) {
-                    const int s = ring_strength(c, BW);
-                    if (s > t2) sorg[y * BW + c0 + x] = (uint8_t)(s - 1);
+        const int f0 = c0 + warp;                                            // first score-plane column of the cell
+        int total = 0;
+        for (int r0 = 0; r0 < h; r0 += 32) {
+            const int row = r0 + lane;
+            unsigned long long m = 0;
+            if (row < h) {
+                const uint32_t* b = bits + row * BITW + (f0 >> 5);
+                const int sh = f0 & 31;
+                const uint32_t w0 = b[0], w1 = b[1], w2 = b[2];              // words past the row's end belong to columns past the cell
+                m = ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+                if (cw < 64) m &= (1ull << cw) - 1ull;
+            }
+            const int cnt = __popcll(m);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            int pos = total + incl - cnt;
+            const uint32_t rowKey = (uint32_t)outX0 | ((uint32_t)(outY0 + row) << 11);
+            const uint8_t* srow = sorg + row * SP + f0;
+            if (cw <= 32) {                     // the usual geometry: 32-bit bit loop
+                uint32_t m32 = (uint32_t)m;
+                while (m32) {
+                    const int x = __ffs((int)m32) - 1;
+                    m32 &= m32 - 1;
+                    out[pos++] = (rowKey + (uint32_t)x) | ((uint32_t)srow[x] << 22);
+                }
+            } else {
+                while (m) {
+                    const int x = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    out[pos++] = (rowKey + (uint32_t)x) | ((uint32_t)srow[x] << 22);
                 }
             }
-            __syncwarp();
-            for (int p = lane; p < npix; p += 32) {
-                const int y = (int)(((uint32_t)p * rcpW) >> 20), x = p - y * cw;
-                const int e = y * BW + c0 + x;
-                const int v = sorg[e];
-                if (v && nms_keep(sorg + e, v, BW, x > 0, x < cw - 1)) {
-                    const int pos = atomicAdd(&sKept[warp], 1);
-                    if (pos < keptCap) myKept[pos] = (uint16_t)e;
-                }
-            }
-            __syncwarp();
-            total = min(sKept[warp], keptCap);
+            total += __shfl_sync(0xffffffffu, incl, 31);
         }
-        emit_cell(myKept, sorg, total, BW, c0, out, outX0, outY0, lane);
         if (lane == 0) P.cellCount[(long long)slot * P.nCellsTotal + cellIdx] = total;
     }
 }
@@ -223,18 +408,20 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n)
         if (r != ORBF_OK) return r;
     }
     FastParams P;
-    size_t smem = 0;
-    const int keptCap = ((c->maxCellW + 1) / 2) * ((c->maxCellH + 1) / 2);     // strict 8-neighbour maxima: <= 1 per 2x2 block
-    P.keptCap = keptCap;
+    int maxBH = 0;
     for (int l = 0; l < c->L; ++l) {
         P.maps[l] = c->tmFast[l];
-        P.BW[l] = (short)c->fastBW[l]; P.BH[l] = (short)c->fastBH[l];
-        const int BW = c->fastBW[l], BH = c->fastBH[l];
-        // 27.2 KB at 640x480: 8 CTAs per SM (the kernel gains ~6 % per extra resident CTA at this point)
-        const size_t need = (size_t)align_up(BW * BH, 128) + align_up(BW * (BH - 4), 16) + (size_t)align_up(ORBF_STRIP_MAX_W * (BH - 6), 8) * sizeof(uint16_t)
-            + (size_t)FS_WARPS * keptCap * sizeof(uint16_t) + 16;
-        smem = std::max(smem, need);
+        P.BH[l] = (short)c->fastBH[l];
+        maxBH = std::max(maxBH, c->fastBH[l]);
     }
+    if (c->maxCellW > 64) return ORBF_ERR_GEOMETRY;                 // a cell's row of the kept-corner bitmap is read as one 64-bit field
+    // regions: [tile BH x BW] [score (h + 2) x SP | bitmap h x BITW words (+ 2 words the output pass may read past the last row)] [list]
+    // 17.4 KB at 640x480
+    const int maxH = maxBH - 6;
+    P.scoreOff = align_up(BW * maxBH, 128);
+    P.bitsOff = P.scoreOff + align_up(SP * (maxH + 2), 16);
+    P.listOff = P.bitsOff + align_up(4 * (BITW * maxH + 2), 16);
+    const size_t smem = (size_t)P.listOff + LIST_CAP * sizeof(uint16_t);
     P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
     P.cellSlotTotal = c->cellSlotTotal; P.nCellsTotal = c->nCellsTotal; P.iniTh = c->cfg.ini_th_fast; P.minTh = c->cfg.min_th_fast;
     P.slot0 = slot0; P.z0 = c->cur_slot0;

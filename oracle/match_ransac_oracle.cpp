@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <set>
 #include <vector>
 
@@ -343,8 +344,13 @@ int orc_knn_match(const uint8_t* q, int nq, const uint8_t* t, int nt, float rati
     return ORC_OK;
 }
 
+// srand() / rand() are the real libc calls (quirk Q5) and share one process-wide state: callers on several threads (bench.py's CPU
+// legs run the oracle frame-parallel) are serialised here, so that every table is the uninterrupted stream of its own seed.
+static std::mutex g_randMutex;
+
 int orc_libc_rand_sequence(unsigned seed, int n, int* out)
 {
+    std::lock_guard<std::mutex> lock(g_randMutex);
     srand(seed);
     for (int i = 0; i < n; ++i) out[i] = rand();
     return ORC_OK;
@@ -352,6 +358,7 @@ int orc_libc_rand_sequence(unsigned seed, int n, int* out)
 
 int orc_sample_table_libc(unsigned seed, int M, int iterations, int sample_size, int* table)
 {
+    std::lock_guard<std::mutex> lock(g_randMutex);
     srand(seed);
     for (int k = 0; k < iterations; ++k) sample_libc(M, sample_size, table + (size_t)k * sample_size);
     return ORC_OK;
