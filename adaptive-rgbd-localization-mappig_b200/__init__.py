@@ -35,7 +35,7 @@ class Config(C.Structure):
                 ("max_frames", C.c_int32), ("max_pairs", C.c_int32), ("device", C.c_int32),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float),
                 ("depth_factor", C.c_float), ("pipeline_chunk", C.c_int32), ("pipeline_streams", C.c_int32),
-                ("depth_zero_copy", C.c_int32), ("reserved_", C.c_int32),
+                ("depth_zero_copy", C.c_int32), ("pipeline_overlap", C.c_int32),
                 ("k1", C.c_float), ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
 
 
@@ -236,6 +236,28 @@ class Context:
                                             C.c_int64(w * h), C.c_float(ratio), int(cross_check), C.byref(cfg) if ransac else None),
                   "track_sequence")
         return n - 1
+
+    def track_sequence_at(self, frames, depths, ratio, slot0, pair_slot0, cross_check=False, ransac=True, **kw):
+        """track_sequence into frame slots [slot0, slot0 + n) and pair slots [pair_slot0, pair_slot0 + n - 1): with
+        pipeline_overlap=1 two sequences can be double-buffered in one context."""
+        n, h, w = frames.shape
+        cfg = default_ransac_config(**kw)
+        self._chk(lib().orbf_track_sequence_at(self._h, slot0, pair_slot0, n, _p(frames), C.c_int64(w), C.c_int64(w * h), _p(depths), C.c_int64(w),
+                                               C.c_int64(w * h), C.c_float(ratio), int(cross_check), C.byref(cfg) if ransac else None),
+                  "track_sequence_at")
+        return n - 1
+
+    def read_results_async(self, slot0, pair_slot0, n, frame_counts, match_counts, ransac, marker):
+        """Asynchronous D2H of frame counts [n] i32, match counts [n - 1] i32 and RANSAC results [n - 1] RANSAC_RESULT_DT into caller
+        arrays (page-locked for a truly asynchronous copy), then marker `marker`; wait_marker(marker) blocks until they have arrived."""
+        self._chk(lib().orbf_read_results_async(self._h, slot0, pair_slot0, n, _p(frame_counts), _p(match_counts), _p(ransac), marker), "read_results_async")
+
+    def read_features_async(self, slot0, pair_slot0, n, kps, desc, xyz, matches, marker):
+        """Asynchronous D2H of kps [n, K] KEYPOINT_DT, desc [n, K, 32] u8, xyz [3, n, K] f32, matches [n - 1, K] DMATCH_DT (any may be None)."""
+        self._chk(lib().orbf_read_features_async(self._h, slot0, pair_slot0, n, _p(kps), _p(desc), _p(xyz), _p(matches), marker), "read_features_async")
+
+    def wait_marker(self, marker):
+        self._chk(lib().orbf_wait_marker(self._h, marker), "wait_marker")
 
     def track_sequence_device(self, d_gray_ptr, pitch, frame_stride, n, d_depth_ptr, depth_pitch, depth_frame_stride, ratio,
                               cross_check=False, ransac=True, slot0=0, **kw):

@@ -52,30 +52,36 @@ static int run_extract(orbf_context* c, int slot0, int n, bool sideStream)
 // ------------------------------------------------------------------------------------------------------
 // chunked multi-stream pipeline
 // ------------------------------------------------------------------------------------------------------
-// A batch call forks the caller-visible stream into the context's worker streams and joins them before it returns
-// (everything stays asynchronous with respect to the host).  Chunk k runs on worker k % nWork: its H2D copies, every
-// extraction stage of its frames and — for the sequence calls — matching + RANSAC of its consecutive frame pairs.
-// The copy of chunk k+1 therefore overlaps the kernels of chunk k, and the latency-bound stages of one chunk
-// (quadtree, sort replay, hypothesis scoring) overlap the throughput-bound stages (FAST, blur, Hamming) of another.
+// A batched host-input call cuts its frames into chunks.  ALL H2D copies go back to back on the context's copy stream (the PCIe link,
+// which bounds this path, never waits for a kernel), one event per chunk; chunk k's kernels — every extraction stage of its frames and,
+// for the sequence calls, matching of its consecutive frame pairs — run on worker stream k % nWork behind that event, so the
+// latency-bound stages of one chunk (quadtree, descriptor gathers) overlap the throughput-bound stages (FAST, blur, Hamming) of
+// another.  The caller-visible stream is forked into copy + worker streams at the start and joins them before the call returns
+// (everything stays asynchronous with respect to the host); with orbf_config.pipeline_overlap the fork is dropped, so the copies
+// of the next call start while this call's tail (last chunks, RANSAC, result read-back) is still running.
 // With per-stage profiling on, or pipeline_chunk < 0, everything runs as one chunk on the caller-visible stream.
 struct Pipeline {
     orbf_context* c;
     cudaStream_t main;
     bool used[ORBF_MAX_WORKERS];
-    bool active;
-    explicit Pipeline(orbf_context* ctx) : c(ctx), main(ctx->stream), active(false) { for (bool& u : used) u = false; }
+    bool active, forked;
+    explicit Pipeline(orbf_context* ctx) : c(ctx), main(ctx->stream), active(false), forked(false) { for (bool& u : used) u = false; }
     ~Pipeline() { c->stream = main; }
     int begin(bool wanted)
     {
-        active = wanted && c->nWork > 0 && c->chunkFrames > 0 && !c->profiling;
-        if (active) ORBF_CUDA(c, cudaEventRecord(c->evFork, main));
+        active = wanted && c->nWork > 0 && c->chunkFrames > 0 && !c->profiling && c->copy;
+        forked = active && !c->cfg.pipeline_overlap;
+        if (forked) {
+            ORBF_CUDA(c, cudaEventRecord(c->evFork, main));
+            ORBF_CUDA(c, cudaStreamWaitEvent(c->copy, c->evFork, 0));
+        }
         return ORBF_OK;
     }
     int enter(int k)   // make worker k % nWork the current stream
     {
         if (!active) return ORBF_OK;
         const int s = k % c->nWork;
-        if (!used[s]) { ORBF_CUDA(c, cudaStreamWaitEvent(c->work[s], c->evFork, 0)); used[s] = true; }
+        if (!used[s]) { if (forked) ORBF_CUDA(c, cudaStreamWaitEvent(c->work[s], c->evFork, 0)); used[s] = true; }
         c->stream = c->work[s];
         return ORBF_OK;
     }
@@ -151,21 +157,26 @@ static int run_match_group(orbf_context* c, int pair0, int npairs, float ratio, 
     return ORBF_OK;
 }
 
+// pair slot table entries [pair0, pair0 + np): pair slot p = (frame slot f0 + (p - pair0), the next one)
+__global__ void consecutive_pairs_kernel(int* pairs, int pair0, int np, int f0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) { pairs[2 * (pair0 + i)] = f0 + i; pairs[2 * (pair0 + i) + 1] = f0 + i + 1; }
+}
+
 // Extraction of frames [slot0, slot0+n) and, when `track` is set, matching + RANSAC of the n-1 consecutive pairs
-// (pair slot p = (slot0+p, slot0+p+1)), chunk by chunk.  The pair that straddles two chunks runs with the later chunk,
+// (pair slot pairSlot0 + p = (slot0+p, slot0+p+1)), chunk by chunk.  The pair that straddles two chunks runs with the later chunk,
 // after an event says the earlier chunk's extraction is complete.
-struct TrackArgs { float ratio; bool cross; const orbf_ransac_config* rcfg; };
+struct TrackArgs { float ratio; bool cross; const orbf_ransac_config* rcfg; int pairSlot0; };
 
 static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, const TrackArgs* track)
 {
     const int npairs = track ? n - 1 : 0;
+    const int ps0 = track ? track->pairSlot0 : 0;
     if (track && npairs > 0) {
-        if (npairs > c->P) return ORBF_ERR_ARG;
+        if (ps0 < 0 || ps0 + npairs > c->P) return ORBF_ERR_ARG;
         if (track->rcfg) TRY(orbf_ransac_reserve(c, *track->rcfg));
-        std::vector<int> pr(2 * (size_t)npairs);
-        for (int p = 0; p < npairs; ++p) { pr[2 * p] = slot0 + p; pr[2 * p + 1] = slot0 + p + 1; }
-        ORBF_CUDA(c, cudaMemcpyAsync(c->d_pairs, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        c->lastNPairs = npairs; c->pairsFromSlots = true;
+        c->lastNPairs = ps0 + npairs; c->pairsFromSlots = true;
     }
     // Measured on B200 (profiles/r1d_pipeline_sweep.txt): the stages are instruction-issue bound, so running chunks on
     // concurrent streams buys nothing when the inputs are already in HBM (7.36 ms/512 frames on one stream vs 7.4-9.5 ms
@@ -173,27 +184,42 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
     // host inputs.
     Pipeline pl(c);
     TRY(pl.begin(hf && hf->gray));
-    const int chunk = pl.active ? c->chunkFrames : n;
+    int chunk = pl.active ? c->chunkFrames : n;
     // chunk boundaries: quarter- and half-size chunks at both ends, so that the first kernels start after a short copy and the
     // last copy is followed by a short tail of compute (the link, not the SMs, bounds this path)
-    std::vector<int> bounds{0};
-    if (pl.active && chunk >= 64 && n >= 4 * chunk) {
-        const int q = chunk / 4, h = chunk / 2;
-        bounds.push_back(q); bounds.push_back(q + h);
-        const int tailStart = n - q - h;
-        for (int a = q + h; a + chunk <= tailStart; a += chunk) bounds.push_back(a + chunk);
-        if (bounds.back() < tailStart) bounds.push_back(tailStart);
-        bounds.push_back(n - q); bounds.push_back(n);
-    } else {
-        for (int a = chunk; a < n; a += chunk) bounds.push_back(a);
-        bounds.push_back(n);
+    std::vector<int> bounds;
+    for (;; chunk *= 2) {
+        bounds.assign(1, 0);
+        if (pl.active && chunk >= 64 && n >= 4 * chunk) {
+            const int q = chunk / 4, h = chunk / 2;
+            bounds.push_back(q); bounds.push_back(q + h);
+            const int tailStart = n - q - h;
+            for (int a = q + h; a + chunk <= tailStart; a += chunk) bounds.push_back(a + chunk);
+            if (bounds.back() < tailStart) bounds.push_back(tailStart);
+            bounds.push_back(n - q); bounds.push_back(n);
+        } else {
+            for (int a = chunk; a < n; a += chunk) bounds.push_back(a);
+            bounds.push_back(n);
+        }
+        if (!pl.active || (int)bounds.size() - 1 <= ORBF_MAX_CHUNKS) break;      // one copy-done event per chunk
+    }
+    const int nChunks = (int)bounds.size() - 1;
+    if (pl.active) {      // every H2D copy of the call, back to back on the copy stream
+        StreamSwap sw(c, c->copy);
+        for (int k = 0; k < nChunks; ++k) {
+            const int a = bounds[k], b = bounds[k + 1];
+            if (b <= a) continue;
+            TRY(upload_chunk(c, *hf, slot0 + a, a, b - a));
+            ORBF_CUDA(c, cudaEventRecord(c->evCopy[k], c->copy));
+        }
     }
     int prevWorker = -1;
-    for (int k = 0; k + 1 < (int)bounds.size(); ++k) {
+    for (int k = 0; k < nChunks; ++k) {
         const int a = bounds[k], b = bounds[k + 1];
         if (b <= a) continue;
         TRY(pl.enter(k));
-        if (hf && hf->gray) TRY(upload_chunk(c, *hf, slot0 + a, a, b - a));
+        if (pl.active) ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evCopy[k], 0));
+        else if (hf && hf->gray) TRY(upload_chunk(c, *hf, slot0 + a, a, b - a));
         TRY(run_extract(c, slot0 + a, b - a, !pl.active));
         const int wk = pl.active ? k % c->nWork : -1;
         if (pl.active && track) ORBF_CUDA(c, cudaEventRecord(c->evExtract[wk], c->stream));
@@ -201,17 +227,29 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
             const int pa = std::max(a - 1, 0), pb = b - 1;          // pairs [pa, pb): the straddling pair a-1 belongs to this chunk
             if (pb > pa) {
                 if (pl.active && a > 0 && prevWorker != wk) ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evExtract[prevWorker], 0));
-                TRY(run_match_group(c, pa, pb - pa, track->ratio, track->cross));
-                // RANSAC is a chain of ten latency-bound launches whose duration barely depends on the number of pairs: per
+                consecutive_pairs_kernel<<<(pb - pa + 127) / 128, 128, 0, c->stream>>>(c->d_pairs, ps0 + pa, pb - pa, slot0 + pa);
+                ORBF_LAUNCH_CHECK(c);
+                TRY(run_match_group(c, ps0 + pa, pb - pa, track->ratio, track->cross));
+                // RANSAC is a chain of latency-bound launches whose duration barely depends on the number of pairs: per
                 // chunk it would be paid once per chunk, so the pipelined path runs it once, after the join, for all pairs
-                if (track->rcfg && !pl.active) TRY(orbf_launch_ransac(c, slot_ransac_set(c), pa, pb - pa, *track->rcfg, nullptr, false));
+                if (track->rcfg && !pl.active) TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0 + pa, pb - pa, *track->rcfg, nullptr, false));
             }
         }
         prevWorker = wk;
     }
     const bool deferred = pl.active;
     TRY(pl.end());
-    if (deferred && track && npairs > 0 && track->rcfg) TRY(orbf_launch_ransac(c, slot_ransac_set(c), 0, npairs, *track->rcfg, nullptr, false));
+    if (deferred && track && npairs > 0 && track->rcfg) {
+        // RANSAC for all pairs behind the join, on the high-priority stream: its chain of small dependent launches is placed ahead of
+        // the queued CTAs of the next call's extraction kernels (pipeline_overlap), instead of waiting behind each of them
+        if (c->hi) {
+            ORBF_CUDA(c, cudaEventRecord(c->evHiA, c->stream));
+            ORBF_CUDA(c, cudaStreamWaitEvent(c->hi, c->evHiA, 0));
+            { StreamSwap sw(c, c->hi); TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0, npairs, *track->rcfg, nullptr, false)); }
+            ORBF_CUDA(c, cudaEventRecord(c->evHiB, c->hi));
+            ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evHiB, 0));
+        } else TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0, npairs, *track->rcfg, nullptr, false));
+    }
     return ORBF_OK;
 }
 
@@ -329,8 +367,62 @@ extern "C" int orbf_track_sequence(orbf_context* c, int32_t slot0, int32_t n, co
     CTX_ENTER(c);
     HostFrames hf;
     TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
-    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg };
+    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg, 0 };
     return run_batch(c, slot0, n, &hf, &ta);
+}
+
+extern "C" int orbf_track_sequence_at(orbf_context* c, int32_t slot0, int32_t pair_slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg)
+{
+    CTX_ENTER(c);
+    HostFrames hf;
+    TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
+    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg, pair_slot0 };
+    return run_batch(c, slot0, n, &hf, &ta);
+}
+
+extern "C" int orbf_read_results_async(orbf_context* c, int32_t slot0, int32_t pair_slot0, int32_t n, int32_t* frame_counts, int32_t* match_counts,
+    orbf_ransac_result* ransac, int32_t marker)
+{
+    CTX_ENTER(c);
+    if (n < 1 || slot0 < 0 || slot0 + n > c->B || marker < 0 || marker >= ORBF_MARKERS) return ORBF_ERR_ARG;
+    if ((match_counts || ransac) && (n < 2 || pair_slot0 < 0 || pair_slot0 + n - 1 > c->P)) return ORBF_ERR_ARG;
+    if (frame_counts) ORBF_CUDA(c, cudaMemcpyAsync(frame_counts, c->d_count + slot0, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (match_counts) ORBF_CUDA(c, cudaMemcpyAsync(match_counts, c->d_matchCount + pair_slot0, (n - 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (ransac) ORBF_CUDA(c, cudaMemcpyAsync(ransac, c->d_rres + pair_slot0, (size_t)(n - 1) * sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaEventRecord(c->evMarker[marker], c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_read_features_async(orbf_context* c, int32_t slot0, int32_t pair_slot0, int32_t n, orbf_keypoint* kps, uint8_t* desc, float* xyz,
+    orbf_dmatch* matches, int32_t marker)
+{
+    CTX_ENTER(c);
+    if (n < 1 || slot0 < 0 || slot0 + n > c->B || marker < 0 || marker >= ORBF_MARKERS) return ORBF_ERR_ARG;
+    if (matches && (n < 2 || pair_slot0 < 0 || pair_slot0 + n - 1 > c->P)) return ORBF_ERR_ARG;
+    const size_t K = c->K, o = (size_t)slot0 * K, N = (size_t)n * K;
+    if (kps) {
+        TRY(orbf_launch_pack_aos(c, slot0, n));
+        ORBF_CUDA(c, cudaMemcpyAsync(kps, c->d_kpAos + o, N * sizeof(orbf_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (desc) ORBF_CUDA(c, cudaMemcpyAsync(desc, c->d_desc + o * 32, N * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (xyz) {
+        ORBF_CUDA(c, cudaMemcpyAsync(xyz, c->d_ptx + o, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(xyz + N, c->d_pty + o, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(xyz + 2 * N, c->d_ptz + o, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (matches) ORBF_CUDA(c, cudaMemcpyAsync(matches, c->d_matches + (size_t)pair_slot0 * K, (size_t)(n - 1) * K * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaEventRecord(c->evMarker[marker], c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_wait_marker(orbf_context* c, int32_t marker)
+{
+    CTX_ENTER(c);
+    if (marker < 0 || marker >= ORBF_MARKERS) return ORBF_ERR_ARG;
+    ORBF_CUDA(c, cudaEventSynchronize(c->evMarker[marker]));
+    return ORBF_OK;
 }
 
 extern "C" int orbf_track_sequence_device(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
@@ -339,7 +431,7 @@ extern "C" int orbf_track_sequence_device(orbf_context* c, int32_t slot0, int32_
 {
     CTX_ENTER(c);
     TRY(set_device_inputs(c, slot0, n, d_gray, gray_pitch, gray_frame_stride, d_depth, depth_pitch_elems, depth_frame_stride_elems));
-    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg };
+    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg, 0 };
     return run_batch(c, slot0, n, nullptr, &ta);
 }
 

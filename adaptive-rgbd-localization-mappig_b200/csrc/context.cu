@@ -93,7 +93,7 @@ extern "C" void orbf_default_config(orbf_config* c)
     c->fx = 517.3f; c->fy = 516.5f; c->cx = 318.6f; c->cy = 255.3f;   // Utils/common.h:35-38 (FR1)
     c->mbf = 40.0f;
     c->depth_factor = 1.0f / 5000.0f;
-    c->pipeline_chunk = 0; c->pipeline_streams = 0; c->depth_zero_copy = 0; c->reserved_ = 0;
+    c->pipeline_chunk = 0; c->pipeline_streams = 0; c->depth_zero_copy = 0; c->pipeline_overlap = 0;
     c->k1 = c->k2 = c->p1 = c->p2 = c->k3 = 0.0f;               // the synthetic configurations zero the distortion (frame.cpp:288-291)
 }
 
@@ -279,7 +279,10 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->nWork = 0; c->evFork = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
     for (int i = 0; i < 8; ++i) c->evHiGroup[i] = nullptr;
     for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
-    c->chunkFrames = cfg->pipeline_chunk == 0 ? 64 : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
+    c->copy = nullptr;
+    for (int i = 0; i < ORBF_MAX_CHUNKS; ++i) c->evCopy[i] = nullptr;
+    for (int i = 0; i < ORBF_MARKERS; ++i) c->evMarker[i] = nullptr;
+    c->chunkFrames = cfg->pipeline_chunk == 0 ? (cfg->pipeline_overlap ? 256 : 64) : (cfg->pipeline_chunk < 0 ? 0 : std::max(cfg->pipeline_chunk, 2));
     for (int i = 0; i < ST_COUNT; ++i) { c->evA[i] = c->evB[i] = nullptr; c->evPending[i] = false; c->stageMs[i] = 0; c->stageCalls[i] = 0; }
     c->hypCap = 0; c->descStageRows = 0; c->xyzStageRows = 0; c->kfCap = 0; c->lastNPairs = 0; c->pairsFromSlots = false;
     c->cur_gray = nullptr; c->cur_depth = nullptr; c->cur_slot0 = 0; c->cur_n = 0;
@@ -298,7 +301,9 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
         c->ownStream = true;
         const int nw = cfg->pipeline_streams <= 0 ? 4 : std::min(cfg->pipeline_streams, ORBF_MAX_WORKERS);
         auto ev = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-        bool ok = ev(&c->evFork);
+        bool ok = ev(&c->evFork) && cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; ok && i < ORBF_MAX_CHUNKS; ++i) ok = ev(&c->evCopy[i]);
+        for (int i = 0; ok && i < ORBF_MARKERS; ++i) ok = ev(&c->evMarker[i]);
         for (int i = 0; ok && i < nw; ++i) {
             ok = cudaStreamCreateWithFlags(&c->work[i], cudaStreamNonBlocking) == cudaSuccess && ev(&c->evDone[i]) && ev(&c->evExtract[i]);
             if (ok) c->nWork = i + 1;
@@ -409,6 +414,9 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (c->evHiB) cudaEventDestroy(c->evHiB);
     for (int i = 0; i < 8; ++i) if (c->evHiGroup[i]) cudaEventDestroy(c->evHiGroup[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    for (int i = 0; i < ORBF_MAX_CHUNKS; ++i) if (c->evCopy[i]) cudaEventDestroy(c->evCopy[i]);
+    for (int i = 0; i < ORBF_MARKERS; ++i) if (c->evMarker[i]) cudaEventDestroy(c->evMarker[i]);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ORBF_OK;

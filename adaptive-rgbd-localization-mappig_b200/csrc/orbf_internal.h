@@ -26,6 +26,8 @@
 #define ORBF_RAW_BW 48        // describe.cu: TMA box of the orientation disc, (2 * 15 + 1) rows x 48 bytes of the raw level
 #define ORBF_RAW_BH 31
 #define ORBF_MAX_WORKERS 4    // internal worker streams of the chunked pipeline (c_abi.cu)
+#define ORBF_MAX_CHUNKS 64    // chunks of one pipelined call (one copy-done event each)
+#define ORBF_MARKERS 8        // caller-visible progress markers (orbf_read_results_async / orbf_wait_marker)
 
 struct LevelView {
     const uint8_t* base;      // address of slot 0's plane
@@ -87,6 +89,9 @@ struct orbf_context {
     // chunk k (H2D copies + all stages of its frames and frame pairs) on worker k % nWork, and joins them again
     cudaStream_t work[ORBF_MAX_WORKERS]; int nWork, chunkFrames;
     cudaEvent_t evFork, evDone[ORBF_MAX_WORKERS], evExtract[ORBF_MAX_WORKERS];
+    // all H2D copies of a pipelined call go back to back on their own stream, so the link never waits for a kernel; chunk k's
+    // kernels wait for evCopy[k]
+    cudaStream_t copy; cudaEvent_t evCopy[ORBF_MAX_CHUNKS]; cudaEvent_t evMarker[ORBF_MARKERS];
     // high-priority side stream for the latency-bound stages (quadtree, RANSAC): their few, long-running CTAs are placed as
     // soon as SM resources free up and overlap the throughput-bound kernels (blur, Hamming) still running on the main stream
     cudaStream_t hi; cudaEvent_t evHiA, evHiB, evHiGroup[8];

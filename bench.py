@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=192, help="frames of the cpu_baseline sample (rank 0, N=1; 0 = skip)")
     ap.add_argument("--chunk", type=int, default=0, help="pipeline chunk in frames (0 = library default, <0 = no chunking)")
     ap.add_argument("--streams", type=int, default=0, help="pipeline worker streams (0 = library default)")
+    ap.add_argument("--no-overlap", action="store_true", help="e2e arm: every call starts after the previous one has finished on the device")
     ap.add_argument("--depth-copy", action="store_true", help="e2e arm: stage whole depth planes in HBM instead of sampling pinned host memory in place")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -268,11 +269,20 @@ def main():
     ob = load_pkg()
     F = args.frames
     frames, depths = make_inputs(F, seed=rank)            # each rank its own shard of the sequence (weak scaling)
+    try:        # one group of host cores per rank: the ranks' launch threads and pinned-buffer traffic do not migrate onto each other
+        ncpu = os.cpu_count() or 1
+        per = max(1, ncpu // max(world, 1))
+        os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))) or set(range(ncpu)))
+    except (AttributeError, OSError):
+        pass
     ctx = ob.Context(max_frames=F, max_pairs=F, device=local, pipeline_chunk=args.chunk, pipeline_streams=args.streams,
                      depth_zero_copy=-1 if args.depth_copy else 0)
     stream = torch.cuda.Stream(device=local)
     ctx.set_stream(stream.cuda_stream)
-    pairs = np.array([[i, i + 1] for i in range(F - 1)], np.int32)
+    # the end-to-end arm double-buffers whole sequences in one context (frame / pair slot halves): the H2D copies of step i + 1 run under
+    # the last kernels, RANSAC and result read-back of step i
+    ectx = ob.Context(max_frames=2 * F, max_pairs=2 * F, device=local, pipeline_chunk=args.chunk, pipeline_streams=args.streams,
+                      depth_zero_copy=-1 if args.depth_copy else 0, pipeline_overlap=0 if args.no_overlap else 1)
 
     d_gray = torch.from_numpy(frames).cuda(local)
     d_depth = torch.from_numpy(depths.view(np.int16)).cuda(local)
@@ -283,11 +293,31 @@ def main():
     def step_device():
         ctx.track_sequence_device(d_gray.data_ptr(), W, W * H, F, d_depth.data_ptr(), W, W * H, RATIO, CROSS, seed=42)
 
-    def step_e2e():
-        ctx.track_sequence(hg, hd, RATIO, CROSS, seed=42)   # pinned host frames -> chunked H2D overlapped with the kernels
-        summ = ctx.download_ransac_summary(F - 1)           # poses + inlier counts
-        mc = ctx.match_counts(F - 1); fc = ctx.frame_counts(F)
-        return summ, mc, fc
+    pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+    res = [dict(fc=pin(F, torch.int32), mc=pin(F - 1, torch.int32), rr=pin((F - 1) * ob.RANSAC_RESULT_DT.itemsize, torch.uint8)) for _ in range(2)]
+    K = ectx.K
+    feat = None
+
+    def issue_e2e(i, full=False):
+        """Step i of the end-to-end arm: pinned host frames -> H2D -> path -> asynchronous D2H of the results (poses, inlier / match /
+        keypoint counts; with full=True also every keypoint, descriptor, 3D point and match) into pinned host memory."""
+        h = i & 1
+        ectx.track_sequence_at(hg, hd, RATIO, h * F, h * F, CROSS, seed=42)
+        r = res[h]
+        if full:
+            f = feat[h]
+            ectx.read_features_async(h * F, h * F, F, f["kps"].numpy().view(ob.KEYPOINT_DT), f["desc"].numpy(), f["xyz"].numpy(),
+                                     f["m"].numpy().view(ob.DMATCH_DT), 2 + h)
+        ectx.read_results_async(h * F, h * F, F, r["fc"].numpy(), r["mc"].numpy(), r["rr"].numpy().view(ob.RANSAC_RESULT_DT), h)
+
+    def run_e2e(steps, full=False):
+        issue_e2e(0, full)
+        for i in range(1, steps):
+            issue_e2e(i, full)
+            ectx.wait_marker((i - 1) & 1)                   # results of step i - 1 are on the host
+        ectx.wait_marker((steps - 1) & 1)
+        r = res[(steps - 1) & 1]
+        return r["rr"].numpy().view(ob.RANSAC_RESULT_DT).copy(), r["mc"].numpy().copy(), r["fc"].numpy().copy()
 
     def barrier():
         if world > 1:
@@ -318,15 +348,25 @@ def main():
     launches = ctx.launch_count() - l0
     ms = ev0.elapsed_time(ev1) / args.steps
     # ---- end-to-end timing (host buffers, copies inside the timed region) ----
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    run_e2e(max(2, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        summ, mc, fc = step_e2e()
+    summ, mc, fc = run_e2e(args.steps)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_ms = (t1 - t0) * 1e3 / args.steps
+    barrier()
+    # the same with everything the reference's calls hand back to host vectors (keypoints, descriptors, 3D points, matches) read back too
+    feat = [dict(kps=pin(F * K * ob.KEYPOINT_DT.itemsize, torch.uint8), desc=pin((F, K, 32), torch.uint8), xyz=pin((3, F, K), torch.float32),
+                 m=pin((F - 1) * K * ob.DMATCH_DT.itemsize, torch.uint8)) for _ in range(2)]
+    run_e2e(2, full=True)
+    barrier()
+    tf0 = time.perf_counter()
+    run_e2e(args.steps, full=True)
+    torch.cuda.synchronize()
+    tf1 = time.perf_counter()
+    full_ms = (tf1 - tf0) * 1e3 / args.steps
+    full_d2h = int(sum(t.numel() * t.element_size() for t in feat[0].values()))
     barrier()
     clocks = sampler.stop([(tw0, tw1), (t0, t1)])
     clocks["load_window_s"] = round(t1 - t_load0, 3)
@@ -345,10 +385,13 @@ def main():
     ctx.profile_enable(False)
     stage_ms = {k: float(np.median([it[k] for it in per_iter])) for k in per_iter[0]}     # median over the profiled steps
 
+    per_rank = None
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        mine = torch.tensor([ms, e2e_ms, full_ms], device=f"cuda:{local}", dtype=torch.float64)
+        allr = torch.empty((world, 3), device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {"device_ms": [float(x) for x in allr[:, 0]], "e2e_ms": [float(x) for x in allr[:, 1]], "e2e_full_ms": [float(x) for x in allr[:, 2]]}
+        ms, e2e_ms, full_ms = float(allr[:, 0].max()), float(allr[:, 1].max()), float(allr[:, 2].max())
     total_frames = F * world
     value = total_frames / (ms * 1e-3)
     e2e_value = total_frames / (e2e_ms * 1e-3)
@@ -396,23 +439,29 @@ def main():
             dt = time.perf_counter() - t0
             cpu = {"value": ns / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                    "sample": f"first {ns} frames of the step's batch (extract {ns}, match+RANSAC {ns - 1} pairs), oracle -O3 -march=native, {dt:.1f} s"}
-            step_e2e(); torch.cuda.synchronize()            # the results compared are those of the end-to-end path
-            parity = parity_in_bench(orc, ctx, frames, depths, ns, 42)
+            run_e2e(1); torch.cuda.synchronize()            # the results compared are those of the end-to-end path (slot half 0)
+            parity = parity_in_bench(orc, ectx, frames, depths, ns, 42)
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": config_object(F),
                "arm": {"depth": "e2e: " + ("whole planes copied to HBM" if args.depth_copy else "pinned host planes sampled in place over PCIe (one 32-byte sector per keypoint); --depth-copy stages them instead"),
-                       "pipeline": f"e2e: orbf_track_sequence, chunks of {ctx.cfg.pipeline_chunk or 64} frames over {ctx.cfg.pipeline_streams or 4} worker streams; device-resident: one stream"},
+                       "pipeline": (f"e2e: orbf_track_sequence_at into alternating slot halves of one context, H2D on a copy stream, chunks of {ectx.cfg.pipeline_chunk or (64 if args.no_overlap else 256)} "
+                                    f"frames over {ectx.cfg.pipeline_streams or 4} worker streams, " + ("calls serialised" if args.no_overlap else "consecutive calls overlap (pipeline_overlap): results of "
+                                    "step i are read back while step i + 1 runs") + "; device-resident: one stream"),
+                       "per_rank_ms": per_rank},
                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": d2h},
+               "e2e_full_download": {"value": total_frames / (full_ms * 1e-3), "unit": "frames/s", "ms_per_step": full_ms, "h2d_bytes_per_step": h2d,
+                                     "d2h_bytes_per_step": d2h + full_d2h,
+                                     "what": "as e2e, plus every frame's keypoints (cv::KeyPoint layout), descriptors, 3D points and every pair's matches copied to pinned host memory"},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_in_bench": parity,
                "results": {"mean_keypoints": float(np.mean(fc)), "mean_matches": float(np.mean(mc)),
                            "ransac_ok_frac": float(np.mean(summ["ok"])), "mean_inliers": float(np.mean(summ["n_inliers"]))}}
         print(json.dumps(out))
         if parity is not None and not parity["identical"]:
-            ctx.close()
+            ctx.close(); ectx.close()
             raise SystemExit("bench.py: the timed path disagrees with the oracle: " + "; ".join(parity["mismatches"]))
-    ctx.close()
+    ctx.close(); ectx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -71,12 +71,17 @@ typedef struct {
     int32_t device;                    /* CUDA device ordinal                                    */
     float fx, fy, cx, cy, mbf;         /* Calibration:: (Utils/common.h:35-38,71)               */
     float depth_factor;                /* Calibration::depthFactor = 1/5000 (Utils/common.h:67) */
-    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default 64, < 0 = no chunking) */
+    int32_t pipeline_chunk;            /* frames per pipeline chunk of the batched calls (0 = default: 64, or 256 with
+                                          pipeline_overlap; < 0 = no chunking) */
     int32_t pipeline_streams;          /* internal worker streams, 1..4 (0 = default 4)           */
     int32_t depth_zero_copy;           /* host depth planes in pinned (page-locked) memory are not copied: the ~1000 depth
                                           samples a frame needs are read in place over PCIe by the kernel that unprojects
                                           the keypoints (0 = default on, -1 = always stage the whole plane in HBM)          */
-    int32_t reserved_;
+    int32_t pipeline_overlap;          /* 1 = consecutive batched host-input calls may overlap on the device: a call's H2D copies and
+                                          kernels are ordered only behind the copies / kernels of earlier calls on the same internal
+                                          streams, not behind everything enqueued on the context stream.  The caller then alternates
+                                          between disjoint frame / pair slot ranges (orbf_track_sequence_at) and does not reuse a range
+                                          before it has read that range's results (0 = default: every call starts after the previous) */
     float k1, k2, p1, p2, k3;          /* Calibration::k1.. (Utils/common.h:40-44) as Frame::Frame loads them into mDistCoef
                                           (Core/frame.cpp:32-42).  k1 == 0 (the default, and what the synthetic benchmarks use)
                                           is the reference's own shortcut mvKeysUn = mvKeys (frame.cpp:288-291); otherwise
@@ -162,6 +167,23 @@ int orbf_download_gray(orbf_context* ctx, int32_t slot, uint8_t* out, int32_t ou
 int orbf_track_sequence(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
     int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, float ratio,
     int32_t cross_check, const orbf_ransac_config* ransac_cfg);
+/* The same with the pair results in pair slots pair_slot0 .. pair_slot0 + n - 2 (orbf_track_sequence uses pair_slot0 = 0): lets a
+ * caller double-buffer whole sequences in one context (frame slots [slot0, slot0 + n), pair slots [pair_slot0, ..)) so that, with
+ * orbf_config.pipeline_overlap, the H2D copies of one call run under the kernels and result read-back of the previous one.        */
+int orbf_track_sequence_at(orbf_context* ctx, int32_t slot0, int32_t pair_slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg);
+/* Asynchronous result read-back for such double-buffered use: copies frame counts [slot0, +n), match counts and RANSAC results of pair
+ * slots [pair_slot0, +n-1) into caller buffers (page-locked memory for a truly asynchronous copy; any may be NULL) on the context
+ * stream and records marker `marker` (0..7) behind them; orbf_wait_marker blocks the host until that point has been reached.          */
+int orbf_read_results_async(orbf_context* ctx, int32_t slot0, int32_t pair_slot0, int32_t n, int32_t* frame_counts, int32_t* match_counts,
+    orbf_ransac_result* ransac, int32_t marker);
+int orbf_wait_marker(orbf_context* ctx, int32_t marker);
+/* The per-frame outputs the reference hands back to host vectors, for n frames at once and asynchronously: kps [n][K] in cv::KeyPoint
+ * layout, desc [n][K][32], xyz [3][n][K] (mvKeys3Dc as x / y / z planes), matches [n - 1][K] (K = orbf_keypoint_capacity; rows past a
+ * frame's / pair's count are unspecified; any pointer may be NULL), then marker `marker`.                                        */
+int orbf_read_features_async(orbf_context* ctx, int32_t slot0, int32_t pair_slot0, int32_t n, orbf_keypoint* kps, uint8_t* desc, float* xyz,
+    orbf_dmatch* matches, int32_t marker);
 int orbf_track_sequence_device(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
     int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems, float ratio,
     int32_t cross_check, const orbf_ransac_config* ransac_cfg);
