@@ -510,6 +510,41 @@ class Context:
         self._chk(lib().orbf_kfdb_attach_device(self._h, C.c_void_p(d_desc_ptr) if d_desc_ptr else None,
                                                 C.c_void_p(d_counts_ptr) if d_counts_ptr else None, n_kf), "kfdb_attach_device")
 
+    def kfdb_match_slot(self, slot, kf0, nkf, ratio):
+        """Device-resident query (frame slot) against keyframes [kf0, kf0 + nkf); asynchronous."""
+        self._chk(lib().orbf_kfdb_match_slot(self._h, slot, kf0, nkf, C.c_float(ratio)), "kfdb_match_slot")
+
+    def kfdb_results(self, nkf, nq, tables=True):
+        o = [np.zeros((nkf, nq), np.int32) for _ in range(4)] if tables else [None] * 4
+        surv = np.zeros(nkf, np.int32)
+        self._chk(lib().orbf_kfdb_results(self._h, nkf, nq, _p(o[0]), _p(o[1]), _p(o[2]), _p(o[3]), _p(surv)), "kfdb_results")
+        return o[0], o[1], o[2], o[3], surv
+
+    # ---- multi-GPU keyframe store ----
+    def comm_init(self, id128, nranks, rank):
+        id128 = np.ascontiguousarray(id128, np.uint8); assert id128.size == 128
+        self._chk(lib().orbf_comm_init(self._h, _p(id128), nranks, rank), "comm_init")
+
+    def comm_destroy(self):
+        self._chk(lib().orbf_comm_destroy(self._h), "comm_destroy")
+
+    def kfdb_allgather(self):
+        n = C.c_int32(0)
+        self._chk(lib().orbf_kfdb_allgather(self._h, C.byref(n)), "kfdb_allgather")
+        return n.value
+
+    def kfdb_ipc_handles(self):
+        a = np.zeros(64, np.uint8); b = np.zeros(64, np.uint8)
+        self._chk(lib().orbf_kfdb_ipc_handles(self._h, _p(a), _p(b)), "kfdb_ipc_handles")
+        return a, b
+
+    def kfdb_attach_peers(self, desc_handles, count_handles, nranks, rank, kf_per_rank):
+        dh = np.ascontiguousarray(desc_handles, np.uint8).reshape(nranks, 64); ch = np.ascontiguousarray(count_handles, np.uint8).reshape(nranks, 64)
+        self._chk(lib().orbf_kfdb_attach_peers(self._h, _p(dh), _p(ch), nranks, rank, kf_per_rank), "kfdb_attach_peers")
+
+    def kfdb_detach_peers(self):
+        self._chk(lib().orbf_kfdb_detach_peers(self._h), "kfdb_detach_peers")
+
     def kfdb_survivors(self, q, kf0, nkf, ratio):
         """Number of ratio-test survivors of the query against each keyframe (no top-2 tables downloaded)."""
         q = np.ascontiguousarray(q, np.uint8)
@@ -560,3 +595,12 @@ def selftest_sincosf(lo_bits, hi_bits, want_values=False):
     if rc:
         raise OrbfError(rc, "selftest_sincosf")
     return nd.value, out
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 draws it, the application broadcasts it, every rank passes it to Context.comm_init)."""
+    out = np.zeros(128, np.uint8)
+    rc = lib().orbf_comm_unique_id(_p(out))
+    if rc:
+        raise OrbfError(rc, "comm_unique_id")
+    return out

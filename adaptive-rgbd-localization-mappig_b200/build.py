@@ -15,7 +15,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "liborbfront_b200.so"
-SOURCES = ["context.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "match.cu", "ransac.cu", "kfdb.cu", "adaptive.cu", "projection.cu", "c_abi.cu"]
+SOURCES = ["context.cu", "pyramid.cu", "fast.cu", "quadtree.cu", "describe.cu", "match.cu", "ransac.cu", "kfdb.cu", "comm.cu", "adaptive.cu", "projection.cu", "c_abi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--threads", "0"]
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
             return str(OUT)
         want = source_hash()
         tmp = HERE / f"liborbfront_b200.so.tmp.{os.getpid()}"
-        cmd = [NVCC] + FLAGS + ["-shared", "-o", str(tmp)] + [str(CSRC / s) for s in SOURCES]
+        cmd = [NVCC] + FLAGS + ["-shared", "-o", str(tmp)] + [str(CSRC / s) for s in SOURCES] + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         (HERE / "build.log").write_text(log)

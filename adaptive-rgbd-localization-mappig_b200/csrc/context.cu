@@ -363,6 +363,9 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->d_kfDesc = nullptr; c->d_kfCount = nullptr; c->d_kfExtDesc = nullptr; c->d_kfExtCount = nullptr; c->kfExtN = 0;
     c->d_pts = nullptr; c->ptsCap = 0; c->d_userSamples = nullptr; c->userSamplesCap = 0; c->d_kabsch = nullptr; c->kabschCap = 0;
     c->d_kfKnn = nullptr; c->d_kfSurv = nullptr; c->d_kfPairs = nullptr; c->d_kfQCount = nullptr; c->kfOutCap = 0;
+    c->ncclComm = nullptr; c->commRanks = 1; c->commRank = 0; c->d_kfGather = nullptr; c->d_kfGatherCount = nullptr; c->kfGatherCap = 0;
+    c->d_peerDesc = nullptr; c->d_peerCount = nullptr; c->nPeers = 0; c->peerKf = 0;
+    for (void*& q : c->peerOpened) q = nullptr;
     c->h_kp = nullptr; c->h_desc = nullptr; c->h_xyz = nullptr; c->h_counts = nullptr;
     auto cu = [&](cudaError_t e3, const char* w) { if (e3 != cudaSuccess) { orbf_cuda_fail(c, e3, w, __FILE__, __LINE__); return false; } return true; };
     if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
@@ -391,6 +394,7 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (!c) return ORBF_ERR_ARG;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    orbf_comm_release(c);
     void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_blTiles, c->d_rsTiles, c->d_bgr, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpux, c->d_kpuy, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,

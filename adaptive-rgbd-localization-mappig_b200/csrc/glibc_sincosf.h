@@ -2,7 +2,7 @@
 //
 // Why: computeOrbDescriptor (reference Features/orbextractor.cpp:45-46) writes  float a = (float)cos(angle), b = (float)sin(angle);
 // with a FLOAT argument under `using namespace std`, so overload resolution picks std::cos(float) / std::sin(float) — libm's
-// cosf / sinf, not the double functions.  (oracle/_ref compiles that very line; (float)cos((double)angle) differs from cosf(angle)
+// cosf / sinf, not the double functions.  (the reference-source build used by the tests compiles that very line; (float)cos((double)angle) differs from cosf(angle)
 // in the last bit for ~2.6 % of the angles, which can move a rotated test point across a rounding boundary.)  Like std::sort and
 // rand() (csrc/replay.h) this is library behaviour the reference inherits, so it is replayed, not approximated.
 //

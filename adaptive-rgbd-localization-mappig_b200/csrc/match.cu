@@ -125,6 +125,18 @@ __device__ __forceinline__ void fold_columns(const uint32_t* sCol, uint32_t* rev
     }
 }
 
+// train side of pair slot ts: rows + row count, from the single store or from the shard (possibly a peer GPU's memory) that owns it
+__device__ __forceinline__ const uint8_t* train_rows(const MatchSet& ms, int ts, int& nt)
+{
+    if (ms.tShards) {
+        const int sh = ts / ms.shardKf, local = ts - sh * ms.shardKf;
+        nt = ms.tShardCounts[sh][local];
+        return ms.tShards[sh] + (long long)local * ms.tStride;
+    }
+    nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
+    return ms.tdesc + (long long)ts * ms.tStride;
+}
+
 template <bool CROSS>
 __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
 {
@@ -136,11 +148,12 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
     const int pair = ms.pair0 + blockIdx.y;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
-    const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq, nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
+    int nt;
+    const uint32_t* T = reinterpret_cast<const uint32_t*>(train_rows(ms, ts, nt));
+    const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq;
     const int qBase = blockIdx.x * UM_ROWS;
     if (qBase >= nq) return;
     const uint32_t* Q = reinterpret_cast<const uint32_t*>(ms.qdesc + (long long)qs * ms.qStride);
-    const uint32_t* T = reinterpret_cast<const uint32_t*>(ms.tdesc + (long long)ts * ms.tStride);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = warp & 3, colHalf = warp >> 2;         // TMEM lanes 32 * quarter .. + 31, chunk columns 128 * colHalf .. + 127
     uint8_t* sA = umSmemRaw + ((1024u - (smem_u32(umSmemRaw) & 1023u)) & 1023u);
@@ -286,7 +299,9 @@ __global__ void __launch_bounds__(MS_THREADS) match_select_kernel(MatchSet ms, i
     const int pair = ms.pair0 + blockIdx.x;
     int qs = 0, ts = 0;
     if (ms.pairs) { qs = ms.pairs[2 * pair]; ts = ms.pairs[2 * pair + 1]; }
-    const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq, nt = ms.tCounts ? ms.tCounts[ts] : ms.nt;
+    int nt;
+    (void)train_rows(ms, ts, nt);
+    const int nq = ms.qCounts ? ms.qCounts[qs] : ms.nq;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) sBase = 0;
     __syncthreads();

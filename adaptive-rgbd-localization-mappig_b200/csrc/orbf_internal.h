@@ -158,6 +158,11 @@ struct orbf_context {
     uint8_t* d_kfDesc; int* d_kfCount; int kfCap;
     const uint8_t* d_kfExtDesc; const int* d_kfExtCount; int kfExtN;   // caller-owned store (orbf_kfdb_attach_device)
     uint32_t* d_kfKnn; int* d_kfSurv; int* d_kfPairs; int* d_kfQCount; int kfOutCap;
+    // multi-GPU keyframe store (comm.cu): NCCL communicator (loaded with dlopen), all-gathered copy of every rank's store, and the
+    // peer stores opened through CUDA IPC for the gather-free path
+    void* ncclComm; int commRanks, commRank;
+    uint8_t* d_kfGather; int* d_kfGatherCount; int kfGatherCap;
+    const uint8_t** d_peerDesc; const int** d_peerCount; void* peerOpened[2 * 64]; int nPeers, peerKf;
 };
 
 // ---- error helpers --------------------------------------------------------------------------------
@@ -179,6 +184,8 @@ __host__ __device__ static inline int align_up(int v, int a) { return (v + a - 1
 void orbf_prof_begin(orbf_context* c, int stage);
 void orbf_prof_end(orbf_context* c, int stage);
 
+void orbf_comm_release(orbf_context* c);      // comm.cu: communicator, gathered store, peer mappings
+
 // ---- stage launchers (each enqueues on ctx->stream for slots [slot0, slot0+n)) ---------------------
 PyrView orbf_pyr_view(const orbf_context* ctx, bool blurred);
 int orbf_refresh_maps(orbf_context* ctx);
@@ -195,6 +202,9 @@ struct MatchSet {
     const uint8_t* qdesc; const uint8_t* tdesc;   // base of slot 0 (row stride 32 B)
     long long qStride, tStride;                    // bytes per slot (K*32), 0 when every pair uses slot 0
     const int* qCounts; const int* tCounts;        // per-slot row counts (NULL => nq / nt)
+    // sharded train side (keyframe stores of several GPUs read in place over NVLink): train slot ts lives on shard ts / shardKf at
+    // local index ts % shardKf; tShards / tShardCounts are device arrays of (peer) pointers.  NULL => tdesc / tCounts above
+    const uint8_t* const* tShards = nullptr; const int* const* tShardCounts = nullptr; int shardKf = 0;
     const int* pairs;                              // [npairs][2] (query slot, train slot); NULL => slots (0, 0)
     int pair0;                                     // first pair slot of this launch (pair = pair0 + blockIdx)
     int nq, nt;

@@ -220,6 +220,127 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_config5(args):
+    """--config 5: keyframe-database many-to-many matching (BASELINE configs[4]): every rank holds 2048 / N keyframes (~1000 rows of 32
+    bytes each) and matches its own 1000-keypoint query against ALL 2048.  Two ways to reach the other ranks' keyframes, both timed with
+    CUDA events on the context stream, max over ranks:  allgather = ncclAllGather of the stores into a gathered copy + local match;
+    peers = no collective, the matcher reads every keyframe from its owner's HBM over NVLink (CUDA IPC).  Parity: a sample of
+    keyframes from every rank against the oracle (top-2 tables and ratio survivors)."""
+    import torch
+    import torch.distributed as dist
+    import synth
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local)); dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    ob = load_pkg()
+    NKF, NBASE = 2048, 16
+    kf_local = NKF // world
+    tex = synth.make_texture(0, H, W)
+    base = np.stack([synth.make_frame(tex, 2 * i, W, H, 0) for i in range(NBASE)])          # "every 2nd frame's output"
+    qframe = synth.make_frame(tex, 2 * rank + 1, W, H, 0)[None]
+    ctx = ob.Context(max_frames=NBASE + 1, device=local)
+    stream = torch.cuda.Stream(device=local); ctx.set_stream(stream.cuda_stream)
+    ctx.extract_batch(base); ctx.extract_batch(qframe, slot0=NBASE)
+    counts = ctx.frame_counts(NBASE + 1)
+    nq = int(counts[NBASE])
+    ctx.kfdb_reserve(kf_local)
+    for k in range(kf_local):
+        ctx.kfdb_add_from_slot(k, (rank * kf_local + k) % NBASE)       # global keyframe g holds base frame g % NBASE
+    ctx.synchronize()
+    kf_rows = np.array([counts[g % NBASE] for g in range(NKF)], np.int64)
+    pairs_per_query = float(nq * kf_rows.sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
+        return ms
+
+    out = {}
+    results = {}
+    if world > 1:
+        idt = torch.from_numpy(ob.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda(local)
+        dist.broadcast(idt, 0)
+        ctx.comm_init(idt.cpu().numpy(), world, rank)
+        assert ctx.kfdb_allgather() == NKF
+        gather_ms = timed(lambda: ctx.kfdb_allgather())
+        match_ms = timed(lambda: ctx.kfdb_match_slot(NBASE, 0, NKF, 0.8))
+        both_ms = timed(lambda: (ctx.kfdb_allgather(), ctx.kfdb_match_slot(NBASE, 0, NKF, 0.8)))
+        results["allgather"] = ctx.kfdb_results(NKF, nq)
+        gbytes = kf_local * ctx.K * 32
+        out["allgather"] = {"gather_ms": gather_ms, "match_ms": match_ms, "gather_plus_match_ms": both_ms, "bytes_per_rank": gbytes,
+                            "bus_GBps": gbytes * (world - 1) / (gather_ms * 1e-3) / 1e9, "nvlink5_peak_GBps_per_direction": 900.0,
+                            "frac_of_nvlink": gbytes * (world - 1) / (gather_ms * 1e-3) / 1e9 / 900.0,
+                            "pairs_per_s": world * pairs_per_query / (both_ms * 1e-3)}
+        a, b = ctx.kfdb_ipc_handles()
+        mine = torch.from_numpy(np.concatenate([a, b])).cuda(local); allh = torch.empty((world, 128), dtype=torch.uint8, device=f"cuda:{local}")
+        dist.all_gather_into_tensor(allh, mine)
+        hh = allh.cpu().numpy()
+        ctx.kfdb_attach_peers(hh[:, :64].copy(), hh[:, 64:].copy(), world, rank, kf_local)
+        peers_ms = timed(lambda: ctx.kfdb_match_slot(NBASE, 0, NKF, 0.8))
+        results["peers"] = ctx.kfdb_results(NKF, nq)
+        out["peers"] = {"match_ms": peers_ms, "pairs_per_s": world * pairs_per_query / (peers_ms * 1e-3),
+                        "remote_bytes_per_rank": int((world - 1) * kf_local * ctx.K * 32),
+                        "remote_read_GBps": (world - 1) * kf_local * ctx.K * 32 / (peers_ms * 1e-3) / 1e9}
+        headline_ms, how = min((both_ms, "allgather + match"), (peers_ms, "peer reads, no collective"))
+    else:
+        headline_ms = timed(lambda: ctx.kfdb_match_slot(NBASE, 0, NKF, 0.8))
+        how = "single GPU holds all keyframes"
+        results["local"] = ctx.kfdb_results(NKF, nq)
+        out["local"] = {"match_ms": headline_ms, "pairs_per_s": pairs_per_query / (headline_ms * 1e-3)}
+    # parity against the oracle: 3 keyframes of every rank's shard (global ids), every route measured
+    from oracle import oracle as orc
+    orc.build()
+    bdesc = [orc.extract(base[i])[1] for i in range(NBASE)]
+    q = orc.extract(qframe[0])[1]
+    bad = []
+    sample = sorted({r * kf_local + j for r in range(world) for j in (0, kf_local // 2, kf_local - 1)})
+    for route, (i1, d1, i2, d2, surv) in results.items():
+        for g in sample:
+            ref = orc.knn2(q, bdesc[g % NBASE])
+            if not (np.array_equal(i1[g], ref[0]) and np.array_equal(d1[g], ref[1]) and np.array_equal(i2[g], ref[2]) and np.array_equal(d2[g], ref[3])
+                    and int(surv[g]) == len(orc.knn_match(q, bdesc[g % NBASE], 0.8))):
+                bad.append(f"{route}: keyframe {g}")
+    ok = torch.tensor([0 if bad else 1], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        value = world * pairs_per_query / (headline_ms * 1e-3)
+        print(json.dumps({"metric": "descriptor_pairs_per_sec_kfdb_1000kp_query_vs_2048_keyframes", "value": value, "unit": "pairs/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": headline_ms, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[4]: keyframe-database many-to-many Hamming kNN-2 + ratio 0.8, one ~1000-keypoint query per rank against 2048 "
+                                                 "keyframes sharded over the ranks", "keyframes": NKF, "keyframes_per_rank": kf_local, "query_rows": nq,
+                                     "mean_keyframe_rows": float(kf_rows.mean()), "route": how},
+                          "routes": out, "parity": {"keyframes_checked_per_route": len(sample), "identical_on_every_rank": bool(int(ok[0])), "mismatches": bad[:6]},
+                          "gpu_launches": int(ctx.launch_count())}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if bad:
+        raise SystemExit("bench.py --config 5: device results disagree with the oracle: " + "; ".join(bad[:6]))
+
+
 def knn2_view(frame_counts, ms):
     """The matcher is the one compute-bound stage: descriptor pairs/s, and the same number as int8 tensor-core throughput
     (tcgen05 kind::i8: every pair is a 256-long s8 dot product = 512 ops; dense peak = 16384 ops/clk/SM, the figure ncu
@@ -242,11 +363,15 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=192, help="frames of the cpu_baseline sample (rank 0, N=1; 0 = skip)")
     ap.add_argument("--chunk", type=int, default=0, help="pipeline chunk in frames (0 = library default, <0 = no chunking)")
     ap.add_argument("--streams", type=int, default=0, help="pipeline worker streams (0 = library default)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5], help="3 = the headline sequence workload (default); 4 = 1280x720 / 2000 kp "
+                    "with adapted thresholds; 5 = keyframe-database many-to-many matching over NCCL / NVLink")
     ap.add_argument("--no-overlap", action="store_true", help="e2e arm: every call starts after the previous one has finished on the device")
     ap.add_argument("--depth-copy", action="store_true", help="e2e arm: stage whole depth planes in HBM instead of sampling pinned host memory in place")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 5:
+        return run_config5(args)
 
     import torch
     import torch.distributed as dist

@@ -292,6 +292,26 @@ int orbf_kfdb_attach_device(orbf_context* ctx, const uint8_t* d_desc, const int3
 int orbf_kfdb_match(orbf_context* ctx, const uint8_t* q, int32_t nq, int32_t kf0, int32_t nkf, float ratio,
     int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors);
 
+/* Device-resident query (BASELINE config 5 at scale): the descriptors of frame slot `slot` against keyframes [kf0, kf0 + nkf) of the
+ * current store; asynchronous.  orbf_kfdb_results returns the tables / survivor counts of the last match (synchronises).          */
+int orbf_kfdb_match_slot(orbf_context* ctx, int32_t slot, int32_t kf0, int32_t nkf, float ratio);
+int orbf_kfdb_results(orbf_context* ctx, int32_t nkf, int32_t nq, int32_t* idx1, int32_t* d1, int32_t* idx2, int32_t* d2, int32_t* survivors);
+
+/* ---- multi-GPU keyframe store: one process per GPU, every rank holds a shard of the keyframes -------------------
+ * (a) NCCL: rank 0 draws a 128-byte id (orbf_comm_unique_id), the host application hands it to every rank by any means, every rank
+ *     calls orbf_comm_init; orbf_kfdb_allgather then all-gathers the stores over NVLink (ncclAllGather, uint8) into a gathered copy
+ *     that orbf_kfdb_match* read: keyframe g = rank * capacity + local index.  NCCL is loaded with dlopen on first use.
+ * (b) no collective: every rank exports its store (orbf_kfdb_ipc_handles, 2 x 64 bytes), the application exchanges the handles, and
+ *     orbf_kfdb_attach_peers makes the matcher read every keyframe's rows from the GPU that owns it over NVLink (CUDA IPC).       */
+int orbf_comm_unique_id(uint8_t* id128);
+int orbf_comm_init(orbf_context* ctx, const uint8_t* id128, int32_t nranks, int32_t rank);
+int orbf_comm_destroy(orbf_context* ctx);
+int orbf_kfdb_allgather(orbf_context* ctx, int32_t* n_kf_total);
+int orbf_kfdb_ipc_handles(orbf_context* ctx, uint8_t* desc_handle64, uint8_t* count_handle64);
+int orbf_kfdb_attach_peers(orbf_context* ctx, const uint8_t* desc_handles, const uint8_t* count_handles, int32_t nranks, int32_t rank,
+    int32_t kf_per_rank);
+int orbf_kfdb_detach_peers(orbf_context* ctx);
+
 /* ---- adaptive-threshold FAST detector (Extractor mode ADAPTIVE with the FAST detector) ---------- */
 typedef struct {
     int32_t min_features, max_features, max_iters, max_per_cell, grid, edge;   /* 67, 113, 5, 113, 3, 31 (extractor.cpp:65-77)   */
