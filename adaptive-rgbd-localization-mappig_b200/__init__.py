@@ -490,6 +490,22 @@ class Context:
         self._chk(lib().orbf_selftest_sincosf_device(self._h, C.c_uint32(lo_bits), C.c_uint32(hi_bits), _p(out)), "selftest_sincosf_device")
         return out
 
+    def extract_adapted(self, frames, thresh, depths=None, slot0=0, **kw):
+        """BASELINE config 4, 8-level variant: ORB extraction with per-region adapted iniThFAST, frames in order; `thresh` [grid*grid]
+        float64 is updated in place.  Returns (region_th [n, g2], region_found [n, g2]); results live in the frame slots."""
+        cfg = AdaptiveConfig()
+        lib().orbf_default_adaptive_config(C.byref(cfg))
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        g2 = cfg.grid * cfg.grid
+        assert thresh.dtype == np.float64 and len(thresh) == g2
+        used = np.zeros((n, g2), np.int32); found = np.zeros((n, g2), np.int32)
+        self._chk(lib().orbf_extract_adapted(self._h, slot0, n, _p(frames), C.c_int64(w), C.c_int64(w * h), _p(depths), C.c_int64(w), C.c_int64(w * h),
+                                             C.byref(cfg), _p(thresh), _p(used), _p(found)), "extract_adapted")
+        return used, found
+
     # ---- keyframe store ----
     def kfdb_reserve(self, n):
         self._chk(lib().orbf_kfdb_reserve(self._h, n), "kfdb_reserve")

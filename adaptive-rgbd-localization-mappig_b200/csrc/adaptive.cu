@@ -278,7 +278,92 @@ __global__ void __launch_bounds__(CS_THREADS) cell_select_kernel(const __grid_co
     if (tid == 0) P.outCount[slot] = min(sBase[1], N);
 }
 
+// ---- BASELINE config 4, 8-level variant: per-region controllers around the ORB extractor ------------------------------------------
+// One CTA after the quadtree of frame slot `slot`: found[region] = keypoints the extractor returned there (their image coordinates
+// are level coordinates * scale[level], as the output assembly computes them), log of (threshold used, found) for the frame, then one
+// DetectorAdjuster step per region (tooFew: *= dec, tooMany: *= inc, clamped) and the integer thresholds of the NEXT frame's cells.
+struct RegionParams {
+    const uint32_t* lkp; const int* lkpCount; int kpStageTotal, L, slot, frameIdx;
+    int kpOff[ORBF_MAX_LEVELS]; float scale[ORBF_MAX_LEVELS];
+    int grid, width, height, minFeat, maxFeat, minThFast;
+    double minTh, maxTh, inc, dec;
+    int* regionTh; double* state; int* log;         // log [frame][2][grid * grid]: thresholds used, keypoints found
+};
+
+__global__ void __launch_bounds__(256) region_control_kernel(const RegionParams P)
+{
+    __shared__ int sFound[AD_MAX_CELLS];
+    const int tid = threadIdx.x, g2 = P.grid * P.grid;
+    if (tid < AD_MAX_CELLS) sFound[tid] = 0;
+    __syncthreads();
+    for (int l = 0; l < P.L; ++l) {
+        const int n = P.lkpCount[P.slot * ORBF_MAX_LEVELS + l];
+        const uint32_t* kp = P.lkp + (long long)P.slot * P.kpStageTotal + P.kpOff[l];
+        for (int i = tid; i < n; i += 256) {
+            const uint32_t key = kp[i];
+            float x = (float)((int)(key & 0x7FF) + ORBF_MINB), y = (float)((int)((key >> 11) & 0x7FF) + ORBF_MINB);
+            if (l > 0) { x = __fmul_rn(x, P.scale[l]); y = __fmul_rn(y, P.scale[l]); }
+            const int ry = min(P.grid - 1, (int)y * P.grid / P.height), rx = min(P.grid - 1, (int)x * P.grid / P.width);
+            atomicAdd(&sFound[ry * P.grid + rx], 1);
+        }
+    }
+    __syncthreads();
+    if (tid < g2) {
+        const int found = sFound[tid];
+        int* log = P.log + (long long)P.frameIdx * 2 * g2;
+        log[tid] = P.regionTh[tid]; log[g2 + tid] = found;
+        double st = P.state[tid];
+        if (found < P.minFeat) { st *= P.dec; if (st < P.minTh) st = P.minTh; }
+        else if (found > P.maxFeat) { st *= P.inc; if (st > P.maxTh) st = P.maxTh; }
+        P.state[tid] = st;
+        P.regionTh[tid] = max(P.minThFast, min(254, (int)st));
+    }
+}
+
 }  // namespace
+
+int orbf_launch_region_control(orbf_context* c, int slot, int frameIdx, const orbf_adaptive_config& cfg)
+{
+    RegionParams P;
+    P.lkp = c->d_lkp; P.lkpCount = c->d_lkpCount; P.kpStageTotal = c->kpStageTotal; P.L = c->L; P.slot = slot; P.frameIdx = frameIdx;
+    for (int l = 0; l < c->L; ++l) { P.kpOff[l] = c->lg[l].kpOff; P.scale[l] = c->scale[l]; }
+    P.grid = cfg.grid; P.width = c->cfg.width; P.height = c->cfg.height; P.minFeat = cfg.min_features; P.maxFeat = cfg.max_features;
+    P.minThFast = c->cfg.min_th_fast; P.minTh = cfg.min_th; P.maxTh = cfg.max_th; P.inc = cfg.inc; P.dec = cfg.dec;
+    P.regionTh = c->d_regionTh; P.state = c->d_regionState; P.log = c->d_regionLog;
+    region_control_kernel<<<1, 256, 0, c->stream>>>(P);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
+
+// region of every FAST cell for a grid x grid partition: that of the cell's first scored pixel mapped to the image (the same float
+// product and integer division as the oracle's definition), and room for nFrames log rows
+int orbf_region_tables(orbf_context* c, int grid, int nFrames)
+{
+    const int g2 = grid * grid;
+    if (c->cellRegionGrid != grid) {
+        std::vector<uint8_t> reg(c->h_cells.size());
+        for (size_t i = 0; i < c->h_cells.size(); ++i) {
+            const CellDesc& d = c->h_cells[i];
+            const float sc = c->scale[d.level];
+            const int ry = std::min(grid - 1, (int)((float)d.y0 * sc) * grid / c->cfg.height), rx = std::min(grid - 1, (int)((float)d.x0 * sc) * grid / c->cfg.width);
+            reg[i] = (uint8_t)(ry * grid + rx);
+        }
+        if (!c->d_cellRegion) ORBF_CUDA(c, cudaMalloc((void**)&c->d_cellRegion, std::max<size_t>(reg.size(), 1)));
+        if (!c->d_regionTh) ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionTh, AD_MAX_CELLS * sizeof(int)));
+        if (!c->d_regionState) ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionState, AD_MAX_CELLS * sizeof(double)));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->d_cellRegion, reg.data(), reg.size(), cudaMemcpyHostToDevice, c->stream));
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->cellRegionGrid = grid;
+    }
+    if (nFrames * 2 * g2 > c->regionLogCap) {
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_regionLog) cudaFree(c->d_regionLog);
+        c->d_regionLog = nullptr; c->regionLogCap = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionLog, (size_t)nFrames * 2 * g2 * sizeof(int)));
+        c->regionLogCap = nFrames * 2 * g2;
+    }
+    return ORBF_OK;
+}
 
 extern "C" void orbf_default_adaptive_config(orbf_adaptive_config* c)
 {

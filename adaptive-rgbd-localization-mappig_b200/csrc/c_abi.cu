@@ -348,6 +348,50 @@ extern "C" int orbf_extract_batch_bgr(orbf_context* c, int32_t slot0, int32_t n,
     return run_batch(c, slot0, n, nullptr, nullptr);
 }
 
+// BASELINE config 4, 8-level variant (defined by the oracle's orc_extract_adapted): ORB extraction of n host
+// frames, in order, with iniThFAST adapted per region of a grid x grid partition by controllers that carry their state from frame to
+// frame.  The pyramid, blur and descriptor stages run batched over all frames; FAST -> quadtree -> controller step form a chain per
+// frame (frame i + 1's thresholds depend on the keypoints frame i returned), enqueued back to back without touching the host.
+extern "C" int orbf_extract_adapted(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
+    const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, const orbf_adaptive_config* cfg, double* thresh,
+    int32_t* region_th, int32_t* region_found)
+{
+    CTX_ENTER(c);
+    if (!cfg || !thresh || cfg->grid < 1 || cfg->grid > 5) return ORBF_ERR_ARG;
+    const int g2 = cfg->grid * cfg->grid;
+    HostFrames hf;
+    TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
+    TRY(orbf_region_tables(c, cfg->grid, n));
+    TRY(upload_chunk(c, hf, slot0, 0, n));
+    std::vector<double> st(thresh, thresh + g2);
+    std::vector<int> th(g2);
+    for (int r = 0; r < g2; ++r) {
+        if (!(st[r] > 0)) st[r] = cfg->init_th;
+        th[r] = std::max(c->cfg.min_th_fast, std::min(254, (int)st[r]));
+    }
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_regionState, st.data(), g2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_regionTh, th.data(), g2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    TRY(orbf_launch_pyramid(c, slot0, n));
+    for (int i = 0; i < n; ++i) {
+        TRY(orbf_launch_fast(c, slot0 + i, 1, /*adapted=*/true));
+        TRY(orbf_launch_quadtree(c, slot0 + i, 1));
+        TRY(orbf_launch_region_control(c, slot0 + i, i, *cfg));
+    }
+    TRY(orbf_launch_blur(c, slot0, n));
+    TRY(orbf_launch_describe(c, slot0, n));
+    std::vector<int> log((size_t)n * 2 * g2);
+    ORBF_CUDA(c, cudaMemcpyAsync(st.data(), c->d_regionState, g2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(log.data(), c->d_regionLog, log.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::copy(st.begin(), st.end(), thresh);
+    for (int i = 0; i < n; ++i)
+        for (int r = 0; r < g2; ++r) {
+            if (region_th) region_th[(size_t)i * g2 + r] = log[(size_t)i * 2 * g2 + r];
+            if (region_found) region_found[(size_t)i * g2 + r] = log[(size_t)i * 2 * g2 + g2 + r];
+        }
+    return ORBF_OK;
+}
+
 extern "C" int orbf_download_gray(orbf_context* c, int32_t slot, uint8_t* out, int32_t out_stride)
 {
     CTX_ENTER(c);

@@ -290,6 +290,8 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->tmStaticReady = false; c->tm0Base = nullptr; c->tm0Pitch = c->tm0FrameStride = 0; c->tm0Frames = 0;
     int rc = build_geometry(c, tab, cells, strips, blTiles, rsTiles);
     c->nStrips = (int)strips.size(); c->nBlTiles = (int)blTiles.size();
+    c->h_cells = cells;
+    c->d_cellRegion = nullptr; c->cellRegionGrid = 0; c->d_regionTh = nullptr; c->d_regionState = nullptr; c->d_regionLog = nullptr; c->regionLogCap = 0;
     if (rc != ORBF_OK) { delete c; return rc; }
 
     cudaError_t e = cudaSetDevice(cfg->device);
@@ -400,7 +402,7 @@ extern "C" int orbf_destroy(orbf_context* c)
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpux, c->d_kpuy, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,
         c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts,
-        c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount };
+        c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount, c->d_cellRegion, c->d_regionTh, c->d_regionState, c->d_regionLog };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < c->L; ++l) { if (c->d_pyr[l]) cudaFree(c->d_pyr[l]); if (c->d_blur[l]) cudaFree(c->d_blur[l]); }
     if (c->h_kp) cudaFreeHost(c->h_kp);

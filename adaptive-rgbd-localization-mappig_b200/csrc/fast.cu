@@ -53,6 +53,8 @@ struct FastParams {
     uint32_t* cellCand; int* cellCount;
     int cellSlotTotal, nCellsTotal, iniTh, minTh, slot0, z0;   // z coordinate of a slot: slot - z0 on level 0, slot elsewhere
     int scoreOff, listOff, bitsOff;                             // byte offsets of the shared-memory regions
+    // region-adapted variant (orbf_extract_adapted): iniTh of a cell = regionTh[cellRegion[cell]]; NULL => iniTh everywhere
+    const uint8_t* cellRegion; const int* regionTh;
     short BH[ORBF_MAX_LEVELS];
 };
 
@@ -160,7 +162,7 @@ __device__ __forceinline__ void pretest(const uint8_t* tile, uint16_t* list, int
 // the list — as score-plane positions — so that the NMS pass runs with full warps.  A round reads 2 * FS_THREADS entries before
 // anything is appended, and the appends of round k stay below the entries consumed so far, so the only hazard is inside a round
 // (the barrier).  Ends with a barrier: *sCorner is the corner count.
-__device__ __forceinline__ void strengths(const uint8_t* org, uint8_t* sorg, uint16_t* list, int n, int* sCorner, int th, const uint8_t* sCellOf, const int* sC0, int tid)
+__device__ __forceinline__ void strengths(const uint8_t* org, uint8_t* sorg, uint16_t* list, int n, int* sCorner, const int* sTh, const uint8_t* sCellOf, const int* sC0, int tid)
 {
     const int lane = tid & 31;
 #if !FV_CELLTAB
@@ -168,25 +170,29 @@ __device__ __forceinline__ void strengths(const uint8_t* org, uint8_t* sorg, uin
 #endif
     for (int base = 0; base < n; base += 2 * FS_THREADS) {
         const int ia = base + 2 * tid;
-        int pa = 0, pb = 0, sa = 0, sb = 0;
+        int pa = 0, pb = 0, sa = 0, sb = 0, tha = 255, thb = 255;
         if (ia < n) {
             const int ea = list[ia], eb = list[min(ia + 1, n - 1)];
             const uint32_t s = ring_strength_x2(org + ea, org + eb, BW);
             sa = (int)(s & 0xFFFFu); sb = ia + 1 < n ? (int)(s >> 16) : 0;
             const int ra = ea / BW, rb = eb / BW;                        // score-plane position = tile offset + (SP - BW) * row + cell index
 #if FV_CELLTAB
-            pa = ea + (SP - BW) * ra + sCellOf[ea - ra * BW];
-            pb = eb + (SP - BW) * rb + sCellOf[eb - rb * BW];
+            const int ka = sCellOf[ea - ra * BW], kb = sCellOf[eb - rb * BW];
+            pa = ea + (SP - BW) * ra + ka;
+            pb = eb + (SP - BW) * rb + kb;
+            tha = sTh[ka]; thb = sTh[kb];
 #else
             const int ca = ea - ra * BW, cb = eb - rb * BW;
-            pa = ea + (SP - BW) * ra + (ca >= b1) + (ca >= b2) + (ca >= b3);
-            pb = eb + (SP - BW) * rb + (cb >= b1) + (cb >= b2) + (cb >= b3);
+            const int ka = (ca >= b1) + (ca >= b2) + (ca >= b3), kb = (cb >= b1) + (cb >= b2) + (cb >= b3);
+            pa = ea + (SP - BW) * ra + ka;
+            pb = eb + (SP - BW) * rb + kb;
+            tha = sTh[ka]; thb = sTh[kb];                                 // a cell's own threshold decides (they differ in the region-adapted variant)
 #endif
-            if (sa > th) sorg[pa] = (uint8_t)(sa - 1);
-            if (sb > th) sorg[pb] = (uint8_t)(sb - 1);
+            if (sa > tha) sorg[pa] = (uint8_t)(sa - 1);
+            if (sb > thb) sorg[pb] = (uint8_t)(sb - 1);
         }
         __syncthreads();
-        const int na = sa > th, nb = sb > th;
+        const int na = sa > tha, nb = sb > thb;
 #if FV_CORNER_COOP
         // ballot-aggregated compaction: one shared-memory atomic per warp and round
         const uint32_t ma = __ballot_sync(0xffffffffu, na), mb = __ballot_sync(0xffffffffu, nb);
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
     __shared__ __align__(8) uint64_t bar;
     __shared__ int sCount, sCorner, sDense;
     __shared__ int sHas[FS_WARPS];                                          // cell has a kept corner (cells the strip does not have: 1)
+    __shared__ int sTh[FS_WARPS];                                           // threshold of each cell in the current pass
     __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
     __shared__ __align__(8) uint32_t sMask[BW / 4 + 2];                     // per tile word: 0x80 in the bytes inside the scored interior
     __shared__ uint8_t sCellOf[BW], sCellOfG[SP];                           // cell index of a tile column / of a score-plane column
@@ -292,7 +299,12 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
     uint16_t* list = reinterpret_cast<uint16_t*>(smem + P.listOff);         // pretest survivors (tile offsets), then corners (score-plane positions)
 
     if (tid == 0) { mbar_init(&bar, 1); sCount = 0; sCorner = 0; sDense = 0; }
-    if (tid < FS_WARPS) sHas[tid] = tid < sd.nCells ? 0 : 1;
+    if (tid < FS_WARPS) {
+        sHas[tid] = tid < sd.nCells ? 0 : 1;
+        int t = P.iniTh;
+        if (P.regionTh && tid < sd.nCells) t = P.regionTh[P.cellRegion[sd.firstCell + tid]];
+        sTh[tid] = tid < sd.nCells ? t : 255;
+    }
     if (tid <= FS_WARPS) sC0[tid] = tid < sd.nCells ? S.ax + P.cells[sd.firstCell + tid].x0 - sd.x0 : S.ax + S.W + (tid > sd.nCells ? 4096 : 0);
     __syncthreads();
     if (tid == 0) {
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
 
     const uint8_t* org = tile + 3 * BW;
     uint8_t* sorg = score + SP;
-    int th = P.iniTh;
+    int th = min(min(sTh[0], sTh[1]), min(sTh[2], sTh[3]));                 // pretest at the lowest cell threshold of the strip
     bool second = false;
     while (true) {
         pretest(tile, list, &sCount, S, th, second, sMask, sCellOf, sC0, sHas, tid);
@@ -336,12 +348,18 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
             if (tid == 0) sDense = 1;
             break;
         }
-        strengths(org, sorg, list, n, &sCorner, th, sCellOf, sC0, tid);
+        strengths(org, sorg, list, n, &sCorner, sTh, sCellOf, sC0, tid);
         nms(sorg, list, sCorner, bits, sHas, sCellOfG, sC0, tid);
         __syncthreads();
-        if (second || P.minTh >= th || (sHas[0] & sHas[1] & sHas[2] & sHas[3])) break;
+        if (second || (sHas[0] & sHas[1] & sHas[2] & sHas[3])) break;
+        {   // cells left empty at a threshold above minTh get the second pass
+            bool any = false;
+            for (int k = 0; k < FS_WARPS; ++k) any |= !sHas[k] && sTh[k] > P.minTh;
+            if (!any) break;
+        }
         __syncthreads();
         if (tid == 0) { sCount = 0; sCorner = 0; }
+        if (tid < FS_WARPS) { if (sTh[tid] <= P.minTh) sHas[tid] |= 2; sTh[tid] = P.minTh; }     // bit 1: already ran at (or below) minTh, nothing to redo
         th = P.minTh; second = true;       // cells without a kept corner at iniTh: the same pass at minTh, restricted to them
         __syncthreads();
     }
@@ -355,8 +373,10 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
             // overflow in the first pass: nothing is scored yet, every cell goes through iniTh and, if still empty, minTh; overflow in
             // the second pass: only the cells the first pass left empty are redone, at minTh.  Responses do not depend on the
             // threshold, so a dense pass over a cell that already holds some only adds to them.
-            if (!second) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, P.iniTh, lane);
-            if (!sHas[warp] && P.minTh < P.iniTh) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, P.minTh, lane);
+            int cellTh0 = P.iniTh;
+            if (P.regionTh) cellTh0 = P.regionTh[P.cellRegion[cellIdx]];
+            if (!second) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, cellTh0, lane);
+            if (!sHas[warp] && P.minTh < cellTh0) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, P.minTh, lane);
         }
         uint32_t* out = P.cellCand + (long long)slot * P.cellSlotTotal + cd.slotOff;
         const int outX0 = cd.x0 + cd.relx, outY0 = cd.y0 + cd.rely;
@@ -401,7 +421,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
 
 }  // namespace
 
-int orbf_launch_fast(orbf_context* c, int slot0, int n)
+int orbf_launch_fast(orbf_context* c, int slot0, int n, bool adapted)
 {
     {
         const int r = orbf_refresh_maps(c);
@@ -425,6 +445,7 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n)
     P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
     P.cellSlotTotal = c->cellSlotTotal; P.nCellsTotal = c->nCellsTotal; P.iniTh = c->cfg.ini_th_fast; P.minTh = c->cfg.min_th_fast;
     P.slot0 = slot0; P.z0 = c->cur_slot0;
+    P.cellRegion = adapted ? c->d_cellRegion : nullptr; P.regionTh = adapted ? c->d_regionTh : nullptr;
     if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
     {   // static + dynamic shared memory can exceed the 48 KB default while the dynamic part alone does not: always opt in
         cudaError_t e = cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -15,13 +15,14 @@
 //     irrelevant as long as both operands use the same one.
 //   * The train tile is expanded and multiplied in two halves of 128 rows: one thread issues the 8 K-steps of a half
 //     (UTCIMMA 128 x 128 x 32) and commits to that half's mbarrier, so the first half is in the tensor core while the second is
-//     still being expanded and the warps of column half 0 start before half 1 is done.  Every thread then reads its own row
-//     with tcgen05.ld (32x32b.x32) and works on two columns per register (VIMNMX.U16x2):
-//       value v = accumulator + 64 * 256 + rc = 128 * (256 - hamming) + rc, rc = 32 - lane in the low 7 bits;
-//       rows:    per 128 columns a packed running top-2 of (v with rc replaced by 64 - pair index), decoded into
-//                (distance << 16 | trainIdx) keys once per 128 columns;
-//       columns (cross-check, quirk Q10): a 31-shuffle halving butterfly leaves lane L with the best (256 - hamming, row) of the
-//                warp's 32 rows for column pair L; the 4 lane quarters are folded through shared memory once per chunk.
+//     still being expanded and the warps of column half 0 start before half 1 is done.  A 9th K step carries constants that
+//     make the accumulator itself the comparable value: acc = 128 * (256 - hamming) + code, code = 64 - column-pair index.
+//     Every thread then reads its own row with tcgen05.ld 32x32b.x32.pack::16b — two adjacent columns per register, 64 columns
+//     per load — and works on two columns per instruction (VIMNMX.U16x2), 3 instructions per register and nothing else:
+//       rows:    per 128 columns a packed running top-2, decoded into (distance << 16 | trainIdx) keys once per 128 columns;
+//       columns (cross-check, quirk Q10): the low 7 bits take the row code rc = 32 - lane instead; a 31-shuffle halving butterfly
+//                leaves lane L with the best (256 - hamming, row) of the warp's 32 rows for column pair L; the 4 lane quarters are
+//                folded through shared memory once per chunk.
 // History: a POPC/LOP3 kernel (integer-ALU bound, 0.81 ms per 511 pairs), then mma.sync IMMA s8 (0.43 ms; warp-level MMAs block
 // the issue port ~6 of every 8.3 clk, tools/bmma_probe.cu), now tcgen05 (tools/umma_probe.cu pins the descriptor fields).
 #include "orbf_internal.h"
@@ -29,12 +30,14 @@
 namespace {
 
 constexpr int UM_THREADS = 256, UM_ROWS = 128, UM_CHUNK = 256;
-constexpr uint32_t UM_LBO = 128, UM_SBO = 16 * 128;             // bytes: next 16-byte K chunk / next 8-row group
-constexpr size_t UM_SMEM_A = (size_t)UM_ROWS * 256, UM_SMEM_B = (size_t)UM_CHUNK * 256, UM_SMEM_COL = 4 * (UM_CHUNK / 2) * sizeof(uint32_t);
+// K = 256 descriptor dimensions + one extra K step of 32 whose only non-zero bytes carry the bias and the column code (below):
+// 18 K chunks of 16 bytes per row
+constexpr int UM_KCHUNKS = 18, UM_KSTEPS = 9;
+constexpr uint32_t UM_LBO = 128, UM_SBO = UM_KCHUNKS * 128;     // bytes: next 16-byte K chunk / next 8-row group
+constexpr size_t UM_SMEM_A = (size_t)UM_ROWS * UM_KCHUNKS * 16, UM_SMEM_B = (size_t)UM_CHUNK * UM_KCHUNKS * 16, UM_SMEM_COL = 4 * (UM_CHUNK / 2) * sizeof(uint32_t);
 constexpr size_t UM_SMEM = UM_SMEM_A + UM_SMEM_B + UM_SMEM_COL + 1024;   // + slack to align the operand tiles
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr int V_SHIFT = 7;
-constexpr uint32_t V_BIAS = 64 * 256;
 static_assert(UM_THREADS == UM_CHUNK && UM_THREADS == 2 * UM_ROWS, "operand expansion maps one train row / half a query row to a thread");
 constexpr int OPERAND_MAG = 8;                                  // both operands are +-8: a product of two equal bits is +64
 
@@ -77,15 +80,27 @@ __device__ __forceinline__ void expand_half(uint8_t* tile, int row, int half, ui
     }
 }
 
+// The 9th K step: query rows carry (1, 127, 127, 1), train row `col` carries (code, 127, 2, 1) with code = 64 - (col % 128) / 2, so the
+// tensor core itself adds 127 * 127 + 127 * 2 + 1 = 64 * 256 (the bias that makes every accumulator positive) and the column-pair code
+// that the packed top-2 carries in its low 7 bits: the epilogue neither adds nor masks anything.  Rows / columns past the end stay
+// zero and produce accumulator 0, which loses against every real entry (>= 1).
+__device__ __forceinline__ void bias_chunks(uint8_t* tile, int row, uint32_t word0)
+{
+    uint8_t* dst = tile + (row >> 3) * UM_SBO + 16 * UM_LBO + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(word0, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(dst + UM_LBO) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr)
 {
     // start address, leading / stride byte offsets (all >> 4), descriptor version 1 (sm_100), layout type 0 = no swizzle
     return (uint64_t)((addr >> 4) & 0x3FFFu) | (uint64_t)(UM_LBO >> 4) << 16 | (uint64_t)(UM_SBO >> 4) << 32 | (uint64_t)1 << 46;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+// 64 accumulator columns as 32 registers: low 16 bits of column 2j | low 16 bits of column 2j + 1 << 16 (tools/tmem_pack_probe.cu)
+__device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[32])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
                    "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
                    "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
@@ -173,11 +188,15 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         const int r = tid & (UM_ROWS - 1), half = tid >> 7;
         const bool valid = qBase + r < nq;
         expand_half(sA, r, half, valid ? __ldg(reinterpret_cast<const uint4*>(Q + (long long)(qBase + r) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
+        if (half == 0) bias_chunks(sA, r, valid ? (1u | (127u << 8) | (127u << 16) | (1u << 24)) : 0u);
+        // the train tile's 9th K step depends on the column only: written once for full chunks (a short last chunk rewrites it)
+        bias_chunks(sB, tid, (64u - (uint32_t)((tid & 127) >> 1)) | (127u << 8) | (2u << 16) | (1u << 24));
     }
     // this thread's query row = TMEM lane 32 * quarter + lane; two threads (colHalf 0 / 1) share a row
     const int row = qBase + quarter * 32 + lane;
     const bool rowValid = row < nq;
-    const uint32_t vadd = rowValid ? (V_BIAS + 32u - (uint32_t)lane) * 0x10001u : 0u;   // both halves: + 64 * 256 + rc
+    // cross-check: the row code replaces the column code (one LOP3 per register; rows past nq become 0 and never win)
+    const uint32_t rowCode = rowValid ? (32u - (uint32_t)lane) * 0x10001u : 0u, rowMask = rowValid ? 0xFF80FF80u : 0u;
     uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
     // instruction descriptor: D s32 (2 @ bit 4), A / B signed 8-bit (1 @ 7, 1 @ 10), both K-major, N >> 3 @ 17, M >> 4 @ 24
     const uint32_t idescHalf = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((UM_CHUNK / 2) >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
@@ -195,6 +214,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
                 const int col = part * (UM_CHUNK / 2) + (tid & (UM_CHUNK / 2 - 1)), half = tid >> 7;
                 const bool valid = col < cn;
                 expand_half(sB, col, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + col) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
+                if (half == 1 && cn < UM_CHUNK) bias_chunks(sB, col, valid ? ((64u - (uint32_t)((col & 127) >> 1)) | (127u << 8) | (2u << 16) | (1u << 24)) : 0u);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> the tensor core's async proxy
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // orders the previous chunk's tcgen05.ld before the MMAs
@@ -203,7 +223,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
             tmem = sTmem;
             if (tid == 0) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < UM_KSTEPS; ++ks) {
                     const uint64_t da = umma_desc(smem_u32(sA) + ks * 2 * UM_LBO);
                     const uint64_t db = umma_desc(smem_u32(sB) + part * (UM_CHUNK / 2 / 8) * UM_SBO + ks * 2 * UM_LBO);
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -225,36 +245,24 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // this warp's 32 rows x 128 columns = 64 column pairs: two batches of 32 pairs
+        // this warp's 32 rows x 128 columns = 64 column pairs: two batches of 32 pairs, each one packed TMEM load.  A register holds
+        // 128 * (256 - hamming) + code for two adjacent columns (bias and code come out of the 9th K step), ready for the packed top-2
         const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + colHalf * 128;
         uint32_t b1 = 0u, b2 = 0u;                             // packed running top-2 of the even / odd column streams
 #pragma unroll
         for (int bt = 0; bt < 2; ++bt) {
             const int colBase = colHalf * 128 + bt * 64;
-            uint32_t P[32];                                    // raw pair = acc(2j) + (acc(2j + 1) << 16): multiples of 128 in both halves
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t v[32];
-                tmem_ld32(tbase + bt * 64 + hf * 32, v);
-                if (colBase + hf * 32 + 32 > cn) {
-                    // columns past nt (zero operand rows) must lose against every real column: hamming 256
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (colBase + hf * 32 + j >= cn) v[j] = 0u - V_BIAS;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) P[hf * 16 + j] = v[2 * j] + (v[2 * j + 1] << 16);
-            }
+            uint32_t P[32];
+            tmem_ld64_packed(tbase + bt * 64, P);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                // + 64 * 256 leaves 128 * (256 - hamming) with clear low 7 bits, which take the code 64 - pair index
-                const uint32_t e = P[j] + ((V_BIAS + 64u - (uint32_t)(bt * 32 + j)) * 0x10001u);
-                b2 = __vmaxu2(b2, __vminu2(b1, e));
-                b1 = __vmaxu2(b1, e);
+                b2 = __vmaxu2(b2, __vminu2(b1, P[j]));
+                b1 = __vmaxu2(b1, P[j]);
             }
             if (CROSS) {
+                // columns: the low 7 bits take the row code instead (0 for rows past nq, which then never win: see fold_columns)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) P[j] += vadd;
+                for (int j = 0; j < 32; ++j) P[j] = (P[j] & rowMask) | rowCode;
                 bfly_max<16>(P, lane); bfly_max<8>(P, lane); bfly_max<4>(P, lane); bfly_max<2>(P, lane); bfly_max<1>(P, lane);
                 sCol[quarter * (UM_CHUNK / 2) + (colBase >> 1) + lane] = P[0];
             }

@@ -326,6 +326,17 @@ void orbf_default_adaptive_config(orbf_adaptive_config* cfg);
 int orbf_adaptive_detect(orbf_context* ctx, const orbf_adaptive_config* cfg, const uint8_t* gray, int32_t n, int32_t stride,
     int64_t frame_stride, double* thresh, orbf_keypoint* out, int32_t* counts, int32_t cap, int32_t* cell_thresh, int32_t* cell_found);
 
+/* BASELINE config 4, 8-level variant (a north-star extension — the reference's adaptive routes are single-scale):
+ * ORB extraction of n host frames, in order, into frame slots [slot0, slot0 + n), with iniThFAST of every FAST cell replaced by the
+ * state of its image region's controller: threshold = max(minThFAST, min(254, (int)state[region])), and after each frame
+ * found[region] < cfg->min_features => state *= dec, > cfg->max_features => state *= inc (clamped to [min_th, max_th]); regions =
+ * cfg->grid x cfg->grid partition of the image.  thresh [grid * grid] in / out (<= 0 => init_th) continues the video across calls;
+ * region_th / region_found (optional, [n][grid * grid]): thresholds each frame was detected with, keypoints it returned per region.
+ * Results are read like those of orbf_extract_batch (orbf_download_frame, matching, ...).                                        */
+int orbf_extract_adapted(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
+    const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, const orbf_adaptive_config* cfg, double* thresh,
+    int32_t* region_th, int32_t* region_found);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,6 +285,23 @@ def adaptive_detect(img, thresh, retain_best=0, cfg=None):
     return out[:n.value].copy(), found, used
 
 
+def extract_adapted(img, thresh, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, cfg=None):
+    """BASELINE config 4, 8-level variant: ORB extraction with per-region adapted iniThFAST; `thresh` [grid*grid] float64 is updated in
+    place.  cfg.min_features / max_features = per-region band.  Returns (kps, desc, region_th, region_found)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    ecfg = ExtractCfg(w, h, nfeatures, nlevels, scale_factor, ini_th, min_th)
+    cfg = cfg or adaptive_default()
+    g2 = cfg.grid * cfg.grid
+    assert thresh.dtype == np.float64 and len(thresh) == g2
+    cap = 2 * nfeatures + 64 * nlevels
+    kps = np.zeros(cap, KEYPOINT_DT); desc = np.zeros((cap, 32), np.uint8); n = C.c_int(0)
+    used = np.zeros(g2, np.int32); found = np.zeros(g2, np.int32)
+    _chk(lib().orc_extract_adapted(C.byref(ecfg), C.byref(cfg), _p(img), w, _p(thresh), _p(kps), _p(desc), cap, C.byref(n), _p(used), _p(found)),
+         "extract_adapted")
+    return kps[:n.value].copy(), desc[:n.value].copy(), used, found
+
+
 def projection_match(kp_x, kp_y, kp_octave, desc, lm_desc, proj_x, proj_y, lm_flags, feat_taken=None, radius=8.0, nn_ratio=0.8, th_high=100.0):
     """Matcher::ProjectionMatch (Features/matcher.cpp:90-143): (best feature per landmark or -1, number of matches)."""
     kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32)

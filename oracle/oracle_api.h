@@ -69,6 +69,12 @@ int orc_adaptive_default(orc_adaptive_cfg* cfg);
 int orc_adaptive_detect(const orc_adaptive_cfg* cfg, const uint8_t* img, int w, int h, int stride, double* thresh, int retain_best,
     orc_keypoint* out, int cap, int* n_out, int* cell_found, int* cell_thresh);
 
+/* BASELINE config 4, 8-level variant: ORB extraction with iniThFAST adapted per grid region by DetectorAdjuster-style controllers that
+ * carry their state from frame to frame (defined in orb_oracle.cpp).  min_features / max_features of acfg are
+ * the per-region band, grid the partition; thresh [grid * grid] in / out. */
+int orc_extract_adapted(const orc_extract_cfg* cfg, const orc_adaptive_cfg* acfg, const uint8_t* img, int stride, double* thresh, orc_keypoint* kps,
+    uint8_t* desc, int cap, int* n_out, int* region_th, int* region_found);
+
 /* Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks */
 int orc_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_landmarks, int* best, int* best_median);
 /* Matcher::Fuse, search part (Features/matcher.cpp:212-296) and Matcher::BoWMatch (Features/matcher.cpp:145-209) */

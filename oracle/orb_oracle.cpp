@@ -27,6 +27,7 @@
 #include <cstring>
 #include <list>
 #include <utility>
+#include <functional>
 #include <vector>
 
 #include "oracle_api.h"
@@ -222,8 +223,9 @@ void fast_roi(const uint8_t* roi, int stride, int roiW, int roiH, int th, std::v
 
 // a-2: per-cell FAST with ini/min threshold fallback (orbextractor.cpp:665-723).  Output
 // coordinates are relative to minBorder (16); order = cell row-major, row-major inside a cell.
+// cellTh (optional): iniTh of the cell whose first scored pixel is (x, y) — the region-adapted variant (orc_extract_adapted)
 void fast_cells(const uint8_t* img, int w, int h, int stride, int iniTh, int minTh, std::vector<orc_cand>& cands,
-    std::vector<int>* cellFallback)
+    std::vector<int>* cellFallback, const std::function<int(int, int)>* cellTh = nullptr)
 {
     cands.clear();
     const int minBorderX = kEdgeThreshold - 3, minBorderY = minBorderX;
@@ -248,7 +250,7 @@ void fast_cells(const uint8_t* img, int w, int h, int stride, int iniTh, int min
             if (maxX > maxBorderX) maxX = (float)maxBorderX;
             const int x0 = (int)iniX, y0 = (int)iniY, rw = (int)maxX - x0, rh = (int)maxY - y0;
             const uint8_t* roi = img + (size_t)y0 * stride + x0;
-            fast_roi(roi, stride, rw, rh, iniTh, scoreBuf, cell);
+            fast_roi(roi, stride, rw, rh, cellTh ? (*cellTh)(x0 + 3, y0 + 3) : iniTh, scoreBuf, cell);
             int fb = 0;
             if (cell.empty()) { fast_roi(roi, stride, rw, rh, minTh, scoreBuf, cell); fb = 1; }
             if (cellFallback) (*cellFallback)[(size_t)i * nCols + j] = cell.empty() ? (fb ? 2 : 0) : fb;
@@ -624,9 +626,55 @@ int orc_rbrief(const uint8_t* blurred, int w, int h, int stride, const int* xs, 
 
 const int8_t* orc_pattern(void) { return kPattern; }
 
+static int extract_impl(const orc_extract_cfg* cfg, const uint8_t* img, int stride, orc_keypoint* kps, uint8_t* desc, int cap,
+    int* n_out, orc_extract_debug* dbg, int grid, const int* regionTh);
+
 // a-8: ORBextractor::operator() (orbextractor.cpp:756-815).  Optional per-stage dumps in `dbg`.
 int orc_extract(const orc_extract_cfg* cfg, const uint8_t* img, int stride, orc_keypoint* kps, uint8_t* desc, int cap,
     int* n_out, orc_extract_debug* dbg)
+{
+    return extract_impl(cfg, img, stride, kps, desc, cap, n_out, dbg, 0, nullptr);
+}
+
+// BASELINE config 4, 8-level variant (SURVEY.md quirk Q14 — a north-star extension, DEFINED here; the reference's adaptive routes are
+// single-scale): the ORB-SLAM2 extractor with iniThFAST replaced, per region of a grid x grid partition of the image, by the state of a
+// DetectorAdjuster-style controller (detectoradjuster.cpp:22-59) that is fed the number of keypoints the extractor returned in that
+// region and carries its threshold from frame to frame like the stateful detectors (videodynamicadaptedfeaturedetector.cpp:24-44):
+//   * threshold of a FAST cell = max(minThFAST, min(254, (int)state[region])) — int truncation as detectoradjuster.cpp:27 — where the
+//     cell's region is that of its first scored pixel (x, y) of level l mapped to the image: ((int)((float)y * scale[l]) * grid / height,
+//     (int)((float)x * scale[l]) * grid / width), clamped to grid - 1;  the minThFAST fallback of empty cells is unchanged;
+//   * after the frame: found[region] = keypoints returned there (region of ((int)kp.y * grid / height, (int)kp.x * grid / width));
+//     found < min_features => state *= dec (tooFew), found > max_features => state *= inc (tooMany), clamped to [min_th, max_th]:
+//     one controller step per frame.
+// thresh [grid * grid] in / out (<= 0: init_th); region_th / region_found (optional): thresholds used for this frame, keypoints found.
+int orc_extract_adapted(const orc_extract_cfg* cfg, const orc_adaptive_cfg* acfg, const uint8_t* img, int stride, double* thresh, orc_keypoint* kps,
+    uint8_t* desc, int cap, int* n_out, int* region_th, int* region_found)
+{
+    if (!cfg || !acfg || !thresh || acfg->grid < 1 || acfg->grid > 5) return ORC_ERR_ARG;
+    const int g = acfg->grid;
+    std::vector<int> th(g * g);
+    for (int r = 0; r < g * g; ++r) {
+        if (!(thresh[r] > 0)) thresh[r] = acfg->init_th;
+        th[r] = std::max(cfg->min_th_fast, std::min(254, (int)thresh[r]));
+        if (region_th) region_th[r] = th[r];
+    }
+    const int rc = extract_impl(cfg, img, stride, kps, desc, cap, n_out, nullptr, g, th.data());
+    if (rc != ORC_OK) return rc;
+    std::vector<int> found(g * g, 0);
+    for (int i = 0; i < *n_out; ++i) {
+        const int ry = std::min(g - 1, (int)kps[i].y * g / cfg->height), rx = std::min(g - 1, (int)kps[i].x * g / cfg->width);
+        found[ry * g + rx]++;
+    }
+    for (int r = 0; r < g * g; ++r) {
+        if (region_found) region_found[r] = found[r];
+        if (found[r] < acfg->min_features) { thresh[r] *= acfg->dec; if (thresh[r] < acfg->min_th) thresh[r] = acfg->min_th; }
+        else if (found[r] > acfg->max_features) { thresh[r] *= acfg->inc; if (thresh[r] > acfg->max_th) thresh[r] = acfg->max_th; }
+    }
+    return ORC_OK;
+}
+
+static int extract_impl(const orc_extract_cfg* cfg, const uint8_t* img, int stride, orc_keypoint* kps, uint8_t* desc, int cap,
+    int* n_out, orc_extract_debug* dbg, int grid, const int* regionTh)
 {
     if (!cfg || !n_out) return ORC_ERR_ARG;
     *n_out = 0;
@@ -650,7 +698,12 @@ int orc_extract(const orc_extract_cfg* cfg, const uint8_t* img, int stride, orc_
     for (int l = 0; l < nl; ++l) {
         const uint8_t* L = pyr.data() + off[l];
         std::vector<orc_cand> cands;
-        fast_cells(L, lw[l], lh[l], lw[l], cfg->ini_th_fast, cfg->min_th_fast, cands, nullptr);
+        const float sc = t.scale[l];
+        const std::function<int(int, int)> cellTh = [&](int x, int y) {
+            const int ry = std::min(grid - 1, (int)((float)y * sc) * grid / h), rx = std::min(grid - 1, (int)((float)x * sc) * grid / w);
+            return regionTh[ry * grid + rx];
+        };
+        fast_cells(L, lw[l], lh[l], lw[l], cfg->ini_th_fast, cfg->min_th_fast, cands, nullptr, regionTh ? &cellTh : nullptr);
         if (dbg && dbg->cands) {
             if (candTotal + (int)cands.size() > dbg->cand_cap) return ORC_ERR_CAPACITY;
             std::copy(cands.begin(), cands.end(), dbg->cands + candTotal);

@@ -10,7 +10,8 @@ OUT=build/variants; mkdir -p $OUT/obj
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off"
 for f in context pyramid fast quadtree describe match ransac kfdb comm adaptive projection c_abi; do
   [ "$f.cu" = "$SRC" ] && continue
-  if [ ! -f $OUT/obj/$f.o ] || [ $CS/$f.cu -nt $OUT/obj/$f.o ]; then nvcc $FLAGS -c $CS/$f.cu -o $OUT/obj/$f.o & fi
+  newest=$(ls -t $CS/*.h $CS/*.inc include/orbfront.h $CS/$f.cu | head -1)
+  if [ ! -f $OUT/obj/$f.o ] || [ $newest -nt $OUT/obj/$f.o ]; then nvcc $FLAGS -c $CS/$f.cu -o $OUT/obj/$f.o & fi
 done
 wait
 OBJS=""
