@@ -52,7 +52,7 @@ struct FastParams {
     const StripDesc* strips; const CellDesc* cells;
     uint32_t* cellCand; int* cellCount;
     int cellSlotTotal, nCellsTotal, iniTh, minTh, slot0, z0;   // z coordinate of a slot: slot - z0 on level 0, slot elsewhere
-    int scoreOff, listOff, bitsOff;                             // byte offsets of the shared-memory regions
+    int scoreOff, listOff, bitsOff, sbmOff, sbmWords;           // byte offsets of the shared-memory regions; words of the survivor bitmap
     // region-adapted variant (orbf_extract_adapted): iniTh of a cell = regionTh[cellRegion[cell]]; NULL => iniTh everywhere
     const uint8_t* cellRegion; const int* regionTh;
     short BH[ORBF_MAX_LEVELS];
@@ -74,26 +74,20 @@ __device__ __forceinline__ int cell_of(const uint8_t* sCellOf, const int* sC0, i
 #endif
 }
 
-__device__ __forceinline__ void pretest(const uint8_t* tile, uint16_t* list, int* sCount, const Strip& S, int th, bool onlyEmpty, const uint32_t* sMask,
+__device__ __forceinline__ void pretest(const uint8_t* tile, uint8_t* sbm, const Strip& S, int th, bool onlyEmpty, const uint32_t* sMask,
     const uint8_t* sCellOf, const int* sC0, const int* sHas, int tid)
 {
-    const int lane = tid & 31;
     const int wFirst = S.ax >> 3, wpr = ((S.ax + S.W + 7) >> 3) - wFirst, nTasks = S.h * wpr;
     const uint32_t rcp = ((1u << 20) + wpr - 1) / wpr;
-    // per byte x = |r - v|: bit 7 of ((x & 0x7f) + K) | x (th < 128, K = 127 - th) or of ((x & 0x7f) + K) & x (th >= 128,
-    // K = 255 - th) is set iff x > th
-    const bool hiTh = th >= 128;
-    const uint32_t K = (uint32_t)(hiTh ? 255 - th : 127 - th) * 0x01010101u, M7 = 0x7F7F7F7Fu;
-#if FV_APPEND_COOP
-    const int nRounds = (nTasks + FS_THREADS - 1) / FS_THREADS;
-    for (int rd = 0; rd < nRounds; ++rd) {          // every thread runs every round: the append below is warp-cooperative
-        const int t = rd * FS_THREADS + tid;
-#else
+    // per byte x = |r - v| (th < 128, K = 127 - th in every byte): bit 7 of (x + K) | x is set if x > th.  The add runs over the whole
+    // word: a byte with x >= 129 + th carries into its left neighbour, which can only turn a neighbour with x == th into a false
+    // positive (the exact strength decides later), never drop a corner: x + K overflows the byte only when x >= 129, and then bit 7 of
+    // x itself is set.  th >= 128 never reaches this function (the kernel takes the dense path).
+    const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;
     for (int t = tid; t < nTasks; t += FS_THREADS) {
-#endif
-        uint32_t all[2] = { 0u, 0u };
-        int e = 0;
-        if (t < nTasks) {
+        uint32_t all[2];
+        int e;
+        {
             const int row = (int)(((uint32_t)t * rcp) >> 20), x8 = 8 * (wFirst + (t - row * wpr));
             e = row * BW + x8;
             const uint8_t* p = tile + e;                                                 // image row y - 3 of the task's 8 columns
@@ -123,10 +117,7 @@ __device__ __forceinline__ void pretest(const uint8_t* tile, uint16_t* list, int
                 ad[7] = __vabsdiffu4(__funnelshift_r(DL, D, 16), C);                                             // ring 14 (-2, +2)
                 uint32_t a = w ? m0.y : m0.x;
 #pragma unroll
-                for (int k = 0; k < 8; k += 2) {
-                    const uint32_t ta = (ad[k] & M7) + K, tb = (ad[k + 1] & M7) + K;
-                    a &= hiTh ? ((ta & ad[k]) | (tb & ad[k + 1])) : (ta | tb | ad[k] | ad[k + 1]);
-                }
+                for (int k = 0; k < 8; k += 2) a &= (ad[k] + K) | (ad[k + 1] + K) | ad[k] | ad[k + 1];
                 all[w] = a;
             }
             if (onlyEmpty && (all[0] | all[1])) {            // rare pass: drop survivors of cells that already have a kept corner
@@ -135,27 +126,40 @@ __device__ __forceinline__ void pretest(const uint8_t* tile, uint16_t* list, int
                     if (sHas[cell_of(sCellOf, sC0, x8 + b)]) all[b >> 2] &= ~(0x80u << (8 * (b & 3)));
             }
         }
-        const int cnt = __popc(all[0]) + __popc(all[1]);
-#if FV_APPEND_COOP
-        // warp-cooperative append: exclusive prefix of the survivor counts, one shared-memory atomic per warp
-        if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
+        // flag bytes -> one bit per pixel: byte (e >> 3) of the survivor bitmap, whose bit index is the tile offset
+        sbm[e >> 3] = (uint8_t)(((((all[0] >> 7) * 0x00204081u) >> 21) & 0xFu) | ((((all[1] >> 7) * 0x00204081u) >> 17) & 0xF0u));
+    }
+}
+
+// ---- 1b. survivor bitmap -> list of tile offsets in raster order.  Lanes of a warp then work on neighbouring pixels in the strength and
+// NMS steps: their byte gathers fall into distinct banks far more often than with an arbitrary order (the shared-memory data pipe is what
+// binds this kernel).  Every thread takes 64 consecutive bits; returns the survivor count (uniform).  Nothing is written when the count
+// exceeds LIST_CAP.
+__device__ __forceinline__ int compact_survivors(const uint32_t* sbm32, uint16_t* list, int nWords, int* sTot, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    int total = 0;
+    for (int w0 = 0; w0 < nWords; w0 += 2 * FS_THREADS) {
+        const int w = w0 + 2 * tid;
+        uint2 v = make_uint2(0u, 0u);
+        if (w < nWords) v = *reinterpret_cast<const uint2*>(sbm32 + w);          // the bitmap is padded to an even word count
+        const int cnt = __popc(v.x) + __popc(v.y);
         int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        int base = 0;
-        if (lane == 31) base = atomicAdd(sCount, incl);
-        int pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-#else
-        if (cnt == 0) continue;
-        int pos = atomicAdd(sCount, cnt);
-#endif
-        if (pos <= LIST_CAP - 8) {          // a task that would cross the end writes nothing: the count alone says "overflow"
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) sTot[warp] = incl;
+        __syncthreads();
+        int pos = total + incl - cnt;
 #pragma unroll
-            for (int b = 0; b < 8; ++b)
-                if (all[b >> 2] & (0x80u << (8 * (b & 3)))) list[pos++] = (uint16_t)(e + b);
+        for (int k = 0; k < FS_WARPS; ++k) { const int t = sTot[k]; if (k < warp) pos += t; total += t; }
+        __syncthreads();                    // sTot is rewritten by the next round
+        if (total <= LIST_CAP) {
+            const int e0 = 32 * w;
+            while (v.x) { const int b = __ffs((int)v.x) - 1; v.x &= v.x - 1; list[pos++] = (uint16_t)(e0 + b); }
+            while (v.y) { const int b = __ffs((int)v.y) - 1; v.y &= v.y - 1; list[pos++] = (uint16_t)(e0 + 32 + b); }
         }
     }
-    (void)lane;
+    return total;
 }
 
 // ---- 2. corner strength, two survivors per thread; the corners (44 % of the survivors) are compacted in place at the front of
@@ -279,7 +283,8 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int sCount, sCorner, sDense;
+    __shared__ int sCorner, sDense;
+    __shared__ int sTot[FS_WARPS];                                          // per-warp survivor counts of the ordered compaction
     __shared__ int sHas[FS_WARPS];                                          // cell has a kept corner (cells the strip does not have: 1)
     __shared__ int sTh[FS_WARPS];                                           // threshold of each cell in the current pass
     __shared__ int sC0[FS_WARPS + 1];                                       // first tile column of each cell, then the strip's end
@@ -297,8 +302,9 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
     uint8_t* score = smem + P.scoreOff;                                     // (h + 2) x SP responses, interior (0,0) of cell k at [1][ax + k]
     uint32_t* bits = reinterpret_cast<uint32_t*>(smem + P.bitsOff);         // [h][BITW] kept corners, score-plane columns
     uint16_t* list = reinterpret_cast<uint16_t*>(smem + P.listOff);         // pretest survivors (tile offsets), then corners (score-plane positions)
+    uint8_t* sbm = smem + P.sbmOff;                                         // survivor bitmap of the pretest: bit index = tile offset (h x BW bits)
 
-    if (tid == 0) { mbar_init(&bar, 1); sCount = 0; sCorner = 0; sDense = 0; }
+    if (tid == 0) { mbar_init(&bar, 1); sCorner = 0; sDense = 0; }
     if (tid < FS_WARPS) {
         sHas[tid] = tid < sd.nCells ? 0 : 1;
         int t = P.iniTh;
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
         (void)b1; (void)b2; (void)b3;
 #endif
     }
-    mbar_wait(&bar, 0);
+    if (warp == 0) mbar_wait(&bar, 0);                                      // one warp polls the mbarrier, the others sleep in the barrier
     __syncthreads();
 
     const uint8_t* org = tile + 3 * BW;
@@ -341,10 +347,14 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
     int th = min(min(sTh[0], sTh[1]), min(sTh[2], sTh[3]));                 // pretest at the lowest cell threshold of the strip
     bool second = false;
     while (true) {
-        pretest(tile, list, &sCount, S, th, second, sMask, sCellOf, sC0, sHas, tid);
+        int n = LIST_CAP + 1;                                               // the byte-parallel pretest is written for th < 128
+        if (th < 128) {
+            pretest(tile, sbm, S, th, second, sMask, sCellOf, sC0, sHas, tid);
+            __syncthreads();
+            n = compact_survivors(reinterpret_cast<const uint32_t*>(sbm), list, min(P.sbmWords, (S.h * BW + 31) >> 5), sTot, tid);
+        }
         __syncthreads();
-        const int n = sCount;
-        if (n > LIST_CAP - 8) {            // dense path below; nothing was scored in this pass
+        if (n > LIST_CAP) {                // dense path below; nothing was scored in this pass
             if (tid == 0) sDense = 1;
             break;
         }
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
             if (!any) break;
         }
         __syncthreads();
-        if (tid == 0) { sCount = 0; sCorner = 0; }
+        if (tid == 0) sCorner = 0;
         if (tid < FS_WARPS) { if (sTh[tid] <= P.minTh) sHas[tid] |= 2; sTh[tid] = P.minTh; }     // bit 1: already ran at (or below) minTh, nothing to redo
         th = P.minTh; second = true;       // cells without a kept corner at iniTh: the same pass at minTh, restricted to them
         __syncthreads();
@@ -435,12 +445,14 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n, bool adapted)
         maxBH = std::max(maxBH, c->fastBH[l]);
     }
     if (c->maxCellW > 64) return ORBF_ERR_GEOMETRY;                 // a cell's row of the kept-corner bitmap is read as one 64-bit field
-    // regions: [tile BH x BW] [score (h + 2) x SP | bitmap h x BITW words (+ 2 words the output pass may read past the last row)] [list]
-    // 17.4 KB at 640x480
+    // regions: [tile BH x BW] [score (h + 2) x SP | bitmap h x BITW words (+ 2 words the output pass may read past the last row) | survivor
+    // bitmap h x BW bits] [list]; 18.2 KB at 640x480
     const int maxH = maxBH - 6;
     P.scoreOff = align_up(BW * maxBH, 128);
     P.bitsOff = P.scoreOff + align_up(SP * (maxH + 2), 16);
-    P.listOff = P.bitsOff + align_up(4 * (BITW * maxH + 2), 16);
+    P.sbmOff = P.bitsOff + align_up(4 * (BITW * maxH + 2), 16);
+    P.sbmWords = align_up((maxH * BW + 31) / 32, 2);
+    P.listOff = P.sbmOff + align_up(4 * P.sbmWords, 16);
     const size_t smem = (size_t)P.listOff + LIST_CAP * sizeof(uint16_t);
     P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
     P.cellSlotTotal = c->cellSlotTotal; P.nCellsTotal = c->nCellsTotal; P.iniTh = c->cfg.ini_th_fast; P.minTh = c->cfg.min_th_fast;
