@@ -341,6 +341,194 @@ def run_config5(args):
         raise SystemExit("bench.py --config 5: device results disagree with the oracle: " + "; ".join(bad[:6]))
 
 
+def run_config4(args):
+    """--config 4 (BASELINE configs[3]): 1280x720 frames, 2000 keypoints, 8 levels, detector thresholds adapted per 3x3 image region by
+    stateful controllers.  One GPU per rank, every rank its own clip (weak scaling, no collective).  Lines of the object:
+      value / extract_adapted : the 8-level ORB extractor with iniThFAST driven by the controller state (orbf_extract_adapted, host frames in,
+                                controller step chained per frame on the device) — frames/s, wall clock around the call + synchronize;
+      extract_fixed_device    : the same extractor with the global thresholds on frames resident in HBM (CUDA events);
+      chain_device            : extract + kNN-2 (ratio 0.8, cross-check) + RANSAC over consecutive pairs at 2000 keypoints (CUDA events);
+      adaptive_detect         : the reference's own config-4 code path — single-scale FAST with the grid / dynamic adjusters
+                                (videogridadaptedfeaturedetector.cpp:52-84), host frames in, host keypoints out.
+    Parity inside the run: the first frames of the adapted clip against the oracle (keypoints, descriptors, thresholds used)."""
+    import torch
+    import torch.distributed as dist
+    import synth
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local)); dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    ob = load_pkg()
+    w, h, nf = 1280, 720, 2000
+    F = min(args.frames, 128)
+    tex = synth.make_texture(rank, h, w)
+    base = [synth.make_frame(tex, i, w, h, rank) for i in range(16)]
+    frames = np.stack([base[i % 30 if i % 30 < 16 else 30 - i % 30] for i in range(F)])             # ping-pong: consecutive motions
+    depths = np.stack([synth.make_depth(i % 16, w, h, rank) for i in range(F)])
+    band = dict(min_features=round(0.6 * nf / 9), max_features=round(1.02 * nf / 9))
+    ctx = ob.Context(width=w, height=h, nfeatures=nf, max_frames=F, max_pairs=F, device=local)
+    stream = torch.cuda.Stream(device=local); ctx.set_stream(stream.cuda_stream)
+    steps = max(1, min(args.steps, 20))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def wall(fn):
+        for _ in range(max(1, min(args.warmup, 3))):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / steps
+
+    def events(fn):
+        for _ in range(max(1, min(args.warmup, 3))):
+            fn()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    hfr = torch.from_numpy(frames).pin_memory().numpy()
+    th = np.zeros(9)
+
+    def adapted():
+        ctx.extract_adapted(hfr, th, **band); ctx.synchronize()
+    adapted_ms = wall(adapted)
+    l0 = ctx.launch_count(); adapted(); adapted_launches = ctx.launch_count() - l0
+    kp_adapted = float(ctx.frame_counts(F).mean())
+    d_gray = torch.from_numpy(frames).cuda(local); d_depth = torch.from_numpy(depths.view(np.int16)).cuda(local)
+    fixed_ms = events(lambda: ctx.extract_batch_device(d_gray.data_ptr(), w, w * h, F))
+    kp_fixed = float(ctx.frame_counts(F).mean())
+    chain_ms = events(lambda: ctx.track_sequence_device(d_gray.data_ptr(), w, w * h, F, d_depth.data_ptr(), w, w * h, RATIO, CROSS, seed=42))
+    summ = ctx.download_ransac_summary(F - 1); mc = ctx.match_counts(F - 1)
+    nd = min(F, 64)
+    dctx = ob.Context(width=w, height=h, nfeatures=nf, max_frames=1, device=local)
+    th2 = np.zeros(9)
+    dctx.adaptive_detect(frames[:nd], th2)                  # thresholds settle
+    t0 = time.perf_counter(); kps, used, found = dctx.adaptive_detect(frames[:nd], th2); det_ms = (time.perf_counter() - t0) * 1e3
+    dctx.close()
+    # parity: a fresh controller state over the first frames against the oracle
+    parity = None
+    if rank == 0 and args.cpu_sample > 0:
+        from oracle import oracle as orc
+        orc.build()
+        ns = min(4, F)
+        cfg = orc.adaptive_default(); cfg.min_features, cfg.max_features = band["min_features"], band["max_features"]
+        th_ref = np.zeros(9); th_got = np.zeros(9)
+        t0 = time.perf_counter()
+        ref = [orc.extract_adapted(f, th_ref, nfeatures=nf, cfg=cfg) for f in frames[:ns]]
+        cpu_dt = time.perf_counter() - t0
+        used_g, found_g = ctx.extract_adapted(frames[:ns], th_got, **band)
+        bad = []
+        for i in range(ns):
+            k, d, _ = ctx.download_frame(i)
+            if k.tobytes() != ref[i][0].tobytes() or not np.array_equal(d, ref[i][1]) or not np.array_equal(used_g[i], ref[i][2]):
+                bad.append(f"frame {i}")
+        if not np.array_equal(th_ref, th_got):
+            bad.append("controller state")
+        parity = {"frames": ns, "identical": not bad, "mismatches": bad, "checked": "keypoints, descriptors, thresholds used per region, controller state"}
+        cpu = {"value": ns / cpu_dt, "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"oracle extract_adapted on the first {ns} frames, {cpu_dt:.1f} s"}
+    else:
+        cpu = None
+    vals = torch.tensor([adapted_ms, fixed_ms, chain_ms, det_ms / nd], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    adapted_ms, fixed_ms, chain_ms, det_ms_per = [float(x) for x in vals]
+    if rank == 0:
+        px = sum(int(round(w / 1.2 ** l)) * int(round(h / 1.2 ** l)) for l in range(8))
+        out = {"metric": "frames_per_sec_orb_extract_1280x720_2000kp_adapted_thresholds", "value": world * F / (adapted_ms * 1e-3), "unit": "frames/s",
+               "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": adapted_ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+               "config": {"workload": "BASELINE configs[3]: 1280x720, 2000 kp, 8 levels, scale 1.2, iniThFAST adapted per 3x3 region by stateful controllers "
+                                      "(x0.7 below / x1.3 above the band), frames in video order", "frames_per_step_per_gpu": F,
+                          "band": band, "l2": f"per-step input {F * w * h / 1e6:.0f} MB of gray planes from pinned host memory"},
+               "routes": {"extract_adapted": {"frames_per_s": world * F / (adapted_ms * 1e-3), "ms_per_step": adapted_ms, "mean_keypoints": kp_adapted,
+                                              "input": "pinned host frames, H2D inside the timed region; per-frame controller step on the device",
+                                              "launches_per_step": int(adapted_launches)},
+                          "extract_fixed_device": {"frames_per_s": world * F / (fixed_ms * 1e-3), "ms_per_step": fixed_ms, "mean_keypoints": kp_fixed,
+                                                   "input": "frames resident in HBM", "algorithmic_bytes_per_frame": 14_193_683,
+                                                   "frac_of_hbm": 14_193_683 * F / (fixed_ms * 1e-3) / 1e9 / 6538.9},
+                          "chain_device": {"frames_per_s": world * F / (chain_ms * 1e-3), "ms_per_step": chain_ms, "mean_matches": float(mc.mean()),
+                                           "ransac_ok_frac": float(np.mean(summ["ok"])), "mean_inliers": float(np.mean(summ["n_inliers"])),
+                                           "what": "extract + kNN-2 (ratio 0.8, cross-check) + RANSAC(200,20,3.0,4), consecutive pairs, inputs in HBM"},
+                          "adaptive_detect": {"frames_per_s": world * 1e3 / det_ms_per, "ms_per_frame": det_ms_per, "mean_keypoints": float(np.mean([len(k) for k in kps])),
+                                              "what": "single-scale FAST + grid / dynamic adjusters (the reference's own config-4 route), host frames in, "
+                                                      "host keypoints out, controllers settled"}},
+               "pixels_per_frame_all_levels": px, "gpu_launches": int(adapted_launches), "cpu_baseline": cpu, "parity_in_bench": parity}
+        print(json.dumps(out))
+        if parity is not None and not parity["identical"]:
+            raise SystemExit("bench.py --config 4: device results disagree with the oracle: " + "; ".join(parity["mismatches"]))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def latency_arm(ob, local, frames, depths, n):
+    """The reference's per-frame tracking loop (System/tracking.cpp:38-46,193-208; protocol of Tests/detector-descriptor-speed-test.cpp:53-70)
+    through the drop-in calls, ONE frame at a time from pageable host memory: extraction + depth unprojection of the frame with every
+    result copied back to host vectors, Matcher::KnnMatch against the previous frame's descriptors, Ransac::Iterate on the 3D-3D pairs —
+    host in, host out, a synchronisation after every call.  Milliseconds per frame (frame + its pair), wall clock."""
+    ctx = ob.Context(max_frames=2, max_pairs=2, device=local)
+    fr = [np.array(f) for f in frames[:n]]; dp = [np.array(d) for d in depths[:n]]      # separate pageable arrays, as a loader hands them over
+    prev = None; ts = {"extract": [], "match": [], "ransac": [], "total": []}
+    for i in range(n):
+        t0 = time.perf_counter()
+        ctx.extract_batch(fr[i][None], dp[i][None], slot0=i & 1)
+        k, d, xyz = ctx.download_frame(i & 1)
+        t1 = time.perf_counter()
+        if prev is not None:
+            m = ctx.knn_match(prev[0], d, RATIO, CROSS)
+            t2 = time.perf_counter()
+            ctx.ransac_iterate(prev[1], xyz, m, want_table=False, seed=42 + i)
+            t3 = time.perf_counter()
+            if i >= 8:                                     # the first calls pay allocation / module load
+                ts["extract"].append(t1 - t0); ts["match"].append(t2 - t1); ts["ransac"].append(t3 - t2); ts["total"].append(t3 - t0)
+        prev = (d, xyz)
+    ctx.close()
+    q = lambda a, p: float(np.percentile(np.array(a) * 1e3, p))
+    return {"unit": "ms per frame (extract + match with the previous frame + RANSAC), one frame at a time, pageable host in / host out",
+            "frames": len(ts["total"]), "p50": q(ts["total"], 50), "p99": q(ts["total"], 99), "mean": float(np.mean(ts["total"]) * 1e3),
+            "p50_by_call": {k: q(v, 50) for k, v in ts.items() if k != "total"},
+            "calls": "orbf_extract_batch(n=1) + orbf_download_frame, orbf_knn_match, orbf_ransac_iterate through ctypes"}
+
+
+def fast_smem_view(F, ms, sm_mhz):
+    """FAST against the resource that binds it: the shared-memory data pipe (1 wavefront / clk / SM).  Wavefronts per pixel from the committed
+    ncu capture (profiles/r2i_fast_kernel.txt: l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / pixels of the launch); achieved = that x the
+    pixels of this launch / its CUDA-event time."""
+    wpp = 0.445; px = 950_532 * F; clk = (sm_mhz or 1965.0) * 1e6
+    ach = wpp * px / (ms * 1e-3)
+    return {"bound": "shared-memory data pipe", "wavefronts_per_pixel": wpp, "achieved_wavefronts_per_s": ach, "peak_wavefronts_per_s": 148 * clk,
+            "frac": ach / (148 * clk), "source": "profiles/r2i_fast_kernel.txt (ncu --set full of this kernel at 128 frames)"}
+
+
+def ransac_view(summ, stage_ms):
+    """unit = hypothesis x pair Mahalanobis evaluation (~150 f64 flops).  Counted as the reference's loop would execute them at
+    least: one scoring pass over the pair's good matches per VALID hypothesis (the <= 19 refit passes per hypothesis are not counted), over
+    the time of the RANSAC kernels of the step.  Latency-bound (a chain of ~10 dependent launches), no roofline claimed."""
+    evals = float(np.sum(summ["valid_iters"].astype(np.int64) * summ["n_good"].astype(np.int64)))
+    ms = stage_ms["ransac_prepare"] + stage_ms["ransac_hyp"] + stage_ms["ransac_select"]
+    return {"hyp_pair_evals_per_step": evals, "ms_per_step": ms, "hyp_pair_evals_per_s": evals / (ms * 1e-3), "f64_flops_per_eval": 150,
+            "f64_flops_per_s": 150 * evals / (ms * 1e-3), "bound": "latency (dependent launches; warp per hypothesis, f64 Mahalanobis)",
+            "mean_valid_hypotheses_per_pair": float(np.mean(summ["valid_iters"])), "mean_good_matches_per_pair": float(np.mean(summ["n_good"]))}
+
+
 def knn2_view(frame_counts, ms):
     """The matcher is the one compute-bound stage: descriptor pairs/s, and the same number as int8 tensor-core throughput
     (tcgen05 kind::i8: every pair is a 256-long s8 dot product = 512 ops; dense peak = 16384 ops/clk/SM, the figure ncu
@@ -365,6 +553,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="pipeline worker streams (0 = library default)")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5], help="3 = the headline sequence workload (default); 4 = 1280x720 / 2000 kp "
                     "with adapted thresholds; 5 = keyframe-database many-to-many matching over NCCL / NVLink")
+    ap.add_argument("--latency-frames", type=int, default=200, help="frames of the one-frame-at-a-time latency arm (rank 0, N=1; 0 = skip)")
     ap.add_argument("--no-overlap", action="store_true", help="e2e arm: every call starts after the previous one has finished on the device")
     ap.add_argument("--depth-copy", action="store_true", help="e2e arm: stage whole depth planes in HBM instead of sampling pinned host memory in place")
     args = ap.parse_args()
@@ -372,6 +561,8 @@ def main():
         return run_reference(args)
     if args.config == 5:
         return run_config5(args)
+    if args.config == 4:
+        return run_config4(args)
 
     import torch
     import torch.distributed as dist
@@ -546,15 +737,20 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": launches_per_step,
                     "avg_launch_ms": stage_ms[dom] / launches_per_step, "peak_source": peak_src,
-                    "note": ("the dominant kernel by time (fast_cell) is bound by the integer ALU pipe, not by HBM (ncu, profiles/r1x_kernels.csv: "
-                             "ALU pipe 57 %, issue slots 67 %, DRAM 6 %): its HBM fraction is small by construction.  stage_hbm_frac has the "
-                             "HBM-class stages (pyramid resize, blur), hamming_knn2 the tensor-core view of the matcher."),
+                    "note": ("the dominant kernel by time (fast_cell) is bound by the shared-memory data pipe, not by HBM (ncu, profiles/r2i_fast_kernel.txt: "
+                             "81 % of the peak wavefront rate, issue slots 71 %, DRAM 6 %): its HBM fraction is small by construction and fast_cell_smem "
+                             "is its real roofline.  stage_hbm_frac has the HBM-class stages (pyramid resize, blur), hamming_knn2 the tensor-core view "
+                             "of the matcher, ransac the hypothesis x pair rate."),
                     "stage_ms_per_step": stage_ms,
                     "stage_hbm_frac": {k: STAGE_BYTES[k] * F / (stage_ms[k] * 1e-3) / 1e9 / peak for k in STAGE_BYTES},
                     "whole_path": {"algorithmic_bytes_per_frame": FRAME_BYTES, "achieved_GBps": FRAME_BYTES * F / (ms * 1e-3) / 1e9,
                                    "frac_of_hbm": FRAME_BYTES * F / (ms * 1e-3) / 1e9 / peak},
-                    "hamming_knn2": knn2_view(fc, stage_ms["hamming_knn2"])}
-        cpu = None; parity = None
+                    "hamming_knn2": knn2_view(fc, stage_ms["hamming_knn2"]),
+                    "fast_cell_smem": fast_smem_view(F, stage_ms["fast_cell"], clocks.get("sm_mhz")),
+                    "ransac": ransac_view(summ, stage_ms)}
+        cpu = None; parity = None; latency = None
+        if world == 1 and args.latency_frames > 0:
+            latency = latency_arm(ob, local, frames, depths, min(F, args.latency_frames))
         if world == 1 and args.cpu_sample > 0:
             from oracle import oracle as orc
             orc.build()
@@ -566,6 +762,8 @@ def main():
                    "sample": f"first {ns} frames of the step's batch (extract {ns}, match+RANSAC {ns - 1} pairs), oracle -O3 -march=native, {dt:.1f} s"}
             run_e2e(1); torch.cuda.synchronize()            # the results compared are those of the end-to-end path (slot half 0)
             parity = parity_in_bench(orc, ectx, frames, depths, ns, 42)
+            if latency is not None:
+                latency["cpu_port_ms_per_frame"] = 1e3 / cpu["value"]
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": config_object(F),
@@ -579,7 +777,7 @@ def main():
                "e2e_full_download": {"value": total_frames / (full_ms * 1e-3), "unit": "frames/s", "ms_per_step": full_ms, "h2d_bytes_per_step": h2d,
                                      "d2h_bytes_per_step": d2h + full_d2h,
                                      "what": "as e2e, plus every frame's keypoints (cv::KeyPoint layout), descriptors, 3D points and every pair's matches copied to pinned host memory"},
-               "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_in_bench": parity,
+               "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_in_bench": parity, "latency": latency,
                "results": {"mean_keypoints": float(np.mean(fc)), "mean_matches": float(np.mean(mc)),
                            "ransac_ok_frac": float(np.mean(summ["ok"])), "mean_inliers": float(np.mean(summ["n_inliers"]))}}
         print(json.dumps(out))
