@@ -369,6 +369,17 @@ class Context:
                                               _p(dist), _p(out) if len(xy) else None), "undistort_points")
         return out
 
+    def unproject_keypoints(self, kps, depth):
+        """Frame::ExtractFeatures' tail for external keypoints: (xyz [n, 3], u_right [n], xy_un [n, 2]); depth [H, W] u16 or None."""
+        kps = np.ascontiguousarray(kps, KEYPOINT_DT); n = len(kps)
+        xyz = np.zeros((n, 3), np.float32); ur = np.zeros(n, np.float32); un = np.zeros((n, 2), np.float32)
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, np.uint16); h, w = depth.shape
+        else:
+            h, w = self.cfg.height, self.cfg.width
+        self._chk(lib().orbf_unproject_keypoints(self._h, _p(kps), n, _p(depth), w, h, C.c_int64(w), _p(xyz), _p(ur), _p(un)), "unproject_keypoints")
+        return xyz, ur, un
+
     def fuse_search(self, Rcw, tcw, camera, lm_pos, lm_desc, lm_valid, slot=-1, kp_x=None, kp_y=None, u_right=None, desc=None, radius=3.0, th_low=50):
         """Matcher::Fuse, projection + windowed search (Features/matcher.cpp:212-296): (best feature or -1, its distance or -1) per landmark.
         camera = (fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY)."""
@@ -458,6 +469,18 @@ class Context:
         out = np.zeros(npairs, RANSAC_RESULT_DT)
         self._chk(lib().orbf_download_ransac_summary(self._h, npairs, _p(out)), "download_ransac_summary")
         return out
+
+    def download_ransac_clouds(self, pair):
+        """Ransac::mpSourceCloud / mpTargetCloud of a pair last solved: two [n, 4] float32 arrays (x, y, z, 1 — pcl::PointXYZ records)."""
+        a = np.zeros((self.K, 4), np.float32); b = np.zeros((self.K, 4), np.float32); n = C.c_int32(0)
+        self._chk(lib().orbf_download_ransac_clouds(self._h, pair, _p(a), _p(b), self.K, C.byref(n)), "download_ransac_clouds")
+        return a[:n.value].copy(), b[:n.value].copy()
+
+    def ransac_clouds_device(self, pair0, npairs):
+        """Device-resident clouds of pairs [pair0, pair0 + npairs): (src pointer, tgt pointer, counts pointer, points per pair)."""
+        ps = C.c_void_p(); pt = C.c_void_p(); pc = C.c_void_p(); k = C.c_int32(0)
+        self._chk(lib().orbf_ransac_clouds(self._h, pair0, npairs, C.byref(ps), C.byref(pt), C.byref(pc), C.byref(k)), "ransac_clouds")
+        return ps.value, pt.value, pc.value, k.value
 
     def kabsch(self, A, B):
         A = np.ascontiguousarray(A, np.float32).reshape(-1, 3); B = np.ascontiguousarray(B, np.float32).reshape(-1, 3)

@@ -799,6 +799,32 @@ extern "C" int orbf_undistort_points(orbf_context* c, const float* xy, int32_t n
     return ORBF_OK;
 }
 
+extern "C" int orbf_unproject_keypoints(orbf_context* c, const orbf_keypoint* kps, int32_t n, const uint16_t* depth, int32_t width, int32_t height,
+    int64_t depth_stride_elems, float* xyz, float* u_right, float* xy_un)
+{
+    CTX_ENTER(c);
+    if (n < 0 || (n > 0 && (!kps || !xyz || !u_right || !xy_un)) || (depth && depth_stride_elems < width)) return ORBF_ERR_ARG;
+    if (n == 0) return ORBF_OK;
+    // the caller's plane is indexed here (one sample per keypoint at the truncated, distorted position, Core/frame.cpp:152-155): the
+    // n samples cross the link instead of the plane; all arithmetic (undistortion, unprojection) runs on the device
+    std::vector<float> xy((size_t)n * 2); std::vector<uint16_t> raw((size_t)n, 0);
+    for (int i = 0; i < n; ++i) {
+        xy[2 * i] = kps[i].x; xy[2 * i + 1] = kps[i].y;
+        const int u = (int)kps[i].x, v = (int)kps[i].y;
+        if (depth && u >= 0 && v >= 0 && u < width && v < height) raw[i] = depth[(int64_t)v * depth_stride_elems + u];
+    }
+    Scratch sc;
+    const size_t oXy = sc.take((size_t)n * 8), oRaw = sc.take((size_t)n * 2), oXyz = sc.take((size_t)n * 12), oUr = sc.take((size_t)n * 4), oUn = sc.take((size_t)n * 8);
+    SC_CUDA(sc.alloc());
+    SC_H2D(oXy, xy.data(), (size_t)n * 8); SC_H2D(oRaw, raw.data(), (size_t)n * 2);
+    TRY(orbf_launch_unproject(c, sc.at<float>(oXy), sc.at<uint16_t>(oRaw), n, sc.at<float>(oXyz), sc.at<float>(oUr), sc.at<float>(oUn)));
+    SC_CUDA(cudaMemcpyAsync(xyz, sc.at<float>(oXyz), (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaMemcpyAsync(u_right, sc.at<float>(oUr), (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaMemcpyAsync(xy_un, sc.at<float>(oUn), (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
 extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float* kp_x, const float* kp_y, const int32_t* kp_octave, const uint8_t* desc,
     int32_t n_feat, const uint8_t* lm_desc, const float* proj_x, const float* proj_y, const uint8_t* lm_flags, int32_t n_landmarks,
     const uint8_t* feat_taken, float radius, float nn_ratio, int32_t th_high, int32_t* best_idx, int32_t* n_matches)
@@ -1027,6 +1053,38 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
     if (good_sorted_out && out->n_good > 0)
         ORBF_CUDA(c, cudaMemcpyAsync(good_sorted_out, c->d_good, (size_t)out->n_good * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
     if (sample_table_out) ORBF_CUDA(c, cudaMemcpyAsync(sample_table_out, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
+
+extern "C" int orbf_ransac_clouds(orbf_context* c, int32_t pair0, int32_t npairs, const float** d_src_xyzw, const float** d_tgt_xyzw,
+    const int32_t** d_counts, int32_t* points_per_pair)
+{
+    CTX_ENTER(c);
+    if (npairs < 1 || pair0 < 0 || pair0 + npairs > c->P) return ORBF_ERR_ARG;
+    if (c->lastNPairs <= 0) return ORBF_ERR_STATE;
+    TRY(orbf_launch_ransac_clouds(c, pair0, npairs));
+    if (d_src_xyzw) *d_src_xyzw = reinterpret_cast<const float*>(c->d_cloudSrc);
+    if (d_tgt_xyzw) *d_tgt_xyzw = reinterpret_cast<const float*>(c->d_cloudTgt);
+    if (d_counts) *d_counts = c->d_cloudCount;
+    if (points_per_pair) *points_per_pair = c->K;
+    return ORBF_OK;
+}
+
+extern "C" int orbf_download_ransac_clouds(orbf_context* c, int32_t pair, float* src_xyzw, float* tgt_xyzw, int32_t cap, int32_t* n_out)
+{
+    CTX_ENTER(c);
+    if (!n_out || pair < 0 || pair >= c->P) return ORBF_ERR_ARG;
+    if (c->lastNPairs <= 0) return ORBF_ERR_STATE;
+    TRY(orbf_launch_ransac_clouds(c, pair, 1));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_cloudCount + pair, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int n = c->h_counts[0];
+    *n_out = n;
+    if (n > cap) return ORBF_ERR_CAPACITY;
+    if (n == 0) return ORBF_OK;
+    if (src_xyzw) ORBF_CUDA(c, cudaMemcpyAsync(src_xyzw, c->d_cloudSrc + (size_t)pair * c->K, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (tgt_xyzw) ORBF_CUDA(c, cudaMemcpyAsync(tgt_xyzw, c->d_cloudTgt + (size_t)pair * c->K, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     return ORBF_OK;
 }

@@ -363,7 +363,8 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->d_qdesc = c->d_tdesc = nullptr; c->d_sxyz = c->d_txyz = nullptr;
     c->d_bgr = nullptr; c->bgrSlots = 0;
     c->d_kfDesc = nullptr; c->d_kfCount = nullptr; c->d_kfExtDesc = nullptr; c->d_kfExtCount = nullptr; c->kfExtN = 0;
-    c->d_pts = nullptr; c->ptsCap = 0; c->d_userSamples = nullptr; c->userSamplesCap = 0; c->d_kabsch = nullptr; c->kabschCap = 0;
+    c->d_pts = nullptr; c->ptsCap = 0; c->d_userSamples = nullptr; c->userSamplesCap = 0; c->d_cloudSrc = c->d_cloudTgt = nullptr; c->d_cloudCount = nullptr; c->cloudCap = 0;
+    memset(&c->lastRs, 0, sizeof(c->lastRs)); memset(&c->lastRansacCfg, 0, sizeof(c->lastRansacCfg)); c->d_kabsch = nullptr; c->kabschCap = 0;
     c->d_kfKnn = nullptr; c->d_kfSurv = nullptr; c->d_kfPairs = nullptr; c->d_kfQCount = nullptr; c->kfOutCap = 0;
     c->ncclComm = nullptr; c->commRanks = 1; c->commRank = 0; c->d_kfGather = nullptr; c->d_kfGatherCount = nullptr; c->kfGatherCap = 0;
     c->d_peerDesc = nullptr; c->d_peerCount = nullptr; c->nPeers = 0; c->peerKf = 0;
@@ -401,7 +402,7 @@ extern "C" int orbf_destroy(orbf_context* c)
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpux, c->d_kpuy, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,
-        c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts,
+        c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts, c->d_cloudSrc, c->d_cloudTgt, c->d_cloudCount,
         c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount, c->d_cellRegion, c->d_regionTh, c->d_regionState, c->d_regionLog };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < c->L; ++l) { if (c->d_pyr[l]) cudaFree(c->d_pyr[l]); if (c->d_blur[l]) cudaFree(c->d_blur[l]); }

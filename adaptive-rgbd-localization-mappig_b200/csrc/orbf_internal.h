@@ -73,6 +73,15 @@ struct LevelGeom {
 enum OrbfStage { ST_PYRAMID = 0, ST_FAST, ST_QUADTREE, ST_BLUR, ST_DESCRIBE, ST_KNN2, ST_MATCH_SELECT, ST_RANSAC_PREPARE,
     ST_RANSAC_HYP, ST_RANSAC_SELECT, ST_COUNT };
 
+// inputs of a RANSAC call: 3D points of the frames (slot SoA or standalone arrays) and the matches of each pair
+struct RansacSet {
+    const float *sx, *sy, *sz, *tx, *ty, *tz;     // SoA bases of slot 0 (or standalone arrays)
+    long long slotStride;                          // elements per slot (K) or 0
+    const int* pairs;                              // [npairs][2] or NULL
+    const orbf_dmatch* matches; const int* matchCount;   // [P][K] input matches
+    int nsrc, ndst;
+};
+
 struct orbf_context {
     orbf_config cfg;
     int L;
@@ -139,6 +148,8 @@ struct orbf_context {
     uint32_t* d_rev;          // [P][K] packed best query per train (cross-check)
     orbf_dmatch* d_matches; int* d_matchCount;   // [P][K]
     int lastNPairs; bool pairsFromSlots;
+    RansacSet lastRs; orbf_ransac_config lastRansacCfg;            // what orbf_launch_ransac last ran on
+    float4* d_cloudSrc; float4* d_cloudTgt; int* d_cloudCount; size_t cloudCap;   // Ransac::mpSourceCloud / mpTargetCloud of the pairs last solved (lazy)
     // standalone matching staging
     uint8_t* d_qdesc; uint8_t* d_tdesc; int descStageRows;
 
@@ -220,6 +231,7 @@ struct MatchSet {
 int orbf_launch_knn2(orbf_context* ctx, const MatchSet& ms, int npairs, bool cross);
 int orbf_launch_distinctive(orbf_context* ctx, const uint8_t* d_desc, const int* d_offsets, int nLandmarks, int* d_best, int* d_median);
 int orbf_launch_undistort(orbf_context* ctx, const float* d_xy, int n, float fx, float fy, float cx, float cy, const float* dist5, float* d_out);
+int orbf_launch_unproject(orbf_context* ctx, const float* d_xy, const uint16_t* d_raw, int n, float* d_xyz, float* d_uright, float* d_xyUn);
 int orbf_launch_compose(orbf_context* ctx, int npairs, const float* d_pose0, float* d_poses, uint8_t* d_outlier);
 int orbf_launch_fuse_search(orbf_context* ctx, const float* Rcw, const float* tcw, const float* camera, const float* d_kpx, const float* d_kpy, const float* d_uright,
     const uint8_t* d_desc, int nFeat, const float* d_lmPos, const uint8_t* d_lmDesc, const uint8_t* d_lmValid, int nLm, float radius, int thLow, int* d_bestIdx,
@@ -232,16 +244,11 @@ int orbf_launch_projection_match(orbf_context* ctx, const float* d_kpx, const fl
     int thHigh, uint32_t* d_cand, int* d_candCount, uint8_t* d_taken, int* d_bestIdx, int* d_nMatches);
 int orbf_launch_match_select(orbf_context* ctx, const MatchSet& ms, int npairs, float ratio, bool cross);
 // RANSAC
-struct RansacSet {
-    const float *sx, *sy, *sz, *tx, *ty, *tz;     // SoA bases of slot 0 (or standalone arrays)
-    long long slotStride;                          // elements per slot (K) or 0
-    const int* pairs;                              // [npairs][2] or NULL
-    const orbf_dmatch* matches; const int* matchCount;   // [P][K] input matches
-    int nsrc, ndst;
-};
 int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int n, float* dT);
 // pairs [pair0, pair0 + npairs).  The depth covariance (quirk Q7) is latched by the first pair, in enqueue order, that reaches
 // scoring; standalone = the call neither sees nor replaces the value latched on the context (orbf_ransac_iterate).
 int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);
+// mpSourceCloud / mpTargetCloud (Odometry/ransac.cpp:171-189) of pairs [pair0, pair0 + npairs) of the set last handed to orbf_launch_ransac
+int orbf_launch_ransac_clouds(orbf_context* ctx, int pair0, int npairs);
 int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
     const int* d_userSamples, bool standalone, bool fullTable = false, bool probeOnly = false);

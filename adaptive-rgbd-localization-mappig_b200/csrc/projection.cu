@@ -241,7 +241,40 @@ __global__ void __launch_bounds__(128) undistort_kernel(UndistortParams U, const
     undistort_point(U, xy[2 * i], xy[2 * i + 1], &out[2 * i], &out[2 * i + 1]);
 }
 
+// ---- Frame::ExtractFeatures' per-keypoint tail (Core/frame.cpp:148-164) for keypoints that did not come out of the ORB extractor
+// (the adaptive-FAST route): mvKeysUn, mvuRight and mvKeys3Dc from the keypoint position and its raw depth sample (0 = outside the
+// image / no sample).  Same operation order as describe.cu; thread per keypoint.
+__global__ void __launch_bounds__(128) unproject_kernel(UndistortParams U, int distorted, const float* __restrict__ xy, const uint16_t* __restrict__ raw, int n,
+    float cx, float cy, float invfx, float invfy, float mbf, float depthFactor, float* __restrict__ xyz, float* __restrict__ uright, float* __restrict__ xyUn)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const float x = xy[2 * i], y = xy[2 * i + 1];
+    float uX = x, uY = y;
+    if (distorted) undistort_point(U, x, y, &uX, &uY);
+    float X = 0.f, Y = 0.f, Z = 0.f, ur = -1.f;
+    const float z = __fmul_rn((float)raw[i], depthFactor);
+    if (z > 0) {
+        ur = __fsub_rn(uX, __fdiv_rn(mbf, z));
+        X = __fmul_rn(__fmul_rn(__fsub_rn(uX, cx), z), invfx);
+        Y = __fmul_rn(__fmul_rn(__fsub_rn(uY, cy), z), invfy);
+        Z = z;
+    }
+    xyz[3 * i] = X; xyz[3 * i + 1] = Y; xyz[3 * i + 2] = Z; uright[i] = ur; xyUn[2 * i] = uX; xyUn[2 * i + 1] = uY;
+}
+
 }  // namespace
+
+int orbf_launch_unproject(orbf_context* c, const float* d_xy, const uint16_t* d_raw, int n, float* d_xyz, float* d_uright, float* d_xyUn)
+{
+    if (n <= 0) return ORBF_OK;
+    const orbf_config& g = c->cfg;
+    UndistortParams U{(double)g.fx, (double)g.fy, (double)g.cx, (double)g.cy, (double)g.k1, (double)g.k2, (double)g.p1, (double)g.p2, (double)g.k3};
+    unproject_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(U, g.k1 != 0.f ? 1 : 0, d_xy, d_raw, n, g.cx, g.cy, 1.0f / g.fx, 1.0f / g.fy, g.mbf, g.depth_factor,
+        d_xyz, d_uright, d_xyUn);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
 
 int orbf_launch_projection_match(orbf_context* c, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat, const uint8_t* d_lmDesc,
     const float* d_projX, const float* d_projY, const uint8_t* d_lmFlags, int nLm, const uint8_t* d_featTaken, float radius, float nnRatio, int thHigh,

@@ -877,6 +877,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
         if (r != ORBF_OK) return r;
     }
     const int iters = cfg.iterations, S = (int)cfg.sample_size;
+    if (!probeOnly) { c->lastRs = rs; c->lastRansacCfg = cfg; }
     RansacParams P;
     P.rs = rs; P.cfg = cfg; P.good = c->d_good; P.goodCount = c->d_goodCount; P.pts = reinterpret_cast<Pt6*>(c->d_pts);
     P.samples = c->d_samples; P.userSamples = d_userSamples; P.hyp = c->d_hyp; P.res = c->d_rres; P.inliers = c->d_inliers;
@@ -971,7 +972,70 @@ __global__ void __launch_bounds__(256) inlier_flag_kernel(const orbf_ransac_resu
     const int n = res[p].n_inliers;
     for (int i = threadIdx.x; i < n; i += 256) outlier[(size_t)(p + 1) * K + inliers[(size_t)p * K + i].trainIdx] = 0;
 }
+
+// Ransac::mpSourceCloud / mpTargetCloud (Odometry/ransac.cpp:163-189): the 3D points of the depth-valid matches in m12 order (before the
+// sort), one pcl::PointXYZ (16 bytes: x, y, z, 1.0f) per point; both stay empty when m12 has fewer than min_inlier_th entries.  CTA per pair.
+__global__ void __launch_bounds__(256) ransac_clouds_kernel(RansacSet rs, int K, int pair0, unsigned minInl, int checkDepth, float4* __restrict__ src,
+    float4* __restrict__ tgt, int* __restrict__ counts)
+{
+    __shared__ int sWarp[8];
+    __shared__ int sBase;
+    const int pair = pair0 + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int qs = 0, ts = 0;
+    if (rs.pairs) { qs = rs.pairs[2 * pair]; ts = rs.pairs[2 * pair + 1]; }
+    const long long so = (long long)qs * rs.slotStride, to = (long long)ts * rs.slotStride;
+    const orbf_dmatch* m12 = rs.matches + (long long)pair * K;
+    const int nm = rs.matchCount[pair];
+    float4* os = src + (long long)pair * K; float4* ot = tgt + (long long)pair * K;
+    if (tid == 0) sBase = 0;
+    __syncthreads();
+    if ((unsigned)nm >= minInl) {
+        for (int base = 0; base < nm; base += 256) {
+            const int i = base + tid;
+            bool keep = false;
+            float4 a = make_float4(0.f, 0.f, 0.f, 1.f), b = a;
+            if (i < nm) {
+                const orbf_dmatch m = m12[i];
+                a.x = rs.sx[so + m.queryIdx]; a.y = rs.sy[so + m.queryIdx]; a.z = rs.sz[so + m.queryIdx];
+                b.x = rs.tx[to + m.trainIdx]; b.y = rs.ty[to + m.trainIdx]; b.z = rs.tz[to + m.trainIdx];
+                keep = !(checkDepth && (isnan(a.z) || isnan(b.z) || a.z <= 0 || b.z <= 0));
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) sWarp[warp] = __popc(mk);
+            __syncthreads();
+            int off = sBase;
+            for (int w = 0; w < warp; ++w) off += sWarp[w];
+            if (keep) { const int o = off + __popc(mk & ((1u << lane) - 1)); os[o] = a; ot[o] = b; }
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += sWarp[w]; sBase += t; }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) counts[pair] = sBase;
+}
 }  // namespace
+
+int orbf_launch_ransac_clouds(orbf_context* c, int pair0, int npairs)
+{
+    if (npairs <= 0) return ORBF_OK;
+    if (!c->lastRs.matches) return ORBF_ERR_STATE;
+    const size_t need = (size_t)c->P * c->K;
+    if (c->cloudCap < need) {
+        if (c->d_cloudSrc) cudaFree(c->d_cloudSrc);
+        if (c->d_cloudTgt) cudaFree(c->d_cloudTgt);
+        if (c->d_cloudCount) cudaFree(c->d_cloudCount);
+        c->d_cloudSrc = c->d_cloudTgt = nullptr; c->d_cloudCount = nullptr; c->cloudCap = 0;
+        ORBF_CUDA(c, cudaMalloc(&c->d_cloudSrc, need * sizeof(float4)));
+        ORBF_CUDA(c, cudaMalloc(&c->d_cloudTgt, need * sizeof(float4)));
+        ORBF_CUDA(c, cudaMalloc(&c->d_cloudCount, (size_t)c->P * sizeof(int)));
+        c->cloudCap = need;
+    }
+    ransac_clouds_kernel<<<npairs, 256, 0, c->stream>>>(c->lastRs, c->K, pair0, c->lastRansacCfg.min_inlier_th, c->lastRansacCfg.check_depth, c->d_cloudSrc,
+        c->d_cloudTgt, c->d_cloudCount);
+    ORBF_LAUNCH_CHECK(c);
+    return ORBF_OK;
+}
 
 int orbf_launch_compose(orbf_context* c, int npairs, const float* d_pose0, float* d_poses, uint8_t* d_outlier)
 {

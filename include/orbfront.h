@@ -219,6 +219,12 @@ int orbf_distinctive_descriptors(orbf_context* ctx, const uint8_t* desc, const i
  * ComputeImageBounds (frame.cpp:320-343).  The extraction entry points apply the same arithmetic to their keypoints when
  * orbf_config.k1 != 0 (see there).                                                                                      */
 int orbf_undistort_points(orbf_context* ctx, const float* xy, int32_t n, float fx, float fy, float cx, float cy, const float* dist, float* out);
+/* The per-keypoint tail of Frame::ExtractFeatures (Core/frame.cpp:138-164) for keypoints that did not come out of the ORB extractor
+ * (the adaptive-FAST route of Extractor): mvKeysUn (xy_un, n interleaved pairs; cv::undistortPoints when orbf_config.k1 != 0),
+ * mvuRight (u_right, -1 without depth) and mvKeys3Dc (xyz, n interleaved triples, zeros without depth) from the keypoints and the
+ * u16 depth plane (host; NULL = no depth; sampled at the truncated distorted position, scaled by orbf_config.depth_factor).            */
+int orbf_unproject_keypoints(orbf_context* ctx, const orbf_keypoint* kps, int32_t n, const uint16_t* depth, int32_t width, int32_t height,
+    int64_t depth_stride_elems, float* xyz, float* u_right, float* xy_un);
 /* Matcher::ProjectionMatch (Features/matcher.cpp:90-143) for one frame: landmarks projected into the frame are matched, in order,
  * to the features inside the square window |dx| < radius && |dy| < radius; best <= th_high, and rejected when best and second best
  * share an octave and best > nn_ratio * second; a feature given to a landmark with Observations() > 0 is skipped by later landmarks.
@@ -268,6 +274,16 @@ int orbf_ransac_pairs(orbf_context* ctx, int32_t npairs, const orbf_ransac_confi
 int orbf_ransac_probe_depth_cov(orbf_context* ctx, int32_t npairs, const orbf_ransac_config* cfg, double* cov);
 int orbf_download_ransac(orbf_context* ctx, int32_t pair, orbf_ransac_result* out, orbf_dmatch* inliers, int32_t cap);
 int orbf_download_ransac_summary(orbf_context* ctx, int32_t npairs, orbf_ransac_result* out /* [npairs] */);
+/* Ransac::mpSourceCloud / mpTargetCloud (Odometry/ransac.h:67-68, filled at Odometry/ransac.cpp:163-189 for the GICP refinement that
+ * follows): for every pair last solved (orbf_ransac_pairs / orbf_track_sequence* / orbf_ransac_iterate = pair 0), the 3D points of its
+ * depth-valid matches in m12 order, as pcl::PointXYZ records (16 bytes: x, y, z, 1.0f), source frame and target frame; empty when the
+ * pair had fewer than min_inlier_th matches (the early return at ransac.cpp:166-167).  orbf_ransac_clouds fills the device-resident
+ * buffers for pairs [pair0, pair0 + npairs) and hands out their base pointers: cloud of pair p at base + p * points_per_pair * 4 floats,
+ * its length at d_counts[p] — valid until the next RANSAC call on the context (asynchronous on the context stream).
+ * orbf_download_ransac_clouds copies one pair's clouds to host arrays of cap points each.                                              */
+int orbf_ransac_clouds(orbf_context* ctx, int32_t pair0, int32_t npairs, const float** d_src_xyzw, const float** d_tgt_xyzw,
+    const int32_t** d_counts, int32_t* points_per_pair);
+int orbf_download_ransac_clouds(orbf_context* ctx, int32_t pair, float* src_xyzw, float* tgt_xyzw, int32_t cap, int32_t* n_out);
 int orbf_kabsch(orbf_context* ctx, const float* setA, const float* setB, int32_t n, float* T16);
 /* Odometry::Compute, RANSAC strategy (Odometry/odometry.cpp:78-90) for the npairs consecutive pairs last solved by orbf_ransac_pairs /
  * orbf_track_sequence: poses[0] = pose0 (row-major 4x4, NULL = identity), poses[k + 1] = T12[k] * poses[k] with cv::Mat's float product;

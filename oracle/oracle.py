@@ -448,3 +448,33 @@ def ransac_iterate(src_xyz, dst_xyz, m12, iterations=200, min_inlier_th=20, max_
                 valid_iters=out.valid_iters, used_identity=bool(out.used_identity),
                 depth_cov=float(out.depth_cov_used), hyp=hyp, good_sorted=good[:out.n_good].copy(),
                 sample_table=tab_out)
+
+
+def ransac_clouds(src_xyz, dst_xyz, m12, min_inlier_th=20, check_depth=True):
+    """Ransac::mpSourceCloud / mpTargetCloud as Iterate leaves them (ransac.cpp:163-189): cleared; nothing more when m12 has fewer than
+    min_inlier_th entries; otherwise one pcl::PointXYZ (x, y, z, 1) per match whose two depths are valid, in m12 order (before the sort).
+    Plain numpy restatement (an index gather: nothing to compile)."""
+    src = np.asarray(src_xyz, np.float32).reshape(-1, 3); dst = np.asarray(dst_xyz, np.float32).reshape(-1, 3)
+    a = np.zeros((0, 4), np.float32)
+    if len(m12) < min_inlier_th:
+        return a, a.copy()
+    s = src[m12["queryIdx"]]; t = dst[m12["trainIdx"]]
+    keep = np.ones(len(m12), bool)
+    if check_depth:
+        keep = ~(np.isnan(s[:, 2]) | np.isnan(t[:, 2]) | (s[:, 2] <= 0) | (t[:, 2] <= 0))
+    one = np.ones((int(keep.sum()), 1), np.float32)
+    return np.hstack([s[keep], one]), np.hstack([t[keep], one])
+
+
+def knn_match_keyframe(kf_desc, f2_desc, ratio, kf_landmarks, is_bad, f2_landmarks):
+    """Matcher::KnnMatch(KeyFrame*, Frame&, vMatches12) (matcher.cpp:23-53): ratio survivors in query order, kept when the keyframe holds a
+    landmark at queryIdx (kf_landmarks[i] != 0) that is not bad and the frame's feature at trainIdx is still free; an accepted match
+    hands the landmark to the frame (f2_landmarks is updated in place) — so a later match onto the same feature is skipped."""
+    out = []
+    for m in knn_match(kf_desc, f2_desc, ratio, False):
+        lm = kf_landmarks[m["queryIdx"]]
+        if lm == 0 or is_bad(lm) or f2_landmarks[m["trainIdx"]] != 0:
+            continue
+        f2_landmarks[m["trainIdx"]] = lm
+        out.append(m)
+    return np.array(out, DMATCH_DT) if out else np.zeros(0, DMATCH_DT)

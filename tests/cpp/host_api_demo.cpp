@@ -2,6 +2,7 @@
 // tracking loop does (System/tracking.cpp:38-46, 193-208): Frame::ExtractFeatures -> Matcher(ratio).KnnMatch(last, cur)
 // -> Ransac::Iterate(last, cur, m12).  Reads raw frames from argv[1], writes every result to argv[2] for
 // tests/test_cpp_host.py to compare with the oracle.  Exit code 3 = no CUDA device (there is no CPU fallback).
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -44,7 +45,8 @@ int main(int argc, char** argv)
             std::vector<DMatch> m12;
             Matcher matcher(0.8f);
             matcher.KnnMatch(frames[i - 1], frames[i], m12, /*crossCheck=*/true);
-            const bool ok = odometry.Compute(&frames[i - 1], &frames[i], m12);
+            odometry.Compute(&frames[i - 1], &frames[i], m12);
+            const bool ok = odometry.mbConverged;
             puti(out, (int)m12.size());
             put(out, m12.data(), m12.size() * sizeof(DMatch));
             puti(out, ok ? 1 : 0);
@@ -60,6 +62,53 @@ int main(int argc, char** argv)
         for (auto& p : B) { const float x = p.x; p.x = -p.y + 0.1f; p.y = x - 0.2f; p.z += 0.3f; }      // 90 deg about z + translation
         const Matrix4f T = Kabsch().Compute(A, B);
         put(out, T.m, sizeof(float) * 16);
+        {   // Kabsch::Compute(MatrixXf, MatrixXf): the reference's signature (kabsch.h:10), rows = points
+            MatrixXf MA((int)A.size(), 3), MB((int)B.size(), 3);
+            for (int i = 0; i < (int)A.size(); ++i) { MA(i, 0) = A[i].x; MA(i, 1) = A[i].y; MA(i, 2) = A[i].z; MB(i, 0) = B[i].x; MB(i, 1) = B[i].y; MB(i, 2) = B[i].z; }
+            const Matrix4f T2 = Kabsch().Compute(MA, MB);
+            put(out, T2.m, sizeof(float) * 16);
+        }
+        // poses after Odometry::Compute's composition rule (odometry.cpp:82-86); frame 0 keeps the identity
+        for (int i = 0; i < n; ++i) { const Matrix4f P = frames[i].GetPose(); put(out, P.m, sizeof(float) * 16); }
+        // ORBextractor::mvImagePyramid[2] of the last frame extracted (orbextractor.h:57)
+        {
+            const Mat8u lvl = extractor.detector()->mvImagePyramid[2];
+            puti(out, (int)extractor.detector()->mvImagePyramid.size()); puti(out, lvl.cols); puti(out, lvl.rows);
+            put(out, lvl.data, (size_t)lvl.cols * lvl.rows);
+        }
+        if (n >= 2) {
+            // Matcher::KnnMatch(KeyFrame*, Frame&, .) (matcher.cpp:23-53): landmarks at the even features of the keyframe, every fifth of
+            // them bad, one feature of the frame already taken
+            KeyFrame kf0(frames[0]), kf1(frames[1]);
+            for (size_t j = 0; j < kf0.N; j += 2) kf0.AddLandmark(reinterpret_cast<Landmark*>((uintptr_t)(j + 1)), j);
+            Frame f2 = frames[1];
+            if (f2.N > 7) f2.AddLandmark(reinterpret_cast<Landmark*>((uintptr_t)0x7fff), 7);
+            std::vector<DMatch> mk;
+            Matcher(0.8f).KnnMatch(&kf0, f2, mk, [](Landmark* p) { return ((uintptr_t)p - 1) % 10 == 0; });
+            puti(out, (int)mk.size());
+            put(out, mk.data(), mk.size() * sizeof(DMatch));
+            int nOut = 0;
+            for (size_t j = 0; j < f2.N; ++j) nOut += f2.IsOutlier(j) ? 1 : 0;
+            puti(out, nOut);
+            // Ransac(KeyFrame*, KeyFrame*, matches).Iterate() (ransac.cpp:26-36,44-153) and the clouds it leaves behind
+            std::vector<DMatch> m01;
+            Matcher(0.8f).KnnMatch(frames[0], frames[1], m01, /*crossCheck=*/true);
+            Ransac::Seed() = 100;
+            Ransac bound(&kf0, &kf1, m01);
+            const bool ok2 = bound.Iterate();
+            puti(out, ok2 ? 1 : 0);
+            put(out, bound.mT12.m, sizeof(float) * 16);
+            puti(out, (int)bound.mvInliers.size());
+            put(out, bound.mvInliers.data(), bound.mvInliers.size() * sizeof(DMatch));
+            puti(out, (int)bound.mpSourceCloud->points.size());
+            put(out, bound.mpSourceCloud->points.data(), bound.mpSourceCloud->points.size() * sizeof(PointXYZ));
+            put(out, bound.mpTargetCloud->points.data(), bound.mpTargetCloud->points.size() * sizeof(PointXYZ));
+            // too few matches: the early return leaves everything cleared
+            std::vector<DMatch> few(m01.begin(), m01.begin() + std::min<size_t>(5, m01.size()));
+            Ransac r3;
+            const bool ok3 = r3.Iterate(&frames[0], &frames[1], few);
+            puti(out, ok3 ? 1 : 0); puti(out, (int)r3.mpSourceCloud->points.size()); puti(out, (int)r3.mvInliers.size());
+        }
         // Extractor(FAST, ., ADAPTIVE): the stateful grid detector over the same frames (extractor.cpp:52-77)
         Extractor adaptive(Extractor::FAST, Extractor::BRIEF, Extractor::ADAPTIVE);
         for (int i = 0; i < n; ++i) {
@@ -67,6 +116,15 @@ int main(int argc, char** argv)
             adaptive.Extract(Mat8u(h, w, gray.data() + (size_t)i * w * h), Mat8u(), kps, none);
             puti(out, (int)kps.size());
             put(out, kps.data(), kps.size() * sizeof(KeyPoint));
+        }
+        {   // Frame::ExtractFeatures on the adaptive route: the detector's keypoints unprojected on the device (frame.cpp:138-164)
+            Extractor adaptive2(Extractor::FAST, Extractor::BRIEF, Extractor::ADAPTIVE);
+            Frame fa(Mat8u(h, w, gray.data()), Mat16u(h, w, depth.data()), 0.0);
+            fa.ExtractFeatures(&adaptive2);
+            puti(out, (int)fa.N);
+            put(out, fa.mvKeys.data(), fa.N * sizeof(KeyPoint));
+            put(out, fa.mvKeys3Dc.data(), fa.N * sizeof(Point3f));
+            put(out, fa.mvuRight.data(), fa.N * sizeof(float));
         }
         put(out, adaptive.AdaptiveThresholds().data(), 9 * sizeof(double));
         Runtime::Shutdown();

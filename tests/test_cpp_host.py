@@ -59,7 +59,7 @@ def test_host_mirror_matches_oracle(demo, ob, orc, texture, tmp_path):
         a = np.frombuffer(buf, dtype, count, pos); pos += a.nbytes
         return a
 
-    prev = None; cov = -1.0
+    prev = None; cov = -1.0; T12s = []; hostd = []
     for i in range(n):
         N = int(take(np.int32, 1)[0])
         k = take(ob.KEYPOINT_DT, N); d = take(np.uint8, N * 32).reshape(N, 32); xyz = take(np.float32, N * 3).reshape(N, 3)
@@ -75,16 +75,80 @@ def test_host_mirror_matches_oracle(demo, ob, orc, texture, tmp_path):
             cov = ro["depth_cov"]
             assert ok == int(ro["ok"]) and inl.tobytes() == ro["inliers"].tobytes() and rmse == ro["rmse"]
             assert np.abs(T - ro["T12"]).max() <= 1e-5
-        prev = (do, xo)
+            T12s.append(T)
+        prev = (do, xo); hostd.append((do, xo))
     dist = int(take(np.int32, 1)[0])
     d0 = orc.extract(frames[0])[1]
     assert dist == int(np.unpackbits(d0[0] ^ d0[1]).sum())                                   # Matcher::DescriptorDistance
     T = take(np.float32, 16).reshape(4, 4)
     assert np.abs(T[:3, :3] - np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)).max() < 1e-4
     assert np.abs(T[:3, 3] - np.array([0.1, -0.2, 0.3], np.float32)).max() < 1e-4
+    T2 = take(np.float32, 16).reshape(4, 4)
+    assert np.array_equal(T2, T)                                                             # Kabsch::Compute(MatrixXf, MatrixXf) = the same call
+    poses = take(np.float32, 16 * n).reshape(n, 4, 4)                                        # Odometry::Compute: T12 * pF1->GetPose() (odometry.cpp:82-86)
+    assert np.array_equal(poses, orc.compose_trajectory(np.stack(T12s)))
+    nl, pw, ph = (int(x) for x in take(np.int32, 3))                                         # ORBextractor::mvImagePyramid[2] of the last frame
+    lvl = take(np.uint8, pw * ph).reshape(ph, pw)
+    assert nl == 8 and np.array_equal(lvl, orc.pyramid(frames[n - 1])[2])
+    # Matcher::KnnMatch(KeyFrame*, Frame&, .): landmark j + 1 at every even feature j of the keyframe, (j % 10 == 0) bad, feature 7 of F2 taken
+    nk = int(take(np.int32, 1)[0]); mk = take(ob.DMATCH_DT, nk); n_out = int(take(np.int32, 1)[0])
+    lm1 = np.array([j + 1 if j % 2 == 0 else 0 for j in range(len(hostd[0][0]))]); lm2 = np.zeros(len(hostd[1][0]), np.int64); lm2[7] = 0x7fff
+    want = orc.knn_match_keyframe(hostd[0][0], hostd[1][0], 0.8, lm1, lambda p: (p - 1) % 10 == 0, lm2)
+    assert mk.tobytes() == want.tobytes() and 0 < nk < len(orc.knn_match(hostd[0][0], hostd[1][0], 0.8, False)) and n_out == nk
+    # Ransac(KeyFrame*, KeyFrame*, matches).Iterate() and its clouds
+    ok2 = int(take(np.int32, 1)[0]); Tb = take(np.float32, 16).reshape(4, 4); nib = int(take(np.int32, 1)[0]); inlb = take(ob.DMATCH_DT, nib)
+    nc = int(take(np.int32, 1)[0]); cs = take(np.float32, nc * 4).reshape(nc, 4); ct = take(np.float32, nc * 4).reshape(nc, 4)
+    m01 = orc.knn_match(hostd[0][0], hostd[1][0], 0.8, True)
+    rb = orc.ransac_iterate(hostd[0][1], hostd[1][1], m01, seed=100, depth_cov=cov)
+    assert ok2 == int(rb["ok"]) and inlb.tobytes() == rb["inliers"].tobytes() and np.abs(Tb - rb["T12"]).max() <= 1e-5
+    ws, wt = orc.ransac_clouds(hostd[0][1], hostd[1][1], m01)
+    assert nc == len(ws) > 20 and np.array_equal(cs, ws) and np.array_equal(ct, wt)
+    assert tuple(int(x) for x in take(np.int32, 3)) == (0, 0, 0)                             # fewer than minInlierTh matches: early return
     th = np.full(9, 20.0)
     for i in range(n):                                                                       # Extractor(FAST, ., ADAPTIVE)
         N = int(take(np.int32, 1)[0]); k = take(ob.KEYPOINT_DT, N)
         assert k.tobytes() == orc.adaptive_detect(frames[i], th, retain_best=1000)[0].tobytes(), f"adaptive frame {i}"
+    Na = int(take(np.int32, 1)[0]); ka = take(ob.KEYPOINT_DT, Na); xa = take(np.float32, Na * 3).reshape(Na, 3); ua = take(np.float32, Na)
+    tha = np.full(9, 20.0)                                                                   # Frame::ExtractFeatures on the adaptive route
+    kref = orc.adaptive_detect(frames[0], tha, retain_best=1000)[0]
+    xref, uref = orc.unproject(kref, depths[0])
+    assert ka.tobytes() == kref.tobytes() and np.array_equal(xa, xref) and np.array_equal(ua, uref)
     assert np.array_equal(take(np.float64, 9), th)
     assert pos == len(buf)
+
+
+@pytest.fixture(scope="module")
+def ocv_demo(ob, tmp_path_factory):
+    """The ORBF_WITH_OPENCV overload set (cv::InputArray / cv::OutputArray / cv::Mat signatures of the reference) compiled against the
+    stand-in header tests/cpp/stub/opencv2/core.hpp — this image has no OpenCV headers."""
+    ob.lib()
+    exe = tmp_path_factory.mktemp("cpp_ocv") / "opencv_signatures"
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tests' / 'cpp' / 'stub'}", "-o", str(exe),
+           str(ROOT / "tests" / "cpp" / "opencv_signatures.cpp"), f"-L{PKG}", "-lorbfront_b200", f"-Wl,-rpath,{PKG}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_opencv_overloads_compile_and_refuse_without_gpu(ocv_demo, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    write_input(tmp_path / "in.raw", np.zeros((1, 480, 640), np.uint8), np.zeros((1, 480, 640), np.uint16))
+    r = subprocess.run([str(ocv_demo), str(tmp_path / "in.raw"), str(tmp_path / "out.raw")], capture_output=True, text=True)
+    assert r.returncode == 3 and "CUDA" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_opencv_overloads_match_oracle(ocv_demo, ob, orc, texture, tmp_path):
+    frame = synth.make_frame(texture, 77)
+    write_input(tmp_path / "in.raw", frame[None], np.zeros((1, 480, 640), np.uint16))
+    r = subprocess.run([str(ocv_demo), str(tmp_path / "in.raw"), str(tmp_path / "out.raw")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = (tmp_path / "out.raw").read_bytes()
+    n = int(np.frombuffer(buf, np.int32, 1, 0)[0])
+    k = np.frombuffer(buf, ob.KEYPOINT_DT, n, 4); d = np.frombuffer(buf, np.uint8, n * 32, 4 + 28 * n).reshape(n, 32)
+    same, dist, kept = (int(x) for x in np.frombuffer(buf, np.int32, 3, 4 + 60 * n))
+    ko, do = orc.extract(frame)
+    assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
+    assert same == 1 and kept == 3 and dist == int(np.unpackbits(do[0] ^ do[1]).sum())
