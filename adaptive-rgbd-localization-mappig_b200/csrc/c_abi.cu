@@ -17,6 +17,43 @@
     } while (0)
 #define TRY(x) do { int r__ = (x); if (r__ != ORBF_OK) return r__; } while (0)
 
+// ---- page-locked staging arena (one-frame-at-a-time calls) ---------------------------------------------------------------
+// arena_begin: start of a call that stages through the arena; waits for the transfers of the previous such call that may still read it.
+static int arena_begin(orbf_context* c, size_t need)
+{
+    if (c->arenaBusy) { ORBF_CUDA(c, cudaEventSynchronize(c->evArena)); c->arenaBusy = false; }
+    if (need > c->arenaCap) {
+        if (c->h_arena) cudaFreeHost(c->h_arena);
+        c->h_arena = nullptr; c->arenaCap = 0;
+        const size_t cap = (need + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+        ORBF_CUDA(c, cudaMallocHost((void**)&c->h_arena, cap));
+        c->arenaCap = cap;
+    }
+    if (!c->evArena) ORBF_CUDA(c, cudaEventCreateWithFlags(&c->evArena, cudaEventDisableTiming));
+    c->arenaUsed = 0;
+    return ORBF_OK;
+}
+static uint8_t* arena_take(orbf_context* c, size_t bytes)
+{
+    uint8_t* p = c->h_arena + c->arenaUsed;
+    c->arenaUsed = (c->arenaUsed + bytes + 255) & ~(size_t)255;
+    return p;
+}
+// marks the arena as read by work queued on `stream` (a later arena_begin waits for it); calls that end with a stream
+// synchronisation do not need it
+static int arena_fence(orbf_context* c, cudaStream_t stream)
+{
+    ORBF_CUDA(c, cudaEventRecord(c->evArena, stream));
+    c->arenaBusy = true;
+    return ORBF_OK;
+}
+static bool is_pageable(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 struct DistanceLess { ORBF_HD bool operator()(const orbf_dmatch& a, const orbf_dmatch& b) const { return a.distance < b.distance; } };
 
 struct StreamSwap {   // runs the launches of a scope on another stream
@@ -183,7 +220,7 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
     // chunked; re-measured after the kernel rewrites: 4.09 ms vs 4.06 ms) — the pipeline exists to hide the PCIe copies of
     // host inputs.
     Pipeline pl(c);
-    TRY(pl.begin(hf && hf->gray));
+    TRY(pl.begin(hf && hf->gray && n > 1));          // a single frame has nothing to overlap: copy and kernels on the caller's stream
     int chunk = pl.active ? c->chunkFrames : n;
     // chunk boundaries: quarter- and half-size chunks at both ends, so that the first kernels start after a short copy and the
     // last copy is followed by a short tail of compute (the link, not the SMs, bounds this path)
@@ -304,6 +341,24 @@ extern "C" int orbf_extract_batch(orbf_context* c, int32_t slot0, int32_t n, con
 {
     CTX_ENTER(c);
     HostFrames hf;
+    if (n == 1 && gray && gray_stride >= c->cfg.width && is_pageable(gray)) {
+        // the per-frame drop-in call (ORBextractor::operator() / Frame::ExtractFeatures): a pageable plane goes through the page-locked
+        // arena (one host memcpy, then a truly asynchronous DMA) instead of the driver's own staged, host-blocking copy
+        const int w = c->cfg.width, h = c->cfg.height;
+        const bool withDepth = depth && depth_stride_elems >= w;
+        TRY(arena_begin(c, (size_t)w * h * (withDepth ? 3 : 1) + 1024));
+        uint8_t* g = arena_take(c, (size_t)w * h);
+        for (int y = 0; y < h; ++y) memcpy(g + (size_t)y * w, gray + (size_t)y * gray_stride, (size_t)w);
+        uint16_t* d = nullptr;
+        if (withDepth) {
+            d = reinterpret_cast<uint16_t*>(arena_take(c, (size_t)w * h * 2));
+            for (int y = 0; y < h; ++y) memcpy(d + (size_t)y * w, depth + (size_t)y * depth_stride_elems, (size_t)w * 2);
+        }
+        TRY(set_host_inputs(c, slot0, 1, g, w, (int64_t)w * h, d, w, (int64_t)w * h, hf));
+        const int r = run_batch(c, slot0, 1, &hf, nullptr);
+        if (r != ORBF_OK) return r;
+        return arena_fence(c, c->stream);
+    }
     TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
     return run_batch(c, slot0, n, &hf, nullptr);
 }
@@ -493,25 +548,25 @@ extern "C" int orbf_download_frame(orbf_context* c, int32_t slot, orbf_keypoint*
 {
     CTX_ENTER(c);
     if (!n_out || slot < 0 || slot >= c->B) return ORBF_ERR_ARG;
-    TRY(orbf_launch_pack_aos(c, slot, 1));
+    if (kps) TRY(orbf_launch_pack_aos(c, slot, 1));
+    // the count and every array at full capacity (76 KB at K = 1056) into page-locked memory, then ONE synchronisation
+    const size_t o = (size_t)slot * c->K, K = (size_t)c->K;
     ORBF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (kps) ORBF_CUDA(c, cudaMemcpyAsync(c->h_kp, c->d_kpAos + o, K * sizeof(orbf_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (desc) ORBF_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc + o * 32, K * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (xyz) {
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz, c->d_ptx + o, K * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + K, c->d_pty + o, K * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + 2 * K, c->d_ptz + o, K * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     const int n = c->h_counts[0];
     *n_out = n;
     if (n > cap) return ORBF_ERR_CAPACITY;
     if (n == 0) return ORBF_OK;
-    const size_t o = (size_t)slot * c->K;
-    if (kps) ORBF_CUDA(c, cudaMemcpyAsync(c->h_kp, c->d_kpAos + o, n * sizeof(orbf_keypoint), cudaMemcpyDeviceToHost, c->stream));
-    if (desc) ORBF_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc + o * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
-    if (xyz) {
-        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz, c->d_ptx + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + c->K, c->d_pty + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        ORBF_CUDA(c, cudaMemcpyAsync(c->h_xyz + 2 * c->K, c->d_ptz + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    }
-    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (kps) memcpy(kps, c->h_kp, n * sizeof(orbf_keypoint));
     if (desc) memcpy(desc, c->h_desc, (size_t)n * 32);
-    if (xyz) for (int i = 0; i < n; ++i) { xyz[3 * i] = c->h_xyz[i]; xyz[3 * i + 1] = c->h_xyz[c->K + i]; xyz[3 * i + 2] = c->h_xyz[2 * c->K + i]; }
+    if (xyz) for (int i = 0; i < n; ++i) { xyz[3 * i] = c->h_xyz[i]; xyz[3 * i + 1] = c->h_xyz[K + i]; xyz[3 * i + 2] = c->h_xyz[2 * K + i]; }
     return ORBF_OK;
 }
 
@@ -609,8 +664,11 @@ static int standalone_knn(orbf_context* c, const uint8_t* q, int nq, const uint8
     // pair slot 0 holds the result; K bounds both sets because the packed key stores a 16-bit index per slot row
     if (nq < 0 || nt < 0 || nq > c->K || nt > 65535) return ORBF_ERR_ARG;
     TRY(ensure_desc_stage(c, std::max(std::max(nq, nt), 1)));
-    if (nq) ORBF_CUDA(c, cudaMemcpyAsync(c->d_qdesc, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
-    if (nt) ORBF_CUDA(c, cudaMemcpyAsync(c->d_tdesc, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
+    // through the page-locked arena: both uploads and the result read-back of the calling function are asynchronous, the call
+    // synchronises once (the arena also has room for the matches that come back: see orbf_knn_match)
+    TRY(arena_begin(c, ((size_t)nq + nt) * 32 + (size_t)c->K * sizeof(orbf_dmatch) + 4096));
+    if (nq) { uint8_t* hq = arena_take(c, (size_t)nq * 32); memcpy(hq, q, (size_t)nq * 32); ORBF_CUDA(c, cudaMemcpyAsync(c->d_qdesc, hq, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream)); }
+    if (nt) { uint8_t* ht = arena_take(c, (size_t)nt * 32); memcpy(ht, t, (size_t)nt * 32); ORBF_CUDA(c, cudaMemcpyAsync(c->d_tdesc, ht, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream)); }
     ms.qdesc = c->d_qdesc; ms.tdesc = c->d_tdesc; ms.qStride = ms.tStride = 0; ms.qCounts = ms.tCounts = nullptr; ms.pairs = nullptr;
     ms.pair0 = 0;
     ms.nq = nq; ms.nt = nt; ms.knn = c->d_knn; ms.rev = c->d_rev; ms.matches = c->d_matches; ms.matchCount = c->d_matchCount;
@@ -656,7 +714,16 @@ extern "C" int orbf_knn_match(orbf_context* c, const uint8_t* q, int32_t nq, con
     TRY(standalone_knn(c, q, nq, t, nt, cross_check != 0, ms));
     TRY(orbf_launch_match_select(c, ms, 1, ratio, cross_check != 0));
     c->lastNPairs = 1; c->pairsFromSlots = false;
-    return orbf_download_matches(c, 0, out, cap, n_out);
+    // count and matches (at most nq of them) into the arena, one synchronisation
+    int* hn = reinterpret_cast<int*>(arena_take(c, sizeof(int)));
+    orbf_dmatch* hm = reinterpret_cast<orbf_dmatch*>(arena_take(c, (size_t)nq * sizeof(orbf_dmatch)));
+    ORBF_CUDA(c, cudaMemcpyAsync(hn, c->d_matchCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(hm, c->d_matches, (size_t)nq * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_out = *hn;
+    if (*hn > cap) return ORBF_ERR_CAPACITY;
+    if (*hn && out) memcpy(out, hm, (size_t)*hn * sizeof(orbf_dmatch));
+    return ORBF_OK;
 }
 
 // Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks: desc holds every landmark's
@@ -1019,15 +1086,27 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
         c->xyzStageRows = rows;
     }
     const int R = c->xyzStageRows;
-    std::vector<float> soa((size_t)R * 3, 0.f);
-    for (int i = 0; i < nsrc; ++i) { soa[i] = src_xyz[3 * i]; soa[R + i] = src_xyz[3 * i + 1]; soa[2 * (size_t)R + i] = src_xyz[3 * i + 2]; }
-    ORBF_CUDA(c, cudaMemcpyAsync(c->d_sxyz, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < ndst; ++i) { soa[i] = dst_xyz[3 * i]; soa[R + i] = dst_xyz[3 * i + 1]; soa[2 * (size_t)R + i] = dst_xyz[3 * i + 2]; }
-    ORBF_CUDA(c, cudaMemcpyAsync(c->d_txyz, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (nm) ORBF_CUDA(c, cudaMemcpyAsync(c->d_matches, m12, nm * sizeof(orbf_dmatch), cudaMemcpyHostToDevice, c->stream));
-    ORBF_CUDA(c, cudaMemcpyAsync(c->d_matchCount, &nm, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int tabN0 = cfg->iterations * (int)cfg->sample_size;
+    // every transfer of the call goes through the page-locked arena: uploads, kernels and read-backs are queued without a host
+    // wait in between and the call synchronises once, before the results are handed to the caller
+    TRY(arena_begin(c, (size_t)R * 24 + (size_t)nm * 3 * sizeof(orbf_dmatch) + (size_t)cfg->iterations * sizeof(orbf_hyp_trace) + (size_t)tabN0 * 8 + 8192));
+    {
+        float* hs = reinterpret_cast<float*>(arena_take(c, (size_t)R * 12)); float* ht = reinterpret_cast<float*>(arena_take(c, (size_t)R * 12));
+        for (int i = 0; i < nsrc; ++i) { hs[i] = src_xyz[3 * i]; hs[R + i] = src_xyz[3 * i + 1]; hs[2 * (size_t)R + i] = src_xyz[3 * i + 2]; }
+        for (int i = 0; i < ndst; ++i) { ht[i] = dst_xyz[3 * i]; ht[R + i] = dst_xyz[3 * i + 1]; ht[2 * (size_t)R + i] = dst_xyz[3 * i + 2]; }
+        for (int k = 0; k < 3; ++k) {          // rows past nsrc / ndst are never indexed (the matches were range-checked above)
+            if (nsrc) ORBF_CUDA(c, cudaMemcpyAsync(c->d_sxyz + (size_t)k * R, hs + (size_t)k * R, (size_t)nsrc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            if (ndst) ORBF_CUDA(c, cudaMemcpyAsync(c->d_txyz + (size_t)k * R, ht + (size_t)k * R, (size_t)ndst * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        }
+        int* hnm = reinterpret_cast<int*>(arena_take(c, sizeof(int)));
+        *hnm = nm;
+        if (nm) {
+            orbf_dmatch* hm = reinterpret_cast<orbf_dmatch*>(arena_take(c, (size_t)nm * sizeof(orbf_dmatch)));
+            memcpy(hm, m12, (size_t)nm * sizeof(orbf_dmatch));
+            ORBF_CUDA(c, cudaMemcpyAsync(c->d_matches, hm, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyHostToDevice, c->stream));
+        }
+        ORBF_CUDA(c, cudaMemcpyAsync(c->d_matchCount, hnm, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     c->pairsFromSlots = false; c->lastNPairs = 1;
     const int tabN = cfg->iterations * (int)cfg->sample_size;
     int* dTab = nullptr;
@@ -1038,8 +1117,9 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
             ORBF_CUDA(c, cudaMalloc((void**)&c->d_userSamples, (size_t)tabN * sizeof(int)));
             c->userSamplesCap = tabN;
         }
-        ORBF_CUDA(c, cudaMemcpyAsync(c->d_userSamples, sample_table, (size_t)tabN * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+        int* htab = reinterpret_cast<int*>(arena_take(c, (size_t)tabN * sizeof(int)));
+        memcpy(htab, sample_table, (size_t)tabN * sizeof(int));
+        ORBF_CUDA(c, cudaMemcpyAsync(c->d_userSamples, htab, (size_t)tabN * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         dTab = c->d_userSamples;
     }
     const orbf_ransac_config& cf = *cfg;     // standalone: depth_cov < 0 latches within this call only (one oracle call with depth_cov < 0)
@@ -1048,12 +1128,24 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
     rs.tx = c->d_txyz; rs.ty = c->d_txyz + R; rs.tz = c->d_txyz + 2 * (size_t)R;
     rs.slotStride = 0; rs.pairs = nullptr; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount; rs.nsrc = nsrc; rs.ndst = ndst;
     TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, /*standalone=*/true, /*fullTable=*/sample_table_out != nullptr));
-    TRY(orbf_download_ransac(c, 0, out, inliers_out, cap));
-    if (hyp_trace) ORBF_CUDA(c, cudaMemcpyAsync(hyp_trace, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
-    if (good_sorted_out && out->n_good > 0)
-        ORBF_CUDA(c, cudaMemcpyAsync(good_sorted_out, c->d_good, (size_t)out->n_good * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
-    if (sample_table_out) ORBF_CUDA(c, cudaMemcpyAsync(sample_table_out, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // results: everything the caller asked for into the arena (inliers / sorted matches at their upper bound nm), one synchronisation
+    orbf_ransac_result* hres = reinterpret_cast<orbf_ransac_result*>(arena_take(c, sizeof(orbf_ransac_result)));
+    orbf_dmatch* hinl = inliers_out && nm ? reinterpret_cast<orbf_dmatch*>(arena_take(c, (size_t)nm * sizeof(orbf_dmatch))) : nullptr;
+    orbf_dmatch* hgood = good_sorted_out && nm ? reinterpret_cast<orbf_dmatch*>(arena_take(c, (size_t)nm * sizeof(orbf_dmatch))) : nullptr;
+    orbf_hyp_trace* hhyp = hyp_trace ? reinterpret_cast<orbf_hyp_trace*>(arena_take(c, (size_t)cfg->iterations * sizeof(orbf_hyp_trace))) : nullptr;
+    int* htabOut = sample_table_out ? reinterpret_cast<int*>(arena_take(c, (size_t)tabN * sizeof(int))) : nullptr;
+    ORBF_CUDA(c, cudaMemcpyAsync(hres, c->d_rres, sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
+    if (hinl) ORBF_CUDA(c, cudaMemcpyAsync(hinl, c->d_inliers, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+    if (hgood) ORBF_CUDA(c, cudaMemcpyAsync(hgood, c->d_good, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+    if (hhyp) ORBF_CUDA(c, cudaMemcpyAsync(hhyp, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
+    if (htabOut) ORBF_CUDA(c, cudaMemcpyAsync(htabOut, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = *hres;
+    if (inliers_out && out->n_inliers > cap) return ORBF_ERR_CAPACITY;
+    if (hinl && out->n_inliers > 0) memcpy(inliers_out, hinl, (size_t)out->n_inliers * sizeof(orbf_dmatch));
+    if (hgood && out->n_good > 0) memcpy(good_sorted_out, hgood, (size_t)out->n_good * sizeof(orbf_dmatch));
+    if (hhyp) memcpy(hyp_trace, hhyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace));
+    if (htabOut) memcpy(sample_table_out, htabOut, (size_t)tabN * sizeof(int));
     return ORBF_OK;
 }
 

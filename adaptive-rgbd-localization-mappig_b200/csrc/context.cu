@@ -370,6 +370,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->d_peerDesc = nullptr; c->d_peerCount = nullptr; c->nPeers = 0; c->peerKf = 0;
     for (void*& q : c->peerOpened) q = nullptr;
     c->h_kp = nullptr; c->h_desc = nullptr; c->h_xyz = nullptr; c->h_counts = nullptr;
+    c->h_arena = nullptr; c->arenaCap = 0; c->arenaUsed = 0; c->evArena = nullptr; c->arenaBusy = false;
     auto cu = [&](cudaError_t e3, const char* w) { if (e3 != cudaSuccess) { orbf_cuda_fail(c, e3, w, __FILE__, __LINE__); return false; } return true; };
     if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice), "cells")) return fail(ORBF_ERR_CUDA);
@@ -406,6 +407,8 @@ extern "C" int orbf_destroy(orbf_context* c)
         c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount, c->d_cellRegion, c->d_regionTh, c->d_regionState, c->d_regionLog };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < c->L; ++l) { if (c->d_pyr[l]) cudaFree(c->d_pyr[l]); if (c->d_blur[l]) cudaFree(c->d_blur[l]); }
+    if (c->h_arena) cudaFreeHost(c->h_arena);
+    if (c->evArena) cudaEventDestroy(c->evArena);
     if (c->h_kp) cudaFreeHost(c->h_kp);
     if (c->h_desc) cudaFreeHost(c->h_desc);
     if (c->h_xyz) cudaFreeHost(c->h_xyz);

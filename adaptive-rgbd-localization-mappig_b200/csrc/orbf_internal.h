@@ -141,6 +141,9 @@ struct orbf_context {
     orbf_keypoint* d_kpAos;   // staging for D2H in cv::KeyPoint layout
     // host staging (pinned)
     orbf_keypoint* h_kp; uint8_t* h_desc; float* h_xyz; int* h_counts;
+    // page-locked staging arena of the one-frame-at-a-time calls (orbf_extract*, orbf_knn_match, orbf_ransac_iterate): pageable caller
+    // buffers are copied through it so that every transfer of a call is asynchronous and the call synchronises once
+    uint8_t* h_arena; size_t arenaCap, arenaUsed; cudaEvent_t evArena; bool arenaBusy;
 
     // matching (pair slots)
     int* d_pairs;             // [P][2]

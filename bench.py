@@ -502,10 +502,45 @@ def latency_arm(ob, local, frames, depths, n):
         prev = (d, xyz)
     ctx.close()
     q = lambda a, p: float(np.percentile(np.array(a) * 1e3, p))
-    return {"unit": "ms per frame (extract + match with the previous frame + RANSAC), one frame at a time, pageable host in / host out",
-            "frames": len(ts["total"]), "p50": q(ts["total"], 50), "p99": q(ts["total"], 99), "mean": float(np.mean(ts["total"]) * 1e3),
-            "p50_by_call": {k: q(v, 50) for k, v in ts.items() if k != "total"},
-            "calls": "orbf_extract_batch(n=1) + orbf_download_frame, orbf_knn_match, orbf_ransac_iterate through ctypes"}
+    py = {"frames": len(ts["total"]), "p50": q(ts["total"], 50), "p99": q(ts["total"], 99), "mean": float(np.mean(ts["total"]) * 1e3),
+          "p50_by_call": {k: q(v, 50) for k, v in ts.items() if k != "total"},
+          "calls": "orbf_extract_batch(n=1) + orbf_download_frame, orbf_knn_match, orbf_ransac_iterate through ctypes (numpy allocations included)"}
+    out = {"unit": "ms per frame (extract + match with the previous frame + RANSAC), one frame at a time, pageable host in / host out"}
+    cpp = latency_cpp(frames, depths, n)
+    if cpp is not None:
+        out.update(cpp)
+        out["calls"] = ("C++ host mirror (include/orbfront_host.hpp, tools/latency_cpp.cpp): Frame::ExtractFeatures, Matcher::KnnMatch(last, cur, cross-check), "
+                        "Odometry::Compute (Ransac::Iterate + clouds + composition rule), std::chrono around each call")
+        out["python_ctypes"] = py
+    else:
+        out.update(py)
+    return out
+
+
+def latency_cpp(frames, depths, n):
+    """Builds tools/latency_cpp.cpp against the C++ host mirror and runs it on the first n frames; None when no host compiler is there."""
+    import shutil
+    import struct
+    import tempfile
+    if not shutil.which("g++"):
+        return None
+    pkg = ROOT / "adaptive-rgbd-localization-mappig_b200"
+    with tempfile.TemporaryDirectory() as td:
+        exe = Path(td) / "latency_cpp"
+        r = subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT / 'include'}", "-o", str(exe), str(ROOT / "tools" / "latency_cpp.cpp"), f"-L{pkg}",
+                            "-lorbfront_b200", f"-Wl,-rpath,{pkg}"], capture_output=True, text=True)
+        if r.returncode != 0:
+            return None
+        raw = Path(td) / "in.raw"
+        with open(raw, "wb") as f:
+            f.write(struct.pack("3i", n, W, H)); f.write(np.ascontiguousarray(frames[:n]).tobytes()); f.write(np.ascontiguousarray(depths[:n]).tobytes())
+        r = subprocess.run([str(exe), str(raw)], capture_output=True, text=True)
+        if r.returncode != 0:
+            return None
+        try:
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            return None
 
 
 def fast_smem_view(F, ms, sm_mhz):
