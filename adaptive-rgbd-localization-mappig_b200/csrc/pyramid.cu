@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int TL_W = 128, TL_WARPS = 4, TL_THREADS = TL_WARPS * 32;
-constexpr int BL_H = 35, BL_BW = 160, BL_BH = BL_H + 6, BL_TILE_BYTES = ((BL_BW * BL_BH + 127) / 128) * 128;   // 5 x 7-row ring turns
+constexpr int BL_H = 36, BL_BW = 160, BL_BH = BL_H + 6, BL_TILE_BYTES = ((BL_BW * BL_BH + 127) / 128) * 128;   // 6 turns of the 6-entry row-pair ring
 constexpr int RS_H = 16;
 
 struct StageParams {
@@ -95,20 +95,36 @@ __global__ void __launch_bounds__(TL_THREADS) blur_tile_kernel(const __grid_cons
     uint8_t* q = P.dst[level] + (long long)slot * P.dstFrameStride[level] + (long long)y0 * P.dstPitch[level] + x;
     const int pitch = P.dstPitch[level];
     const bool colOk = x < w;
-    uint32_t ring[7][4];
+    // Vertical pass on ROW PAIRS: ring entry j holds, per pixel, the horizontal sums (< 2^16) of tile rows r and r + 1 packed into one
+    // word, so an output row is three IDP.2A (taps 18,34 | 48,56 | 48,34 against the pairs of rows y..y+5) on top of 18 * row y+6 +
+    // rounding: 4 multiply-adds + 1 PRMT (the new pair) per pixel instead of 3 adds + 4 multiply-adds.
+    uint32_t pr[6][4], prevH[4];
+    {
+        uint32_t h0[4], h1[4];
+        hrow7(rowp, h0);
 #pragma unroll
-    for (int r = 0; r < 6; ++r) hrow7(rowp + r * (BL_BW / 4), ring[r]);
+        for (int r = 0; r < 5; ++r) {
+            hrow7(rowp + (r + 1) * (BL_BW / 4), h1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { pr[r][k] = __byte_perm(h0[k], h1[k], 0x5410); h0[k] = h1[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) prevH[k] = h0[k];                 // tile row 5
+    }
 #pragma unroll 1
-    for (int turn = 0; turn < BL_H / 7; ++turn) {
+    for (int turn = 0; turn < BL_H / 6; ++turn) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int row = turn * 7 + i;
-            hrow7(rowp + (row + 6) * (BL_BW / 4), ring[(i + 6) % 7]);
+        for (int i = 0; i < 6; ++i) {
+            const int row = turn * 6 + i;                             // output row: tile rows row .. row + 6; pr[(row + j) % 6] = rows (row + j, row + j + 1)
+            uint32_t hn[4];
+            hrow7(rowp + (row + 6) * (BL_BW / 4), hn);
             uint32_t acc[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                acc[k] = 18u * (ring[i % 7][k] + ring[(i + 6) % 7][k]) + 34u * (ring[(i + 1) % 7][k] + ring[(i + 5) % 7][k])
-                    + 48u * (ring[(i + 2) % 7][k] + ring[(i + 4) % 7][k]) + 56u * ring[(i + 3) % 7][k] + 32768u;
+            for (int k = 0; k < 4; ++k) {
+                acc[k] = __dp2a_lo(pr[i % 6][k], 0x2212u, __dp2a_lo(pr[(i + 2) % 6][k], 0x3830u, __dp2a_lo(pr[(i + 4) % 6][k], 0x2230u, 18u * hn[k] + 32768u)));
+                pr[(i + 5) % 6][k] = __byte_perm(prevH[k], hn[k], 0x5410);          // rows (row + 5, row + 6): first used by the next output row
+                prevH[k] = hn[k];
+            }
             // acc < 2^24: the rounded result is byte 2 of each accumulator
             const uint32_t packed = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
             if (colOk && y0 + row < h) *reinterpret_cast<uint32_t*>(q) = packed;
@@ -169,17 +185,23 @@ __global__ void __launch_bounds__(TL_THREADS) resize_tile_kernel(const __grid_co
     uint32_t hA[4], hB[4];
     int rowB = -1;                                                   // tile row held in hB
     const int rows = min(RS_H, h - y0);
+    // row coefficients of the tile's RS_H output rows: lane i fetches row i once, the loop takes them by shuffle (no dependent global
+    // load inside the loop)
+    static_assert(RS_H <= 32, "one lane per output row");
+    const ResizeCoef myRow = ty[min(y0 + lane, h - 1)];
+    const int myOfs = myRow.ofs - ys;
+    const uint32_t myAB = (uint32_t)(uint16_t)myRow.a0 | ((uint32_t)(uint16_t)myRow.a1 << 16);
 #pragma unroll 1
     for (int i = 0; i < rows; ++i) {
-        const ResizeCoef cy = ty[y0 + i];
-        const int r = cy.ofs - ys;
+        const int r = __shfl_sync(0xffffffffu, myOfs, i);
+        const uint32_t ab = __shfl_sync(0xffffffffu, myAB, i);
         if (r == rowB) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) hA[k] = hB[k];
         } else RS_HROW(r, hA);
         RS_HROW(r + 1, hB);                                            // r + 1 is inside the box; past the source edge its weight is 0
         rowB = r + 1;
-        const uint32_t b0 = (uint32_t)cy.a0 << 16, b1 = (uint32_t)cy.a1 << 16;
+        const uint32_t b0 = ab << 16, b1 = ab & 0xFFFF0000u;
         uint32_t v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = (__umulhi(hA[k], b0) + __umulhi(hB[k], b1) + 2u) >> 2;     // (b*(h>>4))>>16 == umulhi(h>>4, b<<16)
