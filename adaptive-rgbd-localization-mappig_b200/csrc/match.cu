@@ -25,6 +25,13 @@
 //                folded through shared memory once per chunk.
 // History: a POPC/LOP3 kernel (integer-ALU bound, 0.81 ms per 511 pairs), then mma.sync IMMA s8 (0.43 ms; warp-level MMAs block
 // the issue port ~6 of every 8.3 clk, tools/bmma_probe.cu), now tcgen05 (tools/umma_probe.cu pins the descriptor fields).
+// Round 2 measured two restructurings against this kernel (0.255 ms per 511 pairs) and kept neither: (a) 256 rows per CTA with the
+// cross-check as a second, transposed product with a top-1 epilogue instead of the butterfly — 0.263 ms: the transposed role repeats
+// the operand expansion, so the ALU work per pair stays the same (~3.0e5 warp instructions) while the tensor work doubles; (b) the
+// same with one CTA per SM and double-buffered column tile + accumulators (MMAs of chunk c + 1 issued before the epilogue of chunk c)
+// — 0.359 ms: 16 warps per SM do not hide the TMEM-load and barrier latencies.  What ncu shows for all variants: tensor-active % +
+// ALU-active % ~ 100 %, i.e. the two co-resident CTAs run in lockstep (the tensor pipe serves both CTAs' MMAs interleaved, then both
+// run their epilogues), so the kernel time is T_tensor + T_alu and only less ALU work per pair makes it faster.
 #include "orbf_internal.h"
 
 namespace {
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
         // the train tile's 9th K step depends on the column only: written once for full chunks (a short last chunk rewrites it)
         bias_chunks(sB, tid, (64u - (uint32_t)((tid & 127) >> 1)) | (127u << 8) | (2u << 16) | (1u << 24));
     }
+    __syncthreads();        // a short first chunk rewrites these column codes from OTHER threads (below): order the two writes
     // this thread's query row = TMEM lane 32 * quarter + lane; two threads (colHalf 0 / 1) share a row
     const int row = qBase + quarter * 32 + lane;
     const bool rowValid = row < nq;
