@@ -553,6 +553,27 @@ def fast_smem_view(F, ms, sm_mhz):
             "frac": ach / (148 * clk), "source": "profiles/r2i_fast_kernel.txt (ncu --set full of this kernel at 128 frames)"}
 
 
+def int_pipe_view(F, stage_ms, sm_mhz):
+    """The integer-pipe view of the three stencil stages (north star: '>= 60 % of the HBM or integer-pipe roofline per stage').  Every
+    integer pipe of a B200 SM issues 64 lanes / clk (profiles/int_pipe_peaks.json, tools/pipe_bench.cu: LOP3, IADD3, VIMNMX, IDP.4A, IMAD
+    all 64 / clk / SM).  algorithmic = thread-level operations the stage's arithmetic needs on its binding pipe per pixel, derived in
+    DESIGN.md section 4.  frac = algorithmic ops/s / peak."""
+    clk = (sm_mhz or 1965.0) * 1e6
+    peak = 64.0 * 148 * clk
+    px = 950_532 * F
+    rows = {"blur7": ("IMAD / IDP pipe (ncu: math-pipe throttle is the top stall; issue slots 72 %)", 5.25,
+                      "7 IDP.4A (28 horizontal MACs / 4) + 14 IDP.2A (28 vertical MACs / 2) per 4 pixels; the kernel issues 10 + 12 + 4 per 4 pixels on 42 rows per 36"),
+            "fast_cell": ("ALU pipe (ncu: 57 % busy; the kernel is bound by the shared-memory data pipe, see fast_cell_smem)", 9.6,
+                          "pretest 8 VABSDIFF4 + 8 IADD + 8 LOP3 per 4 pixels = 6 / px, strength 80 packed min / max per 2 survivors x 8.3 % = 3.3 / px, NMS 8 compares x 3.6 % = 0.3 / px"),
+            "pyr_resize": ("IMAD / IDP pipe (ncu: ALU pipe 48 %, issue slots 68 %, warps active 61 %)", 3.2,
+                           "per destination pixel of levels 1..7 (643,332 px / frame): 1.2 source rows x 1 IDP.2A + 2 IMAD.HI")}
+    out = {"peak_lane_ops_per_s_per_pipe": peak, "peak_source": "measured 64 lanes / clk / SM for every integer pipe (profiles/int_pipe_peaks.json)"}
+    for k, (pipe, alg, how) in rows.items():
+        n = (643_332 if k == "pyr_resize" else 950_532) * F
+        out[k] = {"pipe": pipe, "algorithmic_ops_per_px": alg, "frac": alg * n / (stage_ms[k] * 1e-3) / peak, "how": how}
+    return out
+
+
 def ransac_view(summ, stage_ms):
     """unit = hypothesis x pair Mahalanobis evaluation (~150 f64 flops).  Counted as the reference's loop would execute them at
     least: one scoring pass over the pair's good matches per VALID hypothesis (the <= 19 refit passes per hypothesis are not counted), over
@@ -794,6 +815,7 @@ def main():
                                    "frac_of_hbm": FRAME_BYTES * F / (ms * 1e-3) / 1e9 / peak},
                     "hamming_knn2": knn2_view(fc, stage_ms["hamming_knn2"]),
                     "fast_cell_smem": fast_smem_view(F, stage_ms["fast_cell"], clocks.get("sm_mhz")),
+                    "int_pipe": int_pipe_view(F, stage_ms, clocks.get("sm_mhz")),
                     "ransac": ransac_view(summ, stage_ms)}
         cpu = None; parity = None; latency = None
         if world == 1 and args.latency_frames > 0:
