@@ -27,7 +27,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int orbf_tma_encode_u8(orbf_context* ctx, CUtensorMap* out, const void* base, int w, int h, int frames, long long pitch,
-    long long frameStride, int boxW, int boxH)
+    long long frameStride, int boxW, int boxH, bool swizzle64)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -39,12 +39,13 @@ int orbf_tma_encode_u8(orbf_context* ctx, CUtensorMap* out, const void* base, in
         fn = (EncodeTiledFn)p;
     }
     if (((uintptr_t)base & 15) || (pitch & 15) || (frameStride & 15) || (boxW & 15) || boxW > 256 || boxH > 256) return ORBF_ERR_ALIGNMENT;
+    if (swizzle64 && boxW != 64) return ORBF_ERR_ALIGNMENT;
     const cuuint64_t gdim[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames };
     const cuuint64_t gstride[2] = { (cuuint64_t)pitch, (cuuint64_t)frameStride };
     const cuuint32_t box[3] = { (cuuint32_t)boxW, (cuuint32_t)boxH, 1u };
     const cuuint32_t estr[3] = { 1u, 1u, 1u };
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[96];
         snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -498,8 +499,11 @@ int orbf_refresh_maps(orbf_context* c)
             if (l + 1 < c->L)
                 ENC(c->tmResize[l + 1], c->d_pyr[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, c->rsBW[l + 1], c->rsBH[l + 1]);
         }
-        for (int l = 0; l < c->L; ++l)
-            ENC(c->tmPatchBlur[l], c->d_blur[l], l, c->B, c->lg[l].pitch, (long long)c->lg[l].plane, ORBF_PATCH_BW, ORBF_PATCH_BH);
+        for (int l = 0; l < c->L; ++l) {     // the descriptor windows arrive 64B-swizzled (describe.cu: bank spreading of the rBRIEF gathers)
+            const int r__ = orbf_tma_encode_u8(c, &c->tmPatchBlur[l], c->d_blur[l], c->lg[l].w, c->lg[l].h, c->B, c->lg[l].pitch, (long long)c->lg[l].plane,
+                ORBF_PATCH_BW, ORBF_PATCH_BH, true);
+            if (r__ != ORBF_OK) return r__;
+        }
         c->tmStaticReady = true;
     }
     if (c->tm0Base != c->cur_gray || c->tm0Pitch != c->cur_grayPitch || c->tm0FrameStride != c->cur_grayFrameStride || c->tm0Frames != c->cur_n) {

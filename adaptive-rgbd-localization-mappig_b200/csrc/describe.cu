@@ -62,6 +62,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 constexpr int DS_WARPS = 4, DS_KPW = 16;     // keypoints per warp: window of keypoint k+1 is in flight while keypoint k is computed
 constexpr int DS_WIN_BYTES = (ORBF_PATCH_BW * ORBF_PATCH_BH + 127) / 128 * 128;     // TMA destinations: 128-byte aligned
 
+static_assert(DS_WIN_BYTES % 512 == 0 && ORBF_PATCH_BW == 64, "the descriptor window is loaded with CU_TENSOR_MAP_SWIZZLE_64B");
+
 struct KpLoc { int level, x, y, score; };
 
 // keypoint i of the frame (level-major, quadtree list order inside a level): its level and integer level coordinates
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     // per warp, double buffered: the keypoint's 31 x 48 window of the raw level (orientation disc) and its 39 x 64 window of the
     // blurred level (descriptor), fetched by two TMA box loads — ~70 sectors instead of ~450 scattered byte gathers through L1
     __shared__ __align__(128) uint8_t sRaw[DS_WARPS][2][DS_RAW_BYTES];
-    __shared__ __align__(128) uint8_t sBlur[DS_WARPS][2][DS_WIN_BYTES];
+    __shared__ __align__(512) uint8_t sBlur[DS_WARPS][2][DS_WIN_BYTES];    // 64B-swizzled by the TMA (512-byte swizzle atoms)
     __shared__ __align__(8) uint64_t sBar[DS_WARPS][2];
     for (int i = threadIdx.x; i < 256; i += DS_WARPS * 32) sPat[i] = g_patF[i];
     if (threadIdx.x < 16) sCoef[threadIdx.x] = g_icCoef[threadIdx.x];
@@ -194,7 +196,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         const float ar = __fmul_rn(angle, factorPI);
         const float a = replay::glibc_cosf(ar), b = replay::glibc_sinf(ar);     // std::cos(float) / std::sin(float) of the reference: libm's cosf / sinf
         const int cx0 = x - ((x - ORBF_EDGE) & ~15);                      // window column of the keypoint
-        const uint8_t* cb = sBlur[warp][buf] + ORBF_EDGE * ORBF_PATCH_BW + cx0;
+        // The window is stored 64B-swizzled (chunk of 16 bytes ^= (row >> 1) & 3): with the plain 64-byte pitch all rows of one parity
+        // share their banks and a warp-wide gather took ~4.8 wavefronts; swizzled, a column's rows spread over 8 bank groups.
+        const uint8_t* wb = sBlur[warp][buf];
+        auto at = [&](int r, int cc) { const int row = r + ORBF_EDGE, col = cc + cx0; return (int)wb[row * ORBF_PATCH_BW + (col ^ ((row & 6) << 3))]; };
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
             const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.x, a), __fmul_rn(w.y, b)), kMagic)) - 0x4B400000;
             const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(w.z, b), __fmul_rn(w.w, a)), kMagic)) - 0x4B400000;
             const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(w.z, a), __fmul_rn(w.w, b)), kMagic)) - 0x4B400000;
-            const int t0 = cb[r0 * ORBF_PATCH_BW + c0], t1 = cb[r1 * ORBF_PATCH_BW + c1];
+            const int t0 = at(r0, c0), t1 = at(r1, c1);
             val |= (t0 < t1) << k;
         }
         P.desc[o * 32 + lane] = (uint8_t)val;

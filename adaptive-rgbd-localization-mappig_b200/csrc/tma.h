@@ -12,8 +12,10 @@ struct orbf_context;
 // Encodes a rank-3 u8 map: dims (w, h, frames), strides (pitch, frameStride) bytes, box (boxW, boxH, 1).
 // boxW must be a multiple of 16 and <= 256, boxH <= 256; base 16-byte aligned, strides multiples of 16, and the x
 // coordinate of every box load a multiple of 16 (a misaligned start traps as 'illegal instruction', tools/tma_probe.cu).
+// swizzle64: CU_TENSOR_MAP_SWIZZLE_64B (box width must be 64 bytes, destination 512-byte aligned): the 16-byte chunk index of a row
+// is XORed with bits 7..8 of the shared-memory address, i.e. with (row >> 1) & 3 — rows of one parity no longer share their banks.
 int orbf_tma_encode_u8(orbf_context* ctx, CUtensorMap* out, const void* base, int w, int h, int frames, long long pitch,
-    long long frameStride, int boxW, int boxH);
+    long long frameStride, int boxW, int boxH, bool swizzle64 = false);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
