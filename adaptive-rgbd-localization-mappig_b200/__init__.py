@@ -529,6 +529,22 @@ class Context:
                                              C.byref(cfg), _p(thresh), _p(used), _p(found)), "extract_adapted")
         return used, found
 
+    def extract_adapted_videos(self, videos, thresh, slot0=0, **kw):
+        """V independent videos advancing together: videos [V, T, H, W] u8, thresh [V, grid*grid] float64 (updated in place).  Frame t of
+        video v lands in slot slot0 + t * V + v.  Returns (region_th [T, V, g2], region_found [T, V, g2])."""
+        cfg = AdaptiveConfig()
+        lib().orbf_default_adaptive_config(C.byref(cfg))
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        videos = np.ascontiguousarray(videos, np.uint8)
+        V, T, h, w = videos.shape
+        g2 = cfg.grid * cfg.grid
+        assert thresh.dtype == np.float64 and thresh.shape == (V, g2) and thresh.flags.c_contiguous
+        used = np.zeros((T, V, g2), np.int32); found = np.zeros((T, V, g2), np.int32)
+        self._chk(lib().orbf_extract_adapted_videos(self._h, slot0, V, T, _p(videos), C.c_int64(w), C.c_int64(w * h), C.c_int64(T * w * h), None, C.c_int64(w),
+                                                    C.c_int64(w * h), C.c_int64(T * w * h), C.byref(cfg), _p(thresh), _p(used), _p(found)), "extract_adapted_videos")
+        return used, found
+
     # ---- keyframe store ----
     def kfdb_reserve(self, n):
         self._chk(lib().orbf_kfdb_reserve(self._h, n), "kfdb_reserve")

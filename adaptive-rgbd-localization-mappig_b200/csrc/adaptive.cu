@@ -288,6 +288,7 @@ struct RegionParams {
     int grid, width, height, minFeat, maxFeat, minThFast;
     double minTh, maxTh, inc, dec;
     int* regionTh; double* state; int* log;         // log [frame][2][grid * grid]: thresholds used, keypoints found
+    int nVideos;                                    // block v: slot + v, frame log row frameIdx + v, state / thresholds of video v (25 entries each)
 };
 
 __global__ void __launch_bounds__(256) region_control_kernel(const RegionParams P)
@@ -296,9 +297,10 @@ __global__ void __launch_bounds__(256) region_control_kernel(const RegionParams 
     const int tid = threadIdx.x, g2 = P.grid * P.grid;
     if (tid < AD_MAX_CELLS) sFound[tid] = 0;
     __syncthreads();
+    const int v = blockIdx.x, slot = P.slot + v;
     for (int l = 0; l < P.L; ++l) {
-        const int n = P.lkpCount[P.slot * ORBF_MAX_LEVELS + l];
-        const uint32_t* kp = P.lkp + (long long)P.slot * P.kpStageTotal + P.kpOff[l];
+        const int n = P.lkpCount[slot * ORBF_MAX_LEVELS + l];
+        const uint32_t* kp = P.lkp + (long long)slot * P.kpStageTotal + P.kpOff[l];
         for (int i = tid; i < n; i += 256) {
             const uint32_t key = kp[i];
             float x = (float)((int)(key & 0x7FF) + ORBF_MINB), y = (float)((int)((key >> 11) & 0x7FF) + ORBF_MINB);
@@ -310,19 +312,20 @@ __global__ void __launch_bounds__(256) region_control_kernel(const RegionParams 
     __syncthreads();
     if (tid < g2) {
         const int found = sFound[tid];
-        int* log = P.log + (long long)P.frameIdx * 2 * g2;
-        log[tid] = P.regionTh[tid]; log[g2 + tid] = found;
-        double st = P.state[tid];
+        int* log = P.log + (long long)(P.frameIdx + v) * 2 * g2;
+        int* regionTh = P.regionTh + v * AD_MAX_CELLS; double* state = P.state + v * AD_MAX_CELLS;
+        log[tid] = regionTh[tid]; log[g2 + tid] = found;
+        double st = state[tid];
         if (found < P.minFeat) { st *= P.dec; if (st < P.minTh) st = P.minTh; }
         else if (found > P.maxFeat) { st *= P.inc; if (st > P.maxTh) st = P.maxTh; }
-        P.state[tid] = st;
-        P.regionTh[tid] = max(P.minThFast, min(254, (int)st));
+        state[tid] = st;
+        regionTh[tid] = max(P.minThFast, min(254, (int)st));
     }
 }
 
 }  // namespace
 
-int orbf_launch_region_control(orbf_context* c, int slot, int frameIdx, const orbf_adaptive_config& cfg)
+int orbf_launch_region_control(orbf_context* c, int slot, int frameIdx, const orbf_adaptive_config& cfg, int nVideos)
 {
     RegionParams P;
     P.lkp = c->d_lkp; P.lkpCount = c->d_lkpCount; P.kpStageTotal = c->kpStageTotal; P.L = c->L; P.slot = slot; P.frameIdx = frameIdx;
@@ -330,14 +333,15 @@ int orbf_launch_region_control(orbf_context* c, int slot, int frameIdx, const or
     P.grid = cfg.grid; P.width = c->cfg.width; P.height = c->cfg.height; P.minFeat = cfg.min_features; P.maxFeat = cfg.max_features;
     P.minThFast = c->cfg.min_th_fast; P.minTh = cfg.min_th; P.maxTh = cfg.max_th; P.inc = cfg.inc; P.dec = cfg.dec;
     P.regionTh = c->d_regionTh; P.state = c->d_regionState; P.log = c->d_regionLog;
-    region_control_kernel<<<1, 256, 0, c->stream>>>(P);
+    P.nVideos = nVideos;
+    region_control_kernel<<<nVideos, 256, 0, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }
 
 // region of every FAST cell for a grid x grid partition: that of the cell's first scored pixel mapped to the image (the same float
 // product and integer division as the oracle's definition), and room for nFrames log rows
-int orbf_region_tables(orbf_context* c, int grid, int nFrames)
+int orbf_region_tables(orbf_context* c, int grid, int nFrames, int nVideos)
 {
     const int g2 = grid * grid;
     if (c->cellRegionGrid != grid) {
@@ -349,11 +353,19 @@ int orbf_region_tables(orbf_context* c, int grid, int nFrames)
             reg[i] = (uint8_t)(ry * grid + rx);
         }
         if (!c->d_cellRegion) ORBF_CUDA(c, cudaMalloc((void**)&c->d_cellRegion, std::max<size_t>(reg.size(), 1)));
-        if (!c->d_regionTh) ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionTh, AD_MAX_CELLS * sizeof(int)));
-        if (!c->d_regionState) ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionState, AD_MAX_CELLS * sizeof(double)));
+
         ORBF_CUDA(c, cudaMemcpyAsync(c->d_cellRegion, reg.data(), reg.size(), cudaMemcpyHostToDevice, c->stream));
         ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
         c->cellRegionGrid = grid;
+    }
+    if (nVideos > c->regionVideos) {
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_regionTh) cudaFree(c->d_regionTh);
+        if (c->d_regionState) cudaFree(c->d_regionState);
+        c->d_regionTh = nullptr; c->d_regionState = nullptr; c->regionVideos = 0;
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionTh, (size_t)nVideos * AD_MAX_CELLS * sizeof(int)));
+        ORBF_CUDA(c, cudaMalloc((void**)&c->d_regionState, (size_t)nVideos * AD_MAX_CELLS * sizeof(double)));
+        c->regionVideos = nVideos;
     }
     if (nFrames * 2 * g2 > c->regionLogCap) {
         ORBF_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -403,48 +403,84 @@ extern "C" int orbf_extract_batch_bgr(orbf_context* c, int32_t slot0, int32_t n,
     return run_batch(c, slot0, n, nullptr, nullptr);
 }
 
-// BASELINE config 4, 8-level variant (defined by the oracle's orc_extract_adapted): ORB extraction of n host
-// frames, in order, with iniThFAST adapted per region of a grid x grid partition by controllers that carry their state from frame to
+// BASELINE config 4, 8-level variant (defined by the oracle's orc_extract_adapted): ORB extraction of host frames,
+// in video order, with iniThFAST adapted per region of a grid x grid partition by controllers that carry their state from frame to
 // frame.  The pyramid, blur and descriptor stages run batched over all frames; FAST -> quadtree -> controller step form a chain per
-// frame (frame i + 1's thresholds depend on the keypoints frame i returned), enqueued back to back without touching the host.
-extern "C" int orbf_extract_adapted(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
-    const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, const orbf_adaptive_config* cfg, double* thresh,
-    int32_t* region_th, int32_t* region_found)
+// frame (frame t + 1's thresholds depend on the keypoints frame t returned), enqueued back to back without touching the host.  With
+// V independent videos (cameras / sequences) the chain has T links of V frames each: frame t of video v lives in slot slot0 + t * V + v.
+static int extract_adapted_impl(orbf_context* c, int slot0, int V, int T, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
+    int64_t gray_video_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, int64_t depth_video_stride_elems,
+    const orbf_adaptive_config* cfg, double* thresh, int32_t* region_th, int32_t* region_found)
 {
-    CTX_ENTER(c);
-    if (!cfg || !thresh || cfg->grid < 1 || cfg->grid > 5) return ORBF_ERR_ARG;
-    const int g2 = cfg->grid * cfg->grid;
+    if (!cfg || !thresh || cfg->grid < 1 || cfg->grid > 5 || V < 1 || T < 1) return ORBF_ERR_ARG;
+    const int g2 = cfg->grid * cfg->grid, n = V * T, w = c->cfg.width, h = c->cfg.height;
     HostFrames hf;
     TRY(set_host_inputs(c, slot0, n, gray, gray_stride, gray_frame_stride, depth, depth_stride_elems, depth_frame_stride_elems, hf));
-    TRY(orbf_region_tables(c, cfg->grid, n));
-    TRY(upload_chunk(c, hf, slot0, 0, n));
-    std::vector<double> st(thresh, thresh + g2);
-    std::vector<int> th(g2);
-    for (int r = 0; r < g2; ++r) {
-        if (!(st[r] > 0)) st[r] = cfg->init_th;
-        th[r] = std::max(c->cfg.min_th_fast, std::min(254, (int)st[r]));
+    TRY(orbf_region_tables(c, cfg->grid, n, V));
+    if (V == 1) TRY(upload_chunk(c, hf, slot0, 0, n));
+    else {
+        hf.depthInPlace = false;                               // frames are re-ordered into step-major slots: depth is staged, not sampled in place
+        if (depth) { c->cur_depth = c->d_depthIn + (size_t)slot0 * w * h; c->cur_depthPitch = w; c->cur_depthFrameStride = (long long)w * h; }
+        for (int v = 0; v < V; ++v)
+            for (int t = 0; t < T; ++t) {
+                const size_t slot = (size_t)slot0 + (size_t)t * V + v;
+                ORBF_CUDA(c, cudaMemcpy2DAsync(c->d_in + slot * c->inPlane, c->inPitch, gray + (size_t)v * gray_video_stride + (size_t)t * gray_frame_stride,
+                    gray_stride, w, h, cudaMemcpyHostToDevice, c->stream));
+                if (depth)
+                    ORBF_CUDA(c, cudaMemcpy2DAsync(c->d_depthIn + slot * w * h, (size_t)w * 2, depth + (size_t)v * depth_video_stride_elems + (size_t)t * depth_frame_stride_elems,
+                        (size_t)depth_stride_elems * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, c->stream));
+            }
     }
-    ORBF_CUDA(c, cudaMemcpyAsync(c->d_regionState, st.data(), g2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    ORBF_CUDA(c, cudaMemcpyAsync(c->d_regionTh, th.data(), g2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> st((size_t)V * 25, 0.0);
+    std::vector<int> th((size_t)V * 25, 0);
+    for (int v = 0; v < V; ++v)
+        for (int r = 0; r < g2; ++r) {
+            double s0 = thresh[(size_t)v * g2 + r];
+            if (!(s0 > 0)) s0 = cfg->init_th;
+            st[(size_t)v * 25 + r] = s0;
+            th[(size_t)v * 25 + r] = std::max(c->cfg.min_th_fast, std::min(254, (int)s0));
+        }
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_regionState, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(c->d_regionTh, th.data(), th.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));           // st / th are locals
     TRY(orbf_launch_pyramid(c, slot0, n));
-    for (int i = 0; i < n; ++i) {
-        TRY(orbf_launch_fast(c, slot0 + i, 1, /*adapted=*/true));
-        TRY(orbf_launch_quadtree(c, slot0 + i, 1));
-        TRY(orbf_launch_region_control(c, slot0 + i, i, *cfg));
+    for (int t = 0; t < T; ++t) {
+        TRY(orbf_launch_fast(c, slot0 + t * V, V, /*adapted=*/true, /*perVideo=*/true));
+        TRY(orbf_launch_quadtree(c, slot0 + t * V, V));
+        TRY(orbf_launch_region_control(c, slot0 + t * V, t * V, *cfg, V));
     }
     TRY(orbf_launch_blur(c, slot0, n));
     TRY(orbf_launch_describe(c, slot0, n));
     std::vector<int> log((size_t)n * 2 * g2);
-    ORBF_CUDA(c, cudaMemcpyAsync(st.data(), c->d_regionState, g2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ORBF_CUDA(c, cudaMemcpyAsync(st.data(), c->d_regionState, st.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaMemcpyAsync(log.data(), c->d_regionLog, log.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::copy(st.begin(), st.end(), thresh);
-    for (int i = 0; i < n; ++i)
+    for (int v = 0; v < V; ++v)
+        for (int r = 0; r < g2; ++r) thresh[(size_t)v * g2 + r] = st[(size_t)v * 25 + r];
+    for (int i = 0; i < n; ++i)                                // log row i = slot order (step-major): [t][v]
         for (int r = 0; r < g2; ++r) {
             if (region_th) region_th[(size_t)i * g2 + r] = log[(size_t)i * 2 * g2 + r];
             if (region_found) region_found[(size_t)i * g2 + r] = log[(size_t)i * 2 * g2 + g2 + r];
         }
     return ORBF_OK;
+}
+
+extern "C" int orbf_extract_adapted(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
+    const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, const orbf_adaptive_config* cfg, double* thresh,
+    int32_t* region_th, int32_t* region_found)
+{
+    CTX_ENTER(c);
+    return extract_adapted_impl(c, slot0, 1, n, gray, gray_stride, gray_frame_stride, 0, depth, depth_stride_elems, depth_frame_stride_elems, 0, cfg, thresh,
+        region_th, region_found);
+}
+
+extern "C" int orbf_extract_adapted_videos(orbf_context* c, int32_t slot0, int32_t n_videos, int32_t frames_per_video, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, int64_t gray_video_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems,
+    int64_t depth_video_stride_elems, const orbf_adaptive_config* cfg, double* thresh, int32_t* region_th, int32_t* region_found)
+{
+    CTX_ENTER(c);
+    return extract_adapted_impl(c, slot0, n_videos, frames_per_video, gray, gray_stride, gray_frame_stride, gray_video_stride, depth, depth_stride_elems,
+        depth_frame_stride_elems, depth_video_stride_elems, cfg, thresh, region_th, region_found);
 }
 
 extern "C" int orbf_download_gray(orbf_context* c, int32_t slot, uint8_t* out, int32_t out_stride)

@@ -292,7 +292,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     int rc = build_geometry(c, tab, cells, strips, blTiles, rsTiles);
     c->nStrips = (int)strips.size(); c->nBlTiles = (int)blTiles.size();
     c->h_cells = cells;
-    c->d_cellRegion = nullptr; c->cellRegionGrid = 0; c->d_regionTh = nullptr; c->d_regionState = nullptr; c->d_regionLog = nullptr; c->regionLogCap = 0;
+    c->d_cellRegion = nullptr; c->cellRegionGrid = 0; c->d_regionTh = nullptr; c->d_regionState = nullptr; c->d_regionLog = nullptr; c->regionLogCap = 0; c->regionVideos = 0;
     if (rc != ORBF_OK) { delete c; return rc; }
 
     cudaError_t e = cudaSetDevice(cfg->device);

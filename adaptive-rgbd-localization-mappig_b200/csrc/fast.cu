@@ -54,7 +54,7 @@ struct FastParams {
     int cellSlotTotal, nCellsTotal, iniTh, minTh, slot0, z0;   // z coordinate of a slot: slot - z0 on level 0, slot elsewhere
     int scoreOff, listOff, bitsOff, sbmOff, sbmWords;           // byte offsets of the shared-memory regions; words of the survivor bitmap
     // region-adapted variant (orbf_extract_adapted): iniTh of a cell = regionTh[cellRegion[cell]]; NULL => iniTh everywhere
-    const uint8_t* cellRegion; const int* regionTh;
+    const uint8_t* cellRegion; const int* regionTh; int regionThStride;   // stride: entries between the tables of consecutive frames (videos) of the launch, or 0
     short BH[ORBF_MAX_LEVELS];
 };
 
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
     if (tid < FS_WARPS) {
         sHas[tid] = tid < sd.nCells ? 0 : 1;
         int t = P.iniTh;
-        if (P.regionTh && tid < sd.nCells) t = P.regionTh[P.cellRegion[sd.firstCell + tid]];
+        if (P.regionTh && tid < sd.nCells) t = P.regionTh[blockIdx.y * P.regionThStride + P.cellRegion[sd.firstCell + tid]];
         sTh[tid] = tid < sd.nCells ? t : 255;
     }
     if (tid <= FS_WARPS) sC0[tid] = tid < sd.nCells ? S.ax + P.cells[sd.firstCell + tid].x0 - sd.x0 : S.ax + S.W + (tid > sd.nCells ? 4096 : 0);
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
             // the second pass: only the cells the first pass left empty are redone, at minTh.  Responses do not depend on the
             // threshold, so a dense pass over a cell that already holds some only adds to them.
             int cellTh0 = P.iniTh;
-            if (P.regionTh) cellTh0 = P.regionTh[P.cellRegion[cellIdx]];
+            if (P.regionTh) cellTh0 = P.regionTh[blockIdx.y * P.regionThStride + P.cellRegion[cellIdx]];
             if (!second) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, cellTh0, lane);
             if (!sHas[warp] && P.minTh < cellTh0) dense_cell(org, sorg, bits, sHas, warp, c0, cw, h, P.minTh, lane);
         }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(FS_THREADS) fast_strip_kernel
 
 }  // namespace
 
-int orbf_launch_fast(orbf_context* c, int slot0, int n, bool adapted)
+int orbf_launch_fast(orbf_context* c, int slot0, int n, bool adapted, bool perVideo)
 {
     {
         const int r = orbf_refresh_maps(c);
@@ -457,7 +457,7 @@ int orbf_launch_fast(orbf_context* c, int slot0, int n, bool adapted)
     P.strips = c->d_strips; P.cells = c->d_cells; P.cellCand = c->d_cellCand; P.cellCount = c->d_cellCount;
     P.cellSlotTotal = c->cellSlotTotal; P.nCellsTotal = c->nCellsTotal; P.iniTh = c->cfg.ini_th_fast; P.minTh = c->cfg.min_th_fast;
     P.slot0 = slot0; P.z0 = c->cur_slot0;
-    P.cellRegion = adapted ? c->d_cellRegion : nullptr; P.regionTh = adapted ? c->d_regionTh : nullptr;
+    P.cellRegion = adapted ? c->d_cellRegion : nullptr; P.regionTh = adapted ? c->d_regionTh : nullptr; P.regionThStride = perVideo ? 25 : 0;
     if (smem > 200 * 1024) return ORBF_ERR_GEOMETRY;
     {   // static + dynamic shared memory can exceed the 48 KB default while the dynamic part alone does not: always opt in
         cudaError_t e = cudaFuncSetAttribute(fast_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -121,7 +121,7 @@ struct orbf_context {
     CellDesc* d_cells; std::vector<CellDesc> h_cells;
     // region-adapted extraction (BASELINE config 4, 8-level variant): region of every FAST cell for the current grid, integer thresholds
     // of the regions for the frame being detected, controller state, per-frame logs
-    uint8_t* d_cellRegion; int cellRegionGrid; int* d_regionTh; double* d_regionState; int* d_regionLog; int regionLogCap;
+    uint8_t* d_cellRegion; int cellRegionGrid; int* d_regionTh; double* d_regionState; int* d_regionLog; int regionLogCap; int regionVideos;   // controller state of regionVideos videos, 25 entries each
     StripDesc* d_strips; int nStrips; int fastBW[ORBF_MAX_LEVELS], fastBH[ORBF_MAX_LEVELS];   // TMA box per level (fast.cu)
     TileDesc* d_blTiles; int nBlTiles;                                                       // blur tiles of all levels
     TileDesc* d_rsTiles; int rsTile0[ORBF_MAX_LEVELS], rsTileN[ORBF_MAX_LEVELS];             // resize tiles per destination level
@@ -209,9 +209,10 @@ int orbf_refresh_maps(orbf_context* ctx);
 void orbf_stage_tile_geometry(int* tileW, int* blurH, int* blurBW, int* blurBH, int* resizeH);
 int orbf_launch_pyramid(orbf_context* ctx, int slot0, int n);
 int orbf_launch_blur(orbf_context* ctx, int slot0, int n);
-int orbf_launch_fast(orbf_context* ctx, int slot0, int n, bool adapted = false);   // adapted: per-region thresholds (d_cellRegion / d_regionTh)
-int orbf_launch_region_control(orbf_context* ctx, int slot, int frameIdx, const orbf_adaptive_config& cfg);
-int orbf_region_tables(orbf_context* ctx, int grid, int nFrames);
+// adapted: per-region thresholds (d_cellRegion / d_regionTh); perVideo: frame i of the launch reads the thresholds of video i (25 entries each)
+int orbf_launch_fast(orbf_context* ctx, int slot0, int n, bool adapted = false, bool perVideo = false);
+int orbf_launch_region_control(orbf_context* ctx, int slot, int frameIdx, const orbf_adaptive_config& cfg, int nVideos = 1);
+int orbf_region_tables(orbf_context* ctx, int grid, int nFrames, int nVideos = 1);
 int orbf_launch_quadtree(orbf_context* ctx, int slot0, int n);
 int orbf_launch_describe(orbf_context* ctx, int slot0, int n);
 int orbf_launch_pack_aos(orbf_context* ctx, int slot0, int n);

@@ -412,6 +412,15 @@ def run_config4(args):
     adapted_ms = wall(adapted)
     l0 = ctx.launch_count(); adapted(); adapted_launches = ctx.launch_count() - l0
     kp_adapted = float(ctx.frame_counts(F).mean())
+    # the same chain with V independent videos advancing together (V frames per link): what a multi-camera rig / several sequences give
+    V = 16 if F % 16 == 0 else 1
+    T = F // V
+    vids = hfr.reshape(V, T, h, w)
+    thv = np.zeros((V, 9))
+
+    def adapted_videos():
+        ctx.extract_adapted_videos(vids, thv, **band); ctx.synchronize()
+    videos_ms = wall(adapted_videos)
     d_gray = torch.from_numpy(frames).cuda(local); d_depth = torch.from_numpy(depths.view(np.int16)).cuda(local)
     fixed_ms = events(lambda: ctx.extract_batch_device(d_gray.data_ptr(), w, w * h, F))
     kp_fixed = float(ctx.frame_counts(F).mean())
@@ -446,10 +455,10 @@ def run_config4(args):
         cpu = {"value": ns / cpu_dt, "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"oracle extract_adapted on the first {ns} frames, {cpu_dt:.1f} s"}
     else:
         cpu = None
-    vals = torch.tensor([adapted_ms, fixed_ms, chain_ms, det_ms / nd], device=f"cuda:{local}", dtype=torch.float64)
+    vals = torch.tensor([adapted_ms, fixed_ms, chain_ms, det_ms / nd, videos_ms], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    adapted_ms, fixed_ms, chain_ms, det_ms_per = [float(x) for x in vals]
+    adapted_ms, fixed_ms, chain_ms, det_ms_per, videos_ms = [float(x) for x in vals]
     if rank == 0:
         px = sum(int(round(w / 1.2 ** l)) * int(round(h / 1.2 ** l)) for l in range(8))
         out = {"metric": "frames_per_sec_orb_extract_1280x720_2000kp_adapted_thresholds", "value": world * F / (adapted_ms * 1e-3), "unit": "frames/s",
@@ -461,6 +470,9 @@ def run_config4(args):
                "routes": {"extract_adapted": {"frames_per_s": world * F / (adapted_ms * 1e-3), "ms_per_step": adapted_ms, "mean_keypoints": kp_adapted,
                                               "input": "pinned host frames, H2D inside the timed region; per-frame controller step on the device",
                                               "launches_per_step": int(adapted_launches)},
+                          "extract_adapted_videos": {"frames_per_s": world * F / (videos_ms * 1e-3), "ms_per_step": videos_ms, "videos": V, "frames_per_video": T,
+                                                     "input": "pinned host frames of V independent videos, H2D inside the timed region; V frames per link of the "
+                                                              "FAST -> quadtree -> controller chain (orbf_extract_adapted_videos)"},
                           "extract_fixed_device": {"frames_per_s": world * F / (fixed_ms * 1e-3), "ms_per_step": fixed_ms, "mean_keypoints": kp_fixed,
                                                    "input": "frames resident in HBM", "algorithmic_bytes_per_frame": 14_193_683,
                                                    "frac_of_hbm": 14_193_683 * F / (fixed_ms * 1e-3) / 1e9 / 6538.9},

@@ -352,6 +352,13 @@ int orbf_adaptive_detect(orbf_context* ctx, const orbf_adaptive_config* cfg, con
 int orbf_extract_adapted(orbf_context* ctx, int32_t slot0, int32_t n, const uint8_t* gray, int64_t gray_stride, int64_t gray_frame_stride,
     const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, const orbf_adaptive_config* cfg, double* thresh,
     int32_t* region_th, int32_t* region_found);
+/* The same for n_videos INDEPENDENT videos (cameras / sequences) of frames_per_video frames each: a video is sequential by definition
+ * (frame t + 1's thresholds depend on frame t's keypoints), several videos advance together, V frames per step of the chain.
+ * gray: frame t of video v at gray + v * gray_video_stride + t * gray_frame_stride; results: frame t of video v in slot
+ * slot0 + t * n_videos + v.  thresh [n_videos][grid * grid] in / out; region_th / region_found [frames_per_video][n_videos][grid * grid]. */
+int orbf_extract_adapted_videos(orbf_context* ctx, int32_t slot0, int32_t n_videos, int32_t frames_per_video, const uint8_t* gray, int64_t gray_stride,
+    int64_t gray_frame_stride, int64_t gray_video_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems,
+    int64_t depth_video_stride_elems, const orbf_adaptive_config* cfg, double* thresh, int32_t* region_th, int32_t* region_found);
 
 #ifdef __cplusplus
 }

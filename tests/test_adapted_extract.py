@@ -88,3 +88,39 @@ def test_adapted_extraction_leaves_the_plain_path_untouched(ob, orc):
             assert k.tobytes() == k0.tobytes() and np.array_equal(d, d0)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_several_videos_advance_together(ob, orc):
+    """orbf_extract_adapted_videos: V independent videos, V frames per link of the FAST -> quadtree -> controller chain; every video must
+    come out exactly as if it had been run alone (frame t of video v in slot t * V + v)."""
+    V, T = 3, 5
+    videos = np.stack([_clip(T, seed=10 + v) for v in range(V)])
+    videos[1, :, :, 320:] = 90                                   # video 1: right half flat -> its right-hand controllers run down to the floor
+    ctx = ob.Context(max_frames=V * T)
+    try:
+        th = np.zeros((V, 9))
+        used, found = ctx.extract_adapted_videos(videos, th)
+        for v in range(V):
+            th_ref = np.zeros(9)
+            for t in range(T):
+                k0, d0, u0, f0 = orc.extract_adapted(videos[v, t], th_ref)
+                k, d, _ = ctx.download_frame(t * V + v)
+                assert np.array_equal(used[t, v], u0) and np.array_equal(found[t, v], f0), f"video {v} frame {t}: thresholds / counts"
+                assert k.tobytes() == k0.tobytes() and np.array_equal(d, d0), f"video {v} frame {t}: keypoints / descriptors"
+            assert np.array_equal(th[v], th_ref), f"video {v}: controller state"
+        assert len({tuple(used[T - 1, v]) for v in range(V)}) == V, "the videos must end on different thresholds"
+        # and the single-video entry point still gives the same for video 0
+        th1 = np.zeros(9)
+        ctx.extract_adapted(videos[0], th1)
+        assert np.array_equal(th1, th[0])
+        assert ctx.download_frame(T - 1)[0].tobytes() == orc.extract_adapted(videos[0, T - 1], np.array(_state_before_last(orc, videos[0])))[0].tobytes()
+    finally:
+        ctx.close()
+
+
+def _state_before_last(orc, clip):
+    th = np.zeros(9)
+    for f in clip[:-1]:
+        orc.extract_adapted(f, th)
+    return th
