@@ -704,6 +704,131 @@ __global__ void __launch_bounds__(HY_WARPS * 32) ransac_hyp_kernel(RansacParams 
     }
 }
 
+// The same hypothesis by a whole CTA (4 warps), for the first waves: they hold only a few hypotheses per pair (2, then 6), so a warp per
+// hypothesis leaves the GPU idle and the refit loop's latency is what the stage costs (on the bench sequence 507 of 511 pairs end in
+// the first wave).  Warp 0 fits the transform (the PCL recurrence and its accW prefix are sequential by definition); ALL warps then
+// score the pairs (f64 Mahalanobis, independent per pair); the inliers' distances are compacted in match order and summed by one
+// thread from shared memory — the reference's sequential double accumulation, 8 loads in flight per add instead of two shuffles per
+// add.  Bit-identical to ransac_hyp_kernel (same operations in the same order; tests/test_gpu_ransac.py compares the traces).
+constexpr int HC_WARPS = 4, HC_THREADS = HC_WARPS * 32;
+
+__global__ void __launch_bounds__(HC_THREADS) ransac_hyp_coop_kernel(RansacParams P)
+{
+    __shared__ uint32_t sMask[MAX_WORDS];
+    __shared__ int sBase[MAX_WORDS + 1];
+    __shared__ float sT[16];
+    __shared__ double sErr;
+    extern __shared__ __align__(16) uint8_t hsmem[];             // K doubles (distances by match index), K doubles (compacted), K floats, K u16
+    double* sD = reinterpret_cast<double*>(hsmem);
+    double* sDense = sD + P.K;
+    float* sAl = reinterpret_cast<float*>(sDense + P.K);
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sAl + P.K);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pair = P.pair0 + blockIdx.y;
+    const int k = P.hypLo + blockIdx.x;
+    if (k >= P.hypHi) return;
+    if (P.state[pair].done) return;          // the sequential loop already ended before this wave (early exit / skip-ahead)
+    const int M = P.goodCount[pair];
+    orbf_hyp_trace* tr = P.hyp + (long long)pair * P.iters + k;
+    float refT[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) refT[i] = (i % 5 == 0) ? 1.f : 0.f;
+    int nRefined = 0, rounds = -1;
+    double refErr = 1e6;
+    if ((unsigned)M >= P.cfg.min_inlier_th && M >= P.S && M <= MAX_WORDS * 32) {
+        const Pt6* pts = P.pts + (long long)pair * P.K;
+        const int* row = P.samples + ((long long)pair * P.iters + k) * P.S;
+        const double cz = *P.depthCov;
+        const double thr = (double)(P.cfg.max_mahal * P.cfg.max_mahal);
+        const int words = (M + 31) >> 5;
+        for (int w = tid; w < words; w += HC_THREADS) sMask[w] = 0;
+        __syncthreads();
+        if (tid == 0) for (int s = 0; s < P.S; ++s) { const int id = row[s]; if (id >= 0 && id < M) sMask[id >> 5] |= 1u << (id & 31); }
+        __syncthreads();
+        rounds = 0;
+        for (int refinements = 1; refinements < 20; ++refinements) {
+            if (warp == 0) {
+                Tfc tfc;
+                tfc_from_mask(pts, sMask, words, sIdx, sAl, tfc, lane);
+                float T[16];
+                tfc.transform(T);
+                if (lane == 0) for (int i = 0; i < 16; ++i) sT[i] = T[i];
+            }
+            ++rounds;
+            __syncthreads();
+            float T4[16];
+            double T[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { T4[i] = sT[i]; T[i] = (double)T4[i]; }
+            // ComputeInliersAndError (ransac.cpp:315-348): chunks of 32 matches per warp, so a warp's ballot is one word of the mask
+            for (int b = warp * 32; b < M; b += HC_THREADS) {
+                const int i = b + lane;
+                bool in = false;
+                double d = 0.0;
+                if (i < M) {
+                    const Pt6 p = pts[i];
+                    if (!(p.sz == 0.0f || p.tx == 0.0f)) {            // sic: target.x (quirk Q8)
+                        d = mahal2(p, T, cz, P.covX, P.covY);
+                        in = !(d > thr) && (d >= 0.0);
+                    }
+                    sD[i] = d;
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, in);
+                if (lane == 0) sMask[b >> 5] = mk;
+            }
+            __syncthreads();
+            if (warp == 0) {                                       // exclusive prefix of the words' inlier counts
+                int carry = 0;
+                for (int w0 = 0; w0 < words; w0 += 32) {
+                    const int w = w0 + lane;
+                    const int c = w < words ? __popc(sMask[w]) : 0;
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    if (w < words) sBase[w] = carry + incl - c;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) sBase[words] = carry;
+            }
+            __syncthreads();
+            for (int b = warp * 32; b < M; b += HC_THREADS) {      // inlier distances, compacted in match order
+                const uint32_t mk = sMask[b >> 5];
+                if ((mk >> lane) & 1u) sDense[sBase[b >> 5] + __popc(mk & ((1u << lane) - 1u))] = sD[b + lane];
+            }
+            __syncthreads();
+            const int nInl = sBase[words];
+            if (tid == 0) {                                        // meanError += mahalDist, in match order (sequential double adds)
+                double mean = 0.0;
+                int j = 0;
+                for (; j + 8 <= nInl; j += 8) {
+                    const double v0 = sDense[j], v1 = sDense[j + 1], v2 = sDense[j + 2], v3 = sDense[j + 3], v4 = sDense[j + 4], v5 = sDense[j + 5],
+                        v6 = sDense[j + 6], v7 = sDense[j + 7];
+                    mean += v0; mean += v1; mean += v2; mean += v3; mean += v4; mean += v5; mean += v6; mean += v7;
+                }
+                for (; j < nInl; ++j) mean += sDense[j];
+                double e = 1e9;
+                if (nInl >= 3) { mean /= (double)nInl; e = sqrt(mean); }
+                sErr = e;
+            }
+            __syncthreads();
+            const double err = sErr;
+            if ((unsigned)nInl < P.cfg.min_inlier_th || err > (double)P.cfg.max_mahal) break;
+            if (nInl >= nRefined && err <= refErr) {
+                const int prev = nRefined;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) refT[i] = T4[i];
+                nRefined = nInl;
+                refErr = err;
+                if (nInl == prev) break;
+            } else break;
+        }
+    }
+    if (tid == 0) {
+        tr->n_refined = nRefined; tr->rounds = rounds; tr->refined_error = refErr;
+        for (int i = 0; i < 16; ++i) tr->T[i] = refT[i];
+    }
+}
+
 // The reference's accept / skip-ahead / early-exit rule (ransac.cpp:233-249), continued over the hypotheses of the
 // wave that just finished: one thread per pair, hypotheses consumed strictly in sample order.
 __global__ void ransac_replay_kernel(RansacParams P, int npairs)
@@ -911,6 +1036,11 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
         cudaError_t e = cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hypSmem);
         if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac hyp smem attr", __FILE__, __LINE__);
     }
+    const size_t coopSmem = (size_t)c->K * (2 * sizeof(double) + sizeof(float) + sizeof(uint16_t));
+    {
+        cudaError_t e = cudaFuncSetAttribute(ransac_hyp_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coopSmem);
+        if (e != cudaSuccess) return orbf_cuda_fail(c, e, "ransac coop smem attr", __FILE__, __LINE__);
+    }
     // (a first wave of 2 covers the common case — on well-matched consecutive frames the loop ends after its first accepted
     // hypothesis — and keeps that wave inside one residency of the GPU; every later wave is a few microseconds when nothing is left)
     const int waveEnd[5] = { 2, 8, 32, 96, iters };
@@ -924,8 +1054,12 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
             P.tabRows = iters;
         }
         P.hypLo = lo; P.hypHi = hi;
-        dim3 grid((hi - lo + HY_WARPS - 1) / HY_WARPS, npairs);
-        ransac_hyp_kernel<<<grid, HY_WARPS * 32, hypSmem, c->stream>>>(P);
+        if (hi - lo <= 8) {                   // few hypotheses per pair: a CTA per hypothesis (parallel scoring) instead of a warp
+            ransac_hyp_coop_kernel<<<dim3(hi - lo, npairs), HC_THREADS, coopSmem, c->stream>>>(P);
+        } else {
+            dim3 grid((hi - lo + HY_WARPS - 1) / HY_WARPS, npairs);
+            ransac_hyp_kernel<<<grid, HY_WARPS * 32, hypSmem, c->stream>>>(P);
+        }
         ORBF_LAUNCH_CHECK(c);
         ransac_replay_kernel<<<(npairs + 127) / 128, 128, 0, c->stream>>>(P, npairs);
         ORBF_LAUNCH_CHECK(c);
