@@ -862,11 +862,16 @@ __global__ void ransac_replay_kernel(RansacParams P, int npairs)
     P.state[pair] = st;
 }
 
-__global__ void __launch_bounds__(32) ransac_select_kernel(RansacParams P)
+// One CTA (4 warps) per pair.  The winner's inlier set only needs the pass / fail flag of every pair (its error is known from the
+// hypothesis trace), so all four warps score; the identity fallback (no valid hypothesis at all, ransac.cpp:252-262) needs the ordered
+// error sum as well and is left to warp 0.
+constexpr int SEL_THREADS = 128;
+__global__ void __launch_bounds__(SEL_THREADS) ransac_select_kernel(RansacParams P)
 {
     __shared__ uint32_t sMask[MAX_WORDS];
-    __shared__ int sWin, sIdentity;
-    const int pair = P.pair0 + blockIdx.x, lane = threadIdx.x;
+    __shared__ int sIdentity;
+    __shared__ double sErr;
+    const int pair = P.pair0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.goodCount[pair];
     const int nm = P.rs.matchCount[pair];
     orbf_ransac_result* res = P.res + pair;
@@ -878,33 +883,47 @@ __global__ void __launch_bounds__(32) ransac_select_kernel(RansacParams P)
     const unsigned minInl = P.cfg.min_inlier_th;
     const RState st = P.state[pair];
     float rmse = st.rmse;
-    int win = st.win, realIters = st.realIters, validIters = st.validIters, usedIdentity = 0;
+    const int win = st.win, realIters = st.realIters;
+    int validIters = st.validIters, usedIdentity = 0;
     const bool runnable = (unsigned)nm >= minInl && (unsigned)M >= minInl && M <= MAX_WORDS * 32;
-    if (lane == 0) sWin = win;
-    __syncwarp();
-    win = sWin;
     float T[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
-    int nInl = 0;
     bool haveMask = false;
-    if (runnable && win >= 0) {
+    if (runnable && win >= 0) {                                // vRefinedMatches of the winner, recomputed (flags only)
+        double Td[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) T[i] = hyp[win].T[i];
-        score_all(pts, M, T, cz, P, sMask, nInl);          // vRefinedMatches of the winner, recomputed
+        for (int i = 0; i < 16; ++i) { T[i] = hyp[win].T[i]; Td[i] = (double)T[i]; }
+        const double thr = (double)(P.cfg.max_mahal * P.cfg.max_mahal);
+        for (int b = warp * 32; b < M; b += SEL_THREADS) {
+            const int i = b + lane;
+            bool in = false;
+            if (i < M) {
+                const Pt6 p = pts[i];
+                if (!(p.sz == 0.0f || p.tx == 0.0f)) {          // sic: target.x (quirk Q8)
+                    const double d = mahal2(p, Td, cz, P.covX, P.covY);
+                    in = !(d > thr) && (d >= 0.0);
+                }
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, in);
+            if (lane == 0) sMask[b >> 5] = mk;
+        }
         haveMask = true;
     } else if (runnable && validIters == 0) {
-        const double err = score_all(pts, M, T, cz, P, sMask, nInl);
-        int ok = ((unsigned)nInl > minInl && err < (double)P.cfg.max_mahal) ? 1 : 0;
-        if (lane == 0) sIdentity = ok;
-        __syncwarp();
+        if (warp == 0) {
+            int nInl = 0;
+            const double err = score_all(pts, M, T, cz, P, sMask, nInl);
+            if (lane == 0) { sIdentity = ((unsigned)nInl > minInl && err < (double)P.cfg.max_mahal) ? 1 : 0; sErr = err; }
+        }
+        __syncthreads();
         if (sIdentity) {
             haveMask = true; usedIdentity = 1;
-            rmse = (float)((double)rmse + err);
+            rmse = (float)((double)rmse + sErr);
             validIters = 1;
-        } else nInl = 0;
+        }
     }
+    __syncthreads();
+    if (warp != 0) return;
     int outCount = 0;
     if (haveMask) {
-        __syncwarp();
         for (int b = 0; b < M; b += 32) {
             const uint32_t mk = sMask[b >> 5];
             const int i = b + lane;
@@ -1067,7 +1086,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     }
     orbf_prof_end(c, ST_RANSAC_HYP);
     orbf_prof_begin(c, ST_RANSAC_SELECT);
-    ransac_select_kernel<<<npairs, 32, 0, c->stream>>>(P);
+    ransac_select_kernel<<<npairs, SEL_THREADS, 0, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
     orbf_prof_end(c, ST_RANSAC_SELECT);
     return ORBF_OK;
