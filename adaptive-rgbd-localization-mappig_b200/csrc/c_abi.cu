@@ -483,6 +483,27 @@ extern "C" int orbf_extract_adapted_videos(orbf_context* c, int32_t slot0, int32
         depth_frame_stride_elems, depth_video_stride_elems, cfg, thresh, region_th, region_found);
 }
 
+// Multi-GPU frame sharding, host arithmetic only: the contiguous chunk [start, stop) of rank `rank` among `world` ranks, the
+// halo frame (the previous rank's last frame, extracted again so that the pair straddling two chunks has an owner), the first frame
+// the rank extracts and the global pair indices [pair0, pair1) it owns.  Every pair 0 .. n_frames - 2 has exactly one owner.
+extern "C" int orbf_frame_shard(int32_t n_frames, int32_t world, int32_t rank, int32_t* start, int32_t* stop, int32_t* halo, int32_t* first,
+    int32_t* pair0, int32_t* pair1)
+{
+    if (world < 1 || rank < 0 || rank >= world || n_frames < 0) return ORBF_ERR_ARG;
+    const int base = n_frames / world, extra = n_frames % world;
+    const int s0 = rank * base + std::min(rank, extra);
+    const int s1 = s0 + base + (rank < extra ? 1 : 0);
+    const int h = (rank > 0 && s1 > s0 && s0 > 0) ? 1 : 0;
+    const int f = s0 - h;
+    if (start) *start = s0;
+    if (stop) *stop = s1;
+    if (halo) *halo = h;
+    if (first) *first = f;
+    if (pair0) *pair0 = s1 > s0 ? f : 0;
+    if (pair1) *pair1 = s1 > s0 ? std::max(s1 - 1, f) : 0;
+    return ORBF_OK;
+}
+
 extern "C" int orbf_download_gray(orbf_context* c, int32_t slot, uint8_t* out, int32_t out_stride)
 {
     CTX_ENTER(c);

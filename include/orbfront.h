@@ -291,6 +291,16 @@ int orbf_kabsch(orbf_context* ctx, const float* setA, const float* setB, int32_t
  * (row 0, the first frame, stays all 1).                                                                              */
 int orbf_compose_trajectory(orbf_context* ctx, int32_t npairs, const float* pose0, float* poses /* [(npairs + 1) * 16] */, uint8_t* outlier);
 
+/* ---- multi-GPU frame sharding (one process per GPU, no data-path collective) --------- */
+/* Host arithmetic, no context: the contiguous chunk [start, stop) of `rank` among `world` ranks, the halo frame (the previous rank's
+ * last frame, extracted again so that the pair straddling two chunks has an owner), the first frame the rank extracts (start - halo)
+ * and the global pair indices [pair0, pair1) it owns; any output may be NULL.  A C++ host shards a sequence with this call,
+ * orbf_extract_batch / orbf_match_pairs on its frames, orbf_ransac_probe_depth_cov + its own 8-byte all-gather (the first valid value
+ * in rank order = quirk Q7's latch), orbf_ransac_pairs with that covariance and seed + pair0, and chains the absolute poses with
+ * orbf_compose_trajectory(pose0 = the previous rank's last pose).                                                          */
+int orbf_frame_shard(int32_t n_frames, int32_t world, int32_t rank, int32_t* start, int32_t* stop, int32_t* halo, int32_t* first,
+    int32_t* pair0, int32_t* pair1);
+
 /* ---- keyframe descriptor store (Core/keyframedatabase, BASELINE config 5) --------------------- */
 /* Copies the descriptors of frame slot `slot` into keyframe entry `kf` of the device-resident store
  * (capacity max_keyframes, set on first use); many-to-many matching runs a-16 against every entry.  */

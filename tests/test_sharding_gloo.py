@@ -165,3 +165,25 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path, orc, texture, n, dead
     assert inl.tobytes() == np.concatenate([r["inliers"] for r in ref]).tobytes() and list(rmse) == [r["rmse"] for r in ref]
     kf = [np.load(tmp_path / f"kf{r}.npz") for r in range(2)]
     assert int(kf[0]["gd_sum"]) == int(kf[1]["gd_sum"]) and np.array_equal(kf[0]["gc"], kf[1]["gc"]) and np.array_equal(kf[0]["surv"], kf[1]["surv"])
+
+
+def test_c_abi_frame_shard_equals_the_python_host_logic(ob):
+    """orbf_frame_shard (what a C++ host calls) against sharding.frame_shard for every (n, world, rank) in a grid, incl. fewer frames than ranks."""
+    import ctypes as C
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("orbf_sharding", Path(__file__).resolve().parent.parent / "adaptive-rgbd-localization-mappig_b200" / "sharding.py")
+    sh = importlib.util.module_from_spec(spec); spec.loader.exec_module(sh)
+    L = ob.lib()
+    out = [C.c_int32() for _ in range(6)]
+    for n in (0, 1, 2, 3, 7, 8, 9, 64, 511, 4096):
+        for world in (1, 2, 3, 4, 8):
+            owners = []
+            for rank in range(world):
+                assert L.orbf_frame_shard(n, world, rank, *[C.byref(o) for o in out]) == 0
+                want = sh.frame_shard(n, world, rank)
+                got = dict(start=out[0].value, stop=out[1].value, halo=out[2].value, first=out[3].value, pairs=(out[4].value, out[5].value))
+                assert got == want, (n, world, rank, got, want)
+                owners += list(range(*got["pairs"]))
+            assert owners == list(range(max(n - 1, 0))), (n, world)
+    assert L.orbf_frame_shard(8, 0, 0, *[C.byref(o) for o in out]) != 0 and L.orbf_frame_shard(8, 2, 2, *[C.byref(o) for o in out]) != 0
