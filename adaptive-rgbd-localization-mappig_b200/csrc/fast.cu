@@ -20,8 +20,10 @@
 //   5. cells left empty after NMS are redone at minTh (orbextractor.cpp:709-712) through the same vector path, restricted to
 //      those cells.  A strip whose survivors exceed the list (noise-like content) takes the dense scalar path instead.
 // Arithmetic is all integer min/max/compare: bit-exact by construction.  Not HBM-bound: the binding resource is the shared-memory
-// data pipe (ncu: 83 % of the peak wavefront rate, 45 % of the wavefronts are the ring gathers of step 2 at ~2.7 wavefronts per
-// warp-wide byte gather), with instruction issue close behind (73 %) — profiles/r2c_fast_phases.txt, profiles/r2c_fast_smem.txt.
+// data pipe (ncu: 81 % of the peak wavefront rate, 46 % of the wavefronts are the ring gathers of step 2 at ~2.2 wavefronts per
+// warp-wide byte gather), with instruction issue close behind (71 %) and the CTA barriers between the phases as the top stall reason —
+// profiles/r2i_fast_kernel.txt, r2i_fast_phases.txt.  Measured and not kept: 16-pixel pretest tasks with LDS.128 rows (12 instead of 24
+// load instructions per 16 pixels, ~28 % fewer pretest wavefronts): 0.9038 vs 0.9019 ms — the pretest is not what the pipe waits for.
 #include "orbf_internal.h"
 #include "fast_device.h"
 
