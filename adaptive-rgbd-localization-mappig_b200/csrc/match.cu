@@ -212,16 +212,36 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
 
     // Per chunk the train tile is expanded and multiplied in two halves of 128 rows: the MMAs of half 0 run under the expansion of
     // half 1, and the warps of column half 0 start their epilogue while half 1 is still in the tensor core.
-    for (int c0 = 0; c0 < nt; c0 += UM_CHUNK) {
+    // The train rows are fetched ahead of their expansion — one half-tile ahead with the cross-check (the kernel sits at the 128-register
+    // cap), a whole chunk ahead without it: the loads are in flight during the expansion, MMAs and epilogue of the tiles before, which
+    // hides the L2 latency of a local store and most of the NVLink latency when the rows live in a peer GPU's HBM
+    // (orbf_kfdb_attach_peers: the transfer then overlaps the math tile by tile).
+    constexpr int PD = CROSS ? 1 : 2;                                    // prefetch distance in half-tiles (4 was measured: no better than 2)
+    constexpr int UNR = PD == 4 ? 2 : 1;                                 // chunks per trip of the loop: the PD register slots are indexed statically
+    const int pcol = tid & (UM_CHUNK / 2 - 1), phalf = tid >> 7;
+    uint4 nextBits[PD];
+#pragma unroll
+    for (int d = 0; d < PD; ++d) {
+        const int r0 = d * (UM_CHUNK / 2) + pcol;
+        nextBits[d] = r0 < nt ? __ldg(reinterpret_cast<const uint4*>(T + (long long)r0 * 8) + phalf) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int cc = 0; cc < nt; cc += UNR * UM_CHUNK) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int c0 = cc + u * UM_CHUNK;
+        if (c0 >= nt) break;
         const int cn = min(UM_CHUNK, nt - c0);
         uint32_t tmem = 0;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
             // every thread that gets here has seen the MMAs that read this half of the tile complete (see the syncs below)
             {
-                const int col = part * (UM_CHUNK / 2) + (tid & (UM_CHUNK / 2 - 1)), half = tid >> 7;
+                const int col = part * (UM_CHUNK / 2) + pcol, half = phalf;
                 const bool valid = col < cn;
-                expand_half(sB, col, half, valid ? __ldg(reinterpret_cast<const uint4*>(T + (long long)(c0 + col) * 8) + half) : make_uint4(0u, 0u, 0u, 0u), valid);
+                const uint4 bits = nextBits[(2 * u + part) % PD];
+                const int rowNext = c0 + (part + PD) * (UM_CHUNK / 2) + pcol;       // the same column PD half-tiles further on
+                if (rowNext < nt) nextBits[(2 * u + part) % PD] = __ldg(reinterpret_cast<const uint4*>(T + (long long)rowNext * 8) + half);
+                expand_half(sB, col, half, bits, valid);
                 if (half == 1 && cn < UM_CHUNK) bias_chunks(sB, col, valid ? ((64u - (uint32_t)((col & 127) >> 1)) | (127u << 8) | (2u << 16) | (1u << 24)) : 0u);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> the tensor core's async proxy
@@ -281,6 +301,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) knn2_kernel(MatchSet ms, int K)
             const uint32_t col = (uint32_t)(c0 + colHalf * 128) + (64u - (e & 127u)) * 2u + (k & 1);
             if (e && (int)col < nt) top2_insert(k1, k2, ((256u - (e >> V_SHIFT)) << 16) | col);
         }
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
