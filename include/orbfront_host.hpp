@@ -17,7 +17,7 @@
 // orbf_dmatch have their exact layout) and ORBextractor::operator() / Extractor::Extract / Matcher::DescriptorDistance gain the
 // reference's cv::InputArray / cv::OutputArray / cv::Mat signatures (compile-checked against tests/cpp/stub/opencv2/core.hpp); without it
 // the PODs below stand in.  With Eigen present (define ORBF_WITH_EIGEN) Kabsch::Compute takes Eigen::MatrixXf and returns
-// Eigen::Matrix4f; otherwise Matrix4f is a 16-float row-major POD with operator()(r, c) and MatrixXf a minimal column-major stand-in.
+// Eigen::Matrix4f (compile-checked against tests/cpp/stub/Eigen/Core); otherwise Matrix4f is a 16-float row-major POD with operator()(r, c) and MatrixXf a minimal column-major stand-in.
 // PCL is never required: PointXYZ / PointCloud below have pcl::PointXYZ's 16-byte record and a `points` vector.
 // Every object shares one process-wide device context (Runtime), created on first use: Matcher is constructed per call on
 // the reference's stack (System/tracking.cpp:197), so its constructor allocates nothing.

@@ -152,3 +152,36 @@ def test_opencv_overloads_match_oracle(ocv_demo, ob, orc, texture, tmp_path):
     ko, do = orc.extract(frame)
     assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
     assert same == 1 and kept == 3 and dist == int(np.unpackbits(do[0] ^ do[1]).sum())
+
+
+@pytest.fixture(scope="module")
+def eigen_demo(ob, tmp_path_factory):
+    """Kabsch::Compute(const Eigen::MatrixXf&, const Eigen::MatrixXf&) -> Eigen::Matrix4f (ORBF_WITH_EIGEN) compiled against the stand-in
+    header tests/cpp/stub/Eigen/Core — this image has no Eigen headers."""
+    ob.lib()
+    exe = tmp_path_factory.mktemp("cpp_eigen") / "eigen_signatures"
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tests' / 'cpp' / 'stub'}", "-o", str(exe),
+           str(ROOT / "tests" / "cpp" / "eigen_signatures.cpp"), f"-L{PKG}", "-lorbfront_b200", f"-Wl,-rpath,{PKG}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_eigen_overload_compiles_and_refuses_without_gpu(eigen_demo):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([str(eigen_demo)], capture_output=True, text=True)
+    assert r.returncode == 3 and "CUDA" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_eigen_overload_matches_oracle(eigen_demo, orc):
+    r = subprocess.run([str(eigen_demo)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    T = np.array([float(x) for x in r.stdout.split()], np.float32).reshape(4, 4)
+    i = np.arange(40)
+    A = np.stack([0.1 * i, 0.05 * (i * i % 17), 1.0 + 0.02 * i], 1).astype(np.float32)
+    B = np.stack([-A[:, 1] + np.float32(0.1), A[:, 0] - np.float32(0.2), A[:, 2] + np.float32(0.3)], 1).astype(np.float32)
+    assert np.abs(T - orc.kabsch(A, B)).max() <= 1e-5
+    assert np.abs(T[:3, :3] - np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)).max() < 1e-4
