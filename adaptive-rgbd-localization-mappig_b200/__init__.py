@@ -260,13 +260,18 @@ class Context:
         self._chk(lib().orbf_wait_marker(self._h, marker), "wait_marker")
 
     def track_sequence_device(self, d_gray_ptr, pitch, frame_stride, n, d_depth_ptr, depth_pitch, depth_frame_stride, ratio,
-                              cross_check=False, ransac=True, slot0=0, **kw):
+                              cross_check=False, ransac=True, slot0=0, pair_slot0=0, **kw):
+        """Device-resident sequence.  With pipeline_overlap=1 the call's RANSAC runs on a side stream: alternate disjoint (slot0, pair_slot0)
+        halves between consecutive calls and they overlap; join() / synchronize() / any download orders the context stream behind it."""
         cfg = default_ransac_config(**kw)
-        self._chk(lib().orbf_track_sequence_device(self._h, slot0, n, C.c_void_p(d_gray_ptr), C.c_int64(pitch), C.c_int64(frame_stride),
-                                                   C.c_void_p(d_depth_ptr) if d_depth_ptr else None, C.c_int64(depth_pitch),
-                                                   C.c_int64(depth_frame_stride), C.c_float(ratio), int(cross_check),
-                                                   C.byref(cfg) if ransac else None), "track_sequence_device")
+        self._chk(lib().orbf_track_sequence_device_at(self._h, slot0, pair_slot0, n, C.c_void_p(d_gray_ptr), C.c_int64(pitch), C.c_int64(frame_stride),
+                                                      C.c_void_p(d_depth_ptr) if d_depth_ptr else None, C.c_int64(depth_pitch),
+                                                      C.c_int64(depth_frame_stride), C.c_float(ratio), int(cross_check),
+                                                      C.byref(cfg) if ransac else None), "track_sequence_device")
         return n - 1
+
+    def join(self):
+        self._chk(lib().orbf_join(self._h), "join")
 
     def frame_counts(self, n, slot0=0):
         out = np.zeros(n, np.int32)

@@ -9,11 +9,18 @@
 #include "replay.h"
 #include "glibc_sincosf.h"
 
-#define CTX_ENTER(c)                                                                   \
+#define CTX_ENTER_NOJOIN(c)                                                            \
     do {                                                                               \
         if (!(c)) return ORBF_ERR_ARG;                                                 \
         cudaError_t e_ = cudaSetDevice((c)->cfg.device);                               \
         if (e_ != cudaSuccess) return orbf_cuda_fail((c), e_, "cudaSetDevice", __FILE__, __LINE__); \
+    } while (0)
+// every entry point but orbf_track_sequence_device_at first orders the context stream behind a RANSAC still running on the side stream
+#define CTX_ENTER(c)                                                                   \
+    do {                                                                               \
+        CTX_ENTER_NOJOIN(c);                                                           \
+        const int j_ = orbf_join_side(c);                                              \
+        if (j_ != ORBF_OK) return j_;                                                  \
     } while (0)
 #define TRY(x) do { int r__ = (x); if (r__ != ORBF_OK) return r__; } while (0)
 
@@ -269,7 +276,17 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
                 TRY(run_match_group(c, ps0 + pa, pb - pa, track->ratio, track->cross));
                 // RANSAC is a chain of latency-bound launches whose duration barely depends on the number of pairs: per
                 // chunk it would be paid once per chunk, so the pipelined path runs it once, after the join, for all pairs
-                if (track->rcfg && !pl.active) TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0 + pa, pb - pa, *track->rcfg, nullptr, false));
+                if (track->rcfg && !pl.active) {
+                    if (c->cfg.pipeline_overlap && c->hi && !c->profiling && !(hf && hf->gray)) {
+                        // device inputs under pipeline_overlap: RANSAC (latency-bound, a few CTAs) goes to the high-priority side stream and
+                        // is not joined back here — the next call's pyramid / FAST on the other slot half run over it
+                        ORBF_CUDA(c, cudaEventRecord(c->evRansacIn, c->stream));
+                        ORBF_CUDA(c, cudaStreamWaitEvent(c->hi, c->evRansacIn, 0));
+                        { StreamSwap sw(c, c->hi); TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0 + pa, pb - pa, *track->rcfg, nullptr, false)); }
+                        ORBF_CUDA(c, cudaEventRecord(c->evRansac, c->hi));
+                        c->hiPending = true; c->hiSlot0 = slot0; c->hiN = n; c->hiPair0 = ps0; c->hiNPairs = npairs;
+                    } else TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0 + pa, pb - pa, *track->rcfg, nullptr, false));
+                }
             }
         }
         prevWorker = wk;
@@ -581,14 +598,26 @@ extern "C" int orbf_wait_marker(orbf_context* c, int32_t marker)
     return ORBF_OK;
 }
 
+extern "C" int orbf_track_sequence_device_at(orbf_context* c, int32_t slot0, int32_t pair_slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg)
+{
+    CTX_ENTER_NOJOIN(c);
+    // a RANSAC of an earlier call may still run on the side stream: it reads the frame / pair slots of THAT call, so this one only has
+    // to wait for it when the slot ranges overlap (or when it would run its own RANSAC on the context stream)
+    if (c->hiPending && (!c->cfg.pipeline_overlap || !ransac_cfg || (slot0 < c->hiSlot0 + c->hiN && c->hiSlot0 < slot0 + n)
+            || (pair_slot0 < c->hiPair0 + c->hiNPairs && c->hiPair0 < pair_slot0 + n - 1))) TRY(orbf_join_side(c));
+    TRY(set_device_inputs(c, slot0, n, d_gray, gray_pitch, gray_frame_stride, d_depth, depth_pitch_elems, depth_frame_stride_elems));
+    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg, pair_slot0 };
+    return run_batch(c, slot0, n, nullptr, &ta);
+}
+
 extern "C" int orbf_track_sequence_device(orbf_context* c, int32_t slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
     int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems, float ratio,
     int32_t cross_check, const orbf_ransac_config* ransac_cfg)
 {
-    CTX_ENTER(c);
-    TRY(set_device_inputs(c, slot0, n, d_gray, gray_pitch, gray_frame_stride, d_depth, depth_pitch_elems, depth_frame_stride_elems));
-    TrackArgs ta = { ratio, cross_check != 0, ransac_cfg, 0 };
-    return run_batch(c, slot0, n, nullptr, &ta);
+    return orbf_track_sequence_device_at(c, slot0, 0, n, d_gray, gray_pitch, gray_frame_stride, d_depth, depth_pitch_elems, depth_frame_stride_elems, ratio,
+        cross_check, ransac_cfg);
 }
 
 extern "C" int orbf_frame_counts(orbf_context* c, int32_t slot0, int32_t n, int32_t* counts)

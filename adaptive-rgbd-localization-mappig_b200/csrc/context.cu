@@ -277,7 +277,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     c->B = cfg->max_frames;
     c->P = cfg->max_pairs > 0 ? cfg->max_pairs : cfg->max_frames;
     c->launches = 0; c->stream = nullptr; c->ownStream = false; c->profiling = false;
-    c->nWork = 0; c->evFork = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr;
+    c->nWork = 0; c->evFork = nullptr; c->hi = nullptr; c->evHiA = c->evHiB = nullptr; c->evRansacIn = c->evRansac = nullptr; c->hiPending = false; c->hiSlot0 = 0; c->hiN = 0; c->hiPair0 = 0; c->hiNPairs = 0;
     for (int i = 0; i < 8; ++i) c->evHiGroup[i] = nullptr;
     for (int i = 0; i < ORBF_MAX_WORKERS; ++i) { c->work[i] = nullptr; c->evDone[i] = nullptr; c->evExtract[i] = nullptr; }
     c->copy = nullptr;
@@ -313,7 +313,8 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
         }
         int prLo = 0, prHi = 0;
         ok = ok && cudaDeviceGetStreamPriorityRange(&prLo, &prHi) == cudaSuccess
-            && cudaStreamCreateWithPriority(&c->hi, cudaStreamNonBlocking, prHi) == cudaSuccess && ev(&c->evHiA) && ev(&c->evHiB);
+            && cudaStreamCreateWithPriority(&c->hi, cudaStreamNonBlocking, prHi) == cudaSuccess && ev(&c->evHiA) && ev(&c->evHiB)
+            && ev(&c->evRansacIn) && ev(&c->evRansac);
         for (int i = 0; ok && i < 8; ++i) ok = ev(&c->evHiGroup[i]);
         if (!ok) { orbf_cuda_fail(c, cudaGetLastError(), "worker streams", __FILE__, __LINE__); return fail(ORBF_ERR_CUDA); }
     }
@@ -423,6 +424,8 @@ extern "C" int orbf_destroy(orbf_context* c)
     if (c->hi) { cudaStreamSynchronize(c->hi); cudaStreamDestroy(c->hi); }
     if (c->evHiA) cudaEventDestroy(c->evHiA);
     if (c->evHiB) cudaEventDestroy(c->evHiB);
+    if (c->evRansacIn) cudaEventDestroy(c->evRansacIn);
+    if (c->evRansac) cudaEventDestroy(c->evRansac);
     for (int i = 0; i < 8; ++i) if (c->evHiGroup[i]) cudaEventDestroy(c->evHiGroup[i]);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
@@ -443,9 +446,25 @@ extern "C" int orbf_set_stream(orbf_context* c, void* s)
     return ORBF_OK;
 }
 
+int orbf_join_side(orbf_context* c)
+{
+    if (c->hiPending) {
+        ORBF_CUDA(c, cudaStreamWaitEvent(c->stream, c->evRansac, 0));
+        c->hiPending = false;
+    }
+    return ORBF_OK;
+}
+
+extern "C" int orbf_join(orbf_context* c)
+{
+    if (!c) return ORBF_ERR_ARG;
+    return orbf_join_side(c);
+}
+
 extern "C" int orbf_synchronize(orbf_context* c)
 {
     if (!c) return ORBF_ERR_ARG;
+    { const int r = orbf_join_side(c); if (r != ORBF_OK) return r; }
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     return ORBF_OK;
 }

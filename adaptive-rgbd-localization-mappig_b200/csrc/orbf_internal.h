@@ -104,6 +104,9 @@ struct orbf_context {
     // high-priority side stream for the latency-bound stages (quadtree, RANSAC): their few, long-running CTAs are placed as
     // soon as SM resources free up and overlap the throughput-bound kernels (blur, Hamming) still running on the main stream
     cudaStream_t hi; cudaEvent_t evHiA, evHiB, evHiGroup[8];
+    // device-input calls under pipeline_overlap: RANSAC of a call runs on `hi` and is NOT joined into the context stream until someone
+    // needs it (orbf_join / any other entry point): evRansac marks its end, hiSlot0 / hiN the frame slots it reads
+    cudaEvent_t evRansacIn, evRansac; bool hiPending; int hiSlot0, hiN, hiPair0, hiNPairs;
     int64_t launches;
     bool profiling; cudaEvent_t evA[ST_COUNT], evB[ST_COUNT]; bool evPending[ST_COUNT]; double stageMs[ST_COUNT]; int64_t stageCalls[ST_COUNT];
     std::string lastError;
@@ -249,6 +252,8 @@ int orbf_launch_projection_match(orbf_context* ctx, const float* d_kpx, const fl
 int orbf_launch_match_select(orbf_context* ctx, const MatchSet& ms, int npairs, float ratio, bool cross);
 // RANSAC
 int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int n, float* dT);
+// makes the context stream wait for a RANSAC still running on the side stream (no host wait); no-op when nothing is pending
+int orbf_join_side(orbf_context* ctx);
 // pairs [pair0, pair0 + npairs).  The depth covariance (quirk Q7) is latched by the first pair, in enqueue order, that reaches
 // scoring; standalone = the call neither sees nor replaces the value latched on the context (orbf_ransac_iterate).
 int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);

@@ -77,7 +77,8 @@ typedef struct {
     int32_t depth_zero_copy;           /* host depth planes in pinned (page-locked) memory are not copied: the ~1000 depth
                                           samples a frame needs are read in place over PCIe by the kernel that unprojects
                                           the keypoints (0 = default on, -1 = always stage the whole plane in HBM)          */
-    int32_t pipeline_overlap;          /* 1 = consecutive batched host-input calls may overlap on the device: a call's H2D copies and
+    int32_t pipeline_overlap;          /* 1 = consecutive batched calls may overlap on the device (device inputs: see
+                                          orbf_track_sequence_device_at).  Host inputs: a call's H2D copies and
                                           kernels are ordered only behind the copies / kernels of earlier calls on the same internal
                                           streams, not behind everything enqueued on the context stream.  The caller then alternates
                                           between disjoint frame / pair slot ranges (orbf_track_sequence_at) and does not reuse a range
@@ -173,6 +174,15 @@ int orbf_track_sequence(orbf_context* ctx, int32_t slot0, int32_t n, const uint8
 int orbf_track_sequence_at(orbf_context* ctx, int32_t slot0, int32_t pair_slot0, int32_t n, const uint8_t* gray, int64_t gray_stride,
     int64_t gray_frame_stride, const uint16_t* depth, int64_t depth_stride_elems, int64_t depth_frame_stride_elems, float ratio,
     int32_t cross_check, const orbf_ransac_config* ransac_cfg);
+/* The device-input call with explicit pair slots.  With orbf_config.pipeline_overlap the RANSAC of such a call runs on an internal
+ * high-priority stream and is NOT joined back into the context stream by the call itself: a following orbf_track_sequence_device_at on
+ * DISJOINT frame / pair slots starts its pyramid / FAST kernels under it (RANSAC is a chain of latency-bound launches that leaves the
+ * SMs almost idle).  Every other entry point — result downloads, orbf_synchronize, a call on overlapping slots — first orders the
+ * context stream behind that RANSAC (no host wait); orbf_join does only that, e.g. before the caller records an event of its own.   */
+int orbf_track_sequence_device_at(orbf_context* ctx, int32_t slot0, int32_t pair_slot0, int32_t n, const uint8_t* d_gray, int64_t gray_pitch,
+    int64_t gray_frame_stride, const uint16_t* d_depth, int64_t depth_pitch_elems, int64_t depth_frame_stride_elems, float ratio,
+    int32_t cross_check, const orbf_ransac_config* ransac_cfg);
+int orbf_join(orbf_context* ctx);
 /* Asynchronous result read-back for such double-buffered use: copies frame counts [slot0, +n), match counts and RANSAC results of pair
  * slots [pair_slot0, +n-1) into caller buffers (page-locked memory for a truly asynchronous copy; any may be NULL) on the context
  * stream and records marker `marker` (0..7) behind them; orbf_wait_marker blocks the host until that point has been reached.          */

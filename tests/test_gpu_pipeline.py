@@ -219,3 +219,51 @@ def test_depth_sampled_in_place_from_pinned_memory_equals_staged_copy(ob, textur
         assert all(x.tobytes() == y.tobytes() for x, y in zip(inplace.download_frame(1), staged.download_frame(1)))
     finally:
         staged.close(); inplace.close()
+
+
+def test_device_steps_overlap_on_alternating_slot_halves(ob, texture):
+    """orbf_track_sequence_device_at under pipeline_overlap: the RANSAC of a call runs on the side stream and is joined lazily, the next
+    call (other slot half) starts under it.  Several back-to-back calls without any synchronisation must leave exactly the results
+    of the serial context in both halves; a call on the SAME half must order itself behind the pending RANSAC."""
+    import torch
+    n = 6
+    seqs = []
+    for base in (40, 70):
+        fr = np.stack([synth.make_frame(texture, base + i) for i in range(n)]); dp = np.stack([synth.make_depth(base + i) for i in range(n)])
+        seqs.append((fr, dp, torch.from_numpy(fr).cuda(), torch.from_numpy(dp.view(np.int16)).cuda()))
+    torch.cuda.synchronize()
+    ref = []
+    plain = ob.Context(max_frames=n)
+    try:
+        for fr, dp, dg, dd in seqs:
+            plain.track_sequence_device(dg.data_ptr(), 640, 640 * 480, n, dd.data_ptr(), 640, 640 * 480, 0.8, True, seed=42)
+            plain.synchronize()
+            ref.append(([plain.download_frame(s) for s in range(n)], [plain.download_matches(p) for p in range(n - 1)], [plain.download_ransac(p) for p in range(n - 1)]))
+    finally:
+        plain.close()
+    ctx = ob.Context(max_frames=2 * n, max_pairs=2 * n, pipeline_overlap=1)
+    try:
+        for rep in range(4):                                     # A0 B1 A0 B1 ... : each call overlaps the previous call's RANSAC
+            for h, (fr, dp, dg, dd) in enumerate(seqs):
+                ctx.track_sequence_device(dg.data_ptr(), 640, 640 * 480, n, dd.data_ptr(), 640, 640 * 480, 0.8, True, seed=42, slot0=h * n, pair_slot0=h * n)
+        ctx.join()
+        ctx.synchronize()
+        for h in range(2):
+            frames_ref, matches_ref, ransac_ref = ref[h]
+            for s in range(n):
+                k, d, xyz = ctx.download_frame(h * n + s)
+                assert k.tobytes() == frames_ref[s][0].tobytes() and np.array_equal(d, frames_ref[s][1]) and np.array_equal(xyz, frames_ref[s][2])
+            for p in range(n - 1):
+                assert ctx.download_matches(h * n + p).tobytes() == matches_ref[p].tobytes(), f"half {h} pair {p}: matches"
+                g, r = ctx.download_ransac(h * n + p), ransac_ref[p]
+                assert g["ok"] == r["ok"] and g["inliers"].tobytes() == r["inliers"].tobytes() and np.array_equal(g["T12"], r["T12"]), f"half {h} pair {p}: RANSAC"
+        # the same half twice in a row: the second call must wait for the first one's RANSAC before it overwrites the pair slots
+        fr, dp, dg, dd = seqs[1]
+        ctx.track_sequence_device(dg.data_ptr(), 640, 640 * 480, n, dd.data_ptr(), 640, 640 * 480, 0.8, True, seed=42, slot0=0, pair_slot0=0)
+        fr, dp, dg, dd = seqs[0]
+        ctx.track_sequence_device(dg.data_ptr(), 640, 640 * 480, n, dd.data_ptr(), 640, 640 * 480, 0.8, True, seed=42, slot0=0, pair_slot0=0)
+        for p in range(n - 1):
+            g, r = ctx.download_ransac(p), ref[0][2][p]
+            assert g["inliers"].tobytes() == r["inliers"].tobytes() and np.array_equal(g["T12"], r["T12"])
+    finally:
+        ctx.close()
