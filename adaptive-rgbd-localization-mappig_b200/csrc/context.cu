@@ -399,6 +399,9 @@ extern "C" int orbf_destroy(orbf_context* c)
 {
     if (!c) return ORBF_ERR_ARG;
     cudaSetDevice(c->cfg.device);
+    if (c->hi) cudaStreamSynchronize(c->hi);               // a RANSAC left on the side stream (pipeline_overlap) still reads the buffers freed below
+    if (c->copy) cudaStreamSynchronize(c->copy);
+    for (int i = 0; i < c->nWork; ++i) if (c->work[i]) cudaStreamSynchronize(c->work[i]);
     if (c->stream) cudaStreamSynchronize(c->stream);
     orbf_comm_release(c);
     void* ptrs[] = { c->d_in, c->d_depthIn, c->d_resizeTab, c->d_cells, c->d_strips, c->d_blTiles, c->d_rsTiles, c->d_bgr, c->d_lg, c->d_cellCand, c->d_cellCount, c->d_cand,
@@ -439,6 +442,7 @@ extern "C" int orbf_destroy(orbf_context* c)
 extern "C" int orbf_set_stream(orbf_context* c, void* s)
 {
     if (!c) return ORBF_ERR_ARG;
+    if (c->hiPending) { ORBF_CUDA(c, cudaStreamSynchronize(c->hi)); c->hiPending = false; }   // nothing of the old stream's epoch stays in flight
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)s;
