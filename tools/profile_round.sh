@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # command has exited 0 without ncu; only the raw-page CSV is kept (gpurun brings back at most 64 MiB)
 python bench.py --frames 128 --steps 1 --warmup 1 --cpu-sample 0 > $out/plain_$tag.log 2>&1 || exit 1
 : > $out/prof_${tag}_raw.csv
-for spec in resize_tile:7 fast_strip:1 quadtree:1 blur_tile:1 describe:1 knn2:1 match_select:1 ransac_prepare:1 ransac_hyp:4 ransac_select:1; do
+for spec in resize_tile:7 fast_strip:1 quadtree:1 blur_tile:1 describe:1 knn2:1 match_select:1 ransac_prepare:1 ransac_hyp_coop:2 ransac_hyp_kernel:3 ransac_select:1; do
   k=${spec%%:*}; n=${spec##*:}
   ncu --set full --clock-control none -k regex:$k -c $n -o $out/prof_${tag}_$k -f python bench.py --frames 128 --steps 1 --warmup 1 --cpu-sample 0 > $out/ncu_full_${tag}_$k.log 2>&1
   if [ -s $out/prof_${tag}_raw.csv ]; then ncu -i $out/prof_${tag}_$k.ncu-rep --page raw --csv 2>/dev/null | tail -n +3 >> $out/prof_${tag}_raw.csv
