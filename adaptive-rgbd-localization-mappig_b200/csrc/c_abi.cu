@@ -843,12 +843,26 @@ extern "C" int orbf_distinctive_descriptors(orbf_context* c, const uint8_t* desc
 
 // One device allocation carved into 256-byte aligned pieces, freed on scope exit (the §8f matcher entry points stage host arrays).
 namespace {
-struct Scratch {
-    uint8_t* base = nullptr; size_t size = 0;
+struct Scratch {     // carve-up of the context's persistent device scratch: every user synchronises before it returns, so calls never overlap on it
+    orbf_context* ctx; uint8_t* base = nullptr; size_t size = 0;
+    explicit Scratch(orbf_context* c) : ctx(c) {}
     size_t take(size_t bytes) { const size_t o = size; size = (size + std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; return o; }
-    cudaError_t alloc() { return cudaMalloc((void**)&base, std::max<size_t>(size, 256)); }
+    cudaError_t alloc()
+    {
+        if (size > ctx->scratchCap) {
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) return e;
+            if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+            ctx->d_scratch = nullptr; ctx->scratchCap = 0;
+            const size_t cap = (size + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+            e = cudaMalloc((void**)&ctx->d_scratch, cap);
+            if (e != cudaSuccess) return e;
+            ctx->scratchCap = cap;
+        }
+        base = ctx->d_scratch;
+        return cudaSuccess;
+    }
     template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
-    ~Scratch() { if (base) cudaFree(base); }
 };
 }  // namespace
 #define SC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } while (0)
@@ -866,7 +880,7 @@ extern "C" int orbf_fuse_search(orbf_context* c, int32_t slot, const float* Rcw,
     int nFeat = n_feat;
     if (slot >= 0) { SC_CUDA(cudaMemcpyAsync(&nFeat, c->d_count + slot, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); SC_CUDA(cudaStreamSynchronize(c->stream)); }
     const size_t L = (size_t)n_landmarks, F = (size_t)std::max(nFeat, 0);
-    Scratch sc;
+    Scratch sc(c);
     const size_t oPos = sc.take(L * 12), oLd = sc.take(L * 32), oVal = sc.take(L), oOut = sc.take(L * 8);
     const size_t oKx = sc.take(F * 4), oKy = sc.take(F * 4), oUr = sc.take(F * 4), oDesc = sc.take(F * 32);
     SC_CUDA(sc.alloc());
@@ -903,7 +917,7 @@ extern "C" int orbf_bow_match(orbf_context* c, const int32_t* words1, const int3
     for (int e = 0; e < e1; ++e) if (idx1[e] < 0 || idx1[e] >= n1) return ORBF_ERR_ARG;
     for (int e = 0; e < e2; ++e) if (idx2[e] < 0 || idx2[e] >= n2) return ORBF_ERR_ARG;
     if (e1 == 0 || e2 == 0) return ORBF_OK;
-    Scratch sc;
+    Scratch sc(c);
     const size_t oW1 = sc.take((size_t)nw1 * 4), oO1 = sc.take(((size_t)nw1 + 1) * 4), oI1 = sc.take((size_t)e1 * 4), oD1 = sc.take((size_t)n1 * 32);
     const size_t oW2 = sc.take((size_t)nw2 * 4), oO2 = sc.take(((size_t)nw2 + 1) * 4), oI2 = sc.take((size_t)e2 * 4), oD2 = sc.take((size_t)n2 * 32);
     const size_t oET = sc.take((size_t)e1 * 4), oED = sc.take((size_t)e1 * 4), oFU = sc.take((size_t)n2 * 4), oOut = sc.take((size_t)e1 * sizeof(orbf_dmatch)), oN = sc.take(4);
@@ -926,7 +940,7 @@ extern "C" int orbf_compose_trajectory(orbf_context* c, int32_t npairs, const fl
     CTX_ENTER(c);
     if (!poses || npairs < 0 || npairs > c->P || npairs > c->lastNPairs) return ORBF_ERR_ARG;
     static const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    Scratch sc;
+    Scratch sc(c);
     const size_t oP0 = sc.take(64), oPoses = sc.take(((size_t)npairs + 1) * 64), oOut = sc.take(outlier ? ((size_t)npairs + 1) * c->K : 1);
     SC_CUDA(sc.alloc());
     SC_H2D(oP0, pose0 ? pose0 : eye, 64);
@@ -942,7 +956,7 @@ extern "C" int orbf_undistort_points(orbf_context* c, const float* xy, int32_t n
     CTX_ENTER(c);
     if (n < 0 || !dist || (n > 0 && (!xy || !out))) return ORBF_ERR_ARG;
     if (n == 0) return ORBF_OK;
-    Scratch sc;
+    Scratch sc(c);
     const size_t oIn = sc.take((size_t)n * 8), oOut = sc.take((size_t)n * 8);
     SC_CUDA(sc.alloc());
     SC_H2D(oIn, xy, (size_t)n * 8);
@@ -966,7 +980,7 @@ extern "C" int orbf_unproject_keypoints(orbf_context* c, const orbf_keypoint* kp
         const int u = (int)kps[i].x, v = (int)kps[i].y;
         if (depth && u >= 0 && v >= 0 && u < width && v < height) raw[i] = depth[(int64_t)v * depth_stride_elems + u];
     }
-    Scratch sc;
+    Scratch sc(c);
     const size_t oXy = sc.take((size_t)n * 8), oRaw = sc.take((size_t)n * 2), oXyz = sc.take((size_t)n * 12), oUr = sc.take((size_t)n * 4), oUn = sc.take((size_t)n * 8);
     SC_CUDA(sc.alloc());
     SC_H2D(oXy, xy.data(), (size_t)n * 8); SC_H2D(oRaw, raw.data(), (size_t)n * 2);
@@ -1252,19 +1266,17 @@ extern "C" int orbf_ransac_clouds(orbf_context* c, int32_t pair0, int32_t npairs
 extern "C" int orbf_download_ransac_clouds(orbf_context* c, int32_t pair, float* src_xyzw, float* tgt_xyzw, int32_t cap, int32_t* n_out)
 {
     CTX_ENTER(c);
-    if (!n_out || pair < 0 || pair >= c->P) return ORBF_ERR_ARG;
+    if (!n_out || pair < 0 || pair >= c->P || cap < 0) return ORBF_ERR_ARG;
     if (c->lastNPairs <= 0) return ORBF_ERR_STATE;
     TRY(orbf_launch_ransac_clouds(c, pair, 1));
+    // the count and both clouds at the caller's capacity in one go, ONE synchronisation (entries past the count are never looked at)
+    const size_t m = (size_t)std::min(cap, c->K);
     ORBF_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_cloudCount + pair, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (src_xyzw && m) ORBF_CUDA(c, cudaMemcpyAsync(src_xyzw, c->d_cloudSrc + (size_t)pair * c->K, m * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (tgt_xyzw && m) ORBF_CUDA(c, cudaMemcpyAsync(tgt_xyzw, c->d_cloudTgt + (size_t)pair * c->K, m * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    const int n = c->h_counts[0];
-    *n_out = n;
-    if (n > cap) return ORBF_ERR_CAPACITY;
-    if (n == 0) return ORBF_OK;
-    if (src_xyzw) ORBF_CUDA(c, cudaMemcpyAsync(src_xyzw, c->d_cloudSrc + (size_t)pair * c->K, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-    if (tgt_xyzw) ORBF_CUDA(c, cudaMemcpyAsync(tgt_xyzw, c->d_cloudTgt + (size_t)pair * c->K, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
-    return ORBF_OK;
+    *n_out = c->h_counts[0];
+    return *n_out > cap ? ORBF_ERR_CAPACITY : ORBF_OK;
 }
 
 extern "C" int orbf_kabsch(orbf_context* c, const float* A, const float* B, int32_t n, float* T16)

@@ -373,6 +373,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     for (void*& q : c->peerOpened) q = nullptr;
     c->h_kp = nullptr; c->h_desc = nullptr; c->h_xyz = nullptr; c->h_counts = nullptr;
     c->h_arena = nullptr; c->arenaCap = 0; c->arenaUsed = 0; c->evArena = nullptr; c->arenaBusy = false;
+    c->d_scratch = nullptr; c->scratchCap = 0;
     auto cu = [&](cudaError_t e3, const char* w) { if (e3 != cudaSuccess) { orbf_cuda_fail(c, e3, w, __FILE__, __LINE__); return false; } return true; };
     if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice), "cells")) return fail(ORBF_ERR_CUDA);
@@ -408,7 +409,7 @@ extern "C" int orbf_destroy(orbf_context* c)
         c->d_candCount, c->d_nodeScratch, c->d_lkp, c->d_lkpCount, c->d_kpx, c->d_kpy, c->d_kpsize, c->d_kpangle, c->d_kpresp,
         c->d_ptx, c->d_pty, c->d_ptz, c->d_uright, c->d_kpux, c->d_kpuy, c->d_kpoct, c->d_kplxy, c->d_desc, c->d_count, c->d_kpAos, c->d_pairs,
         c->d_knn, c->d_rev, c->d_matches, c->d_matchCount, c->d_good, c->d_goodCount, c->d_rres, c->d_rstate, c->d_inliers, c->d_depthCov,
-        c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts, c->d_cloudSrc, c->d_cloudTgt, c->d_cloudCount,
+        c->d_samples, c->d_hyp, c->d_qdesc, c->d_tdesc, c->d_sxyz, c->d_txyz, c->d_kfDesc, c->d_kfCount, c->d_pts, c->d_cloudSrc, c->d_cloudTgt, c->d_cloudCount, c->d_scratch,
         c->d_userSamples, c->d_kabsch, c->d_kfKnn, c->d_kfSurv, c->d_kfPairs, c->d_kfQCount, c->d_cellRegion, c->d_regionTh, c->d_regionState, c->d_regionLog };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < c->L; ++l) { if (c->d_pyr[l]) cudaFree(c->d_pyr[l]); if (c->d_blur[l]) cudaFree(c->d_blur[l]); }

@@ -147,6 +147,7 @@ struct orbf_context {
     // page-locked staging arena of the one-frame-at-a-time calls (orbf_extract*, orbf_knn_match, orbf_ransac_iterate): pageable caller
     // buffers are copied through it so that every transfer of a call is asynchronous and the call synchronises once
     uint8_t* h_arena; size_t arenaCap, arenaUsed; cudaEvent_t evArena; bool arenaBusy;
+    uint8_t* d_scratch; size_t scratchCap;       // device scratch of the host-in / host-out helper calls (grows, never freed per call)
 
     // matching (pair slots)
     int* d_pairs;             // [P][2]
