@@ -5,6 +5,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdio>
+#include <cstdlib>
 #include "orbf_internal.h"
 #include "replay.h"
 #include "glibc_sincosf.h"
@@ -43,7 +45,13 @@ static int arena_begin(orbf_context* c, size_t need)
 static uint8_t* arena_take(orbf_context* c, size_t bytes)
 {
     uint8_t* p = c->h_arena + c->arenaUsed;
-    c->arenaUsed = (c->arenaUsed + bytes + 255) & ~(size_t)255;
+    const size_t used = (c->arenaUsed + bytes + 255) & ~(size_t)255;
+    if (used > c->arenaCap) {       // the callers size the arena from upper bounds of what they take: never reached; fail loudly, not silently
+        c->lastError = "staging arena overflow (internal sizing error)";
+        fprintf(stderr, "orbfront: %s\n", c->lastError.c_str());
+        abort();
+    }
+    c->arenaUsed = used;
     return p;
 }
 // marks the arena as read by work queued on `stream` (a later arena_begin waits for it); calls that end with a stream
