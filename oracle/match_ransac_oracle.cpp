@@ -183,6 +183,33 @@ MahalConst mahal_const()
     return { sx * sx, sy * sy };
 }
 
+// Eigen's `S.llt().solve(b)` for a 3x3 double matrix, restated: unblocked Cholesky S = L L^T (lower), then L y = b, L^T x = y.
+// false: S is not positive definite.
+bool llt3_solve(const double S[3][3], const double b[3], double xs[3])
+{
+    double L[3][3] = { { 0 } };
+    for (int k = 0; k < 3; ++k) {
+        double x = S[k][k];
+        for (int j = 0; j < k; ++j) x -= L[k][j] * L[k][j];
+        if (!(x > 0.0)) return false;
+        const double lkk = std::sqrt(x);
+        L[k][k] = lkk;
+        for (int i = k + 1; i < 3; ++i) {
+            double v = S[i][k];
+            for (int j = 0; j < k; ++j) v -= L[i][j] * L[k][j];
+            L[i][k] = v / lkk;
+        }
+    }
+    double y[3];
+    y[0] = b[0] / L[0][0];
+    y[1] = (b[1] - L[1][0] * y[0]) / L[1][1];
+    y[2] = ((b[2] - L[2][0] * y[0]) - L[2][1] * y[1]) / L[2][2];
+    xs[2] = y[2] / L[2][2];
+    xs[1] = (y[1] - L[2][1] * xs[2]) / L[1][1];
+    xs[0] = ((y[0] - L[1][0] * xs[1]) - L[2][0] * xs[2]) / L[0][0];
+    return true;
+}
+
 double mahal2(const float* x1, const float* x2, const double T[16], double cz)
 {
     static const MahalConst K = mahal_const();
@@ -208,27 +235,8 @@ double mahal2(const float* x1, const float* x2, const double T[16], double cz)
             S[i][j] = v + ((i == j) ? c2[i] : 0.0);
         }
     if (std::isnan(dl[2])) return dmax;
-    // unblocked Cholesky S = L L^T (lower), then L y = dl, L^T x = y, d2 = dl . x
-    double L[3][3] = { { 0 } };
-    for (int k = 0; k < 3; ++k) {
-        double x = S[k][k];
-        for (int j = 0; j < k; ++j) x -= L[k][j] * L[k][j];
-        if (!(x > 0.0)) return dmax;                      // not positive definite (degenerate depth)
-        const double lkk = std::sqrt(x);
-        L[k][k] = lkk;
-        for (int i = k + 1; i < 3; ++i) {
-            double v = S[i][k];
-            for (int j = 0; j < k; ++j) v -= L[i][j] * L[k][j];
-            L[i][k] = v / lkk;
-        }
-    }
-    double y[3], xs[3];
-    y[0] = dl[0] / L[0][0];
-    y[1] = (dl[1] - L[1][0] * y[0]) / L[1][1];
-    y[2] = ((dl[2] - L[2][0] * y[0]) - L[2][1] * y[1]) / L[2][2];
-    xs[2] = y[2] / L[2][2];
-    xs[1] = (y[1] - L[2][1] * xs[2]) / L[1][1];
-    xs[0] = ((y[0] - L[1][0] * xs[1]) - L[2][0] * xs[2]) / L[0][0];
+    double xs[3];
+    if (!llt3_solve(S, dl, xs)) return dmax;                  // not positive definite (degenerate depth)
     const double d2 = (dl[0] * xs[0] + dl[1] * xs[1]) + dl[2] * xs[2];
     if (!(d2 >= 0.0)) return dmax;
     return d2;
@@ -388,6 +396,23 @@ int orc_weighted_transform(const float* src_xyz, const float* dst_xyz, int n, fl
     }
     tfc.transform(T16);
     return ORC_OK;
+}
+
+// pcl::TransformationFromCorrespondences over explicit (point, corresponding point, weight) triples, in the order given
+int orc_tfc_transform(const float* p_xyz, const float* q_xyz, const float* w, int n, float* T16)
+{
+    Tfc tfc;
+    for (int i = 0; i < n; ++i) tfc.add(p_xyz + 3 * i, q_xyz + 3 * i, w[i]);
+    tfc.transform(T16);
+    return ORC_OK;
+}
+
+// Eigen `S.llt().solve(b)`, 3x3 double, S row-major; returns 1 when S is positive definite (x written), else 0
+int orc_llt3_solve(const double* S9, const double* b3, double* x3)
+{
+    double S[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) S[i][j] = S9[3 * i + j];
+    return llt3_solve(S, b3, x3) ? 1 : 0;
 }
 
 double orc_mahalanobis2(const float* p1, const float* p2, const float* T16, double depth_cov)

@@ -135,6 +135,9 @@ int orc_std_sort_dmatch(orc_dmatch* m, int n);
 int orc_svd3(const float* A, float* U, float* S, float* V);
 int orc_weighted_transform(const float* src_xyz, const float* dst_xyz, int n, float* T16);
 double orc_mahalanobis2(const float* p1, const float* p2, const float* T16, double depth_cov);
+/* the two third-party numerical routines of the path on their own (shared with the oracle/_ref stand-ins for PCL / Eigen) */
+int orc_tfc_transform(const float* p_xyz, const float* q_xyz, const float* w, int n, float* T16);
+int orc_llt3_solve(const double* S9, const double* b3, double* x3);
 int orc_kabsch(const float* setA, const float* setB, int n, float* T16);
 
 #ifdef __cplusplus

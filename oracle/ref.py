@@ -1,7 +1,7 @@
-"""ctypes binding of oracle/_ref/liborb_ref.so — TEST INFRASTRUCTURE ONLY.
+"""ctypes binding of oracle/_ref/*.so — TEST INFRASTRUCTURE ONLY.
 
-liborb_ref.so is the reference's own Features/orbextractor.cpp, compiled verbatim from /root/reference (oracle/Makefile, target
-_ref) against the OpenCV stand-in under oracle/ref_shim/.  Only tests/, bench.py's CPU legs and __graft_entry__.build() touch it.
+liborb_ref.so is the reference's own Features/orbextractor.cpp, libodometry_ref.so its Odometry/ransac.cpp + Odometry/kabsch.cpp,
+compiled verbatim from /root/reference (oracle/Makefile, target _ref) against the OpenCV / Eigen / PCL stand-ins under oracle/ref_shim/.  Only tests/, bench.py's CPU legs and __graft_entry__.build() touch it.
 It exists where the reference checkout exists (the authoring container); the prebuilt file travels to the GPU box with the
 snapshot (oracle/_ref/ is git-ignored, not gpurun-ignored).  available() says whether it can be used.
 """
@@ -12,10 +12,11 @@ from pathlib import Path
 
 import numpy as np
 
-from .oracle import CAND_DT, KEYPOINT_DT, level_sizes, _p
+from .oracle import CAND_DT, DMATCH_DT, KEYPOINT_DT, RansacCfg, RansacOut, level_sizes, _p
 
 _DIR = Path(__file__).resolve().parent
 SO = _DIR / "_ref" / "liborb_ref.so"
+SO_ODOMETRY = _DIR / "_ref" / "libodometry_ref.so"
 REFERENCE = Path(os.environ.get("ORB_REFERENCE_DIR", "/root/reference"))
 _lib = None
 
@@ -24,11 +25,11 @@ def build():
     """Compile from the reference checkout when it is present; otherwise keep whatever prebuilt file is there."""
     if (REFERENCE / "Features" / "orbextractor.cpp").exists():
         subprocess.run(["make", "-C", str(_DIR), "-s", "_ref", f"REF={REFERENCE}"], check=True)
-    return SO.exists()
+    return SO.exists() and SO_ODOMETRY.exists()
 
 
 def available():
-    return SO.exists() or build()
+    return (SO.exists() and SO_ODOMETRY.exists()) or build()
 
 
 def lib():
@@ -88,3 +89,67 @@ def tables(nfeatures=1000, scale_factor=1.2, nlevels=8):
     nf = np.zeros(nlevels, np.int32); um = np.zeros(16, np.int32)
     lib().ref_tables(nfeatures, C.c_float(scale_factor), nlevels, _p(nf), _p(um))
     return nf, um
+
+
+# ---- Odometry/ransac.cpp + Odometry/kabsch.cpp (libodometry_ref.so) --------------------------------------------------------------
+_odo = None
+
+
+def odometry_lib():
+    global _odo
+    if _odo is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libodometry_ref.so is not built and the reference checkout is absent")
+        _odo = C.CDLL(str(SO_ODOMETRY))
+        _odo.ref_depth_covariance.restype = C.c_double
+        _odo.ref_depth_covariance.argtypes = [C.c_double]
+        _odo.ref_inliers_and_error.restype = C.c_double
+    return _odo
+
+
+def depth_covariance(depth):
+    """Ransac::DepthCovariance(depth) (ransac.cpp:416-421, quirk Q7): the FIRST call in the process — this one, or the first scored
+    point of an earlier Iterate — fixes what every later call returns."""
+    return float(odometry_lib().ref_depth_covariance(float(depth)))
+
+
+def ransac_iterate(src_xyz, dst_xyz, m12, iterations=200, min_inlier_th=20, max_mahal=3.0, sample_size=4, check_depth=True, seed=42,
+                   member_form=False):
+    """The reference's Ransac::Iterate(F1, F2, m12) (ransac.cpp:155-267) or, member_form, Ransac(KF1, KF2, m12) + Iterate()
+    (ransac.cpp:26-36, 44-153), after srand(seed)."""
+    src = np.ascontiguousarray(src_xyz, np.float32); dst = np.ascontiguousarray(dst_xyz, np.float32)
+    m12 = np.ascontiguousarray(m12, DMATCH_DT)
+    cfg = RansacCfg(iterations, min_inlier_th, max_mahal, sample_size, int(check_depth), -1.0)
+    out = RansacOut()
+    inl = np.zeros(max(len(m12), 1), DMATCH_DT)
+    cs = np.zeros((max(len(m12), 1), 3), np.float32); ct = np.zeros_like(cs); nc = C.c_int(0)
+    rc = odometry_lib().ref_ransac_iterate(C.byref(cfg), _p(src), len(src), _p(dst), len(dst), _p(m12), len(m12), C.c_uint(seed),
+                                           int(member_form), _p(inl), len(inl), C.byref(out), _p(cs), _p(ct), C.byref(nc))
+    if rc:
+        raise RuntimeError(f"ref_ransac_iterate rc={rc}")
+    return dict(ok=bool(out.ok), rmse=float(out.rmse), T12=np.array(out.T12, np.float32).reshape(4, 4), inliers=inl[:out.n_inliers].copy(),
+                n_good=out.n_good, cloud_src=cs[:nc.value].copy(), cloud_tgt=ct[:nc.value].copy())
+
+
+def sample_table(seed, M, iterations=200, sample_size=4):
+    """Ransac::SampleMatches (ransac.cpp:269-292) called `iterations` times after srand(seed) on M matches."""
+    tab = np.full((iterations, sample_size), -1, np.int32)
+    odometry_lib().ref_sample_table(C.c_uint(seed), int(M), int(iterations), int(sample_size), _p(tab))
+    return tab
+
+
+def inliers_and_error(src_xyz, dst_xyz, m12, T, max_mahal=3.0):
+    """Ransac::ComputeInliersAndError (ransac.cpp:313-348): (error, positions of the inliers in m12)."""
+    src = np.ascontiguousarray(src_xyz, np.float32); dst = np.ascontiguousarray(dst_xyz, np.float32)
+    m12 = np.ascontiguousarray(m12, DMATCH_DT); T = np.ascontiguousarray(T, np.float32)
+    pos = np.zeros(max(len(m12), 1), np.int32); n = C.c_int(0)
+    e = odometry_lib().ref_inliers_and_error(_p(src), len(src), _p(dst), len(dst), _p(m12), len(m12), _p(T), C.c_float(max_mahal), _p(pos), C.byref(n))
+    return float(e), pos[:n.value].copy()
+
+
+def kabsch(A, B):
+    """Kabsch::Compute(setA, setB) (kabsch.cpp:14-57)."""
+    A = np.ascontiguousarray(A, np.float32).reshape(-1, 3); B = np.ascontiguousarray(B, np.float32).reshape(-1, 3)
+    T = np.zeros((4, 4), np.float32)
+    odometry_lib().ref_kabsch(_p(A), _p(B), len(A), _p(T))
+    return T
