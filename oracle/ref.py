@@ -153,3 +153,27 @@ def kabsch(A, B):
     T = np.zeros((4, 4), np.float32)
     odometry_lib().ref_kabsch(_p(A), _p(B), len(A), _p(T))
     return T
+
+
+# ---- adaptive detector chain (row a-17): Features/extractor.cpp + video*adaptedfeaturedetector.cpp + detectoradjuster.cpp (liborb_ref.so) ----
+class AdaptiveExtractor:
+    """The reference's Extractor(FAST, ORB, ADAPTIVE); extract(img) = Extractor::Extract on the next frame of the video."""
+
+    def __init__(self):
+        L = lib()
+        L.ref_adaptive_create.restype = C.c_void_p
+        L.ref_adaptive_destroy.argtypes = [C.c_void_p]
+        self._h = C.c_void_p(L.ref_adaptive_create())
+
+    def extract(self, img, cap=4096):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.zeros(cap, KEYPOINT_DT); n = C.c_int(0); th = np.zeros(9, np.float64)
+        rc = lib().ref_adaptive_extract(self._h, _p(img), w, h, w, _p(out), cap, C.byref(n), _p(th))
+        if rc:
+            raise RuntimeError(f"ref_adaptive_extract rc={rc}")
+        return out[:n.value].copy(), th
+
+    def close(self):
+        if self._h:
+            lib().ref_adaptive_destroy(self._h); self._h = None

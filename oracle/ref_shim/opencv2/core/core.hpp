@@ -11,6 +11,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -64,6 +65,7 @@ struct DMatch {
 
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 struct Rect { int x, y, width, height; Rect() : x(0), y(0), width(0), height(0) {} Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+struct Range { int start, end; Range() : start(0), end(0) {} Range(int s, int e) : start(s), end(e) {} };
 struct Scalar { double v[4]; static Scalar all(double a) { Scalar s; s.v[0] = s.v[1] = s.v[2] = s.v[3] = a; return s; } };
 
 struct KeyPoint {
@@ -97,6 +99,7 @@ public:
     size_t step1() const { return step / esz_; }
     Size size() const { return Size(cols, rows); }
     Mat operator()(const Rect& r) const { Mat m(*this); m.data = data + (size_t)r.y * step + (size_t)r.x * esz_; m.rows = r.height; m.cols = r.width; return m; }
+    Mat operator()(const Range& rr, const Range& cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * esz_; m.cols = b - a; return m; }
     Mat clone() const
@@ -210,6 +213,27 @@ inline void GaussianBlur(InputArray src_, OutputArray dst_, Size ksize, double s
     assert(rc == ORC_OK); (void)rc;
 }
 
+enum { NORM_L2 = 4, NORM_HAMMING = 6 };
+
+// cv::Ptr (OpenCV 3): a shared pointer with implicit construction from a raw pointer and conversions between related types
+template <typename T> class Ptr {
+public:
+    Ptr() {}
+    Ptr(std::nullptr_t) {}
+    template <typename Y> Ptr(Y* p) : p_(p) {}
+    template <typename Y> Ptr(const Ptr<Y>& o) : p_(o.shared()) {}
+    void reset() { p_.reset(); }
+    template <typename Y> void reset(Y* p) { p_.reset(p); }
+    T* operator->() const { return p_.get(); }
+    T& operator*() const { return *p_; }
+    T* get() const { return p_.get(); }
+    bool empty() const { return !p_; }
+    explicit operator bool() const { return (bool)p_; }
+    const std::shared_ptr<T>& shared() const { return p_; }
+private:
+    std::shared_ptr<T> p_;
+};
+
 class Algorithm { public: virtual ~Algorithm() {} };
 class Feature2D : public Algorithm {
 public:
@@ -217,7 +241,63 @@ public:
     virtual void detect(InputArray, std::vector<KeyPoint>&, InputArray = noArray()) {}
     virtual void compute(InputArray, std::vector<KeyPoint>&, OutputArray) {}
     virtual void detectAndCompute(InputArray, InputArray, std::vector<KeyPoint>&, OutputArray, bool = false) {}
+    virtual int defaultNorm() const { return NORM_L2; }
 };
 typedef Feature2D FeatureDetector;
+typedef Feature2D DescriptorExtractor;
+
+// cv::FastFeatureDetector: cv::FAST on the matrix handed in (threshold is an int: a double argument truncates, as in OpenCV)
+class FastFeatureDetector : public Feature2D {
+public:
+    static Ptr<FastFeatureDetector> create(int threshold = 10, bool nonmaxSuppression = true, int = 2)
+    {
+        FastFeatureDetector* d = new FastFeatureDetector; d->th_ = threshold; d->nms_ = nonmaxSuppression;
+        return Ptr<FastFeatureDetector>(d);
+    }
+    void detect(InputArray image, std::vector<KeyPoint>& keypoints, InputArray = noArray()) override { FAST(image, keypoints, th_, nms_); }
+    int getThreshold() const { return th_; }
+private:
+    int th_ = 10; bool nms_ = true;
+};
+
+// detectors / descriptors the reference can be configured with but the hot path never runs: they exist so that the sources compile,
+// and stop the process if a test ever reaches them
+#define ORBF_SHIM_UNUSED_FEATURE2D(NAME, NORM)                                                                                  \
+    class NAME : public Feature2D {                                                                                             \
+    public:                                                                                                                     \
+        template <typename... A> static Ptr<NAME> create(A...) { return Ptr<NAME>(new NAME); }                                  \
+        void detect(InputArray, std::vector<KeyPoint>&, InputArray = noArray()) override { std::abort(); }                      \
+        void compute(InputArray, std::vector<KeyPoint>&, OutputArray) override {}                                               \
+        int defaultNorm() const override { return NORM; }                                                                       \
+    };
+ORBF_SHIM_UNUSED_FEATURE2D(ORB, NORM_HAMMING)
+ORBF_SHIM_UNUSED_FEATURE2D(BRISK, NORM_HAMMING)
+ORBF_SHIM_UNUSED_FEATURE2D(GFTTDetector, NORM_L2)
+namespace xfeatures2d {
+ORBF_SHIM_UNUSED_FEATURE2D(StarDetector, NORM_L2)
+ORBF_SHIM_UNUSED_FEATURE2D(SURF, NORM_L2)
+ORBF_SHIM_UNUSED_FEATURE2D(SIFT, NORM_L2)
+ORBF_SHIM_UNUSED_FEATURE2D(BriefDescriptorExtractor, NORM_HAMMING)
+ORBF_SHIM_UNUSED_FEATURE2D(FREAK, NORM_HAMMING)
+ORBF_SHIM_UNUSED_FEATURE2D(LATCH, NORM_HAMMING)
+typedef SURF SurfFeatureDetector;
+typedef SIFT SiftFeatureDetector;
+}  // namespace xfeatures2d
+
+// cv::KeyPointsFilter::retainBest (features2d/src/keypoint.cpp): nth_element on the response, then every keypoint whose response
+// equals the one at the cut is kept as well
+struct KeyPointsFilter {
+    static void retainBest(std::vector<KeyPoint>& keypoints, int n_points)
+    {
+        if (n_points >= 0 && keypoints.size() > (size_t)n_points) {
+            if (n_points == 0) { keypoints.clear(); return; }
+            std::nth_element(keypoints.begin(), keypoints.begin() + n_points - 1, keypoints.end(),
+                [](const KeyPoint& a, const KeyPoint& b) { return a.response > b.response; });
+            const float ambiguous = keypoints[(size_t)n_points - 1].response;
+            auto new_end = std::partition(keypoints.begin() + n_points, keypoints.end(), [ambiguous](const KeyPoint& k) { return k.response >= ambiguous; });
+            keypoints.resize((size_t)(new_end - keypoints.begin()));
+        }
+    }
+};
 
 }  // namespace cv
