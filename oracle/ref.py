@@ -177,3 +177,80 @@ class AdaptiveExtractor:
     def close(self):
         if self._h:
             lib().ref_adaptive_destroy(self._h); self._h = None
+
+
+# ---- Features/matcher.cpp (liborb_ref.so): both KnnMatch overloads, ProjectionMatch, BoWMatch, Fuse -------------------------------------
+def _opt(a):
+    return _p(a) if len(a) else None
+
+
+def knn_match_frames(q, t, ratio):
+    """Matcher(ratio).KnnMatch(Frame&, Frame&, matches) (matcher.cpp:55-88), landmark filters passing everything."""
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    out = np.zeros(max(len(q), 1), DMATCH_DT); n = C.c_int(0)
+    rc = lib().ref_knn_match_frames(_opt(q), len(q), _opt(t), len(t), C.c_float(ratio), _p(out), len(out), C.byref(n))
+    if rc:
+        raise RuntimeError(f"ref_knn_match_frames rc={rc}")
+    return out[:n.value].copy()
+
+
+def knn_match_keyframe(q, t, ratio, kf_landmarks, lm_bad, f2_landmarks):
+    """Matcher(ratio).KnnMatch(KeyFrame*, Frame&, matches) (matcher.cpp:23-53); f2_landmarks (int32 ids, 0 = free) is updated in place."""
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    kf = np.ascontiguousarray(kf_landmarks, np.int32); bad = np.ascontiguousarray(lm_bad, np.uint8)
+    assert f2_landmarks.dtype == np.int32 and f2_landmarks.flags.c_contiguous
+    out = np.zeros(max(len(q), 1), DMATCH_DT); n = C.c_int(0)
+    rc = lib().ref_knn_match_keyframe(_opt(q), len(q), _opt(t), len(t), C.c_float(ratio), _p(kf), _p(bad), len(bad), _p(f2_landmarks), _p(out), len(out),
+                                      C.byref(n))
+    if rc:
+        raise RuntimeError(f"ref_knn_match_keyframe rc={rc}")
+    return out[:n.value].copy()
+
+
+def projection_match(kp_x, kp_y, kp_octave, desc, lm_desc, proj_x, proj_y, lm_flags, feat_taken=None, radius=8.0, nn_ratio=0.8, th_high=100.0):
+    """Matcher(nn_ratio).ProjectionMatch(frame, landmarks, radius) (matcher.cpp:90-143): (slot per landmark or -1, nmatches)."""
+    kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32)
+    kp_octave = np.ascontiguousarray(kp_octave, np.int32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    lm_desc = np.ascontiguousarray(lm_desc, np.uint8).reshape(-1, 32)
+    proj_x = np.ascontiguousarray(proj_x, np.float32); proj_y = np.ascontiguousarray(proj_y, np.float32)
+    lm_flags = np.ascontiguousarray(lm_flags, np.uint8)
+    taken = None if feat_taken is None else np.ascontiguousarray(feat_taken, np.uint8)
+    n, L = len(kp_x), len(lm_flags)
+    best = np.full(max(L, 1), -1, np.int32); nm = C.c_int(0)
+    rc = lib().ref_projection_match(_opt(kp_x), _opt(kp_y), _opt(kp_octave), _opt(desc), n, _opt(lm_desc), _opt(proj_x), _opt(proj_y), _opt(lm_flags), L,
+                                    _p(taken) if taken is not None else None, C.c_float(radius), C.c_float(nn_ratio), C.c_double(th_high), _p(best),
+                                    C.byref(nm))
+    if rc:
+        raise RuntimeError(f"ref_projection_match rc={rc}")
+    return best[:L], nm.value
+
+
+def bow_match(words1, off1, idx1, desc1, words2, off2, idx2, desc2, nn_ratio=0.6, th_low=50.0):
+    """Matcher(nn_ratio).BoWMatch(KF1, KF2, matches) (matcher.cpp:145-209)."""
+    w1 = np.ascontiguousarray(words1, np.int32); o1 = np.ascontiguousarray(off1, np.int32); i1 = np.ascontiguousarray(idx1, np.int32)
+    w2 = np.ascontiguousarray(words2, np.int32); o2 = np.ascontiguousarray(off2, np.int32); i2 = np.ascontiguousarray(idx2, np.int32)
+    d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+    out = np.zeros(max(len(i1), 1), DMATCH_DT); n = C.c_int(0)
+    rc = lib().ref_bow_match(_opt(w1), _p(o1), _opt(i1), len(w1), _opt(d1), len(d1), _opt(w2), _p(o2), _opt(i2), len(w2), _opt(d2), len(d2),
+                             C.c_float(nn_ratio), C.c_double(th_low), _p(out), len(out), C.byref(n))
+    if rc:
+        raise RuntimeError(f"ref_bow_match rc={rc}")
+    return out[:n.value].copy()
+
+
+def fuse(Rcw, tcw, bounds, kp_x, kp_y, u_right, desc, lm_pos, lm_desc, lm_state, radius=3.0, th_low=50.0):
+    """Matcher().Fuse(KF, landmarks, radius) (matcher.cpp:212-311) with the reference's compiled-in FR1 calibration; bounds = (min_x, max_x,
+    min_y, max_y); lm_state 0 null / 1 valid / 2 bad / 3 already in the keyframe.  Returns (feature per landmark or -1, nFused)."""
+    Rcw = np.ascontiguousarray(Rcw, np.float32).reshape(9); tcw = np.ascontiguousarray(tcw, np.float32).reshape(3)
+    kp_x = np.ascontiguousarray(kp_x, np.float32); kp_y = np.ascontiguousarray(kp_y, np.float32); u_right = np.ascontiguousarray(u_right, np.float32)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    lm_pos = np.ascontiguousarray(lm_pos, np.float32).reshape(-1, 3); lm_desc = np.ascontiguousarray(lm_desc, np.uint8).reshape(-1, 32)
+    lm_state = np.ascontiguousarray(lm_state, np.uint8)
+    L = len(lm_state)
+    best = np.full(max(L, 1), -1, np.int32); nf = C.c_int(0)
+    x0, x1, y0, y1 = [C.c_float(float(v)) for v in bounds]
+    rc = lib().ref_fuse(_p(Rcw), _p(tcw), x0, x1, y0, y1, _opt(kp_x), _opt(kp_y), _opt(u_right), _opt(desc), len(kp_x), _opt(lm_pos), _opt(lm_desc),
+                        _opt(lm_state), L, C.c_float(radius), C.c_double(th_low), _p(best), C.byref(nf))
+    if rc:
+        raise RuntimeError(f"ref_fuse rc={rc}")
+    return best[:L], nf.value

@@ -66,7 +66,11 @@ struct DMatch {
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 struct Rect { int x, y, width, height; Rect() : x(0), y(0), width(0), height(0) {} Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
 struct Range { int start, end; Range() : start(0), end(0) {} Range(int s, int e) : start(s), end(e) {} };
-struct Scalar { double v[4]; static Scalar all(double a) { Scalar s; s.v[0] = s.v[1] = s.v[2] = s.v[3] = a; return s; } };
+struct Scalar {
+    double v[4];
+    Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; }
+    static Scalar all(double a) { return Scalar(a, a, a, a); }
+};
 
 struct KeyPoint {
     Point2f pt; float size, angle, response; int octave, class_id;
@@ -100,6 +104,7 @@ public:
     Size size() const { return Size(cols, rows); }
     Mat operator()(const Rect& r) const { Mat m(*this); m.data = data + (size_t)r.y * step + (size_t)r.x * esz_; m.rows = r.height; m.cols = r.width; return m; }
     Mat operator()(const Range& rr, const Range& cr) const { return (*this)(Rect(cr.start, rr.start, cr.end - cr.start, rr.end - rr.start)); }
+    Mat row(int r) const { return rowRange(r, r + 1); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * esz_; m.cols = b - a; return m; }
     Mat clone() const
@@ -115,6 +120,8 @@ public:
     }
     template <typename T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <typename T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }                 // vectors
+    template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
     static MatZeros zeros(int r, int c, int type) { MatZeros z = { r, c, type }; return z; }
@@ -151,6 +158,35 @@ public:
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 inline const _OutputArray& noArray() { static _OutputArray none; return none; }
+
+// `A * B + C` on float matrices = cv::gemm(A, B, 1, C, 1) through cv::MatExpr: every element is the products summed left to right in
+// float, then (float)((double)sum * alpha + (double)c * beta) (OpenCV's small-matrix GEMM; the same statement as the oracle's, which
+// tests/test_fuse_bow.py and tests/test_trajectory.py pin against cv2.gemm)
+struct MatMul { Mat a, b; };
+inline MatMul operator*(const Mat& a, const Mat& b) { assert(a.type() == CV_32F && b.type() == CV_32F && a.cols == b.rows); MatMul m = { a, b }; return m; }
+inline Mat operator+(const MatMul& m, const Mat& c)
+{
+    assert(c.type() == CV_32F && c.rows == m.a.rows && c.cols == m.b.cols);
+    Mat d(m.a.rows, m.b.cols, CV_32F);
+    for (int i = 0; i < d.rows; ++i)
+        for (int j = 0; j < d.cols; ++j) {
+            float t = m.a.at<float>(i, 0) * m.b.at<float>(0, j);
+            for (int k = 1; k < m.a.cols; ++k) t = t + m.a.at<float>(i, k) * m.b.at<float>(k, j);
+            d.at<float>(i, j) = (float)((double)t * 1.0 + (double)c.at<float>(i, j) * 1.0);
+        }
+    return d;
+}
+
+enum { NORM_L2 = 4, NORM_HAMMING = 6 };
+// cv::norm(a, b, NORM_HAMMING) on two u8 rows: number of differing bits
+inline double norm(InputArray a_, InputArray b_, int normType)
+{
+    const Mat a = a_.getMat(), b = b_.getMat();
+    assert(normType == NORM_HAMMING && a.type() == CV_8U && a.rows == b.rows && a.cols == b.cols);
+    int d = 0;
+    for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) d += __builtin_popcount((unsigned)(a.ptr(r)[c] ^ b.ptr(r)[c]));
+    return (double)d;
+}
 
 enum { BORDER_CONSTANT = 0, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
 enum { INTER_LINEAR = 1 };
@@ -212,8 +248,6 @@ inline void GaussianBlur(InputArray src_, OutputArray dst_, Size ksize, double s
     const int rc = orc_gaussian_blur7(tmp.data, tmp.cols, tmp.rows, (int)tmp.step, dst.data, (int)dst.step);
     assert(rc == ORC_OK); (void)rc;
 }
-
-enum { NORM_L2 = 4, NORM_HAMMING = 6 };
 
 // cv::Ptr (OpenCV 3): a shared pointer with implicit construction from a raw pointer and conversions between related types
 template <typename T> class Ptr {
@@ -283,6 +317,46 @@ ORBF_SHIM_UNUSED_FEATURE2D(LATCH, NORM_HAMMING)
 typedef SURF SurfFeatureDetector;
 typedef SIFT SiftFeatureDetector;
 }  // namespace xfeatures2d
+
+// cv::BFMatcher::knnMatch(query, train, matches, 2), NORM_HAMMING, no cross-check: per query row the two nearest train rows, ties to
+// the lower train index — the routine tests/test_oracle_vs_cv2.py pins against cv2.BFMatcher.knnMatch (orc_knn2).  Fewer than two train
+// rows give shorter lists, as in OpenCV.
+class DescriptorMatcher : public Algorithm {
+public:
+    virtual void knnMatch(InputArray query, InputArray train, std::vector<std::vector<DMatch>>& matches, int k, InputArray = noArray(), bool = false) const = 0;
+};
+class BFMatcher : public DescriptorMatcher {
+public:
+    static Ptr<BFMatcher> create(int normType = NORM_L2, bool crossCheck = false)
+    {
+        assert(normType == NORM_HAMMING && !crossCheck); (void)normType; (void)crossCheck;
+        return Ptr<BFMatcher>(new BFMatcher);
+    }
+    void knnMatch(InputArray query, InputArray train, std::vector<std::vector<DMatch>>& matches, int k, InputArray = noArray(), bool = false) const override
+    {
+        const Mat q = query.getMat().clone(), t = train.getMat().clone();                  // tight rows
+        assert(k == 2 && (q.empty() || q.cols == 32) && (t.empty() || t.cols == 32)); (void)k;
+        matches.assign((size_t)q.rows, std::vector<DMatch>());
+        if (q.rows == 0 || t.rows == 0) return;
+        std::vector<int> i1((size_t)q.rows), d1((size_t)q.rows), i2((size_t)q.rows), d2((size_t)q.rows);
+        orc_knn2(q.data, q.rows, t.data, t.rows, i1.data(), d1.data(), i2.data(), d2.data());
+        for (int i = 0; i < q.rows; ++i) {
+            if (i1[(size_t)i] >= 0) matches[(size_t)i].push_back(DMatch(i, i1[(size_t)i], 0, (float)d1[(size_t)i]));
+            if (i2[(size_t)i] >= 0) matches[(size_t)i].push_back(DMatch(i, i2[(size_t)i], 0, (float)d2[(size_t)i]));
+        }
+    }
+};
+
+// drawing / display entry points of Matcher::Draw* (never on the hot path): no-ops so that the source compiles
+struct DrawMatchesFlags { enum { DEFAULT = 0, DRAW_OVER_OUTIMG = 1, NOT_DRAW_SINGLE_POINTS = 2, DRAW_RICH_KEYPOINTS = 4 }; };
+enum { COLOR_GRAY2BGR = 8 };
+template <typename... A> inline void drawMatches(A&&...) {}
+template <typename... A> inline void drawKeypoints(A&&...) {}
+template <typename... A> inline void imshow(A&&...) {}
+template <typename... A> inline void cvtColor(A&&...) {}
+template <typename... A> inline void rectangle(A&&...) {}
+template <typename... A> inline void circle(A&&...) {}
+inline int waitKey(int = 0) { return -1; }
 
 // cv::KeyPointsFilter::retainBest (features2d/src/keypoint.cpp): nth_element on the response, then every keypoint whose response
 // equals the one at the cut is kept as well
