@@ -15,6 +15,9 @@
 //   Eigen JacobiSVD<Matrix3f>, Matrix3d::llt().solve — restated as a two-sided Jacobi 3x3 SVD and
 //        an unblocked 3x3 Cholesky; checked against numpy in tests/test_oracle_ransac.py.
 // Float semantics: no FMA contraction (build with -ffp-contract=off), strictly left-to-right sums.
+// Pinned (round 2): the reference-AUTHORED logic restated here is bit-identical to the reference's own ransac.cpp / kabsch.cpp /
+// matcher.cpp compiled verbatim into oracle/_ref (tests/test_oracle_vs_ref_odometry.py, test_oracle_vs_ref_matcher.py); the PCL / Eigen
+// arithmetic named above is shared with that build (orc_tfc_transform, orc_llt3_solve, orc_svd3) and stays "parity unpinned".
 // =====================================================================================
 #include <algorithm>
 #include <cfloat>

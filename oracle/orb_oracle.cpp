@@ -12,9 +12,11 @@
 // tests/test_oracle_vs_cv2.py.
 //
 // PARITY STATUS: the reference ships no golden vectors / known-answer tests for this path
-//  and cannot be compiled here (needs OpenCV/PCL/Eigen headers, absent):
-// "parity unpinned" against a reference binary; pinned against cv2 for every stage that
-// the reference delegates to OpenCV, and against committed goldens (tests/golden/).
+//  and cannot be built as a whole here (needs OpenCV/PCL/Eigen, absent).
+// Pinned (round 2) against the reference's own Features/orbextractor.cpp compiled verbatim into
+// oracle/_ref over an OpenCV stand-in (tests/test_oracle_vs_ref.py: keypoints incl. order, angles,
+// descriptors, pyramid byte-identical); against cv2 for every stage the reference delegates to
+// OpenCV; against committed goldens (tests/golden/).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.  Build: oracle/Makefile  (g++ -O2 -ffp-contract=off, no -march=native:
