@@ -212,8 +212,9 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic",
            "config": config_object(args.frames),
-           "arm": {"frames_per_step": n, "note": "CPU oracle port of the reference path (extraction pinned against the reference's own orbextractor.cpp "
-                                                   "compiled in oracle/_ref; matcher / RANSAC need PCL + Eigen: not buildable here), g++ -O3 -march=native; "
+           "arm": {"frames_per_step": n, "note": "CPU oracle port of the reference path (bit-identical to the reference's own orbextractor.cpp / matcher.cpp / "
+                                                   "ransac.cpp compiled verbatim in oracle/_ref over stand-in OpenCV / PCL / Eigen headers; the real libraries are "
+                                                   "not in the image, so the timed arm is the port), g++ -O3 -march=native; "
                                                    "each step is a bounded sample of the workload"},
            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
