@@ -287,7 +287,8 @@ static int run_batch(orbf_context* c, int slot0, int n, const HostFrames* hf, co
                 if (track->rcfg && !pl.active) {
                     if (c->cfg.pipeline_overlap && c->hi && !c->profiling && !(hf && hf->gray)) {
                         // device inputs under pipeline_overlap: RANSAC (latency-bound, a few CTAs) goes to the high-priority side stream and
-                        // is not joined back here — the next call's pyramid / FAST on the other slot half run over it
+                        // is not joined back here — the next call's pyramid / FAST on the other slot half run over it.  (The matcher on the
+                        // side stream as well was measured: 2.526 -> 2.510 ms per step, 0.6 % — not kept.)
                         ORBF_CUDA(c, cudaEventRecord(c->evRansacIn, c->stream));
                         ORBF_CUDA(c, cudaStreamWaitEvent(c->hi, c->evRansacIn, 0));
                         { StreamSwap sw(c, c->hi); TRY(orbf_launch_ransac(c, slot_ransac_set(c), ps0 + pa, pb - pa, *track->rcfg, nullptr, false)); }
@@ -823,32 +824,6 @@ extern "C" int orbf_knn_match(orbf_context* c, const uint8_t* q, int32_t nq, con
 // Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks: desc holds every landmark's
 // observed descriptors back to back, offsets [n+1] delimits them; best[l] = row (inside landmark l) with the least median
 // Hamming distance to the others (-1 without observations), median[l] optional.  At most 128 observations per landmark count.
-extern "C" int orbf_distinctive_descriptors(orbf_context* c, const uint8_t* desc, const int32_t* offsets, int32_t n_landmarks, int32_t* best,
-    int32_t* median)
-{
-    CTX_ENTER(c);
-    if (!offsets || !best || n_landmarks < 0 || (n_landmarks > 0 && offsets[n_landmarks] > 0 && !desc)) return ORBF_ERR_ARG;
-    if (n_landmarks == 0) return ORBF_OK;
-    for (int l = 0; l < n_landmarks; ++l) if (offsets[l + 1] < offsets[l] || offsets[l] < 0) return ORBF_ERR_ARG;
-    const size_t rows = (size_t)offsets[n_landmarks];
-    uint8_t* dDesc = nullptr; int *dOff = nullptr, *dBest = nullptr;
-    auto freeAll = [&]() { if (dDesc) cudaFree(dDesc); if (dOff) cudaFree(dOff); if (dBest) cudaFree(dBest); };
-#define DD_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeAll(); return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } } while (0)
-    DD_CUDA(cudaMalloc((void**)&dDesc, std::max<size_t>(rows, 1) * 32));
-    DD_CUDA(cudaMalloc((void**)&dOff, ((size_t)n_landmarks + 1) * sizeof(int)));
-    DD_CUDA(cudaMalloc((void**)&dBest, (size_t)n_landmarks * 2 * sizeof(int)));
-    if (rows) DD_CUDA(cudaMemcpyAsync(dDesc, desc, rows * 32, cudaMemcpyHostToDevice, c->stream));
-    DD_CUDA(cudaMemcpyAsync(dOff, offsets, ((size_t)n_landmarks + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    const int rc = orbf_launch_distinctive(c, dDesc, dOff, n_landmarks, dBest, dBest + n_landmarks);
-    if (rc != ORBF_OK) { freeAll(); return rc; }
-    DD_CUDA(cudaMemcpyAsync(best, dBest, (size_t)n_landmarks * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (median) DD_CUDA(cudaMemcpyAsync(median, dBest + n_landmarks, (size_t)n_landmarks * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    DD_CUDA(cudaStreamSynchronize(c->stream));
-#undef DD_CUDA
-    freeAll();
-    return ORBF_OK;
-}
-
 // One device allocation carved into 256-byte aligned pieces, freed on scope exit (the §8f matcher entry points stage host arrays).
 namespace {
 struct Scratch {     // carve-up of the context's persistent device scratch: every user synchronises before it returns, so calls never overlap on it
@@ -875,6 +850,26 @@ struct Scratch {     // carve-up of the context's persistent device scratch: eve
 }  // namespace
 #define SC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } while (0)
 #define SC_H2D(off, src, bytes) do { if ((bytes) > 0) SC_CUDA(cudaMemcpyAsync(sc.base + (off), (src), (bytes), cudaMemcpyHostToDevice, c->stream)); } while (0)
+
+extern "C" int orbf_distinctive_descriptors(orbf_context* c, const uint8_t* desc, const int32_t* offsets, int32_t n_landmarks, int32_t* best,
+    int32_t* median)
+{
+    CTX_ENTER(c);
+    if (!offsets || !best || n_landmarks < 0 || (n_landmarks > 0 && offsets[n_landmarks] > 0 && !desc)) return ORBF_ERR_ARG;
+    if (n_landmarks == 0) return ORBF_OK;
+    for (int l = 0; l < n_landmarks; ++l) if (offsets[l + 1] < offsets[l] || offsets[l] < 0) return ORBF_ERR_ARG;
+    const size_t rows = (size_t)offsets[n_landmarks], L = (size_t)n_landmarks;
+    Scratch sc(c);
+    const size_t oDesc = sc.take(rows * 32), oOff = sc.take((L + 1) * sizeof(int)), oBest = sc.take(L * 2 * sizeof(int));
+    SC_CUDA(sc.alloc());
+    SC_H2D(oDesc, desc, rows * 32); SC_H2D(oOff, offsets, (L + 1) * sizeof(int));
+    int* dBest = sc.at<int>(oBest);
+    TRY(orbf_launch_distinctive(c, sc.at<uint8_t>(oDesc), sc.at<int>(oOff), n_landmarks, dBest, dBest + L));
+    SC_CUDA(cudaMemcpyAsync(best, dBest, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (median) SC_CUDA(cudaMemcpyAsync(median, dBest + L, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
+    return ORBF_OK;
+}
 
 extern "C" int orbf_fuse_search(orbf_context* c, int32_t slot, const float* Rcw, const float* tcw, const float* camera, const float* kp_x, const float* kp_y,
     const float* u_right, const uint8_t* desc, int32_t n_feat, const float* lm_pos, const uint8_t* lm_desc, const uint8_t* lm_valid, int32_t n_landmarks,
@@ -1018,43 +1013,27 @@ extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float*
     }
     if (feat_taken == nullptr && nFeat == 0) { for (int i = 0; i < n_landmarks; ++i) best_idx[i] = -1; return ORBF_OK; }
     const size_t L = (size_t)n_landmarks, F = (size_t)std::max(nFeat, 1);
-    // one allocation: landmark inputs | frame inputs (host route) | scratch | outputs
-    size_t off = 0;
-    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t oLmDesc = take(L * 32), oPx = take(L * 4), oPy = take(L * 4), oFlags = take(L), oTakenIn = take(F), oTaken = take(F);
-    const size_t oKx = take(F * 4), oKy = take(F * 4), oOct = take(F * 4), oDesc = take(F * 32);
-    const size_t oCand = take(L * F * 4), oCnt = take(L * 4), oBest = take((L + 1) * 4);
-    uint8_t* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, off);
-    if (e != cudaSuccess) return orbf_cuda_fail(c, e, "projection_match: scratch", __FILE__, __LINE__);
-#define PJ_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaFree(d); return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } } while (0)
-    PJ_CUDA(cudaMemcpyAsync(d + oLmDesc, lm_desc, L * 32, cudaMemcpyHostToDevice, c->stream));
-    PJ_CUDA(cudaMemcpyAsync(d + oPx, proj_x, L * 4, cudaMemcpyHostToDevice, c->stream));
-    PJ_CUDA(cudaMemcpyAsync(d + oPy, proj_y, L * 4, cudaMemcpyHostToDevice, c->stream));
-    PJ_CUDA(cudaMemcpyAsync(d + oFlags, lm_flags, L, cudaMemcpyHostToDevice, c->stream));
-    if (feat_taken && nFeat > 0) PJ_CUDA(cudaMemcpyAsync(d + oTakenIn, feat_taken, (size_t)nFeat, cudaMemcpyHostToDevice, c->stream));
+    // the context's persistent scratch: landmark inputs | frame inputs (host route) | candidate lists | outputs
+    Scratch sc(c);
+    const size_t oLmDesc = sc.take(L * 32), oPx = sc.take(L * 4), oPy = sc.take(L * 4), oFlags = sc.take(L), oTakenIn = sc.take(F);
+    const size_t oKx = sc.take(F * 4), oKy = sc.take(F * 4), oOct = sc.take(F * 4), oDesc = sc.take(F * 32);
+    const size_t oCand = sc.take(L * F * 4), oCnt = sc.take(L * 4), oBest = sc.take((L + 1) * 4);
+    SC_CUDA(sc.alloc());
+    SC_H2D(oLmDesc, lm_desc, L * 32); SC_H2D(oPx, proj_x, L * 4); SC_H2D(oPy, proj_y, L * 4); SC_H2D(oFlags, lm_flags, L);
+    if (feat_taken && nFeat > 0) SC_H2D(oTakenIn, feat_taken, (size_t)nFeat);
     const float *dKx, *dKy; const int* dOct; const uint8_t* dDesc;
     if (slot >= 0) {
         dKx = c->d_kpux + (size_t)slot * c->K; dKy = c->d_kpuy + (size_t)slot * c->K; dOct = c->d_kpoct + (size_t)slot * c->K; dDesc = c->d_desc + (size_t)slot * c->K * 32;
     } else {
-        if (nFeat > 0) {
-            PJ_CUDA(cudaMemcpyAsync(d + oKx, kp_x, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
-            PJ_CUDA(cudaMemcpyAsync(d + oKy, kp_y, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
-            PJ_CUDA(cudaMemcpyAsync(d + oOct, kp_octave, (size_t)nFeat * 4, cudaMemcpyHostToDevice, c->stream));
-            PJ_CUDA(cudaMemcpyAsync(d + oDesc, desc, (size_t)nFeat * 32, cudaMemcpyHostToDevice, c->stream));
-        }
-        dKx = reinterpret_cast<const float*>(d + oKx); dKy = reinterpret_cast<const float*>(d + oKy); dOct = reinterpret_cast<const int*>(d + oOct); dDesc = d + oDesc;
+        if (nFeat > 0) { SC_H2D(oKx, kp_x, (size_t)nFeat * 4); SC_H2D(oKy, kp_y, (size_t)nFeat * 4); SC_H2D(oOct, kp_octave, (size_t)nFeat * 4); SC_H2D(oDesc, desc, (size_t)nFeat * 32); }
+        dKx = sc.at<float>(oKx); dKy = sc.at<float>(oKy); dOct = sc.at<int>(oOct); dDesc = sc.at<uint8_t>(oDesc);
     }
-    int* dBest = reinterpret_cast<int*>(d + oBest);
-    const int rc = orbf_launch_projection_match(c, dKx, dKy, dOct, dDesc, nFeat, d + oLmDesc, reinterpret_cast<const float*>(d + oPx), reinterpret_cast<const float*>(d + oPy),
-        d + oFlags, n_landmarks, (feat_taken && nFeat > 0) ? d + oTakenIn : nullptr, radius, nn_ratio, th_high, reinterpret_cast<uint32_t*>(d + oCand),
-        reinterpret_cast<int*>(d + oCnt), d + oTaken, dBest, dBest + L);
-    if (rc != ORBF_OK) { cudaFree(d); return rc; }
-    PJ_CUDA(cudaMemcpyAsync(best_idx, dBest, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    PJ_CUDA(cudaMemcpyAsync(n_matches, dBest + L, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    PJ_CUDA(cudaStreamSynchronize(c->stream));
-#undef PJ_CUDA
-    cudaFree(d);
+    int* dBest = sc.at<int>(oBest);
+    TRY(orbf_launch_projection_match(c, dKx, dKy, dOct, dDesc, nFeat, sc.at<uint8_t>(oLmDesc), sc.at<float>(oPx), sc.at<float>(oPy), sc.at<uint8_t>(oFlags), n_landmarks,
+        (feat_taken && nFeat > 0) ? sc.at<uint8_t>(oTakenIn) : nullptr, radius, nn_ratio, th_high, sc.at<uint32_t>(oCand), sc.at<int>(oCnt), dBest, dBest + L));
+    SC_CUDA(cudaMemcpyAsync(best_idx, dBest, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaMemcpyAsync(n_matches, dBest + L, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(cudaStreamSynchronize(c->stream));
     return ORBF_OK;
 }
 
