@@ -1017,7 +1017,7 @@ extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float*
     Scratch sc(c);
     const size_t oLmDesc = sc.take(L * 32), oPx = sc.take(L * 4), oPy = sc.take(L * 4), oFlags = sc.take(L), oTakenIn = sc.take(F);
     const size_t oKx = sc.take(F * 4), oKy = sc.take(F * 4), oOct = sc.take(F * 4), oDesc = sc.take(F * 32);
-    const size_t oCand = sc.take(L * F * 4), oCnt = sc.take(L * 4), oBest = sc.take((L + 1) * 4);
+    const size_t oCand = sc.take(L * F * 4), oCandOct = sc.take(L * 8 * 4), oCnt = sc.take(L * 4), oBest = sc.take((L + 1) * 4);
     SC_CUDA(sc.alloc());
     SC_H2D(oLmDesc, lm_desc, L * 32); SC_H2D(oPx, proj_x, L * 4); SC_H2D(oPy, proj_y, L * 4); SC_H2D(oFlags, lm_flags, L);
     if (feat_taken && nFeat > 0) SC_H2D(oTakenIn, feat_taken, (size_t)nFeat);
@@ -1030,7 +1030,7 @@ extern "C" int orbf_projection_match(orbf_context* c, int32_t slot, const float*
     }
     int* dBest = sc.at<int>(oBest);
     TRY(orbf_launch_projection_match(c, dKx, dKy, dOct, dDesc, nFeat, sc.at<uint8_t>(oLmDesc), sc.at<float>(oPx), sc.at<float>(oPy), sc.at<uint8_t>(oFlags), n_landmarks,
-        (feat_taken && nFeat > 0) ? sc.at<uint8_t>(oTakenIn) : nullptr, radius, nn_ratio, th_high, sc.at<uint32_t>(oCand), sc.at<int>(oCnt), dBest, dBest + L));
+        (feat_taken && nFeat > 0) ? sc.at<uint8_t>(oTakenIn) : nullptr, radius, nn_ratio, th_high, sc.at<uint32_t>(oCand), sc.at<int>(oCandOct), sc.at<int>(oCnt), dBest, dBest + L));
     SC_CUDA(cudaMemcpyAsync(best_idx, dBest, L * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SC_CUDA(cudaMemcpyAsync(n_matches, dBest + L, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SC_CUDA(cudaStreamSynchronize(c->stream));

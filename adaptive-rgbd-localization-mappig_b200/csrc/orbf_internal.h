@@ -249,7 +249,7 @@ int orbf_launch_bow_match(orbf_context* ctx, const int* d_words1, const int* d_o
     int* d_firstUser, orbf_dmatch* d_out, int* d_nOut);
 int orbf_launch_projection_match(orbf_context* ctx, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat,
     const uint8_t* d_lmDesc, const float* d_projX, const float* d_projY, const uint8_t* d_lmFlags, int nLm, const uint8_t* d_featTaken, float radius, float nnRatio,
-    int thHigh, uint32_t* d_cand, int* d_candCount, int* d_bestIdx, int* d_nMatches);
+    int thHigh, uint32_t* d_cand, int* d_candOct /* [nLm][8] */, int* d_candCount, int* d_bestIdx, int* d_nMatches);
 int orbf_launch_match_select(orbf_context* ctx, const MatchSet& ms, int npairs, float ratio, bool cross);
 // RANSAC
 int orbf_launch_kabsch(orbf_context* ctx, const float* dA, const float* dB, int n, float* dT);

@@ -22,9 +22,11 @@ namespace {
 
 constexpr uint32_t PJ_NONE = 0xFFFFFFFFu;
 
-__global__ void __launch_bounds__(128) proj_candidates_kernel(const float* __restrict__ kpx, const float* __restrict__ kpy, const uint8_t* __restrict__ desc, int nFeat,
-    const uint8_t* __restrict__ lmDesc, const float* __restrict__ projX, const float* __restrict__ projY, const uint8_t* __restrict__ lmFlags, int nLm, float radius,
-    uint32_t* __restrict__ cand, int* __restrict__ candCount)
+constexpr int PJ_REG = 8;          // candidates per landmark the resolve pass keeps in registers
+
+__global__ void __launch_bounds__(128) proj_candidates_kernel(const float* __restrict__ kpx, const float* __restrict__ kpy, const int* __restrict__ kpOct,
+    const uint8_t* __restrict__ desc, int nFeat, const uint8_t* __restrict__ lmDesc, const float* __restrict__ projX, const float* __restrict__ projY,
+    const uint8_t* __restrict__ lmFlags, int nLm, float radius, uint32_t* __restrict__ cand, int* __restrict__ candOct /* [nLm][PJ_REG] */, int* __restrict__ candCount)
 {
     const int lane = threadIdx.x & 31, i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= nLm) return;
@@ -45,7 +47,9 @@ __global__ void __launch_bounds__(128) proj_candidates_kernel(const float* __res
                 const uint4 fa = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32)), fb = __ldg(reinterpret_cast<const uint4*>(desc + (size_t)j * 32) + 1);
                 const int d = __popc(la.x ^ fa.x) + __popc(la.y ^ fa.y) + __popc(la.z ^ fa.z) + __popc(la.w ^ fa.w)
                             + __popc(lb.x ^ fb.x) + __popc(lb.y ^ fb.y) + __popc(lb.z ^ fb.z) + __popc(lb.w ^ fb.w);
-                out[n + __popc(m & ((1u << lane) - 1))] = ((uint32_t)d << 16) | (uint32_t)j;
+                const int pos = n + __popc(m & ((1u << lane) - 1));
+                out[pos] = ((uint32_t)d << 16) | (uint32_t)j;
+                if (pos < PJ_REG) candOct[(size_t)i * PJ_REG + pos] = kpOct[j];
             }
             n += __popc(m);
         }
@@ -60,59 +64,93 @@ __device__ __forceinline__ void pj_insert(uint32_t& m1, uint32_t& m2, uint32_t k
 }
 
 // One warp, landmarks in order.  The pass is latency-, not work-bound (a window holds a handful of candidates), so nothing of a
-// landmark's turn may wait on global memory: the warp takes 32 landmarks at a time — lane L fetches landmark L's count, its first
-// PJ_REG candidate keys and their octaves into registers (independent loads, all in flight together) — and then walks the batch in
-// order with the taken flags in shared memory; the owning lane decides its landmark alone from registers.  A landmark with more
-// than PJ_REG candidates (crowded windows) is resolved by the whole warp from the candidate list instead.
-constexpr int PJ_REG = 8;
+// landmark's turn may wait on global memory and as few turns as possible may wait on each other:
+//   * the warp takes 32 landmarks at a time — lane L holds landmark L's count, its first PJ_REG candidate keys and their octaves in
+//     registers, fetched while the previous batch was resolved;
+//   * every lane decides its landmark at once against the taken flags (shared memory) as they stand; a lane whose candidates include
+//     a feature that an EARLIER lane of the batch has just accepted (and will mark taken) is in conflict: everything before the first
+//     such lane is final and is committed, the rest decides again.  Without contention a batch takes one round;
+//   * a landmark with more than PJ_REG candidates (crowded windows) is resolved in its turn by the whole warp from the candidate list.
+// Among a landmark's free candidates the two smallest (distance << 16 | feature) keys are exactly the reference's (best, second best)
+// under its strict '<' updates in feature order.
+struct PjBatch { int n, fl; uint32_t k[PJ_REG]; int oc[PJ_REG]; };
 
-__global__ void __launch_bounds__(32) proj_resolve_kernel(const uint32_t* __restrict__ cand, const int* __restrict__ candCount, const int* __restrict__ kpOct, int nFeat,
-    const uint8_t* __restrict__ lmFlags, int nLm, const uint8_t* __restrict__ featTaken, float nnRatio, int thHigh, int* __restrict__ bestIdx,
-    int* __restrict__ nMatches)
+__device__ __forceinline__ void pj_load(PjBatch& b, int i, int nLm, int nFeat, const uint32_t* __restrict__ cand, const int* __restrict__ candOct,
+    const int* __restrict__ candCount, const uint8_t* __restrict__ lmFlags)
+{
+    b.fl = i < nLm ? lmFlags[i] : 0;
+    b.n = (b.fl & 1) ? candCount[i] : 0;
+#pragma unroll
+    for (int c = 0; c < PJ_REG; ++c) {
+        const bool on = c < b.n && b.n <= PJ_REG;
+        b.k[c] = on ? cand[(size_t)i * nFeat + c] : PJ_NONE;
+        b.oc[c] = on ? candOct[(size_t)i * PJ_REG + c] : -1;
+    }
+}
+
+__global__ void __launch_bounds__(32) proj_resolve_kernel(const uint32_t* __restrict__ cand, const int* __restrict__ candOct, const int* __restrict__ candCount,
+    const int* __restrict__ kpOct, int nFeat, const uint8_t* __restrict__ lmFlags, int nLm, const uint8_t* __restrict__ featTaken, float nnRatio, int thHigh,
+    int* __restrict__ bestIdx, int* __restrict__ nMatches)
 {
     extern __shared__ uint8_t taken[];                        // [nFeat]
     const int lane = threadIdx.x;
+    PjBatch cur, nxt;
+    pj_load(cur, lane, nLm, nFeat, cand, candOct, candCount, lmFlags);
     for (int j = lane; j < nFeat; j += 32) taken[j] = featTaken ? featTaken[j] : 0;
     __syncwarp();
     int nm = 0;
     for (int i0 = 0; i0 < nLm; i0 += 32) {
-        const int i = i0 + lane;
-        const int fl = i < nLm ? lmFlags[i] : 0;
-        const int n = (fl & 1) ? candCount[i] : 0;
-        uint32_t k[PJ_REG]; int oc[PJ_REG];
-#pragma unroll
-        for (int c = 0; c < PJ_REG; ++c) k[c] = (c < n && n <= PJ_REG) ? cand[(size_t)i * nFeat + c] : PJ_NONE;
-#pragma unroll
-        for (int c = 0; c < PJ_REG; ++c) oc[c] = (k[c] != PJ_NONE) ? kpOct[k[c] & 0xFFFFu] : -1;
+        pj_load(nxt, i0 + 32 + lane, nLm, nFeat, cand, candOct, candCount, lmFlags);          // in flight while this batch is resolved
         int best = -1;
-        unsigned todo = __ballot_sync(0xffffffffu, n > 0);
-        while (todo) {
-            const int b = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int nb = __shfl_sync(0xffffffffu, n, b);
-            if (nb <= PJ_REG) {
-                if (lane == b) {
+        const unsigned big = __ballot_sync(0xffffffffu, cur.n > PJ_REG);
+        unsigned pending = __ballot_sync(0xffffffffu, cur.n > 0 && cur.n <= PJ_REG);
+        int pos = 0;
+        while (pos < 32) {
+            const unsigned bigRem = big & (0xffffffffu << pos);
+            const int stop = bigRem ? __ffs(bigRem) - 1 : 32;
+            const unsigned range = (stop >= 32 ? 0xffffffffu : ((1u << stop) - 1)) & (0xffffffffu << pos);
+            unsigned grp = pending & range;
+            while (grp) {
+                const bool mine = (grp >> lane) & 1;
+                int acc = -1;
+                if (mine) {
                     uint32_t k1 = PJ_NONE, k2 = PJ_NONE; int o1 = -1, o2 = -1;
 #pragma unroll
                     for (int c = 0; c < PJ_REG; ++c) {
-                        const uint32_t key = k[c];
+                        const uint32_t key = cur.k[c];
                         if (key != PJ_NONE && !taken[key & 0xFFFFu]) {
-                            if (key < k1) { k2 = k1; o2 = o1; k1 = key; o1 = oc[c]; }
-                            else if (key < k2) { k2 = key; o2 = oc[c]; }
+                            if (key < k1) { k2 = k1; o2 = o1; k1 = key; o1 = cur.oc[c]; }
+                            else if (key < k2) { k2 = key; o2 = cur.oc[c]; }
                         }
                     }
-                    if (k1 != PJ_NONE && (int)(k1 >> 16) <= thHigh) {
-                        // bestLevel == bestLevel2 && bestDist1 > mfNNratio * bestDist2 (float ratio promoted to double)
-                        const bool rej = k2 != PJ_NONE && o1 == o2 && (double)(k1 >> 16) > __dmul_rn((double)nnRatio, (double)(k2 >> 16));
-                        if (!rej) {
-                            best = (int)(k1 & 0xFFFFu);
-                            ++nm;
-                            if (fl & 2) taken[best] = 1;
-                        }
+                    // bestDist1 <= TH_HIGH, and not (bestLevel == bestLevel2 && bestDist1 > mfNNratio * bestDist2) — float ratio promoted to double
+                    if (k1 != PJ_NONE && (int)(k1 >> 16) <= thHigh
+                        && !(k2 != PJ_NONE && o1 == o2 && (double)(k1 >> 16) > __dmul_rn((double)nnRatio, (double)(k2 >> 16))))
+                        acc = (int)(k1 & 0xFFFFu);
+                }
+                // features this round would mark taken, and the lanes after their owner that hold them as a candidate
+                unsigned takers = __ballot_sync(0xffffffffu, mine && acc >= 0 && (cur.fl & 2));
+                bool conflict = false;
+                while (takers) {
+                    const int a = __ffs(takers) - 1;
+                    takers &= takers - 1;
+                    const uint32_t tj = (uint32_t)__shfl_sync(0xffffffffu, acc, a);
+                    if (mine && lane > a) {
+#pragma unroll
+                        for (int c = 0; c < PJ_REG; ++c) conflict |= cur.k[c] != PJ_NONE && (cur.k[c] & 0xFFFFu) == tj;
                     }
                 }
-            } else {
-                const int ib = i0 + b, flb = __shfl_sync(0xffffffffu, fl, b);
+                const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+                const unsigned fin = cm ? ((1u << (__ffs(cm) - 1)) - 1) : 0xffffffffu;         // lanes before the first conflict are final
+                if (mine && ((fin >> lane) & 1)) {
+                    best = acc;
+                    if (acc >= 0) { ++nm; if (cur.fl & 2) taken[acc] = 1; }
+                }
+                __syncwarp();
+                grp &= ~fin;
+            }
+            if (stop < 32) {        // a crowded window: the whole warp on landmark i0 + stop
+                const int ib = i0 + stop, nb = __shfl_sync(0xffffffffu, cur.n, stop), flb = __shfl_sync(0xffffffffu, cur.fl, stop);
                 uint32_t k1 = PJ_NONE, k2 = PJ_NONE;
                 for (int c = lane; c < nb; c += 32) {
                     const uint32_t key = cand[(size_t)ib * nFeat + c];
@@ -131,16 +169,18 @@ __global__ void __launch_bounds__(32) proj_resolve_kernel(const uint32_t* __rest
                         const int j2 = (int)(k2 & 0xFFFFu);
                         if (kpOct[j1] == kpOct[j2] && (double)(k1 >> 16) > __dmul_rn((double)nnRatio, (double)(k2 >> 16))) ok = false;
                     }
-                    if (ok && lane == b) {
+                    if (ok && lane == stop) {
                         best = j1;
                         ++nm;
                         if (flb & 2) taken[j1] = 1;
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
+            pos = stop + 1;
         }
-        if (i < nLm) bestIdx[i] = best;
+        if (i0 + lane < nLm) bestIdx[i0 + lane] = best;
+        cur = nxt;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
@@ -323,14 +363,15 @@ int orbf_launch_unproject(orbf_context* c, const float* d_xy, const uint16_t* d_
 
 int orbf_launch_projection_match(orbf_context* c, const float* d_kpx, const float* d_kpy, const int* d_kpoct, const uint8_t* d_desc, int nFeat, const uint8_t* d_lmDesc,
     const float* d_projX, const float* d_projY, const uint8_t* d_lmFlags, int nLm, const uint8_t* d_featTaken, float radius, float nnRatio, int thHigh,
-    uint32_t* d_cand, int* d_candCount, int* d_bestIdx, int* d_nMatches)
+    uint32_t* d_cand, int* d_candOct, int* d_candCount, int* d_bestIdx, int* d_nMatches)
 {
     if (nLm <= 0) return ORBF_OK;
-    proj_candidates_kernel<<<(nLm + 3) / 4, 128, 0, c->stream>>>(d_kpx, d_kpy, d_desc, nFeat, d_lmDesc, d_projX, d_projY, d_lmFlags, nLm, radius, d_cand, d_candCount);
+    proj_candidates_kernel<<<(nLm + 3) / 4, 128, 0, c->stream>>>(d_kpx, d_kpy, d_kpoct, d_desc, nFeat, d_lmDesc, d_projX, d_projY, d_lmFlags, nLm, radius, d_cand, d_candOct,
+        d_candCount);
     ORBF_LAUNCH_CHECK(c);
     const size_t smem = (size_t)std::max(nFeat, 1);           // nFeat <= 65535 (16-bit feature index in the candidate keys)
     ORBF_CUDA(c, cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    proj_resolve_kernel<<<1, 32, smem, c->stream>>>(d_cand, d_candCount, d_kpoct, nFeat, d_lmFlags, nLm, d_featTaken, nnRatio, thHigh, d_bestIdx, d_nMatches);
+    proj_resolve_kernel<<<1, 32, smem, c->stream>>>(d_cand, d_candOct, d_candCount, d_kpoct, nFeat, d_lmFlags, nLm, d_featTaken, nnRatio, thHigh, d_bestIdx, d_nMatches);
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }
