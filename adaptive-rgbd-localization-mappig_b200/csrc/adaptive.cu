@@ -409,23 +409,18 @@ extern "C" int orbf_adaptive_detect(orbf_context* c, const orbf_adaptive_config*
     P.candCap = candCap;
     const int B = std::min<int>(n, AD_BATCH);
     const int pitch = align_up(w, 128);
-    // scratch of one sub-batch (allocated per call: this route is a controller around one kernel, not the throughput path)
-    uint8_t *dIn = nullptr, *dScore = nullptr; uint32_t* dCand = nullptr; int *dCandCount = nullptr, *dGe = nullptr, *dFinal = nullptr, *dFound = nullptr,
-            *dUnder = nullptr, *dOutCount = nullptr; double* dThresh = nullptr; orbf_keypoint* dOut = nullptr;
-    auto freeAll = [&]() { for (void* p : { (void*)dIn, (void*)dScore, (void*)dCand, (void*)dCandCount, (void*)dGe, (void*)dFinal, (void*)dFound, (void*)dUnder,
-                                   (void*)dOutCount, (void*)dThresh, (void*)dOut }) if (p) cudaFree(p); };
-#define AD_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeAll(); return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } } while (0)
-    AD_CUDA(cudaMalloc((void**)&dIn, (size_t)B * pitch * h));
-    AD_CUDA(cudaMalloc((void**)&dScore, (size_t)B * pitch * h + 256));
-    AD_CUDA(cudaMalloc((void**)&dCand, (size_t)B * nCells * candCap * sizeof(uint32_t)));
-    AD_CUDA(cudaMalloc((void**)&dCandCount, (size_t)B * nCells * sizeof(int)));
-    AD_CUDA(cudaMalloc((void**)&dGe, (size_t)B * nCells * 257 * sizeof(int)));
-    AD_CUDA(cudaMalloc((void**)&dFinal, (size_t)B * nCells * sizeof(int)));
-    AD_CUDA(cudaMalloc((void**)&dFound, (size_t)B * nCells * sizeof(int)));
-    AD_CUDA(cudaMalloc((void**)&dUnder, sizeof(int)));
-    AD_CUDA(cudaMalloc((void**)&dOutCount, (size_t)B * nCells * sizeof(int)));
-    AD_CUDA(cudaMalloc((void**)&dThresh, (size_t)nCells * sizeof(double)));
-    AD_CUDA(cudaMalloc((void**)&dOut, (size_t)B * nCells * cfg->max_per_cell * sizeof(orbf_keypoint)));
+    // scratch of one sub-batch: pieces of the context's persistent scratch (no allocation per call once it has grown)
+    Scratch sc(c);
+    const size_t oIn = sc.take((size_t)B * pitch * h), oScore = sc.take((size_t)B * pitch * h + 256), oCand = sc.take((size_t)B * nCells * candCap * sizeof(uint32_t));
+    const size_t oCandCount = sc.take((size_t)B * nCells * sizeof(int)), oGe = sc.take((size_t)B * nCells * 257 * sizeof(int)), oFinal = sc.take((size_t)B * nCells * sizeof(int));
+    const size_t oFound = sc.take((size_t)B * nCells * sizeof(int)), oUnder = sc.take(sizeof(int)), oOutCount = sc.take((size_t)B * nCells * sizeof(int));
+    const size_t oThresh = sc.take((size_t)nCells * sizeof(double)), oOut = sc.take((size_t)B * nCells * cfg->max_per_cell * sizeof(orbf_keypoint));
+#define AD_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } while (0)
+    AD_CUDA(sc.alloc());
+    uint8_t *dIn = sc.at<uint8_t>(oIn), *dScore = sc.at<uint8_t>(oScore); uint32_t* dCand = sc.at<uint32_t>(oCand);
+    int *dCandCount = sc.at<int>(oCandCount), *dGe = sc.at<int>(oGe), *dFinal = sc.at<int>(oFinal), *dFound = sc.at<int>(oFound), *dUnder = sc.at<int>(oUnder),
+        *dOutCount = sc.at<int>(oOutCount);
+    double* dThresh = sc.at<double>(oThresh); orbf_keypoint* dOut = sc.at<orbf_keypoint>(oOut);
     P.score = dScore; P.scoreFrameStride = (long long)pitch * h; P.scorePitch = pitch;
     P.cand = dCand; P.candCount = dCandCount; P.ge = dGe; P.finalTh = dFinal; P.found = dFound; P.under = dUnder; P.thresh = dThresh;
     P.outKp = dOut; P.outCount = dOutCount;
@@ -503,7 +498,6 @@ extern "C" int orbf_adaptive_detect(orbf_context* c, const orbf_adaptive_config*
             if (out) std::copy(all.begin(), all.end(), out + (size_t)(f0 + i) * cap);
         }
     }
-    freeAll();
 #undef AD_CUDA
     if (rc == ORBF_OK) std::copy(st.begin(), st.end(), thresh);
     return rc;

@@ -824,30 +824,6 @@ extern "C" int orbf_knn_match(orbf_context* c, const uint8_t* q, int32_t nq, con
 // Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) for a batch of landmarks: desc holds every landmark's
 // observed descriptors back to back, offsets [n+1] delimits them; best[l] = row (inside landmark l) with the least median
 // Hamming distance to the others (-1 without observations), median[l] optional.  At most 128 observations per landmark count.
-// One device allocation carved into 256-byte aligned pieces, freed on scope exit (the §8f matcher entry points stage host arrays).
-namespace {
-struct Scratch {     // carve-up of the context's persistent device scratch: every user synchronises before it returns, so calls never overlap on it
-    orbf_context* ctx; uint8_t* base = nullptr; size_t size = 0;
-    explicit Scratch(orbf_context* c) : ctx(c) {}
-    size_t take(size_t bytes) { const size_t o = size; size = (size + std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; return o; }
-    cudaError_t alloc()
-    {
-        if (size > ctx->scratchCap) {
-            cudaError_t e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) return e;
-            if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-            ctx->d_scratch = nullptr; ctx->scratchCap = 0;
-            const size_t cap = (size + (1u << 20)) & ~(size_t)((1u << 20) - 1);
-            e = cudaMalloc((void**)&ctx->d_scratch, cap);
-            if (e != cudaSuccess) return e;
-            ctx->scratchCap = cap;
-        }
-        base = ctx->d_scratch;
-        return cudaSuccess;
-    }
-    template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
-};
-}  // namespace
 #define SC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return orbf_cuda_fail(c, e__, #call, __FILE__, __LINE__); } while (0)
 #define SC_H2D(off, src, bytes) do { if ((bytes) > 0) SC_CUDA(cudaMemcpyAsync(sc.base + (off), (src), (bytes), cudaMemcpyHostToDevice, c->stream)); } while (0)
 

@@ -262,3 +262,28 @@ int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);
 int orbf_launch_ransac_clouds(orbf_context* ctx, int pair0, int npairs);
 int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
     const int* d_userSamples, bool standalone, bool fullTable = false, bool probeOnly = false);
+
+// Carve-up of the context's persistent device scratch (host-in / host-out helper calls: the section-8f matcher entry points, the adaptive
+// detector): 256-byte aligned pieces of ONE allocation that grows and is never freed per call.  Every user synchronises the context
+// stream before it returns, so calls never overlap on it.
+struct Scratch {
+    orbf_context* ctx; uint8_t* base = nullptr; size_t size = 0;
+    explicit Scratch(orbf_context* c) : ctx(c) {}
+    size_t take(size_t bytes) { const size_t o = size; size = (size + (bytes ? bytes : 1) + 255) & ~(size_t)255; return o; }
+    cudaError_t alloc()
+    {
+        if (size > ctx->scratchCap) {
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) return e;
+            if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+            ctx->d_scratch = nullptr; ctx->scratchCap = 0;
+            const size_t cap = (size + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+            e = cudaMalloc((void**)&ctx->d_scratch, cap);
+            if (e != cudaSuccess) return e;
+            ctx->scratchCap = cap;
+        }
+        base = ctx->d_scratch;
+        return cudaSuccess;
+    }
+    template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
+};
