@@ -97,6 +97,13 @@ static int run_extract(orbf_context* c, int slot0, int n, bool sideStream)
         orbf_prof_begin(c, ST_QUADTREE); TRY(orbf_launch_quadtree(c, slot0, n)); orbf_prof_end(c, ST_QUADTREE);
         orbf_prof_begin(c, ST_BLUR); TRY(orbf_launch_blur(c, slot0, n)); orbf_prof_end(c, ST_BLUR);
     }
+    if (c->pendDepthSrc) {
+        // one-frame call: the depth plane goes into the page-locked arena now, on the host, while the kernels queued above run; the
+        // describe kernel (launched after this copy has finished) samples it in place
+        const int w = c->cfg.width, h = c->cfg.height;
+        for (int y = 0; y < h; ++y) memcpy(c->pendDepthDst + (size_t)y * w, c->pendDepthSrc + (size_t)y * c->pendDepthStride, (size_t)w * 2);
+        c->pendDepthSrc = nullptr;
+    }
     orbf_prof_begin(c, ST_DESCRIBE); TRY(orbf_launch_describe(c, slot0, n)); orbf_prof_end(c, ST_DESCRIBE);
     return ORBF_OK;
 }
@@ -375,13 +382,14 @@ extern "C" int orbf_extract_batch(orbf_context* c, int32_t slot0, int32_t n, con
         TRY(arena_begin(c, (size_t)w * h * (withDepth ? 3 : 1) + 1024));
         uint8_t* g = arena_take(c, (size_t)w * h);
         for (int y = 0; y < h; ++y) memcpy(g + (size_t)y * w, gray + (size_t)y * gray_stride, (size_t)w);
-        uint16_t* d = nullptr;
-        if (withDepth) {
-            d = reinterpret_cast<uint16_t*>(arena_take(c, (size_t)w * h * 2));
-            for (int y = 0; y < h; ++y) memcpy(d + (size_t)y * w, depth + (size_t)y * depth_stride_elems, (size_t)w * 2);
-        }
+        uint16_t* d = withDepth ? reinterpret_cast<uint16_t*>(arena_take(c, (size_t)w * h * 2)) : nullptr;
         TRY(set_host_inputs(c, slot0, 1, g, w, (int64_t)w * h, d, w, (int64_t)w * h, hf));
+        if (withDepth) {
+            if (hf.depthInPlace) { c->pendDepthSrc = depth; c->pendDepthDst = d; c->pendDepthStride = depth_stride_elems; }   // copied under the kernels (run_extract)
+            else for (int y = 0; y < h; ++y) memcpy(d + (size_t)y * w, depth + (size_t)y * depth_stride_elems, (size_t)w * 2);
+        }
         const int r = run_batch(c, slot0, 1, &hf, nullptr);
+        c->pendDepthSrc = nullptr;
         if (r != ORBF_OK) return r;
         return arena_fence(c, c->stream);
     }

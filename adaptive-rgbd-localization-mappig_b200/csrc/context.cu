@@ -373,7 +373,7 @@ extern "C" int orbf_create(const orbf_config* cfg, orbf_context** out)
     for (void*& q : c->peerOpened) q = nullptr;
     c->h_kp = nullptr; c->h_desc = nullptr; c->h_xyz = nullptr; c->h_counts = nullptr;
     c->h_arena = nullptr; c->arenaCap = 0; c->arenaUsed = 0; c->evArena = nullptr; c->arenaBusy = false;
-    c->d_scratch = nullptr; c->scratchCap = 0;
+    c->d_scratch = nullptr; c->scratchCap = 0; c->pendDepthSrc = nullptr; c->pendDepthDst = nullptr; c->pendDepthStride = 0;
     auto cu = [&](cudaError_t e3, const char* w) { if (e3 != cudaSuccess) { orbf_cuda_fail(c, e3, w, __FILE__, __LINE__); return false; } return true; };
     if (!cu(cudaMemcpy(c->d_resizeTab, tab.data(), tab.size() * sizeof(ResizeCoef), cudaMemcpyHostToDevice), "tab")) return fail(ORBF_ERR_CUDA);
     if (!cu(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice), "cells")) return fail(ORBF_ERR_CUDA);

@@ -147,6 +147,8 @@ struct orbf_context {
     // page-locked staging arena of the one-frame-at-a-time calls (orbf_extract*, orbf_knn_match, orbf_ransac_iterate): pageable caller
     // buffers are copied through it so that every transfer of a call is asynchronous and the call synchronises once
     uint8_t* h_arena; size_t arenaCap, arenaUsed; cudaEvent_t evArena; bool arenaBusy;
+    // one-frame call: depth plane still to be copied into the staging arena, done on the host under the pyramid / FAST / quadtree kernels
+    const uint16_t* pendDepthSrc; uint16_t* pendDepthDst; int64_t pendDepthStride;
     uint8_t* d_scratch; size_t scratchCap;       // device scratch of the host-in / host-out helper calls (grows, never freed per call)
 
     // matching (pair slots)
