@@ -453,6 +453,22 @@ class Context:
                     used_identity=bool(res.used_identity), depth_cov=float(res.depth_cov_used), hyp=hyp,
                     good_sorted=good[:res.n_good].copy(), sample_table=tab_out)
 
+    def odometry_compute(self, src_xyz, dst_xyz, m12, pose1=None, **kw):
+        """Odometry::Compute, RANSAC strategy, for one frame pair in one call (Odometry/odometry.cpp:44-90): the ransac_iterate result plus
+        cloud_src / cloud_tgt ([n, 4] pcl::PointXYZ records) and pose2 = T12 * pose1."""
+        cfg = default_ransac_config(**kw)
+        src = np.ascontiguousarray(src_xyz, np.float32); dst = np.ascontiguousarray(dst_xyz, np.float32)
+        m12 = np.ascontiguousarray(m12, DMATCH_DT)
+        res = RansacResult(); inl = np.zeros(max(len(m12), 1), DMATCH_DT)
+        cs = np.zeros((max(len(m12), 1), 4), np.float32); ct = np.zeros_like(cs); nc = C.c_int32(0)
+        p1 = None if pose1 is None else np.ascontiguousarray(pose1, np.float32).reshape(16)
+        p2 = np.zeros(16, np.float32)
+        self._chk(lib().orbf_odometry_compute(self._h, C.byref(cfg), _p(src), len(src), _p(dst), len(dst), _p(m12), len(m12), _p(inl), len(inl), C.byref(res),
+                                              _p(cs), _p(ct), len(m12), C.byref(nc), _p(p1) if p1 is not None else None, _p(p2)), "odometry_compute")
+        return dict(ok=bool(res.ok), rmse=float(res.rmse), T12=np.array(res.T12, np.float32).reshape(4, 4), inliers=inl[:res.n_inliers].copy(),
+                    n_good=res.n_good, depth_cov=float(res.depth_cov_used), cloud_src=cs[:nc.value].copy(), cloud_tgt=ct[:nc.value].copy(),
+                    pose2=p2.reshape(4, 4))
+
     def ransac_pairs(self, npairs, **kw):
         cfg = default_ransac_config(**kw)
         self._chk(lib().orbf_ransac_pairs(self._h, npairs, C.byref(cfg)), "ransac_pairs")

@@ -1138,11 +1138,16 @@ extern "C" int orbf_download_ransac_summary(orbf_context* c, int32_t npairs, orb
     return ORBF_OK;
 }
 
-extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc,
+namespace {
+// what Odometry::Compute adds to Ransac::Iterate (orbf_odometry_compute): the GICP clouds and the composed pose, queued behind the
+// RANSAC chain and brought back by the same single synchronisation
+struct OdometryExtras { float* cloudSrc; float* cloudTgt; int cloudCap; int* nCloud; const float* pose1; float* pose2; };
+}  // namespace
+
+static int ransac_iterate_core(orbf_context* c, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc,
     const float* dst_xyz, int32_t ndst, const orbf_dmatch* m12, int32_t nm, const int32_t* sample_table, orbf_dmatch* inliers_out,
-    int32_t cap, orbf_ransac_result* out, orbf_hyp_trace* hyp_trace, orbf_dmatch* good_sorted_out, int32_t* sample_table_out)
+    int32_t cap, orbf_ransac_result* out, orbf_hyp_trace* hyp_trace, orbf_dmatch* good_sorted_out, int32_t* sample_table_out, const OdometryExtras* ex)
 {
-    CTX_ENTER(c);
     if (!cfg || !out || nsrc < 0 || ndst < 0 || nm < 0 || (nm > 0 && (!m12 || !src_xyz || !dst_xyz))) return ORBF_ERR_ARG;
     if (nm > c->K) return ORBF_ERR_CAPACITY;
     for (int i = 0; i < nm; ++i)
@@ -1160,7 +1165,8 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
     const int tabN0 = cfg->iterations * (int)cfg->sample_size;
     // every transfer of the call goes through the page-locked arena: uploads, kernels and read-backs are queued without a host
     // wait in between and the call synchronises once, before the results are handed to the caller
-    TRY(arena_begin(c, (size_t)R * 24 + (size_t)nm * 3 * sizeof(orbf_dmatch) + (size_t)cfg->iterations * sizeof(orbf_hyp_trace) + (size_t)tabN0 * 8 + 8192));
+    TRY(arena_begin(c, (size_t)R * 24 + (size_t)nm * 3 * sizeof(orbf_dmatch) + (size_t)cfg->iterations * sizeof(orbf_hyp_trace) + (size_t)tabN0 * 8 + 8192
+        + (ex ? (size_t)std::max(ex->cloudCap, 0) * 2 * sizeof(float4) + 1024 : 0)));
     {
         float* hs = reinterpret_cast<float*>(arena_take(c, (size_t)R * 12)); float* ht = reinterpret_cast<float*>(arena_take(c, (size_t)R * 12));
         for (int i = 0; i < nsrc; ++i) { hs[i] = src_xyz[3 * i]; hs[R + i] = src_xyz[3 * i + 1]; hs[2 * (size_t)R + i] = src_xyz[3 * i + 2]; }
@@ -1210,14 +1216,71 @@ extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cf
     if (hgood) ORBF_CUDA(c, cudaMemcpyAsync(hgood, c->d_good, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
     if (hhyp) ORBF_CUDA(c, cudaMemcpyAsync(hhyp, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
     if (htabOut) ORBF_CUDA(c, cudaMemcpyAsync(htabOut, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // Odometry::Compute's tail on the same stream, behind the RANSAC chain: mpSourceCloud / mpTargetCloud (ransac.cpp:163-189) and
+    // pose2 = T12 * pose1 (odometry.cpp:82-84)
+    int* hCloudN = nullptr; float4 *hCloudS = nullptr, *hCloudT = nullptr; float* hPose = nullptr;
+    size_t cloudM = 0;
+    if (ex) {
+        TRY(orbf_launch_ransac_clouds(c, 0, 1));
+        cloudM = (size_t)std::min(std::max(ex->cloudCap, 0), c->K);
+        hCloudN = reinterpret_cast<int*>(arena_take(c, sizeof(int)));
+        ORBF_CUDA(c, cudaMemcpyAsync(hCloudN, c->d_cloudCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (ex->cloudSrc && cloudM) {
+            hCloudS = reinterpret_cast<float4*>(arena_take(c, cloudM * sizeof(float4)));
+            ORBF_CUDA(c, cudaMemcpyAsync(hCloudS, c->d_cloudSrc, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (ex->cloudTgt && cloudM) {
+            hCloudT = reinterpret_cast<float4*>(arena_take(c, cloudM * sizeof(float4)));
+            ORBF_CUDA(c, cudaMemcpyAsync(hCloudT, c->d_cloudTgt, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (ex->pose2) {
+            static const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            Scratch sc(c);
+            const size_t oP0 = sc.take(64), oPoses = sc.take(128);
+            ORBF_CUDA(c, sc.alloc());
+            hPose = reinterpret_cast<float*>(arena_take(c, 128));
+            memcpy(hPose, ex->pose1 ? ex->pose1 : eye, 64);
+            ORBF_CUDA(c, cudaMemcpyAsync(sc.at<float>(oP0), hPose, 64, cudaMemcpyHostToDevice, c->stream));
+            TRY(orbf_launch_compose(c, 1, sc.at<float>(oP0), sc.at<float>(oPoses), nullptr));
+            ORBF_CUDA(c, cudaMemcpyAsync(hPose + 16, sc.at<float>(oPoses) + 16, 64, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
     ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     *out = *hres;
+    if (ex) {
+        if (ex->nCloud) *ex->nCloud = *hCloudN;
+        const size_t nc = std::min((size_t)std::max(*hCloudN, 0), cloudM);
+        if (hCloudS && nc) memcpy(ex->cloudSrc, hCloudS, nc * sizeof(float4));
+        if (hCloudT && nc) memcpy(ex->cloudTgt, hCloudT, nc * sizeof(float4));
+        if (hPose) memcpy(ex->pose2, hPose + 16, 64);
+    }
     if (inliers_out && out->n_inliers > cap) return ORBF_ERR_CAPACITY;
     if (hinl && out->n_inliers > 0) memcpy(inliers_out, hinl, (size_t)out->n_inliers * sizeof(orbf_dmatch));
     if (hgood && out->n_good > 0) memcpy(good_sorted_out, hgood, (size_t)out->n_good * sizeof(orbf_dmatch));
     if (hhyp) memcpy(hyp_trace, hhyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace));
     if (htabOut) memcpy(sample_table_out, htabOut, (size_t)tabN * sizeof(int));
+    if (ex && *hCloudN > ex->cloudCap && (ex->cloudSrc || ex->cloudTgt)) return ORBF_ERR_CAPACITY;
     return ORBF_OK;
+}
+
+extern "C" int orbf_ransac_iterate(orbf_context* c, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc,
+    const float* dst_xyz, int32_t ndst, const orbf_dmatch* m12, int32_t nm, const int32_t* sample_table, orbf_dmatch* inliers_out,
+    int32_t cap, orbf_ransac_result* out, orbf_hyp_trace* hyp_trace, orbf_dmatch* good_sorted_out, int32_t* sample_table_out)
+{
+    CTX_ENTER(c);
+    return ransac_iterate_core(c, cfg, src_xyz, nsrc, dst_xyz, ndst, m12, nm, sample_table, inliers_out, cap, out, hyp_trace, good_sorted_out, sample_table_out, nullptr);
+}
+
+// Odometry::Compute, RANSAC strategy (Odometry/odometry.cpp:44-90) for one frame pair in ONE call with one synchronisation:
+// Ransac::Iterate, the clouds it leaves for GICP, and pose2 = T12 * pose1 as cv::Mat evaluates it.
+extern "C" int orbf_odometry_compute(orbf_context* c, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc, const float* dst_xyz, int32_t ndst,
+    const orbf_dmatch* m12, int32_t nm, orbf_dmatch* inliers_out, int32_t cap, orbf_ransac_result* out, float* cloud_src_xyzw, float* cloud_tgt_xyzw,
+    int32_t cloud_cap, int32_t* n_cloud, const float* pose1, float* pose2)
+{
+    CTX_ENTER(c);
+    if (cloud_cap < 0) return ORBF_ERR_ARG;
+    OdometryExtras ex = { cloud_src_xyzw, cloud_tgt_xyzw, cloud_cap, n_cloud, pose1, pose2 };
+    return ransac_iterate_core(c, cfg, src_xyz, nsrc, dst_xyz, ndst, m12, nm, nullptr, inliers_out, cap, out, nullptr, nullptr, nullptr, &ex);
 }
 
 extern "C" int orbf_ransac_clouds(orbf_context* c, int32_t pair0, int32_t npairs, const float** d_src_xyzw, const float** d_tgt_xyzw,

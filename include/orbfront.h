@@ -27,6 +27,7 @@
  *   orbf_ransac_pairs                 Odometry::Compute -> Ransac::Iterate, batched   Odometry/odometry.cpp:48
  *   orbf_kabsch                       Kabsch::Compute                             Odometry/kabsch.cpp:14-57
  *   orbf_compose_trajectory           Odometry::Compute (RANSAC): composition rule + SetInlier   Odometry/odometry.cpp:78-90
+ *   orbf_odometry_compute             Odometry::Compute (RANSAC) for one frame pair: Iterate + clouds + composition   Odometry/odometry.cpp:44-90
  *   orbf_kfdb_*                       keyframe descriptor storage of Core/keyframedatabase (config 5 many-to-many matching)
  *   orbf_adaptive_detect              Extractor(FAST, ., ADAPTIVE): VideoGridAdaptedFeatureDetector over VideoDynamicAdaptedFeatureDetector
  *                                     over DetectorAdjuster(FAST)  Features/extractor.cpp:52-77, videogridadaptedfeaturedetector.cpp:52-84,
@@ -41,8 +42,9 @@ extern "C" {
 #endif
 
 #define ORBF_MAX_LEVELS 16
-#define ORBF_ABI_VERSION 5   /* 4: + projection_match, fuse_search, bow_match, compose_trajectory, undistort_points
-                                5: + distortion coefficients in orbf_config (mvKeysUn feeds the unprojection), orbf_download_keys_un */
+#define ORBF_ABI_VERSION 6   /* 4: + projection_match, fuse_search, bow_match, compose_trajectory, undistort_points
+                                5: + distortion coefficients in orbf_config (mvKeysUn feeds the unprojection), orbf_download_keys_un
+                                6: + orbf_odometry_compute (additive) */
 
 typedef enum {
     ORBF_OK = 0,
@@ -300,6 +302,13 @@ int orbf_kabsch(orbf_context* ctx, const float* setA, const float* setB, int32_t
  * outlier (may be NULL) = [npairs + 1][keypoint capacity] bytes, Frame::mvbOutlier after SetInlier(m.trainIdx) for the pair's inliers
  * (row 0, the first frame, stays all 1).                                                                              */
 int orbf_compose_trajectory(orbf_context* ctx, int32_t npairs, const float* pose0, float* poses /* [(npairs + 1) * 16] */, uint8_t* outlier);
+/* Odometry::Compute, RANSAC strategy (Odometry/odometry.cpp:44-90) for ONE frame pair, host in / host out, in one call with one
+ * synchronisation: Ransac::Iterate(F1, F2, m12) as orbf_ransac_iterate runs it (glibc rand() from cfg->seed), the clouds it leaves for GICP
+ * (cloud_*_xyzw: cloud_cap pcl::PointXYZ records each, may be NULL; *n_cloud = their length) and pose2 = T12 * pose1 with cv::Mat's float
+ * product (pose1 NULL = identity; pose2 may be NULL).  The inlier flags are the caller's SetInlier(m.trainIdx) over inliers_out.      */
+int orbf_odometry_compute(orbf_context* ctx, const orbf_ransac_config* cfg, const float* src_xyz, int32_t nsrc, const float* dst_xyz, int32_t ndst,
+    const orbf_dmatch* m12, int32_t nm, orbf_dmatch* inliers_out, int32_t cap, orbf_ransac_result* out, float* cloud_src_xyzw, float* cloud_tgt_xyzw,
+    int32_t cloud_cap, int32_t* n_cloud, const float* pose1, float* pose2);
 
 /* ---- multi-GPU frame sharding (one process per GPU, no data-path collective) --------- */
 /* Host arithmetic, no context: the contiguous chunk [start, stop) of `rank` among `world` ranks, the halo frame (the previous rank's

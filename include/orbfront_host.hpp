@@ -627,7 +627,9 @@ public:
     std::shared_ptr<PointCloud> mpSourceCloud, mpTargetCloud;
 
 private:
-    bool Solve(const std::vector<DMatch>& m12)
+    bool Solve(const std::vector<DMatch>& m12) { return Solve(m12, nullptr, nullptr); }
+    // pose1 / pose2 (Odometry::Compute): the composition rule T12 * pose1 rides on the same call and synchronisation
+    bool Solve(const std::vector<DMatch>& m12, const Matrix4f* pose1, Matrix4f* pose2)
     {
         rmse = 1e6f; mvInliers.clear(); mT12.setIdentity(); mbSolved = false;
         mpSourceCloud->points.clear(); mpTargetCloud->points.clear();
@@ -642,22 +644,23 @@ private:
         std::vector<DMatch> inl(m12.size() ? m12.size() : 1);
         static_assert(sizeof(Point3f) == 12, "Point3f must be three packed floats");
         const Frame *pF1 = mpSourceFrame, *pF2 = mpTargetFrame;
-        check(orbf_ransac_iterate(ctx, &cfg, reinterpret_cast<const float*>(pF1->mvKeys3Dc.data()), (int)pF1->mvKeys3Dc.size(),
+        int nc = 0;
+        mpSourceCloud->points.resize(m12.size()); mpTargetCloud->points.resize(m12.size());
+        // Iterate, the clouds it leaves for GICP (ransac.cpp:163-189) and, for Odometry::Compute, the composed pose: one call, one synchronisation
+        check(orbf_odometry_compute(ctx, &cfg, reinterpret_cast<const float*>(pF1->mvKeys3Dc.data()), (int)pF1->mvKeys3Dc.size(),
                   reinterpret_cast<const float*>(pF2->mvKeys3Dc.data()), (int)pF2->mvKeys3Dc.size(),
-                  reinterpret_cast<const orbf_dmatch*>(m12.data()), (int)m12.size(), nullptr, reinterpret_cast<orbf_dmatch*>(inl.data()),
-                  (int)inl.size(), &res, nullptr, nullptr, nullptr), "orbf_ransac_iterate");
+                  reinterpret_cast<const orbf_dmatch*>(m12.data()), (int)m12.size(), reinterpret_cast<orbf_dmatch*>(inl.data()), (int)inl.size(), &res,
+                  reinterpret_cast<float*>(mpSourceCloud->points.data()), reinterpret_cast<float*>(mpTargetCloud->points.data()), (int)m12.size(), &nc,
+                  pose1 ? pose1->m : nullptr, pose2 ? pose2->m : nullptr), "orbf_odometry_compute");
         if (LatchedDepthCovariance() < 0.0 && res.depth_cov_used >= 0.0) LatchedDepthCovariance() = res.depth_cov_used;
         rmse = res.rmse;
         std::memcpy(mT12.m, res.T12, sizeof(res.T12));
         mvInliers.assign(inl.begin(), inl.begin() + res.n_inliers);
-        int nc = 0;
-        mpSourceCloud->points.resize(m12.size()); mpTargetCloud->points.resize(m12.size());
-        check(orbf_download_ransac_clouds(ctx, 0, reinterpret_cast<float*>(mpSourceCloud->points.data()), reinterpret_cast<float*>(mpTargetCloud->points.data()),
-                  (int)m12.size(), &nc), "orbf_download_ransac_clouds");
         mpSourceCloud->points.resize((size_t)nc); mpTargetCloud->points.resize((size_t)nc);
         mbSolved = true;
         return res.ok != 0;
     }
+    friend class Odometry;
     int mIterations = 200; unsigned mMinInlierTh = 20; float mMaxMahalanobisDistance = 3.0f; unsigned mSampleSize = 4; bool mCheckDepth = true;
     Frame* mpSourceFrame = nullptr; Frame* mpTargetFrame = nullptr;
     std::vector<DMatch> mvMatchesS2T;
@@ -707,15 +710,11 @@ public:
     void Compute(Frame* pF1, Frame* pF2, const std::vector<DMatch>& vMatches12)
     {
         if (mOdometryAlgorithm != RANSAC) throw std::invalid_argument("orbf::Odometry: only the RANSAC strategy is on the GPU path");
-        mbConverged = mpRansac->Iterate(pF1, pF2, vMatches12);
+        const Matrix4f pose1 = pF1->GetPose();
+        Matrix4f T = pose1;                                 // Iterate returns before anything runs on too few matches: T12 = I, and I * pose is the pose, exactly
+        mpRansac->mpSourceFrame = pF1; mpRansac->mpTargetFrame = pF2;
+        mbConverged = mpRansac->Solve(vMatches12, &pose1, &T);            // Iterate + the composition rule on the device, one call
         mT12 = mpRansac->mT12; mvInliers = mpRansac->mvInliers;
-        Matrix4f T = pF1->GetPose();                       // Iterate returned before anything ran: T12 = I, and I * pose is the pose, exactly
-        if (mpRansac->SolvedOnDevice()) {                   // the solved pair sits in pair slot 0: compose there
-            std::lock_guard<std::mutex> g(Runtime::Lock());
-            Matrix4f poses[2];
-            check(orbf_compose_trajectory(Runtime::Current(), 1, T.m, poses[0].m, nullptr), "orbf_compose_trajectory");
-            T = poses[1];
-        }
         pF2->SetPose(T);
         for (const auto& m : mvInliers) pF2->SetInlier((size_t)m.trainIdx);
     }

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(ob):
     L = ob.lib()
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.orbf_abi_version() == 5
+    assert L.orbf_abi_version() == 6
 
 
 def test_struct_layouts_match_header(ob):

@@ -82,6 +82,38 @@ def test_ransac_clouds_batched_and_standalone(ob, orc, texture):
 
 
 @pytest.mark.gpu
+def test_odometry_compute_is_iterate_plus_clouds_plus_composition(ob, orc):
+    """orbf_odometry_compute (one call, one synchronisation) against the oracle's Ransac::Iterate, the clouds rule and the composition
+    rule of Odometry::Compute (odometry.cpp:82-84) — and against the three separate calls it replaces."""
+    ctx = ob.Context(max_frames=2)
+    try:
+        rng = np.random.default_rng(2)
+        ang = 0.3
+        pose1 = np.eye(4, dtype=np.float32)
+        pose1[:3, :3] = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], np.float32)
+        pose1[:3, 3] = rng.normal(0, 1, 3).astype(np.float32)
+        for seed, outl in ((42, 0.3), (7, 0.6), (9, 1.0)):
+            src, dst, m, _, _ = synth.rigid_pairs(seed=seed, outlier_frac=outl)
+            src = src.copy(); src[m["queryIdx"][::9], 2] = np.nan            # some matches fail the depth check: clouds shorter than m
+            g = ctx.odometry_compute(src, dst, m, pose1=pose1, seed=seed)
+            r = orc.ransac_iterate(src, dst, m, seed=seed)
+            assert g["ok"] == r["ok"] and g["inliers"].tobytes() == r["inliers"].tobytes()
+            assert np.array_equal(g["T12"], r["T12"]) and g["rmse"] == r["rmse"] and g["depth_cov"] == r["depth_cov"]
+            ws, wt = orc.ransac_clouds(src, dst, m)
+            assert np.array_equal(g["cloud_src"], ws) and np.array_equal(g["cloud_tgt"], wt) and len(ws) < len(m)
+            assert np.array_equal(g["pose2"], orc.compose_trajectory(r["T12"][None], pose1)[1])
+            s = ctx.ransac_iterate(src, dst, m, seed=seed)                     # the separate calls
+            cs, ct = ctx.download_ransac_clouds(0)
+            assert s["inliers"].tobytes() == g["inliers"].tobytes() and np.array_equal(cs, g["cloud_src"]) and np.array_equal(ct, g["cloud_tgt"])
+        g = ctx.odometry_compute(src, dst, m[:10], pose1=pose1)                # fewer than min_inlier_th matches: T12 = I, pose2 = pose1
+        assert not g["ok"] and len(g["cloud_src"]) == 0 and np.array_equal(g["pose2"], pose1) and np.array_equal(g["T12"], np.eye(4, dtype=np.float32))
+        g = ctx.odometry_compute(src, dst, m, seed=3)                          # pose1 = NULL: identity
+        assert np.array_equal(g["pose2"], orc.compose_trajectory(g["T12"][None])[1])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dist", [None, FR1_DIST])
 def test_unproject_keypoints_matches_oracle(ob, orc, texture, dist):
     frame = synth.make_frame(texture, 11); depth = synth.make_depth(11)
