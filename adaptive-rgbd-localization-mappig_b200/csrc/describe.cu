@@ -92,7 +92,9 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)          /
     return d;
 }
 
-__global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_constant__ DescParams P)
+// KPW keypoints per warp: 16 for batches (the fetch of keypoint k+1 hides behind keypoint k sixteen times per set-up), 4 for a
+// call on one or two frames, where the length of a warp's chain is the kernel's duration
+template <int KPW> __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_constant__ DescParams P)
 {
     __shared__ float4 sPat[256];
     __shared__ uint32_t sCoef[16];
@@ -108,10 +110,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     __syncthreads();
     const int slot = P.slot0 + blockIdx.y;
     const int* lc = P.lkpCount + slot * ORBF_MAX_LEVELS;
-    const int base = (blockIdx.x * DS_WARPS + warp) * DS_KPW;
-    // lanes 0..DS_KPW-1 locate the warp's keypoints once; each iteration takes its keypoint by shuffle
+    const int base = (blockIdx.x * DS_WARPS + warp) * KPW;
+    // lanes 0..KPW-1 locate the warp's keypoints once; each iteration takes its keypoint by shuffle
     int total;
-    const KpLoc mine = locate(P, lc, slot, base + (lane & (DS_KPW - 1)), total);
+    const KpLoc mine = locate(P, lc, slot, base + (lane & (KPW - 1)), total);
     if (base == 0 && lane == 0) P.count[slot] = total;
     auto take = [&](int it) {
         KpLoc k;
@@ -145,13 +147,13 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
     if (cur.level >= 0 && lane == 0) fetch(cur, 0);
     const float kMagic = 12582912.f;
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    // depth sample of the keypoint (Core/frame.cpp:155): lanes 0..DS_KPW-1 request the samples of the warp's keypoints up front and
+    // depth sample of the keypoint (Core/frame.cpp:155): lanes 0..KPW-1 request the samples of the warp's keypoints up front and
     // unproject them after the loop, so the read — an HBM access, or a ~2 us PCIe round trip when the plane lives in pinned host
     // memory — has the whole warp's work to hide behind
     float myX = (float)mine.x, myY = (float)mine.y;
     if (mine.level > 0) { myX = __fmul_rn(myX, P.scale[mine.level]); myY = __fmul_rn(myY, P.scale[mine.level]); }
     unsigned short myRaw = 0; bool myHave = false;
-    if (lane < DS_KPW && mine.level >= 0 && P.depth) {
+    if (lane < KPW && mine.level >= 0 && P.depth) {
         const int ui = (int)myX, vi = (int)myY;         // float -> int truncation of the (distorted) keypoint
         if (ui >= 0 && vi >= 0 && ui < P.width && vi < P.height) {
             myRaw = __ldg(P.depth + (long long)slot * P.depthFrameStride + (long long)vi * P.depthPitch + ui);
@@ -159,10 +161,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         }
     }
 #pragma unroll 1
-    for (int it = 0; it < DS_KPW && cur.level >= 0; ++it) {
+    for (int it = 0; it < KPW && cur.level >= 0; ++it) {
         const int i = base + it, buf = it & 1;
         KpLoc nxt; nxt.level = -1;
-        if (it + 1 < DS_KPW) nxt = take(it + 1);
+        if (it + 1 < KPW) nxt = take(it + 1);
         if (nxt.level >= 0 && lane == 0) fetch(nxt, buf ^ 1);
         __syncwarp();
         const int level = cur.level, x = cur.x, y = cur.y;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) describe_kernel(const __grid_co
         __syncwarp();                                   // every lane is done with this buffer before it is refilled
         cur = nxt;
     }
-    if (lane < DS_KPW && mine.level >= 0) {
+    if (lane < KPW && mine.level >= 0) {
         // mvKeysUn (frame.cpp:286-313): the depth was looked up at the distorted keypoint above, mvuRight and mvKeys3Dc use the undistorted one
         float uX = myX, uY = myY;
         if (P.distorted) undistort_point(P.und, myX, myY, &uX, &uY);
@@ -290,8 +292,12 @@ int orbf_launch_describe(orbf_context* c, int slot0, int n)
     P.width = c->cfg.width; P.height = c->cfg.height;
     P.cx = c->cfg.cx; P.cy = c->cfg.cy; P.invfx = 1.0f / c->cfg.fx; P.invfy = 1.0f / c->cfg.fy;
     P.mbf = c->cfg.mbf; P.depthFactor = c->cfg.depth_factor;
-    dim3 grid((c->K + DS_WARPS * DS_KPW - 1) / (DS_WARPS * DS_KPW), n);
-    describe_kernel<<<grid, DS_WARPS * 32, 0, c->stream>>>(P);
+    if (n <= 2) {
+        constexpr int KPW = 4;
+        describe_kernel<KPW><<<dim3((c->K + DS_WARPS * KPW - 1) / (DS_WARPS * KPW), n), DS_WARPS * 32, 0, c->stream>>>(P);
+    } else {
+        describe_kernel<DS_KPW><<<dim3((c->K + DS_WARPS * DS_KPW - 1) / (DS_WARPS * DS_KPW), n), DS_WARPS * 32, 0, c->stream>>>(P);
+    }
     ORBF_LAUNCH_CHECK(c);
     return ORBF_OK;
 }
