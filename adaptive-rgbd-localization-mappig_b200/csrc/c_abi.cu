@@ -1204,48 +1204,63 @@ static int ransac_iterate_core(orbf_context* c, const orbf_ransac_config* cfg, c
     rs.sx = c->d_sxyz; rs.sy = c->d_sxyz + R; rs.sz = c->d_sxyz + 2 * (size_t)R;
     rs.tx = c->d_txyz; rs.ty = c->d_txyz + R; rs.tz = c->d_txyz + 2 * (size_t)R;
     rs.slotStride = 0; rs.pairs = nullptr; rs.matches = c->d_matches; rs.matchCount = c->d_matchCount; rs.nsrc = nsrc; rs.ndst = ndst;
-    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, /*standalone=*/true, /*fullTable=*/sample_table_out != nullptr));
+    // The loop of a well-matched pair ends within its first hypotheses (> 80 % inliers), and every later wave is then a chain of empty
+    // launches: the first two waves (8 hypotheses) are queued with the read-back behind them; only a pair whose done flag is still clear
+    // after the synchronisation gets the remaining waves and a second read-back.
+    const bool twoPhase = !hyp_trace && !sample_table_out && cfg->iterations > 8;
+    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, /*standalone=*/true, /*fullTable=*/sample_table_out != nullptr, false, 0, twoPhase ? 2 : 5));
     // results: everything the caller asked for into the arena (inliers / sorted matches at their upper bound nm), one synchronisation
     orbf_ransac_result* hres = reinterpret_cast<orbf_ransac_result*>(arena_take(c, sizeof(orbf_ransac_result)));
+    int* hdone = reinterpret_cast<int*>(arena_take(c, sizeof(int)));
     orbf_dmatch* hinl = inliers_out && nm ? reinterpret_cast<orbf_dmatch*>(arena_take(c, (size_t)nm * sizeof(orbf_dmatch))) : nullptr;
     orbf_dmatch* hgood = good_sorted_out && nm ? reinterpret_cast<orbf_dmatch*>(arena_take(c, (size_t)nm * sizeof(orbf_dmatch))) : nullptr;
     orbf_hyp_trace* hhyp = hyp_trace ? reinterpret_cast<orbf_hyp_trace*>(arena_take(c, (size_t)cfg->iterations * sizeof(orbf_hyp_trace))) : nullptr;
     int* htabOut = sample_table_out ? reinterpret_cast<int*>(arena_take(c, (size_t)tabN * sizeof(int))) : nullptr;
-    ORBF_CUDA(c, cudaMemcpyAsync(hres, c->d_rres, sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
-    if (hinl) ORBF_CUDA(c, cudaMemcpyAsync(hinl, c->d_inliers, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
-    if (hgood) ORBF_CUDA(c, cudaMemcpyAsync(hgood, c->d_good, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
-    if (hhyp) ORBF_CUDA(c, cudaMemcpyAsync(hhyp, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
-    if (htabOut) ORBF_CUDA(c, cudaMemcpyAsync(htabOut, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    // Odometry::Compute's tail on the same stream, behind the RANSAC chain: mpSourceCloud / mpTargetCloud (ransac.cpp:163-189) and
-    // pose2 = T12 * pose1 (odometry.cpp:82-84)
     int* hCloudN = nullptr; float4 *hCloudS = nullptr, *hCloudT = nullptr; float* hPose = nullptr;
     size_t cloudM = 0;
+    size_t oP0 = 0, oPoses = 0;
+    Scratch sc(c);
     if (ex) {
-        TRY(orbf_launch_ransac_clouds(c, 0, 1));
         cloudM = (size_t)std::min(std::max(ex->cloudCap, 0), c->K);
         hCloudN = reinterpret_cast<int*>(arena_take(c, sizeof(int)));
-        ORBF_CUDA(c, cudaMemcpyAsync(hCloudN, c->d_cloudCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (ex->cloudSrc && cloudM) {
-            hCloudS = reinterpret_cast<float4*>(arena_take(c, cloudM * sizeof(float4)));
-            ORBF_CUDA(c, cudaMemcpyAsync(hCloudS, c->d_cloudSrc, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-        }
-        if (ex->cloudTgt && cloudM) {
-            hCloudT = reinterpret_cast<float4*>(arena_take(c, cloudM * sizeof(float4)));
-            ORBF_CUDA(c, cudaMemcpyAsync(hCloudT, c->d_cloudTgt, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-        }
+        if (ex->cloudSrc && cloudM) hCloudS = reinterpret_cast<float4*>(arena_take(c, cloudM * sizeof(float4)));
+        if (ex->cloudTgt && cloudM) hCloudT = reinterpret_cast<float4*>(arena_take(c, cloudM * sizeof(float4)));
         if (ex->pose2) {
             static const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-            Scratch sc(c);
-            const size_t oP0 = sc.take(64), oPoses = sc.take(128);
+            oP0 = sc.take(64); oPoses = sc.take(128);
             ORBF_CUDA(c, sc.alloc());
             hPose = reinterpret_cast<float*>(arena_take(c, 128));
             memcpy(hPose, ex->pose1 ? ex->pose1 : eye, 64);
             ORBF_CUDA(c, cudaMemcpyAsync(sc.at<float>(oP0), hPose, 64, cudaMemcpyHostToDevice, c->stream));
-            TRY(orbf_launch_compose(c, 1, sc.at<float>(oP0), sc.at<float>(oPoses), nullptr));
-            ORBF_CUDA(c, cudaMemcpyAsync(hPose + 16, sc.at<float>(oPoses) + 16, 64, cudaMemcpyDeviceToHost, c->stream));
         }
     }
-    ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1) {
+            if (!twoPhase || *hdone) break;
+            TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, true, false, false, 2, 5));
+        }
+        ORBF_CUDA(c, cudaMemcpyAsync(hres, c->d_rres, sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
+        ORBF_CUDA(c, cudaMemcpyAsync(hdone, orbf_ransac_done_flag(c, 0), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (hinl) ORBF_CUDA(c, cudaMemcpyAsync(hinl, c->d_inliers, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+        if (hgood) ORBF_CUDA(c, cudaMemcpyAsync(hgood, c->d_good, (size_t)nm * sizeof(orbf_dmatch), cudaMemcpyDeviceToHost, c->stream));
+        if (hhyp) ORBF_CUDA(c, cudaMemcpyAsync(hhyp, c->d_hyp, (size_t)cfg->iterations * sizeof(orbf_hyp_trace), cudaMemcpyDeviceToHost, c->stream));
+        if (htabOut) ORBF_CUDA(c, cudaMemcpyAsync(htabOut, c->d_samples, (size_t)tabN * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        // Odometry::Compute's tail on the same stream, behind the RANSAC chain: mpSourceCloud / mpTargetCloud (ransac.cpp:163-189; they do
+        // not depend on the loop) and pose2 = T12 * pose1 (odometry.cpp:82-84)
+        if (ex) {
+            if (phase == 0) {
+                TRY(orbf_launch_ransac_clouds(c, 0, 1));
+                ORBF_CUDA(c, cudaMemcpyAsync(hCloudN, c->d_cloudCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                if (hCloudS) ORBF_CUDA(c, cudaMemcpyAsync(hCloudS, c->d_cloudSrc, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+                if (hCloudT) ORBF_CUDA(c, cudaMemcpyAsync(hCloudT, c->d_cloudTgt, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+            }
+            if (hPose) {
+                TRY(orbf_launch_compose(c, 1, sc.at<float>(oP0), sc.at<float>(oPoses), nullptr));
+                ORBF_CUDA(c, cudaMemcpyAsync(hPose + 16, sc.at<float>(oPoses) + 16, 64, cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     *out = *hres;
     if (ex) {
         if (ex->nCloud) *ex->nCloud = *hCloudN;

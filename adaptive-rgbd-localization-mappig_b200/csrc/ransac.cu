@@ -1012,8 +1012,11 @@ int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
     return ORBF_OK;
 }
 
+// firstWave / lastWave: the hypothesis waves [firstWave, lastWave) of this launch (5 waves in all).  firstWave == 0 prepares the pairs;
+// a later launch with firstWave > 0 on the same set continues where the earlier one stopped (the one-pair call checks the pair's
+// done flag after two waves and only then queues the rest).  Every launch ends with the select kernel.
 int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, bool standalone, bool fullTable, bool probeOnly)
+    const int* d_userSamples, bool standalone, bool fullTable, bool probeOnly, int firstWave, int lastWave)
 {
     if (npairs <= 0) return ORBF_OK;
     {
@@ -1039,12 +1042,14 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     }
     const size_t smem = (size_t)c->K * (sizeof(orbf_dmatch) + 2 * sizeof(unsigned long long) + 2 * sizeof(uint16_t)) + (RAND_BUF + RAND_BUF / 2) * sizeof(uint16_t);
     orbf_prof_begin(c, ST_RANSAC_PREPARE);
+    if (firstWave == 0) {
     ransac_prepare_kernel<<<npairs, PR_THREADS, smem, c->stream>>>(P);
     ORBF_LAUNCH_CHECK(c);
     // every group runs the latch (a no-op once a value >= 0 is there): groups of one sequence are enqueued in pair order on one stream,
     // so a group whose pairs never reach scoring leaves the latch to the next one
     ransac_latch_kernel<<<1, 32, 0, c->stream>>>(P, npairs);
     ORBF_LAUNCH_CHECK(c);
+    }
     orbf_prof_end(c, ST_RANSAC_PREPARE);
     if (probeOnly) return ORBF_OK;
     orbf_prof_begin(c, ST_RANSAC_HYP);
@@ -1063,8 +1068,8 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     // (a first wave of 2 covers the common case — on well-matched consecutive frames the loop ends after its first accepted
     // hypothesis — and keeps that wave inside one residency of the GPU; every later wave is a few microseconds when nothing is left)
     const int waveEnd[5] = { 2, 8, 32, 96, iters };
-    int lo = 0;
-    for (int w = 0; w < 5 && lo < iters; ++w) {
+    int lo = firstWave > 0 ? std::min(waveEnd[std::min(firstWave, 5) - 1], iters) : 0;
+    for (int w = firstWave; w < std::min(lastWave, 5) && lo < iters; ++w) {
         const int hi = std::min(waveEnd[w], iters);
         if (hi <= lo) continue;
         if (hi > P.tabRows && lo <= P.tabRows && P.tabRows < iters) {          // this wave reads rows prepare did not draw
@@ -1091,6 +1096,8 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     orbf_prof_end(c, ST_RANSAC_SELECT);
     return ORBF_OK;
 }
+
+const int* orbf_ransac_done_flag(orbf_context* c, int pair) { return &reinterpret_cast<const RState*>(c->d_rstate)[pair].done; }
 
 // ---- Odometry::Compute, RANSAC strategy (Odometry/odometry.cpp:78-90) along a device-resident sequence --------------------------
 // Composition rule pose[k + 1] = T12[k] * pose[k]: cv::Mat's 4x4 float product (every element = four products summed left to right
