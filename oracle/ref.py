@@ -1,6 +1,7 @@
 """ctypes binding of oracle/_ref/*.so — TEST INFRASTRUCTURE ONLY.
 
-liborb_ref.so is the reference's own Features/orbextractor.cpp, libodometry_ref.so its Odometry/ransac.cpp + Odometry/kabsch.cpp,
+liborb_ref.so is the reference's own Features/orbextractor.cpp (+ matcher.cpp, extractor.cpp and the adaptive detector sources),
+libodometry_ref.so its Odometry/ransac.cpp + Odometry/kabsch.cpp, libframe_ref.so its Core/frame.cpp + keyframe.cpp + landmark.cpp + map.cpp,
 compiled verbatim from /root/reference (oracle/Makefile, target _ref) against the OpenCV / Eigen / PCL stand-ins under oracle/ref_shim/.  Only tests/, bench.py's CPU legs and __graft_entry__.build() touch it.
 It exists where the reference checkout exists (the authoring container); the prebuilt file travels to the GPU box with the
 snapshot (oracle/_ref/ is git-ignored, not gpurun-ignored).  available() says whether it can be used.
@@ -17,6 +18,7 @@ from .oracle import CAND_DT, DMATCH_DT, KEYPOINT_DT, RansacCfg, RansacOut, level
 _DIR = Path(__file__).resolve().parent
 SO = _DIR / "_ref" / "liborb_ref.so"
 SO_ODOMETRY = _DIR / "_ref" / "libodometry_ref.so"
+SO_FRAME = _DIR / "_ref" / "libframe_ref.so"
 REFERENCE = Path(os.environ.get("ORB_REFERENCE_DIR", "/root/reference"))
 _lib = None
 
@@ -25,11 +27,11 @@ def build():
     """Compile from the reference checkout when it is present; otherwise keep whatever prebuilt file is there."""
     if (REFERENCE / "Features" / "orbextractor.cpp").exists():
         subprocess.run(["make", "-C", str(_DIR), "-s", "_ref", f"REF={REFERENCE}"], check=True)
-    return SO.exists() and SO_ODOMETRY.exists()
+    return SO.exists() and SO_ODOMETRY.exists() and SO_FRAME.exists()
 
 
 def available():
-    return (SO.exists() and SO_ODOMETRY.exists()) or build()
+    return (SO.exists() and SO_ODOMETRY.exists() and SO_FRAME.exists()) or build()
 
 
 def lib():
@@ -254,3 +256,42 @@ def fuse(Rcw, tcw, bounds, kp_x, kp_y, u_right, desc, lm_pos, lm_desc, lm_state,
     if rc:
         raise RuntimeError(f"ref_fuse rc={rc}")
     return best[:L], nf.value
+
+
+# ---- Core/frame.cpp + keyframe.cpp + landmark.cpp + map.cpp with the reference's real Core classes (libframe_ref.so) --------------------
+_frame = None
+
+
+def frame_lib():
+    global _frame
+    if _frame is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libframe_ref.so is not built and the reference checkout is absent")
+        _frame = C.CDLL(str(SO_FRAME))
+    return _frame
+
+
+def frame_extract(bgr, depth_u16, cap=4096):
+    """Frame(imColor, imDepth, t) + Frame::ExtractFeatures(Extractor(ORB_SLAM2, ORB_SLAM2, NORMAL)) (Core/frame.cpp:18-45, 135-170) with the
+    calibration compiled into the reference (Utils/common.h: FR1 and its distortion)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8); depth = np.ascontiguousarray(depth_u16, np.uint16)
+    h, w = depth.shape
+    assert bgr.shape == (h, w, 3)
+    kps = np.zeros(cap, KEYPOINT_DT); desc = np.zeros((cap, 32), np.uint8); un = np.zeros((cap, 2), np.float32)
+    xyz = np.zeros((cap, 3), np.float32); ur = np.zeros(cap, np.float32); n = C.c_int(0)
+    gray = np.zeros((h, w), np.uint8); bounds = np.zeros(4, np.float32)
+    rc = frame_lib().ref_frame_extract(_p(bgr), _p(depth), w, h, _p(kps), _p(desc), _p(un), _p(xyz), _p(ur), cap, C.byref(n), _p(gray), _p(bounds))
+    if rc:
+        raise RuntimeError(f"ref_frame_extract rc={rc}")
+    k = n.value
+    return dict(kps=kps[:k].copy(), desc=desc[:k].copy(), xy_un=un[:k].copy(), xyz=xyz[:k].copy(), uright=ur[:k].copy(), gray=gray, bounds=bounds)
+
+
+def distinctive_descriptors(desc, offsets, bad=None):
+    """Landmark::ComputeDistinctiveDescriptors (Core/landmark.cpp:219-273) per landmark: (descriptor [n, 32], set flag [n])."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); offsets = np.ascontiguousarray(offsets, np.int32)
+    n = len(offsets) - 1
+    b = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    out = np.zeros((max(n, 1), 32), np.uint8); has = np.zeros(max(n, 1), np.uint8)
+    frame_lib().ref_distinctive_descriptors(_p(desc) if len(desc) else None, _p(b) if b is not None else None, _p(offsets), n, _p(out), _p(has))
+    return out[:n], has[:n].astype(bool)

@@ -13,7 +13,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <list>
+#include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -22,7 +25,11 @@
 typedef unsigned char uchar;
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_16U 2
 #define CV_32F 5
+#define CV_32FC1 5
+#define CV_32FC2 13
+#define CV_8UC3 16
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_WRAP
 #define CV_OUT
@@ -90,7 +97,9 @@ public:
     Mat(Size sz, int type) : Mat() { create(sz.height, sz.width, type); }
     Mat(int r, int c, int type, void* ext, size_t stp = 0) : rows(r), cols(c), step(stp ? stp : (size_t)c * esz(type)), data((uchar*)ext), type_(type), esz_(esz(type)) {}
     Mat(const MatZeros& z) : Mat() { *this = z; }
-    static int esz(int type) { return type == CV_32F ? 4 : 1; }
+    Mat(const struct MatMul& m);                                       // A * B
+    static int esz(int type) { return type == CV_32F ? 4 : type == CV_32FC2 ? 8 : type == CV_16U ? 2 : type == CV_8UC3 ? 3 : 1; }
+    int channels() const { return type_ == CV_32FC2 ? 2 : type_ == CV_8UC3 ? 3 : 1; }
     void create(int r, int c, int type)
     {
         if (data && r == rows && c == cols && type == type_) return;       // cv::Mat::create: no reallocation for the same shape
@@ -113,11 +122,50 @@ public:
         for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz_);
         return m;
     }
-    void copyTo(Mat& dst) const
+    void copyTo(const class _OutputArray& dst) const;                  // defined below _OutputArray (a temporary view is a valid destination)
+    Mat col(int c) const { return colRange(c, c + 1); }
+    Mat t() const
     {
-        dst.create(rows, cols, type_);
-        for (int r = 0; r < rows; ++r) std::memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz_);
+        assert(type_ == CV_32F);
+        Mat m(cols, rows, CV_32F);
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) m.at<float>(c, r) = at<float>(r, c);
+        return m;
     }
+    static Mat eye(int r, int c, int type)
+    {
+        assert(type == CV_32F);
+        Mat m(r, c, type);
+        for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m.at<float>(i, j) = i == j ? 1.f : 0.f;
+        return m;
+    }
+    void resize(size_t nrows)                                          // cv::Mat::resize: the first rows are kept
+    {
+        Mat m((int)nrows, cols, type_);
+        std::memset(m.data, 0, (size_t)m.rows * m.step);
+        for (int r = 0; r < std::min(rows, m.rows); ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz_);
+        *this = m;
+    }
+    Mat reshape(int cn) const                                          // N x 2 CV_32F <-> N x 1 CV_32FC2 on the same data (continuous only)
+    {
+        assert(step == (size_t)cols * esz_);
+        Mat m(*this);
+        if (cn == 2) { assert(type_ == CV_32F && cols == 2); m.type_ = CV_32FC2; m.esz_ = 8; m.cols = 1; }
+        else { assert(cn == 1 && type_ == CV_32FC2); m.type_ = CV_32F; m.esz_ = 4; m.cols = cols * 2; }
+        m.step = (size_t)m.cols * m.esz_;
+        return m;
+    }
+    // cv::Mat::convertTo(dst, CV_32F, alpha) from 16-bit unsigned: float(src) * float(alpha), one rounding (what the oracle's
+    // unprojection restates; pinned against cv2 in tests/test_ingest.py)
+    void convertTo(Mat& dst, int rtype, double alpha = 1.0) const
+    {
+        assert(type_ == CV_16U && rtype == CV_32F);
+        dst.create(rows, cols, CV_32F);
+        const float a = (float)alpha;
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) dst.at<float>(r, c) = (float)*reinterpret_cast<const uint16_t*>(data + (size_t)r * step + (size_t)c * 2) * a;
+    }
+    template <typename T> T* ptr(int r) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
     template <typename T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <typename T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }                 // vectors
@@ -152,9 +200,16 @@ class _OutputArray : public _InputArray {
 public:
     _OutputArray() {}
     _OutputArray(Mat& m) : _InputArray(m) {}
+    _OutputArray(const Mat& m) : _InputArray(m) {}                     // OpenCV allows a temporary header (a view) as destination
     void create(int r, int c, int type) const { if (m_) m_->create(r, c, type); }
     void release() const { if (m_) m_->release(); }
 };
+inline void Mat::copyTo(const _OutputArray& dst_) const
+{
+    dst_.create(rows, cols, type_);                                    // no reallocation for an unchanged shape: a view keeps pointing into its parent
+    Mat dst = dst_.getMat();
+    for (int r = 0; r < rows; ++r) std::memmove(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz_);
+}
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 inline const _OutputArray& noArray() { static _OutputArray none; return none; }
@@ -162,8 +217,40 @@ inline const _OutputArray& noArray() { static _OutputArray none; return none; }
 // `A * B + C` on float matrices = cv::gemm(A, B, 1, C, 1) through cv::MatExpr: every element is the products summed left to right in
 // float, then (float)((double)sum * alpha + (double)c * beta) (OpenCV's small-matrix GEMM; the same statement as the oracle's, which
 // tests/test_fuse_bow.py and tests/test_trajectory.py pin against cv2.gemm)
-struct MatMul { Mat a, b; };
+struct MatMul {
+    Mat a, b;
+    operator Mat() const                                               // A * B alone: gemm with beta = 0
+    {
+        Mat d(a.rows, b.cols, CV_32F);
+        for (int i = 0; i < d.rows; ++i)
+            for (int j = 0; j < d.cols; ++j) {
+                float t = a.at<float>(i, 0) * b.at<float>(0, j);
+                for (int k = 1; k < a.cols; ++k) t = t + a.at<float>(i, k) * b.at<float>(k, j);
+                d.at<float>(i, j) = (float)((double)t * 1.0);
+            }
+        return d;
+    }
+};
+inline Mat::Mat(const MatMul& m) : Mat() { *this = (Mat)m; }
 inline MatMul operator*(const Mat& a, const Mat& b) { assert(a.type() == CV_32F && b.type() == CV_32F && a.cols == b.rows); MatMul m = { a, b }; return m; }
+inline Mat operator-(const Mat& a)
+{
+    assert(a.type() == CV_32F);
+    Mat d(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) d.at<float>(i, j) = -a.at<float>(i, j);
+    return d;
+}
+// cv::Mat_<float>(r, c) << v0, v1, ...
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_(int r, int c) : Mat(r, c, CV_32F) { static_assert(sizeof(T) == 4, "float only"); }
+    struct Init {
+        Mat m; int k;
+        Init& operator,(T v) { m.at<T>(k / m.cols, k % m.cols) = v; ++k; return *this; }
+        operator Mat() const { return m; }
+    };
+    Init operator<<(T v) { Init i = { *this, 0 }; i, v; return i; }
+};
 inline Mat operator+(const MatMul& m, const Mat& c)
 {
     assert(c.type() == CV_32F && c.rows == m.a.rows && c.cols == m.b.cols);
@@ -349,11 +436,41 @@ public:
 
 // drawing / display entry points of Matcher::Draw* (never on the hot path): no-ops so that the source compiles
 struct DrawMatchesFlags { enum { DEFAULT = 0, DRAW_OVER_OUTIMG = 1, NOT_DRAW_SINGLE_POINTS = 2, DRAW_RICH_KEYPOINTS = 4 }; };
-enum { COLOR_GRAY2BGR = 8 };
+enum { COLOR_BGR2GRAY = 6, COLOR_GRAY2BGR = 8 };
 template <typename... A> inline void drawMatches(A&&...) {}
 template <typename... A> inline void drawKeypoints(A&&...) {}
 template <typename... A> inline void imshow(A&&...) {}
-template <typename... A> inline void cvtColor(A&&...) {}
+// cv::cvtColor(src, dst, COLOR_BGR2GRAY) on 8-bit images: OpenCV's 15-bit fixed point (pinned against cv2 in tests/test_ingest.py);
+// COLOR_GRAY2BGR (Matcher::DrawInlierPoints only) is a no-op here
+inline void cvtColor(InputArray src_, OutputArray dst_, int code)
+{
+    if (code != COLOR_BGR2GRAY) return;
+    const Mat src = src_.getMat();
+    assert(src.type() == CV_8UC3);
+    Mat out(src.rows, src.cols, CV_8UC1);
+    for (int r = 0; r < src.rows; ++r) {
+        const uchar* s = src.ptr(r); uchar* d = out.ptr(r);
+        for (int c = 0; c < src.cols; ++c) d[c] = (uchar)((s[3 * c] * 3735u + s[3 * c + 1] * 19235u + s[3 * c + 2] * 9798u + 16384u) >> 15);
+    }
+    dst_.create(out.rows, out.cols, CV_8UC1);
+    out.copyTo(dst_);
+}
+// cv::undistortPoints(src, dst, K, dist, Mat(), K) on N x 1 CV_32FC2 points: the routine tests/test_undistort.py pins against cv2
+inline void undistortPoints(InputArray src_, OutputArray dst_, InputArray K_, InputArray dist_, InputArray = noArray(), InputArray P_ = noArray())
+{
+    const Mat src = src_.getMat(), K = K_.getMat(), dist = dist_.getMat(), P = P_.getMat();
+    assert(src.type() == CV_32FC2 && src.cols == 1 && K.type() == CV_32F && dist.type() == CV_32F && !P.empty());
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) assert(P.at<float>(i, j) == K.at<float>(i, j));
+    float d5[5] = { 0, 0, 0, 0, 0 };
+    for (int i = 0; i < std::min(dist.rows * dist.cols, 5); ++i) d5[i] = dist.at<float>(i);
+    std::vector<float> out((size_t)src.rows * 2 + 2);
+    const Mat tight = src.clone();
+    const int rc = orc_undistort_points(reinterpret_cast<const float*>(tight.data), src.rows, K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2), d5, out.data());
+    assert(rc == ORC_OK); (void)rc;
+    dst_.create(src.rows, 1, CV_32FC2);
+    Mat dst = dst_.getMat();
+    for (int i = 0; i < src.rows; ++i) std::memcpy(dst.data + (size_t)i * dst.step, &out[2 * (size_t)i], 8);
+}
 template <typename... A> inline void rectangle(A&&...) {}
 template <typename... A> inline void circle(A&&...) {}
 inline int waitKey(int = 0) { return -1; }

@@ -3,9 +3,11 @@
 #pragma once
 #include <memory>
 #include <vector>
+#include <boost/make_shared.hpp>      // the real PCL headers bring boost's smart pointers with them
 namespace pcl {
 template <typename PointT> class PointCloud {
 public:
+    typedef PointT PointType;
     typedef std::shared_ptr<PointCloud<PointT>> Ptr;
     typedef std::shared_ptr<const PointCloud<PointT>> ConstPtr;
     std::vector<PointT> points;

@@ -1,0 +1,93 @@
+"""The oracle's restatement of the per-frame front end against THE REFERENCE'S OWN SOURCE with its REAL Core classes:
+oracle/_ref/libframe_ref.so is Core/frame.cpp + keyframe.cpp + landmark.cpp + map.cpp + Features/extractor.cpp + orbextractor.cpp
+(+ matcher.cpp) compiled verbatim.  Frame::Frame (BGR -> gray, depth scale, the distortion vector of Utils/common.h) and
+Frame::ExtractFeatures (rows a-9, a-10, 8f-2: Extractor::Extract -> ORBextractor, UndistortKeyPoints, the depth gather at the truncated
+distorted position, mvuRight, the unprojection of the undistorted point, ComputeImageBounds) must reproduce the oracle's keypoints,
+descriptors, mvKeysUn, mvKeys3Dc, mvuRight bit for bit; Landmark::ComputeDistinctiveDescriptors (8f-1) the oracle's choice.
+
+CPU-only.  Skipped where neither the reference checkout nor a prebuilt oracle/_ref exists."""
+import numpy as np
+import pytest
+
+import synth
+
+FR1 = dict(fx=517.3, fy=516.5, cx=318.6, cy=255.3)
+FR1_DIST = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)     # k1, k2, p1, p2, k3 (Utils/common.h:40-44)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref as r
+    if not r.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    return r
+
+
+def _bgr(gray_like, seed):
+    """A colour frame whose channels differ, so that the BGR -> gray weights matter."""
+    rng = np.random.default_rng(seed)
+    g = gray_like.astype(np.int16)
+    b = np.clip(g + rng.integers(-20, 21, g.shape), 0, 255); r = np.clip(g - rng.integers(-20, 21, g.shape), 0, 255)
+    return np.stack([b, g, r], -1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("i", [0, 3, 8])
+def test_frame_extract_features_identical_to_reference_source(ref, orc, texture, i):
+    bgr = _bgr(synth.make_frame(texture, i), i)
+    depth = synth.make_depth(i)
+    depth[::7, ::5] = 0                                                  # holes: no 3D point, mvuRight stays -1
+    r = ref.frame_extract(bgr, depth)
+    gray = orc.bgr2gray(bgr)
+    assert np.array_equal(r["gray"], gray)                               # Frame::Frame: cvtColor(BGR2GRAY)
+    k, d = orc.extract(gray)
+    assert len(k) == len(r["kps"]) > 900
+    assert r["kps"].tobytes() == k.tobytes() and np.array_equal(r["desc"], d)
+    xy = np.stack([k["x"], k["y"]], 1).astype(np.float32)
+    un = orc.undistort_points(xy, FR1["fx"], FR1["fy"], FR1["cx"], FR1["cy"], FR1_DIST)
+    assert np.array_equal(r["xy_un"], un)                                # Frame::UndistortKeyPoints
+    assert np.abs(un - xy).max() > 0.5                                   # the FR1 distortion does move the points
+    xyz, ur = orc.unproject(k, depth, dist=FR1_DIST)
+    assert np.array_equal(r["xyz"], xyz) and np.array_equal(r["uright"], ur)
+    assert (ur < 0).any() and (ur >= 0).sum() > 700                      # both branches of `if (z > 0)`
+    # Frame::ComputeImageBounds: the undistorted image corners
+    corners = np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32)
+    c = orc.undistort_points(corners, FR1["fx"], FR1["fy"], FR1["cx"], FR1["cy"], FR1_DIST)
+    exp = np.array([min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])], np.float32)
+    assert np.array_equal(r["bounds"], exp)
+
+
+def test_compute_distinctive_descriptors(ref, orc):
+    rng = np.random.default_rng(4)
+    nobs = rng.integers(0, 20, 300); nobs[:3] = (0, 1, 2)
+    offs = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(nobs), 32), dtype=np.uint8)
+    desc = np.repeat(base, nobs, axis=0)
+    flips = rng.integers(0, 256, (len(desc), 12))
+    for c in range(flips.shape[1]):                                       # noisy copies: medians tie often, the first smallest must win
+        desc[np.arange(len(desc)), flips[:, c] // 8] ^= (1 << (flips[:, c] % 8)).astype(np.uint8)
+    out, has = ref.distinctive_descriptors(desc, offs)
+    best, _ = orc.distinctive_descriptors(desc, offs)
+    for l in range(len(nobs)):
+        if nobs[l] == 0:
+            assert not has[l] and best[l] == -1
+        else:
+            assert has[l] and np.array_equal(out[l], desc[offs[l] + best[l]]), f"landmark {l}"
+
+
+def test_distinctive_descriptors_skip_bad_keyframes(ref, orc):
+    """landmark.cpp:235-238: observations whose keyframe isBad() are left out before the medians are taken."""
+    rng = np.random.default_rng(9)
+    nobs = rng.integers(3, 15, 80)
+    offs = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    desc = rng.integers(0, 256, (int(offs[-1]), 32), dtype=np.uint8)
+    bad = (rng.random(len(desc)) < 0.3).astype(np.uint8)
+    bad[offs[5]:offs[6]] = 1                                              # a landmark whose every observer is bad keeps no descriptor
+    out, has = ref.distinctive_descriptors(desc, offs, bad)
+    keep = bad == 0
+    offs2 = np.concatenate([[0], np.cumsum([int(keep[offs[l]:offs[l + 1]].sum()) for l in range(len(nobs))])]).astype(np.int32)
+    kept = desc[keep]
+    best, _ = orc.distinctive_descriptors(kept, offs2)
+    assert not has[5]
+    for l in range(len(nobs)):
+        if offs2[l + 1] > offs2[l]:
+            assert has[l] and np.array_equal(out[l], kept[offs2[l] + best[l]]), f"landmark {l}"
