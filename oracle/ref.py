@@ -295,3 +295,23 @@ def distinctive_descriptors(desc, offsets, bad=None):
     out = np.zeros((max(n, 1), 32), np.uint8); has = np.zeros(max(n, 1), np.uint8)
     frame_lib().ref_distinctive_descriptors(_p(desc) if len(desc) else None, _p(b) if b is not None else None, _p(offsets), n, _p(out), _p(has))
     return out[:n], has[:n].astype(bool)
+
+
+def frame_depth_covariance(depth):
+    """Ransac::DepthCovariance of libframe_ref.so's copy of ransac.cpp (quirk Q7: first call in the process latches)."""
+    L = frame_lib()
+    L.ref_frame_depth_covariance.restype = C.c_double; L.ref_frame_depth_covariance.argtypes = [C.c_double]
+    return float(L.ref_frame_depth_covariance(float(depth)))
+
+
+def odometry_compute(src_xyz, dst_xyz, m12, pose1, seed=42):
+    """Odometry(RANSAC).Compute(pF1, pF2, m12) (Odometry/odometry.cpp:44, 78-90) on the reference's real Frame objects after srand(seed)."""
+    src = np.ascontiguousarray(src_xyz, np.float32); dst = np.ascontiguousarray(dst_xyz, np.float32)
+    m12 = np.ascontiguousarray(m12, DMATCH_DT); p1 = np.ascontiguousarray(pose1, np.float32).reshape(16)
+    p2 = np.zeros(16, np.float32); outl = np.zeros(max(len(dst), 1), np.uint8); out = RansacOut(); inl = np.zeros(max(len(m12), 1), DMATCH_DT)
+    rc = frame_lib().ref_odometry_compute(_p(src), len(src), _p(dst), len(dst), _p(m12), len(m12), C.c_uint(seed), _p(p1), _p(p2), _p(outl), C.byref(out),
+                                          _p(inl), len(inl))
+    if rc:
+        raise RuntimeError(f"ref_odometry_compute rc={rc}")
+    return dict(ok=bool(out.ok), rmse=float(out.rmse), T12=np.array(out.T12, np.float32).reshape(4, 4), inliers=inl[:out.n_inliers].copy(),
+                pose2=p2.reshape(4, 4), outlier2=outl[:len(dst)].astype(bool))

@@ -1,12 +1,14 @@
 // oracle/ref_frame/ref_bridge_frame.cpp — TEST INFRASTRUCTURE ONLY.
 // (Its own directory: a quoted #include looks next to the including file first, and next to the other bridges sit the Core/ stand-ins.)
 // C entry points over the reference's own Frame and Landmark: Core/frame.cpp, Core/keyframe.cpp, Core/landmark.cpp, Core/map.cpp,
-// Features/extractor.cpp (+ the detector sources it names), Features/matcher.cpp and Features/orbextractor.cpp, each handed to g++
+// Features/extractor.cpp (+ the detector sources it names), Features/matcher.cpp, Features/orbextractor.cpp, Odometry/odometry.cpp and
+// Odometry/ransac.cpp, each handed to g++
 // verbatim from /root/reference by oracle/Makefile (target _ref): oracle/_ref/libframe_ref.so.  Here the reference's REAL Core classes
 // are used (the stand-ins of ref_shim/Core belong to the other two libraries): -I$(REF) comes before -Iref_shim.
 // Run from the reference's source: Frame::Frame (BGR -> gray, depth scale, K and the distortion vector from Utils/common.h),
 // Frame::ExtractFeatures (Extractor::Extract -> ORBextractor, UndistortKeyPoints, the depth gather at the distorted position, mvuRight,
-// the unprojection of the undistorted point, ComputeImageBounds), Landmark::ComputeDistinctiveDescriptors.
+// the unprojection of the undistorted point, ComputeImageBounds), Landmark::ComputeDistinctiveDescriptors, Odometry::Compute (RANSAC
+// strategy: Ransac::Iterate on real Frame objects, the composition rule through cv::Mat, SetPose, SetInlier).
 // Stubbed (each stops the process if reached): Database::Erase (needs the DBoW3 vocabulary) and Converter::toDescriptorVector (g2o).
 #include "../ref_shim/ref_bridge.cpp"        // Features/orbextractor.cpp + the bump arena that fixes quirk Q3's tie order (ArenaScope)
 
@@ -29,9 +31,17 @@
 #include "Features/extractor.h"
 #include "Utils/common.h"
 #include "Utils/converter.h"
+#include "Odometry/generalizedicp.h"
+#include "Odometry/odometry.h"
+#include "Odometry/pnpsolver.h"
+#include "Odometry/ransac.h"
 #undef private
 #undef protected
 
+// the two refinements behind the RANSAC strategy of Odometry::Compute are third-party iterative solvers (PCL GICP, g2o): never constructed here
+GeneralizedICP::GeneralizedICP(int, double) { std::abort(); }
+bool GeneralizedICP::Compute(const pcl::PointCloud<pcl::PointXYZ>::Ptr, const pcl::PointCloud<pcl::PointXYZ>::Ptr, const Eigen::Matrix4f&, const bool) { std::abort(); }
+int PnPSolver::Compute(Frame*) { std::abort(); }
 void Database::Erase(KeyFrame*) { std::abort(); }
 std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat&) { std::abort(); }
 
@@ -112,6 +122,56 @@ int ref_distinctive_descriptors(const uint8_t* desc, const uint8_t* bad, const i
         std::free(block);
     }
     return ORC_OK;
+}
+
+// Ransac::DepthCovariance of THIS library's copy of Odometry/ransac.cpp (quirk Q7: the first call in the process fixes the value)
+double ref_frame_depth_covariance(double depth)
+{
+    Ransac r;
+    return r.DepthCovariance(depth);
+}
+
+// Odometry(RANSAC).Compute(pF1, pF2, m12) (Odometry/odometry.cpp:9-31, 44, 78-90) on the reference's real Frame objects after srand(seed):
+// Ransac::Iterate, T12 * pF1->GetPose() as cv::Mat evaluates it, pF2->SetPose, pF2->SetInlier(m.trainIdx).  pose1: F1's Tcw (row-major 4x4);
+// outlier2 [ndst]: F2's mvbOutlier, all true before the call (what the matcher's SetOutlier leaves for matched features).
+int ref_odometry_compute(const float* src_xyz, int nsrc, const float* dst_xyz, int ndst, const orc_dmatch* m12, int nm, unsigned seed, const float* pose1,
+    float* pose2, uint8_t* outlier2, orc_ransac_out* out, orc_dmatch* inliers_out, int cap)
+{
+    if (!out || !pose1 || !pose2) return ORC_ERR_ARG;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    std::memset(out, 0, sizeof(*out));
+    Frame f1, f2;
+    auto fill = [](Frame& f, const float* xyz, int n) {
+        f.N = (size_t)n; f.mvKeys3Dc.resize((size_t)n); f.mvbOutlier.assign((size_t)n, true); f.mvpLandmarks.assign((size_t)n, nullptr);
+        for (int i = 0; i < n; ++i) f.mvKeys3Dc[(size_t)i] = cv::Point3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    };
+    fill(f1, src_xyz, nsrc); fill(f2, dst_xyz, ndst);
+    cv::Mat T1(4, 4, CV_32F);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T1.at<float>(i, j) = pose1[4 * i + j];
+    f1.SetPose(T1);
+    std::vector<cv::DMatch> ms((size_t)nm);
+    for (int i = 0; i < nm; ++i) ms[(size_t)i] = cv::DMatch(m12[i].queryIdx, m12[i].trainIdx, m12[i].imgIdx, m12[i].distance);
+    // the reference's constructor leaves mpBA unset for the RANSAC strategy and its destructor deletes it when non-null: built in zeroed storage
+    void* mem = std::calloc(1, sizeof(Odometry));
+    Odometry* od = new (mem) Odometry(Odometry::RANSAC);
+    srand(seed);
+    od->Compute(&f1, &f2, ms);
+    const Ransac* r = od->mpRansac;
+    out->rmse = r->rmse; out->n_inliers = (int)r->mvInliers.size(); out->ok = out->n_inliers >= 20 ? 1 : 0;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out->T12[4 * i + j] = r->mT12(i, j);
+    int rc = out->n_inliers > cap ? ORC_ERR_CAPACITY : ORC_OK;
+    for (int i = 0; i < out->n_inliers && inliers_out && rc == ORC_OK; ++i) {
+        const cv::DMatch& m = r->mvInliers[(size_t)i];
+        orc_dmatch o = { m.queryIdx, m.trainIdx, m.imgIdx, m.distance };
+        inliers_out[i] = o;
+    }
+    const cv::Mat T2 = f2.GetPose();
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) pose2[4 * i + j] = T2.at<float>(i, j);
+    if (outlier2) for (int j = 0; j < ndst; ++j) outlier2[j] = f2.mvbOutlier[(size_t)j] ? 1 : 0;
+    od->~Odometry();
+    std::free(mem);
+    return rc;
 }
 
 }  // extern "C"

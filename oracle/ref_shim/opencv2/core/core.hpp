@@ -219,7 +219,8 @@ inline const _OutputArray& noArray() { static _OutputArray none; return none; }
 // tests/test_fuse_bow.py and tests/test_trajectory.py pin against cv2.gemm)
 struct MatMul {
     Mat a, b;
-    operator Mat() const                                               // A * B alone: gemm with beta = 0
+    operator Mat() const { return eval(); }
+    Mat eval() const                                                   // A * B alone: gemm with beta = 0
     {
         Mat d(a.rows, b.cols, CV_32F);
         for (int i = 0; i < d.rows; ++i)
@@ -231,7 +232,7 @@ struct MatMul {
         return d;
     }
 };
-inline Mat::Mat(const MatMul& m) : Mat() { *this = (Mat)m; }
+inline Mat::Mat(const MatMul& m) : Mat() { *this = m.eval(); }
 inline MatMul operator*(const Mat& a, const Mat& b) { assert(a.type() == CV_32F && b.type() == CV_32F && a.cols == b.rows); MatMul m = { a, b }; return m; }
 inline Mat operator-(const Mat& a)
 {

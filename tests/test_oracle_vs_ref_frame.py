@@ -91,3 +91,23 @@ def test_distinctive_descriptors_skip_bad_keyframes(ref, orc):
     for l in range(len(nobs)):
         if offs2[l + 1] > offs2[l]:
             assert has[l] and np.array_equal(out[l], kept[offs2[l] + best[l]]), f"landmark {l}"
+
+
+def test_odometry_compute_on_real_frames(ref, orc):
+    """Odometry(RANSAC).Compute from Odometry/odometry.cpp + ransac.cpp on the reference's real Frame objects: Ransac::Iterate, the
+    composition rule T12 * pF1->GetPose() through cv::Mat (SetPose / GetPose of frame.cpp), SetInlier(m.trainIdx) — against the oracle's
+    ransac_iterate + compose_trajectory."""
+    cov = ref.frame_depth_covariance(2.0)
+    rng = np.random.default_rng(1)
+    ang = 0.2
+    pose1 = np.eye(4, dtype=np.float32)
+    pose1[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+    pose1[:3, 3] = rng.normal(0, 1, 3).astype(np.float32)
+    for seed, outl in ((42, 0.3), (7, 0.6), (9, 1.0)):
+        src, dst, m, _, _ = synth.rigid_pairs(seed=seed, outlier_frac=outl)
+        r = ref.odometry_compute(src, dst, m, pose1, seed=seed)
+        o = orc.ransac_iterate(src, dst, m, seed=seed, depth_cov=cov)
+        assert r["inliers"].tobytes() == o["inliers"].tobytes() and np.array_equal(r["T12"], o["T12"]) and r["rmse"] == o["rmse"]
+        assert np.array_equal(r["pose2"], orc.compose_trajectory(o["T12"][None], pose1)[1])
+        exp = np.ones(len(dst), bool); exp[o["inliers"]["trainIdx"]] = False
+        assert np.array_equal(r["outlier2"], exp)
