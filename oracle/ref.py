@@ -26,7 +26,7 @@ _lib = None
 def build():
     """Compile from the reference checkout when it is present; otherwise keep whatever prebuilt file is there."""
     if (REFERENCE / "Features" / "orbextractor.cpp").exists():
-        subprocess.run(["make", "-C", str(_DIR), "-s", "_ref", f"REF={REFERENCE}"], check=True)
+        subprocess.run(["make", "-C", str(_DIR), "-s", "-j3", "_ref", f"REF={REFERENCE}"], check=True)
     return SO.exists() and SO_ODOMETRY.exists() and SO_FRAME.exists()
 
 
