@@ -315,3 +315,16 @@ def odometry_compute(src_xyz, dst_xyz, m12, pose1, seed=42):
         raise RuntimeError(f"ref_odometry_compute rc={rc}")
     return dict(ok=bool(out.ok), rmse=float(out.rmse), T12=np.array(out.T12, np.float32).reshape(4, 4), inliers=inl[:out.n_inliers].copy(),
                 pose2=p2.reshape(4, 4), outlier2=outl[:len(dst)].astype(bool))
+
+
+def real_knn_match_frames(q, t, ratio, lm_obs1, outlier1, lm_obs2):
+    """Matcher(ratio).KnnMatch(Frame&, Frame&, matches) (matcher.cpp:55-88) on the reference's real Frame / Landmark objects:
+    (matches, slot2 [nt] = F1 feature whose landmark ended in F2's slot or -1, outlier2 [nt])."""
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    o1 = np.ascontiguousarray(lm_obs1, np.int32); x1 = np.ascontiguousarray(outlier1, np.uint8); o2 = np.ascontiguousarray(lm_obs2, np.int32)
+    out = np.zeros(max(len(q), 1), DMATCH_DT); n = C.c_int(0); slot2 = np.zeros(max(len(t), 1), np.int32); outl2 = np.zeros(max(len(t), 1), np.uint8)
+    rc = frame_lib().ref_real_knn_match_frames(_p(q), len(q), _p(t), len(t), C.c_float(ratio), _p(o1), _p(x1), _p(o2), _p(out), len(out), C.byref(n),
+                                               _p(slot2), _p(outl2))
+    if rc:
+        raise RuntimeError(f"ref_real_knn_match_frames rc={rc}")
+    return out[:n.value].copy(), slot2[:len(t)], outl2[:len(t)].astype(bool)

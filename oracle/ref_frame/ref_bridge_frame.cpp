@@ -29,6 +29,7 @@
 #include "Core/landmark.h"
 #include "Core/map.h"
 #include "Features/extractor.h"
+#include "Features/matcher.h"
 #include "Utils/common.h"
 #include "Utils/converter.h"
 #include "Odometry/generalizedicp.h"
@@ -121,6 +122,53 @@ int ref_distinctive_descriptors(const uint8_t* desc, const uint8_t* bad, const i
         for (KeyFrame* kf : kfs) kf->~KeyFrame();
         std::free(block);
     }
+    return ORC_OK;
+}
+
+// Matcher(ratio).KnnMatch(Frame& F1, Frame& F2, matches) (Features/matcher.cpp:55-88) on the reference's REAL Frame / Landmark / Map
+// objects.  lm_obs1[i]: -1 = feature i of F1 holds no landmark, else that landmark's Observations(); outlier1[i]: F1.IsOutlier(i);
+// lm_obs2[j]: the same for F2's slots before the call.  slot2[j] (out): index of the F1 feature whose landmark sits in slot j of F2 after
+// the call, -1 = none or the landmark that was there before; outlier2[j] (out): F2's mvbOutlier.
+int ref_real_knn_match_frames(const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio, const int* lm_obs1, const uint8_t* outlier1, const int* lm_obs2,
+    orc_dmatch* out, int cap, int* n_out, int* slot2, uint8_t* outlier2)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Extractor::mNorm = cv::NORM_HAMMING;
+    Map map;
+    Frame f1, f2;
+    auto fill = [](Frame& f, const uint8_t* d, int n) {
+        f.N = (size_t)n; f.mvbOutlier.assign((size_t)n, false); f.mvpLandmarks.assign((size_t)n, nullptr); f.mvuRight.assign((size_t)n, -1.f);
+        f.mDescriptors = cv::Mat(n, 32, CV_8UC1);
+        if (n > 0) std::memcpy(f.mDescriptors.data, d, (size_t)n * 32);
+    };
+    fill(f1, q, nq); fill(f2, t, nt);
+    cv::Mat pos = cv::Mat::eye(3, 1, CV_32F);
+    std::vector<std::unique_ptr<Landmark>> lms1, lms2;
+    std::map<Landmark*, int> owner;
+    for (int i = 0; i < nq; ++i) {
+        if (outlier1[i]) f1.mvbOutlier[(size_t)i] = true;
+        if (lm_obs1[i] < 0) continue;
+        lms1.emplace_back(new Landmark(pos, &map, &f1, (size_t)i));
+        lms1.back()->nObs = lm_obs1[i];
+        f1.mvpLandmarks[(size_t)i] = lms1.back().get(); owner[lms1.back().get()] = i;
+    }
+    for (int j = 0; j < nt; ++j) {
+        if (lm_obs2[j] < 0) continue;
+        lms2.emplace_back(new Landmark(pos, &map, &f2, (size_t)j));
+        lms2.back()->nObs = lm_obs2[j];
+        f2.mvpLandmarks[(size_t)j] = lms2.back().get();
+    }
+    Matcher m(ratio);
+    std::vector<cv::DMatch> res;
+    *n_out = (int)m.KnnMatch(f1, f2, res);
+    for (int j = 0; j < nt; ++j) {
+        Landmark* p = f2.mvpLandmarks[(size_t)j];
+        slot2[j] = (p && owner.count(p)) ? owner[p] : -1;
+        outlier2[j] = f2.mvbOutlier[(size_t)j] ? 1 : 0;
+    }
+    if (*n_out > cap) return ORC_ERR_CAPACITY;
+    for (size_t i = 0; i < res.size(); ++i) { orc_dmatch o = { res[i].queryIdx, res[i].trainIdx, res[i].imgIdx, res[i].distance }; out[i] = o; }
     return ORC_OK;
 }
 

@@ -111,3 +111,28 @@ def test_odometry_compute_on_real_frames(ref, orc):
         assert np.array_equal(r["pose2"], orc.compose_trajectory(o["T12"][None], pose1)[1])
         exp = np.ones(len(dst), bool); exp[o["inliers"]["trainIdx"]] = False
         assert np.array_equal(r["outlier2"], exp)
+
+
+def test_knn_match_on_real_frames_and_landmarks(ref, orc):
+    """Matcher::KnnMatch(Frame&, Frame&) compiled against the reference's real Core classes: the kNN-2 + ratio survivors of the oracle, then
+    the reference's landmark rules replayed here in query order — F1's feature must hold a landmark and not be an outlier; F2's slot must
+    not hold a landmark with Observations() > 0; an accepted match moves the landmark into the slot and flags it as outlier."""
+    rng = np.random.default_rng(11)
+    q, t = synth.descriptor_sets(n=600, seed=5)[:2]
+    obs1 = rng.integers(0, 4, len(q)).astype(np.int32); obs1[rng.random(len(q)) < 0.2] = -1
+    out1 = (rng.random(len(q)) < 0.1).astype(np.uint8)
+    obs2 = np.full(len(t), -1, np.int32); pick = rng.random(len(t)) < 0.15; obs2[pick] = rng.integers(0, 3, int(pick.sum()))
+    got, slot2, outl2 = ref.real_knn_match_frames(q, t, 0.8, obs1, out1, obs2)
+    base = orc.knn_match(q, t, 0.8, False)
+    slot_obs = obs2.copy(); exp = []; exp_slot = np.full(len(t), -1, np.int32); exp_out = np.zeros(len(t), bool)
+    for m in base:
+        i1, i2 = int(m["queryIdx"]), int(m["trainIdx"])
+        if obs1[i1] < 0 or out1[i1]:
+            continue
+        if slot_obs[i2] > 0:
+            continue
+        slot_obs[i2] = obs1[i1]; exp_slot[i2] = i1; exp_out[i2] = True
+        exp.append(m)
+    exp = np.array(exp, base.dtype)
+    assert got.tobytes() == exp.tobytes() and 100 < len(exp) < len(base)
+    assert np.array_equal(slot2, exp_slot) and np.array_equal(outl2, exp_out)
