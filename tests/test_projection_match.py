@@ -77,7 +77,8 @@ def test_oracle_edge_cases(orc):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,n_feat,n_lm,radius,crowded", [(11, 1000, 900, 8.0, False), (12, 1000, 1500, 15.0, False), (13, 400, 380, 8.0, True),
-                                                            (14, 37, 5, 8.0, False), (15, 2000, 2000, 30.0, True)])
+                                                            (14, 37, 5, 8.0, False), (15, 2000, 2000, 30.0, True),
+                                                            (16, 50000, 300, 8.0, False), (17, 50000, 600, 1.5, False)])       # taken flags beyond the 48 KB default of shared memory: crowded / sparse windows
 def test_cuda_matches_oracle_host_arrays(ob, orc, seed, n_feat, n_lm, radius, crowded):
     ctx = ob.Context(max_frames=2)
     sc = _scene(seed, n_feat, n_lm, radius, crowded=crowded)
