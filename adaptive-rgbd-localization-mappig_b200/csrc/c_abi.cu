@@ -101,7 +101,8 @@ static int run_extract(orbf_context* c, int slot0, int n, bool sideStream)
         // one-frame call: the depth plane goes into the page-locked arena now, on the host, while the kernels queued above run; the
         // describe kernel (launched after this copy has finished) samples it in place
         const int w = c->cfg.width, h = c->cfg.height;
-        for (int y = 0; y < h; ++y) memcpy(c->pendDepthDst + (size_t)y * w, c->pendDepthSrc + (size_t)y * c->pendDepthStride, (size_t)w * 2);
+        if (c->pendDepthStride == w) memcpy(c->pendDepthDst, c->pendDepthSrc, (size_t)w * h * 2);
+        else for (int y = 0; y < h; ++y) memcpy(c->pendDepthDst + (size_t)y * w, c->pendDepthSrc + (size_t)y * c->pendDepthStride, (size_t)w * 2);
         c->pendDepthSrc = nullptr;
     }
     orbf_prof_begin(c, ST_DESCRIBE); TRY(orbf_launch_describe(c, slot0, n)); orbf_prof_end(c, ST_DESCRIBE);
@@ -381,7 +382,8 @@ extern "C" int orbf_extract_batch(orbf_context* c, int32_t slot0, int32_t n, con
         const bool withDepth = depth && depth_stride_elems >= w;
         TRY(arena_begin(c, (size_t)w * h * (withDepth ? 3 : 1) + 1024));
         uint8_t* g = arena_take(c, (size_t)w * h);
-        for (int y = 0; y < h; ++y) memcpy(g + (size_t)y * w, gray + (size_t)y * gray_stride, (size_t)w);
+        if (gray_stride == w) memcpy(g, gray, (size_t)w * h);                    // tight rows: one copy
+        else for (int y = 0; y < h; ++y) memcpy(g + (size_t)y * w, gray + (size_t)y * gray_stride, (size_t)w);
         uint16_t* d = withDepth ? reinterpret_cast<uint16_t*>(arena_take(c, (size_t)w * h * 2)) : nullptr;
         TRY(set_host_inputs(c, slot0, 1, g, w, (int64_t)w * h, d, w, (int64_t)w * h, hf));
         if (withDepth) {
