@@ -34,6 +34,15 @@
 
 namespace {
 
+// Sensitivity probe (tests/test_oracle_ransac.py): Eigen evaluates small fixed-size inner products as a balanced tree
+// (a0 + (a1 + a2), (a0 + a1) + (a2 + a3)) when it unrolls a reduction, and left to right otherwise; which one a given build of the
+// reference uses is not knowable here (the library is absent, section 7 of DESIGN.md).  g_sumTree = 1 switches every 3- / 4-term sum of
+// the PCL / Eigen restatements to the tree order so that the effect on inlier sets and poses can be measured.  Default 0: left to right,
+// the order the CUDA kernels implement.
+int g_sumTree = 0;
+template <typename T> inline T sum3(T a, T b, T c) { return g_sumTree ? a + (b + c) : (a + b) + c; }
+template <typename T> inline T sum4(T a, T b, T c, T d) { return g_sumTree ? (a + b) + (c + d) : ((a + b) + c) + d; }
+
 inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
 
 inline int hamming256(const uint8_t* a, const uint8_t* b)
@@ -166,10 +175,10 @@ struct Tfc {
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) {
                 const float us = U.m[i][2] * s22;
-                R[i][j] = (U.m[i][0] * V.m[j][0] + U.m[i][1] * V.m[j][1]) + us * V.m[j][2];
+                R[i][j] = sum3(U.m[i][0] * V.m[j][0], U.m[i][1] * V.m[j][1], us * V.m[j][2]);
             }
         for (int i = 0; i < 3; ++i) {
-            const float rm = (R[i][0] * m1[0] + R[i][1] * m1[1]) + R[i][2] * m1[2];
+            const float rm = sum3(R[i][0] * m1[0], R[i][1] * m1[1], R[i][2] * m1[2]);
             T[4 * i + 0] = R[i][0]; T[4 * i + 1] = R[i][1]; T[4 * i + 2] = R[i][2];
             T[4 * i + 3] = m2[i] - rm;
         }
@@ -220,10 +229,10 @@ double mahal2(const float* x1, const float* x2, const double T[16], double cz)
     if (std::isnan(x1[2]) || std::isnan(x2[2])) return dmax;
     const double a[3] = { x1[0], x1[1], x1[2] }, b[3] = { x2[0], x2[1], x2[2] };
     double mu12[3], dl[3];
-    for (int i = 0; i < 3; ++i) mu12[i] = ((T[4 * i] * a[0] + T[4 * i + 1] * a[1]) + T[4 * i + 2] * a[2]) + T[4 * i + 3];
+    for (int i = 0; i < 3; ++i) mu12[i] = sum4(T[4 * i] * a[0], T[4 * i + 1] * a[1], T[4 * i + 2] * a[2], T[4 * i + 3]);
     for (int i = 0; i < 3; ++i) dl[i] = mu12[i] - b[i];
     {
-        const double sq = (dl[0] * dl[0] + dl[1] * dl[1]) + dl[2] * dl[2];
+        const double sq = sum3(dl[0] * dl[0], dl[1] * dl[1], dl[2] * dl[2]);
         const double s1 = std::max(K.cov_x, cz), s2 = std::max(K.cov_x, cz);
         if (sq > 2.0 * (s1 + s2)) return dmax;
     }
@@ -233,14 +242,13 @@ double mahal2(const float* x1, const float* x2, const double T[16], double cz)
     double S[3][3];
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
-            const double v = ((T[4 * 0 + i] * c1[0]) * T[4 * 0 + j] + (T[4 * 1 + i] * c1[1]) * T[4 * 1 + j])
-                + (T[4 * 2 + i] * c1[2]) * T[4 * 2 + j];
+            const double v = sum3((T[4 * 0 + i] * c1[0]) * T[4 * 0 + j], (T[4 * 1 + i] * c1[1]) * T[4 * 1 + j], (T[4 * 2 + i] * c1[2]) * T[4 * 2 + j]);
             S[i][j] = v + ((i == j) ? c2[i] : 0.0);
         }
     if (std::isnan(dl[2])) return dmax;
     double xs[3];
     if (!llt3_solve(S, dl, xs)) return dmax;                  // not positive definite (degenerate depth)
-    const double d2 = (dl[0] * xs[0] + dl[1] * xs[1]) + dl[2] * xs[2];
+    const double d2 = sum3(dl[0] * xs[0], dl[1] * xs[1], dl[2] * xs[2]);
     if (!(d2 >= 0.0)) return dmax;
     return d2;
 }
@@ -400,6 +408,9 @@ int orc_weighted_transform(const float* src_xyz, const float* dst_xyz, int n, fl
     tfc.transform(T16);
     return ORC_OK;
 }
+
+// 0 = inner sums left to right (default, what the CUDA path implements), 1 = Eigen's balanced-tree order: a sensitivity probe only
+int orc_set_sum_order(int tree) { const int old = g_sumTree; g_sumTree = tree ? 1 : 0; return old; }
 
 // pcl::TransformationFromCorrespondences over explicit (point, corresponding point, weight) triples, in the order given
 int orc_tfc_transform(const float* p_xyz, const float* q_xyz, const float* w, int n, float* T16)

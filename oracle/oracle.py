@@ -420,6 +420,12 @@ def mahalanobis2(p1, p2, T, depth_cov):
     return float(lib().orc_mahalanobis2(_p(p1), _p(p2), _p(T), C.c_double(depth_cov)))
 
 
+def set_sum_order(tree):
+    """Sensitivity probe: evaluate the 3- / 4-term inner sums of the PCL / Eigen restatements as Eigen's balanced tree (True) instead of
+    left to right (False, the default and what the CUDA path implements).  Returns the previous setting."""
+    return bool(lib().orc_set_sum_order(int(bool(tree))))
+
+
 def kabsch(A, B):
     A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
     T = np.zeros(16, np.float32)

@@ -138,6 +138,8 @@ double orc_mahalanobis2(const float* p1, const float* p2, const float* T16, doub
 /* the two third-party numerical routines of the path on their own (shared with the oracle/_ref stand-ins for PCL / Eigen) */
 int orc_tfc_transform(const float* p_xyz, const float* q_xyz, const float* w, int n, float* T16);
 int orc_llt3_solve(const double* S9, const double* b3, double* x3);
+/* sensitivity probe: 1 = evaluate the 3- / 4-term inner sums of the PCL / Eigen restatements as Eigen's balanced tree; returns the old setting */
+int orc_set_sum_order(int tree);
 int orc_kabsch(const float* setA, const float* setB, int n, float* T16);
 
 #ifdef __cplusplus
