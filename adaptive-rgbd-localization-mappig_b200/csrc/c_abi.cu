@@ -1210,7 +1210,6 @@ static int ransac_iterate_core(orbf_context* c, const orbf_ransac_config* cfg, c
     // launches: the first two waves (8 hypotheses) are queued with the read-back behind them; only a pair whose done flag is still clear
     // after the synchronisation gets the remaining waves and a second read-back.
     const bool twoPhase = !hyp_trace && !sample_table_out && cfg->iterations > 8;
-    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, /*standalone=*/true, /*fullTable=*/sample_table_out != nullptr, false, 0, twoPhase ? 2 : 5));
     // results: everything the caller asked for into the arena (inliers / sorted matches at their upper bound nm), one synchronisation
     orbf_ransac_result* hres = reinterpret_cast<orbf_ransac_result*>(arena_take(c, sizeof(orbf_ransac_result)));
     int* hdone = reinterpret_cast<int*>(arena_take(c, sizeof(int)));
@@ -1236,10 +1235,13 @@ static int ransac_iterate_core(orbf_context* c, const orbf_ransac_config* cfg, c
             ORBF_CUDA(c, cudaMemcpyAsync(sc.at<float>(oP0), hPose, 64, cudaMemcpyHostToDevice, c->stream));
         }
     }
+    const float* dPoseIn = hPose ? sc.at<float>(oP0) : nullptr;              // the select kernel writes pose2 = T12 * pose1 next to the result
+    float* dPoseOut = hPose ? sc.at<float>(oPoses) : nullptr;
+    TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, /*standalone=*/true, /*fullTable=*/sample_table_out != nullptr, false, 0, twoPhase ? 2 : 5, dPoseIn, dPoseOut));
     for (int phase = 0; phase < 2; ++phase) {
         if (phase == 1) {
             if (!twoPhase || *hdone) break;
-            TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, true, false, false, 2, 5));
+            TRY(orbf_launch_ransac(c, rs, 0, 1, cf, dTab, true, false, false, 2, 5, dPoseIn, dPoseOut));
         }
         ORBF_CUDA(c, cudaMemcpyAsync(hres, c->d_rres, sizeof(orbf_ransac_result), cudaMemcpyDeviceToHost, c->stream));
         ORBF_CUDA(c, cudaMemcpyAsync(hdone, orbf_ransac_done_flag(c, 0), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1256,10 +1258,7 @@ static int ransac_iterate_core(orbf_context* c, const orbf_ransac_config* cfg, c
                 if (hCloudS) ORBF_CUDA(c, cudaMemcpyAsync(hCloudS, c->d_cloudSrc, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
                 if (hCloudT) ORBF_CUDA(c, cudaMemcpyAsync(hCloudT, c->d_cloudTgt, cloudM * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
             }
-            if (hPose) {
-                TRY(orbf_launch_compose(c, 1, sc.at<float>(oP0), sc.at<float>(oPoses), nullptr));
-                ORBF_CUDA(c, cudaMemcpyAsync(hPose + 16, sc.at<float>(oPoses) + 16, 64, cudaMemcpyDeviceToHost, c->stream));
-            }
+            if (hPose) ORBF_CUDA(c, cudaMemcpyAsync(hPose + 16, dPoseOut + 16, 64, cudaMemcpyDeviceToHost, c->stream));
         }
         ORBF_CUDA(c, cudaStreamSynchronize(c->stream));
     }

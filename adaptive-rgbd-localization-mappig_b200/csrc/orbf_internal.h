@@ -263,7 +263,8 @@ int orbf_ransac_reserve(orbf_context* ctx, const orbf_ransac_config& cfg);
 // mpSourceCloud / mpTargetCloud (Odometry/ransac.cpp:171-189) of pairs [pair0, pair0 + npairs) of the set last handed to orbf_launch_ransac
 int orbf_launch_ransac_clouds(orbf_context* ctx, int pair0, int npairs);
 int orbf_launch_ransac(orbf_context* ctx, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, bool standalone, bool fullTable = false, bool probeOnly = false, int firstWave = 0, int lastWave = 5);
+    const int* d_userSamples, bool standalone, bool fullTable = false, bool probeOnly = false, int firstWave = 0, int lastWave = 5,
+    const float* d_composeIn = nullptr, float* d_composeOut = nullptr);
 // the done flag of a pair's sequential RANSAC loop (device pointer to one int), valid after orbf_launch_ransac's replay kernels
 const int* orbf_ransac_done_flag(orbf_context* ctx, int pair);
 

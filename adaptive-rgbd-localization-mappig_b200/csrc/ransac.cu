@@ -38,6 +38,7 @@ struct RansacParams {
     double* depthCov;
     int K, iters, S;
     int covReset;             // standalone call: ignore (and do not touch) the covariance latched on the context
+    const float* composeIn; float* composeOut;   // one-pair Odometry::Compute: pose2 = T12 * pose1 written by the select kernel (may be NULL)
     int tabRows;              // sample-table rows ransac_prepare draws itself; ransac_table_kernel completes the table for the pairs that go on
     double covX, covY;
 };
@@ -60,6 +61,51 @@ constexpr int SORT_QCAP = 128;
 constexpr int SORT_THREADS = PR_THREADS - 32;     // warp 1 draws the sample table meanwhile
 __device__ __forceinline__ void sort_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SORT_THREADS) : "memory"); }
 
+// One range of the introsort recursion partitioned by a WARP, with the result of libstdc++'s sequential __unguarded_partition: the k-th
+// element (from the left) that stops the left scan — not less than the pivot — is exchanged with the k-th element (from the right) that
+// stops the right scan — not greater than the pivot — for as long as the two positions have not crossed; neither scan ever looks at an
+// element the other side has already moved before they cross.  So the stop positions follow from two ballot prefix sums over the
+// untouched range, K = the number of pairs before the crossing, and the cut is min(left stop K, right stop K - 1) (left stop 0 when
+// nothing is exchanged).  Exhaustively compared with the sequential loop on random ranges with heavy ties (authoring container).  The
+// u16 position lists live in the range's own part of keys2, which is only written after the recursion.
+__device__ int warp_unguarded_partition(unsigned long long* keys, unsigned long long* keys2, int first, int last, int lane)
+{
+    const uint32_t pv = (uint32_t)(keys[first] >> 32);
+    const int lo0 = first + 1, n = last - lo0;
+    uint16_t* Lpos = reinterpret_cast<uint16_t*>(keys2 + first);
+    uint16_t* Rpos = Lpos + n;
+    const unsigned below = (1u << lane) - 1;
+    int nL = 0, nR = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int i = lo0 + b + lane, j = last - 1 - (b + lane);
+        const bool in = b + lane < n;
+        const bool fl = in && !((uint32_t)(keys[i] >> 32) < pv), fr = in && !(pv < (uint32_t)(keys[j] >> 32));
+        const unsigned ml = __ballot_sync(0xffffffffu, fl), mr = __ballot_sync(0xffffffffu, fr);
+        if (fl) Lpos[nL + __popc(ml & below)] = (uint16_t)i;
+        if (fr) Rpos[nR + __popc(mr & below)] = (uint16_t)j;
+        nL += __popc(ml); nR += __popc(mr);
+    }
+    __syncwarp();
+    const int nmin = min(nL, nR);
+    int K = 0;
+    for (int b = 0; b < nmin; b += 32) {
+        const int k = b + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, k < nmin && Lpos[k] < Rpos[k]);
+        K += __popc(m);
+        if (m != 0xffffffffu) break;
+    }
+    for (int k = lane; k < K; k += 32) {
+        const int p = Lpos[k], q = Rpos[k];
+        const unsigned long long a = keys[p];
+        keys[p] = keys[q]; keys[q] = a;
+    }
+    int cut;
+    if (K == 0) cut = Lpos[0];
+    else { cut = Rpos[K - 1]; if (K < nL && (int)Lpos[K] < cut) cut = Lpos[K]; }
+    __syncwarp();
+    return cut;
+}
+
 __device__ void parallel_std_sort(unsigned long long* keys, unsigned long long* keys2, uint16_t* leafStart, uint16_t* leafEnd, int M, int tid)
 {
     __shared__ int qF[2][SORT_QCAP], qL[2][SORT_QCAP], qD[2][SORT_QCAP];
@@ -80,14 +126,25 @@ __device__ void parallel_std_sort(unsigned long long* keys, unsigned long long* 
     while (true) {
         const int n = qN[cur];
         if (n == 0) break;
-        for (int t = tid; t < n; t += SORT_THREADS) {
+        // the first levels of the recursion hold one, two, ... long ranges: a warp each (the partition of a 400-element range by one
+        // thread is the kernel's critical path); later levels hold many short ranges: a thread each
+        const bool byWarp = n <= SORT_THREADS / 32;
+        for (int t = byWarp ? (tid >> 5) : tid; t < n; t += byWarp ? n : SORT_THREADS) {
             const int first = qF[cur][t], last = qL[cur][t];
             int depth = qD[cur][t];
-            if (depth == 0) { S.heap_sort(first, last); continue; }      // leaf of singletons: already in final order
+            if (depth == 0) { if (!byWarp || (tid & 31) == 0) S.heap_sort(first, last); continue; }      // leaf of singletons: already in final order
             --depth;
             const int mid = first + (last - first) / 2;
-            S.move_median_to_first(first, first + 1, mid, last - 1);
-            const int cut = S.unguarded_partition(first + 1, last, first);
+            int cut;
+            if (byWarp) {
+                if ((tid & 31) == 0) S.move_median_to_first(first, first + 1, mid, last - 1);
+                __syncwarp();
+                cut = warp_unguarded_partition(keys, keys2, first, last, tid & 31);
+                if ((tid & 31) != 0) continue;                       // lane 0 files the two parts
+            } else {
+                S.move_median_to_first(first, first + 1, mid, last - 1);
+                cut = S.unguarded_partition(first + 1, last, first);
+            }
             const int lo[2] = { cut, first }, hi[2] = { last, cut };
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -941,6 +998,22 @@ __global__ void __launch_bounds__(SEL_THREADS) ransac_select_kernel(RansacParams
         r.depth_cov_used = cz;
         *res = r;
     }
+    // Odometry::Compute's composition rule for a one-pair call (odometry.cpp:82-84): cv::Mat's 4x4 float product, every element the four
+    // products summed left to right — the arithmetic of compose_kernel, without its launch
+    if (P.composeOut && blockIdx.x == 0 && lane < 16) {
+        const int rr = lane >> 2, cc = lane & 3;
+        const float* B = P.composeIn;
+        float a0 = T[0], a1 = T[1], a2 = T[2], a3 = T[3];
+        if (rr == 1) { a0 = T[4]; a1 = T[5]; a2 = T[6]; a3 = T[7]; }
+        if (rr == 2) { a0 = T[8]; a1 = T[9]; a2 = T[10]; a3 = T[11]; }
+        if (rr == 3) { a0 = T[12]; a1 = T[13]; a2 = T[14]; a3 = T[15]; }
+        float t = __fmul_rn(a0, B[cc]);
+        t = __fadd_rn(t, __fmul_rn(a1, B[4 + cc]));
+        t = __fadd_rn(t, __fmul_rn(a2, B[8 + cc]));
+        t = __fadd_rn(t, __fmul_rn(a3, B[12 + cc]));
+        P.composeOut[lane] = B[lane];
+        P.composeOut[16 + lane] = t;
+    }
 }
 
 // Kabsch::Compute (kabsch.cpp:14-57), single thread (the reference never calls it on the hot path)
@@ -1016,7 +1089,7 @@ int orbf_ransac_reserve(orbf_context* c, const orbf_ransac_config& cfg)
 // a later launch with firstWave > 0 on the same set continues where the earlier one stopped (the one-pair call checks the pair's
 // done flag after two waves and only then queues the rest).  Every launch ends with the select kernel.
 int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npairs, const orbf_ransac_config& cfg,
-    const int* d_userSamples, bool standalone, bool fullTable, bool probeOnly, int firstWave, int lastWave)
+    const int* d_userSamples, bool standalone, bool fullTable, bool probeOnly, int firstWave, int lastWave, const float* d_composeIn, float* d_composeOut)
 {
     if (npairs <= 0) return ORBF_OK;
     {
@@ -1033,6 +1106,7 @@ int orbf_launch_ransac(orbf_context* c, const RansacSet& rs, int pair0, int npai
     P.covReset = standalone ? 1 : 0;
     P.depthCov = c->d_depthCov + ((standalone || cfg.depth_cov >= 0.0) ? 1 : 0); P.K = c->K; P.iters = iters; P.S = S;
     P.state = reinterpret_cast<RState*>(c->d_rstate); P.hypLo = 0; P.hypHi = iters; P.pair0 = pair0;
+    P.composeIn = d_composeIn; P.composeOut = d_composeIn ? d_composeOut : nullptr;
     constexpr int LAZY_ROWS = 8;                     // = the end of the second hypothesis wave
     P.tabRows = (fullTable || d_userSamples) ? iters : std::min(iters, LAZY_ROWS);
     {   // raster covariances of ErrorFunction2 (ransac.cpp:352-359), host libm like the reference
