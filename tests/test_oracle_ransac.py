@@ -131,6 +131,22 @@ def test_std_sort_replay(ob, orc):
         assert ob.selftest_introsort(d).tobytes() == orc.std_sort_dmatch(d).tobytes()
 
 
+def test_warp_partition_rule_equals_libstdcxx(tmp_path):
+    """The rule csrc/ransac.cu: warp_unguarded_partition is built on (k-th left stop exchanged with k-th right stop until the positions
+    cross; cut from two prefix sums), run as 32 lockstep lanes by tests/cpp/warp_partition_model.cpp, against the REAL
+    std::__unguarded_partition of this libstdc++ and csrc/replay.h's sequential restatement: cut and array contents identical over 20 000
+    ranges with heavy ties, all-equal, sorted and reversed content (Odometry/ransac.cpp:199, quirk Q6)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "warp_partition_model"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", str(exe), str(root / "tests" / "cpp" / "warp_partition_model.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "20000"], capture_output=True, text=True)
+    assert r.returncode == 0 and "20000 ranges identical" in r.stdout, (r.stdout, r.stderr)
+
+
 def test_reduction_order_of_the_absent_libraries_does_not_move_the_result(orc):
     """Eigen unrolls small fixed-size reductions as a balanced tree (a0 + (a1 + a2)) or runs them left to right depending on the
     expression and the build; the library is not in the image, so which one the reference's binary uses cannot be observed.  Measured
