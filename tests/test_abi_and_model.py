@@ -23,6 +23,29 @@ def test_library_exports_every_declared_symbol(ob):
     assert L.orbf_abi_version() == 6
 
 
+def test_integration_index_lists_every_entry_point_with_its_reference_interface():
+    """INTEGRATION.md's entry-point index: every symbol the header declares has a row that names the reference interface it stands for
+    (file:line) or says that it has none; every reference file a row cites is one of the hot path's files."""
+    header = (ROOT / "include" / "orbfront.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(orbf_[a-z0-9_]+)\s*\(", header)))
+    text = (ROOT / "INTEGRATION.md").read_text()
+    index = text[text.index("## Entry-point index"):]
+    rows = [r for r in index.splitlines() if r.startswith("| `orbf_")]
+    listed = {n for r in rows for n in re.findall(r"`(orbf_[a-z0-9_]+)`", r.split("|")[1])}
+    assert not [n for n in names if n not in listed], [n for n in names if n not in listed]
+    assert not [n for n in listed if n not in names], [n for n in listed if n not in names]
+    known = {"Features/orbextractor.cpp", "Features/orbextractor.h", "Features/extractor.cpp", "Features/matcher.cpp", "Features/detectoradjuster.cpp",
+             "Features/videogridadaptedfeaturedetector.cpp", "Features/videodynamicadaptedfeaturedetector.cpp", "Odometry/ransac.cpp", "Odometry/ransac.h",
+             "Odometry/kabsch.cpp", "Odometry/odometry.cpp", "Core/frame.cpp", "Core/landmark.cpp", "Core/keyframedatabase.cpp", "Utils/common.h",
+             "System/tracking.cpp", "Tests/DatabaseTest.cpp"}
+    for r in rows:
+        ref = r.split("|")[2]
+        cited = set(re.findall(r"`((?:Features|Odometry|Core|Utils|System|Tests)/[A-Za-z]+\.(?:cpp|h)):[0-9]", ref))
+        assert cited <= known, (r[:60], cited - known)
+        assert cited or "—" in ref, r[:80]
+
+
 def test_struct_layouts_match_header(ob):
     import ctypes as C
     assert ob.KEYPOINT_DT.itemsize == 28 and ob.DMATCH_DT.itemsize == 16      # cv::KeyPoint / cv::DMatch mirrors
