@@ -187,3 +187,22 @@ def test_c_abi_frame_shard_equals_the_python_host_logic(ob):
                 owners += list(range(*got["pairs"]))
             assert owners == list(range(max(n - 1, 0))), (n, world)
     assert L.orbf_frame_shard(8, 0, 0, *[C.byref(o) for o in out]) != 0 and L.orbf_frame_shard(8, 2, 2, *[C.byref(o) for o in out]) != 0
+
+
+def test_cpp_sequence_shard_host_logic(ob, tmp_path):
+    """include/orbfront_shard.hpp (orbf::SequenceShard: the C++ statement of sharding.run_sequence_shard / compose_trajectory_sharded)
+    over a recording stand-in of the device calls, ranks as threads (tests/cpp/shard_host_logic.cpp): for 0 .. 41 frames on 1 .. 8 ranks,
+    with leading pairs that never score and with explicit covariances, the shards together give the results and absolute poses of one
+    process bit for bit, every pair is solved once with seed + p and the covariance of the globally first scoring pair (quirks Q5 / Q7)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    pkg = root / "adaptive-rgbd-localization-mappig_b200"
+    ob.lib()                                                     # orbf_frame_shard / orbf_status_string are the library's own
+    exe = tmp_path / "shard_host_logic"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", f"-I{root / 'include'}", "-o", str(exe),
+                        str(root / "tests" / "cpp" / "shard_host_logic.cpp"), f"-L{pkg}", "-lorbfront_b200", f"-Wl,-rpath,{pkg}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "360 sharded jobs identical to one process" in r.stdout, (r.stdout, r.stderr)
