@@ -59,3 +59,37 @@ def test_quaternion_branches():
         q = tum.quaternion_from_rotation(R)
         want = np.zeros(4, np.float32); want[axis] = 1
         assert np.array_equal(np.abs(q), want)
+
+
+def test_cpp_header_equals_the_python_host_logic(tmp_path):
+    """include/orbfront_tum.hpp (LoadImages / SaveTrajectory for a C++ host: Utils/utils.cpp:16-38, System/tracking.cpp:566-577) against
+    tum.py: the same association entries (blank lines, no trailing newline) and a byte-identical trajectory file over random poses, the
+    trace <= 0 quaternion branches included; a file that cannot be opened throws instead of the reference's endless `while (!eof())`."""
+    import struct
+    import subprocess
+    exe = tmp_path / "tum_io_demo"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", "-o", str(exe), str(ROOT / "tests" / "cpp" / "tum_io_demo.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assoc = tmp_path / "assoc.txt"
+    assoc.write_text("1305031102.175304 rgb/1305031102.175304.png 1305031102.160407 depth/1305031102.160407.png\n\n"
+                     "1305031102.211214 rgb/1305031102.211214.png 1305031102.226738 depth/1305031102.226738.png\n"
+                     "1305031102.243211 rgb/c.png 1305031102.262886 depth/c.png")
+    rng = np.random.default_rng(1)
+    poses = []
+    for k in range(200):
+        T = np.eye(4, dtype=np.float32); T[:3, :3] = _rot(rng).astype(np.float32); T[:3, 3] = (rng.normal(size=3) * 10.0 ** int(rng.integers(-3, 3))).astype(np.float32)
+        poses.append(T)
+    for axis in range(3):                                        # rotations by pi: the trace <= 0 branches
+        T = np.eye(4, dtype=np.float32); T[:3, :3] = -np.eye(3); T[axis, axis] = 1; T[:3, 3] = [1, -2, 3]
+        poses.append(T)
+    ts = 1305031102.0 + np.arange(len(poses)) * 0.0333333
+    (tmp_path / "poses.bin").write_bytes(struct.pack("i", len(poses)) + ts.astype(np.float64).tobytes() + np.stack(poses).astype(np.float32).tobytes())
+    r = subprocess.run([str(exe), str(assoc), str(tmp_path / "poses.bin"), str(tmp_path / "traj_cpp.txt"), str(tmp_path / "assoc_cpp.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    tum.save_trajectory(tmp_path / "traj_py.txt", ts, poses)
+    assert (tmp_path / "traj_cpp.txt").read_bytes() == (tmp_path / "traj_py.txt").read_bytes()
+    t_py, rgb_py, dep_py = tum.load_associations(assoc)
+    rows = [l.split("|") for l in (tmp_path / "assoc_cpp.txt").read_text().splitlines()]
+    assert [float(a[0]) for a in rows] == t_py.tolist() and [a[1] for a in rows] == rgb_py and [a[2] for a in rows] == dep_py and len(rows) == 3
