@@ -20,8 +20,10 @@
 namespace orbf {
 
 // Every non-empty line of the association file is `t_rgb rgb_file t_depth depth_file`; the first timestamp is the frame's.  Like the
-// reference, a line is parsed whenever it is not empty — fields that are missing come out as 0 / "" (operator>> on an exhausted stream).
-// One deviation: the reference's `while (!f.eof())` never ends on a file that cannot be opened; this throws instead.
+// reference, a line is parsed whenever it is not empty — names that are missing come out as "" (operator>> on an exhausted stream).
+// Compared with the reference's own function (Utils/utils.cpp compiled verbatim, oracle/_ref/ref_utils_demo) by tests/test_tum_io.py.
+// Two deviations, both where the reference has no defined result: its `while (!f.eof())` never ends on a file that cannot be opened —
+// this throws; on a whitespace-only line it pushes an uninitialised double as the timestamp — this pushes 0.
 inline void LoadImages(const std::string& associationFilename, std::vector<std::string>& vImageFilenamesRGB,
     std::vector<std::string>& vImageFilenamesD, std::vector<double>& vTimestamps)
 {

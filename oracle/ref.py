@@ -19,6 +19,7 @@ _DIR = Path(__file__).resolve().parent
 SO = _DIR / "_ref" / "liborb_ref.so"
 SO_ODOMETRY = _DIR / "_ref" / "libodometry_ref.so"
 SO_FRAME = _DIR / "_ref" / "libframe_ref.so"
+UTILS_DEMO = _DIR / "_ref" / "ref_utils_demo"      # Utils/utils.cpp verbatim: the reference's own LoadImages as a small program
 REFERENCE = Path(os.environ.get("ORB_REFERENCE_DIR", "/root/reference"))
 _lib = None
 
@@ -26,7 +27,7 @@ _lib = None
 def build():
     """Compile from the reference checkout when it is present; otherwise keep whatever prebuilt file is there."""
     if (REFERENCE / "Features" / "orbextractor.cpp").exists():
-        subprocess.run(["make", "-C", str(_DIR), "-s", "-j3", "_ref", f"REF={REFERENCE}"], check=True)
+        subprocess.run(["make", "-C", str(_DIR), "-s", "-j4", "_ref", f"REF={REFERENCE}"], check=True)
     return SO.exists() and SO_ODOMETRY.exists() and SO_FRAME.exists()
 
 

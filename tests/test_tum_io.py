@@ -93,3 +93,40 @@ def test_cpp_header_equals_the_python_host_logic(tmp_path):
     t_py, rgb_py, dep_py = tum.load_associations(assoc)
     rows = [l.split("|") for l in (tmp_path / "assoc_cpp.txt").read_text().splitlines()]
     assert [float(a[0]) for a in rows] == t_py.tolist() and [a[1] for a in rows] == rgb_py and [a[2] for a in rows] == dep_py and len(rows) == 3
+
+
+def test_load_images_equals_the_reference_source(tmp_path):
+    """orbf::LoadImages (include/orbfront_tum.hpp) and tum.load_associations against the reference's OWN LoadImages — Utils/utils.cpp
+    compiled verbatim into oracle/_ref/ref_utils_demo (oracle/Makefile): the same timestamps (to the last bit), file names and entry
+    count on well-formed files with blank lines, CRLF line ends, a missing last newline, and on lines with missing trailing fields (empty
+    names, like the reference).  Not compared: whitespace-only lines, where the reference pushes an uninitialised double."""
+    import subprocess
+    sys.path.insert(0, str(ROOT))
+    from oracle import ref
+    if not ref.available() or not ref.UTILS_DEMO.exists():
+        import pytest
+        pytest.skip("oracle/_ref/ref_utils_demo is not built and the reference checkout is absent")
+    exe = tmp_path / "tum_io_demo"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", f"-I{ROOT / 'include'}", "-o", str(exe), str(ROOT / "tests" / "cpp" / "tum_io_demo.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    (tmp_path / "poses.bin").write_bytes(b"\0\0\0\0")
+    rng = np.random.default_rng(3)
+    well = "".join(f"{1305031102.0 + 0.0333 * k + rng.random() * 1e-3:.6f} rgb/{k}.png {1305031102.0 + 0.0333 * k:.6f} depth/{k}.png\n" + ("\n" if k % 7 == 0 else "")
+                   for k in range(100))
+    cases = {"well": well, "no_last_newline": well.rstrip("\n"), "crlf": well.replace("\n\n", "\n").replace("\n", "\r\n"),
+             "missing_fields": "1.5 rgb/a.png 1.6 depth/a.png\n2.5 rgb/b.png 2.6\n3.5 rgb/c.png\n4.5\n5.5 rgb/e.png 5.6 depth/e.png\n", "empty": ""}
+    for name, text in cases.items():
+        p = tmp_path / f"{name}.txt"
+        p.write_bytes(text.encode())
+        r = subprocess.run([str(ref.UTILS_DEMO), str(p), str(tmp_path / f"{name}.ref")], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, (name, r.stderr)
+        r = subprocess.run([str(exe), str(p), str(tmp_path / "poses.bin"), str(tmp_path / "t.txt"), str(tmp_path / f"{name}.cpp")], capture_output=True, text=True)
+        assert r.returncode == 0, (name, r.returncode, r.stderr)
+        want = (tmp_path / f"{name}.ref").read_text()
+        assert (tmp_path / f"{name}.cpp").read_text() == want, name
+        if name in ("well", "no_last_newline", "crlf"):
+            rows = [l.split("|") for l in want.splitlines()]
+            ts, rgb, dep = tum.load_associations(p)
+            assert len(rows) == 100 and ts.tolist() == [float(a[0]) for a in rows] and rgb == [a[1] for a in rows] and dep == [a[2] for a in rows], name
+    assert (tmp_path / "empty.ref").read_text() == ""
