@@ -1,0 +1,103 @@
+#!/usr/bin/env python3
+"""Randomised soak of the CPU oracle against the reference's OWN sources (oracle/_ref: orbextractor.cpp, matcher.cpp, ransac.cpp compiled
+verbatim) — authoring container only (needs the reference checkout).  The committed tests (tests/test_oracle_vs_ref*.py) compare fixed
+cases; this draws random ones for a given number of seconds and reports every disagreement:
+
+  extract  random geometry (160..900 x 120..700), nfeatures 50..2500, 1..9 levels, scale 1.1..2.0, ini / min thresholds, six image
+           kinds (noise, blurred noise, blocks, low contrast = th-7 fallback, checkerboards = ties, the bench's synthetic motion frames):
+           keypoints incl. order and descriptors byte for byte
+  ransac   random rigid problems (30..1500 points, 0..100 % outliers, depth holes / NaN, tie-heavy distances), iterations 1..400,
+           sample size 3..6, inlier threshold, Mahalanobis threshold, depth check on / off, both Iterate forms: ok, inlier list incl.
+           order, T12, rmse bit for bit
+  match    random descriptor sets (1..1500 query rows, 2..1500 train rows, near-duplicates, heavy ties), ratio 0.5..1.0: the DMatch list byte for byte
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match> <seed> <seconds>      -> one JSON line
+"""
+import json
+import sys
+import time
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
+import synth
+from oracle import oracle as orc, ref
+
+mode, seed, seconds = sys.argv[1], int(sys.argv[2]), float(sys.argv[3])
+orc.build(); assert ref.available()
+rng = np.random.default_rng(seed)
+t0 = time.time(); n = 0; bad = []
+
+
+def image(w, h):
+    import cv2
+    kind = int(rng.integers(0, 6))
+    if kind == 0:
+        return kind, rng.integers(0, 256, (h, w)).astype(np.uint8)
+    if kind == 1:
+        img = cv2.GaussianBlur(rng.integers(0, 256, (h, w)).astype(np.uint8), (0, 0), float(rng.uniform(0.7, 4)))
+        return kind, cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX)
+    if kind == 2:
+        img = np.full((h, w), int(rng.integers(0, 256)), np.uint8)
+        for _ in range(int(rng.integers(1, 200))):
+            x, y, s = int(rng.integers(0, w - 8)), int(rng.integers(0, h - 8)), int(rng.integers(2, 9))
+            img[y:y + s, x:x + s] = int(rng.integers(0, 256))
+        return kind, img
+    if kind == 3:
+        base = cv2.GaussianBlur(rng.integers(0, 256, (h, w)).astype(np.uint8), (0, 0), 2.0).astype(np.float32)
+        return kind, np.clip(128 + (base - base.mean()) * float(rng.uniform(0.2, 1.5)), 0, 255).astype(np.uint8)
+    if kind == 4:
+        s = int(rng.integers(3, 20)); yy, xx = np.mgrid[0:h, 0:w]
+        return kind, (((yy // s + xx // s) % 2) * int(rng.integers(30, 255))).astype(np.uint8)
+    tex = synth.make_texture(int(rng.integers(0, 1000)), h, w)
+    return kind, synth.make_frame(tex, int(rng.integers(0, 30)), w, h, seed=int(rng.integers(0, 99)))
+
+
+if mode == "ransac":
+    cov = ref.depth_covariance(1.0)            # quirk Q7: latch the reference's process-wide covariance first, hand the same to the oracle
+while time.time() - t0 < seconds:
+    if mode == "extract":
+        w, h = int(rng.integers(160, 900)), int(rng.integers(120, 700))
+        p = dict(nfeatures=int(rng.integers(50, 2500)), nlevels=int(rng.integers(1, 10)), scale_factor=float(rng.choice([1.1, 1.2, 1.3, 1.5, 2.0])),
+                 ini_th=int(rng.choice([20, 20, 20, 12, 40])), min_th=int(rng.choice([7, 7, 5, 3])))
+        kind, img = image(w, h)
+        try:
+            k, d = orc.extract(img, **p)
+        except Exception:
+            continue                              # geometry too small for this pyramid (ORBF-style error in the oracle; the reference asserts)
+        rk, rd = ref.extract(img, **p)
+        same = k.tobytes() == rk.tobytes() and np.array_equal(d, rd)
+        what = dict(w=w, h=h, kind=kind, **p)
+    elif mode == "ransac":
+        n_pts = int(rng.integers(30, 1500)); m = int(rng.integers(0, n_pts + 1))
+        src, dst, mm, _, _ = synth.rigid_pairs(m=max(m, 12), seed=int(rng.integers(0, 10 ** 6)), outlier_frac=float(rng.choice([0.0, 0.05, 0.3, 0.5, 0.7, 0.9, 1.0])),
+                                               n_pts=max(n_pts, 12))
+        mm = mm[:m]
+        tie = int(rng.integers(0, 4))
+        if tie == 0: mm["distance"] = rng.integers(0, 8, len(mm))
+        elif tie == 1: mm["distance"] = rng.integers(0, 100, len(mm))
+        elif tie == 2: mm["distance"] = 5
+        p = dict(iterations=int(rng.choice([200, 200, 50, 1, 400])), min_inlier_th=int(rng.choice([20, 20, 5, 60])), max_mahal=float(rng.choice([3.0, 3.0, 1.0, 10.0])),
+                 sample_size=int(rng.choice([4, 4, 3, 6])), check_depth=bool(rng.integers(0, 4) > 0), seed=int(rng.integers(0, 2 ** 31)))
+        r = ref.ransac_iterate(src, dst, mm, member_form=bool(rng.integers(0, 2)) and p["check_depth"], **p)
+        o = orc.ransac_iterate(src, dst, mm, depth_cov=cov, **p)
+        same = (r["ok"] == o["ok"] and r["n_good"] == o["n_good"] and r["inliers"].tobytes() == o["inliers"].tobytes()
+                and np.array_equal(r["T12"], o["T12"], equal_nan=True) and (r["rmse"] == o["rmse"] or (np.isnan(r["rmse"]) and np.isnan(o["rmse"]))))
+        what = dict(n_pts=n_pts, m=len(mm), tie=tie, **p)
+    else:
+        nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
+        q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
+        kind = int(rng.integers(0, 3))
+        if kind == 1:                             # near-duplicates of the query rows in the train set
+            for j in range(0, nt, 2):
+                t[j] = q[int(rng.integers(0, nq))]; t[j, int(rng.integers(0, 32))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:                           # few distinct rows: ties everywhere
+            t = t[rng.integers(0, min(nt, 4), nt)]; q = q[rng.integers(0, min(nq, 6), nq)]
+        ratio = float(rng.choice([0.5, 0.6, 0.8, 0.9, 1.0]))
+        a = ref.knn_match_frames(q, t, ratio); b = orc.knn_match(q, t, ratio, False)
+        same = a.tobytes() == b.tobytes()
+        what = dict(nq=nq, nt=nt, kind=kind, ratio=ratio)
+    n += 1
+    if not same:
+        bad.append(what)
+print(json.dumps({"mode": mode, "seed": seed, "seconds": round(time.time() - t0, 1), "cases": n, "mismatches": len(bad), "first_mismatches": bad[:5]}))
