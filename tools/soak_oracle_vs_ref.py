@@ -11,7 +11,11 @@ cases; this draws random ones for a given number of seconds and reports every di
            order, T12, rmse bit for bit
   match    random descriptor sets (1..1500 query rows, 2..1500 train rows, near-duplicates, heavy ties), ratio 0.5..1.0: the DMatch list byte for byte
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match> <seed> <seconds>      -> one JSON line
+  adaptive random clips of 3..8 frames (160..900 x 120..700, the same image kinds, contrast changes in mid-clip) through
+           Extractor(FAST, ., ADAPTIVE): the nine controllers' state, the keypoint count and the multiset of responses frame by frame
+           (keypoints themselves only up to quirk Q15: ties at the std::nth_element cut)
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -84,6 +88,25 @@ while time.time() - t0 < seconds:
         same = (r["ok"] == o["ok"] and r["n_good"] == o["n_good"] and r["inliers"].tobytes() == o["inliers"].tobytes()
                 and np.array_equal(r["T12"], o["T12"], equal_nan=True) and (r["rmse"] == o["rmse"] or (np.isnan(r["rmse"]) and np.isnan(o["rmse"]))))
         what = dict(n_pts=n_pts, m=len(mm), tie=tie, **p)
+    elif mode == "adaptive":
+        from collections import Counter
+        w, h = int(rng.integers(160, 900)), int(rng.integers(120, 700))
+        nfr = int(rng.integers(3, 9)); kind0, base = image(w, h)
+        ex = ref.AdaptiveExtractor(); th = np.full(9, 20.0); same = True
+        for f in range(nfr):
+            if kind0 == 5 or rng.integers(0, 3) == 0:
+                _, img = image(w, h)
+            else:
+                img = np.roll(base, (int(rng.integers(-5, 6)), int(rng.integers(-5, 6))), (0, 1))
+            if rng.integers(0, 3) == 0:
+                img = (img.astype(np.float32) * float(rng.uniform(0.1, 1.0)) + float(rng.uniform(0, 100))).clip(0, 255).astype(np.uint8)
+            rk, rth = ex.extract(img)
+            ok, _, _ = orc.adaptive_detect(img, th, retain_best=1000)
+            same &= bool(np.array_equal(rth, th)) and len(rk) == len(ok) and Counter(rk["response"].tolist()) == Counter(ok["response"].tolist())
+            if not same:
+                break
+        ex.close()
+        what = dict(w=w, h=h, kind=kind0, frames=nfr, failed_at=f)
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
