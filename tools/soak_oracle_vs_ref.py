@@ -15,7 +15,10 @@ cases; this draws random ones for a given number of seconds and reports every di
            Extractor(FAST, ., ADAPTIVE): the nine controllers' state, the keypoint count and the multiset of responses frame by frame
            (keypoints themselves only up to quirk Q15: ties at the std::nth_element cut)
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive> <seed> <seconds>      -> one JSON line
+  8f       random scenes of the tests' generators (tests/test_projection_match.py, tests/test_fuse_bow.py) through ProjectionMatch,
+           BoWMatch and the search of Fuse (matcher.cpp:90-313) with random sizes, radii, ratios and thresholds: indices / DMatch lists
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -107,6 +110,34 @@ while time.time() - t0 < seconds:
                 break
         ex.close()
         what = dict(w=w, h=h, kind=kind0, frames=nfr, failed_at=f)
+    elif mode == "8f":
+        from test_fuse_bow import CAM, _bow_scene, _fuse_scene
+        from test_projection_match import _scene as _proj_scene
+        which = int(rng.integers(0, 3)); sd = int(rng.integers(0, 10 ** 6))
+        if which == 0:
+            nfeat, nlm = int(rng.integers(20, 900)), int(rng.integers(5, 900))
+            sc = _proj_scene(sd, n_feat=nfeat, n_lm=nlm, crowded=bool(rng.integers(0, 2)))
+            kw = dict(radius=float(rng.choice([3.0, 8.0, 15.0])), nn_ratio=float(rng.choice([0.6, 0.8, 0.95])), th_high=float(rng.choice([60.0, 100.0, 256.0])))
+            taken = sc[8] if rng.integers(0, 2) else None
+            b_r, n_r = ref.projection_match(*sc[:8], feat_taken=taken, **kw); b_o, n_o = orc.projection_match(*sc[:8], feat_taken=taken, **kw)
+            same = bool(np.array_equal(b_r, b_o)) and n_r == n_o
+            what = dict(fn="projection", seed=sd, n_feat=nfeat, n_lm=nlm, **kw)
+        elif which == 1:
+            n1, n2, nw = int(rng.integers(10, 900)), int(rng.integers(10, 900)), int(rng.integers(2, 300))
+            sc = _bow_scene(sd, n1=n1, n2=n2, n_words=nw)
+            kw = dict(nn_ratio=float(rng.choice([0.6, 0.75, 0.9])), th_low=float(rng.choice([50.0, 80.0, 30.0])))
+            same = ref.bow_match(*sc, **kw).tobytes() == orc.bow_match(*sc, **kw).tobytes()
+            what = dict(fn="bow", seed=sd, n1=n1, n2=n2, n_words=nw, **kw)
+        else:
+            nfeat, nlm, radius = int(rng.integers(20, 900)), int(rng.integers(5, 800)), float(rng.choice([3.0, 8.0]))
+            R, t, kp_x, kp_y, u_right, desc, pw, lm_desc, valid = _fuse_scene(sd, n_feat=nfeat, n_lm=nlm, radius=radius)
+            state = valid.copy(); inval = np.nonzero(valid == 0)[0]
+            state[inval] = np.array([0, 2, 3], np.uint8)[np.arange(len(inval)) % 3]
+            th = float(rng.choice([50.0, 30.0, 100.0]))
+            b_r, nf = ref.fuse(R, t, CAM[5:9], kp_x, kp_y, u_right, desc, pw, lm_desc, state, radius=radius, th_low=th)
+            b_o, _ = orc.fuse_search(R, t, CAM, kp_x, kp_y, u_right, desc, pw, lm_desc, valid, radius=radius, th_low=th)
+            same = bool(np.array_equal(b_r, b_o)) and nf == int((b_o >= 0).sum())
+            what = dict(fn="fuse", seed=sd, n_feat=nfeat, n_lm=nlm, radius=radius, th_low=th)
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
