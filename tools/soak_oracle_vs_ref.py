@@ -18,7 +18,11 @@ cases; this draws random ones for a given number of seconds and reports every di
   8f       random scenes of the tests' generators (tests/test_projection_match.py, tests/test_fuse_bow.py) through ProjectionMatch,
            BoWMatch and the search of Fuse (matcher.cpp:90-313) with random sizes, radii, ratios and thresholds: indices / DMatch lists
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f> <seed> <seconds>      -> one JSON line
+  frame    random 640x480 colour frames (the calibration compiled into the reference) with random depth planes (holes, far / near
+           ranges) through the reference's real Frame::Frame + Frame::ExtractFeatures (Core/frame.cpp:18-45,135-170,286-313): gray plane,
+           keypoints, descriptors, undistorted keypoints, 3D points, mvuRight bit for bit
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -138,6 +142,23 @@ while time.time() - t0 < seconds:
             b_o, _ = orc.fuse_search(R, t, CAM, kp_x, kp_y, u_right, desc, pw, lm_desc, valid, radius=radius, th_low=th)
             same = bool(np.array_equal(b_r, b_o)) and nf == int((b_o >= 0).sum())
             what = dict(fn="fuse", seed=sd, n_feat=nfeat, n_lm=nlm, radius=radius, th_low=th)
+    elif mode == "frame":
+        from test_oracle_vs_ref_frame import FR1, FR1_DIST
+        kind, g = image(640, 480)
+        gi = g.astype(np.int16)
+        bgr = np.stack([np.clip(gi + rng.integers(-40, 41, g.shape), 0, 255), gi, np.clip(gi - rng.integers(-40, 41, g.shape), 0, 255)], -1).astype(np.uint8)
+        depth = rng.integers(int(rng.choice([0, 2000])), int(rng.choice([8000, 40000, 65536])), (480, 640)).astype(np.uint16)
+        if rng.integers(0, 2):
+            depth[rng.random((480, 640)) < float(rng.uniform(0.01, 0.6))] = 0
+        r = ref.frame_extract(bgr, depth)
+        gray = orc.bgr2gray(bgr)
+        k, d = orc.extract(gray)
+        xy = np.stack([k["x"], k["y"]], 1).astype(np.float32).reshape(-1, 2)
+        un = orc.undistort_points(xy, FR1["fx"], FR1["fy"], FR1["cx"], FR1["cy"], FR1_DIST) if len(k) else xy
+        xyz, ur = orc.unproject(k, depth, dist=FR1_DIST)
+        same = (bool(np.array_equal(r["gray"], gray)) and r["kps"].tobytes() == k.tobytes() and bool(np.array_equal(r["desc"], d)) and bool(np.array_equal(r["xy_un"], un))
+                and bool(np.array_equal(r["xyz"], xyz)) and bool(np.array_equal(r["uright"], ur)))
+        what = dict(kind=kind, nk=len(k))
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
