@@ -22,7 +22,13 @@ cases; this draws random ones for a given number of seconds and reports every di
            ranges) through the reference's real Frame::Frame + Frame::ExtractFeatures (Core/frame.cpp:18-45,135-170,286-313): gray plane,
            keypoints, descriptors, undistorted keypoints, 3D points, mvuRight bit for bit
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame> <seed> <seconds>      -> one JSON line
+  cv2      what oracle/_ref CANNOT see — the OpenCV arithmetic its stand-in headers share with the oracle — against the real library
+           (cv2 4.x): cv2.resize(INTER_LINEAR) at random source / destination sizes, cv2.GaussianBlur(7x7, 2, REFLECT_101), cv2.FAST with
+           NMS on random ROIs and thresholds (positions, order, responses), cv2.fastAtan2, BFMatcher.knnMatch(k = 2) order under ties,
+           cv2.cvtColor(BGR2GRAY), cv2.undistortPoints (5 iterations, P = K) with random coefficients, and the whole extraction against
+           the cv2-driven restatement tests/cv2_oracle.py
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|cv2> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -159,6 +165,68 @@ while time.time() - t0 < seconds:
         same = (bool(np.array_equal(r["gray"], gray)) and r["kps"].tobytes() == k.tobytes() and bool(np.array_equal(r["desc"], d)) and bool(np.array_equal(r["xy_un"], un))
                 and bool(np.array_equal(r["xyz"], xyz)) and bool(np.array_equal(r["uright"], ur)))
         what = dict(kind=kind, nk=len(k))
+    elif mode == "cv2":
+        import cv2
+        import cv2_oracle as co
+        which = int(rng.integers(0, 8))
+        if which == 0:
+            sw, sh = int(rng.integers(8, 900)), int(rng.integers(8, 700)); f = float(rng.uniform(1.05, 2.2))
+            dw, dh = max(int(round(sw / f)), 2), max(int(round(sh / f)), 2)
+            _, img = image(max(sw, 16), max(sh, 16)); img = np.ascontiguousarray(img[:sh, :sw])
+            same = bool(np.array_equal(orc.resize_linear(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)))
+            what = dict(fn="resize", src=(sw, sh), dst=(dw, dh))
+        elif which == 1:
+            w, h = int(rng.integers(4, 900)), int(rng.integers(4, 700))
+            _, img = image(max(w, 16), max(h, 16)); img = np.ascontiguousarray(img[:h, :w])
+            same = bool(np.array_equal(orc.gaussian_blur7(img), cv2.GaussianBlur(img.copy(), (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)))
+            what = dict(fn="blur", size=(w, h))
+        elif which == 2:
+            w, h = int(rng.integers(7, 300)), int(rng.integers(7, 300)); th = int(rng.integers(1, 80))
+            _, img = image(max(w, 16), max(h, 16)); roi = np.ascontiguousarray(img[:h, :w])
+            kps = cv2.FastFeatureDetector_create(th, True).detect(roi)
+            want = [(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in kps]
+            got = [(int(c["x"]), int(c["y"]), int(c["score"])) for c in orc.fast_roi(roi, th)]
+            same = got == want
+            what = dict(fn="fast", size=(w, h), th=th)
+        elif which == 3:
+            ys = rng.integers(-400000, 400000, 3000).astype(np.float32); xs = rng.integers(-400000, 400000, 3000).astype(np.float32)
+            ys[:20] = 0; xs[20:40] = 0; ys[40:60] = xs[40:60]; ys[60:80] = -xs[60:80]
+            same = all(np.float32(cv2.fastAtan2(float(y), float(x))) == np.float32(orc.fast_atan2(y, x)) for y, x in zip(ys, xs))
+            what = dict(fn="fastAtan2")
+        elif which == 4:
+            nq, nt = int(rng.integers(1, 400)), int(rng.integers(2, 400))
+            q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
+            if rng.integers(0, 2):
+                t = t[rng.integers(0, min(nt, 5), nt)]
+            same = all(bool(np.array_equal(g, r)) for g, r in zip(orc.knn2(q, t), co.knn2(q, t)))
+            what = dict(fn="knn2", nq=nq, nt=nt)
+        elif which == 5:
+            w, h = int(rng.integers(1, 700)), int(rng.integers(1, 500))
+            bgr = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+            same = bool(np.array_equal(orc.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)))
+            what = dict(fn="bgr2gray", size=(w, h))
+        elif which == 6:
+            fx, fy, cx, cy = float(rng.uniform(300, 900)), float(rng.uniform(300, 900)), float(rng.uniform(200, 700)), float(rng.uniform(150, 500))
+            dist = np.array([rng.uniform(-0.4, 0.4), rng.uniform(-1.0, 1.0), rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01), rng.choice([0.0, rng.uniform(-1.2, 1.2)])], np.float32)
+            pts = np.stack([rng.uniform(-5, 2 * cx + 5, 500), rng.uniform(-5, 2 * cy + 5, 500)], 1).astype(np.float32)
+            K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+            want = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
+            same = bool(np.array_equal(orc.undistort_points(pts, np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy), dist), want))
+            what = dict(fn="undistortPoints", K=(fx, fy, cx, cy), dist=dist.tolist())
+        else:
+            w, h = int(rng.integers(200, 700)), int(rng.integers(160, 520))
+            p = dict(nfeatures=int(rng.integers(100, 1500)), nlevels=int(rng.integers(1, 9)), scale_factor=float(rng.choice([1.2, 1.2, 1.3, 1.5])))
+            kind, img = image(w, h)
+            try:
+                k, d = orc.extract(img, **p)
+            except Exception:
+                continue
+            try:
+                k2, d2, _ = co.extract(img, orc.pattern(), **p)
+            except (OverflowError, ZeroDivisionError):
+                continue                          # a level narrower than one 30-px cell: width / nCols with nCols = 0 (orbextractor.cpp:683-686), Python raises
+            same = bool(np.array_equal(k, np.array(k2, dtype=orc.KEYPOINT_DT))) and bool(np.array_equal(d, d2))
+            what = dict(fn="extract_via_cv2", w=w, h=h, kind=kind, **p)
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
