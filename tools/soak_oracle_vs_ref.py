@@ -28,7 +28,11 @@ cases; this draws random ones for a given number of seconds and reports every di
            cv2.cvtColor(BGR2GRAY), cv2.undistortPoints (5 iterations, P = K) with random coefficients, and the whole extraction against
            the cv2-driven restatement tests/cv2_oracle.py
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|cv2> <seed> <seconds>      -> one JSON line
+  replay   csrc/replay.h — the std::sort and glibc rand() restatements the RANSAC KERNELS run, host build of the same code inside
+           liborbfront_b200.so — against the real libstdc++ std::sort on DMatch (0..3000 elements, tie-heavy / sorted / reversed /
+           median-of-3-killer inputs: the permutation of equal keys must be the library's) and against libc srand / rand sample tables
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|cv2|replay> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -227,6 +231,29 @@ while time.time() - t0 < seconds:
                 continue                          # a level narrower than one 30-px cell: width / nCols with nCols = 0 (orbextractor.cpp:683-686), Python raises
             same = bool(np.array_equal(k, np.array(k2, dtype=orc.KEYPOINT_DT))) and bool(np.array_equal(d, d2))
             what = dict(fn="extract_via_cv2", w=w, h=h, kind=kind, **p)
+    elif mode == "replay":
+        import bench
+        ob = bench.load_pkg()
+        if rng.integers(0, 3):
+            m = int(rng.integers(0, 3000)); kind = int(rng.integers(0, 6))
+            d = np.zeros(m, ob.DMATCH_DT); d["queryIdx"] = np.arange(m); d["trainIdx"] = rng.permutation(m) if m else 0
+            if kind == 0: d["distance"] = rng.integers(0, 64, m)
+            elif kind == 1: d["distance"] = rng.integers(0, 3, m)
+            elif kind == 2: d["distance"] = np.sort(rng.integers(0, 256, m))[::-1]
+            elif kind == 3: d["distance"] = rng.random(m)
+            elif kind == 4: d["distance"] = np.sort(rng.integers(0, 40, m))
+            elif m >= 2:
+                k = m // 2; a = np.zeros(m, np.float32)
+                for i in range(k):
+                    a[i] = i + 1 if i % 2 == 0 else k + i + (1 if k % 2 else 0)
+                    a[k + i] = 2 * (i + 1)
+                d["distance"] = a
+            same = ob.selftest_introsort(d).tobytes() == orc.std_sort_dmatch(d).tobytes()
+            what = dict(fn="std::sort", m=m, kind=kind)
+        else:
+            sd, M = int(rng.integers(0, 2 ** 32)), int(rng.integers(1, 2000))
+            same = bool(np.array_equal(ob.selftest_sample_table(sd, M), orc.sample_table_libc(sd, M))) and bool(np.array_equal(ob.selftest_glibc_rand(sd, 400), orc.libc_rand_sequence(sd, 400)))
+            what = dict(fn="rand", seed=sd, M=M)
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
