@@ -32,7 +32,13 @@ cases; this draws random ones for a given number of seconds and reports every di
            liborbfront_b200.so — against the real libstdc++ std::sort on DMatch (0..3000 elements, tie-heavy / sorted / reversed /
            median-of-3-killer inputs: the permutation of equal keys must be the library's) and against libc srand / rand sample tables
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|cv2|replay> <seed> <seconds>      -> one JSON line
+  linalg   the arithmetic of the libraries that are in NEITHER the image NOR oracle/_ref (PCL TransformationFromCorrespondences, Eigen
+           JacobiSVD / LLT: restated from their published algorithms, f32 like the reference) against numpy / LAPACK in f64, to
+           tolerance: 3x3 SVD (random, rank-deficient, tiny, diagonal), the weighted rigid transform on noisy correspondences (weights
+           1 / (z1 z2), ransac.cpp:308), Kabsch incl. reflections, the Mahalanobis distance of ErrorFunction2 (ransac.cpp:350-414).
+           A case fails above 2e-5 (relative; 1e-9 for the f64 distance); the JSON line also carries the largest deviation seen
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|cv2|replay|linalg> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -254,6 +260,66 @@ while time.time() - t0 < seconds:
             sd, M = int(rng.integers(0, 2 ** 32)), int(rng.integers(1, 2000))
             same = bool(np.array_equal(ob.selftest_sample_table(sd, M), orc.sample_table_libc(sd, M))) and bool(np.array_equal(ob.selftest_glibc_rand(sd, 400), orc.libc_rand_sequence(sd, 400)))
             what = dict(fn="rand", seed=sd, M=M)
+    elif mode == "linalg":
+        which = int(rng.integers(0, 4)); dev = 0.0
+        if which == 0:
+            A = rng.normal(size=(3, 3)).astype(np.float32); k = int(rng.integers(0, 5))
+            if k == 1: A[:, 2] = A[:, 0] * 2
+            elif k == 2: A *= np.float32(10.0 ** int(rng.integers(-8, 6)))
+            elif k == 3: A = np.diag(rng.normal(size=3)).astype(np.float32)
+            U, S, V = orc.svd3(A); scale = max(float(np.abs(A).max()), 1e-30)
+            sn = np.linalg.svd(A.astype(np.float64), compute_uv=False)
+            dev = max(float(np.abs(U @ np.diag(S) @ V.T - A).max()) / scale, float(np.abs(U.T @ U - np.eye(3)).max()), float(np.abs(V.T @ V - np.eye(3)).max()),
+                      float(np.abs(S - sn).max()) / max(float(sn.max()), 1e-30))
+            same = dev < 2e-5 and bool(S[0] >= S[1] >= S[2] >= 0)
+            what = dict(fn="svd3", kind=k, dev=dev)
+        elif which in (1, 2):
+            npts = int(rng.integers(4, 600))
+            P = np.empty((npts, 3)); P[:, 2] = rng.uniform(0.5, 5.0, npts); P[:, 0] = rng.uniform(-0.6, 0.6, npts) * P[:, 2]; P[:, 1] = rng.uniform(-0.45, 0.45, npts) * P[:, 2]
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = float(rng.uniform(0, 0.6))
+            Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            R = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx; t = rng.normal(0, 0.3, 3)
+            Q = P @ R.T + t + rng.normal(0, float(rng.choice([0.0, 0.002, 0.02])), (npts, 3))
+            Q[:, 2] = np.maximum(Q[:, 2], 0.05)
+            P32, Q32 = P.astype(np.float32), Q.astype(np.float32)
+            Pd, Qd = P32.astype(np.float64), Q32.astype(np.float64)
+            w = 1.0 / (Pd[:, 2] * Qd[:, 2]) if which == 1 else np.ones(npts)
+            m1 = (w[:, None] * Pd).sum(0) / w.sum(); m2 = (w[:, None] * Qd).sum(0) / w.sum()
+            Cm = ((w[:, None] * (Qd - m2)).T @ (Pd - m1)) / w.sum()
+            Uu, Ss, Vt = np.linalg.svd(Cm)
+            Rr = Uu @ np.diag([1, 1, np.sign(np.linalg.det(Uu) * np.linalg.det(Vt))]) @ Vt
+            want = np.eye(4); want[:3, :3] = Rr; want[:3, 3] = m2 - Rr @ m1
+            T = orc.weighted_transform(P32, Q32) if which == 1 else orc.kabsch(P32, Q32)
+            cond = Ss[1] / max(Ss[0], 1e-30)
+            if cond < 1e-3:
+                continue                          # a (nearly) collinear set: the rotation about the line is not determined
+            dev = float(np.abs(T - want).max())
+            same = dev < 2e-5 * max(1.0, float(np.abs(Qd).max())) / min(1.0, cond * 10)
+            what = dict(fn="weighted_transform" if which == 1 else "kabsch", n=npts, dev=dev, cond=float(cond))
+        else:
+            p = np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(0.4, 6)], np.float32)
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = float(rng.uniform(0, 0.5))
+            Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            T = np.eye(4, dtype=np.float32); T[:3, :3] = (np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx).astype(np.float32); T[:3, 3] = rng.normal(0, 0.2, 3).astype(np.float32)
+            Td = T.astype(np.float64)
+            q = (Td[:3, :3] @ p.astype(np.float64) + Td[:3, 3] + rng.normal(0, float(rng.choice([0.001, 0.01, 0.05])), 3)).astype(np.float32)
+            if not q[2] > 0.05:
+                continue
+            cz = float(rng.choice([1.3e-3, 1e-4, 2.5e-2]))
+            cx = (3 * np.tan(58.0 / 180.0 * np.pi / 640)) ** 2; cy = (3 * np.tan(45.0 / 180.0 * np.pi / 480)) ** 2
+            mu = Td[:3, :3] @ p.astype(np.float64) + Td[:3, 3]; dl = mu - q.astype(np.float64)
+            got = orc.mahalanobis2(p, q, T, cz)
+            s1 = max(cx * float(p[2]), cy * float(p[2]), cz); s2 = max(cx * float(q[2]), cy * float(q[2]), cz)
+            if dl @ dl > 2 * (s1 + s2) * 0.98:
+                continue                          # at or beyond the shortcut reject (ransac.cpp:375-381): the function returns DBL_MAX there
+            Sg = Td[:3, :3].T @ np.diag([cx * p[2], cy * p[2], cz]) @ Td[:3, :3] + np.diag([cx * q[2], cy * q[2], cz])
+            want = float(dl @ np.linalg.solve(Sg, dl))
+            if got == np.finfo(np.float64).max:
+                continue
+            dev = abs(got - want) / max(1.0, abs(want))
+            same = dev <= 1e-9
+            what = dict(fn="mahalanobis2", dev=dev)
+        worst = globals().setdefault("worst", {}); worst[what["fn"]] = max(worst.get(what["fn"], 0.0), dev)
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
@@ -270,4 +336,7 @@ while time.time() - t0 < seconds:
     n += 1
     if not same:
         bad.append(what)
-print(json.dumps({"mode": mode, "seed": seed, "seconds": round(time.time() - t0, 1), "cases": n, "mismatches": len(bad), "first_mismatches": bad[:5]}))
+res = {"mode": mode, "seed": seed, "seconds": round(time.time() - t0, 1), "cases": n, "mismatches": len(bad), "first_mismatches": bad[:5]}
+if mode == "linalg":
+    res["largest_deviation"] = globals().get("worst", {})
+print(json.dumps(res))
