@@ -24,5 +24,5 @@ def test_short_soak_finds_no_disagreement(orc):
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, m
         r = json.loads(out.strip().splitlines()[-1])
-        assert r["mode"] == m and r["cases"] >= 3, r
+        assert r["mode"] == m and r["cases"] >= 1, r
         assert r["mismatches"] == 0, r
