@@ -38,7 +38,10 @@ cases; this draws random ones for a given number of seconds and reports every di
            1 / (z1 z2), ransac.cpp:308), Kabsch incl. reflections, the Mahalanobis distance of ErrorFunction2 (ransac.cpp:350-414).
            A case fails above 2e-5 (relative; 1e-9 for the f64 distance); the JSON line also carries the largest deviation seen
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|cv2|replay|linalg> <seed> <seconds>      -> one JSON line
+  landmark random observation sets (0..40 noisy copies of a descriptor per landmark, medians tie often, random bad keyframes) through
+           the reference's real Landmark::ComputeDistinctiveDescriptors over KeyFrame / Landmark / Map objects (Core/landmark.cpp:219-273)
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|landmark|cv2|replay|linalg> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -320,6 +323,26 @@ while time.time() - t0 < seconds:
             same = dev <= 1e-9
             what = dict(fn="mahalanobis2", dev=dev)
         worst = globals().setdefault("worst", {}); worst[what["fn"]] = max(worst.get(what["fn"], 0.0), dev)
+    elif mode == "landmark":
+        nl = int(rng.integers(1, 200)); nobs = rng.integers(0, int(rng.choice([4, 12, 41])), nl)
+        offs = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+        base = rng.integers(0, 256, (nl, 32), dtype=np.uint8); desc = np.repeat(base, nobs, axis=0)
+        flips = rng.integers(0, 256, (len(desc), int(rng.integers(0, 40))))
+        for c in range(flips.shape[1]):
+            desc[np.arange(len(desc)), flips[:, c] // 8] ^= (1 << (flips[:, c] % 8)).astype(np.uint8)
+        badkf = (rng.random(len(desc)) < float(rng.choice([0.0, 0.2, 0.7]))).astype(np.uint8)
+        out, has = ref.distinctive_descriptors(desc, offs, badkf)
+        keep = badkf == 0
+        offs2 = np.concatenate([[0], np.cumsum([int(keep[offs[l]:offs[l + 1]].sum()) for l in range(nl)])]).astype(np.int32)
+        kept = np.ascontiguousarray(desc[keep]).reshape(-1, 32)
+        best, _ = orc.distinctive_descriptors(kept, offs2) if len(kept) else (np.full(nl, -1, np.int32), None)
+        same = True
+        for l in range(nl):
+            if offs2[l + 1] > offs2[l]:
+                same &= bool(has[l]) and bool(np.array_equal(out[l], kept[offs2[l] + best[l]]))
+            else:
+                same &= not bool(has[l])
+        what = dict(n_landmarks=nl, rows=int(len(desc)))
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
