@@ -11,7 +11,7 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
-MODES = ["extract", "ransac", "match", "adaptive", "8f", "frame", "landmark", "cv2", "replay", "linalg"]
+MODES = ["extract", "ransac", "match", "adaptive", "8f", "frame", "landmark", "odometry", "cv2", "replay", "linalg"]
 
 
 def test_short_soak_finds_no_disagreement(orc):

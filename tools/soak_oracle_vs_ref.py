@@ -41,7 +41,11 @@ cases; this draws random ones for a given number of seconds and reports every di
   landmark random observation sets (0..40 noisy copies of a descriptor per landmark, medians tie often, random bad keyframes) through
            the reference's real Landmark::ComputeDistinctiveDescriptors over KeyFrame / Landmark / Map objects (Core/landmark.cpp:219-273)
 
-  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|landmark|cv2|replay|linalg> <seed> <seconds>      -> one JSON line
+  odometry Odometry(RANSAC).Compute (odometry.cpp:44-90) and Matcher::KnnMatch(Frame&, Frame&) with its landmark rules (matcher.cpp:55-88) on
+           the reference's real Frame / Landmark objects: inliers, T12, rmse, the composed pose T12 * pose1 through cv::Mat, the inlier
+           flags; matches, the landmarks handed to the second frame and its outlier flags
+
+  python tools/soak_oracle_vs_ref.py <extract|ransac|match|adaptive|8f|frame|landmark|odometry|cv2|replay|linalg> <seed> <seconds>      -> one JSON line
 """
 import json
 import sys
@@ -343,6 +347,46 @@ while time.time() - t0 < seconds:
             else:
                 same &= not bool(has[l])
         what = dict(n_landmarks=nl, rows=int(len(desc)))
+    elif mode == "odometry":
+        if "cov_frame" not in globals():
+            cov_frame = ref.frame_depth_covariance(2.0)           # quirk Q7 in the frame library's own process-wide static
+        if rng.integers(0, 2):
+            ang = float(rng.uniform(-1, 1)); pose1 = np.eye(4, dtype=np.float32)
+            pose1[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+            pose1[:3, 3] = rng.normal(0, 1, 3).astype(np.float32)
+            n_pts = int(rng.integers(30, 1200)); m = int(rng.integers(1, n_pts + 1)); sd = int(rng.integers(0, 2 ** 31))
+            src, dst, mm, _, _ = synth.rigid_pairs(m=max(m, 12), seed=int(rng.integers(0, 10 ** 6)), outlier_frac=float(rng.choice([0.0, 0.3, 0.6, 0.9, 1.0])), n_pts=max(n_pts, 12))
+            if rng.integers(0, 2):
+                mm["distance"] = rng.integers(0, 30, len(mm))
+            r = ref.odometry_compute(src, dst, mm, pose1, seed=sd)
+            o = orc.ransac_iterate(src, dst, mm, seed=sd, depth_cov=cov_frame)
+            exp = np.ones(len(dst), bool); exp[o["inliers"]["trainIdx"]] = False
+            same = (r["inliers"].tobytes() == o["inliers"].tobytes() and bool(np.array_equal(r["T12"], o["T12"], equal_nan=True)) and (r["rmse"] == o["rmse"] or (np.isnan(r["rmse"]) and np.isnan(o["rmse"])))
+                    and bool(np.array_equal(r["outlier2"], exp)))
+            if o["ok"]:
+                same = same and bool(np.array_equal(r["pose2"], orc.compose_trajectory(o["T12"][None], pose1)[1]))
+            what = dict(fn="Odometry::Compute", n_pts=n_pts, m=len(mm), seed=sd, ok=bool(o["ok"]))
+        else:
+            nq, nt = int(rng.integers(1, 900)), int(rng.integers(2, 900))
+            q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
+            for j in range(0, nt, 2):
+                t[j] = q[int(rng.integers(0, nq))]; t[j, int(rng.integers(0, 32))] ^= 1 << int(rng.integers(0, 8))
+            ratio = float(rng.choice([0.6, 0.8, 0.95]))
+            obs1 = rng.integers(0, 4, nq).astype(np.int32); obs1[rng.random(nq) < 0.2] = -1
+            out1 = (rng.random(nq) < 0.1).astype(np.uint8)
+            obs2 = np.full(nt, -1, np.int32); pick = rng.random(nt) < 0.15; obs2[pick] = rng.integers(0, 3, int(pick.sum()))
+            got, slot2, outl2 = ref.real_knn_match_frames(q, t, ratio, obs1, out1, obs2)
+            base = orc.knn_match(q, t, ratio, False)
+            slot_obs = obs2.copy(); exp = []; exp_slot = np.full(nt, -1, np.int32); exp_out = np.zeros(nt, bool)
+            for mt in base:
+                i1, i2 = int(mt["queryIdx"]), int(mt["trainIdx"])
+                if obs1[i1] < 0 or out1[i1] or slot_obs[i2] > 0:
+                    continue
+                slot_obs[i2] = obs1[i1]; exp_slot[i2] = i1; exp_out[i2] = True
+                exp.append(mt)
+            exp = np.array(exp, base.dtype)
+            same = got.tobytes() == exp.tobytes() and bool(np.array_equal(slot2, exp_slot)) and bool(np.array_equal(outl2, exp_out))
+            what = dict(fn="KnnMatch(Frame&, Frame&)", nq=nq, nt=nt, ratio=ratio)
     else:
         nq, nt = int(rng.integers(1, 1500)), int(rng.integers(2, 1500))      # nt = 1: the reference reads matchesKnn[i][1] of a one-element vector (matcher.cpp:64), undefined
         q = rng.integers(0, 256, (nq, 32)).astype(np.uint8); t = rng.integers(0, 256, (nt, 32)).astype(np.uint8)
